@@ -1,0 +1,103 @@
+#!/usr/bin/env bash
+# Headless build of the UNMODIFIED reference renderer (windy32/win32-ray-tracing-demo,
+# src/RayTracingOpt) into oracle/_ref/libref.so (+ libref_timing.so without observation hooks).
+#
+# TEST INFRASTRUCTURE ONLY.  The sources are compiled from where they lie under
+# $RTB_REFERENCE (default /root/reference); a scratch copy with the mechanical MSVC->g++ patches
+# listed below is made under a temp dir and deleted afterwards.  Nothing but the two .so files
+# (and the STL fixture path note) is written into the repo, and oracle/_ref/ is git-ignored.
+#
+# Patches (none touches arithmetic):
+#   P1 RayContext.h:10      `struct RayContext() :` -> `RayContext() :`          (MSVC-only syntax)
+#   P2 Camera.h:21, .cpp:5  `Vector &front` -> `Vector front`                     (rvalue -> non-const ref)
+#   P3 Tunnel.cpp:46        name the temporary Ray                                (same)
+#   P4 MainWindow.cpp:69,145 trace/radiance take `Ray r` by value                 (same)
+#   P5 Color.h:12           `Color()` zero-initialises                            (removes UB at MainWindow.cpp:92-94)
+#   P6 Scripts.cpp:151      "ball.stl" -> ref_stl_path()                          (fixture location)
+#   P7 observation hooks    REF_HOOK_* macros after Tunnel.cpp:866,1206,1266, Triangle.cpp:40,
+#                           and the scene.intersect() call of trace/radiance       (compiled out when REF_HOOKS=0)
+#   Utils.cpp (Win32) is replaced by oracle/ref/ref_utils.cpp; MainWindow.cpp is not compiled:
+#   only its lines 69-249 (trace, radiance) and 251-303 (Render's pixel loop) are lifted into a
+#   generated include used by oracle/ref/ref_driver.cpp.
+set -euo pipefail
+
+HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+REF="${RTB_REFERENCE:-/root/reference}"
+SRC="$REF/src/RayTracingOpt"
+OUT="$HERE/_ref"
+
+if [ ! -d "$SRC" ]; then
+    echo "build_ref.sh: reference sources not found at $SRC (nothing built)" >&2
+    exit 3
+fi
+
+TMP="$(mktemp -d /tmp/rtb_ref_build.XXXXXX)"
+trap 'rm -rf "$TMP"' EXIT
+mkdir -p "$OUT"
+
+cp "$SRC"/*.h "$SRC"/*.cpp "$TMP"/
+rm -f "$TMP/MainWindow.cpp" "$TMP/Utils.cpp" "$TMP/resource.h"
+
+expect() { # expect <file> <line> <substring>: guard every line-addressed patch
+    sed -n "${2}p" "$SRC/$1" | grep -qF -- "$3" || { echo "build_ref.sh: $1:$2 does not contain '$3'" >&2; exit 4; }
+}
+
+expect RayContext.h 10 'struct RayContext() :'
+sed -i '10s/struct RayContext() :/RayContext() :/' "$TMP/RayContext.h"                       # P1
+expect Camera.h 21 'Vector &front'
+sed -i '21s/Vector &front/Vector front/' "$TMP/Camera.h"                                      # P2
+expect Camera.cpp 5 'Vector &front'
+sed -i '5s/Vector &front/Vector front/' "$TMP/Camera.cpp"
+expect Tunnel.cpp 46 'intersectWithPolygonAtOrigin(Ray(newOrigin, newDir), distance)'
+sed -i '46s/.*/    Ray refTmpRay(newOrigin, newDir); bool intersect = intersectWithPolygonAtOrigin(refTmpRay, distance);/' "$TMP/Tunnel.cpp"  # P3
+expect Color.h 12 'Color()'
+sed -i '12s/Color()/Color() : r(0), g(0), b(0)/' "$TMP/Color.h"                              # P5
+expect Scripts.cpp 151 '"ball.stl"'
+sed -i '151s/"ball.stl"/ref_stl_path()/' "$TMP/Scripts.cpp"                                   # P6
+expect Tunnel.cpp 866 'grid.get(cur_i, cur_j, cur_k);'
+sed -i '866s/$/ REF_HOOK_CELL((cur_i * grid.yLength + cur_j) * grid.zLength + cur_k);/' "$TMP/Tunnel.cpp"   # P7
+expect Tunnel.cpp 1206 'float splitVal = currNode->splitPlane;'
+sed -i '1206s/$/ REF_HOOK_NODE(currNode);/' "$TMP/Tunnel.cpp"
+expect Tunnel.cpp 1266 'float minDistance = FLT_MAX;'
+sed -i '1266s/$/ REF_HOOK_NODE(currNode);/' "$TMP/Tunnel.cpp"
+expect Triangle.cpp 40 'IntersectResult result(false);'
+sed -i '40s/$/ REF_HOOK_TRI();/' "$TMP/Triangle.cpp"
+
+# Lift trace() / radiance() / Render()'s loop out of MainWindow.cpp (never copied into the repo).
+expect MainWindow.cpp 69 'Color trace(GeometrySet &scene, Ray &r, int depth'
+expect MainWindow.cpp 145 'Color radiance(GeometrySet &scene, Ray &r, int depth'
+expect MainWindow.cpp 251 'int Render(GeometrySet &scene, PerspectiveCamera &camera'
+expect MainWindow.cpp 303 'int t2 = Utils::GetTickCount();'
+{
+    sed -n '69,249p' "$SRC/MainWindow.cpp" \
+        | sed -e 's/Ray &r, int depth/Ray r, int depth/' \
+              -e 's/IntersectResult result = scene.intersect(r);/IntersectResult result = scene.intersect(r); REF_HOOK_RAY();/'   # P4, P7
+    sed -n '251,303p' "$SRC/MainWindow.cpp"
+    echo '    ref_render_epilogue(colors);'
+    echo '    delete []colors;'
+    echo '    return t2 - t1;'
+    echo '}'
+} > "$TMP/ref_lifted_render.inc"
+
+CXXFLAGS="-O2 -std=c++14 -fopenmp -fpermissive -w -Wno-narrowing -ffp-contract=off -fPIC -include $HERE/ref/compat.h -I$TMP -I$HERE"
+SOURCES="Vector.cpp Point.cpp Matrix.cpp Camera.cpp Geometry.cpp GeometrySet.cpp Plane.cpp Sphere.cpp
+Triangle.cpp Grid.cpp Polygon.cpp Tunnel.cpp TunnelGenerator.cpp Material.cpp SolidColorMaterial.cpp
+CheckerMaterial.cpp RadianceCheckerMaterial.cpp PhongMaterial.cpp GlassMaterial.cpp RandomColorMaterial.cpp
+Scripts.cpp"
+
+build_variant() { # <hooks 0|1> <output>
+    local objs=()
+    mkdir -p "$TMP/obj$1"
+    for f in $SOURCES; do
+        g++ $CXXFLAGS -DREF_HOOKS=$1 -c "$TMP/$f" -o "$TMP/obj$1/${f%.cpp}.o" &
+        objs+=("$TMP/obj$1/${f%.cpp}.o")
+    done
+    g++ $CXXFLAGS -DREF_HOOKS=$1 -c "$HERE/ref/ref_utils.cpp" -o "$TMP/obj$1/ref_utils.o" &
+    g++ $CXXFLAGS -DREF_HOOKS=$1 -c "$HERE/ref/ref_driver.cpp" -o "$TMP/obj$1/ref_driver.o" &
+    wait
+    g++ -shared -fopenmp -o "$2" "${objs[@]}" "$TMP/obj$1/ref_utils.o" "$TMP/obj$1/ref_driver.o"
+}
+
+build_variant 1 "$OUT/libref.so"
+build_variant 0 "$OUT/libref_timing.so"
+echo "built $OUT/libref.so $OUT/libref_timing.so"

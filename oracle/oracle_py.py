@@ -1,0 +1,119 @@
+"""ctypes front-end for the two CPU checkers (oracle/oracle_abi.h).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  The product package never imports this module.
+
+  run("oracle", ...)      -> oracle/librt_oracle.so   (CPU restatement, rt_oracle.cpp)
+  run("ref", ...)         -> oracle/_ref/libref.so    (the unmodified reference, hooks on)
+  run("ref_timing", ...)  -> oracle/_ref/libref_timing.so (hooks compiled out; for timing)
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+STAT_NAMES = ["n_top", "n_tris", "grid_x", "grid_y", "grid_z", "cells_nonempty", "cell_entries",
+              "cell_max", "kd_nodes", "kd_leaves", "kd_leaf_refs", "kd_max_depth"]
+ALGORITHMS = {"linear": 0, "rgrid": 1, "fgrid": 2, "kd": 3, "sah": 4}
+SETTINGS = {"preset": 0, "simple": 1, "default": 2, "highspeed": 3, "highquality": 4}
+
+
+class OracleJob(C.Structure):
+    _fields_ = [
+        ("preset", C.c_int32), ("algorithm", C.c_int32), ("segments", C.c_int32),
+        ("width", C.c_int32), ("height", C.c_int32), ("samples", C.c_int32),
+        ("setting", C.c_int32), ("threads", C.c_int32), ("rng", C.c_int32),
+        ("seq_cap", C.c_int32), ("tri_cap", C.c_int32), ("repeat", C.c_int32),
+        ("seed", C.c_uint64), ("stl_path", C.c_char_p),
+        ("rgb", C.c_void_p), ("hit_id", C.c_void_p), ("hit_t", C.c_void_p),
+        ("seq_len", C.c_void_p), ("seq_hash", C.c_void_p), ("seq_buf", C.c_void_p),
+        ("tri_out", C.c_void_p), ("tri_mat", C.c_void_p),
+        ("n_rays", C.c_int64), ("n_tri_tests", C.c_int64), ("n_steps", C.c_int64),
+        ("render_ms", C.c_double), ("prepare_ms", C.c_double),
+        ("stats", C.c_int64 * 16), ("struct_hash", C.c_uint64), ("tri_hash", C.c_uint64),
+    ]
+
+
+_LIBS = {
+    "oracle": (os.path.join(HERE, "librt_oracle.so"), "rt_oracle_run"),
+    "ref": (os.path.join(HERE, "_ref", "libref.so"), "ref_run"),
+    "ref_timing": (os.path.join(HERE, "_ref", "libref_timing.so"), "ref_run"),
+}
+_loaded = {}
+
+
+def stl_fixture():
+    return os.path.join(os.path.dirname(HERE), "tests", "golden", "ball_fixture.stl")
+
+
+def available(which):
+    return os.path.exists(_LIBS[which][0])
+
+
+def build_oracle():
+    subprocess.check_call(["make", "-s", "-C", HERE, "librt_oracle.so"])
+
+
+def _fn(which):
+    if which not in _loaded:
+        path, sym = _LIBS[which]
+        if which == "oracle" and not os.path.exists(path):
+            build_oracle()
+        lib = C.CDLL(path)
+        fn = getattr(lib, sym)
+        fn.argtypes = [C.POINTER(OracleJob)]
+        fn.restype = C.c_int
+        _loaded[which] = fn
+    return _loaded[which]
+
+
+def run(which, preset, algorithm="linear", segments=150, width=400, height=300, samples=1,
+        setting="preset", threads=0, rng=0, seed=0, image=False, hits=False, seq=False, seq_cap=0,
+        triangles=False, repeat=0, stl_path=None):
+    """Run one job; returns a dict of numpy arrays / scalars."""
+    job = OracleJob()
+    job.preset = preset
+    job.algorithm = ALGORITHMS[algorithm] if isinstance(algorithm, str) else int(algorithm)
+    job.segments, job.width, job.height, job.samples = segments, width, height, samples
+    job.setting = SETTINGS[setting] if isinstance(setting, str) else int(setting)
+    job.threads, job.rng, job.seed, job.repeat = threads, rng, seed, repeat
+    job.stl_path = (stl_path or stl_fixture()).encode()
+    n = width * height
+    keep = {}
+
+    def out(name, arr):
+        keep[name] = arr
+        setattr(job, name, arr.ctypes.data)
+
+    if image:
+        out("rgb", np.zeros((width, height, 3), np.float32))  # reference order: [x][y]
+    if hits:
+        out("hit_id", np.full(n, -2, np.int32))
+        out("hit_t", np.zeros(n, np.float32))
+    if seq:
+        out("seq_len", np.zeros(n, np.int32))
+        out("seq_hash", np.zeros(n, np.uint64))
+        if seq_cap:
+            job.seq_cap = seq_cap
+            out("seq_buf", np.zeros((n, seq_cap), np.int32))
+    if triangles:
+        cap = 2 * (segments + 3) * segments + 16
+        job.tri_cap = cap
+        out("tri_out", np.zeros((cap, 12), np.float32))
+        out("tri_mat", np.zeros(cap, np.int32))
+    rc = _fn(which)(C.byref(job))
+    if rc != 0:
+        raise RuntimeError(f"{which} job failed rc={rc}")
+    res = dict(keep)
+    res["stats"] = {k: int(job.stats[i]) for i, k in enumerate(STAT_NAMES)}
+    if triangles:
+        nt = res["stats"]["n_tris"]
+        res["tri_out"] = res["tri_out"][:nt]
+        res["tri_mat"] = res["tri_mat"][:nt]
+    if image:
+        res["image"] = np.ascontiguousarray(res["rgb"].transpose(1, 0, 2))  # [y][x][3]
+    for k in ("n_rays", "n_tri_tests", "n_steps", "render_ms", "prepare_ms", "struct_hash", "tri_hash"):
+        res[k] = getattr(job, k)
+    return res
