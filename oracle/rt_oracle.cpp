@@ -1,0 +1,1170 @@
+// rt_oracle.cpp -- CPU restatement of the reference's ray-generation / intersection / shading path.
+//
+// TEST INFRASTRUCTURE ONLY.  This file is the parity ORACLE of the repo: a from-scratch, scalar
+// C++ restatement of windy32/win32-ray-tracing-demo's hot path (src/RayTracingOpt), each routine
+// citing the reference file:line it follows.  Only tests/, __graft_entry__.smoke() and bench.py's
+// cpu_baseline / --impl reference legs may load it; the product (CUDA) path never does.
+//
+// PINNING: tests/test_oracle_vs_ref.py runs identical jobs through this restatement and through
+// oracle/_ref/libref.so (the unmodified reference sources compiled headless by build_ref.sh) and
+// demands bit-equality of triangle streams, accelerator structure hashes, per-primary-ray hit ids,
+// distances and traversal sequences, Whitted images and erand48 Monte-Carlo images.  Where the
+// reference is absent (the GPU box) the same outputs are pinned by the committed fixtures in
+// tests/golden/ (generated from libref.so by tests/golden/make_golden.py).
+//
+// All arithmetic is IEEE float32 evaluated in the reference's operation order; build with
+// -ffp-contract=off and without -ffast-math / -march=native (oracle/Makefile).
+#include <algorithm>
+#include <chrono>
+#include <cfloat>
+#include <climits>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include <omp.h>
+
+#include "oracle_abi.h"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// float3 algebra -- reference Vector.cpp:48-86, Point.cpp:20-23
+// ------------------------------------------------------------------------------------------
+struct V3 { float x, y, z; };
+const float PI_F = 3.14159265359f; // Vector.h:8
+
+inline V3 v3(float x, float y, float z) { V3 r = {x, y, z}; return r; }
+inline V3 operator+(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+inline V3 operator-(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+inline V3 operator*(V3 a, float s) { return v3(a.x * s, a.y * s, a.z * s); }
+inline V3 mul(V3 a, V3 b) { return v3(a.x * b.x, a.y * b.y, a.z * b.z); }
+inline float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+inline V3 cross(V3 a, V3 b) { return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+inline V3 normalize(V3 a) { return a * (1 / sqrtf(a.x * a.x + a.y * a.y + a.z * a.z)); } // Vector.cpp:68-71
+inline float length(V3 a) { return sqrtf(a.x * a.x + a.y * a.y + a.z * a.z); }
+inline float comp(const V3 &a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
+inline float &comp(V3 &a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
+
+struct RayO { V3 o, d; };
+inline V3 at(const RayO &r, float t) { return r.o + r.d * t; } // Ray.h:24-27
+
+// ------------------------------------------------------------------------------------------
+// RNG -- erand48 (reference erand48.h:53-81: 48-bit LCG a=0x5DEECE66D c=0xB) and the
+// counter-based generator the CUDA path uses (Philox4x32-10), so that Monte-Carlo parity can be
+// checked path-for-path as well as statistically.
+// ------------------------------------------------------------------------------------------
+struct Rng
+{
+    int kind;        // ORACLE_RNG_*
+    uint64_t x48;    // erand48 state
+    uint32_t key[2]; // philox key
+    uint32_t ctr[4]; // philox counter (ctr[0] = block index)
+    uint32_t buf[4];
+    int used;        // lanes of buf consumed (4 = refill)
+};
+
+inline void philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
+{
+    uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
+    for (int r = 0; r < 10; r++)
+    {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+inline void rngSeedRow(Rng &g, int y)
+{ // MainWindow.cpp:273  Xi = {0, 0, (ushort)(y*y*y)}; xseed[2] is the most significant word
+    g.kind = ORACLE_RNG_ERAND48;
+    const uint32_t y3 = (uint32_t)y * (uint32_t)y * (uint32_t)y;
+    g.x48 = (uint64_t)(uint16_t)y3 << 32;
+}
+
+inline void rngSeedSample(Rng &g, uint64_t seed, uint32_t pixel, uint32_t sample)
+{ // include/rtb.h "counter-based RNG": key = (pixel, sample), counter = (block, seed_lo, seed_hi, 0)
+    g.kind = ORACLE_RNG_COUNTER;
+    g.key[0] = pixel; g.key[1] = sample;
+    g.ctr[0] = 0; g.ctr[1] = (uint32_t)seed; g.ctr[2] = (uint32_t)(seed >> 32); g.ctr[3] = 0;
+    g.used = 4;
+}
+
+inline double rngNext(Rng &g)
+{
+    if (g.kind == ORACLE_RNG_ERAND48)
+    { // erand48.h:53-81
+        g.x48 = (g.x48 * 0x5DEECE66Dull + 0xBull) & 0xFFFFFFFFFFFFull;
+        return ldexp((double)(g.x48 & 0xFFFF), -48) + ldexp((double)((g.x48 >> 16) & 0xFFFF), -32) +
+               ldexp((double)((g.x48 >> 32) & 0xFFFF), -16);
+    }
+    if (g.used == 4)
+    {
+        philox4x32_10(g.ctr, g.key, g.buf);
+        g.ctr[0]++;
+        g.used = 0;
+    }
+    return (double)((float)(g.buf[g.used++] >> 8) * (1.0f / 16777216.0f));
+}
+
+// ------------------------------------------------------------------------------------------
+// Materials -- Material.cpp, SolidColorMaterial.cpp:11-19, CheckerMaterial.cpp:11-23,
+// RadianceCheckerMaterial.cpp:12-29, PhongMaterial.cpp:13-29, GlassMaterial.cpp:3-7
+// ------------------------------------------------------------------------------------------
+enum { MAT_SOLID = 0, MAT_CHECKER = 1, MAT_RADIANCE_CHECKER = 2, MAT_PHONG = 3 };
+enum { DIR_XOZ = 0, DIR_XOY = 1, DIR_YOZ = 2 };
+
+struct Mat
+{
+    int kind;
+    float diffusiveness, reflectiveness, refractiveness, refractive_index;
+    V3 a;        // solid: local colour; phong: diffuse
+    V3 b;        // solid: emission;     phong: specular
+    float scale; // checker scale
+    float p;     // radiance-checker radiance / phong shininess
+    int dir;
+};
+
+Mat solid(V3 local, V3 emission, float d, float r, float t)
+{
+    Mat m; memset(&m, 0, sizeof(m));
+    m.kind = MAT_SOLID; m.a = local; m.b = emission;
+    m.diffusiveness = d; m.reflectiveness = r; m.refractiveness = t;
+    return m;
+}
+Mat glass(float index = 1.46) { Mat m = solid(v3(1, 1, 1), v3(0, 0, 0), 0, 0, 1); m.refractive_index = index; return m; }
+Mat checker(float scale, int dir = DIR_XOZ, float refl = 0)
+{ // CheckerMaterial.cpp:4-9: Material(1 - reflectiveness, reflectiveness, 0)
+    Mat m = solid(v3(0, 0, 0), v3(0, 0, 0), 1 - refl, refl, 0);
+    m.kind = MAT_CHECKER; m.scale = scale; m.dir = dir;
+    return m;
+}
+Mat radianceChecker(float radiance, float scale, int dir = DIR_XOZ)
+{
+    Mat m = solid(v3(0, 0, 0), v3(0, 0, 0), 1, 0, 0);
+    m.kind = MAT_RADIANCE_CHECKER; m.scale = scale; m.p = radiance; m.dir = dir;
+    return m;
+}
+Mat phong(V3 diffuse, V3 specular, float shininess, float refl = 0)
+{
+    Mat m = solid(diffuse, specular, 1 - refl, refl, 0);
+    m.kind = MAT_PHONG; m.p = shininess;
+    return m;
+}
+
+inline float checkerParity(const Mat &m, V3 pos)
+{ // CheckerMaterial.cpp:13-21: d = abs(floor(u*s) + floor(v*s)); d = fmod(d, 2)
+    float d;
+    if (m.dir == DIR_XOZ) d = fabsf(floorf(pos.x * m.scale) + floorf(pos.z * m.scale));
+    else if (m.dir == DIR_YOZ) d = fabsf(floorf(pos.y * m.scale) + floorf(pos.z * m.scale));
+    else d = fabsf(floorf(pos.x * m.scale) + floorf(pos.y * m.scale));
+    return (float)fmod((double)d, 2.0);
+}
+
+V3 matLocal(const Mat &m, const RayO &ray, V3 pos, V3 normal)
+{
+    switch (m.kind)
+    {
+    case MAT_SOLID: return m.a;
+    case MAT_CHECKER: return checkerParity(m, pos) < 1 ? v3(0.15f, 0.15f, 0.15f) : v3(1, 1, 1);
+    case MAT_RADIANCE_CHECKER: return v3(0.15f, 0.15f, 0.15f);
+    default:
+    { // PhongMaterial.cpp:13-29 (uses the stored, unflipped normal; white light from (-1,1,1))
+        const V3 lightDir = normalize(v3(-1, 1, 1));
+        float NdotL = dot(normal, lightDir);
+        NdotL = (NdotL < 0.0f) ? 0.0f : NdotL;
+        const V3 H = normalize(lightDir - ray.d);
+        float NdotH = dot(normal, H);
+        NdotH = (NdotH < 0.0f) ? 0.0f : NdotH;
+        const V3 diffuseTerm = m.a * NdotL;
+        const V3 specularTerm = m.b * powf(NdotH, m.p);
+        return mul(v3(1, 1, 1), diffuseTerm + specularTerm);
+    }
+    }
+}
+
+V3 matEmission(const Mat &m, V3 pos)
+{
+    if (m.kind == MAT_SOLID) return m.b;
+    if (m.kind == MAT_RADIANCE_CHECKER) return checkerParity(m, pos) < 1 ? v3(m.p, m.p, m.p) : v3(0, 0, 0);
+    return v3(0, 0, 0); // Material.cpp:19-22
+}
+
+// ------------------------------------------------------------------------------------------
+// Primitives -- Plane.cpp:3-34, Sphere.cpp:10-37, Triangle.cpp:17-121, Grid.cpp:30-116
+// ------------------------------------------------------------------------------------------
+struct Hit { bool hit; int id; float t; V3 pos, n; int mat; };
+
+struct Tri { V3 a, b, c, n; int mat; };
+
+struct Counters { long long rays, tris, steps; };
+struct Probe { std::vector<int> *seq; Counters *cnt; };
+
+inline float det3(float a11, float a12, float a13, float a21, float a22, float a23, float a31, float a32, float a33)
+{ // Triangle.cpp:25-36
+    return a11 * a22 * a33 + a12 * a23 * a31 + a13 * a21 * a32 - a13 * a22 * a31 - a11 * a23 * a32 - a12 * a21 * a33;
+}
+
+inline bool triIntersect(const Tri &T, const RayO &ray, float &tOut, Probe *pr)
+{ // Triangle.cpp:38-121 (Cramer's rule; early-out order det -> t -> beta -> gamma)
+    if (pr && pr->cnt) pr->cnt->tris++;
+    const float m11 = T.a.x - T.b.x, m21 = T.a.y - T.b.y, m31 = T.a.z - T.b.z;
+    const float m12 = T.a.x - T.c.x, m22 = T.a.y - T.c.y, m32 = T.a.z - T.c.z;
+    const float m13 = ray.d.x, m23 = ray.d.y, m33 = ray.d.z;
+    const float b1 = T.a.x - ray.o.x, b2 = T.a.y - ray.o.y, b3 = T.a.z - ray.o.z;
+    const float detM = det3(m11, m12, m13, m21, m22, m23, m31, m32, m33);
+    if ((double)fabsf(detM) < 1e-10) return false; // double-typed compare, Triangle.cpp:90
+    const float t = det3(m11, m12, b1, m21, m22, b2, m31, m32, b3) / detM;
+    if (t < 0.0005f) return false;
+    const float beta = det3(b1, m12, m13, b2, m22, m23, b3, m32, m33) / detM;
+    if (beta < -0.0001f || beta > 1.0001f) return false;
+    const float gamma = det3(m11, b1, m13, m21, b2, m23, m31, b3, m33) / detM;
+    if (gamma < -0.0001f || gamma > 1.0001f || 1 - beta - gamma < -0.0001f || 1 - beta - gamma > 1.0001f) return false;
+    tOut = t;
+    return true;
+}
+
+struct PlaneO { V3 normal, position; float dist; };
+struct SphereO { V3 center; float radius; };
+
+inline bool planeIntersect(const PlaneO &P, const RayO &ray, float &tOut)
+{ // Plane.cpp:9-34
+    const V3 op = P.position - ray.o;
+    const bool back = dot(P.normal, op) > 0;
+    const V3 n = back ? P.normal : P.normal * -1;
+    if (dot(n, ray.d) > 0)
+    {
+        const float distance = dot(op, n) / dot(ray.d, n);
+        if (distance >= 0.0005f) { tOut = distance; return true; }
+    }
+    return false;
+}
+
+inline bool sphereIntersect(const SphereO &S, const RayO &ray, float &tOut)
+{ // Sphere.cpp:10-37 (assumes a unit direction)
+    const V3 co = ray.o - S.center;
+    const float b = dot(ray.d, co);
+    float delta = b * b - (dot(co, co) - S.radius * S.radius);
+    if (delta >= 0)
+    {
+        delta = sqrtf(delta);
+        if (-b + delta >= 0.0005f)
+        {
+            tOut = (-b - delta >= 0.0005f) ? -b - delta : -b + delta;
+            return true;
+        }
+    }
+    return false;
+}
+
+inline void updateEntryExit(float &entry, float &exit, float v)
+{ // Grid.cpp:30-67
+    if (entry == FLT_MAX && exit == FLT_MAX) entry = v;
+    else if (exit == FLT_MAX)
+    {
+        if (v > entry) exit = v;
+        else { exit = entry; entry = v; }
+    }
+    else
+    {
+        if (v < entry) { exit = entry; entry = v; }
+        else if (v < exit) exit = v;
+    }
+}
+
+inline bool boxIntersect(V3 nearP, V3 size, const RayO &ray, float &entry, float &exit)
+{ // Grid.cpp:70-116
+    const V3 farP = nearP + size;
+    entry = FLT_MAX; exit = FLT_MAX;
+    for (int axis = 0; axis < 3; axis++)
+    {
+        const int a1 = (axis + 1) % 3, a2 = (axis + 2) % 3;
+        if ((double)fabsf(comp(ray.d, axis)) > 1e-10)
+        {
+            float distance = (comp(nearP, axis) - comp(ray.o, axis)) / comp(ray.d, axis);
+            V3 p = at(ray, distance);
+            if (comp(p, a1) >= comp(nearP, a1) && comp(p, a1) <= comp(farP, a1) &&
+                comp(p, a2) >= comp(nearP, a2) && comp(p, a2) <= comp(farP, a2))
+                updateEntryExit(entry, exit, distance);
+            distance = (comp(farP, axis) - comp(ray.o, axis)) / comp(ray.d, axis);
+            p = at(ray, distance);
+            if (comp(p, a1) >= comp(nearP, a1) && comp(p, a1) <= comp(farP, a1) &&
+                comp(p, a2) >= comp(nearP, a2) && comp(p, a2) <= comp(farP, a2))
+                updateEntryExit(entry, exit, distance);
+        }
+    }
+    return entry != FLT_MAX;
+}
+
+inline void triBounds(const Tri &t, V3 &mn, V3 &mx)
+{ // Triangle.cpp:201-237
+    mn = v3(std::min(std::min(t.a.x, t.b.x), t.c.x), std::min(std::min(t.a.y, t.b.y), t.c.y), std::min(std::min(t.a.z, t.b.z), t.c.z));
+    mx = v3(std::max(std::max(t.a.x, t.b.x), t.c.x), std::max(std::max(t.a.y, t.b.y), t.c.y), std::max(std::max(t.a.z, t.b.z), t.c.z));
+}
+
+// ------------------------------------------------------------------------------------------
+// Tunnel: tessellation (TunnelGenerator.cpp:6-366) and accelerators (Tunnel.cpp)
+// ------------------------------------------------------------------------------------------
+struct KdNodeO { int axis; float split; int left, right; std::vector<int> list; V3 mn, mx; };
+
+struct TunnelO
+{
+    int algorithm;
+    std::vector<Tri> tris; // surface[seg][j] flattened in (seg, j) order
+    // grid (Tunnel.h:51-67)
+    V3 origin; float csx, csy, csz; int nx, ny, nz;
+    std::vector<std::vector<int>> cells;
+    // k-d tree (Tunnel.h:75-93); nodes are stored in creation = pre-order
+    std::vector<KdNodeO> nodes;
+    int leaves; long long leafRefs; int maxDepth;
+};
+
+bool ringConvexity(const std::vector<V3> &front, const std::vector<V3> &rear, std::vector<int> &conn)
+{ // TunnelGenerator.cpp:6-176 createPolyhedron; conn: 0 BC, 1 AD, 2 Both, 3 Invalid
+    const float TOL = 0.001f;
+    const size_t n = front.size();
+    int invalid = 0;
+    conn.clear();
+    // "every other vertex of both rings lies behind the plane (base, normal)" -- lines 46-64 etc.
+    auto othersBehind = [&](V3 nrm, V3 base, size_t j, size_t k) {
+        for (size_t m = 0; m < n; m++)
+            if (m != j && m != k)
+            {
+                const V3 e = normalize(front[m] - base), f = normalize(rear[m] - base);
+                if (dot(nrm, e) > TOL || dot(nrm, f) > TOL) return false;
+            }
+        return true;
+    };
+    for (size_t j = 0; j < n; j++)
+    {
+        const size_t k = (j + 1) % n;
+        const V3 A = front[j], B = front[k], C = rear[j], D = rear[k];
+        const V3 nCBA = normalize(cross(B - C, A - B)), nCDB = normalize(cross(D - C, B - D));
+        bool ok1 = true;
+        if (dot(nCBA, normalize(D - A)) > TOL) ok1 = false;
+        if (ok1) ok1 = othersBehind(nCBA, A, j, k);
+        if (dot(nCDB, normalize(A - C)) > TOL) ok1 = false;
+        if (ok1) ok1 = othersBehind(nCDB, C, j, k);
+        const V3 nADB = normalize(cross(D - A, B - D)), nACD = normalize(cross(C - A, D - C));
+        bool ok2 = true;
+        if (dot(nADB, normalize(C - A)) > TOL) ok2 = false;
+        if (ok2) ok2 = othersBehind(nADB, A, j, k);
+        if (dot(nACD, normalize(B - A)) > TOL) ok2 = false;
+        if (ok2) ok2 = othersBehind(nACD, A, j, k);
+        if (ok1 && !ok2) conn.push_back(0);
+        else if (!ok1 && ok2) conn.push_back(1);
+        else if (ok1 && ok2) conn.push_back(2);
+        else { conn.push_back(3); invalid++; }
+    }
+    return invalid == 0;
+}
+
+inline Tri makeTri(V3 a, V3 b, V3 c, int mat)
+{ // Triangle.cpp:17-23: normal = (b-a) x (c-b), normalised
+    Tri t; t.a = a; t.b = b; t.c = c; t.n = normalize(cross(b - a, c - b)); t.mat = mat;
+    return t;
+}
+
+void generateTunnel(TunnelO &T, float rectWidth, float rectHeight, float archHeight, float pathRadius,
+                    float pathAngle, int archSegments, int pathSegments, int groundMat, int wallMat)
+{ // TunnelGenerator.cpp:197-366
+    std::vector<V3> cs;
+    cs.push_back(v3(rectWidth * 0.5f, 0.0f, 0.0f));
+    for (int i = 0; i <= archSegments; i++)
+    {
+        const float angle = PI_F * i / archSegments;
+        cs.push_back(v3(cosf(angle) * rectWidth * 0.5f, sinf(angle) * archHeight + rectHeight, 0.0f));
+    }
+    cs.push_back(v3(-rectWidth * 0.5f, 0.0f, 0.0f));
+
+    std::vector<std::vector<Tri>> surface(pathSegments);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int i = 0; i < pathSegments; i++)
+    {
+        const float theta1 = pathAngle * i / pathSegments;
+        const float theta2 = pathAngle * (i + 1) / pathSegments;
+        const V3 p1 = v3(pathRadius * (1.0f - cosf(theta1)), 0.0f, -pathRadius * sinf(theta1));
+        const V3 p2 = v3(pathRadius * (1.0f - cosf(theta2)), 0.0f, -pathRadius * sinf(theta2));
+        const float delta = (i == pathSegments - 1) ? 0 : pathAngle / pathSegments;
+        const V3 fwd = v3(0, 0, -1), seg = p2 - p1;
+        const float offsetAngle1 = acosf(dot(fwd, seg) * (1.0f / (length(fwd) * length(seg)))); // Vector.cpp:88-91
+        const float offsetAngle2 = offsetAngle1 + delta;
+        std::vector<V3> front, rear;
+        for (size_t j = 0; j < cs.size(); j++)
+        {
+            const V3 p = cs[j];
+            front.push_back(v3(p.x * cosf(offsetAngle1) - p.z * sinf(offsetAngle1), p.y,
+                               p.x * sinf(offsetAngle1) + p.z * cosf(offsetAngle1)) + (p1 - v3(0, 0, 0)));
+            rear.push_back(v3(p.x * cosf(offsetAngle2) - p.z * sinf(offsetAngle2), p.y,
+                              p.x * sinf(offsetAngle2) + p.z * cosf(offsetAngle2)) + (p2 - v3(0, 0, 0)));
+        }
+        std::vector<int> conn;
+        if (!ringConvexity(front, rear, conn)) continue; // non-convex segment contributes nothing (313-317)
+        for (size_t j = 0; j < cs.size(); j++)
+        {
+            const V3 A = front[j], B = front[(j + 1) % front.size()], C = rear[j], D = rear[(j + 1) % rear.size()];
+            const int mat = (j == cs.size() - 1) ? groundMat : wallMat;
+            if (conn[j] == 1) { surface[i].push_back(makeTri(A, C, D, mat)); surface[i].push_back(makeTri(A, D, B, mat)); }
+            else { surface[i].push_back(makeTri(C, D, B, mat)); surface[i].push_back(makeTri(C, B, A, mat)); }
+        }
+    }
+    T.tris.clear();
+    for (int i = 0; i < pathSegments; i++) T.tris.insert(T.tris.end(), surface[i].begin(), surface[i].end());
+}
+
+void tunnelBounds(const TunnelO &T, V3 &mn, V3 &mx)
+{ // Tunnel.cpp:351-370 / 487-506
+    mn = v3(FLT_MAX, FLT_MAX, FLT_MAX); mx = v3(-FLT_MAX, -FLT_MAX, -FLT_MAX);
+    for (size_t i = 0; i < T.tris.size(); i++)
+    {
+        V3 a, b; triBounds(T.tris[i], a, b);
+        mn = v3(std::min(mn.x, a.x), std::min(mn.y, a.y), std::min(mn.z, a.z));
+        mx = v3(std::max(mx.x, b.x), std::max(mx.y, b.y), std::max(mx.z, b.z));
+    }
+}
+
+void initGrid(TunnelO &T)
+{ // Tunnel.cpp:346-465
+    V3 mn, mx; tunnelBounds(T, mn, mx);
+    const float width = mx.x - mn.x, height = mx.y - mn.y, depth = mx.z - mn.z;
+    if (T.algorithm == 1)
+    {
+        const float maxLength = std::max(std::max(width, height), depth);
+        const float size = maxLength / 399;
+        T.origin = v3(mn.x - size / 2, mn.y - size / 2, mn.z - size / 2);
+        T.csx = T.csy = T.csz = size;
+        T.nx = (int)(width / T.csx + 1.5f); T.ny = (int)(height / T.csy + 1.5f); T.nz = (int)(depth / T.csz + 1.5f);
+    }
+    else
+    {
+        T.csx = width / 399; T.csy = height / 399; T.csz = depth / 399;
+        T.origin = v3(mn.x - T.csx / 2, mn.y - T.csy / 2, mn.z - T.csz / 2);
+        T.nx = T.ny = T.nz = 400;
+    }
+    T.cells.clear();
+    T.cells.resize((size_t)T.nx * T.ny * T.nz);
+    for (size_t m = 0; m < T.tris.size(); m++)
+    { // AABB-overlap binning (the exact SAT test is disabled in the reference, Tunnel.cpp:435-445)
+        V3 a, b; triBounds(T.tris[m], a, b);
+        const int xb = (int)((a.x - T.origin.x) / T.csx), yb = (int)((a.y - T.origin.y) / T.csy), zb = (int)((a.z - T.origin.z) / T.csz);
+        const int xe = (int)((b.x - T.origin.x) / T.csx), ye = (int)((b.y - T.origin.y) / T.csy), ze = (int)((b.z - T.origin.z) / T.csz);
+        for (int i = xb; i <= xe; i++)
+            for (int j = yb; j <= ye; j++)
+                for (int k = zb; k <= ze; k++) T.cells[((size_t)i * T.ny + j) * T.nz + k].push_back((int)m);
+    }
+}
+
+struct CentroidLess
+{ // Tunnel.cpp:519-544
+    const std::vector<Tri> *tris; int axis;
+    bool operator()(int p, int q) const
+    {
+        const Tri &s = (*tris)[p], &t = (*tris)[q];
+        const float c1 = (comp(s.a, axis) + comp(s.b, axis) + comp(s.c, axis)) / 3;
+        const float c2 = (comp(t.a, axis) + comp(t.b, axis) + comp(t.c, axis)) / 3;
+        return c1 < c2;
+    }
+};
+
+float splitMedian(TunnelO &T, int axis, std::vector<int> &list)
+{ // Tunnel.cpp:649-669 (std::sort reorders the caller's list; children inherit that order)
+    CentroidLess less = {&T.tris, axis};
+    std::sort(list.begin(), list.end(), less);
+    const Tri &t = T.tris[list[list.size() / 2]];
+    return (comp(t.a, axis) + comp(t.b, axis) + comp(t.c, axis)) / 3;
+}
+
+float splitSAH(TunnelO &T, int node, const std::vector<int> &list, int &bestAxis)
+{ // Tunnel.cpp:671-784: 99 uniform candidates per axis, first strict minimum wins
+    float minSAH = FLT_MAX, minSplit = 0;
+    const V3 mn = T.nodes[node].mn, mx = T.nodes[node].mx;
+    for (int axis = 0; axis < 3; axis++)
+    {
+        const int N = 100;
+        float cand[N];
+        int lc[N], rc[N];
+        for (int i = 1; i < N; i++) cand[i] = comp(mn, axis) + (comp(mx, axis) - comp(mn, axis)) * i / N;
+        const int nextAxis = (axis + 1) % 3, prevAxis = (axis + 2) % 3;
+#pragma omp parallel for schedule(static) if (list.size() > 4096)
+        for (int i = 1; i < N; i++)
+        {
+            const float s = cand[i];
+            int l = 0, r = 0;
+            for (size_t j = 0; j < list.size(); j++)
+            {
+                const Tri &t = T.tris[list[j]];
+                if (comp(t.a, axis) < s || comp(t.b, axis) < s || comp(t.c, axis) < s) l++;
+                if (comp(t.a, axis) >= s || comp(t.b, axis) >= s || comp(t.c, axis) >= s) r++;
+            }
+            lc[i] = l; rc[i] = r;
+        }
+        for (int i = 1; i < N; i++)
+        {
+            const V3 boxSize = mx - mn;
+            const float leftWidth = cand[i] - comp(mn, axis), rightWidth = comp(mx, axis) - cand[i];
+            const float height = comp(boxSize, nextAxis), depth = comp(boxSize, prevAxis);
+            const float SAH = (leftWidth * height + leftWidth * depth + height * depth) * lc[i] +
+                              (rightWidth * height + rightWidth * depth + height * depth) * rc[i];
+            if (SAH < minSAH) { minSAH = SAH; minSplit = cand[i]; bestAxis = axis; }
+        }
+    }
+    return minSplit;
+}
+
+void buildKd(TunnelO &T, int node, std::vector<int> &list, int depth)
+{ // Tunnel.cpp:546-638
+    if (depth > T.maxDepth) T.maxDepth = depth;
+    if (list.size() <= 8 || depth > 18)
+    {
+        T.nodes[node].axis = 3;
+        T.nodes[node].split = 0.0f;
+        T.nodes[node].left = T.nodes[node].right = -1;
+        T.nodes[node].list = list;
+        T.leaves++;
+        T.leafRefs += (long long)list.size();
+        return;
+    }
+    int axis = 0;
+    float median;
+    if (T.algorithm == 3) { axis = depth % 3; median = splitMedian(T, axis, list); }
+    else median = splitSAH(T, node, list, axis);
+    std::vector<int> leftPart, rightPart;
+    for (size_t i = 0; i < list.size(); i++)
+    { // straddlers go to both sides (619-634)
+        const Tri &t = T.tris[list[i]];
+        if (comp(t.a, axis) < median || comp(t.b, axis) < median || comp(t.c, axis) < median) leftPart.push_back(list[i]);
+        if (comp(t.a, axis) >= median || comp(t.b, axis) >= median || comp(t.c, axis) >= median) rightPart.push_back(list[i]);
+    }
+    T.nodes[node].axis = axis;
+    T.nodes[node].split = median;
+    const V3 mn = T.nodes[node].mn, mx = T.nodes[node].mx;
+    const int L = (int)T.nodes.size();
+    T.nodes.push_back(KdNodeO());
+    T.nodes[node].left = L;
+    T.nodes[L].mn = mn; T.nodes[L].mx = mx; comp(T.nodes[L].mx, axis) = median;
+    buildKd(T, L, leftPart, depth + 1);
+    const int R = (int)T.nodes.size();
+    T.nodes.push_back(KdNodeO());
+    T.nodes[node].right = R;
+    T.nodes[R].mn = mn; T.nodes[R].mx = mx; comp(T.nodes[R].mn, axis) = median;
+    buildKd(T, R, rightPart, depth + 1);
+}
+
+void initKd(TunnelO &T)
+{ // Tunnel.cpp:467-517
+    std::vector<int> list(T.tris.size());
+    for (size_t i = 0; i < list.size(); i++) list[i] = (int)i;
+    T.nodes.clear();
+    T.nodes.push_back(KdNodeO());
+    tunnelBounds(T, T.nodes[0].mn, T.nodes[0].mx);
+    T.leaves = 0; T.leafRefs = 0; T.maxDepth = 0;
+    buildKd(T, 0, list, 0);
+}
+
+// nearest hit of a triangle list, first-in-list wins ties (strict <)
+inline bool nearestInList(const TunnelO &T, const std::vector<int> &list, const RayO &ray, float lo, float hi,
+                          bool window, int &triOut, float &tOut, Probe *pr)
+{
+    float minDistance = FLT_MAX;
+    bool found = false;
+    for (size_t i = 0; i < list.size(); i++)
+    {
+        float t;
+        if (!triIntersect(T.tris[list[i]], ray, t, pr)) continue;
+        if (window && !(t >= lo && t <= hi)) continue;
+        if (t < minDistance) { minDistance = t; triOut = list[i]; found = true; }
+    }
+    tOut = minDistance;
+    return found;
+}
+
+inline void indexInGrid(const TunnelO &T, V3 p, int &i, int &j, int &k)
+{ // Tunnel.cpp:806-817
+    i = (int)((p.x - T.origin.x) / T.csx); j = (int)((p.y - T.origin.y) / T.csy); k = (int)((p.z - T.origin.z) / T.csz);
+    if (i < 0) i = 0;
+    if (j < 0) j = 0;
+    if (k < 0) k = 0;
+    if (i > T.nx - 1) i = T.nx - 1;
+    if (j > T.ny - 1) j = T.ny - 1;
+    if (k > T.nz - 1) k = T.nz - 1;
+}
+
+bool gridIntersect(const TunnelO &T, const RayO &ray, int &triOut, float &tOut, Probe *pr)
+{ // Tunnel.cpp:819-970 (3D-DDA; accepts the nearest hit of the current cell's list even outside the cell)
+    const V3 nearP = T.origin;
+    const V3 extent = v3(T.csx * T.nx, T.csy * T.ny, T.csz * T.nz);
+    const V3 farP = T.origin + extent;
+    int ci, cj, ck; float cd; V3 cp;
+    if (ray.o.x < nearP.x || ray.o.x > farP.x || ray.o.y < nearP.y || ray.o.y > farP.y || ray.o.z < nearP.z || ray.o.z > farP.z)
+    {
+        float entry, exit;
+        if (!boxIntersect(T.origin, extent, ray, entry, exit)) return false;
+        cd = entry; cp = at(ray, entry);
+        indexInGrid(T, cp, ci, cj, ck);
+    }
+    else { cp = ray.o; cd = 0; indexInGrid(T, ray.o, ci, cj, ck); }
+    while (true)
+    {
+        const int cell = (ci * T.ny + cj) * T.nz + ck;
+        if (pr) { if (pr->seq) pr->seq->push_back(cell); if (pr->cnt) pr->cnt->steps++; }
+        if (nearestInList(T, T.cells[cell], ray, 0, 0, false, triOut, tOut, pr)) return true;
+        const V3 p1 = T.origin + v3(ci * T.csx, cj * T.csy, ck * T.csz);
+        const V3 p2 = T.origin + v3((ci + 1) * T.csx, (cj + 1) * T.csy, (ck + 1) * T.csz);
+        float dx, dy, dz; int di, dj, dk;
+        if (ray.d.x > 0) { dx = (p2.x - cp.x) / ray.d.x; di = 1; } else { dx = (cp.x - p1.x) / -ray.d.x; di = -1; }
+        if (ray.d.y > 0) { dy = (p2.y - cp.y) / ray.d.y; dj = 1; } else { dy = (cp.y - p1.y) / -ray.d.y; dj = -1; }
+        if (ray.d.z > 0) { dz = (p2.z - cp.z) / ray.d.z; dk = 1; } else { dz = (cp.z - p1.z) / -ray.d.z; dk = -1; }
+        if (dx < dy && dx < dz) { ci += di; cd += dx; }
+        else if (dy < dz) { cj += dj; cd += dy; }
+        else { ck += dk; cd += dz; }
+        cp = at(ray, cd);
+        if (ci < 0 || ci > T.nx - 1 || cj < 0 || cj > T.ny - 1 || ck < 0 || ck > T.nz - 1) break;
+    }
+    return false;
+}
+
+bool kdIntersect(const TunnelO &T, const RayO &ray, int &triOut, float &tOut, Probe *pr)
+{ // Tunnel.cpp:1163-1297 (Havran TA_rec_B, 50-entry stack)
+    struct Elem { int node; float t; V3 pb; int prev; };
+    float a, b, t;
+    if (!boxIntersect(T.nodes[0].mn, T.nodes[0].mx - T.nodes[0].mn, ray, a, b)) return false; // Grid(near, far): size = far - near
+    Elem stack[50];
+    int cur = 0, farChild = -1;
+    int enPt = 0;
+    stack[enPt].t = a;
+    if (a >= 0) stack[enPt].pb = ray.o + ray.d * a; else stack[enPt].pb = ray.o;
+    int exPt = 1;
+    stack[exPt].t = b;
+    stack[exPt].pb = ray.o + ray.d * b;
+    stack[exPt].node = -1;
+    while (cur != -1)
+    {
+        while (T.nodes[cur].axis != 3)
+        {
+            if (pr) { if (pr->seq) pr->seq->push_back(cur); if (pr->cnt) pr->cnt->steps++; }
+            const float splitVal = T.nodes[cur].split;
+            const int axis = T.nodes[cur].axis, nextAxis = (axis + 1) % 3, prevAxis = (axis + 2) % 3;
+            if (comp(stack[enPt].pb, axis) <= splitVal)
+            {
+                if (comp(stack[exPt].pb, axis) <= splitVal) { cur = T.nodes[cur].left; continue; }
+                if (comp(stack[exPt].pb, axis) == splitVal) { cur = T.nodes[cur].right; continue; }
+                farChild = T.nodes[cur].right; cur = T.nodes[cur].left;
+            }
+            else
+            {
+                if (splitVal < comp(stack[exPt].pb, axis)) { cur = T.nodes[cur].right; continue; }
+                farChild = T.nodes[cur].left; cur = T.nodes[cur].right;
+            }
+            t = (splitVal - comp(ray.o, axis)) / comp(ray.d, axis);
+            const int tmp = exPt++;
+            if (exPt == enPt) exPt += 1;
+            stack[exPt].prev = tmp;
+            stack[exPt].t = t;
+            stack[exPt].node = farChild;
+            comp(stack[exPt].pb, axis) = splitVal;
+            comp(stack[exPt].pb, nextAxis) = comp(ray.o, nextAxis) + t * comp(ray.d, nextAxis);
+            comp(stack[exPt].pb, prevAxis) = comp(ray.o, prevAxis) + t * comp(ray.d, prevAxis);
+        }
+        if (pr) { if (pr->seq) pr->seq->push_back(cur); if (pr->cnt) pr->cnt->steps++; }
+        if (nearestInList(T, T.nodes[cur].list, ray, stack[enPt].t - 0.001f, stack[exPt].t + 0.001f, true, triOut, tOut, pr)) return true;
+        enPt = exPt;
+        cur = stack[exPt].node;
+        exPt = stack[enPt].prev;
+    }
+    return false;
+}
+
+bool linearIntersect(const TunnelO &T, const RayO &ray, int &triOut, float &tOut, Probe *pr)
+{ // Tunnel.cpp:786-804
+    float minDistance = FLT_MAX;
+    bool found = false;
+    for (size_t i = 0; i < T.tris.size(); i++)
+    {
+        float t;
+        if (triIntersect(T.tris[i], ray, t, pr) && t < minDistance) { minDistance = t; triOut = (int)i; found = true; }
+    }
+    tOut = minDistance;
+    return found;
+}
+
+// ------------------------------------------------------------------------------------------
+// Scene, camera, settings -- GeometrySet.cpp, Camera.cpp:4-26, RenderSetting.h:40-78
+// ------------------------------------------------------------------------------------------
+enum { PRIM_PLANE = 0, PRIM_SPHERE = 1, PRIM_TRIANGLE = 2, PRIM_TUNNEL = 3 };
+struct Prim { int type; PlaneO plane; SphereO sphere; Tri tri; int mat; };
+
+struct Camera { V3 eye, front, up, right; float ratio, xcenter, fov, fovScale, forward; };
+
+Camera makeCamera(V3 eye, V3 front, V3 up, float ratio, float fov, float forward)
+{ // Camera.cpp:4-18 (front is normalised in place before right/up are derived)
+    Camera c;
+    c.eye = eye;
+    front = normalize(front);
+    c.front = front;
+    c.ratio = ratio; c.fov = fov; c.forward = forward;
+    c.right = normalize(cross(front, up));
+    c.up = normalize(cross(c.right, front));
+    c.xcenter = ratio * 0.5f;
+    c.fovScale = tanf(fov * (PI_F * 0.5f / 180)) * 2;
+    return c;
+}
+
+inline RayO generateRay(const Camera &c, float x, float y)
+{ // Camera.cpp:20-26
+    const V3 r = c.right * ((x - c.xcenter) * c.fovScale);
+    const V3 u = c.up * ((y - 0.5f) * c.fovScale);
+    const V3 dir = normalize(c.front + r + u);
+    RayO ray = {c.eye + dir * c.forward, dir};
+    return ray;
+}
+
+struct Setting { bool mc; int maxDepth, terminationDepth, singleTracingDepth; };
+Setting settingOf(int which)
+{
+    switch (which)
+    {
+    case ORACLE_SETTING_HIGHSPEED: { Setting s = {true, 6, 2, 0}; return s; }
+    case ORACLE_SETTING_HIGHQUALITY: { Setting s = {true, 8, INT_MAX, INT_MAX}; return s; }
+    case ORACLE_SETTING_DEFAULT: { Setting s = {true, INT_MAX, 5, 2}; return s; }
+    default: { Setting s = {false, 20, INT_MAX, 0}; return s; }
+    }
+}
+
+struct Scene
+{
+    std::vector<Prim> prims;
+    std::vector<Mat> mats;
+    TunnelO tunnel;
+    bool hasTunnel;
+    Camera cam;
+    Setting setting;
+};
+
+int addMat(Scene &s, const Mat &m) { s.mats.push_back(m); return (int)s.mats.size() - 1; }
+void addPlane(Scene &s, V3 normal, float dist, int mat)
+{ // Plane.cpp:3-7
+    Prim p; memset(&p, 0, sizeof(p));
+    p.type = PRIM_PLANE; p.plane.normal = normal; p.plane.dist = dist;
+    p.plane.position = v3(0, 0, 0) + normal * dist; p.mat = mat;
+    s.prims.push_back(p);
+}
+void addSphere(Scene &s, V3 c, float r, int mat)
+{
+    Prim p; memset(&p, 0, sizeof(p));
+    p.type = PRIM_SPHERE; p.sphere.center = c; p.sphere.radius = r; p.mat = mat;
+    s.prims.push_back(p);
+}
+
+bool addStl(Scene &s, const char *path, int mat, V3 offset)
+{ // GeometrySet.cpp:33-86 with the identity matrix Script3 passes (Scripts.cpp:146-151)
+    FILE *fp = fopen(path, "rb");
+    if (!fp) return false;
+    char header[80]; int32_t count = 0;
+    if (fread(header, 80, 1, fp) != 1 || fread(&count, 4, 1, fp) != 1) { fclose(fp); return false; }
+    for (int i = 0; i < count; i++)
+    {
+        float f[12]; int16_t attr;
+        if (fread(f, 4, 12, fp) != 12 || fread(&attr, 2, 1, fp) != 1) { fclose(fp); return false; }
+        auto xform = [&](V3 p) { // Matrix.cpp:21-28 with m = identity, then + offset
+            return v3(1 * p.x + 0 * p.y + 0 * p.z, 0 * p.x + 1 * p.y + 0 * p.z, 0 * p.x + 0 * p.y + 1 * p.z) + offset;
+        };
+        Prim p; memset(&p, 0, sizeof(p));
+        p.type = PRIM_TRIANGLE; p.mat = mat;
+        p.tri.a = xform(v3(f[3], f[4], f[5])); p.tri.b = xform(v3(f[6], f[7], f[8])); p.tri.c = xform(v3(f[9], f[10], f[11]));
+        const V3 n = normalize(v3(f[0], f[1], f[2]));
+        p.tri.n = v3(1 * n.x + 0 * n.y + 0 * n.z, 0 * n.x + 1 * n.y + 0 * n.z, 0 * n.x + 0 * n.y + 1 * n.z);
+        p.tri.mat = mat;
+        s.prims.push_back(p);
+    }
+    fclose(fp);
+    return true;
+}
+
+bool buildPreset(Scene &s, const oracle_job *job)
+{ // Scripts.cpp:22-278
+    s.hasTunnel = false;
+    const V3 black = v3(0, 0, 0), white = v3(1, 1, 1);
+    if (job->preset == 1)
+    {
+        addPlane(s, v3(0, 1, 0), 0, addMat(s, radianceChecker(1.2f, 0.025f)));
+        addSphere(s, v3(-10, 15, -30), 15, addMat(s, solid(white, black, 1, 0, 0)));
+        addSphere(s, v3(20, 10, -20), 10, addMat(s, solid(white, black, 1, 0, 0)));
+        s.cam = makeCamera(v3(0, 15, 30), v3(0, 0, -1), v3(0, 1, 0), 1.3333f, 65, 0);
+        s.setting = settingOf(ORACLE_SETTING_DEFAULT);
+    }
+    else if (job->preset == 2 || job->preset == 3)
+    {
+        addPlane(s, v3(1, 0, 0), 1, addMat(s, solid(v3(0.75f, 0.25f, 0.25f), black, 1, 0, 0)));
+        addPlane(s, v3(1, 0, 0), 99, addMat(s, solid(v3(0.25f, 0.25f, 0.75f), black, 1, 0, 0)));
+        addPlane(s, v3(0, 1, 0), 0, addMat(s, solid(v3(0.75f, 0.75f, 0.75f), black, 1, 0, 0)));
+        addPlane(s, v3(0, 1, 0), 81.6f, addMat(s, solid(v3(0.75f, 0.75f, 0.75f), black, 1, 0, 0)));
+        addPlane(s, v3(0, 0, 1), 0, addMat(s, solid(v3(0.75f, 0.75f, 0.75f), black, 1, 0, 0)));
+        addPlane(s, v3(0, 0, 1), 170, addMat(s, solid(v3(0, 0, 0), black, 1, 0, 0)));
+        addSphere(s, v3(50, 681.6f - 0.27f, 81.6f), 600, addMat(s, solid(black, v3(24, 24, 24), 1, 0, 0)));
+        if (job->preset == 2)
+        {
+            addSphere(s, v3(27, 16.5f, 47), 16.5f, addMat(s, solid(white, black, 0, 1, 0)));
+            addSphere(s, v3(73, 16.5f, 78), 16.5f, addMat(s, glass()));
+        }
+        else if (!addStl(s, job->stl_path ? job->stl_path : "ball.stl", addMat(s, glass()), v3(50, 0, 40)))
+            return false;
+        s.cam = makeCamera(v3(50, 52, 295), v3(0, -0.045f, -1), v3(0, 1, -0.045f), 1.3333f, 28, 140.0f);
+        s.setting = settingOf(ORACLE_SETTING_DEFAULT);
+    }
+    else
+    {
+        const bool wide = job->preset == 4;
+        addSphere(s, wide ? v3(74.12f, 15, -96.59f) : v3(5000, 15, -5000), 15, addMat(s, phong(v3(1, 0, 0), white, 16)));
+        addPlane(s, v3(0, 1, 0), -0.01f, addMat(s, solid(v3(0.25, 0.25, 0.25), black, 1, 0, 0)));
+        addPlane(s, v3(0, 1, 0), 1000, addMat(s, solid(white, black, 1, 0, 0)));
+        const int ground = addMat(s, checker(0.05f));
+        const int wall = addMat(s, solid(black, black, 0.333f, 0.667f, 0));
+        s.tunnel.algorithm = job->algorithm;
+        generateTunnel(s.tunnel, 50, 25, 25, wide ? 100.0f : 5000.0f, wide ? PI_F * 0.416667f : PI_F * 0.5f,
+                       job->segments, job->segments, ground, wall);
+        Prim p; memset(&p, 0, sizeof(p));
+        p.type = PRIM_TUNNEL;
+        s.prims.push_back(p);
+        s.hasTunnel = true;
+        s.cam = makeCamera(v3(0, 25, 20), v3(0, 0, -1), v3(0, 1, 0), 1.3333f, 65, 0.0f);
+        s.setting = settingOf(ORACLE_SETTING_SIMPLE);
+    }
+    return true;
+}
+
+Hit sceneIntersect(const Scene &s, const RayO &ray, Probe *pr)
+{ // GeometrySet.cpp:95-110 (strict <, insertion order) + Tunnel.cpp:1299-1309 dispatch
+    if (pr && pr->cnt) pr->cnt->rays++;
+    Hit best; memset(&best, 0, sizeof(best));
+    best.hit = false; best.id = -1;
+    float minDistance = FLT_MAX;
+    const int nTop = (int)s.prims.size();
+    for (int i = 0; i < nTop; i++)
+    {
+        const Prim &p = s.prims[i];
+        float t; Hit h; h.hit = false;
+        if (p.type == PRIM_PLANE)
+        {
+            if (planeIntersect(p.plane, ray, t)) { h.hit = true; h.id = i; h.t = t; h.pos = at(ray, t); h.n = p.plane.normal; h.mat = p.mat; }
+        }
+        else if (p.type == PRIM_SPHERE)
+        {
+            if (sphereIntersect(p.sphere, ray, t)) { h.hit = true; h.id = i; h.t = t; h.pos = at(ray, t); h.n = normalize(h.pos - p.sphere.center); h.mat = p.mat; }
+        }
+        else if (p.type == PRIM_TRIANGLE)
+        {
+            if (triIntersect(p.tri, ray, t, pr)) { h.hit = true; h.id = i; h.t = t; h.pos = at(ray, t); h.n = p.tri.n; h.mat = p.mat; }
+        }
+        else
+        {
+            int tri = -1; bool ok;
+            const TunnelO &T = s.tunnel;
+            if (T.algorithm == 1 || T.algorithm == 2) ok = gridIntersect(T, ray, tri, t, pr);
+            else if (T.algorithm == 3 || T.algorithm == 4) ok = kdIntersect(T, ray, tri, t, pr);
+            else ok = linearIntersect(T, ray, tri, t, pr);
+            if (ok) { h.hit = true; h.id = nTop + tri; h.t = t; h.pos = at(ray, t); h.n = T.tris[tri].n; h.mat = T.tris[tri].mat; }
+        }
+        if (h.hit && h.t < minDistance) { minDistance = h.t; best = h; }
+    }
+    return best;
+}
+
+// ------------------------------------------------------------------------------------------
+// Shading -- MainWindow.cpp:69-143 (trace) and 145-249 (radiance)
+// ------------------------------------------------------------------------------------------
+struct Fresnel { RayO refl; V3 tdir; bool tir; float Re, Tr, P, RP, TP; };
+
+inline Fresnel refraction(const RayO &r, V3 p, V3 n, V3 nl, float nt)
+{ // MainWindow.cpp:111-133 == 212-231
+    Fresnel f; memset(&f, 0, sizeof(f));
+    f.refl.o = p; f.refl.d = r.d - n * 2 * dot(n, r.d);
+    const bool into = dot(n, nl) > 0;
+    const float nc = 1;
+    const float nnt = into ? nc / nt : nt / nc;
+    const float ddn = dot(r.d, nl);
+    const float cos2t = 1 - nnt * nnt * (1 - ddn * ddn);
+    f.tir = cos2t < 0;
+    if (f.tir) return f;
+    f.tdir = normalize(r.d * nnt - n * ((into ? 1 : -1) * (ddn * nnt + sqrtf(cos2t))));
+    const float a = nt - nc, b = nt + nc;
+    const float R0 = a * a / (b * b);
+    const float c = 1 - (into ? -ddn : dot(f.tdir, n));
+    f.Re = R0 + (1 - R0) * c * c * c * c * c;
+    f.Tr = 1 - f.Re;
+    f.P = 0.25f + 0.5f * f.Re;
+    f.RP = f.Re / f.P;
+    f.TP = f.Tr / (1 - f.P);
+    return f;
+}
+
+V3 trace(const Scene &s, RayO r, int depth, Probe *pr)
+{
+    const Hit res = sceneIntersect(s, r, pr);
+    if (!res.hit) return v3(0, 0, 0);
+    const Mat &m = s.mats[res.mat];
+    const V3 p = res.pos, n = res.n;
+    const V3 nl = (dot(n, r.d) < 0) ? n : n * -1;
+    const V3 local = matLocal(m, r, p, res.n);
+    if (++depth > s.setting.maxDepth) return v3(0, 0, 0);
+    if (depth > 100) return v3(0, 0, 0);
+    V3 diffusive = v3(0, 0, 0), reflective = v3(0, 0, 0), refractive = v3(0, 0, 0); // zero-initialised
+    if (m.diffusiveness > 0) diffusive = local;
+    if (m.reflectiveness > 0)
+    {
+        RayO nr = {p, r.d - nl * 2 * dot(nl, r.d)};
+        reflective = trace(s, nr, depth, pr);
+    }
+    if (m.refractiveness > 0)
+    {
+        const Fresnel f = refraction(r, p, n, nl, m.refractive_index);
+        if (f.tir) refractive = trace(s, f.refl, depth, pr);
+        else
+        {
+            const V3 a = trace(s, f.refl, depth, pr) * f.Re;
+            RayO tr = {p, f.tdir};
+            refractive = a + trace(s, tr, depth, pr) * f.Tr;
+        }
+    }
+    return diffusive * m.diffusiveness + reflective * m.reflectiveness + refractive * m.refractiveness;
+}
+
+V3 radiance(const Scene &s, RayO r, int depth, Rng &rng, Probe *pr)
+{
+    const Hit res = sceneIntersect(s, r, pr);
+    if (!res.hit) return v3(0, 0, 0);
+    const Mat &m = s.mats[res.mat];
+    const V3 p = res.pos, n = res.n;
+    const V3 nl = (dot(n, r.d) < 0) ? n : n * -1;
+    V3 local = matLocal(m, r, p, res.n);
+    const V3 emission = matEmission(m, p);
+    const float maxColor = (local.x + local.y + local.z) * 0.333333f;
+    if (++depth > s.setting.maxDepth) return emission;
+    if (depth > s.setting.terminationDepth)
+    {
+        if (rngNext(rng) < maxColor) local = local * (1 / maxColor);
+        else return emission;
+    }
+    if (depth > 100) return emission;
+    const float p_type = (float)rngNext(rng);
+    if (m.diffusiveness > 0 && p_type < m.diffusiveness)
+    { // uniform hemisphere, unit weight (MainWindow.cpp:185-200)
+        const float r1 = (float)rngNext(rng), r2 = (float)rngNext(rng);
+        const float theta = 2 * PI_F * r1;
+        const float phi = acosf(r2);
+        const V3 w = nl;
+        const V3 u = ((double)fabsf(w.x) > 0.1) ? normalize(cross(v3(0, 1, 0), w)) : normalize(cross(v3(1, 0, 0), w));
+        const V3 v = cross(w, u);
+        const V3 dir = u * (cosf(theta) * sinf(phi)) + v * (sinf(theta) * sinf(phi)) + w * cosf(phi);
+        RayO nr = {p, dir};
+        return emission + mul(local, radiance(s, nr, depth, rng, pr));
+    }
+    if (m.reflectiveness > 0 && p_type >= m.diffusiveness && p_type <= m.diffusiveness + m.reflectiveness)
+    {
+        RayO nr = {p, r.d - nl * 2 * dot(nl, r.d)};
+        return emission + mul(local, radiance(s, nr, depth, rng, pr));
+    }
+    if (m.refractiveness > 0 && p_type > m.diffusiveness + m.reflectiveness)
+    {
+        const Fresnel f = refraction(r, p, n, nl, m.refractive_index);
+        if (f.tir) return emission + mul(local, radiance(s, f.refl, depth, rng, pr));
+        RayO tr = {p, f.tdir};
+        if (depth > s.setting.singleTracingDepth)
+        {
+            if ((float)rngNext(rng) < f.P) return radiance(s, f.refl, depth, rng, pr) * f.RP;
+            return radiance(s, tr, depth, rng, pr) * f.TP;
+        }
+        // C++ leaves the evaluation order of the two operands of `+` unspecified; the g++ 13 build of
+        // the reference (oracle/_ref) evaluates the TRANSMITTED subtree first, which fixes the order
+        // in which the two subtrees consume the per-row erand48 stream (MainWindow.cpp:242-243).
+        const V3 b = radiance(s, tr, depth, rng, pr) * f.Tr;
+        const V3 a = radiance(s, f.refl, depth, rng, pr) * f.Re;
+        return a + b;
+    }
+    return emission;
+}
+
+void render(const Scene &s, const oracle_job *job, float *rgb, Counters *total)
+{ // MainWindow.cpp:251-303
+    const int width = job->width, height = job->height, samples = job->samples;
+    const float dx = 1.0f / height, dy = 1.0f / height;
+    std::vector<Counters> cnt(omp_get_max_threads() + 1);
+    memset(cnt.data(), 0, cnt.size() * sizeof(Counters));
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int y = 0; y < height; y++)
+    {
+        Probe pr = {nullptr, &cnt[omp_get_thread_num()]};
+        Rng rng;
+        rngSeedRow(rng, y);
+        for (int x = 0; x < width; x++)
+        {
+            const size_t index = (size_t)x * height + y;
+            V3 c;
+            if (s.setting.mc)
+            {
+                c = v3(0, 0, 0);
+                for (int i = 0; i < samples; i++)
+                {
+                    if (job->rng == ORACLE_RNG_COUNTER) rngSeedSample(rng, job->seed, (uint32_t)(y * width + x), (uint32_t)i);
+                    const float r1 = (float)rngNext(rng), r2 = (float)rngNext(rng);
+                    const float sx = (x + r1) * dx, sy = 1 - (y + r2) * dy;
+                    c = c + radiance(s, generateRay(s.cam, sx, sy), 0, rng, &pr) * (1.0f / samples);
+                }
+            }
+            else
+            {
+                const float sx = (x + 0.5f) * dx, sy = 1 - (y + 0.5f) * dy;
+                c = trace(s, generateRay(s.cam, sx, sy), 0, &pr);
+            }
+            if (rgb) { rgb[3 * index] = c.x; rgb[3 * index + 1] = c.y; rgb[3 * index + 2] = c.z; }
+        }
+    }
+    total->rays = total->tris = total->steps = 0;
+    for (size_t i = 0; i < cnt.size(); i++) { total->rays += cnt[i].rays; total->tris += cnt[i].tris; total->steps += cnt[i].steps; }
+}
+
+// ------------------------------------------------------------------------------------------
+// canonical structure hashes (same definition in ref_driver.cpp and the product binding)
+// ------------------------------------------------------------------------------------------
+inline void hmix(uint64_t &h, uint32_t v) { h = (h ^ v) * 0x100000001b3ull; }
+inline uint32_t fbits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+const uint64_t H0 = 0xcbf29ce484222325ull;
+
+void hashKd(const TunnelO &T, int node, uint64_t &h)
+{
+    const KdNodeO &n = T.nodes[node];
+    if (n.axis == 3)
+    {
+        hmix(h, 3); hmix(h, (uint32_t)n.list.size());
+        for (size_t i = 0; i < n.list.size(); i++) hmix(h, (uint32_t)n.list[i]);
+        return;
+    }
+    hmix(h, (uint32_t)n.axis); hmix(h, fbits(n.split));
+    hashKd(T, n.left, h);
+    hashKd(T, n.right, h);
+}
+
+} // namespace
+
+extern "C" int rt_oracle_run(oracle_job *job)
+{
+    if (!job || job->preset < 1 || job->preset > 5) return -1;
+    if (job->algorithm < 0 || job->algorithm > 4) return -2;
+    if (job->width <= 0 || job->height <= 0) return -3;
+    Scene s;
+    if (!buildPreset(s, job)) return -4;
+    if (job->setting != ORACLE_SETTING_PRESET) s.setting = settingOf(job->setting);
+
+    memset(job->stats, 0, sizeof(job->stats));
+    job->struct_hash = 0; job->tri_hash = 0; job->prepare_ms = 0;
+    const int nTop = (int)s.prims.size();
+    job->stats[ORACLE_STAT_N_TOP] = nTop;
+    if (s.hasTunnel)
+    {
+        TunnelO &T = s.tunnel;
+        const auto t0 = std::chrono::steady_clock::now();
+        if (T.algorithm == 1 || T.algorithm == 2) initGrid(T);
+        else if (T.algorithm == 3 || T.algorithm == 4) initKd(T);
+        job->prepare_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        job->stats[ORACLE_STAT_N_TRIS] = (int64_t)T.tris.size();
+        uint64_t th = H0;
+        for (size_t k = 0; k < T.tris.size(); k++)
+        {
+            const Tri &t = T.tris[k];
+            const float v[12] = {t.a.x, t.a.y, t.a.z, t.b.x, t.b.y, t.b.z, t.c.x, t.c.y, t.c.z, t.n.x, t.n.y, t.n.z};
+            const int mat = (t.mat == T.tris.back().mat) ? 1 : 0; // the last triangle of a ring is ground
+            for (int q = 0; q < 12; q++) hmix(th, fbits(v[q]));
+            hmix(th, (uint32_t)mat);
+            if (job->tri_out && (int)k < job->tri_cap) memcpy(job->tri_out + 12 * k, v, sizeof(v));
+            if (job->tri_mat && (int)k < job->tri_cap) job->tri_mat[k] = mat;
+        }
+        job->tri_hash = th;
+        if (T.algorithm == 1 || T.algorithm == 2)
+        {
+            uint64_t h = H0;
+            hmix(h, 0x47524944u);
+            hmix(h, (uint32_t)T.nx); hmix(h, (uint32_t)T.ny); hmix(h, (uint32_t)T.nz);
+            hmix(h, fbits(T.origin.x)); hmix(h, fbits(T.origin.y)); hmix(h, fbits(T.origin.z));
+            hmix(h, fbits(T.csx)); hmix(h, fbits(T.csy)); hmix(h, fbits(T.csz));
+            job->stats[ORACLE_STAT_GRID_X] = T.nx; job->stats[ORACLE_STAT_GRID_Y] = T.ny; job->stats[ORACLE_STAT_GRID_Z] = T.nz;
+            for (size_t c = 0; c < T.cells.size(); c++)
+            {
+                const std::vector<int> &l = T.cells[c];
+                if (l.empty()) continue;
+                job->stats[ORACLE_STAT_CELLS_NONEMPTY]++;
+                job->stats[ORACLE_STAT_CELL_ENTRIES] += (int64_t)l.size();
+                if ((int64_t)l.size() > job->stats[ORACLE_STAT_CELL_MAX]) job->stats[ORACLE_STAT_CELL_MAX] = (int64_t)l.size();
+                hmix(h, (uint32_t)c); hmix(h, (uint32_t)l.size());
+                for (size_t i = 0; i < l.size(); i++) hmix(h, (uint32_t)l[i]);
+            }
+            job->struct_hash = h;
+        }
+        else if (T.algorithm == 3 || T.algorithm == 4)
+        {
+            uint64_t h = H0;
+            hmix(h, 0x4b445452u);
+            hmix(h, fbits(T.nodes[0].mn.x)); hmix(h, fbits(T.nodes[0].mn.y)); hmix(h, fbits(T.nodes[0].mn.z));
+            hmix(h, fbits(T.nodes[0].mx.x)); hmix(h, fbits(T.nodes[0].mx.y)); hmix(h, fbits(T.nodes[0].mx.z));
+            hashKd(T, 0, h);
+            job->struct_hash = h;
+            job->stats[ORACLE_STAT_KD_NODES] = (int64_t)T.nodes.size();
+            job->stats[ORACLE_STAT_KD_LEAVES] = T.leaves;
+            job->stats[ORACLE_STAT_KD_LEAF_REFS] = T.leafRefs;
+            job->stats[ORACLE_STAT_KD_MAX_DEPTH] = T.maxDepth;
+        }
+    }
+
+    const int width = job->width, height = job->height;
+    if (job->hit_id || job->hit_t || job->seq_len || job->seq_hash || job->seq_buf)
+    {
+        const float dx = 1.0f / height, dy = 1.0f / height;
+#pragma omp parallel for schedule(dynamic, 1)
+        for (int y = 0; y < height; y++)
+        {
+            std::vector<int> rec;
+            for (int x = 0; x < width; x++)
+            {
+                const float sx = (x + 0.5f) * dx, sy = 1 - (y + 0.5f) * dy;
+                rec.clear();
+                Probe pr = {&rec, nullptr};
+                const Hit h = sceneIntersect(s, generateRay(s.cam, sx, sy), &pr);
+                const size_t p = (size_t)y * width + x;
+                if (job->hit_id) job->hit_id[p] = h.hit ? h.id : -1;
+                if (job->hit_t) job->hit_t[p] = h.hit ? h.t : -1.0f;
+                if (job->seq_len) job->seq_len[p] = (int)rec.size();
+                if (job->seq_hash)
+                {
+                    uint64_t hh = H0;
+                    for (size_t i = 0; i < rec.size(); i++) hmix(hh, (uint32_t)rec[i]);
+                    job->seq_hash[p] = hh;
+                }
+                if (job->seq_buf)
+                    for (int i = 0; i < job->seq_cap; i++) job->seq_buf[p * job->seq_cap + i] = i < (int)rec.size() ? rec[i] : -1;
+            }
+        }
+    }
+
+    job->n_rays = job->n_tri_tests = job->n_steps = 0;
+    job->render_ms = 0;
+    if (job->rgb || job->repeat > 0)
+    {
+        omp_set_num_threads(job->threads > 0 ? job->threads : omp_get_num_procs());
+        const int reps = job->repeat > 0 ? job->repeat : 1;
+        double best = 1e300;
+        Counters total = {0, 0, 0};
+        for (int r = 0; r < reps; r++)
+        {
+            const auto t0 = std::chrono::steady_clock::now();
+            render(s, job, r == 0 ? job->rgb : nullptr, &total);
+            const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            if (ms < best) best = ms;
+        }
+        job->render_ms = best;
+        job->n_rays = total.rays; job->n_tri_tests = total.tris; job->n_steps = total.steps;
+    }
+    return 0;
+}

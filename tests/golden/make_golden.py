@@ -1,0 +1,72 @@
+"""Generate tests/golden/ref_golden.{json,npz} from the UNMODIFIED reference (oracle/_ref/libref.so).
+
+Run in the build container, where /root/reference exists:
+
+    make -C oracle ref && python tests/golden/make_golden.py
+
+The reference ships no per-ray or per-pixel golden vectors, so these
+fixtures are outputs of the reference itself, compiled headless by oracle/build_ref.sh.  They
+travel with the repo to the GPU box, where /root/reference does not exist, and pin both the CPU
+restatement (oracle/rt_oracle.cpp) and the CUDA path.
+
+Small jobs keep their full arrays in the .npz; full-size jobs keep sha256 digests + scalars.
+"""
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from oracle import oracle_py as O  # noqa: E402
+
+ARRAYS = ["image", "hit_id", "hit_t", "seq_len", "seq_hash"]
+
+# (name, kwargs, keep_arrays)
+JOBS = []
+for alg in ["linear", "rgrid", "fgrid", "kd", "sah"]:
+    JOBS.append((f"p5_{alg}_s12_80x60", dict(preset=5, algorithm=alg, segments=12, width=80, height=60), True))
+    JOBS.append((f"p4_{alg}_s12_80x60", dict(preset=4, algorithm=alg, segments=12, width=80, height=60), True))
+for alg in ["rgrid", "fgrid", "kd", "sah"]:
+    JOBS.append((f"p5_{alg}_s150_400x300", dict(preset=5, algorithm=alg, segments=150, width=400, height=300), False))
+for alg in ["rgrid", "sah"]:
+    JOBS.append((f"p4_{alg}_s150_400x300", dict(preset=4, algorithm=alg, segments=150, width=400, height=300), False))
+JOBS += [
+    ("p5_sah_s40_160x120", dict(preset=5, algorithm="sah", segments=40, width=160, height=120), True),
+    ("p5_rgrid_s40_160x120", dict(preset=5, algorithm="rgrid", segments=40, width=160, height=120), True),
+    ("p1_mc_80x60_spp4", dict(preset=1, width=80, height=60, samples=4), True),
+    ("p2_mc_80x60_spp4", dict(preset=2, width=80, height=60, samples=4), True),
+    ("p3_mc_40x30_spp2", dict(preset=3, width=40, height=30, samples=2), True),
+    ("p2_hq_40x30_spp3", dict(preset=2, width=40, height=30, samples=3, setting="highquality"), True),
+    ("p2_hs_40x30_spp3", dict(preset=2, width=40, height=30, samples=3, setting="highspeed"), True),
+    ("p1_simple_80x60", dict(preset=1, width=80, height=60, setting="simple"), True),
+    ("p2_simple_80x60", dict(preset=2, width=80, height=60, setting="simple"), True),
+    ("p3_simple_40x30", dict(preset=3, width=40, height=30, setting="simple"), True),
+]
+
+
+def digest(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def main():
+    meta, arrays = {}, {}
+    for name, kw, keep in JOBS:
+        r = O.run("ref", image=True, hits=True, seq=True, **kw)
+        entry = {"job": kw, "stats": r["stats"], "struct_hash": f"{r['struct_hash']:016x}",
+                 "tri_hash": f"{r['tri_hash']:016x}", "n_rays": r["n_rays"], "n_tri_tests": r["n_tri_tests"],
+                 "n_steps": r["n_steps"], "sha256": {k: digest(r[k]) for k in ARRAYS}}
+        meta[name] = entry
+        if keep:
+            for k in ARRAYS:
+                arrays[f"{name}.{k}"] = r[k]
+        print(name, entry["stats"], entry["n_rays"], flush=True)
+    with open(os.path.join(HERE, "ref_golden.json"), "w") as f:
+        json.dump(meta, f, indent=1, sort_keys=True)
+    np.savez_compressed(os.path.join(HERE, "ref_golden.npz"), **arrays)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,87 @@
+"""The CPU oracle (oracle/rt_oracle.cpp) against the reference's own outputs.
+
+* test_oracle_matches_golden: every committed fixture produced by the unmodified reference
+  (tests/golden/make_golden.py) is reproduced bit for bit by the restatement -- structural KATs
+  of the reference's logs (grid 400x5x400, 121941 / 34478 leaves), triangle streams, accelerator
+  hashes, hit ids, distances, traversal sequences, Whitted and erand48 Monte-Carlo images.
+* test_oracle_matches_ref_live: the same comparison against oracle/_ref/libref.so on fresh job
+  shapes, when the reference library is present (it is built only where /root/reference exists).
+"""
+import hashlib
+import json
+
+import numpy as np
+import pytest
+
+from oracle import oracle_py as O
+
+ARRAYS = ["image", "hit_id", "hit_t", "seq_len", "seq_hash"]
+
+
+def _digest(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def _names():
+    import os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "ref_golden.json")) as f:
+        return sorted(json.load(f).keys())
+
+
+@pytest.mark.parametrize("name", _names())
+def test_oracle_matches_golden(golden, name):
+    meta, arrays = golden
+    g = meta[name]
+    r = O.run("oracle", image=True, hits=True, seq=True, **g["job"])
+    assert r["stats"] == g["stats"]
+    assert f"{r['struct_hash']:016x}" == g["struct_hash"]
+    assert f"{r['tri_hash']:016x}" == g["tri_hash"]
+    assert (r["n_rays"], r["n_tri_tests"], r["n_steps"]) == (g["n_rays"], g["n_tri_tests"], g["n_steps"])
+    for k in ARRAYS:
+        assert _digest(r[k]) == g["sha256"][k], k
+        if f"{name}.{k}" in arrays:
+            assert np.array_equal(r[k].view(np.uint8), arrays[f"{name}.{k}"].view(np.uint8)), k
+
+
+def test_reference_log_kats(golden):
+    """Structural values printed in the reference's own logs."""
+    meta, _ = golden
+    s = meta["p5_rgrid_s150_400x300"]["stats"]      # logs/test-tessellation-150/rgrid.log:7
+    assert (s["grid_x"], s["grid_y"], s["grid_z"]) == (400, 5, 400)
+    s = meta["p5_fgrid_s150_400x300"]["stats"]      # fgrid.log
+    assert (s["grid_x"], s["grid_y"], s["grid_z"]) == (400, 400, 400)
+    s = meta["p5_kd_s150_400x300"]["stats"]         # kd-tree.txt:7-8
+    assert s["kd_leaves"] == 121941 and s["kd_leaf_refs"] // s["kd_leaves"] == 8
+    s = meta["p5_sah_s150_400x300"]["stats"]        # kd-sah.log:7-8
+    assert s["kd_leaves"] == 34478 and s["kd_leaf_refs"] // s["kd_leaves"] == 11
+    assert meta["p5_sah_s150_400x300"]["stats"]["n_tris"] == 45900
+
+
+LIVE = [
+    dict(preset=5, algorithm="sah", segments=20, width=64, height=48),
+    dict(preset=5, algorithm="fgrid", segments=9, width=48, height=36),
+    dict(preset=4, algorithm="kd", segments=17, width=64, height=48),
+    dict(preset=4, algorithm="rgrid", segments=8, width=48, height=36),
+    dict(preset=2, width=32, height=24, samples=5),
+    dict(preset=1, width=32, height=24, samples=3, setting="highspeed"),
+]
+
+
+@pytest.mark.skipif(not O.available("ref"), reason="oracle/_ref/libref.so not built (no /root/reference)")
+@pytest.mark.parametrize("job", LIVE, ids=lambda j: "-".join(f"{k}{v}" for k, v in j.items()))
+def test_oracle_matches_ref_live(job):
+    a = O.run("ref", image=True, hits=True, seq=True, seq_cap=16, triangles=job["preset"] >= 4, **job)
+    b = O.run("oracle", image=True, hits=True, seq=True, seq_cap=16, triangles=job["preset"] >= 4, **job)
+    keys = ARRAYS + ["seq_buf"] + (["tri_out", "tri_mat"] if job["preset"] >= 4 else [])
+    for k in keys:
+        assert np.array_equal(a[k].view(np.uint8), b[k].view(np.uint8)), k
+    for k in ["stats", "struct_hash", "tri_hash", "n_rays", "n_tri_tests", "n_steps"]:
+        assert a[k] == b[k], k
+
+
+def test_counter_rng_mode_is_unbiased_vs_erand48():
+    """The counter-based stream (what the CUDA path uses) must estimate the same image as the
+    reference's erand48 stream: compare image means of preset 1 at 64 spp."""
+    a = O.run("oracle", 1, width=48, height=36, samples=64, image=True, rng=0)["image"]
+    b = O.run("oracle", 1, width=48, height=36, samples=64, image=True, rng=1, seed=7)["image"]
+    assert abs(a.mean() - b.mean()) / a.mean() < 0.02
