@@ -1,0 +1,202 @@
+/* rtb.h -- C ABI of the B200 ray-tracing hot path (librtb200.so).
+ *
+ * This is the drop-in boundary for ONE path of windy32/win32-ray-tracing-demo: per-pixel camera
+ * ray generation -> ray/scene intersection through the regular-grid / flat-grid / k-d (median,
+ * SAH) accelerators and the plane / sphere / triangle primitives -> Whitted `trace` and
+ * Monte-Carlo `radiance` shading.  Every entry point cites the reference interface it replaces
+ * (paths relative to the reference's src/RayTracingOpt/).
+ *
+ * Plain pointers and sizes only; no C++ / torch types.  The caller owns every host buffer it
+ * passes; the library owns device memory behind the opaque handles.  All functions return
+ * RTB_OK (0) or a negative rtb_status and are re-entrant per context (one context = one CUDA
+ * device + one stream).  There is NO CPU fallback: without a CUDA device rtb_init fails.
+ *
+ * Host-side builders (grid, k-d tree: reference Tunnel.cpp:346-784) stay on the host and hand
+ * their output over as the flattened SoA buffers of rtb_flat_scene.
+ */
+#ifndef RTB_H
+#define RTB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RTB_ABI_VERSION 1
+
+typedef enum rtb_status {
+    RTB_OK = 0,
+    RTB_ERR_INVALID = -1,     /* bad argument / inconsistent flat scene          */
+    RTB_ERR_NO_DEVICE = -2,   /* no usable CUDA device (there is no CPU path)    */
+    RTB_ERR_CUDA = -3,        /* CUDA runtime error; see rtb_last_error          */
+    RTB_ERR_UNSUPPORTED = -4, /* valid request outside the implemented path      */
+    RTB_ERR_OOM = -5
+} rtb_status;
+
+/* ---- materials: reference Material.h:7-38 and subclasses, flattened to a tagged POD ------- */
+enum { RTB_MAT_SOLID = 0,            /* SolidColorMaterial.cpp:11-19 (GlassMaterial.cpp:3-7 is SOLID white, (0,0,1), n=1.46) */
+       RTB_MAT_CHECKER = 1,          /* CheckerMaterial.cpp:11-23                 */
+       RTB_MAT_RADIANCE_CHECKER = 2, /* RadianceCheckerMaterial.cpp:12-29         */
+       RTB_MAT_PHONG = 3 };          /* PhongMaterial.cpp:13-29                   */
+enum { RTB_DIR_XOZ = 0, RTB_DIR_XOY = 1, RTB_DIR_YOZ = 2 }; /* CheckerMaterial.h:9 */
+
+typedef struct rtb_material {
+    int32_t kind;
+    float diffusiveness, reflectiveness, refractiveness, refractive_index; /* Material.h:18-24 */
+    float a[3];   /* SOLID: local colour;  PHONG: diffuse  */
+    float b[3];   /* SOLID: emission;      PHONG: specular */
+    float scale;  /* checker scale                         */
+    float p;      /* RADIANCE_CHECKER: radiance; PHONG: shininess */
+    int32_t dir;  /* RTB_DIR_*                             */
+    int32_t pad_[2];
+} rtb_material;   /* 64 bytes */
+
+/* ---- top-level geometries: reference GeometrySet.cpp:95-110 iterates them in insertion order */
+enum { RTB_PRIM_PLANE = 0,     /* Plane.cpp:3-34: v = normal xyz, position xyz, dist              */
+       RTB_PRIM_SPHERE = 1,    /* Sphere.cpp:4-37: v = center xyz, radius                         */
+       RTB_PRIM_TRIANGLES = 2, /* run of loose Triangle geometries (GeometrySet.cpp:33-86): first/count index loose_tri */
+       RTB_PRIM_TUNNEL = 3 };  /* the Tunnel geometry (Tunnel.cpp:1299-1309), traversed with `accel` */
+
+typedef struct rtb_prim {
+    int32_t type;
+    int32_t material; /* index into materials (ignored for TUNNEL: per-triangle) */
+    int32_t base_id;  /* top-level geometry index of this record (of its first triangle for a run) */
+    int32_t first, count; /* TRIANGLES: range in loose_tri */
+    float v[7];
+} rtb_prim;           /* 48 bytes */
+
+/* ---- accelerators: reference Tunnel.h:16-22 ---------------------------------------------- */
+enum { RTB_ACCEL_LINEAR = 0,       /* Tunnel.cpp:786-804  */
+       RTB_ACCEL_REGULAR_GRID = 1, /* Tunnel.cpp:346-465 (uniform cell = maxExtent/399), 819-970 */
+       RTB_ACCEL_FLAT_GRID = 2,    /* 400^3 anisotropic cells                                  */
+       RTB_ACCEL_KD_MEDIAN = 3,    /* Tunnel.cpp:546-669, 1163-1297                            */
+       RTB_ACCEL_KD_SAH = 4 };     /* Tunnel.cpp:671-784                                       */
+
+/* 8-byte k-d node, nodes stored in pre-order (left child = index + 1).
+ *   inner: a = float bits of the split position, b = (right_child_index << 2) | axis (0,1,2)
+ *   leaf : a = first index into kd_leaf_tris,    b = (count << 2) | 3                          */
+typedef struct rtb_kdnode { uint32_t a, b; } rtb_kdnode;
+
+/* Sparse grid cell directory: one word pair per 32 consecutive linear cell indices
+ * ((x*ny + y)*nz + z, reference Tunnel.h:63-66): `bits` marks non-empty cells, `rank` is the
+ * number of non-empty cells before this word.  Non-empty cell r owns
+ * grid_cell_tris[grid_cell_start[r] .. grid_cell_start[r+1]).                                   */
+typedef struct rtb_cellword { uint32_t bits, rank; } rtb_cellword;
+
+typedef struct rtb_flat_scene {
+    int32_t n_prims;      const rtb_prim *prims;
+    int32_t n_materials;  const rtb_material *materials;
+    int32_t n_top;        /* number of top-level geometries; tunnel triangle k has hit id n_top + k */
+    int32_t n_loose;      const float *loose_tri;  /* [n_loose][12]: a, b, c, normal (Triangle.h:10-11) */
+    int32_t n_tris;       const float *tri;        /* [n_tris][12] tunnel triangles in surface[seg][j] order */
+                          const int32_t *tri_material; /* [n_tris] */
+    int32_t accel;        /* RTB_ACCEL_* used by the TUNNEL prim */
+    /* grid (RTB_ACCEL_REGULAR_GRID / FLAT_GRID): reference Tunnel.h:51-67 */
+    float grid_origin[3], grid_cell[3];
+    int32_t grid_dims[3];
+    int64_t n_cellwords;  const rtb_cellword *grid_words;      /* ceil(nx*ny*nz / 32)        */
+    int64_t n_cells_used; const uint32_t *grid_cell_start;     /* [n_cells_used + 1]         */
+    int64_t n_cell_refs;  const uint32_t *grid_cell_tris;      /* [n_cell_refs]              */
+    /* k-d tree (RTB_ACCEL_KD_*): reference Tunnel.h:75-93 */
+    float kd_min[3], kd_max[3];                                 /* root box                   */
+    int32_t n_kd_nodes;   const rtb_kdnode *kd_nodes;
+    int64_t n_kd_refs;    const uint32_t *kd_leaf_tris;
+} rtb_flat_scene;
+
+/* ---- camera: reference Camera.h:7-23; the derived fields are computed on the host exactly as
+ * Camera.cpp:4-18 does (fovScale needs the host tanf)                                        */
+typedef struct rtb_camera {
+    float eye[3], front[3], up[3], right[3];
+    float xcenter, fov_scale, forward;
+} rtb_camera;
+
+/* ---- render policy: reference RenderSetting.h:6-79 ---------------------------------------- */
+typedef struct rtb_render_setting {
+    int32_t enable_monte_carlo;
+    int32_t max_depth, termination_depth, single_tracing_depth;
+} rtb_render_setting;
+
+/* ---- frame description: the file-statics width/height/samples of reference
+ * MainWindow.cpp:33-36 plus the tile-row shard this device renders.
+ * Rows are dealt to ranks in blocks of `row_block` rows, block b going to rank b % world
+ * (the reference's `omp parallel for schedule(dynamic,1)` over y, MainWindow.cpp:267-269, made
+ * static across devices).  The output holds this rank's rows only, in increasing y, row-major
+ * [local_row][x][3] float RGB -- unless RTB_LAYOUT_REFERENCE is set (world must be 1), which
+ * gives the reference framebuffer order index = x*height + y (MainWindow.cpp:276).          */
+enum { RTB_LAYOUT_ROWMAJOR = 0, RTB_LAYOUT_REFERENCE = 1 };
+typedef struct rtb_frame {
+    int32_t width, height;
+    int32_t samples;      /* spp when enable_monte_carlo                                      */
+    uint64_t seed;        /* counter-based RNG frame seed (key = pixel, sample)               */
+    int32_t rank, world;  /* shard selector; 0,1 = whole frame                                */
+    int32_t row_block;    /* rows per dealt block (multiple of 8; 0 = default 8)              */
+    int32_t layout;       /* RTB_LAYOUT_*                                                     */
+    int32_t counters;     /* non-zero: also count triangle tests / traversal steps (slower)   */
+} rtb_frame;
+
+typedef struct rtb_stats {
+    int64_t n_rays;        /* scene intersections issued (primary + secondary)                */
+    int64_t n_tri_tests;   /* frame.counters only                                             */
+    int64_t n_steps;       /* cells / k-d nodes visited; frame.counters only                  */
+    int64_t n_local_rows;  /* rows rendered by this rank                                      */
+    float kernel_ms;       /* CUDA-event time of the render kernel(s) on the context stream   */
+    float total_ms;        /* CUDA-event time of the whole call incl. copies                  */
+    int32_t n_launches;    /* kernels launched by the call                                    */
+    int32_t pad_;
+} rtb_stats;
+
+typedef struct rtb_ctx rtb_ctx;
+typedef struct rtb_scene rtb_scene;
+
+/* Context = one CUDA device.  `stream` may be 0 (library-owned stream) or a caller's
+ * cudaStream_t cast to void* (e.g. torch's current stream) for rtb_render_device.            */
+int rtb_init(int device, rtb_ctx **ctx);
+int rtb_shutdown(rtb_ctx *ctx);
+const char *rtb_last_error(const rtb_ctx *ctx); /* ctx may be NULL: last global error       */
+int rtb_abi_version(void);
+
+/* Number of rows / first-row list of a shard (pure host arithmetic; no device needed).       */
+int64_t rtb_shard_rows(const rtb_frame *frame);
+
+/* Upload a flattened scene.  Replaces nothing in the reference (it has no device); it is the
+ * device-side image of GeometrySet + Tunnel::grid / Tunnel::root.                           */
+int rtb_scene_upload(rtb_ctx *ctx, const rtb_flat_scene *flat, rtb_scene **scene);
+int rtb_scene_free(rtb_ctx *ctx, rtb_scene *scene);
+int64_t rtb_scene_device_bytes(const rtb_scene *scene);
+
+/* Replaces `int Render(GeometrySet&, PerspectiveCamera&, RenderSetting&, ProgressCallback)`
+ * (reference MainWindow.cpp:251-303, the RenderProc of Scripts.h:11-12): ray generation,
+ * trace()/radiance() and the framebuffer store for this rank's rows.  `rgb_out` is a HOST
+ * buffer of rtb_shard_rows(frame)*width*3 floats; the device->host copy is part of the call. */
+int rtb_render(rtb_ctx *ctx, const rtb_scene *scene, const rtb_camera *camera,
+               const rtb_render_setting *setting, const rtb_frame *frame, float *rgb_out,
+               rtb_stats *stats);
+
+/* Same, writing to a DEVICE buffer on `stream` without synchronising (stats are filled only if
+ * non-NULL, which forces a sync).  Used to keep the framebuffer resident for the NCCL gather.   */
+int rtb_render_device(rtb_ctx *ctx, const rtb_scene *scene, const rtb_camera *camera,
+                      const rtb_render_setting *setting, const rtb_frame *frame,
+                      void *rgb_device, void *stream, rtb_stats *stats);
+
+/* Parity hook: primary rays only (pixel centres, MainWindow.cpp:294-297) through
+ * GeometrySet::intersect.  Arrays are row-major [y*width + x] HOST buffers, any may be NULL.
+ * seq_* record the accelerator steps of the TUNNEL prim (cell indices / pre-order node ids):
+ * seq_hash folds h = (h ^ id) * 0x100000001b3 from 0xcbf29ce484222325; seq_buf keeps the first
+ * seq_cap ids per ray (-1 padded).                                                            */
+int rtb_trace_primary(rtb_ctx *ctx, const rtb_scene *scene, const rtb_camera *camera,
+                      int32_t width, int32_t height, int32_t *hit_id, float *hit_t,
+                      int32_t *seq_len, uint64_t *seq_hash, int32_t *seq_buf, int32_t seq_cap);
+
+/* Replaces `IntersectResult Geometry::intersect(Ray&)` (reference Geometry.h:17) and PT's
+ * `Accelerator::intersect` (PerformanceTest/Accelerator.h:6-15) for a BATCH of rays:
+ * rays = [n][6] origin, direction (HOST); outputs (HOST, any may be NULL): hit id (-1 miss),
+ * distance, position xyz, normal xyz (the stored, unflipped normal).                         */
+int rtb_intersect_rays(rtb_ctx *ctx, const rtb_scene *scene, int64_t n, const float *rays,
+                       int32_t *hit_id, float *hit_t, float *position, float *normal);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTB_H */

@@ -1,0 +1,371 @@
+"""rtb200 -- Python harness over the C ABI (include/rtb.h) and the C++ host API (host/rt.h).
+
+The product is the two in-tree shared libraries; this module only binds them with ctypes for the
+tests, bench.py and torch.distributed plumbing.  The directory name is not a Python identifier, so
+import it through `rtb200.py` at the repo root (`import rtb200`).
+
+There is no CPU fallback anywhere below: every compute call goes to librtb200.so's CUDA kernels
+and raises RtbError when the library or a CUDA device is missing.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+CUDA_LIB = os.path.join(PKG, "librtb200.so")
+HOST_LIB = os.path.join(PKG, "librtb200_host.so")
+
+ALGORITHMS = {"linear": 0, "rgrid": 1, "fgrid": 2, "kd": 3, "sah": 4}
+STAT_NAMES = ["n_top", "n_tris", "grid_x", "grid_y", "grid_z", "cells_nonempty", "cell_entries",
+              "cell_max", "kd_nodes", "kd_leaves", "kd_leaf_refs", "kd_max_depth"]
+LAYOUT_ROWMAJOR, LAYOUT_REFERENCE = 0, 1
+
+
+class RtbError(RuntimeError):
+    pass
+
+
+# ---- ctypes mirrors of include/rtb.h ---------------------------------------------------------
+class Material(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("diffusiveness", C.c_float), ("reflectiveness", C.c_float),
+                ("refractiveness", C.c_float), ("refractive_index", C.c_float), ("a", C.c_float * 3),
+                ("b", C.c_float * 3), ("scale", C.c_float), ("p", C.c_float), ("dir", C.c_int32),
+                ("pad_", C.c_int32 * 2)]
+
+
+class Prim(C.Structure):
+    _fields_ = [("type", C.c_int32), ("material", C.c_int32), ("base_id", C.c_int32),
+                ("first", C.c_int32), ("count", C.c_int32), ("v", C.c_float * 7)]
+
+
+class KdNode(C.Structure):
+    _fields_ = [("a", C.c_uint32), ("b", C.c_uint32)]
+
+
+class CellWord(C.Structure):
+    _fields_ = [("bits", C.c_uint32), ("rank", C.c_uint32)]
+
+
+class FlatScene(C.Structure):
+    _fields_ = [
+        ("n_prims", C.c_int32), ("prims", C.POINTER(Prim)),
+        ("n_materials", C.c_int32), ("materials", C.POINTER(Material)),
+        ("n_top", C.c_int32),
+        ("n_loose", C.c_int32), ("loose_tri", C.POINTER(C.c_float)),
+        ("n_tris", C.c_int32), ("tri", C.POINTER(C.c_float)), ("tri_material", C.POINTER(C.c_int32)),
+        ("accel", C.c_int32),
+        ("grid_origin", C.c_float * 3), ("grid_cell", C.c_float * 3), ("grid_dims", C.c_int32 * 3),
+        ("n_cellwords", C.c_int64), ("grid_words", C.POINTER(CellWord)),
+        ("n_cells_used", C.c_int64), ("grid_cell_start", C.POINTER(C.c_uint32)),
+        ("n_cell_refs", C.c_int64), ("grid_cell_tris", C.POINTER(C.c_uint32)),
+        ("kd_min", C.c_float * 3), ("kd_max", C.c_float * 3),
+        ("n_kd_nodes", C.c_int32), ("kd_nodes", C.POINTER(KdNode)),
+        ("n_kd_refs", C.c_int64), ("kd_leaf_tris", C.POINTER(C.c_uint32)),
+    ]
+
+
+class Camera(C.Structure):
+    _fields_ = [("eye", C.c_float * 3), ("front", C.c_float * 3), ("up", C.c_float * 3),
+                ("right", C.c_float * 3), ("xcenter", C.c_float), ("fov_scale", C.c_float),
+                ("forward", C.c_float)]
+
+
+class RenderSetting(C.Structure):
+    _fields_ = [("enable_monte_carlo", C.c_int32), ("max_depth", C.c_int32),
+                ("termination_depth", C.c_int32), ("single_tracing_depth", C.c_int32)]
+
+
+INT_MAX = 2 ** 31 - 1
+SETTINGS = {  # reference RenderSetting.h:40-78
+    "simple": (0, 20, INT_MAX, 0), "default": (1, INT_MAX, 5, 2),
+    "highspeed": (1, 6, 2, 0), "highquality": (1, 8, INT_MAX, INT_MAX),
+}
+
+
+class Frame(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("samples", C.c_int32),
+                ("seed", C.c_uint64), ("rank", C.c_int32), ("world", C.c_int32),
+                ("row_block", C.c_int32), ("layout", C.c_int32), ("counters", C.c_int32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("n_rays", C.c_int64), ("n_tri_tests", C.c_int64), ("n_steps", C.c_int64),
+                ("n_local_rows", C.c_int64), ("kernel_ms", C.c_float), ("total_ms", C.c_float),
+                ("n_launches", C.c_int32), ("pad_", C.c_int32)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "pad_"}
+
+
+ABI_SYMBOLS = ["rtb_init", "rtb_shutdown", "rtb_last_error", "rtb_abi_version", "rtb_shard_rows",
+               "rtb_scene_upload", "rtb_scene_free", "rtb_scene_device_bytes", "rtb_render",
+               "rtb_render_device", "rtb_trace_primary", "rtb_intersect_rays"]
+
+_cuda = None
+_host = None
+
+
+def cuda_lib():
+    """librtb200.so; raises RtbError (never falls back) when it has not been built."""
+    global _cuda
+    if _cuda is None:
+        if not os.path.exists(CUDA_LIB):
+            raise RtbError(f"{CUDA_LIB} is missing: run `python __graft_entry__.py build` (there is no CPU fallback)")
+        lib = C.CDLL(CUDA_LIB, mode=C.RTLD_GLOBAL)
+        vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+        lib.rtb_init.argtypes = [C.c_int, C.POINTER(vp)]
+        lib.rtb_shutdown.argtypes = [vp]
+        lib.rtb_last_error.argtypes = [vp]
+        lib.rtb_last_error.restype = C.c_char_p
+        lib.rtb_shard_rows.argtypes = [C.POINTER(Frame)]
+        lib.rtb_shard_rows.restype = i64
+        lib.rtb_scene_upload.argtypes = [vp, C.POINTER(FlatScene), C.POINTER(vp)]
+        lib.rtb_scene_free.argtypes = [vp, vp]
+        lib.rtb_scene_device_bytes.argtypes = [vp]
+        lib.rtb_scene_device_bytes.restype = i64
+        lib.rtb_render.argtypes = [vp, vp, C.POINTER(Camera), C.POINTER(RenderSetting), C.POINTER(Frame), vp,
+                                   C.POINTER(Stats)]
+        lib.rtb_render_device.argtypes = [vp, vp, C.POINTER(Camera), C.POINTER(RenderSetting), C.POINTER(Frame),
+                                          vp, vp, C.POINTER(Stats)]
+        lib.rtb_trace_primary.argtypes = [vp, vp, C.POINTER(Camera), i32, i32, vp, vp, vp, vp, vp, i32]
+        lib.rtb_intersect_rays.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp]
+        _cuda = lib
+    return _cuda
+
+
+def host_lib():
+    global _host
+    if _host is None:
+        cuda_lib()
+        if not os.path.exists(HOST_LIB):
+            raise RtbError(f"{HOST_LIB} is missing: run `python __graft_entry__.py build`")
+        lib = C.CDLL(HOST_LIB)
+        vp = C.c_void_p
+        lib.rtbh_preset_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_char_p]
+        lib.rtbh_preset_create.restype = vp
+        lib.rtbh_free.argtypes = [vp]
+        lib.rtbh_flat.argtypes = [vp]
+        lib.rtbh_flat.restype = C.POINTER(FlatScene)
+        lib.rtbh_camera.argtypes = [vp]
+        lib.rtbh_camera.restype = C.POINTER(Camera)
+        lib.rtbh_setting.argtypes = [vp]
+        lib.rtbh_setting.restype = C.POINTER(RenderSetting)
+        for f in ("rtbh_prepare_ms", "rtbh_build_ms"):
+            getattr(lib, f).argtypes = [vp]
+            getattr(lib, f).restype = C.c_double
+        lib.rtbh_host_bytes.argtypes = [vp]
+        lib.rtbh_host_bytes.restype = C.c_int64
+        lib.rtbh_stats.argtypes = [vp, C.POINTER(C.c_int64)]
+        for f in ("rtbh_tri_hash", "rtbh_struct_hash"):
+            getattr(lib, f).argtypes = [vp]
+            getattr(lib, f).restype = C.c_uint64
+        lib.rtbh_script_run.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int,
+                                        C.c_char_p, vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(Stats)]
+        lib.rtbh_last_error.restype = C.c_char_p
+        lib.rtbh_intersect_batch.argtypes = [vp, C.c_int64, vp, vp, vp, vp, vp]
+        lib.rtbh_intersect_one.argtypes = [vp, vp, vp, vp, vp, vp]
+        _host = lib
+    return _host
+
+
+def stl_fixture():
+    return os.path.join(ROOT, "tests", "golden", "ball_fixture.stl")
+
+
+def _alg(a):
+    return ALGORITHMS[a] if isinstance(a, str) else int(a)
+
+
+def make_setting(name):
+    return RenderSetting(*SETTINGS[name])
+
+
+# ---- host side: preset scenes built by the C++ host API ----------------------------------------
+class PresetScene:
+    """A reference preset (Scripts.cpp Script1..5) built and flattened by the C++ host library."""
+
+    def __init__(self, preset, algorithm="linear", segments=150, stl_path=None):
+        lib = host_lib()
+        self.preset, self.algorithm, self.segments = preset, algorithm, segments
+        self._h = lib.rtbh_preset_create(preset, _alg(algorithm), segments, (stl_path or stl_fixture()).encode())
+        if not self._h:
+            raise RtbError("rtbh_preset_create failed (bad preset / algorithm / STL path)")
+        self.flat = lib.rtbh_flat(self._h)
+        self.camera = lib.rtbh_camera(self._h).contents
+        self.setting = lib.rtbh_setting(self._h).contents
+
+    def close(self):
+        if self._h:
+            host_lib().rtbh_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def prepare_ms(self):
+        return host_lib().rtbh_prepare_ms(self._h)
+
+    @property
+    def build_ms(self):
+        return host_lib().rtbh_build_ms(self._h)
+
+    @property
+    def host_bytes(self):
+        return host_lib().rtbh_host_bytes(self._h)
+
+    def stats(self):
+        out = (C.c_int64 * 16)()
+        host_lib().rtbh_stats(self._h, out)
+        return {k: int(out[i]) for i, k in enumerate(STAT_NAMES)}
+
+    def struct_hash(self):
+        return int(host_lib().rtbh_struct_hash(self._h))
+
+    def tri_hash(self):
+        return int(host_lib().rtbh_tri_hash(self._h))
+
+    def triangles(self):
+        f = self.flat.contents
+        n = f.n_tris
+        if n == 0:
+            return np.zeros((0, 12), np.float32), np.zeros(0, np.int32)
+        tri = np.ctypeslib.as_array(f.tri, shape=(n, 12)).copy()
+        mat = np.ctypeslib.as_array(f.tri_material, shape=(n,)).copy()
+        return tri, (mat == mat[-1]).astype(np.int32)
+
+    def intersect_batch(self, rays):
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 6)
+        n = rays.shape[0]
+        hid, ht = np.zeros(n, np.int32), np.zeros(n, np.float32)
+        pos, nrm = np.zeros((n, 3), np.float32), np.zeros((n, 3), np.float32)
+        rc = host_lib().rtbh_intersect_batch(self._h, n, rays.ctypes.data, hid.ctypes.data, ht.ctypes.data,
+                                             pos.ctypes.data, nrm.ctypes.data)
+        if rc != 0:
+            raise RtbError("GeometrySet::intersectBatch failed: " + host_lib().rtbh_last_error().decode())
+        return hid, ht, pos, nrm
+
+    def intersect_one(self, ray):
+        ray = np.ascontiguousarray(ray, np.float32).reshape(6)
+        hid, ht = C.c_int32(-1), C.c_float(0)
+        pos, nrm = np.zeros(3, np.float32), np.zeros(3, np.float32)
+        host_lib().rtbh_intersect_one(self._h, ray.ctypes.data, C.byref(hid), C.byref(ht), pos.ctypes.data, nrm.ctypes.data)
+        return hid.value, ht.value, pos, nrm
+
+
+def script_run(preset, algorithm="linear", segments=150, width=400, height=300, samples=1, seed=0, device=0,
+               stl_path=None):
+    """The drop-in path: Script::Run(CudaRenderer::Render, ...) -- returns (image[y][x][3], info)."""
+    lib = host_lib()
+    rgb = np.zeros((width, height, 3), np.float32)
+    prep, exe, st = C.c_int(0), C.c_int(0), Stats()
+    rc = lib.rtbh_script_run(preset, _alg(algorithm), segments, width, height, samples, seed, device,
+                             (stl_path or stl_fixture()).encode(), rgb.ctypes.data, C.byref(prep), C.byref(exe),
+                             C.byref(st))
+    if rc != 0:
+        raise RtbError(f"Script::Run failed rc={rc}: {lib.rtbh_last_error().decode()}")
+    info = st.as_dict()
+    info.update(prepare_ms=prep.value, exec_ms=exe.value)
+    return np.ascontiguousarray(rgb.transpose(1, 0, 2)), info
+
+
+# ---- device side: context + uploaded scene over the C ABI --------------------------------------
+class Context:
+    def __init__(self, device=0):
+        self._lib = cuda_lib()
+        self._h = C.c_void_p()
+        rc = self._lib.rtb_init(device, C.byref(self._h))
+        if rc != 0:
+            raise RtbError(f"rtb_init({device}) failed rc={rc}: {self._lib.rtb_last_error(None).decode()}")
+        self.device = device
+
+    def close(self):
+        if self._h:
+            self._lib.rtb_shutdown(self._h)
+            self._h = C.c_void_p()
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise RtbError(f"{what} failed rc={rc}: {self._lib.rtb_last_error(self._h).decode()}")
+
+    def upload(self, flat):
+        return DeviceScene(self, flat)
+
+
+def shard_rows(frame):
+    return int(cuda_lib().rtb_shard_rows(C.byref(frame)))
+
+
+def make_frame(width, height, samples=1, seed=0, rank=0, world=1, row_block=8, layout=LAYOUT_ROWMAJOR, counters=0):
+    return Frame(width, height, samples, seed, rank, world, row_block, layout, counters)
+
+
+def shard_row_indices(height, rank, world, row_block=8):
+    """Global y of each local row of a shard (block b of row_block rows goes to rank b % world)."""
+    ys = []
+    b = rank
+    while b * row_block < height:
+        ys.extend(range(b * row_block, min((b + 1) * row_block, height)))
+        b += world
+    return np.asarray(ys, np.int64)
+
+
+class DeviceScene:
+    def __init__(self, ctx, flat):
+        self.ctx = ctx
+        self._h = C.c_void_p()
+        ctx._check(ctx._lib.rtb_scene_upload(ctx._h, flat, C.byref(self._h)), "rtb_scene_upload")
+
+    def close(self):
+        if self._h:
+            self.ctx._lib.rtb_scene_free(self.ctx._h, self._h)
+            self._h = C.c_void_p()
+
+    @property
+    def device_bytes(self):
+        return int(self.ctx._lib.rtb_scene_device_bytes(self._h))
+
+    def render(self, camera, setting, frame, out=None):
+        """rtb_render with HOST buffers; returns (rows x width x 3 float32 | reference-order array, stats)."""
+        rows = shard_rows(frame)
+        if out is None:
+            shape = (frame.width, frame.height, 3) if frame.layout == LAYOUT_REFERENCE else (rows, frame.width, 3)
+            out = np.zeros(shape, np.float32)
+        st = Stats()
+        self.ctx._check(self.ctx._lib.rtb_render(self.ctx._h, self._h, C.byref(camera), C.byref(setting), C.byref(frame),
+                                                 out.ctypes.data, C.byref(st)), "rtb_render")
+        return out, st.as_dict()
+
+    def render_device(self, camera, setting, frame, device_ptr, stream=0, want_stats=False):
+        """rtb_render_device into DEVICE memory (e.g. a torch tensor's data_ptr()) on `stream`."""
+        st = Stats()
+        self.ctx._check(self.ctx._lib.rtb_render_device(self.ctx._h, self._h, C.byref(camera), C.byref(setting),
+                                                        C.byref(frame), C.c_void_p(device_ptr), C.c_void_p(stream),
+                                                        C.byref(st) if want_stats else None), "rtb_render_device")
+        return st.as_dict() if want_stats else None
+
+    def trace_primary(self, camera, width, height, seq=True, seq_cap=0):
+        n = width * height
+        hid, ht = np.zeros(n, np.int32), np.zeros(n, np.float32)
+        slen = np.zeros(n, np.int32) if seq else None
+        shash = np.zeros(n, np.uint64) if seq else None
+        sbuf = np.zeros((n, seq_cap), np.int32) if seq_cap else None
+        p = lambda a: a.ctypes.data if a is not None else None
+        self.ctx._check(self.ctx._lib.rtb_trace_primary(self.ctx._h, self._h, C.byref(camera), width, height, p(hid), p(ht),
+                                                        p(slen), p(shash), p(sbuf), seq_cap), "rtb_trace_primary")
+        return {"hit_id": hid, "hit_t": ht, "seq_len": slen, "seq_hash": shash, "seq_buf": sbuf}
+
+    def intersect_rays(self, rays):
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 6)
+        n = rays.shape[0]
+        hid, ht = np.zeros(n, np.int32), np.zeros(n, np.float32)
+        pos, nrm = np.zeros((n, 3), np.float32), np.zeros((n, 3), np.float32)
+        self.ctx._check(self.ctx._lib.rtb_intersect_rays(self.ctx._h, self._h, n, rays.ctypes.data, hid.ctypes.data,
+                                                         ht.ctypes.data, pos.ctypes.data, nrm.ctypes.data),
+                        "rtb_intersect_rays")
+        return hid, ht, pos, nrm

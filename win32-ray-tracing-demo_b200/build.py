@@ -1,0 +1,66 @@
+"""In-tree build of the two shared libraries of the package (no JIT cache, no pip install):
+
+  librtb200.so       csrc/rtb_abi.cu  -- CUDA kernels + the C ABI of include/rtb.h   (nvcc, sm_100a)
+  librtb200_host.so  host/rt_*.cpp    -- reference-shaped C++ host API + builders   (g++)
+
+Parity flags: device code is compiled with -fmad=false (no FMA contraction) and the default
+IEEE division / square root; host code with -ffp-contract=off and no fast-math, so the host
+builders and the kernels evaluate the reference's float expressions as the x86-64 reference does.
+"""
+import os
+import shutil
+import subprocess
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+CUDA_LIB = os.path.join(PKG, "librtb200.so")
+HOST_LIB = os.path.join(PKG, "librtb200_host.so")
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-fmad=false", "-Xcompiler", "-fPIC", "-shared"]
+GXX_FLAGS = ["-O2", "-std=c++17", "-fopenmp", "-ffp-contract=off", "-fPIC", "-shared", "-Wall"]
+
+
+def _newer(target, sources):
+    if not os.path.exists(target):
+        return False
+    t = os.path.getmtime(target)
+    return all(os.path.getmtime(s) <= t for s in sources)
+
+
+def _nvcc():
+    return shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+
+
+def build_cuda(force=False, verbose=False):
+    src = [os.path.join(PKG, "csrc", f) for f in ("rtb_abi.cu", "rtb_kernels.cuh", "rtb_device.cuh")]
+    src.append(os.path.join(ROOT, "include", "rtb.h"))
+    if not force and _newer(CUDA_LIB, src):
+        return CUDA_LIB
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", CUDA_LIB, src[0]]
+    subprocess.check_call(cmd, cwd=PKG)
+    return CUDA_LIB
+
+
+def build_host(force=False):
+    src = [os.path.join(PKG, "host", f) for f in ("rt_scene.cpp", "rt_tunnel.cpp", "rt_render.cpp")]
+    deps = src + [os.path.join(PKG, "host", "rt.h"), os.path.join(ROOT, "include", "rtb.h")]
+    if not force and _newer(HOST_LIB, deps) and os.path.getmtime(HOST_LIB) >= os.path.getmtime(CUDA_LIB):
+        return HOST_LIB
+    # plain `g++` from PATH: the image's $CXX wrapper lacks libgomp
+    cmd = ["g++"] + GXX_FLAGS + ["-o", HOST_LIB] + src + ["-L" + PKG, "-lrtb200", "-Wl,-rpath,$ORIGIN"]
+    subprocess.check_call(cmd, cwd=PKG)
+    return HOST_LIB
+
+
+def build_all(force=False, verbose=False):
+    build_cuda(force, verbose)
+    build_host(force)
+    return CUDA_LIB, HOST_LIB
+
+
+if __name__ == "__main__":
+    import sys
+    build_all(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    print(CUDA_LIB)
+    print(HOST_LIB)

@@ -1,0 +1,450 @@
+// rtb_abi.cu -- implementation of the C ABI declared in include/rtb.h (librtb200.so).
+// Host glue only: argument validation, upload of the flattened scene, kernel launches on the
+// context stream, CUDA-event timing, and the host<->device copies of the host-buffer calls.
+// There is no CPU path in this library.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "rtb_kernels.cuh"
+
+using namespace rtb;
+
+struct rtb_ctx
+{
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    Counters *d_counters = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::string error;
+};
+
+struct rtb_scene
+{
+    DScene d;
+    std::vector<void *> allocs;
+    int64_t bytes = 0;
+    bool has_refractive = false;
+    bool has_tunnel = false;
+};
+
+static std::string g_error;
+static std::mutex g_error_mutex;
+
+static int fail(rtb_ctx *ctx, int code, const std::string &msg)
+{
+    {
+        std::lock_guard<std::mutex> lock(g_error_mutex);
+        g_error = msg;
+    }
+    if (ctx) ctx->error = msg;
+    return code;
+}
+
+#define CUDA_TRY(ctx, call)                                                                         \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess)                                                                      \
+            return fail(ctx, RTB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));     \
+    } while (0)
+
+extern "C" int rtb_abi_version(void) { return RTB_ABI_VERSION; }
+
+extern "C" const char *rtb_last_error(const rtb_ctx *ctx)
+{
+    if (ctx) return ctx->error.c_str();
+    std::lock_guard<std::mutex> lock(g_error_mutex);
+    static thread_local std::string copy;
+    copy = g_error;
+    return copy.c_str();
+}
+
+extern "C" int rtb_init(int device, rtb_ctx **out)
+{
+    if (!out) return fail(nullptr, RTB_ERR_INVALID, "rtb_init: null output pointer");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, RTB_ERR_NO_DEVICE, std::string("rtb_init: no CUDA device (") + cudaGetErrorString(e) +
+                                                    "); this library has no CPU path");
+    if (device < 0 || device >= count) return fail(nullptr, RTB_ERR_INVALID, "rtb_init: device index out of range");
+    cudaDeviceProp prop;
+    CUDA_TRY(nullptr, cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(nullptr, RTB_ERR_NO_DEVICE, "rtb_init: kernels are built for sm_100a only (device is sm_" +
+                                                    std::to_string(prop.major * 10 + prop.minor) + ")");
+    rtb_ctx *ctx = new rtb_ctx();
+    ctx->device = device;
+    CUDA_TRY(ctx, cudaSetDevice(device));
+    CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CUDA_TRY(ctx, cudaMalloc(&ctx->d_counters, sizeof(Counters)));
+    for (int i = 0; i < 4; i++) CUDA_TRY(ctx, cudaEventCreate(&ctx->ev[i]));
+    *out = ctx;
+    return RTB_OK;
+}
+
+extern "C" int rtb_shutdown(rtb_ctx *ctx)
+{
+    if (!ctx) return RTB_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < 4; i++)
+        if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->d_counters) cudaFree(ctx->d_counters);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return RTB_OK;
+}
+
+static int normRowBlock(const rtb_frame *f) { return f->row_block > 0 ? f->row_block : 8; }
+
+extern "C" int64_t rtb_shard_rows(const rtb_frame *f)
+{
+    if (!f || f->width <= 0 || f->height <= 0) return -1;
+    const int world = f->world > 0 ? f->world : 1, rank = f->rank, rb = normRowBlock(f);
+    if (rank < 0 || rank >= world || rb % 8 != 0) return -1;
+    int64_t rows = 0;
+    for (int64_t b = rank; b * rb < f->height; b += world)
+    {
+        const int64_t y0 = b * rb, y1 = y0 + rb < f->height ? y0 + rb : f->height;
+        rows += y1 - y0;
+    }
+    return rows;
+}
+
+// ---- scene upload -----------------------------------------------------------------------------
+template <class T>
+static int uploadArray(rtb_ctx *ctx, rtb_scene *s, const T *host, size_t n, const T **dev)
+{
+    *dev = nullptr;
+    if (n == 0) n = 1; // keep pointers valid
+    void *p = nullptr;
+    CUDA_TRY(ctx, cudaMalloc(&p, n * sizeof(T)));
+    s->allocs.push_back(p);
+    s->bytes += (int64_t)(n * sizeof(T));
+    if (host) CUDA_TRY(ctx, cudaMemcpyAsync(p, host, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    else CUDA_TRY(ctx, cudaMemsetAsync(p, 0, n * sizeof(T), ctx->stream));
+    *dev = (const T *)p;
+    return RTB_OK;
+}
+
+// a,b,c,normal (12 floats) -> {a.xyz, e1.x} {e1.yz, e2.xy} {e2.z, n.xyz}; e1 = a - b, e2 = a - c are
+// the float subtractions reference Triangle.cpp:73-79 performs per test, done once here.
+static void packTriangles(const float *src, size_t n, std::vector<float4> &dst)
+{
+    dst.resize(3 * n);
+    for (size_t i = 0; i < n; i++)
+    {
+        const float *t = src + 12 * i;
+        const float e1x = t[0] - t[3], e1y = t[1] - t[4], e1z = t[2] - t[5];
+        const float e2x = t[0] - t[6], e2y = t[1] - t[7], e2z = t[2] - t[8];
+        dst[3 * i + 0] = make_float4(t[0], t[1], t[2], e1x);
+        dst[3 * i + 1] = make_float4(e1y, e1z, e2x, e2y);
+        dst[3 * i + 2] = make_float4(e2z, t[9], t[10], t[11]);
+    }
+}
+
+static int kdDepth(const rtb_kdnode *nodes, int n, int node, int depth, int &maxDepth, int &visited)
+{
+    if (node < 0 || node >= n || depth > 64) return -1;
+    visited++;
+    if (depth > maxDepth) maxDepth = depth;
+    if ((nodes[node].b & 3u) == 3u) return 0;
+    const int right = (int)(nodes[node].b >> 2);
+    if (right <= node + 1) return -1;
+    if (kdDepth(nodes, n, node + 1, depth + 1, maxDepth, visited) != 0) return -1;
+    return kdDepth(nodes, n, right, depth + 1, maxDepth, visited);
+}
+
+extern "C" int rtb_scene_upload(rtb_ctx *ctx, const rtb_flat_scene *f, rtb_scene **out)
+{
+    if (!ctx || !f || !out) return fail(ctx, RTB_ERR_INVALID, "rtb_scene_upload: null argument");
+    *out = nullptr;
+    if (f->n_prims <= 0 || !f->prims) return fail(ctx, RTB_ERR_INVALID, "rtb_scene_upload: empty scene");
+    if (f->n_prims > RTB_MAX_INLINE_PRIMS)
+        return fail(ctx, RTB_ERR_UNSUPPORTED, "rtb_scene_upload: more than 16 top-level records (runs of loose triangles count once)");
+    if (f->n_materials <= 0 || f->n_materials > RTB_MAX_INLINE_MATS || !f->materials)
+        return fail(ctx, RTB_ERR_UNSUPPORTED, "rtb_scene_upload: between 1 and 16 materials are supported");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+
+    rtb_scene *s = new rtb_scene();
+    DScene &d = s->d;
+    memset(&d, 0, sizeof(d));
+    d.n_prims = f->n_prims; d.n_materials = f->n_materials; d.n_top = f->n_top; d.accel = f->accel;
+    int tunnels = 0;
+    for (int i = 0; i < f->n_prims; i++)
+    {
+        const rtb_prim &p = f->prims[i];
+        d.prims[i] = p;
+        bool ok = p.type >= RTB_PRIM_PLANE && p.type <= RTB_PRIM_TUNNEL;
+        if (p.type != RTB_PRIM_TUNNEL) ok = ok && p.material >= 0 && p.material < f->n_materials;
+        if (p.type == RTB_PRIM_TRIANGLES) ok = ok && p.first >= 0 && p.count >= 0 && p.first + p.count <= f->n_loose && f->loose_tri;
+        if (p.type == RTB_PRIM_TUNNEL) tunnels++;
+        if (!ok) { delete s; return fail(ctx, RTB_ERR_INVALID, "rtb_scene_upload: bad top-level record " + std::to_string(i)); }
+    }
+    if (tunnels > 1) { delete s; return fail(ctx, RTB_ERR_UNSUPPORTED, "rtb_scene_upload: one tunnel per scene"); }
+    s->has_tunnel = tunnels == 1;
+    for (int i = 0; i < f->n_materials; i++)
+    {
+        d.mats[i] = f->materials[i];
+        if (f->materials[i].refractiveness > 0) s->has_refractive = true;
+    }
+
+    int rc = RTB_OK;
+    std::vector<float4> packed;
+    auto bail = [&](int code) { rtb_scene_free(ctx, s); return code; };
+
+    packTriangles(f->loose_tri, f->loose_tri ? (size_t)f->n_loose : 0, packed);
+    if ((rc = uploadArray(ctx, s, packed.data(), packed.size(), &d.loose)) != RTB_OK) return bail(rc);
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)); // `packed` is reused below
+
+    if (s->has_tunnel)
+    {
+        if (f->n_tris < 0 || (f->n_tris > 0 && (!f->tri || !f->tri_material)))
+            return bail(fail(ctx, RTB_ERR_INVALID, "rtb_scene_upload: tunnel triangle streams missing"));
+        for (int i = 0; i < f->n_tris; i++)
+            if (f->tri_material[i] < 0 || f->tri_material[i] >= f->n_materials)
+                return bail(fail(ctx, RTB_ERR_INVALID, "rtb_scene_upload: triangle material out of range"));
+        packTriangles(f->tri, (size_t)f->n_tris, packed);
+        if ((rc = uploadArray(ctx, s, packed.data(), packed.size(), &d.tri)) != RTB_OK) return bail(rc);
+        if ((rc = uploadArray(ctx, s, f->tri_material, (size_t)f->n_tris, &d.tri_material)) != RTB_OK) return bail(rc);
+        d.n_tris = f->n_tris;
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+
+        if (f->accel == RTB_ACCEL_REGULAR_GRID || f->accel == RTB_ACCEL_FLAT_GRID)
+        {
+            const int64_t cells = (int64_t)f->grid_dims[0] * f->grid_dims[1] * f->grid_dims[2];
+            if (f->grid_dims[0] <= 0 || f->grid_dims[1] <= 0 || f->grid_dims[2] <= 0 || cells > 0x7fffffffLL ||
+                f->n_cellwords != (cells + 31) / 32 || !f->grid_words || !f->grid_cell_start ||
+                (f->n_cell_refs > 0 && !f->grid_cell_tris))
+                return bail(fail(ctx, RTB_ERR_INVALID, "rtb_scene_upload: inconsistent grid directory"));
+            for (int64_t i = 0; i < f->n_cell_refs; i++)
+                if (f->grid_cell_tris[i] >= (uint32_t)f->n_tris)
+                    return bail(fail(ctx, RTB_ERR_INVALID, "rtb_scene_upload: grid triangle reference out of range"));
+            d.g_origin = {f->grid_origin[0], f->grid_origin[1], f->grid_origin[2]};
+            d.g_cell = {f->grid_cell[0], f->grid_cell[1], f->grid_cell[2]};
+            d.nx = f->grid_dims[0]; d.ny = f->grid_dims[1]; d.nz = f->grid_dims[2];
+            // reference Tunnel.cpp:822-825: far = origin + Vector(cellSize * length)
+            d.g_extent = {d.g_cell.x * d.nx, d.g_cell.y * d.ny, d.g_cell.z * d.nz};
+            d.g_far = {d.g_origin.x + d.g_extent.x, d.g_origin.y + d.g_extent.y, d.g_origin.z + d.g_extent.z};
+            const uint2 *words = nullptr;
+            if ((rc = uploadArray(ctx, s, (const uint2 *)f->grid_words, (size_t)f->n_cellwords, &words)) != RTB_OK) return bail(rc);
+            d.g_words = words;
+            if ((rc = uploadArray(ctx, s, f->grid_cell_start, (size_t)f->n_cells_used + 1, &d.g_start)) != RTB_OK) return bail(rc);
+            if ((rc = uploadArray(ctx, s, f->grid_cell_tris, (size_t)f->n_cell_refs, &d.g_tris)) != RTB_OK) return bail(rc);
+        }
+        else if (f->accel == RTB_ACCEL_KD_MEDIAN || f->accel == RTB_ACCEL_KD_SAH)
+        {
+            if (f->n_kd_nodes <= 0 || !f->kd_nodes || (f->n_kd_refs > 0 && !f->kd_leaf_tris))
+                return bail(fail(ctx, RTB_ERR_INVALID, "rtb_scene_upload: k-d tree missing"));
+            int maxDepth = 0, visited = 0;
+            if (kdDepth(f->kd_nodes, f->n_kd_nodes, 0, 0, maxDepth, visited) != 0 || visited != f->n_kd_nodes)
+                return bail(fail(ctx, RTB_ERR_INVALID, "rtb_scene_upload: k-d nodes are not a pre-order tree"));
+            if (2 * maxDepth + 2 >= RTB_KD_STACK)
+                return bail(fail(ctx, RTB_ERR_UNSUPPORTED, "rtb_scene_upload: k-d tree deeper than the 50-entry traversal stack allows"));
+            for (int i = 0; i < f->n_kd_nodes; i++)
+                if ((f->kd_nodes[i].b & 3u) == 3u && (int64_t)f->kd_nodes[i].a + (f->kd_nodes[i].b >> 2) > f->n_kd_refs)
+                    return bail(fail(ctx, RTB_ERR_INVALID, "rtb_scene_upload: k-d leaf range out of bounds"));
+            for (int64_t i = 0; i < f->n_kd_refs; i++)
+                if (f->kd_leaf_tris[i] >= (uint32_t)f->n_tris)
+                    return bail(fail(ctx, RTB_ERR_INVALID, "rtb_scene_upload: k-d triangle reference out of range"));
+            d.kd_min = {f->kd_min[0], f->kd_min[1], f->kd_min[2]};
+            // reference Grid.cpp:13-17: Grid(near, far) keeps size = far - near
+            d.kd_size = {f->kd_max[0] - f->kd_min[0], f->kd_max[1] - f->kd_min[1], f->kd_max[2] - f->kd_min[2]};
+            const uint2 *nodes = nullptr;
+            if ((rc = uploadArray(ctx, s, (const uint2 *)f->kd_nodes, (size_t)f->n_kd_nodes, &nodes)) != RTB_OK) return bail(rc);
+            d.kd_nodes = nodes;
+            if ((rc = uploadArray(ctx, s, f->kd_leaf_tris, (size_t)f->n_kd_refs, &d.kd_tris)) != RTB_OK) return bail(rc);
+        }
+        else if (f->accel != RTB_ACCEL_LINEAR)
+            return bail(fail(ctx, RTB_ERR_UNSUPPORTED, "rtb_scene_upload: accelerator outside the hot path (convex variants are out of scope)"));
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = s;
+    return RTB_OK;
+}
+
+extern "C" int rtb_scene_free(rtb_ctx *ctx, rtb_scene *s)
+{
+    if (!s) return RTB_OK;
+    if (ctx) cudaSetDevice(ctx->device);
+    for (void *p : s->allocs) cudaFree(p);
+    delete s;
+    return RTB_OK;
+}
+
+extern "C" int64_t rtb_scene_device_bytes(const rtb_scene *s) { return s ? s->bytes : 0; }
+
+// ---- render -----------------------------------------------------------------------------------
+static int makeFrame(rtb_ctx *ctx, const rtb_scene *scene, const rtb_camera *cam, const rtb_render_setting *setting,
+                     const rtb_frame *frame, FrameParams &F)
+{
+    if (!ctx || !scene || !cam || !setting || !frame) return fail(ctx, RTB_ERR_INVALID, "render: null argument");
+    if (frame->width <= 0 || frame->height <= 0) return fail(ctx, RTB_ERR_INVALID, "render: bad image size");
+    const int64_t rows = rtb_shard_rows(frame);
+    if (rows < 0) return fail(ctx, RTB_ERR_INVALID, "render: bad shard (rank/world/row_block; row_block must be a multiple of 8)");
+    const int world = frame->world > 0 ? frame->world : 1;
+    if (frame->layout == RTB_LAYOUT_REFERENCE && world != 1)
+        return fail(ctx, RTB_ERR_INVALID, "render: the reference (column-major) layout needs the whole frame on one rank");
+    if (setting->enable_monte_carlo)
+    {
+        if (frame->samples <= 0) return fail(ctx, RTB_ERR_INVALID, "render: samples must be positive");
+        int need = setting->single_tracing_depth;
+        if (setting->max_depth < need) need = setting->max_depth;
+        if (need > RTB_MAX_DEPTH) need = RTB_MAX_DEPTH;
+        if (need > RTB_MC_STACK)
+            return fail(ctx, RTB_ERR_UNSUPPORTED, "render: min(single_tracing_depth, max_depth) above 32 pending split rays");
+    }
+    else if (scene->has_refractive && setting->max_depth > (RTB_TREE_STACK - 3) / 2)
+        return fail(ctx, RTB_ERR_UNSUPPORTED, "render: Whitted with refractive materials supports max_depth <= 30");
+    memset(&F, 0, sizeof(F));
+    F.cam = *cam;
+    F.setting = *setting;
+    F.width = frame->width; F.height = frame->height; F.samples = frame->samples;
+    F.rank = frame->rank; F.world = world; F.row_block = normRowBlock(frame); F.layout = frame->layout;
+    F.n_local_rows = (int)rows;
+    F.seed = frame->seed;
+    return RTB_OK;
+}
+
+template <class Probe>
+static void launchRender(const rtb_scene *scene, const FrameParams &F, float *out, Counters *counters, cudaStream_t stream)
+{
+    const dim3 grid((F.width + RTB_TILE_W - 1) / RTB_TILE_W, (F.n_local_rows + RTB_TILE_H - 1) / RTB_TILE_H);
+    if (F.setting.enable_monte_carlo) k_montecarlo<Probe><<<grid, RTB_CTA_THREADS, 0, stream>>>(scene->d, F, out, counters);
+    else if (scene->has_refractive) k_whitted_tree<Probe><<<grid, RTB_CTA_THREADS, 0, stream>>>(scene->d, F, out, counters);
+    else k_whitted_chain<Probe><<<grid, RTB_CTA_THREADS, 0, stream>>>(scene->d, F, out, counters);
+}
+
+static int renderCommon(rtb_ctx *ctx, const rtb_scene *scene, const FrameParams &F, const rtb_frame *frame, float *d_out,
+                        cudaStream_t stream, rtb_stats *stats, float *h_out)
+{
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t bytes = (size_t)F.n_local_rows * F.width * 3 * sizeof(float);
+    if (F.n_local_rows == 0)
+    {
+        if (stats) { memset(stats, 0, sizeof(*stats)); }
+        return RTB_OK;
+    }
+    if (stats || h_out) CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(Counters), stream));
+    if (stats) CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], stream));
+    if (frame->counters) launchRender<CountProbe>(scene, F, d_out, ctx->d_counters, stream);
+    else launchRender<NoProbe>(scene, F, d_out, ctx->d_counters, stream);
+    CUDA_TRY(ctx, cudaGetLastError());
+    if (stats) CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], stream));
+    if (h_out) CUDA_TRY(ctx, cudaMemcpyAsync(h_out, d_out, bytes, cudaMemcpyDeviceToHost, stream));
+    if (stats || h_out)
+    {
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev[3], stream));
+        Counters c;
+        if (stats) CUDA_TRY(ctx, cudaMemcpyAsync(&c, ctx->d_counters, sizeof(c), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(stream));
+        if (stats)
+        {
+            memset(stats, 0, sizeof(*stats));
+            stats->n_rays = (int64_t)c.rays; stats->n_tri_tests = (int64_t)c.tris; stats->n_steps = (int64_t)c.steps;
+            stats->n_local_rows = F.n_local_rows;
+            CUDA_TRY(ctx, cudaEventElapsedTime(&stats->kernel_ms, ctx->ev[1], ctx->ev[2]));
+            CUDA_TRY(ctx, cudaEventElapsedTime(&stats->total_ms, ctx->ev[0], ctx->ev[3]));
+            stats->n_launches = 1;
+        }
+    }
+    return RTB_OK;
+}
+
+extern "C" int rtb_render(rtb_ctx *ctx, const rtb_scene *scene, const rtb_camera *cam, const rtb_render_setting *setting,
+                          const rtb_frame *frame, float *rgb_out, rtb_stats *stats)
+{
+    FrameParams F;
+    int rc = makeFrame(ctx, scene, cam, setting, frame, F);
+    if (rc != RTB_OK) return rc;
+    if (!rgb_out) return fail(ctx, RTB_ERR_INVALID, "rtb_render: null output buffer");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t bytes = (size_t)F.n_local_rows * F.width * 3 * sizeof(float);
+    float *d_out = nullptr;
+    CUDA_TRY(ctx, cudaMalloc(&d_out, bytes ? bytes : 4));
+    rc = renderCommon(ctx, scene, F, frame, d_out, ctx->stream, stats, rgb_out);
+    cudaFree(d_out);
+    return rc;
+}
+
+extern "C" int rtb_render_device(rtb_ctx *ctx, const rtb_scene *scene, const rtb_camera *cam,
+                                 const rtb_render_setting *setting, const rtb_frame *frame, void *rgb_device,
+                                 void *stream, rtb_stats *stats)
+{
+    FrameParams F;
+    int rc = makeFrame(ctx, scene, cam, setting, frame, F);
+    if (rc != RTB_OK) return rc;
+    if (!rgb_device) return fail(ctx, RTB_ERR_INVALID, "rtb_render_device: null output buffer");
+    return renderCommon(ctx, scene, F, frame, (float *)rgb_device, stream ? (cudaStream_t)stream : ctx->stream, stats, nullptr);
+}
+
+// ---- parity hooks -----------------------------------------------------------------------------
+template <class T> struct DevBuf
+{
+    T *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t n) { return cudaMalloc(&p, (n ? n : 1) * sizeof(T)); }
+};
+
+extern "C" int rtb_trace_primary(rtb_ctx *ctx, const rtb_scene *scene, const rtb_camera *cam, int32_t width, int32_t height,
+                                 int32_t *hit_id, float *hit_t, int32_t *seq_len, uint64_t *seq_hash, int32_t *seq_buf,
+                                 int32_t seq_cap)
+{
+    if (!ctx || !scene || !cam || width <= 0 || height <= 0) return fail(ctx, RTB_ERR_INVALID, "rtb_trace_primary: bad argument");
+    if (seq_buf && seq_cap <= 0) return fail(ctx, RTB_ERR_INVALID, "rtb_trace_primary: seq_buf needs seq_cap > 0");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    FrameParams F;
+    memset(&F, 0, sizeof(F));
+    F.cam = *cam; F.width = width; F.height = height; F.rank = 0; F.world = 1; F.row_block = 8; F.n_local_rows = height;
+    const size_t n = (size_t)width * height;
+    DevBuf<int> d_id, d_len, d_buf;
+    DevBuf<float> d_t;
+    DevBuf<unsigned long long> d_hash;
+    if (hit_id) CUDA_TRY(ctx, d_id.alloc(n));
+    if (hit_t) CUDA_TRY(ctx, d_t.alloc(n));
+    if (seq_len) CUDA_TRY(ctx, d_len.alloc(n));
+    if (seq_hash) CUDA_TRY(ctx, d_hash.alloc(n));
+    if (seq_buf) CUDA_TRY(ctx, d_buf.alloc(n * seq_cap));
+    const dim3 grid((width + RTB_TILE_W - 1) / RTB_TILE_W, (height + RTB_TILE_H - 1) / RTB_TILE_H);
+    k_trace_primary<<<grid, RTB_CTA_THREADS, 0, ctx->stream>>>(scene->d, F, d_id.p, d_t.p, d_len.p, d_hash.p, d_buf.p, seq_cap);
+    CUDA_TRY(ctx, cudaGetLastError());
+    if (hit_id) CUDA_TRY(ctx, cudaMemcpyAsync(hit_id, d_id.p, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (hit_t) CUDA_TRY(ctx, cudaMemcpyAsync(hit_t, d_t.p, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (seq_len) CUDA_TRY(ctx, cudaMemcpyAsync(seq_len, d_len.p, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (seq_hash) CUDA_TRY(ctx, cudaMemcpyAsync(seq_hash, d_hash.p, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (seq_buf) CUDA_TRY(ctx, cudaMemcpyAsync(seq_buf, d_buf.p, n * seq_cap * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return RTB_OK;
+}
+
+extern "C" int rtb_intersect_rays(rtb_ctx *ctx, const rtb_scene *scene, int64_t n, const float *rays, int32_t *hit_id,
+                                  float *hit_t, float *position, float *normal)
+{
+    if (!ctx || !scene || n < 0 || (n > 0 && !rays)) return fail(ctx, RTB_ERR_INVALID, "rtb_intersect_rays: bad argument");
+    if (n == 0) return RTB_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    DevBuf<float> d_rays, d_t, d_pos, d_nrm;
+    DevBuf<int> d_id;
+    CUDA_TRY(ctx, d_rays.alloc((size_t)n * 6));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_rays.p, rays, (size_t)n * 6 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    if (hit_id) CUDA_TRY(ctx, d_id.alloc((size_t)n));
+    if (hit_t) CUDA_TRY(ctx, d_t.alloc((size_t)n));
+    if (position) CUDA_TRY(ctx, d_pos.alloc((size_t)n * 3));
+    if (normal) CUDA_TRY(ctx, d_nrm.alloc((size_t)n * 3));
+    const unsigned int blocks = (unsigned int)((n + RTB_CTA_THREADS - 1) / RTB_CTA_THREADS);
+    k_intersect_rays<<<blocks, RTB_CTA_THREADS, 0, ctx->stream>>>(scene->d, (long long)n, d_rays.p, d_id.p, d_t.p, d_pos.p, d_nrm.p);
+    CUDA_TRY(ctx, cudaGetLastError());
+    if (hit_id) CUDA_TRY(ctx, cudaMemcpyAsync(hit_id, d_id.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (hit_t) CUDA_TRY(ctx, cudaMemcpyAsync(hit_t, d_t.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (position) CUDA_TRY(ctx, cudaMemcpyAsync(position, d_pos.p, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (normal) CUDA_TRY(ctx, cudaMemcpyAsync(normal, d_nrm.p, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return RTB_OK;
+}

@@ -1,0 +1,597 @@
+// rtb_device.cuh -- device-side scene image and intersection routines (sm_100a).
+//
+// Arithmetic contract: every decision-making expression is IEEE float32 evaluated in the
+// reference's operation order.  This translation unit is compiled with -fmad=false (no FMA
+// contraction; the x86-64 reference build has none), default -prec-div/-prec-sqrt (correctly
+// rounded / and sqrt) and -ftz=false.  Comparisons the reference performs in double against
+// double literals are folded into the equivalent float thresholds:
+//     fabs(x) <  1e-10 (double)  <=>  fabsf(x) <  1e-10f   (float(1e-10) is the least float >= 1e-10)
+//     fabs(x) >  1e-10 (double)  <=>  fabsf(x) >= 1e-10f
+//     fabs(x) >  0.1   (double)  <=>  fabsf(x) >= 0.1f     (float(0.1) is the least float >= 0.1)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <float.h>
+#include "../../include/rtb.h"
+
+#define RTB_MAX_INLINE_PRIMS 16
+#define RTB_MAX_INLINE_MATS 16
+#define RTB_KD_STACK 50 // reference Tunnel.cpp:1176
+
+namespace rtb {
+
+// ---------------------------------------------------------------------------------------------
+// float3 algebra in the reference's operation order (Vector.cpp:48-86)
+// ---------------------------------------------------------------------------------------------
+struct V3 { float x, y, z; };
+__device__ __forceinline__ V3 v3(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ V3 operator+(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ V3 operator-(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ V3 operator*(V3 a, float s) { return v3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ V3 mul(V3 a, V3 b) { return v3(a.x * b.x, a.y * b.y, a.z * b.z); }
+__device__ __forceinline__ float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ V3 cross(V3 a, V3 b) { return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+__device__ __forceinline__ V3 normalize(V3 a) { return a * (1 / sqrtf(a.x * a.x + a.y * a.y + a.z * a.z)); }
+__device__ __forceinline__ float comp(const V3 &a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
+__device__ __forceinline__ V3 ld3(const float *p) { return v3(p[0], p[1], p[2]); }
+
+struct Ray { V3 o, d; };
+__device__ __forceinline__ V3 at(const Ray &r, float t) { return r.o + r.d * t; } // Ray.h:24-27
+
+// x86 cvttss2si semantics of the reference's (int) casts: out-of-range / NaN -> INT_MIN
+__device__ __forceinline__ int f2i(float f)
+{
+    return (f >= -2147483648.0f && f < 2147483648.0f) ? (int)f : (int)0x80000000;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Device scene image.  Passed to kernels by value as a __grid_constant__ parameter: the handful
+// of analytic primitives and materials live in the constant bank (warp-uniform reads), the
+// triangle / accelerator streams are pointers into HBM (L2-resident after first touch).
+// ---------------------------------------------------------------------------------------------
+struct DScene
+{
+    int n_prims, n_materials, n_top, accel;
+    rtb_prim prims[RTB_MAX_INLINE_PRIMS];
+    rtb_material mats[RTB_MAX_INLINE_MATS];
+    // triangles: 3 x float4 per triangle = {a.xyz, e1.x} {e1.yz, e2.xy} {e2.z, n.xyz},
+    // e1 = a - b, e2 = a - c precomputed with the same float subtraction Triangle.cpp:73-79 does
+    const float4 *loose;
+    const float4 *tri;
+    const int *tri_material;
+    int n_tris;
+    // grid
+    V3 g_origin, g_cell, g_far; // g_far = origin + cell * dims (Tunnel.cpp:822-825)
+    V3 g_extent;                // cell * dims
+    int nx, ny, nz;
+    const uint2 *g_words;
+    const uint32_t *g_start;
+    const uint32_t *g_tris;
+    // k-d
+    V3 kd_min, kd_size; // Grid(near, far): pos = near, size = far - near (Grid.cpp:13-17)
+    const uint2 *kd_nodes;
+    const uint32_t *kd_tris;
+};
+
+struct Counters { unsigned long long rays, tris, steps; };
+
+// Probes: compile-time observation policy.  NoProbe costs nothing.
+struct NoProbe
+{
+    __device__ __forceinline__ void step(int) {}
+    __device__ __forceinline__ void tri() {}
+};
+struct CountProbe
+{
+    unsigned int tris = 0, steps = 0;
+    __device__ __forceinline__ void step(int) { steps++; }
+    __device__ __forceinline__ void tri() { tris++; }
+};
+struct SeqProbe
+{ // records the traversal sequence of one primary ray
+    int len = 0;
+    unsigned long long hash = 0xcbf29ce484222325ull;
+    int *buf = nullptr;
+    int cap = 0;
+    __device__ __forceinline__ void step(int id)
+    {
+        hash = (hash ^ (unsigned int)id) * 0x100000001b3ull;
+        if (len < cap) buf[len] = id;
+        len++;
+    }
+    __device__ __forceinline__ void tri() {}
+};
+
+// ---------------------------------------------------------------------------------------------
+// Triangle -- reference Triangle.cpp:25-121 (Cramer's rule, four 3x3 determinants)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float det3(float a11, float a12, float a13, float a21, float a22, float a23,
+                                      float a31, float a32, float a33)
+{
+    return a11 * a22 * a33 + a12 * a23 * a31 + a13 * a21 * a32 - a13 * a22 * a31 - a11 * a23 * a32 - a12 * a21 * a33;
+}
+
+struct TriData { float4 q0, q1, q2; };
+__device__ __forceinline__ TriData loadTri(const float4 *base, unsigned int idx)
+{
+    const float4 *p = base + 3ull * idx;
+    TriData t;
+    t.q0 = __ldg(p);
+    t.q1 = __ldg(p + 1);
+    t.q2 = __ldg(p + 2);
+    return t;
+}
+__device__ __forceinline__ V3 triNormal(const TriData &t) { return v3(t.q2.y, t.q2.z, t.q2.w); }
+
+__device__ __forceinline__ bool triIntersect(const TriData &T, const Ray &ray, float &tOut)
+{
+    const float m11 = T.q0.w, m21 = T.q1.x, m31 = T.q1.y; // a - b
+    const float m12 = T.q1.z, m22 = T.q1.w, m32 = T.q2.x; // a - c
+    const float m13 = ray.d.x, m23 = ray.d.y, m33 = ray.d.z;
+    const float b1 = T.q0.x - ray.o.x, b2 = T.q0.y - ray.o.y, b3 = T.q0.z - ray.o.z;
+    const float detM = det3(m11, m12, m13, m21, m22, m23, m31, m32, m33);
+    if (fabsf(detM) < 1e-10f) return false;
+    const float t = det3(m11, m12, b1, m21, m22, b2, m31, m32, b3) / detM;
+    if (t < 0.0005f) return false;
+    const float beta = det3(b1, m12, m13, b2, m22, m23, b3, m32, m33) / detM;
+    if (beta < -0.0001f || beta > 1.0001f) return false;
+    const float gamma = det3(m11, b1, m13, m21, b2, m23, m31, b3, m33) / detM;
+    if (gamma < -0.0001f || gamma > 1.0001f || 1 - beta - gamma < -0.0001f || 1 - beta - gamma > 1.0001f) return false;
+    tOut = t;
+    return true;
+}
+
+// nearest hit of a list of triangle references; first in list wins ties (strict <)
+template <bool WINDOW, class Probe>
+__device__ __forceinline__ bool nearestInList(const DScene &S, const uint32_t *refs, uint32_t first, uint32_t last,
+                                              const Ray &ray, float lo, float hi, int &triOut, float &tOut,
+                                              V3 &nOut, Probe &pr)
+{
+    float minDistance = FLT_MAX;
+    bool found = false;
+    for (uint32_t i = first; i < last; i++)
+    {
+        const uint32_t idx = __ldg(refs + i);
+        const TriData T = loadTri(S.tri, idx);
+        pr.tri();
+        float t;
+        if (!triIntersect(T, ray, t)) continue;
+        if (WINDOW && !(t >= lo && t <= hi)) continue;
+        if (t < minDistance)
+        {
+            minDistance = t;
+            triOut = (int)idx;
+            nOut = triNormal(T);
+            found = true;
+        }
+    }
+    tOut = minDistance;
+    return found;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Box entry / exit -- reference Grid.cpp:30-116
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void updateEntryExit(float &entry, float &exit, float v)
+{
+    if (entry == FLT_MAX && exit == FLT_MAX) entry = v;
+    else if (exit == FLT_MAX)
+    {
+        if (v > entry) exit = v;
+        else { exit = entry; entry = v; }
+    }
+    else
+    {
+        if (v < entry) { exit = entry; entry = v; }
+        else if (v < exit) exit = v;
+    }
+}
+
+__device__ __forceinline__ void boxFace(float planePos, float o, float d, const Ray &ray, int a1, int a2,
+                                        const V3 &nearP, const V3 &farP, float &entry, float &exit)
+{
+    const float distance = (planePos - o) / d;
+    const V3 p = at(ray, distance);
+    const float u = comp(p, a1), v = comp(p, a2);
+    if (u >= comp(nearP, a1) && u <= comp(farP, a1) && v >= comp(nearP, a2) && v <= comp(farP, a2))
+        updateEntryExit(entry, exit, distance);
+}
+
+__device__ __forceinline__ bool boxIntersect(V3 nearP, V3 size, const Ray &ray, float &entry, float &exit)
+{
+    const V3 farP = nearP + size;
+    entry = FLT_MAX;
+    exit = FLT_MAX;
+    if (fabsf(ray.d.x) >= 1e-10f)
+    {
+        boxFace(nearP.x, ray.o.x, ray.d.x, ray, 1, 2, nearP, farP, entry, exit);
+        boxFace(farP.x, ray.o.x, ray.d.x, ray, 1, 2, nearP, farP, entry, exit);
+    }
+    if (fabsf(ray.d.y) >= 1e-10f)
+    {
+        boxFace(nearP.y, ray.o.y, ray.d.y, ray, 2, 0, nearP, farP, entry, exit);
+        boxFace(farP.y, ray.o.y, ray.d.y, ray, 2, 0, nearP, farP, entry, exit);
+    }
+    if (fabsf(ray.d.z) >= 1e-10f)
+    {
+        boxFace(nearP.z, ray.o.z, ray.d.z, ray, 0, 1, nearP, farP, entry, exit);
+        boxFace(farP.z, ray.o.z, ray.d.z, ray, 0, 1, nearP, farP, entry, exit);
+    }
+    return entry != FLT_MAX;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Grid 3D-DDA -- reference Tunnel.cpp:806-970
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void indexInGrid(const DScene &S, V3 p, int &i, int &j, int &k)
+{
+    i = f2i((p.x - S.g_origin.x) / S.g_cell.x);
+    j = f2i((p.y - S.g_origin.y) / S.g_cell.y);
+    k = f2i((p.z - S.g_origin.z) / S.g_cell.z);
+    if (i < 0) i = 0;
+    if (j < 0) j = 0;
+    if (k < 0) k = 0;
+    if (i > S.nx - 1) i = S.nx - 1;
+    if (j > S.ny - 1) j = S.ny - 1;
+    if (k > S.nz - 1) k = S.nz - 1;
+}
+
+template <class Probe>
+__device__ bool gridIntersect(const DScene &S, const Ray &ray, int &triOut, float &tOut, V3 &nOut, Probe &pr)
+{
+    int ci, cj, ck;
+    float cd;
+    V3 cp;
+    if (ray.o.x < S.g_origin.x || ray.o.x > S.g_far.x || ray.o.y < S.g_origin.y || ray.o.y > S.g_far.y ||
+        ray.o.z < S.g_origin.z || ray.o.z > S.g_far.z)
+    {
+        float entry, exit;
+        if (!boxIntersect(S.g_origin, S.g_extent, ray, entry, exit)) return false;
+        cd = entry;
+        cp = at(ray, entry);
+        indexInGrid(S, cp, ci, cj, ck);
+    }
+    else
+    {
+        cp = ray.o;
+        cd = 0;
+        indexInGrid(S, ray.o, ci, cj, ck);
+    }
+    const bool px = ray.d.x > 0, py = ray.d.y > 0, pz = ray.d.z > 0;
+    while (true)
+    {
+        const int cell = (ci * S.ny + cj) * S.nz + ck;
+        pr.step(cell);
+        const uint2 w = __ldg(S.g_words + ((unsigned int)cell >> 5));
+        const unsigned int bit = 1u << (cell & 31);
+        if (w.x & bit)
+        {
+            const unsigned int r = w.y + __popc(w.x & (bit - 1));
+            const uint32_t first = __ldg(S.g_start + r), last = __ldg(S.g_start + r + 1);
+            if (nearestInList<false>(S, S.g_tris, first, last, ray, 0.f, 0.f, triOut, tOut, nOut, pr)) return true;
+        }
+        // distance to the exit plane of the current cell on each axis; cell corners are recomputed
+        // from the integer indices every step (Tunnel.cpp:885-938); IEEE inf/NaN semantics kept
+        float dx, dy, dz;
+        if (px) dx = ((S.g_origin.x + (ci + 1) * S.g_cell.x) - cp.x) / ray.d.x;
+        else dx = (cp.x - (S.g_origin.x + ci * S.g_cell.x)) / -ray.d.x;
+        if (py) dy = ((S.g_origin.y + (cj + 1) * S.g_cell.y) - cp.y) / ray.d.y;
+        else dy = (cp.y - (S.g_origin.y + cj * S.g_cell.y)) / -ray.d.y;
+        if (pz) dz = ((S.g_origin.z + (ck + 1) * S.g_cell.z) - cp.z) / ray.d.z;
+        else dz = (cp.z - (S.g_origin.z + ck * S.g_cell.z)) / -ray.d.z;
+        if (dx < dy && dx < dz) { ci += px ? 1 : -1; cd += dx; }
+        else if (dy < dz) { cj += py ? 1 : -1; cd += dy; }
+        else { ck += pz ? 1 : -1; cd += dz; }
+        cp = at(ray, cd);
+        if (ci < 0 || ci > S.nx - 1 || cj < 0 || cj > S.ny - 1 || ck < 0 || ck > S.nz - 1) break;
+    }
+    return false;
+}
+
+// ---------------------------------------------------------------------------------------------
+// k-d tree -- reference Tunnel.cpp:1163-1297 (Havran TA_rec_B).
+// The reference keeps {node, t, pb, prev} per stack element.  pb is a pure function of
+// (t, axis, split): pb[axis] = split, pb[other] = o + t*d (lines 1260-1262), so an element is
+// stored as 16 bytes {node, t, split, axis | prev<<2} and pb is re-derived bit-exactly when the
+// element becomes the exit point again.  The current entry/exit elements live in registers.
+// axis code 3 = "all three components are o + t*d" (the initial exit point, line 1196).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ V3 kdPoint(const Ray &ray, float t, float split, int axis)
+{
+    V3 p = v3(ray.o.x + t * ray.d.x, ray.o.y + t * ray.d.y, ray.o.z + t * ray.d.z);
+    if (axis == 0) p.x = split;
+    else if (axis == 1) p.y = split;
+    else if (axis == 2) p.z = split;
+    return p;
+}
+
+template <class Probe>
+__device__ bool kdIntersect(const DScene &S, const Ray &ray, int &triOut, float &tOut, V3 &nOut, Probe &pr)
+{
+    float a, b;
+    if (!boxIntersect(S.kd_min, S.kd_size, ray, a, b)) return false;
+    int4 stack[RTB_KD_STACK];
+    // entry point (element 0)
+    float enT = a;
+    V3 enP = (a >= 0) ? (ray.o + ray.d * a) : ray.o;
+    int enPt = 0;
+    // exit point (element 1), node -1 = termination flag
+    int exPt = 1;
+    float exT = b;
+    V3 exP = ray.o + ray.d * b;
+    int exNode = -1, exPrev = 0;
+    stack[1] = make_int4(-1, __float_as_int(b), 0, 3);
+    int cur = 0;
+    while (cur != -1)
+    {
+        uint2 nd = __ldg(S.kd_nodes + cur);
+        while ((nd.y & 3u) != 3u)
+        {
+            pr.step(cur);
+            const float splitVal = __uint_as_float(nd.x);
+            const int axis = (int)(nd.y & 3u);
+            const int right = (int)(nd.y >> 2), left = cur + 1;
+            const float en = comp(enP, axis), ex = comp(exP, axis);
+            int farChild;
+            if (en <= splitVal)
+            {
+                if (ex <= splitVal) { cur = left; nd = __ldg(S.kd_nodes + cur); continue; }
+                if (ex == splitVal) { cur = right; nd = __ldg(S.kd_nodes + cur); continue; } // unreachable, kept for fidelity (line 1223)
+                farChild = right; cur = left;
+            }
+            else
+            {
+                if (splitVal < ex) { cur = right; nd = __ldg(S.kd_nodes + cur); continue; }
+                farChild = left; cur = right;
+            }
+            const float t = (splitVal - comp(ray.o, axis)) / comp(ray.d, axis);
+            const int tmp = exPt++;
+            if (exPt == enPt) exPt += 1;
+            exPrev = tmp; exT = t; exNode = farChild;
+            exP = kdPoint(ray, t, splitVal, axis);
+            stack[exPt] = make_int4(farChild, __float_as_int(t), __float_as_int(splitVal), axis | (tmp << 2));
+            nd = __ldg(S.kd_nodes + cur);
+        }
+        pr.step(cur);
+        const uint32_t first = nd.x, count = nd.y >> 2;
+        if (count && nearestInList<true>(S, S.kd_tris, first, first + count, ray, enT - 0.001f, exT + 0.001f,
+                                         triOut, tOut, nOut, pr))
+            return true;
+        // pop: the signed distance intervals are adjacent
+        enPt = exPt; enT = exT; enP = exP;
+        cur = exNode;
+        if (cur == -1) break;
+        exPt = exPrev;
+        const int4 e = stack[exPt];
+        exNode = e.x; exT = __int_as_float(e.y); exPrev = e.w >> 2;
+        exP = kdPoint(ray, exT, __int_as_float(e.z), e.w & 3);
+    }
+    return false;
+}
+
+template <class Probe>
+__device__ bool linearIntersect(const DScene &S, const Ray &ray, int &triOut, float &tOut, V3 &nOut, Probe &pr)
+{ // reference Tunnel.cpp:786-804
+    float minDistance = FLT_MAX;
+    bool found = false;
+    for (int i = 0; i < S.n_tris; i++)
+    {
+        const TriData T = loadTri(S.tri, i);
+        pr.tri();
+        float t;
+        if (triIntersect(T, ray, t) && t < minDistance) { minDistance = t; triOut = i; nOut = triNormal(T); found = true; }
+    }
+    tOut = minDistance;
+    return found;
+}
+
+// ---------------------------------------------------------------------------------------------
+// GeometrySet::intersect -- reference GeometrySet.cpp:95-110 (+ Plane.cpp:9-34, Sphere.cpp:10-37)
+// ---------------------------------------------------------------------------------------------
+struct Hit { int id; int mat; float t; V3 pos, n; };
+
+template <class Probe>
+__device__ bool sceneIntersect(const DScene &S, const Ray &ray, Hit &best, Probe &pr)
+{
+    float minDistance = FLT_MAX;
+    best.id = -1;
+    for (int i = 0; i < S.n_prims; i++)
+    {
+        const rtb_prim &P = S.prims[i];
+        if (P.type == RTB_PRIM_PLANE)
+        {
+            const V3 normal = v3(P.v[0], P.v[1], P.v[2]);
+            const V3 op = v3(P.v[3], P.v[4], P.v[5]) - ray.o;
+            const bool back = dot(normal, op) > 0;
+            const V3 n = back ? normal : normal * -1;
+            if (dot(n, ray.d) > 0)
+            {
+                const float distance = dot(op, n) / dot(ray.d, n);
+                if (distance >= 0.0005f && distance < minDistance)
+                {
+                    minDistance = distance;
+                    best.id = P.base_id; best.mat = P.material; best.n = normal;
+                }
+            }
+        }
+        else if (P.type == RTB_PRIM_SPHERE)
+        {
+            const V3 center = v3(P.v[0], P.v[1], P.v[2]);
+            const float radius = P.v[3];
+            const V3 co = ray.o - center;
+            const float b = dot(ray.d, co);
+            float delta = b * b - (dot(co, co) - radius * radius);
+            if (delta >= 0)
+            {
+                delta = sqrtf(delta);
+                if (-b + delta >= 0.0005f)
+                {
+                    const float distance = (-b - delta >= 0.0005f) ? -b - delta : -b + delta;
+                    if (distance < minDistance)
+                    {
+                        minDistance = distance;
+                        best.id = P.base_id; best.mat = P.material;
+                        best.n = normalize(at(ray, distance) - center);
+                    }
+                }
+            }
+        }
+        else if (P.type == RTB_PRIM_TRIANGLES)
+        {
+            for (int k = 0; k < P.count; k++)
+            {
+                const TriData T = loadTri(S.loose, P.first + k);
+                pr.tri();
+                float t;
+                if (triIntersect(T, ray, t) && t < minDistance)
+                {
+                    minDistance = t;
+                    best.id = P.base_id + k; best.mat = P.material; best.n = triNormal(T);
+                }
+            }
+        }
+        else
+        {
+            int tri = -1;
+            float t;
+            V3 n;
+            bool ok;
+            if (S.accel == RTB_ACCEL_REGULAR_GRID || S.accel == RTB_ACCEL_FLAT_GRID) ok = gridIntersect(S, ray, tri, t, n, pr);
+            else if (S.accel == RTB_ACCEL_KD_MEDIAN || S.accel == RTB_ACCEL_KD_SAH) ok = kdIntersect(S, ray, tri, t, n, pr);
+            else ok = linearIntersect(S, ray, tri, t, n, pr);
+            if (ok && t < minDistance)
+            {
+                minDistance = t;
+                best.id = S.n_top + tri; best.mat = __ldg(S.tri_material + tri); best.n = n;
+            }
+        }
+    }
+    if (best.id < 0) return false;
+    best.t = minDistance;
+    best.pos = at(ray, minDistance);
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Camera -- reference Camera.cpp:20-26
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ Ray generateRay(const rtb_camera &c, float x, float y)
+{
+    const V3 right = ld3(c.right), up = ld3(c.up), front = ld3(c.front), eye = ld3(c.eye);
+    const V3 r = right * ((x - c.xcenter) * c.fov_scale);
+    const V3 u = up * ((y - 0.5f) * c.fov_scale);
+    const V3 dir = normalize(front + r + u);
+    Ray ray;
+    ray.o = eye + dir * c.forward;
+    ray.d = dir;
+    return ray;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Materials -- reference *Material.cpp
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float checkerParity(const rtb_material &m, V3 pos)
+{ // CheckerMaterial.cpp:13-21; d is a non-negative integer-valued float, so fmod(d, 2) is exact
+    float d;
+    if (m.dir == RTB_DIR_XOZ) d = fabsf(floorf(pos.x * m.scale) + floorf(pos.z * m.scale));
+    else if (m.dir == RTB_DIR_YOZ) d = fabsf(floorf(pos.y * m.scale) + floorf(pos.z * m.scale));
+    else d = fabsf(floorf(pos.x * m.scale) + floorf(pos.y * m.scale));
+    return fmodf(d, 2.0f);
+}
+
+__device__ __forceinline__ V3 matLocal(const rtb_material &m, const Ray &ray, V3 pos, V3 normal)
+{
+    if (m.kind == RTB_MAT_SOLID) return ld3(m.a);
+    if (m.kind == RTB_MAT_CHECKER) return checkerParity(m, pos) < 1 ? v3(0.15f, 0.15f, 0.15f) : v3(1, 1, 1);
+    if (m.kind == RTB_MAT_RADIANCE_CHECKER) return v3(0.15f, 0.15f, 0.15f);
+    // PhongMaterial.cpp:13-29: stored (unflipped) normal, white light from normalize(-1,1,1)
+    const V3 lightDir = normalize(v3(-1, 1, 1));
+    float NdotL = dot(normal, lightDir);
+    NdotL = (NdotL < 0.0f) ? 0.0f : NdotL;
+    const V3 H = normalize(lightDir - ray.d);
+    float NdotH = dot(normal, H);
+    NdotH = (NdotH < 0.0f) ? 0.0f : NdotH;
+    const V3 diffuseTerm = ld3(m.a) * NdotL;
+    const V3 specularTerm = ld3(m.b) * powf(NdotH, m.p);
+    return mul(v3(1, 1, 1), diffuseTerm + specularTerm);
+}
+
+__device__ __forceinline__ V3 matEmission(const rtb_material &m, V3 pos)
+{
+    if (m.kind == RTB_MAT_SOLID) return ld3(m.b);
+    if (m.kind == RTB_MAT_RADIANCE_CHECKER) return checkerParity(m, pos) < 1 ? v3(m.p, m.p, m.p) : v3(0, 0, 0);
+    return v3(0, 0, 0);
+}
+
+// Refraction set-up shared by trace() and radiance() -- reference MainWindow.cpp:111-133 == 212-231
+struct Fresnel { V3 refl, tdir; bool tir; float Re, Tr, P, RP, TP; };
+__device__ __forceinline__ Fresnel refraction(const Ray &r, V3 n, V3 nl, float nt)
+{
+    Fresnel f;
+    f.refl = r.d - n * 2 * dot(n, r.d);
+    const bool into = dot(n, nl) > 0;
+    const float nc = 1;
+    const float nnt = into ? nc / nt : nt / nc;
+    const float ddn = dot(r.d, nl);
+    const float cos2t = 1 - nnt * nnt * (1 - ddn * ddn);
+    f.tir = cos2t < 0;
+    f.tdir = v3(0, 0, 0);
+    f.Re = f.Tr = f.P = f.RP = f.TP = 0;
+    if (f.tir) return f;
+    f.tdir = normalize(r.d * nnt - n * ((into ? 1 : -1) * (ddn * nnt + sqrtf(cos2t))));
+    const float a = nt - nc, b = nt + nc;
+    const float R0 = a * a / (b * b);
+    const float c = 1 - (into ? -ddn : dot(f.tdir, n));
+    f.Re = R0 + (1 - R0) * c * c * c * c * c;
+    f.Tr = 1 - f.Re;
+    f.P = 0.25f + 0.5f * f.Re;
+    f.RP = f.Re / f.P;
+    f.TP = f.Tr / (1 - f.P);
+    return f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Counter-based RNG: Philox4x32-10, key = (pixel, sample), counter = (block, seed_lo, seed_hi, 0).
+// Replaces the reference's per-row erand48 stream (erand48.h:53-81, MainWindow.cpp:273), which
+// is inherently sequential; statistical parity only (oracle/rt_oracle.cpp mirrors this stream
+// in its ORACLE_RNG_COUNTER mode so paths can also be compared one to one).
+// ---------------------------------------------------------------------------------------------
+struct Philox
+{
+    uint32_t key0, key1, c0, c1, c2;
+    uint32_t buf[4];
+    int used;
+    __device__ __forceinline__ void seed(uint64_t s, uint32_t pixel, uint32_t sample)
+    {
+        key0 = pixel; key1 = sample;
+        c0 = 0; c1 = (uint32_t)s; c2 = (uint32_t)(s >> 32);
+        used = 4;
+    }
+    __device__ __forceinline__ void refill()
+    {
+        uint32_t x0 = c0, x1 = c1, x2 = c2, x3 = 0, k0 = key0, k1 = key1;
+#pragma unroll
+        for (int r = 0; r < 10; r++)
+        {
+            const uint32_t hi0 = __umulhi(0xD2511F53u, x0), lo0 = 0xD2511F53u * x0;
+            const uint32_t hi1 = __umulhi(0xCD9E8D57u, x2), lo1 = 0xCD9E8D57u * x2;
+            const uint32_t n0 = hi1 ^ x1 ^ k0, n2 = hi0 ^ x3 ^ k1;
+            x0 = n0; x1 = lo1; x2 = n2; x3 = lo0;
+            k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+        }
+        buf[0] = x0; buf[1] = x1; buf[2] = x2; buf[3] = x3;
+        c0++;
+        used = 0;
+    }
+    __device__ __forceinline__ float next()
+    {
+        if (used == 4) refill();
+        uint32_t v;
+        // select without dynamic register-array indexing
+        v = used == 0 ? buf[0] : (used == 1 ? buf[1] : (used == 2 ? buf[2] : buf[3]));
+        used++;
+        return (float)(v >> 8) * (1.0f / 16777216.0f);
+    }
+};
+
+} // namespace rtb

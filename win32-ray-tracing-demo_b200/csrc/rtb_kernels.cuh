@@ -1,0 +1,366 @@
+// rtb_kernels.cuh -- the render / trace kernels (sm_100a).  One thread owns one pixel; a warp
+// owns an 8x4 pixel tile, a 256-thread CTA a 32x8 tile, so primary rays of a warp are coherent
+// and a CTA row band coincides with the 8-row granularity of the tile-row sharding.
+#pragma once
+#include "rtb_device.cuh"
+
+namespace rtb {
+
+struct FrameParams
+{
+    rtb_camera cam;
+    rtb_render_setting setting;
+    int width, height, samples;
+    int rank, world, row_block, layout;
+    int n_local_rows;
+    unsigned long long seed;
+};
+
+#define RTB_CTA_THREADS 256
+#define RTB_TILE_W 32
+#define RTB_TILE_H 8
+
+// thread -> (x, local row, global y); false when outside this rank's shard
+__device__ __forceinline__ bool pixelOfThread(const FrameParams &F, int &x, int &lr, int &y)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    x = blockIdx.x * RTB_TILE_W + (warp & 3) * 8 + (lane & 7);
+    lr = blockIdx.y * RTB_TILE_H + (warp >> 2) * 4 + (lane >> 3);
+    const int lb = lr / F.row_block;
+    y = (lb * F.world + F.rank) * F.row_block + (lr - lb * F.row_block);
+    return x < F.width && lr < F.n_local_rows && y < F.height;
+}
+
+__device__ __forceinline__ size_t pixelSlot(const FrameParams &F, int x, int lr, int y)
+{
+    return F.layout == RTB_LAYOUT_REFERENCE ? ((size_t)x * F.height + y) : ((size_t)lr * F.width + x);
+}
+
+// CTA-level reduction of the per-thread counters, one atomic triple per CTA
+__device__ __forceinline__ void flushCounters(Counters *g, unsigned int rays, unsigned int tris, unsigned int steps)
+{
+    __shared__ unsigned int s[3];
+    if (threadIdx.x < 3) s[threadIdx.x] = 0;
+    __syncthreads();
+    rays = __reduce_add_sync(0xffffffffu, rays);
+    tris = __reduce_add_sync(0xffffffffu, tris);
+    steps = __reduce_add_sync(0xffffffffu, steps);
+    if ((threadIdx.x & 31) == 0)
+    {
+        atomicAdd(&s[0], rays);
+        if (tris) atomicAdd(&s[1], tris);
+        if (steps) atomicAdd(&s[2], steps);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        atomicAdd(&g->rays, (unsigned long long)s[0]);
+        if (s[1]) atomicAdd(&g->tris, (unsigned long long)s[1]);
+        if (s[2]) atomicAdd(&g->steps, (unsigned long long)s[2]);
+    }
+}
+
+template <class Probe> struct ProbeCounts
+{
+    static __device__ __forceinline__ unsigned int tris(const Probe &) { return 0; }
+    static __device__ __forceinline__ unsigned int steps(const Probe &) { return 0; }
+};
+template <> struct ProbeCounts<CountProbe>
+{
+    static __device__ __forceinline__ unsigned int tris(const CountProbe &p) { return p.tris; }
+    static __device__ __forceinline__ unsigned int steps(const CountProbe &p) { return p.steps; }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Whitted, scenes without refractive materials: the recursion of reference MainWindow.cpp:69-143
+// degenerates to a chain of reflections.  The chain is walked forward keeping (diffusive*d, r)
+// per vertex, then folded back innermost-first so the float result is bit-identical to the
+// recursive evaluation `diffusive*d + reflective*r + refractive*t`.
+// ---------------------------------------------------------------------------------------------
+#define RTB_MAX_DEPTH 100 // the reference's hard recursion cap (MainWindow.cpp:86)
+
+template <class Probe>
+__global__ void __launch_bounds__(RTB_CTA_THREADS)
+k_whitted_chain(const __grid_constant__ DScene S, const __grid_constant__ FrameParams F, float *__restrict__ out,
+                Counters *__restrict__ counters)
+{
+    int x, lr, y;
+    const bool active = pixelOfThread(F, x, lr, y);
+    unsigned int rays = 0;
+    Probe pr;
+    if (active)
+    {
+        const float dx = 1.0f / F.height, dy = 1.0f / F.height; // MainWindow.cpp:254-255
+        const float sx = (x + 0.5f) * dx, sy = 1 - (y + 0.5f) * dy;
+        Ray r = generateRay(F.cam, sx, sy);
+        float4 fold[RTB_MAX_DEPTH + 1];
+        int n = 0, depth = 0;
+        V3 c = v3(0, 0, 0); // value returned by the innermost call
+        const V3 zero = v3(0, 0, 0);
+        while (true)
+        {
+            rays++;
+            Hit h;
+            if (!sceneIntersect(S, r, h, pr)) break; // Color::Black()
+            const rtb_material &m = S.mats[h.mat];
+            const V3 nl = (dot(h.n, r.d) < 0) ? h.n : h.n * -1;
+            const V3 local = matLocal(m, r, h.pos, h.n);
+            if (++depth > F.setting.max_depth) break;
+            if (depth > RTB_MAX_DEPTH) break;
+            const V3 diffusive = (m.diffusiveness > 0) ? local : zero;
+            const V3 term = diffusive * m.diffusiveness;
+            if (m.reflectiveness > 0)
+            {
+                fold[n++] = make_float4(term.x, term.y, term.z, m.reflectiveness);
+                const V3 v = r.d - nl * 2 * dot(nl, r.d);
+                r.o = h.pos;
+                r.d = v;
+                continue;
+            }
+            c = term + zero * m.reflectiveness + zero * m.refractiveness;
+            break;
+        }
+        while (n > 0)
+        {
+            const float4 f = fold[--n];
+            c = v3(f.x, f.y, f.z) + c * f.w + zero * 0.0f;
+        }
+        float *o = out + 3 * pixelSlot(F, x, lr, y);
+        o[0] = c.x; o[1] = c.y; o[2] = c.z;
+    }
+    flushCounters(counters, rays, ProbeCounts<Probe>::tris(pr), ProbeCounts<Probe>::steps(pr));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Whitted, general scenes (refractive materials present): the ray tree of MainWindow.cpp:69-143
+// is walked depth-first with an explicit stack of {ray, scalar weight, depth}.  All branch weights
+// (reflectiveness, refractiveness*Re, refractiveness*Tr) are scalars, so a node contributes
+// weight * diffusive * d.  Accumulation order differs from the recursion: results agree within
+// ~1e-6 relative (the stated tolerance is 1e-5), not bit for bit.
+// ---------------------------------------------------------------------------------------------
+#define RTB_TREE_STACK 64 // live items <= 2*max_depth + 1
+struct TreeItem { V3 o, d; float w; int depth; };
+
+template <class Probe>
+__global__ void __launch_bounds__(RTB_CTA_THREADS)
+k_whitted_tree(const __grid_constant__ DScene S, const __grid_constant__ FrameParams F, float *__restrict__ out,
+               Counters *__restrict__ counters)
+{
+    int x, lr, y;
+    const bool active = pixelOfThread(F, x, lr, y);
+    unsigned int rays = 0;
+    Probe pr;
+    if (active)
+    {
+        const float dx = 1.0f / F.height, dy = 1.0f / F.height;
+        const float sx = (x + 0.5f) * dx, sy = 1 - (y + 0.5f) * dy;
+        const Ray primary = generateRay(F.cam, sx, sy);
+        const int cap = RTB_TREE_STACK;
+        TreeItem stack[RTB_TREE_STACK];
+        int sp = 0;
+        stack[sp].o = primary.o; stack[sp].d = primary.d; stack[sp].w = 1.0f; stack[sp].depth = 0; sp++;
+        V3 c = v3(0, 0, 0);
+        while (sp > 0)
+        {
+            const TreeItem it = stack[--sp];
+            Ray r; r.o = it.o; r.d = it.d;
+            int depth = it.depth;
+            rays++;
+            Hit h;
+            if (!sceneIntersect(S, r, h, pr)) continue;
+            const rtb_material &m = S.mats[h.mat];
+            const V3 nl = (dot(h.n, r.d) < 0) ? h.n : h.n * -1;
+            const V3 local = matLocal(m, r, h.pos, h.n);
+            if (++depth > F.setting.max_depth) continue;
+            if (depth > RTB_MAX_DEPTH) continue;
+            if (m.diffusiveness > 0) c = c + local * (it.w * m.diffusiveness);
+            if (sp + 3 > cap) continue; // excluded by rtb_render: max_depth <= (RTB_TREE_STACK - 3) / 2
+            // children are pushed in reverse so they pop in the reference's order
+            if (m.refractiveness > 0)
+            {
+                const Fresnel f = refraction(r, h.n, nl, m.refractive_index);
+                const float wt = it.w * m.refractiveness;
+                if (f.tir) { stack[sp].o = h.pos; stack[sp].d = f.refl; stack[sp].w = wt; stack[sp].depth = depth; sp++; }
+                else
+                {
+                    stack[sp].o = h.pos; stack[sp].d = f.tdir; stack[sp].w = wt * f.Tr; stack[sp].depth = depth; sp++;
+                    stack[sp].o = h.pos; stack[sp].d = f.refl; stack[sp].w = wt * f.Re; stack[sp].depth = depth; sp++;
+                }
+            }
+            if (m.reflectiveness > 0)
+            {
+                stack[sp].o = h.pos; stack[sp].d = r.d - nl * 2 * dot(nl, r.d);
+                stack[sp].w = it.w * m.reflectiveness; stack[sp].depth = depth; sp++;
+            }
+        }
+        float *o = out + 3 * pixelSlot(F, x, lr, y);
+        o[0] = c.x; o[1] = c.y; o[2] = c.z;
+    }
+    flushCounters(counters, rays, ProbeCounts<Probe>::tris(pr), ProbeCounts<Probe>::steps(pr));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Monte-Carlo path tracing -- reference MainWindow.cpp:145-249 (radiance) + 277-291 (sampling).
+// The recursion is unrolled into throughput form: `emission + local.mult(child)` becomes
+// L += T*emission; T *= local.  The two-ray refraction split (depth <= singleTracingDepth) pushes
+// the reflected ray and continues with the transmitted one -- the order in which the g++ build of
+// the reference consumes its random stream -- so with the counter-based stream the draws line up
+// with oracle/rt_oracle.cpp's ORACLE_RNG_COUNTER mode one to one.
+// ---------------------------------------------------------------------------------------------
+#define RTB_MC_STACK 32
+struct McItem { V3 o, d, T; int depth; };
+
+template <class Probe>
+__global__ void __launch_bounds__(RTB_CTA_THREADS)
+k_montecarlo(const __grid_constant__ DScene S, const __grid_constant__ FrameParams F, float *__restrict__ out,
+             Counters *__restrict__ counters)
+{
+    int x, lr, y;
+    const bool active = pixelOfThread(F, x, lr, y);
+    unsigned int rays = 0;
+    Probe pr;
+    if (active)
+    {
+        const float dx = 1.0f / F.height, dy = 1.0f / F.height;
+        const float PI_F = 3.14159265359f; // Vector.h:8
+        const float inv = 1.0f / F.samples;
+        V3 acc = v3(0, 0, 0);
+        Philox rng;
+        McItem stack[RTB_MC_STACK];
+        for (int s = 0; s < F.samples; s++)
+        {
+            rng.seed(F.seed, (uint32_t)(y * F.width + x), (uint32_t)s);
+            const float j1 = rng.next(), j2 = rng.next();
+            const float sx = (x + j1) * dx, sy = 1 - (y + j2) * dy;
+            Ray r = generateRay(F.cam, sx, sy);
+            V3 L = v3(0, 0, 0), T = v3(1, 1, 1);
+            int depth = 0, sp = 0;
+            while (true)
+            {
+                bool alive = false; // does the current path continue with (r, T, depth)?
+                rays++;
+                Hit h;
+                if (sceneIntersect(S, r, h, pr))
+                {
+                    const rtb_material &m = S.mats[h.mat];
+                    const V3 n = h.n;
+                    const V3 nl = (dot(n, r.d) < 0) ? n : n * -1;
+                    V3 local = matLocal(m, r, h.pos, n);
+                    const V3 emission = matEmission(m, h.pos);
+                    const float maxColor = (local.x + local.y + local.z) * 0.333333f;
+                    bool stop = false;
+                    if (++depth > F.setting.max_depth) stop = true;
+                    if (!stop && depth > F.setting.termination_depth)
+                    {
+                        if (rng.next() < maxColor) local = local * (1 / maxColor);
+                        else stop = true;
+                    }
+                    if (!stop && depth > RTB_MAX_DEPTH) stop = true;
+                    if (stop) L = L + mul(T, emission);
+                    else
+                    {
+                        const float p_type = rng.next();
+                        const float dif = m.diffusiveness, ref = m.reflectiveness, rfr = m.refractiveness;
+                        if (dif > 0 && p_type < dif)
+                        { // uniform hemisphere about nl, unit weight (MainWindow.cpp:185-200)
+                            const float r1 = rng.next(), r2 = rng.next();
+                            const float theta = 2 * PI_F * r1;
+                            const float phi = acosf(r2);
+                            const V3 w = nl;
+                            const V3 u = (fabsf(w.x) >= 0.1f) ? normalize(cross(v3(0, 1, 0), w)) : normalize(cross(v3(1, 0, 0), w));
+                            const V3 v = cross(w, u);
+                            const V3 dir = u * (cosf(theta) * sinf(phi)) + v * (sinf(theta) * sinf(phi)) + w * cosf(phi);
+                            L = L + mul(T, emission); T = mul(T, local);
+                            r.o = h.pos; r.d = dir; alive = true;
+                        }
+                        else if (ref > 0 && p_type >= dif && p_type <= dif + ref)
+                        {
+                            L = L + mul(T, emission); T = mul(T, local);
+                            const V3 v = r.d - nl * 2 * dot(nl, r.d);
+                            r.o = h.pos; r.d = v; alive = true;
+                        }
+                        else if (rfr > 0 && p_type > dif + ref)
+                        {
+                            const Fresnel f = refraction(r, n, nl, m.refractive_index);
+                            if (f.tir)
+                            {
+                                L = L + mul(T, emission); T = mul(T, local);
+                                r.o = h.pos; r.d = f.refl; alive = true;
+                            }
+                            else if (depth > F.setting.single_tracing_depth)
+                            {
+                                if (rng.next() < f.P) { T = T * f.RP; r.d = f.refl; }
+                                else { T = T * f.TP; r.d = f.tdir; }
+                                r.o = h.pos; alive = true;
+                            }
+                            else
+                            {
+                                if (sp < RTB_MC_STACK)
+                                {
+                                    stack[sp].o = h.pos; stack[sp].d = f.refl; stack[sp].T = T * f.Re; stack[sp].depth = depth; sp++;
+                                }
+                                T = T * f.Tr; r.o = h.pos; r.d = f.tdir; alive = true;
+                            }
+                        }
+                        else L = L + mul(T, emission); // "impossible to reach" tail, MainWindow.cpp:247-248
+                    }
+                }
+                if (alive) continue;
+                if (sp == 0) break;
+                --sp;
+                r.o = stack[sp].o; r.d = stack[sp].d; T = stack[sp].T; depth = stack[sp].depth;
+            }
+            acc = acc + L * inv;
+        }
+        float *o = out + 3 * pixelSlot(F, x, lr, y);
+        o[0] = acc.x; o[1] = acc.y; o[2] = acc.z;
+    }
+    flushCounters(counters, rays, ProbeCounts<Probe>::tris(pr), ProbeCounts<Probe>::steps(pr));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Parity hooks: primary rays with traversal recording, and arbitrary ray batches
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(RTB_CTA_THREADS)
+k_trace_primary(const __grid_constant__ DScene S, const __grid_constant__ FrameParams F, int *__restrict__ hit_id,
+                float *__restrict__ hit_t, int *__restrict__ seq_len, unsigned long long *__restrict__ seq_hash,
+                int *__restrict__ seq_buf, int seq_cap)
+{
+    int x, lr, y;
+    if (!pixelOfThread(F, x, lr, y)) return;
+    const float dx = 1.0f / F.height, dy = 1.0f / F.height;
+    const float sx = (x + 0.5f) * dx, sy = 1 - (y + 0.5f) * dy;
+    const Ray r = generateRay(F.cam, sx, sy);
+    const size_t p = (size_t)y * F.width + x;
+    SeqProbe pr;
+    pr.buf = seq_buf ? seq_buf + p * seq_cap : nullptr;
+    pr.cap = seq_buf ? seq_cap : 0;
+    Hit h;
+    const bool ok = sceneIntersect(S, r, h, pr);
+    if (hit_id) hit_id[p] = ok ? h.id : -1;
+    if (hit_t) hit_t[p] = ok ? h.t : -1.0f;
+    if (seq_len) seq_len[p] = pr.len;
+    if (seq_hash) seq_hash[p] = pr.hash;
+    if (seq_buf)
+        for (int i = pr.len; i < seq_cap; i++) seq_buf[p * seq_cap + i] = -1;
+}
+
+__global__ void __launch_bounds__(RTB_CTA_THREADS)
+k_intersect_rays(const __grid_constant__ DScene S, long long n, const float *__restrict__ rays, int *__restrict__ hit_id,
+                 float *__restrict__ hit_t, float *__restrict__ position, float *__restrict__ normal)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Ray r;
+    r.o = v3(rays[6 * i], rays[6 * i + 1], rays[6 * i + 2]);
+    r.d = v3(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]);
+    NoProbe pr;
+    Hit h;
+    const bool ok = sceneIntersect(S, r, h, pr);
+    if (hit_id) hit_id[i] = ok ? h.id : -1;
+    if (hit_t) hit_t[i] = ok ? h.t : -1.0f;
+    if (position) { position[3 * i] = ok ? h.pos.x : 0; position[3 * i + 1] = ok ? h.pos.y : 0; position[3 * i + 2] = ok ? h.pos.z : 0; }
+    if (normal) { normal[3 * i] = ok ? h.n.x : 0; normal[3 * i + 1] = ok ? h.n.y : 0; normal[3 * i + 2] = ok ? h.n.z : 0; }
+}
+
+} // namespace rtb

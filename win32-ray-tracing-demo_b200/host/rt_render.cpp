@@ -1,0 +1,415 @@
+// rt_render.cpp -- the GPU RenderProc (CudaRenderer), the preset scene scripts, the GPU-served
+// Geometry::intersect, and a small C API (rtbh_*) used by the Python tests / bench to reach the
+// host builders and the drop-in entry point.
+#include "rt.h"
+
+#include <chrono>
+#include <cstring>
+#include <mutex>
+
+namespace rt {
+
+static double nowMs()
+{
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// ---- CudaRenderer -------------------------------------------------------------------------------
+CudaRenderer &CudaRenderer::instance()
+{
+    static CudaRenderer r;
+    return r;
+}
+
+void CudaRenderer::configure(int width, int height, int samples, int device, uint64_t seed)
+{
+    if (ctx_ && device != device_) shutdown();
+    width_ = width; height_ = height; samples_ = samples; device_ = device; seed_ = seed;
+}
+
+rtb_ctx *CudaRenderer::context()
+{
+    if (!ctx_)
+    {
+        const int rc = rtb_init(device_, &ctx_);
+        if (rc != RTB_OK) { error_ = rtb_last_error(nullptr); ctx_ = nullptr; }
+    }
+    return ctx_;
+}
+
+void CudaRenderer::shutdown()
+{
+    if (ctx_) rtb_shutdown(ctx_);
+    ctx_ = nullptr;
+}
+
+int CudaRenderer::Render(GeometrySet &scene, PerspectiveCamera &camera, RenderSetting &setting, ProgressCallback progress)
+{ // replaces reference MainWindow.cpp:251-316
+    CudaRenderer &self = instance();
+    rtb_ctx *ctx = self.context();
+    if (!ctx) return -1;
+    const double t0 = nowMs();
+    FlatScene flat;
+    scene.flatten(flat);
+    flat.finish();
+    rtb_scene *dev = nullptr;
+    int rc = rtb_scene_upload(ctx, &flat.view, &dev);
+    if (rc != RTB_OK) { self.error_ = rtb_last_error(ctx); return -2; }
+    const rtb_camera cam = camera.flatten();
+    const rtb_render_setting rs = setting.flatten();
+    rtb_frame frame;
+    memset(&frame, 0, sizeof(frame));
+    frame.width = self.width_; frame.height = self.height_; frame.samples = self.samples_;
+    frame.seed = self.seed_; frame.rank = 0; frame.world = 1; frame.row_block = 8;
+    frame.layout = RTB_LAYOUT_REFERENCE; // Color colors[x*height + y], MainWindow.cpp:276
+    self.image_.assign((size_t)self.width_ * self.height_ * 3, 0.0f);
+    rc = rtb_render(ctx, dev, &cam, &rs, &frame, self.image_.data(), &self.stats_);
+    rtb_scene_free(ctx, dev);
+    if (rc != RTB_OK) { self.error_ = rtb_last_error(ctx); return -3; }
+    if (progress) progress(self.height_, self.height_);
+    const double ms = nowMs() - t0;
+    return ms < 1.0 ? 1 : (int)(ms + 0.5);
+}
+
+// ---- GPU-served single-ray queries --------------------------------------------------------------
+struct Geometry::DeviceCache
+{
+    rtb_scene *scene = nullptr;
+    ~DeviceCache()
+    {
+        if (scene) rtb_scene_free(CudaRenderer::instance().context(), scene);
+    }
+};
+
+void Geometry::invalidate() { cache_.reset(); }
+Geometry *Geometry::resolveHit(int) { return this; }
+
+Geometry *GeometrySet::resolveHit(int id)
+{
+    if (id >= 0 && id < (int)geometries.size()) return geometries[id];
+    return geometries.empty() ? this : geometries.back(); // tunnel triangle ids follow the top-level ones
+}
+
+static rtb_scene *uploadGeometry(const Geometry &g)
+{
+    rtb_ctx *ctx = CudaRenderer::instance().context();
+    if (!ctx) return nullptr;
+    FlatScene flat;
+    g.flatten(flat);
+    flat.finish();
+    rtb_scene *dev = nullptr;
+    if (rtb_scene_upload(ctx, &flat.view, &dev) != RTB_OK) return nullptr;
+    return dev;
+}
+
+IntersectResult Geometry::intersect(Ray &ray)
+{
+    IntersectResult res(false);
+    if (!cache_)
+    {
+        cache_ = std::make_shared<DeviceCache>();
+        cache_->scene = uploadGeometry(*this);
+    }
+    if (!cache_->scene) return res;
+    const float r[6] = {ray.origin.x, ray.origin.y, ray.origin.z, ray.direction.x, ray.direction.y, ray.direction.z};
+    int32_t id = -1;
+    float t = 0, pos[3], nrm[3];
+    if (rtb_intersect_rays(CudaRenderer::instance().context(), cache_->scene, 1, r, &id, &t, pos, nrm) != RTB_OK || id < 0)
+        return res;
+    res.hit = true;
+    res.id = id;
+    res.geometry = resolveHit(id);
+    res.distance = t;
+    res.position = Point(pos[0], pos[1], pos[2]);
+    res.normal = Vector(nrm[0], nrm[1], nrm[2]);
+    return res;
+}
+
+bool GeometrySet::intersectBatch(const float *rays, int64_t n, int32_t *hitId, float *hitT, float *position, float *normal)
+{
+    Ray probe(Point(0, 0, 0), Vector(0, 0, 1));
+    rtb_scene *dev = uploadGeometry(*this);
+    if (!dev) return false;
+    rtb_ctx *ctx = CudaRenderer::instance().context();
+    const int rc = rtb_intersect_rays(ctx, dev, n, rays, hitId, hitT, position, normal);
+    rtb_scene_free(ctx, dev);
+    return rc == RTB_OK;
+}
+
+// ---- preset scene scripts (reference Scripts.cpp:22-278) ----------------------------------------
+static Ptr<Material> solid(const Color &local, const Color &emission, float d, float r, float t)
+{
+    return Ptr<Material>(new SolidColorMaterial(local, emission, d, r, t));
+}
+
+static void addCornellBox(GeometrySet &scene)
+{ // the smallpt box of presets 2 and 3: six planes and the r=600 light sphere
+    const struct { Vector n; float d; Color c; } walls[6] = {
+        {Vector(1, 0, 0), 1, Color(0.75f, 0.25f, 0.25f)}, {Vector(1, 0, 0), 99, Color(0.25f, 0.25f, 0.75f)},
+        {Vector(0, 1, 0), 0, Color(0.75f, 0.75f, 0.75f)}, {Vector(0, 1, 0), 81.6f, Color(0.75f, 0.75f, 0.75f)},
+        {Vector(0, 0, 1), 0, Color(0.75f, 0.75f, 0.75f)}, {Vector(0, 0, 1), 170, Color(0, 0, 0)}};
+    for (const auto &w : walls)
+    {
+        Plane *p = new Plane(w.n, w.d);
+        p->material = solid(w.c, Color::Black(), 1, 0, 0);
+        scene.add(p);
+    }
+    Sphere *light = new Sphere(Point(50, 681.6f - 0.27f, 81.6f), 600);
+    light->material = solid(Color::Black(), Color(24, 24, 24), 1, 0, 0);
+    scene.add(light);
+}
+
+bool Script::Build(GeometrySet &scene, std::unique_ptr<PerspectiveCamera> &camera, RenderSetting &setting,
+                   int tunnelAlgorithm, int &prepareTime) const
+{
+    prepareTime = 0;
+    if (preset == 1)
+    {
+        Plane *ground = new Plane(Vector(0, 1, 0), 0);
+        ground->material = Ptr<Material>(new RadianceCheckerMaterial(1.2f, 0.025f));
+        scene.add(ground);
+        Sphere *s1 = new Sphere(Point(-10, 15, -30), 15), *s2 = new Sphere(Point(20, 10, -20), 10);
+        s1->material = solid(Color::White(), Color::Black(), 1, 0, 0);
+        s2->material = solid(Color::White(), Color::Black(), 1, 0, 0);
+        scene.add(s1);
+        scene.add(s2);
+        camera.reset(new PerspectiveCamera(Point(0, 15, 30), Vector(0, 0, -1), Vector(0, 1, 0), 1.3333f, 65, 0));
+        setting = RenderSetting::Default();
+        return true;
+    }
+    if (preset == 2 || preset == 3)
+    {
+        addCornellBox(scene);
+        if (preset == 2)
+        {
+            Sphere *mirror = new Sphere(Point(27, 16.5f, 47), 16.5f), *glass = new Sphere(Point(73, 16.5f, 78), 16.5f);
+            mirror->material = solid(Color::White(), Color::Black(), 0, 1, 0);
+            glass->material = Ptr<Material>(new GlassMaterial());
+            scene.add(mirror);
+            scene.add(glass);
+        }
+        else if (!scene.addStlFile(stlPath.c_str(), Ptr<Material>(new GlassMaterial()), Matrix(1, 0, 0, 0, 1, 0, 0, 0, 1),
+                                   Vector(50, 0, 40)))
+            return false;
+        camera.reset(new PerspectiveCamera(Point(50, 52, 295), Vector(0, -0.045f, -1), Vector(0, 1, -0.045f), 1.3333f, 28, 140.0f));
+        setting = RenderSetting::Default();
+        return true;
+    }
+    // presets 4 (short wide tunnel) and 5 (long narrow tunnel)
+    const bool wide = preset == 4;
+    Sphere *ball = new Sphere(wide ? Point(74.12f, 15, -96.59f) : Point(5000, 15, -5000), 15);
+    ball->material = Ptr<Material>(new PhongMaterial(Color(1, 0, 0), Color::White(), 16));
+    scene.add(ball);
+    Plane *ground = new Plane(Vector(0, 1, 0), -0.01f);
+    ground->material = solid(Color(0.25, 0.25, 0.25), Color::Black(), 1, 0, 0);
+    scene.add(ground);
+    Plane *sky = new Plane(Vector(0, 1, 0), 1000);
+    sky->material = solid(Color::White(), Color::Black(), 1, 0, 0);
+    scene.add(sky);
+    TunnelGenerator g;
+    g.create(50, 25, 25, wide ? 100.0f : 5000.0f, wide ? PI * 0.416667f : PI * 0.5f, tunnelSegments, tunnelSegments, scene,
+             Ptr<Material>(new CheckerMaterial(0.05f)), solid(Color::Black(), Color::Black(), 0.333f, 0.667f, 0),
+             (Tunnel::Algorithm)tunnelAlgorithm);
+    const double t1 = nowMs();
+    static_cast<Tunnel *>(scene.last())->init();
+    prepareTime = (int)(nowMs() - t1 + 0.5);
+    camera.reset(new PerspectiveCamera(Point(0, 25, 20), Vector(0, 0, -1), Vector(0, 1, 0), 1.3333f, 65, 0.0f));
+    setting = RenderSetting::Simple();
+    return true;
+}
+
+void Script::Run(RenderProc render, int tunnelAlgorithm, LogCallback log, ProgressCallback progress, int &prepareTime,
+                 int &execTime)
+{
+    GeometrySet scene;
+    std::unique_ptr<PerspectiveCamera> camera;
+    RenderSetting setting = RenderSetting::Simple();
+    if (!Build(scene, camera, setting, tunnelAlgorithm, prepareTime))
+    {
+        if (log) log("Script: cannot build the scene (missing STL file?)\r\n");
+        execTime = -1;
+        return;
+    }
+    execTime = render(scene, *camera, setting, progress);
+}
+
+static Script s1("checker ground and balls", Script::FLAG_MONTE_CARLO, 0, 1000, 1);
+static Script s2("smallpt", Script::FLAG_MONTE_CARLO, 0, 1000, 2);
+static Script s3("smallpt (stl)", Script::FLAG_MONTE_CARLO, 0, 1000, 3);
+static Script s4("tunnel (short and wide)", Script::FLAG_TUNNEL, 150, 0, 4);
+static Script s5("tunnel (long and narrow)", Script::FLAG_TUNNEL, 150, 0, 5);
+Script *scripts[5] = {&s1, &s2, &s3, &s4, &s5};
+
+} // namespace rt
+
+// ---- C API for the Python harness ----------------------------------------------------------------
+using namespace rt;
+
+struct rtbh_scene
+{
+    GeometrySet scene;
+    std::unique_ptr<PerspectiveCamera> camera;
+    RenderSetting setting;
+    FlatScene flat;
+    rtb_camera cam;
+    rtb_render_setting rs;
+    int prepareMs = 0;
+    double buildMs = 0, flattenMs = 0;
+    Tunnel *tunnel = nullptr;
+};
+
+static inline void hmix(uint64_t &h, uint32_t v) { h = (h ^ v) * 0x100000001b3ull; }
+static inline uint32_t fbits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+
+extern "C" {
+
+// Build preset `preset` (1..5, reference Scripts.cpp) with the host builders and flatten it.
+rtbh_scene *rtbh_preset_create(int preset, int algorithm, int segments, const char *stl_path)
+{
+    if (preset < 1 || preset > 5 || algorithm < 0 || algorithm > 4) return nullptr;
+    rtbh_scene *h = new rtbh_scene();
+    Script script = *scripts[preset - 1];
+    script.tunnelSegments = segments;
+    if (stl_path) script.stlPath = stl_path;
+    const double t0 = nowMs();
+    if (!script.Build(h->scene, h->camera, h->setting, algorithm, h->prepareMs)) { delete h; return nullptr; }
+    h->buildMs = nowMs() - t0;
+    const double t1 = nowMs();
+    h->scene.flatten(h->flat);
+    h->flat.finish();
+    h->flattenMs = nowMs() - t1;
+    h->cam = h->camera->flatten();
+    h->rs = h->setting.flatten();
+    if (preset >= 4) h->tunnel = static_cast<Tunnel *>(h->scene.last());
+    return h;
+}
+void rtbh_free(rtbh_scene *h) { delete h; }
+const rtb_flat_scene *rtbh_flat(const rtbh_scene *h) { return &h->flat.view; }
+const rtb_camera *rtbh_camera(const rtbh_scene *h) { return &h->cam; }
+const rtb_render_setting *rtbh_setting(const rtbh_scene *h) { return &h->rs; }
+double rtbh_prepare_ms(const rtbh_scene *h) { return h->prepareMs; }
+double rtbh_build_ms(const rtbh_scene *h) { return h->buildMs; }
+int64_t rtbh_host_bytes(const rtbh_scene *h) { return (int64_t)h->flat.hostBytes(); }
+
+// stats in the order of oracle_abi.h's ORACLE_STAT_* (n_top, n_tris, grid xyz, cells, entries, max, kd nodes, leaves, refs, depth)
+void rtbh_stats(const rtbh_scene *h, int64_t *out)
+{
+    memset(out, 0, 16 * sizeof(int64_t));
+    out[0] = h->flat.view.n_top;
+    out[1] = h->flat.view.n_tris;
+    if (h->tunnel)
+    {
+        const Tunnel::BuildStats &s = h->tunnel->stats;
+        out[2] = s.gridX; out[3] = s.gridY; out[4] = s.gridZ;
+        out[5] = s.cellsNonEmpty; out[6] = s.cellEntries; out[7] = s.cellMax;
+        out[8] = s.kdNodes; out[9] = s.kdLeaves; out[10] = s.kdLeafRefs; out[11] = s.kdMaxDepth;
+    }
+}
+
+// canonical digest of the tunnel triangle stream (a, b, c, normal, ground flag)
+uint64_t rtbh_tri_hash(const rtbh_scene *h)
+{
+    const rtb_flat_scene &f = h->flat.view;
+    if (f.n_tris == 0) return 0;
+    uint64_t x = 0xcbf29ce484222325ull;
+    const int groundMat = f.tri_material[f.n_tris - 1];
+    for (int k = 0; k < f.n_tris; k++)
+    {
+        for (int q = 0; q < 12; q++) hmix(x, fbits(f.tri[12 * (size_t)k + q]));
+        hmix(x, f.tri_material[k] == groundMat ? 1u : 0u);
+    }
+    return x;
+}
+
+// canonical digest of the flattened accelerator, computed from the FLAT buffers: walks the sparse
+// cell directory / the pre-order node array exactly as the kernels read them
+uint64_t rtbh_struct_hash(const rtbh_scene *h)
+{
+    const rtb_flat_scene &f = h->flat.view;
+    uint64_t x = 0xcbf29ce484222325ull;
+    if (f.n_tris == 0) return 0;
+    if (f.accel == RTB_ACCEL_REGULAR_GRID || f.accel == RTB_ACCEL_FLAT_GRID)
+    {
+        hmix(x, 0x47524944u);
+        for (int a = 0; a < 3; a++) hmix(x, (uint32_t)f.grid_dims[a]);
+        for (int a = 0; a < 3; a++) hmix(x, fbits(f.grid_origin[a]));
+        for (int a = 0; a < 3; a++) hmix(x, fbits(f.grid_cell[a]));
+        for (int64_t w = 0; w < f.n_cellwords; w++)
+        {
+            uint32_t bits = f.grid_words[w].bits, r = f.grid_words[w].rank;
+            while (bits)
+            {
+                const int b = __builtin_ctz(bits);
+                bits &= bits - 1;
+                const uint32_t first = f.grid_cell_start[r], last = f.grid_cell_start[r + 1];
+                hmix(x, (uint32_t)(w * 32 + b));
+                hmix(x, last - first);
+                for (uint32_t e = first; e < last; e++) hmix(x, f.grid_cell_tris[e]);
+                r++;
+            }
+        }
+        return x;
+    }
+    if (f.accel == RTB_ACCEL_KD_MEDIAN || f.accel == RTB_ACCEL_KD_SAH)
+    {
+        hmix(x, 0x4b445452u);
+        for (int a = 0; a < 3; a++) hmix(x, fbits(f.kd_min[a]));
+        for (int a = 0; a < 3; a++) hmix(x, fbits(f.kd_max[a]));
+        for (int i = 0; i < f.n_kd_nodes; i++) // array order IS pre-order
+        {
+            const rtb_kdnode &n = f.kd_nodes[i];
+            if ((n.b & 3u) == 3u)
+            {
+                hmix(x, 3);
+                hmix(x, n.b >> 2);
+                for (uint32_t e = 0; e < (n.b >> 2); e++) hmix(x, f.kd_leaf_tris[n.a + e]);
+            }
+            else { hmix(x, n.b & 3u); hmix(x, n.a); }
+        }
+        return x;
+    }
+    return 0;
+}
+
+// The drop-in path end to end: Script::Run(CudaRenderer::Render, ...) exactly as the reference's
+// RenderThread calls it (MainWindow.cpp:369).  rgb_out (may be NULL): w*h*3 floats, reference order.
+int rtbh_script_run(int preset, int algorithm, int segments, int width, int height, int samples, uint64_t seed,
+                    int device, const char *stl_path, float *rgb_out, int *prepare_ms, int *exec_ms, rtb_stats *stats)
+{
+    if (preset < 1 || preset > 5) return -1;
+    CudaRenderer &r = CudaRenderer::instance();
+    r.configure(width, height, samples, device, seed);
+    Script script = *scripts[preset - 1];
+    script.tunnelSegments = segments;
+    script.samples = samples;
+    if (stl_path) script.stlPath = stl_path;
+    int prep = 0, exec = 0;
+    script.Run(CudaRenderer::Render, algorithm, nullptr, nullptr, prep, exec);
+    if (prepare_ms) *prepare_ms = prep;
+    if (exec_ms) *exec_ms = exec;
+    if (exec < 0) return exec;
+    if (rgb_out) memcpy(rgb_out, r.image().data(), r.image().size() * sizeof(float));
+    if (stats) *stats = r.stats();
+    return 0;
+}
+
+const char *rtbh_last_error() { return CudaRenderer::instance().lastError().c_str(); }
+
+// Geometry::intersect / GeometrySet::intersectBatch through the host API (GPU-served)
+int rtbh_intersect_batch(rtbh_scene *h, int64_t n, const float *rays, int32_t *hit_id, float *hit_t, float *position,
+                         float *normal)
+{
+    return h->scene.intersectBatch(rays, n, hit_id, hit_t, position, normal) ? 0 : -1;
+}
+int rtbh_intersect_one(rtbh_scene *h, const float *ray6, int32_t *hit_id, float *hit_t, float *position, float *normal)
+{
+    Ray r(Point(ray6[0], ray6[1], ray6[2]), Vector(ray6[3], ray6[4], ray6[5]));
+    IntersectResult res = h->scene.intersect(r);
+    *hit_id = res.hit ? res.id : -1;
+    *hit_t = res.hit ? res.distance : -1.0f;
+    if (position) { position[0] = res.position.x; position[1] = res.position.y; position[2] = res.position.z; }
+    if (normal) { normal[0] = res.normal.x; normal[1] = res.normal.y; normal[2] = res.normal.z; }
+    return 0;
+}
+
+} // extern "C"
