@@ -180,6 +180,14 @@ int rtb_render_device(rtb_ctx *ctx, const rtb_scene *scene, const rtb_camera *ca
                       const rtb_render_setting *setting, const rtb_frame *frame,
                       void *rgb_device, void *stream, rtb_stats *stats);
 
+/* Multi-GPU assembly: `gathered` is the NCCL all-gather of every rank's rtb_render_device output,
+ * [world][rows_per_rank][width][3] floats (each rank's rows padded to rows_per_rank); writes the
+ * frame in image row order [height][width][3] to `image`.  Both are DEVICE buffers; asynchronous
+ * on `stream`.  (The reference has a single framebuffer, MainWindow.cpp:257; this is its
+ * reassembly after tile-row sharding.)                                                        */
+int rtb_unshard_device(rtb_ctx *ctx, const void *gathered, void *image, int32_t width, int32_t height,
+                       int32_t world, int32_t row_block, int64_t rows_per_rank, void *stream);
+
 /* Parity hook: primary rays only (pixel centres, MainWindow.cpp:294-297) through
  * GeometrySet::intersect.  Arrays are row-major [y*width + x] HOST buffers, any may be NULL.
  * seq_* record the accelerator steps of the TUNNEL prim (cell indices / pre-order node ids):

@@ -101,7 +101,7 @@ class Stats(C.Structure):
 
 ABI_SYMBOLS = ["rtb_init", "rtb_shutdown", "rtb_last_error", "rtb_abi_version", "rtb_shard_rows",
                "rtb_scene_upload", "rtb_scene_free", "rtb_scene_device_bytes", "rtb_render",
-               "rtb_render_device", "rtb_trace_primary", "rtb_intersect_rays"]
+               "rtb_render_device", "rtb_unshard_device", "rtb_trace_primary", "rtb_intersect_rays"]
 
 _cuda = None
 _host = None
@@ -129,6 +129,7 @@ def cuda_lib():
                                    C.POINTER(Stats)]
         lib.rtb_render_device.argtypes = [vp, vp, C.POINTER(Camera), C.POINTER(RenderSetting), C.POINTER(Frame),
                                           vp, vp, C.POINTER(Stats)]
+        lib.rtb_unshard_device.argtypes = [vp, vp, vp, i32, i32, i32, i32, i64, vp]
         lib.rtb_trace_primary.argtypes = [vp, vp, C.POINTER(Camera), i32, i32, vp, vp, vp, vp, vp, i32]
         lib.rtb_intersect_rays.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp]
         _cuda = lib
@@ -295,6 +296,11 @@ class Context:
 
     def upload(self, flat):
         return DeviceScene(self, flat)
+
+
+def unshard_device(ctx, gathered_ptr, image_ptr, width, height, world, row_block, rows_per_rank, stream=0):
+    ctx._check(ctx._lib.rtb_unshard_device(ctx._h, C.c_void_p(gathered_ptr), C.c_void_p(image_ptr), width, height, world,
+                                           row_block, rows_per_rank, C.c_void_p(stream)), "rtb_unshard_device")
 
 
 def shard_rows(frame):

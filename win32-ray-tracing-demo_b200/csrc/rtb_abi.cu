@@ -385,6 +385,22 @@ extern "C" int rtb_render_device(rtb_ctx *ctx, const rtb_scene *scene, const rtb
     return renderCommon(ctx, scene, F, frame, (float *)rgb_device, stream ? (cudaStream_t)stream : ctx->stream, stats, nullptr);
 }
 
+extern "C" int rtb_unshard_device(rtb_ctx *ctx, const void *gathered, void *image, int32_t width, int32_t height,
+                                  int32_t world, int32_t row_block, int64_t rows_per_rank, void *stream)
+{
+    if (!ctx || !gathered || !image || width <= 0 || height <= 0 || world <= 0 || row_block <= 0 || rows_per_rank <= 0)
+        return fail(ctx, RTB_ERR_INVALID, "rtb_unshard_device: bad argument");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t rowFloats = (size_t)width * 3;
+    unsigned int bx = (unsigned int)((rowFloats / 4 + 255) / 256);
+    if (bx == 0) bx = 1;
+    if (bx > 8) bx = 8;
+    k_unshard<<<dim3(bx, height), 256, 0, stream ? (cudaStream_t)stream : ctx->stream>>>(
+        (const float *)gathered, (float *)image, width, height, world, row_block, (int)rows_per_rank);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return RTB_OK;
+}
+
 // ---- parity hooks -----------------------------------------------------------------------------
 template <class T> struct DevBuf
 {

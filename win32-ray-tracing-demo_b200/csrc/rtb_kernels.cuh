@@ -363,4 +363,29 @@ k_intersect_rays(const __grid_constant__ DScene S, long long n, const float *__r
     if (normal) { normal[3 * i] = ok ? h.n.x : 0; normal[3 * i + 1] = ok ? h.n.y : 0; normal[3 * i + 2] = ok ? h.n.z : 0; }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Un-shard: after the NCCL all-gather the frame lives as [world][rows_per_rank][width][3] in
+// block-cyclic row order; this puts it back into image row order [height][width][3].
+// Pure 128-bit copies when width*3 floats is a multiple of 4 (every 4:3 frame is).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_unshard(const float *__restrict__ gathered, float *__restrict__ image, int width, int height, int world, int row_block,
+          int rows_per_rank)
+{
+    const int y = blockIdx.y;
+    const int b = y / row_block, rank = b % world, lb = b / world;
+    const int lr = lb * row_block + (y - b * row_block);
+    const size_t rowFloats = (size_t)width * 3;
+    const float *src = gathered + ((size_t)rank * rows_per_rank + lr) * rowFloats;
+    float *dst = image + (size_t)y * rowFloats;
+    if ((rowFloats & 3) == 0)
+    {
+        const float4 *s4 = reinterpret_cast<const float4 *>(src);
+        float4 *d4 = reinterpret_cast<float4 *>(dst);
+        for (size_t i = blockIdx.x * blockDim.x + threadIdx.x; i < rowFloats / 4; i += (size_t)gridDim.x * blockDim.x) d4[i] = s4[i];
+    }
+    else
+        for (size_t i = blockIdx.x * blockDim.x + threadIdx.x; i < rowFloats; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
 } // namespace rtb
