@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""bench.py -- Mrays/s of the ray-generation / intersection / shading hot path on N B200s.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME]
+  (N > 1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...)
+
+A step = one frame of the workload rendered by the hot path (ray generation -> accelerator traversal
+-> triangle / sphere / plane tests -> Whitted or Monte-Carlo shading -> framebuffer), tile-row
+sharded over the ranks and, for N > 1, all-gathered over NCCL and put back into image row order.
+`value` times that with the scene resident in HBM; `e2e` times the same frame through the
+reference-facing host-buffer call (scene upload H2D + rtb_render + framebuffer D2H every step).
+
+Prints ONE JSON line (rank 0).  --impl reference times the unmodified reference renderer
+(oracle/_ref, else the CPU port oracle/rt_oracle.cpp) on the host cores instead.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json: "150-segment tunnel (k-d tree SAH ...)", config[4] "4K tunnel ... stress render"
+    "p5_sah_4k": dict(preset=5, algorithm="sah", segments=150, width=3840, height=2880, samples=1,
+                      desc="preset 5 long narrow tunnel, 150-segment tessellation (45,900 triangles), k-d tree SAH "
+                           "(leaf<=8, depth<=18), Whitted Simple() maxDepth 20, 3840x2880 (4:3), 1 spp"),
+    "p5_rgrid_4k": dict(preset=5, algorithm="rgrid", segments=150, width=3840, height=2880, samples=1,
+                        desc="preset 5, regular grid 400x5x400, Whitted, 3840x2880, 1 spp"),
+    "p5_kd_4k": dict(preset=5, algorithm="kd", segments=150, width=3840, height=2880, samples=1,
+                     desc="preset 5, k-d median, Whitted, 3840x2880, 1 spp"),
+    "p5_fgrid_4k": dict(preset=5, algorithm="fgrid", segments=150, width=3840, height=2880, samples=1,
+                        desc="preset 5, flat grid 400^3, Whitted, 3840x2880, 1 spp"),
+    "p4_sah_4k": dict(preset=4, algorithm="sah", segments=150, width=3840, height=2880, samples=1,
+                      desc="preset 4 short wide tunnel, k-d SAH, Whitted, 3840x2880, 1 spp"),
+    "p2_smallpt_64": dict(preset=2, algorithm="linear", segments=0, width=1280, height=960, samples=64,
+                          desc="preset 2 smallpt Cornell box, Monte Carlo Default(), 1280x960, 64 spp"),
+    "p5_sah_400": dict(preset=5, algorithm="sah", segments=150, width=400, height=300, samples=1,
+                       desc="preset 5, k-d SAH, Whitted, demo default 400x300, 1 spp"),
+}
+EXTRAS = ["p5_rgrid_4k", "p5_kd_4k", "p5_fgrid_4k", "p4_sah_4k", "p2_smallpt_64"]
+ROW_BLOCK = 16
+METRIC = "Mrays/s on tunnel scenes (grid/k-d tree) at 1/2/4/8 B200 vs CPU render secs"
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+# ---- clocks: sampled while the timed region runs ----------------------------------------------------
+class ClockSampler:
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, index):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self._nv = None
+
+    def _run(self):
+        nv = self._nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.004)
+
+    def start(self):
+        if self._nv:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread:
+            self._thread.join()
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ---- the reference arm / cpu baseline ----------------------------------------------------------------
+def cpu_reference(wl, width, height, repeat, warmup=0):
+    """Time the reference's own Render() on the host cores (all threads)."""
+    from oracle import oracle_py as O
+    kind = "reference" if O.available("ref_timing") else "port"
+    which = "ref_timing" if kind == "reference" else "oracle"
+    cores = os.cpu_count() or 1
+    kw = dict(preset=wl["preset"], algorithm=wl["algorithm"], segments=wl["segments"], width=width, height=height,
+              samples=wl["samples"], threads=cores)
+    # ray count of this exact job: the hooks build (or the port, which always counts)
+    counted = O.run("ref" if O.available("ref") else "oracle", repeat=1, **kw)
+    r = O.run(which, repeat=repeat + warmup, **kw)
+    times = np.asarray(r["render_ms_all"][warmup:], np.float64)
+    return dict(kind=kind, cores=cores, rays=int(counted["n_rays"]), ms=times, prepare_ms=float(r["prepare_ms"]))
+
+
+def run_reference(args, wl_name):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = WORKLOADS[wl_name]
+    # bounded sample: the same scene, camera and setting at 1/4 of the linear resolution (1/16 of the rays)
+    w, h = (wl["width"] // 4, wl["height"] // 4) if wl["width"] >= 1600 else (wl["width"], wl["height"])
+    spp = wl["samples"]
+    if spp > 4:
+        wl = dict(wl, samples=4)
+    res = cpu_reference(wl, w, h, args.steps, args.warmup)
+    ms = float(res["ms"].mean())
+    value = res["rays"] / ms / 1e3
+    sample = f"{w}x{h} frame of the same scene/camera/setting" + (f", {wl['samples']} of {spp} spp" if spp != wl["samples"] else "")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl_name, "description": wl["desc"], "sample": sample, "rays_per_step": res["rays"]},
+            "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": res["cores"], "kind": res["kind"], "sample": sample,
+                             "render_s": ms / 1e3, "prepare_s": res["prepare_ms"] / 1e3},
+            "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---- the B200 arm ----------------------------------------------------------------------------------
+def run_b200(args, wl_name):
+    import torch
+    import rtb200
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev_t = torch.device("cuda", local)
+
+    def allmax(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev_t)
+        if dist:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev_t)
+        if dist:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def barrier():
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    wl = WORKLOADS[wl_name]
+    W, H, spp = wl["width"], wl["height"], wl["samples"]
+    t0 = time.perf_counter()
+    scene = rtb200.PresetScene(wl["preset"], wl["algorithm"], wl["segments"])
+    host_build_s = time.perf_counter() - t0
+    ctx = rtb200.Context(local)
+    dscene = ctx.upload(scene.flat)
+    frame = rtb200.make_frame(W, H, samples=spp, seed=0, rank=rank, world=world, row_block=ROW_BLOCK)
+    rows = rtb200.shard_rows(frame)
+    rows_max = int(allmax(rows))
+    stream = torch.cuda.current_stream().cuda_stream
+
+    image = torch.zeros((H, W, 3), dtype=torch.float32, device=dev_t)
+    if world > 1:
+        local_buf = torch.zeros((rows_max, W, 3), dtype=torch.float32, device=dev_t)
+        gathered = torch.zeros((world, rows_max, W, 3), dtype=torch.float32, device=dev_t)
+    flush = torch.empty(384 * 1024 * 1024, dtype=torch.uint8, device=dev_t)  # > 126 MB L2
+
+    def step():
+        if world == 1:
+            dscene.render_device(scene.camera, scene.setting, frame, image.data_ptr(), stream)
+        else:
+            dscene.render_device(scene.camera, scene.setting, frame, local_buf.data_ptr(), stream)
+            dist.all_gather_into_tensor(gathered, local_buf)
+            rtb200.unshard_device(ctx, gathered.data_ptr(), image.data_ptr(), W, H, world, ROW_BLOCK, rows_max, stream)
+
+    launches_per_step = 1 if world == 1 else 2
+
+    # ray / test / step counts of one frame (deterministic), outside the timed region
+    cframe = rtb200.make_frame(W, H, samples=spp, seed=0, rank=rank, world=world, row_block=ROW_BLOCK, counters=1)
+    tmp = local_buf if world > 1 else image
+    cst = dscene.render_device(scene.camera, scene.setting, cframe, tmp.data_ptr(), stream, want_stats=True)
+    rays_frame = allsum(cst["n_rays"])
+    tests_frame = allsum(cst["n_tri_tests"])
+    steps_frame = allsum(cst["n_steps"])
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+
+    # kernel-only duration of this rank's render launch (CUDA events on the launching stream)
+    kst = dscene.render_device(scene.camera, scene.setting, frame, tmp.data_ptr(), stream, want_stats=True)
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    if sampler:
+        sampler.start()
+    for i in range(args.steps):
+        flush.zero_()  # L2 flush between timed iterations (not timed)
+        ev[i][0].record()
+        if world == 1:
+            step()
+            kev[i] = ev[i]
+        else:
+            kev[i][0].record()
+            dscene.render_device(scene.camera, scene.setting, frame, local_buf.data_ptr(), stream)
+            kev[i][1].record()
+            dist.all_gather_into_tensor(gathered, local_buf)
+            rtb200.unshard_device(ctx, gathered.data_ptr(), image.data_ptr(), W, H, world, ROW_BLOCK, rows_max, stream)
+        ev[i][1].record()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    total_ms = allmax(sum(a.elapsed_time(b) for a, b in ev))
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    kernel_ms_max = allmax(kernel_ms)
+    ms_per_step = total_ms / args.steps
+    value = rays_frame / ms_per_step / 1e3  # Mrays/s, whole job
+
+    # ---- e2e: host buffers through the C ABI, H2D scene upload + D2H framebuffer inside the timed region
+    pinned = torch.empty((max(rows, 1), W, 3), dtype=torch.float32).pin_memory()
+    host_out = pinned.numpy()
+    e2e_steps = max(3, min(args.steps, 10))
+    h2d = dscene.device_bytes
+    d2h = rows * W * 3 * 4
+
+    def e2e_step():
+        d = ctx.upload(scene.flat)
+        d.render(scene.camera, scene.setting, frame, out=host_out)
+        d.close()
+
+    e2e_step()
+    barrier()
+    t1 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_ms = allmax((time.perf_counter() - t1) * 1e3) / e2e_steps
+    e2e_value = rays_frame / e2e_ms / 1e3
+
+    # ---- roofline of the dominant kernel (the render kernel of this rank)
+    peaks, peak_kind = measured_peaks()
+    pixels_rank = rows * W
+    # algorithmic bytes (DESIGN.md "Roofline"): 8 B per visited cell / k-d node, 4 B index + 36 B vertices per
+    # triangle test, 12 B normal + 4 B material per ray, 12 B framebuffer store per pixel
+    algo_bytes = 8 * cst["n_steps"] + 40 * cst["n_tri_tests"] + 16 * cst["n_rays"] + 12 * pixels_rank
+    achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_kind,
+                "kernel": "k_montecarlo" if spp > 1 or wl["preset"] <= 3 else "k_whitted_chain",
+                "kernel_ms": kernel_ms, "kernel_ms_cold_single": kst["kernel_ms"],
+                "algorithmic_bytes_per_launch": algo_bytes, "bytes_per_ray": algo_bytes / max(cst["n_rays"], 1),
+                "note": "scene (<10 MB) is L2-resident by design, so the HBM fraction is low; the binding limits are "
+                        "L2->SM bytes and warp-instruction issue (see profiles/ and DESIGN.md)"}
+
+    # ---- other preset configs, one device-resident frame each (rank-local shard), not part of `value`
+    others = {}
+    if not args.no_extras and world == 1:
+        for name in EXTRAS:
+            o = WORKLOADS[name]
+            try:
+                s2 = rtb200.PresetScene(o["preset"], o["algorithm"], o["segments"])
+                d2 = ctx.upload(s2.flat)
+                buf = torch.empty((o["height"], o["width"], 3), dtype=torch.float32, device=dev_t)
+                f2 = rtb200.make_frame(o["width"], o["height"], samples=o["samples"])
+                d2.render_device(s2.camera, s2.setting, f2, buf.data_ptr(), stream, want_stats=True)
+                best = None
+                for _ in range(3):
+                    st = d2.render_device(s2.camera, s2.setting, f2, buf.data_ptr(), stream, want_stats=True)
+                    best = st if best is None or st["kernel_ms"] < best["kernel_ms"] else best
+                others[name] = {"Mrays/s": best["n_rays"] / best["kernel_ms"] / 1e3, "ms": best["kernel_ms"],
+                                "rays": best["n_rays"], "host_build_s": s2.build_ms / 1e3}
+                d2.close(); s2.close(); del buf
+            except Exception as e:  # report, do not hide
+                others[name] = {"error": str(e)}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            small = WORKLOADS["p5_sah_400"] if wl["preset"] >= 4 else dict(wl, width=400, height=300, samples=min(spp, 4))
+            small = dict(small, preset=wl["preset"], algorithm=wl["algorithm"], segments=wl["segments"])
+            res = cpu_reference(small, small["width"], small["height"], repeat=5, warmup=1)
+            ms = float(res["ms"].mean())
+            cpu = {"value": res["rays"] / ms / 1e3, "unit": "Mrays/s", "cores": res["cores"], "kind": res["kind"],
+                   "sample": f"{small['width']}x{small['height']} frame of the same scene/camera/setting, mean of 5 Render() calls",
+                   "render_s": ms / 1e3, "prepare_s": res["prepare_ms"] / 1e3}
+        except Exception as e:
+            cpu = {"error": str(e)}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": wl_name, "description": wl["desc"], "rays_per_step": rays_frame,
+                           "tri_tests_per_step": tests_frame, "traversal_steps_per_step": steps_frame,
+                           "sharding": f"tile rows, blocks of {ROW_BLOCK} rows dealt round-robin to {world} rank(s)"
+                                       + ("; NCCL all_gather_into_tensor + unshard kernel every step" if world > 1 else ""),
+                           "l2": "flushed between timed iterations (384 MiB memset, untimed)",
+                           "host_build_s": host_build_s, "scene_device_bytes": h2d},
+                "roofline": roofline, "cpu_baseline": cpu,
+                "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                        "ms_per_step": e2e_ms, "steps": e2e_steps,
+                        "path": "rtb_scene_upload (H2D) + rtb_render (kernel + D2H to pinned host) + rtb_scene_free per step"},
+                "gpu_launches": launches_per_step * args.steps,
+                "kernel_ms_max_over_ranks": kernel_ms_max, "clocks": clocks, "others": others}
+        print(json.dumps(line), flush=True)
+    dscene.close(); scene.close(); ctx.close()
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="p5_sah_4k", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args, args.workload)
+    else:
+        run_b200(args, args.workload)
+
+
+if __name__ == "__main__":
+    main()

@@ -86,6 +86,7 @@ typedef struct oracle_job {
     int64_t stats[ORACLE_STAT_COUNT];
     uint64_t struct_hash;/* canonical hash of the accelerator (see rt_oracle.cpp)         */
     uint64_t tri_hash;   /* hash of the tunnel triangle stream                            */
+    double *render_ms_all; /* optional [repeat]: every render's interval, in order (input ptr)   */
 } oracle_job;
 
 int rt_oracle_run(oracle_job *job);

@@ -33,6 +33,7 @@ class OracleJob(C.Structure):
         ("n_rays", C.c_int64), ("n_tri_tests", C.c_int64), ("n_steps", C.c_int64),
         ("render_ms", C.c_double), ("prepare_ms", C.c_double),
         ("stats", C.c_int64 * 16), ("struct_hash", C.c_uint64), ("tri_hash", C.c_uint64),
+        ("render_ms_all", C.c_void_p),
     ]
 
 
@@ -103,6 +104,8 @@ def run(which, preset, algorithm="linear", segments=150, width=400, height=300, 
         job.tri_cap = cap
         out("tri_out", np.zeros((cap, 12), np.float32))
         out("tri_mat", np.zeros(cap, np.int32))
+    if repeat > 0:
+        out("render_ms_all", np.zeros(repeat, np.float64))
     rc = _fn(which)(C.byref(job))
     if rc != 0:
         raise RuntimeError(f"{which} job failed rc={rc}")

@@ -238,6 +238,7 @@ static int jobRender(GeometrySet &scene, PerspectiveCamera &camera, RenderSettin
             Render(scene, camera, setting, noProgress);
             g_counting = false;
             const double ms = ref_last_tick_interval_ms();
+            if (job->render_ms_all) job->render_ms_all[r] = ms;
             if (ms < best) best = ms;
         }
         job->render_ms = best;

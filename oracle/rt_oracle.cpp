@@ -1161,6 +1161,7 @@ extern "C" int rt_oracle_run(oracle_job *job)
             const auto t0 = std::chrono::steady_clock::now();
             render(s, job, r == 0 ? job->rgb : nullptr, &total);
             const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            if (job->render_ms_all) job->render_ms_all[r] = ms;
             if (ms < best) best = ms;
         }
         job->render_ms = best;

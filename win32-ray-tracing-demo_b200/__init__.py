@@ -339,6 +339,8 @@ class DeviceScene:
     def render(self, camera, setting, frame, out=None):
         """rtb_render with HOST buffers; returns (rows x width x 3 float32 | reference-order array, stats)."""
         rows = shard_rows(frame)
+        if rows < 0:
+            raise RtbError("bad frame: size / rank / world / row_block (must be a multiple of 8)")
         if out is None:
             shape = (frame.width, frame.height, 3) if frame.layout == LAYOUT_REFERENCE else (rows, frame.width, 3)
             out = np.zeros(shape, np.float32)
