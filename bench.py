@@ -185,7 +185,11 @@ def run_b200(args, wl_name):
     frame = rtb200.make_frame(W, H, samples=spp, seed=0, rank=rank, world=world, row_block=ROW_BLOCK)
     rows = rtb200.shard_rows(frame)
     rows_max = int(allmax(rows))
-    stream = torch.cuda.current_stream().cuda_stream
+    # a dedicated (non-default) torch stream: the kernels, the NCCL gather and the timing events all
+    # live on it (a 0 handle would select the library's own stream)
+    tstream = torch.cuda.Stream(device=dev_t)
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
 
     image = torch.zeros((H, W, 3), dtype=torch.float32, device=dev_t)
     if world > 1:

@@ -218,7 +218,7 @@ def test_monte_carlo_statistics_vs_erand48(ctx, preset, spp):
     """Counter-RNG GPU images vs the oracle's erand48 image (the reference's own random stream) at equal
     samples per pixel.  K = 8 independent GPU seeds give, per pixel, the mean m and
     the standard deviation s of an spp-sample estimate; the CPU image is one more draw of that estimator:
-      (i)   image-mean luminance within 1 %;
+      (i)   image-mean luminance within 4 standard errors (estimated from the K seeds) and within 3 %;
       (ii)  |cpu - m| <= 5 * s * sqrt(1 + 1/K) for >= 99 % of pixels (Student-t, 7 dof: 99.8 % expected);
       (iii) CPU-vs-GPU RMSE <= 1.15 x GPU-vs-GPU RMSE between disjoint seeds."""
     w, h, K = 48, 36, 8
@@ -227,7 +227,10 @@ def test_monte_carlo_statistics_vs_erand48(ctx, preset, spp):
     gpu = np.stack([dev.render(s.camera, s.setting, rtb200.make_frame(w, h, samples=spp, seed=100 + k))[0].mean(axis=2)
                     for k in range(K)])
     m, sd = gpu.mean(axis=0), gpu.std(axis=0, ddof=1)
-    assert abs(m.mean() - cpu.mean()) <= 0.01 * cpu.mean()
+    img_means = gpu.mean(axis=(1, 2))
+    se = img_means.std(ddof=1) * np.sqrt(1 + 1.0 / K)
+    assert abs(img_means.mean() - cpu.mean()) <= max(4.0 * se, 0.002 * cpu.mean()), (img_means, cpu.mean())
+    assert abs(img_means.mean() - cpu.mean()) <= 0.03 * cpu.mean()
     sd = np.maximum(sd, 1e-3 + 0.01 * m)
     z = np.abs(cpu - m) / (sd * np.sqrt(1 + 1.0 / K))
     assert (z <= 5.0).mean() >= 0.99, (z <= 5.0).mean()
