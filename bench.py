@@ -250,8 +250,8 @@ def run_b200(args, wl_name):
     value = rays_frame / ms_per_step / 1e3  # Mrays/s, whole job
 
     # ---- e2e: host buffers through the C ABI, H2D scene upload + D2H framebuffer inside the timed region
-    pinned = torch.empty((max(rows, 1), W, 3), dtype=torch.float32).pin_memory()
-    host_out = pinned.numpy()
+    pinned = rtb200.PinnedArray((max(rows, 1), W, 3))  # rtb_host_alloc: page-locked host framebuffer
+    host_out = pinned.array
     e2e_steps = max(3, min(args.steps, 10))
     h2d = dscene.device_bytes
     d2h = rows * W * 3 * 4

@@ -157,6 +157,11 @@ int rtb_shutdown(rtb_ctx *ctx);
 const char *rtb_last_error(const rtb_ctx *ctx); /* ctx may be NULL: last global error       */
 int rtb_abi_version(void);
 
+/* Page-locked host memory for the host-buffer calls (optional: any host pointer is accepted, but
+ * device->host copies into pageable memory are staged by the driver and several times slower).   */
+int rtb_host_alloc(size_t bytes, void **out);
+int rtb_host_free(void *p);
+
 /* Number of rows / first-row list of a shard (pure host arithmetic; no device needed).       */
 int64_t rtb_shard_rows(const rtb_frame *frame);
 

@@ -100,6 +100,7 @@ class Stats(C.Structure):
 
 
 ABI_SYMBOLS = ["rtb_init", "rtb_shutdown", "rtb_last_error", "rtb_abi_version", "rtb_shard_rows",
+               "rtb_host_alloc", "rtb_host_free",
                "rtb_scene_upload", "rtb_scene_free", "rtb_scene_device_bytes", "rtb_render",
                "rtb_render_device", "rtb_unshard_device", "rtb_trace_primary", "rtb_intersect_rays"]
 
@@ -119,6 +120,8 @@ def cuda_lib():
         lib.rtb_shutdown.argtypes = [vp]
         lib.rtb_last_error.argtypes = [vp]
         lib.rtb_last_error.restype = C.c_char_p
+        lib.rtb_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+        lib.rtb_host_free.argtypes = [vp]
         lib.rtb_shard_rows.argtypes = [C.POINTER(Frame)]
         lib.rtb_shard_rows.restype = i64
         lib.rtb_scene_upload.argtypes = [vp, C.POINTER(FlatScene), C.POINTER(vp)]
@@ -301,6 +304,24 @@ class Context:
 def unshard_device(ctx, gathered_ptr, image_ptr, width, height, world, row_block, rows_per_rank, stream=0):
     ctx._check(ctx._lib.rtb_unshard_device(ctx._h, C.c_void_p(gathered_ptr), C.c_void_p(image_ptr), width, height, world,
                                            row_block, rows_per_rank, C.c_void_p(stream)), "rtb_unshard_device")
+
+
+class PinnedArray:
+    """float32 numpy view over page-locked host memory from rtb_host_alloc."""
+
+    def __init__(self, shape):
+        self.shape = tuple(int(x) for x in shape)
+        n = int(np.prod(self.shape))
+        self._p = C.c_void_p()
+        rc = cuda_lib().rtb_host_alloc(max(n, 1) * 4, C.byref(self._p))
+        if rc != 0:
+            raise RtbError("rtb_host_alloc failed: " + cuda_lib().rtb_last_error(None).decode())
+        self.array = np.ctypeslib.as_array(C.cast(self._p, C.POINTER(C.c_float)), shape=(max(n, 1),))[:n].reshape(self.shape)
+
+    def close(self):
+        if self._p:
+            cuda_lib().rtb_host_free(self._p)
+            self._p = C.c_void_p()
 
 
 def shard_rows(frame):

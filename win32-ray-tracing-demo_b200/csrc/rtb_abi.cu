@@ -20,6 +20,8 @@ struct rtb_ctx
     cudaStream_t stream = nullptr;
     Counters *d_counters = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    float *d_frame = nullptr; // grow-only device framebuffer of the host-buffer render call
+    size_t d_frame_bytes = 0;
     std::string error;
 };
 
@@ -30,6 +32,7 @@ struct rtb_scene
     int64_t bytes = 0;
     bool has_refractive = false;
     bool has_tunnel = false;
+    cudaEvent_t last_use = nullptr; // recorded after every launch that reads the scene
 };
 
 static std::string g_error;
@@ -82,6 +85,13 @@ extern "C" int rtb_init(int device, rtb_ctx **out)
     ctx->device = device;
     CUDA_TRY(ctx, cudaSetDevice(device));
     CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    { // scene buffers come from the stream-ordered pool and are kept for reuse: cudaMalloc/cudaFree cost
+      // milliseconds and synchronise the device, which would dominate a per-frame upload
+        cudaMemPool_t pool;
+        CUDA_TRY(ctx, cudaDeviceGetDefaultMemPool(&pool, device));
+        unsigned long long keep = ~0ull;
+        CUDA_TRY(ctx, cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     CUDA_TRY(ctx, cudaMalloc(&ctx->d_counters, sizeof(Counters)));
     for (int i = 0; i < 4; i++) CUDA_TRY(ctx, cudaEventCreate(&ctx->ev[i]));
     *out = ctx;
@@ -96,6 +106,7 @@ extern "C" int rtb_shutdown(rtb_ctx *ctx)
     for (int i = 0; i < 4; i++)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
+    if (ctx->d_frame) cudaFree(ctx->d_frame);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return RTB_OK;
@@ -124,7 +135,7 @@ static int uploadArray(rtb_ctx *ctx, rtb_scene *s, const T *host, size_t n, cons
     *dev = nullptr;
     if (n == 0) n = 1; // keep pointers valid
     void *p = nullptr;
-    CUDA_TRY(ctx, cudaMalloc(&p, n * sizeof(T)));
+    CUDA_TRY(ctx, cudaMallocAsync(&p, n * sizeof(T), ctx->stream));
     s->allocs.push_back(p);
     s->bytes += (int64_t)(n * sizeof(T));
     if (host) CUDA_TRY(ctx, cudaMemcpyAsync(p, host, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
@@ -175,6 +186,11 @@ extern "C" int rtb_scene_upload(rtb_ctx *ctx, const rtb_flat_scene *f, rtb_scene
     rtb_scene *s = new rtb_scene();
     DScene &d = s->d;
     memset(&d, 0, sizeof(d));
+    if (cudaEventCreateWithFlags(&s->last_use, cudaEventDisableTiming) != cudaSuccess)
+    {
+        delete s;
+        return fail(ctx, RTB_ERR_CUDA, "rtb_scene_upload: cudaEventCreate failed");
+    }
     d.n_prims = f->n_prims; d.n_materials = f->n_materials; d.n_top = f->n_top; d.accel = f->accel;
     int tunnels = 0;
     for (int i = 0; i < f->n_prims; i++)
@@ -272,8 +288,15 @@ extern "C" int rtb_scene_upload(rtb_ctx *ctx, const rtb_flat_scene *f, rtb_scene
 extern "C" int rtb_scene_free(rtb_ctx *ctx, rtb_scene *s)
 {
     if (!s) return RTB_OK;
-    if (ctx) cudaSetDevice(ctx->device);
-    for (void *p : s->allocs) cudaFree(p);
+    if (ctx)
+    { // stream-ordered release: after the last launch that read the scene (on whichever stream it ran)
+        cudaSetDevice(ctx->device);
+        if (s->last_use) cudaStreamWaitEvent(ctx->stream, s->last_use, 0);
+        for (void *p : s->allocs) cudaFreeAsync(p, ctx->stream);
+    }
+    else
+        for (void *p : s->allocs) cudaFree(p);
+    if (s->last_use) cudaEventDestroy(s->last_use);
     delete s;
     return RTB_OK;
 }
@@ -337,6 +360,7 @@ static int renderCommon(rtb_ctx *ctx, const rtb_scene *scene, const FrameParams 
     if (frame->counters) launchRender<CountProbe>(scene, F, d_out, ctx->d_counters, stream);
     else launchRender<NoProbe>(scene, F, d_out, ctx->d_counters, stream);
     CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, cudaEventRecord(scene->last_use, stream));
     if (stats) CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], stream));
     if (h_out) CUDA_TRY(ctx, cudaMemcpyAsync(h_out, d_out, bytes, cudaMemcpyDeviceToHost, stream));
     if (stats || h_out)
@@ -367,11 +391,15 @@ extern "C" int rtb_render(rtb_ctx *ctx, const rtb_scene *scene, const rtb_camera
     if (!rgb_out) return fail(ctx, RTB_ERR_INVALID, "rtb_render: null output buffer");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     const size_t bytes = (size_t)F.n_local_rows * F.width * 3 * sizeof(float);
-    float *d_out = nullptr;
-    CUDA_TRY(ctx, cudaMalloc(&d_out, bytes ? bytes : 4));
-    rc = renderCommon(ctx, scene, F, frame, d_out, ctx->stream, stats, rgb_out);
-    cudaFree(d_out);
-    return rc;
+    if (bytes > ctx->d_frame_bytes)
+    {
+        if (ctx->d_frame) cudaFree(ctx->d_frame);
+        ctx->d_frame = nullptr;
+        ctx->d_frame_bytes = 0;
+        CUDA_TRY(ctx, cudaMalloc(&ctx->d_frame, bytes));
+        ctx->d_frame_bytes = bytes;
+    }
+    return renderCommon(ctx, scene, F, frame, ctx->d_frame, ctx->stream, stats, rgb_out);
 }
 
 extern "C" int rtb_render_device(rtb_ctx *ctx, const rtb_scene *scene, const rtb_camera *cam,
@@ -383,6 +411,21 @@ extern "C" int rtb_render_device(rtb_ctx *ctx, const rtb_scene *scene, const rtb
     if (rc != RTB_OK) return rc;
     if (!rgb_device) return fail(ctx, RTB_ERR_INVALID, "rtb_render_device: null output buffer");
     return renderCommon(ctx, scene, F, frame, (float *)rgb_device, stream ? (cudaStream_t)stream : ctx->stream, stats, nullptr);
+}
+
+extern "C" int rtb_host_alloc(size_t bytes, void **out)
+{
+    if (!out) return fail(nullptr, RTB_ERR_INVALID, "rtb_host_alloc: null output pointer");
+    *out = nullptr;
+    cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) return fail(nullptr, RTB_ERR_CUDA, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
+    return RTB_OK;
+}
+
+extern "C" int rtb_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+    return RTB_OK;
 }
 
 extern "C" int rtb_unshard_device(rtb_ctx *ctx, const void *gathered, void *image, int32_t width, int32_t height,

@@ -414,6 +414,8 @@ private:
     uint64_t seed_ = 0;
     rtb_ctx *ctx_ = nullptr;
     std::vector<float> image_;
+    float *pinned_ = nullptr;
+    size_t pinnedFloats_ = 0;
     rtb_stats stats_;
     std::string error_;
 };

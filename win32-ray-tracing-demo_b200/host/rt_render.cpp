@@ -39,6 +39,9 @@ rtb_ctx *CudaRenderer::context()
 
 void CudaRenderer::shutdown()
 {
+    if (pinned_) rtb_host_free(pinned_);
+    pinned_ = nullptr;
+    pinnedFloats_ = 0;
     if (ctx_) rtb_shutdown(ctx_);
     ctx_ = nullptr;
 }
@@ -62,10 +65,21 @@ int CudaRenderer::Render(GeometrySet &scene, PerspectiveCamera &camera, RenderSe
     frame.width = self.width_; frame.height = self.height_; frame.samples = self.samples_;
     frame.seed = self.seed_; frame.rank = 0; frame.world = 1; frame.row_block = 8;
     frame.layout = RTB_LAYOUT_REFERENCE; // Color colors[x*height + y], MainWindow.cpp:276
-    self.image_.assign((size_t)self.width_ * self.height_ * 3, 0.0f);
-    rc = rtb_render(ctx, dev, &cam, &rs, &frame, self.image_.data(), &self.stats_);
+    const size_t floats = (size_t)self.width_ * self.height_ * 3;
+    if (floats > self.pinnedFloats_)
+    { // page-locked staging buffer so the framebuffer read-back runs at full PCIe rate
+        if (self.pinned_) rtb_host_free(self.pinned_);
+        self.pinned_ = nullptr;
+        self.pinnedFloats_ = 0;
+        void *p = nullptr;
+        if (rtb_host_alloc(floats * sizeof(float), &p) != RTB_OK) { rtb_scene_free(ctx, dev); self.error_ = rtb_last_error(nullptr); return -4; }
+        self.pinned_ = (float *)p;
+        self.pinnedFloats_ = floats;
+    }
+    rc = rtb_render(ctx, dev, &cam, &rs, &frame, self.pinned_, &self.stats_);
     rtb_scene_free(ctx, dev);
     if (rc != RTB_OK) { self.error_ = rtb_last_error(ctx); return -3; }
+    self.image_.assign(self.pinned_, self.pinned_ + floats);
     if (progress) progress(self.height_, self.height_);
     const double ms = nowMs() - t0;
     return ms < 1.0 ? 1 : (int)(ms + 0.5);
