@@ -133,7 +133,9 @@ typedef struct rtb_frame {
     int32_t rank, world;  /* shard selector; 0,1 = whole frame                                */
     int32_t row_block;    /* rows per dealt block (multiple of 8; 0 = default 8)              */
     int32_t layout;       /* RTB_LAYOUT_*                                                     */
-    int32_t counters;     /* non-zero: also count triangle tests / traversal steps (slower)   */
+    int32_t counters;     /* 1: also count triangle tests / traversal steps (slower); 2: as 1 and write a
+                             per-pixel cost map (thread cycles, rays, steps + tests) instead of the colour
+                             (profiling aid, Whitted chain kernel only)                          */
 } rtb_frame;
 
 typedef struct rtb_stats {

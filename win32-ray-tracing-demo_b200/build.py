@@ -37,7 +37,8 @@ def build_cuda(force=False, verbose=False):
     src.append(os.path.join(ROOT, "include", "rtb.h"))
     if not force and _newer(CUDA_LIB, src):
         return CUDA_LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", CUDA_LIB, src[0]]
+    extra = os.environ.get("RTB_NVCC_EXTRA", "").split()  # tuning experiments, e.g. -DRTB_CHAIN_MIN_CTAS=6
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", CUDA_LIB, src[0]]
     subprocess.check_call(cmd, cwd=PKG)
     return CUDA_LIB
 

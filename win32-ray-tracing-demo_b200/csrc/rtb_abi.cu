@@ -22,6 +22,11 @@ struct rtb_ctx
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     float *d_frame = nullptr; // grow-only device framebuffer of the host-buffer render call
     size_t d_frame_bytes = 0;
+    // heaviest-first tile scheduling (rtb_kernels.cuh): cost of the last frame and the order derived from it
+    unsigned int *d_cost = nullptr, *d_order = nullptr, *d_hist = nullptr, *d_cursor = nullptr;
+    size_t tile_capacity = 0;
+    bool order_valid = false;
+    long long order_key[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     std::string error;
 };
 
@@ -107,6 +112,11 @@ extern "C" int rtb_shutdown(rtb_ctx *ctx)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->d_frame) cudaFree(ctx->d_frame);
+    if (ctx->d_cost) cudaFreeAsync(ctx->d_cost, ctx->stream);
+    if (ctx->d_order) cudaFreeAsync(ctx->d_order, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->d_hist) cudaFree(ctx->d_hist);
+    if (ctx->d_cursor) cudaFree(ctx->d_cursor);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return RTB_OK;
@@ -331,6 +341,9 @@ static int makeFrame(rtb_ctx *ctx, const rtb_scene *scene, const rtb_camera *cam
     F.width = frame->width; F.height = frame->height; F.samples = frame->samples;
     F.rank = frame->rank; F.world = world; F.row_block = normRowBlock(frame); F.layout = frame->layout;
     F.n_local_rows = (int)rows;
+    F.tiles_x = (frame->width + RTB_TILE_W - 1) / RTB_TILE_W;
+    F.n_tiles = F.tiles_x * (int)((rows + RTB_TILE_H - 1) / RTB_TILE_H);
+    F.cost_map = frame->counters == 2;
     F.seed = frame->seed;
     return RTB_OK;
 }
@@ -338,13 +351,48 @@ static int makeFrame(rtb_ctx *ctx, const rtb_scene *scene, const rtb_camera *cam
 template <class Probe>
 static void launchRender(const rtb_scene *scene, const FrameParams &F, float *out, Counters *counters, cudaStream_t stream)
 {
-    const dim3 grid((F.width + RTB_TILE_W - 1) / RTB_TILE_W, (F.n_local_rows + RTB_TILE_H - 1) / RTB_TILE_H);
+    const int warpsPerCta = RTB_CTA_THREADS / 32;
+    const dim3 grid((unsigned int)((F.n_tiles + warpsPerCta - 1) / warpsPerCta));
     if (F.setting.enable_monte_carlo) k_montecarlo<Probe><<<grid, RTB_CTA_THREADS, 0, stream>>>(scene->d, F, out, counters);
     else if (scene->has_refractive) k_whitted_tree<Probe><<<grid, RTB_CTA_THREADS, 0, stream>>>(scene->d, F, out, counters);
     else k_whitted_chain<Probe><<<grid, RTB_CTA_THREADS, 0, stream>>>(scene->d, F, out, counters);
 }
 
-static int renderCommon(rtb_ctx *ctx, const rtb_scene *scene, const FrameParams &F, const rtb_frame *frame, float *d_out,
+// Attach the tile order learnt from the previous frame of the same geometry (if any) and the cost buffer
+static int prepareTileOrder(rtb_ctx *ctx, FrameParams &F)
+{
+    if ((size_t)F.n_tiles > ctx->tile_capacity)
+    {
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->d_cost) CUDA_TRY(ctx, cudaFreeAsync(ctx->d_cost, ctx->stream));
+        ctx->d_cost = nullptr;
+        if (ctx->d_order) CUDA_TRY(ctx, cudaFreeAsync(ctx->d_order, ctx->stream));
+        ctx->d_order = nullptr;
+        ctx->tile_capacity = 0;
+        ctx->order_valid = false;
+        CUDA_TRY(ctx, cudaMallocAsync(&ctx->d_cost, (size_t)F.n_tiles * sizeof(unsigned int), ctx->stream));
+        CUDA_TRY(ctx, cudaMallocAsync(&ctx->d_order, (size_t)F.n_tiles * sizeof(unsigned int), ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->tile_capacity = (size_t)F.n_tiles;
+    }
+    if (!ctx->d_hist)
+    {
+        CUDA_TRY(ctx, cudaMalloc(&ctx->d_hist, RTB_COST_BUCKETS * sizeof(unsigned int)));
+        CUDA_TRY(ctx, cudaMalloc(&ctx->d_cursor, RTB_COST_BUCKETS * sizeof(unsigned int)));
+        CUDA_TRY(ctx, cudaMemset(ctx->d_hist, 0, RTB_COST_BUCKETS * sizeof(unsigned int)));
+    }
+    const long long key[8] = {F.width, F.height, F.rank, F.world, F.row_block, F.layout, F.setting.enable_monte_carlo, F.n_tiles};
+    if (memcmp(key, ctx->order_key, sizeof(key)) != 0)
+    {
+        ctx->order_valid = false;
+        memcpy(ctx->order_key, key, sizeof(key));
+    }
+    F.order = ctx->order_valid ? ctx->d_order : nullptr;
+    F.cost = ctx->d_cost;
+    return RTB_OK;
+}
+
+static int renderCommon(rtb_ctx *ctx, const rtb_scene *scene, FrameParams &F, const rtb_frame *frame, float *d_out,
                         cudaStream_t stream, rtb_stats *stats, float *h_out)
 {
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -354,14 +402,26 @@ static int renderCommon(rtb_ctx *ctx, const rtb_scene *scene, const FrameParams 
         if (stats) { memset(stats, 0, sizeof(*stats)); }
         return RTB_OK;
     }
+    int rc = prepareTileOrder(ctx, F);
+    if (rc != RTB_OK) return rc;
     if (stats || h_out) CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], stream));
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(Counters), stream));
     if (stats) CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], stream));
+    CUDA_TRY(ctx, cudaPeekAtLastError()); // anything stale is reported here, not blamed on the launch
     if (frame->counters) launchRender<CountProbe>(scene, F, d_out, ctx->d_counters, stream);
     else launchRender<NoProbe>(scene, F, d_out, ctx->d_counters, stream);
     CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cudaEventRecord(scene->last_use, stream));
     if (stats) CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], stream));
+    { // heaviest-first order for the next frame of this geometry: counting sort of the recorded tile costs
+        int blocks = (F.n_tiles + 1023) / 1024;
+        if (blocks > 296) blocks = 296;
+        k_cost_histogram<<<blocks, 256, 0, stream>>>(ctx->d_cost, F.n_tiles, ctx->d_hist);
+        k_cost_offsets<<<1, 32, 0, stream>>>(ctx->d_hist, ctx->d_cursor);
+        k_cost_scatter<<<blocks, 256, 0, stream>>>(ctx->d_cost, F.n_tiles, ctx->d_cursor, ctx->d_order);
+        CUDA_TRY(ctx, cudaGetLastError());
+        ctx->order_valid = true;
+    }
     if (h_out) CUDA_TRY(ctx, cudaMemcpyAsync(h_out, d_out, bytes, cudaMemcpyDeviceToHost, stream));
     if (stats || h_out)
     {
@@ -376,7 +436,7 @@ static int renderCommon(rtb_ctx *ctx, const rtb_scene *scene, const FrameParams 
             stats->n_local_rows = F.n_local_rows;
             CUDA_TRY(ctx, cudaEventElapsedTime(&stats->kernel_ms, ctx->ev[1], ctx->ev[2]));
             CUDA_TRY(ctx, cudaEventElapsedTime(&stats->total_ms, ctx->ev[0], ctx->ev[3]));
-            stats->n_launches = 1;
+            stats->n_launches = 4; // render + 3 tile-order kernels
         }
     }
     return RTB_OK;
@@ -393,7 +453,7 @@ extern "C" int rtb_render(rtb_ctx *ctx, const rtb_scene *scene, const rtb_camera
     const size_t bytes = (size_t)F.n_local_rows * F.width * 3 * sizeof(float);
     if (bytes > ctx->d_frame_bytes)
     {
-        if (ctx->d_frame) cudaFree(ctx->d_frame);
+        if (ctx->d_frame) CUDA_TRY(ctx, cudaFree(ctx->d_frame));
         ctx->d_frame = nullptr;
         ctx->d_frame_bytes = 0;
         CUDA_TRY(ctx, cudaMalloc(&ctx->d_frame, bytes));
@@ -462,6 +522,8 @@ extern "C" int rtb_trace_primary(rtb_ctx *ctx, const rtb_scene *scene, const rtb
     FrameParams F;
     memset(&F, 0, sizeof(F));
     F.cam = *cam; F.width = width; F.height = height; F.rank = 0; F.world = 1; F.row_block = 8; F.n_local_rows = height;
+    F.tiles_x = (width + RTB_TILE_W - 1) / RTB_TILE_W;
+    F.n_tiles = F.tiles_x * ((height + RTB_TILE_H - 1) / RTB_TILE_H);
     const size_t n = (size_t)width * height;
     DevBuf<int> d_id, d_len, d_buf;
     DevBuf<float> d_t;
@@ -471,7 +533,7 @@ extern "C" int rtb_trace_primary(rtb_ctx *ctx, const rtb_scene *scene, const rtb
     if (seq_len) CUDA_TRY(ctx, d_len.alloc(n));
     if (seq_hash) CUDA_TRY(ctx, d_hash.alloc(n));
     if (seq_buf) CUDA_TRY(ctx, d_buf.alloc(n * seq_cap));
-    const dim3 grid((width + RTB_TILE_W - 1) / RTB_TILE_W, (height + RTB_TILE_H - 1) / RTB_TILE_H);
+    const dim3 grid((unsigned int)((F.n_tiles + RTB_CTA_THREADS / 32 - 1) / (RTB_CTA_THREADS / 32)));
     k_trace_primary<<<grid, RTB_CTA_THREADS, 0, ctx->stream>>>(scene->d, F, d_id.p, d_t.p, d_len.p, d_hash.p, d_buf.p, seq_cap);
     CUDA_TRY(ctx, cudaGetLastError());
     if (hit_id) CUDA_TRY(ctx, cudaMemcpyAsync(hit_id, d_id.p, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));

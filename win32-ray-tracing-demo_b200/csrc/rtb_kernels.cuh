@@ -1,6 +1,14 @@
-// rtb_kernels.cuh -- the render / trace kernels (sm_100a).  One thread owns one pixel; a warp
-// owns an 8x4 pixel tile, a 256-thread CTA a 32x8 tile, so primary rays of a warp are coherent
-// and a CTA row band coincides with the 8-row granularity of the tile-row sharding.
+// rtb_kernels.cuh -- the render / trace kernels (sm_100a).
+//
+// Work decomposition: one thread owns one pixel, one WARP owns an 8x4 pixel tile (coherent primary
+// rays, 4 x 96-byte row segments on the framebuffer store).  Tiles are the scheduling unit: warp w of
+// the launch renders tile order[w].  Pixel cost on the tunnel scenes is extremely skewed -- the
+// ~0.1 % of tiles around the vanishing point run 21-ray reflection chains that take ~60 x the median
+// tile and, scheduled in raster order, ARE the kernel's critical path (profiles/r01_cost_map.md).
+// So every render records the cycles each tile took and a counting sort turns that into a
+// heaviest-first order for the next frame rendered with the same frame geometry (temporal
+// coherence; the first frame of a geometry runs in raster order).  The order only changes
+// scheduling: every pixel is computed by the same code whatever the order, so images are identical.
 #pragma once
 #include "rtb_device.cuh"
 
@@ -13,19 +21,29 @@ struct FrameParams
     int width, height, samples;
     int rank, world, row_block, layout;
     int n_local_rows;
+    int cost_map;
+    int tiles_x, n_tiles;
+    const unsigned int *order; // [n_tiles] tile ids, heaviest first; nullptr = raster order
+    unsigned int *cost;        // [n_tiles] cycles >> 6 spent on each tile by this launch; may be nullptr
     unsigned long long seed;
 };
 
-#define RTB_CTA_THREADS 256
-#define RTB_TILE_W 32
-#define RTB_TILE_H 8
+#define RTB_CTA_THREADS 128 // 4 warp tiles per CTA: small CTAs retire (and free registers) early
+#define RTB_TILE_W 8
+#define RTB_TILE_H 4
+#define RTB_COST_BUCKETS 128
 
-// thread -> (x, local row, global y); false when outside this rank's shard
-__device__ __forceinline__ bool pixelOfThread(const FrameParams &F, int &x, int &lr, int &y)
+// warp -> tile -> (x, local row, global y); false when the thread has no pixel
+__device__ __forceinline__ bool pixelOfThread(const FrameParams &F, int &x, int &lr, int &y, unsigned int &tile)
 {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    x = blockIdx.x * RTB_TILE_W + (warp & 3) * 8 + (lane & 7);
-    lr = blockIdx.y * RTB_TILE_H + (warp >> 2) * 4 + (lane >> 3);
+    const unsigned int w = blockIdx.x * (RTB_CTA_THREADS / 32) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    tile = 0;
+    if (w >= (unsigned int)F.n_tiles) return false;
+    tile = F.order ? __ldg(F.order + w) : w;
+    const int ty = tile / F.tiles_x, tx = tile - ty * F.tiles_x;
+    x = tx * RTB_TILE_W + (lane & 7);
+    lr = ty * RTB_TILE_H + (lane >> 3);
     const int lb = lr / F.row_block;
     y = (lb * F.world + F.rank) * F.row_block + (lr - lb * F.row_block);
     return x < F.width && lr < F.n_local_rows && y < F.height;
@@ -36,28 +54,67 @@ __device__ __forceinline__ size_t pixelSlot(const FrameParams &F, int x, int lr,
     return F.layout == RTB_LAYOUT_REFERENCE ? ((size_t)x * F.height + y) : ((size_t)lr * F.width + x);
 }
 
-// CTA-level reduction of the per-thread counters, one atomic triple per CTA
-__device__ __forceinline__ void flushCounters(Counters *g, unsigned int rays, unsigned int tris, unsigned int steps)
+// per-warp epilogue: record the tile's cost, add the warp's counters to the frame totals
+__device__ __forceinline__ void finishWarp(const FrameParams &F, Counters *g, unsigned int tile, long long t_start,
+                                           unsigned int rays, unsigned int tris, unsigned int steps)
 {
-    __shared__ unsigned int s[3];
-    if (threadIdx.x < 3) s[threadIdx.x] = 0;
-    __syncthreads();
+    __syncwarp();
     rays = __reduce_add_sync(0xffffffffu, rays);
     tris = __reduce_add_sync(0xffffffffu, tris);
     steps = __reduce_add_sync(0xffffffffu, steps);
     if ((threadIdx.x & 31) == 0)
     {
-        atomicAdd(&s[0], rays);
-        if (tris) atomicAdd(&s[1], tris);
-        if (steps) atomicAdd(&s[2], steps);
+        const unsigned int w = blockIdx.x * (RTB_CTA_THREADS / 32) + (threadIdx.x >> 5);
+        if (F.cost && w < (unsigned int)F.n_tiles)
+        {
+            const long long dt = (clock64() - t_start) >> 6;
+            F.cost[tile] = dt > 0xffffffffll ? 0xffffffffu : (unsigned int)dt;
+        }
+        if (rays) atomicAdd(&g->rays, (unsigned long long)rays);
+        if (tris) atomicAdd(&g->tris, (unsigned long long)tris);
+        if (steps) atomicAdd(&g->steps, (unsigned long long)steps);
     }
+}
+
+// ---- heaviest-first tile order from the recorded costs: a counting sort over 128 log-scale buckets ----
+__device__ __forceinline__ int costBucket(unsigned int c)
+{ // 4 buckets per power of two, bucket 127 = heaviest
+    if (c < 4) return (int)c;
+    const int e = 31 - __clz(c);
+    return e * 4 + (int)((c >> (e - 2)) & 3u) - 4;
+}
+
+__global__ void k_cost_histogram(const unsigned int *__restrict__ cost, int n, unsigned int *__restrict__ hist)
+{
+    __shared__ unsigned int h[RTB_COST_BUCKETS];
+    for (int i = threadIdx.x; i < RTB_COST_BUCKETS; i += blockDim.x) h[i] = 0;
     __syncthreads();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) atomicAdd(&h[costBucket(cost[i])], 1u);
+    __syncthreads();
+    for (int i = threadIdx.x; i < RTB_COST_BUCKETS; i += blockDim.x)
+        if (h[i]) atomicAdd(&hist[i], h[i]);
+}
+
+// one warp: hist[] -> descending exclusive offsets in cursor[], hist[] cleared for the next frame
+__global__ void k_cost_offsets(unsigned int *__restrict__ hist, unsigned int *__restrict__ cursor)
+{
     if (threadIdx.x == 0)
     {
-        atomicAdd(&g->rays, (unsigned long long)s[0]);
-        if (s[1]) atomicAdd(&g->tris, (unsigned long long)s[1]);
-        if (s[2]) atomicAdd(&g->steps, (unsigned long long)s[2]);
+        unsigned int run = 0;
+        for (int b = RTB_COST_BUCKETS - 1; b >= 0; b--)
+        {
+            cursor[b] = run;
+            run += hist[b];
+            hist[b] = 0;
+        }
     }
+}
+
+__global__ void k_cost_scatter(const unsigned int *__restrict__ cost, int n, unsigned int *__restrict__ cursor,
+                               unsigned int *__restrict__ order)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        order[atomicAdd(&cursor[costBucket(cost[i])], 1u)] = (unsigned int)i;
 }
 
 template <class Probe> struct ProbeCounts
@@ -78,14 +135,19 @@ template <> struct ProbeCounts<CountProbe>
 // recursive evaluation `diffusive*d + reflective*r + refractive*t`.
 // ---------------------------------------------------------------------------------------------
 #define RTB_MAX_DEPTH 100 // the reference's hard recursion cap (MainWindow.cpp:86)
+#ifndef RTB_CHAIN_MIN_CTAS
+#define RTB_CHAIN_MIN_CTAS 8 // 64 registers: measured best (5.9 ms vs 7.5 ms at 4) on the 4K SAH frame
+#endif
 
 template <class Probe>
-__global__ void __launch_bounds__(RTB_CTA_THREADS)
+__global__ void __launch_bounds__(RTB_CTA_THREADS, RTB_CHAIN_MIN_CTAS)
 k_whitted_chain(const __grid_constant__ DScene S, const __grid_constant__ FrameParams F, float *__restrict__ out,
                 Counters *__restrict__ counters)
 {
     int x, lr, y;
-    const bool active = pixelOfThread(F, x, lr, y);
+    unsigned int tile;
+    const long long t_start = clock64();
+    const bool active = pixelOfThread(F, x, lr, y, tile);
     unsigned int rays = 0;
     Probe pr;
     if (active)
@@ -126,9 +188,14 @@ k_whitted_chain(const __grid_constant__ DScene S, const __grid_constant__ FrameP
             c = v3(f.x, f.y, f.z) + c * f.w + zero * 0.0f;
         }
         float *o = out + 3 * pixelSlot(F, x, lr, y);
-        o[0] = c.x; o[1] = c.y; o[2] = c.z;
+        if (F.cost_map)
+        { // profiling aid: (thread cycles, rays, traversal steps + triangle tests) instead of the colour
+            o[0] = (float)(clock64() - t_start); o[1] = (float)rays;
+            o[2] = (float)(ProbeCounts<Probe>::tris(pr) + ProbeCounts<Probe>::steps(pr));
+        }
+        else { o[0] = c.x; o[1] = c.y; o[2] = c.z; }
     }
-    flushCounters(counters, rays, ProbeCounts<Probe>::tris(pr), ProbeCounts<Probe>::steps(pr));
+    finishWarp(F, counters, tile, t_start, rays, ProbeCounts<Probe>::tris(pr), ProbeCounts<Probe>::steps(pr));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -147,7 +214,9 @@ k_whitted_tree(const __grid_constant__ DScene S, const __grid_constant__ FramePa
                Counters *__restrict__ counters)
 {
     int x, lr, y;
-    const bool active = pixelOfThread(F, x, lr, y);
+    unsigned int tile;
+    const long long t_start = clock64();
+    const bool active = pixelOfThread(F, x, lr, y, tile);
     unsigned int rays = 0;
     Probe pr;
     if (active)
@@ -196,7 +265,7 @@ k_whitted_tree(const __grid_constant__ DScene S, const __grid_constant__ FramePa
         float *o = out + 3 * pixelSlot(F, x, lr, y);
         o[0] = c.x; o[1] = c.y; o[2] = c.z;
     }
-    flushCounters(counters, rays, ProbeCounts<Probe>::tris(pr), ProbeCounts<Probe>::steps(pr));
+    finishWarp(F, counters, tile, t_start, rays, ProbeCounts<Probe>::tris(pr), ProbeCounts<Probe>::steps(pr));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -216,7 +285,9 @@ k_montecarlo(const __grid_constant__ DScene S, const __grid_constant__ FramePara
              Counters *__restrict__ counters)
 {
     int x, lr, y;
-    const bool active = pixelOfThread(F, x, lr, y);
+    unsigned int tile;
+    const long long t_start = clock64();
+    const bool active = pixelOfThread(F, x, lr, y, tile);
     unsigned int rays = 0;
     Probe pr;
     if (active)
@@ -315,7 +386,7 @@ k_montecarlo(const __grid_constant__ DScene S, const __grid_constant__ FramePara
         float *o = out + 3 * pixelSlot(F, x, lr, y);
         o[0] = acc.x; o[1] = acc.y; o[2] = acc.z;
     }
-    flushCounters(counters, rays, ProbeCounts<Probe>::tris(pr), ProbeCounts<Probe>::steps(pr));
+    finishWarp(F, counters, tile, t_start, rays, ProbeCounts<Probe>::tris(pr), ProbeCounts<Probe>::steps(pr));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -327,7 +398,8 @@ k_trace_primary(const __grid_constant__ DScene S, const __grid_constant__ FrameP
                 int *__restrict__ seq_buf, int seq_cap)
 {
     int x, lr, y;
-    if (!pixelOfThread(F, x, lr, y)) return;
+    unsigned int tile;
+    if (!pixelOfThread(F, x, lr, y, tile)) return;
     const float dx = 1.0f / F.height, dy = 1.0f / F.height;
     const float sx = (x + 0.5f) * dx, sy = 1 - (y + 0.5f) * dy;
     const Ray r = generateRay(F.cam, sx, sy);
