@@ -202,7 +202,7 @@ def run_b200(args, wl_name):
             dscene.render_device(scene.camera, scene.setting, frame, image.data_ptr(), stream)
         else:
             dscene.render_device(scene.camera, scene.setting, frame, local_buf.data_ptr(), stream)
-            dist.all_gather_into_tensor(gathered, local_buf)
+            dist.all_gather_into_tensor(gathered.view(world * rows_max, W, 3), local_buf)
             rtb200.unshard_device(ctx, gathered.data_ptr(), image.data_ptr(), W, H, world, ROW_BLOCK, rows_max, stream)
 
     launches_per_step = 4 if world == 1 else 5  # render + 3 tile-order kernels (+ unshard)
@@ -238,7 +238,7 @@ def run_b200(args, wl_name):
             kev[i][0].record()
             dscene.render_device(scene.camera, scene.setting, frame, local_buf.data_ptr(), stream)
             kev[i][1].record()
-            dist.all_gather_into_tensor(gathered, local_buf)
+            dist.all_gather_into_tensor(gathered.view(world * rows_max, W, 3), local_buf)
             rtb200.unshard_device(ctx, gathered.data_ptr(), image.data_ptr(), W, H, world, ROW_BLOCK, rows_max, stream)
         ev[i][1].record()
     barrier()

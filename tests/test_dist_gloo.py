@@ -1,0 +1,76 @@
+"""N > 1 host logic on CPU (gloo, world_size 2 and 3): the tile-row shard arithmetic of include/rtb.h
+(rtb_shard_rows, block-cyclic dealing), the padded all-gather layout bench.py uses, and the row order
+rtb_unshard_device restores.  No GPU kernels run here; each rank fills its shard with a function of the
+global row index so the reassembled frame can be checked exactly."""
+import os
+import socket
+import subprocess
+import sys
+import textwrap
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = textwrap.dedent("""
+    import os, sys
+    sys.path.insert(0, %r)
+    import numpy as np, torch, torch.distributed as dist
+    import rtb200
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    W, H, RB = 40, 300, 16
+    frame = rtb200.make_frame(W, H, rank=rank, world=world, row_block=RB)
+    rows = rtb200.shard_rows(frame)                         # C ABI: rtb_shard_rows
+    ys = rtb200.shard_row_indices(H, rank, world, RB)
+    assert rows == len(ys)
+    t = torch.tensor([rows], dtype=torch.int64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    rows_max = int(t.item())
+    local = torch.zeros((rows_max, W, 3), dtype=torch.float32)
+    xs = torch.arange(W, dtype=torch.float32)
+    for lr, y in enumerate(ys):                              # "render": pixel value encodes (y, x, channel)
+        for c in range(3):
+            local[lr, :, c] = float(y) * 1000 + xs + c * 0.25
+    gathered = torch.zeros((world, rows_max, W, 3), dtype=torch.float32)
+    dist.all_gather_into_tensor(gathered.view(world * rows_max, W, 3), local)
+    # the permutation rtb_unshard_device applies (k_unshard): row y lives at [b %% world][ (b // world)*RB + y - b*RB ]
+    image = torch.empty((H, W, 3), dtype=torch.float32)
+    for y in range(H):
+        b = y // RB
+        image[y] = gathered[b %% world, (b // world) * RB + (y - b * RB)]
+    expect = torch.arange(H, dtype=torch.float32)[:, None, None] * 1000 + xs[None, :, None] + torch.tensor([0, 0.25, 0.5])[None, None, :]
+    assert torch.equal(image, expect), "reassembled frame differs"
+    total = torch.tensor([rows], dtype=torch.int64)
+    dist.all_reduce(total)
+    assert int(total.item()) == H
+    dist.barrier()
+    if rank == 0:
+        print("GLOO_OK", world, rows_max)
+    dist.destroy_process_group()
+""")
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_frame_reassembles_over_gloo(tmp_path, world):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER % ROOT)
+    port = _free_port()
+    procs = []
+    for rank in range(world):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank),
+                   MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), CUDA_VISIBLE_DEVICES="")
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+    assert any("GLOO_OK" in o for o in outs)
