@@ -10,7 +10,7 @@
 #include <string>
 #include <vector>
 
-#include "rtb_kernels.cuh"
+#include "rtb_chain_sm.cuh"
 
 using namespace rtb;
 
@@ -20,10 +20,12 @@ struct rtb_ctx
     cudaStream_t stream = nullptr;
     Counters *d_counters = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t aux = nullptr;                 // high-priority side stream of the latency-critical tiles
+    cudaEvent_t fork = nullptr, join = nullptr;
     float *d_frame = nullptr; // grow-only device framebuffer of the host-buffer render call
     size_t d_frame_bytes = 0;
     // heaviest-first tile scheduling (rtb_kernels.cuh): cost of the last frame and the order derived from it
-    unsigned int *d_cost = nullptr, *d_order = nullptr, *d_hist = nullptr, *d_cursor = nullptr;
+    unsigned int *d_cost = nullptr, *d_order = nullptr, *d_hist = nullptr, *d_cursor = nullptr, *d_heavy = nullptr;
     size_t tile_capacity = 0;
     bool order_valid = false;
     long long order_key[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -97,6 +99,13 @@ extern "C" int rtb_init(int device, rtb_ctx **out)
         unsigned long long keep = ~0ull;
         CUDA_TRY(ctx, cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
     }
+    {
+        int lo = 0, hi = 0;
+        CUDA_TRY(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CUDA_TRY(ctx, cudaStreamCreateWithPriority(&ctx->aux, cudaStreamNonBlocking, hi));
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->fork, cudaEventDisableTiming));
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->join, cudaEventDisableTiming));
+    }
     CUDA_TRY(ctx, cudaMalloc(&ctx->d_counters, sizeof(Counters)));
     for (int i = 0; i < 4; i++) CUDA_TRY(ctx, cudaEventCreate(&ctx->ev[i]));
     *out = ctx;
@@ -110,6 +119,9 @@ extern "C" int rtb_shutdown(rtb_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < 4; i++)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->aux) { cudaStreamSynchronize(ctx->aux); cudaStreamDestroy(ctx->aux); }
+    if (ctx->fork) cudaEventDestroy(ctx->fork);
+    if (ctx->join) cudaEventDestroy(ctx->join);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->d_frame) cudaFree(ctx->d_frame);
     if (ctx->d_cost) cudaFreeAsync(ctx->d_cost, ctx->stream);
@@ -117,6 +129,7 @@ extern "C" int rtb_shutdown(rtb_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     if (ctx->d_hist) cudaFree(ctx->d_hist);
     if (ctx->d_cursor) cudaFree(ctx->d_cursor);
+    if (ctx->d_heavy) cudaFree(ctx->d_heavy);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return RTB_OK;
@@ -349,13 +362,34 @@ static int makeFrame(rtb_ctx *ctx, const rtb_scene *scene, const rtb_camera *cam
 }
 
 template <class Probe>
-static void launchRender(const rtb_scene *scene, const FrameParams &F, float *out, Counters *counters, cudaStream_t stream)
+static int launchRender(rtb_ctx *ctx, const rtb_scene *scene, FrameParams &F, float *out, Counters *counters, cudaStream_t stream)
 {
     const int warpsPerCta = RTB_CTA_THREADS / 32;
     const dim3 grid((unsigned int)((F.n_tiles + warpsPerCta - 1) / warpsPerCta));
+    static const bool resumable = !(getenv("RTB_CHAIN_SM") && atoi(getenv("RTB_CHAIN_SM")) == 0); // A/B switch for profiling
+    const int accel = scene->d.accel;
+    const bool grid_accel = accel == RTB_ACCEL_REGULAR_GRID || accel == RTB_ACCEL_FLAT_GRID;
+    const bool kd_accel = accel == RTB_ACCEL_KD_MEDIAN || accel == RTB_ACCEL_KD_SAH;
+    F.skip_heavy = 0;
     if (F.setting.enable_monte_carlo) k_montecarlo<Probe><<<grid, RTB_CTA_THREADS, 0, stream>>>(scene->d, F, out, counters);
     else if (scene->has_refractive) k_whitted_tree<Probe><<<grid, RTB_CTA_THREADS, 0, stream>>>(scene->d, F, out, counters);
+    else if (resumable && scene->has_tunnel && grid_accel)
+        k_whitted_chain_sm<Probe, true><<<grid, RTB_CTA_THREADS, 0, stream>>>(scene->d, F, out, counters);
+    else if (resumable && scene->has_tunnel && kd_accel && F.order)
+    { // k-d with a known tile order: the latency-critical head of the order runs the resumable walk on the
+      // high-priority side stream, concurrently with the per-ray walk of all other tiles
+        F.skip_heavy = 1;
+        const int heavyCap = F.n_tiles / RTB_HEAVY_FRACTION + 1; // upper bound of *n_heavy (k_cost_offsets)
+        const dim3 hgrid((unsigned int)((heavyCap + warpsPerCta - 1) / warpsPerCta));
+        CUDA_TRY(ctx, cudaEventRecord(ctx->fork, stream));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->aux, ctx->fork, 0));
+        k_whitted_chain_sm<Probe, false><<<hgrid, RTB_CTA_THREADS, 0, ctx->aux>>>(scene->d, F, out, counters);
+        CUDA_TRY(ctx, cudaEventRecord(ctx->join, ctx->aux));
+        k_whitted_chain<Probe><<<grid, RTB_CTA_THREADS, 0, stream>>>(scene->d, F, out, counters);
+        CUDA_TRY(ctx, cudaStreamWaitEvent(stream, ctx->join, 0));
+    }
     else k_whitted_chain<Probe><<<grid, RTB_CTA_THREADS, 0, stream>>>(scene->d, F, out, counters);
+    return RTB_OK;
 }
 
 // Attach the tile order learnt from the previous frame of the same geometry (if any) and the cost buffer
@@ -380,6 +414,8 @@ static int prepareTileOrder(rtb_ctx *ctx, FrameParams &F)
         CUDA_TRY(ctx, cudaMalloc(&ctx->d_hist, RTB_COST_BUCKETS * sizeof(unsigned int)));
         CUDA_TRY(ctx, cudaMalloc(&ctx->d_cursor, RTB_COST_BUCKETS * sizeof(unsigned int)));
         CUDA_TRY(ctx, cudaMemset(ctx->d_hist, 0, RTB_COST_BUCKETS * sizeof(unsigned int)));
+        CUDA_TRY(ctx, cudaMalloc(&ctx->d_heavy, sizeof(unsigned int)));
+        CUDA_TRY(ctx, cudaMemset(ctx->d_heavy, 0, sizeof(unsigned int)));
     }
     const long long key[8] = {F.width, F.height, F.rank, F.world, F.row_block, F.layout, F.setting.enable_monte_carlo, F.n_tiles};
     if (memcmp(key, ctx->order_key, sizeof(key)) != 0)
@@ -389,6 +425,7 @@ static int prepareTileOrder(rtb_ctx *ctx, FrameParams &F)
     }
     F.order = ctx->order_valid ? ctx->d_order : nullptr;
     F.cost = ctx->d_cost;
+    F.n_heavy = ctx->d_heavy;
     return RTB_OK;
 }
 
@@ -408,8 +445,9 @@ static int renderCommon(rtb_ctx *ctx, const rtb_scene *scene, FrameParams &F, co
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(Counters), stream));
     if (stats) CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], stream));
     CUDA_TRY(ctx, cudaPeekAtLastError()); // anything stale is reported here, not blamed on the launch
-    if (frame->counters) launchRender<CountProbe>(scene, F, d_out, ctx->d_counters, stream);
-    else launchRender<NoProbe>(scene, F, d_out, ctx->d_counters, stream);
+    if (frame->counters) rc = launchRender<CountProbe>(ctx, scene, F, d_out, ctx->d_counters, stream);
+    else rc = launchRender<NoProbe>(ctx, scene, F, d_out, ctx->d_counters, stream);
+    if (rc != RTB_OK) return rc;
     CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cudaEventRecord(scene->last_use, stream));
     if (stats) CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], stream));
@@ -417,7 +455,7 @@ static int renderCommon(rtb_ctx *ctx, const rtb_scene *scene, FrameParams &F, co
         int blocks = (F.n_tiles + 1023) / 1024;
         if (blocks > 296) blocks = 296;
         k_cost_histogram<<<blocks, 256, 0, stream>>>(ctx->d_cost, F.n_tiles, ctx->d_hist);
-        k_cost_offsets<<<1, 32, 0, stream>>>(ctx->d_hist, ctx->d_cursor);
+        k_cost_offsets<<<1, 32, 0, stream>>>(ctx->d_hist, ctx->d_cursor, ctx->d_heavy, F.n_tiles);
         k_cost_scatter<<<blocks, 256, 0, stream>>>(ctx->d_cost, F.n_tiles, ctx->d_cursor, ctx->d_order);
         CUDA_TRY(ctx, cudaGetLastError());
         ctx->order_valid = true;
@@ -436,7 +474,7 @@ static int renderCommon(rtb_ctx *ctx, const rtb_scene *scene, FrameParams &F, co
             stats->n_local_rows = F.n_local_rows;
             CUDA_TRY(ctx, cudaEventElapsedTime(&stats->kernel_ms, ctx->ev[1], ctx->ev[2]));
             CUDA_TRY(ctx, cudaEventElapsedTime(&stats->total_ms, ctx->ev[0], ctx->ev[3]));
-            stats->n_launches = 4; // render + 3 tile-order kernels
+            stats->n_launches = F.skip_heavy ? 5 : 4; // render (+ heavy-tile kernel) + 3 tile-order kernels
         }
     }
     return RTB_OK;

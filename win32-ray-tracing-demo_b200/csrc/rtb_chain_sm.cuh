@@ -1,0 +1,288 @@
+// rtb_chain_sm.cuh -- Whitted reflection chains with a RESUMABLE accelerator traversal (sm_100a).
+//
+// Same arithmetic and same results as k_whitted_chain (rtb_kernels.cuh) -- the k-d walk is reference
+// Tunnel.cpp:1163-1297, the grid walk Tunnel.cpp:819-970, shading MainWindow.cpp:69-143 -- but the
+// control flow is one per-lane loop over the states
+//      STEP   advance the accelerator (k-d: one inner node or leaf entry; grid: one cell)
+//      LEAF   test triangles of the current leaf / cell
+//      SHADE  close the ray (top-level geometries + tunnel result), shade, fold, spawn the reflection
+// A lane that has finished a ray shades it and starts the next ray of ITS OWN chain at once instead of
+// waiting, at a per-ray reconvergence point, for the slowest traversal in the warp.  On the tunnel
+// frames the tiles at the vanishing point run 21-ray chains whose per-ray costs are heavy-tailed; with
+// per-ray reconvergence the warp pays the maximum over its lanes for every bounce
+// (profiles/r01_cost_map.md), which is the critical path of the 8-GPU frame.
+#pragma once
+#include "rtb_kernels.cuh"
+
+namespace rtb {
+
+#ifndef RTB_SM_STEP_BURST
+#define RTB_SM_STEP_BURST 1000 // accelerator steps taken before the warp looks at the other states
+#endif
+#ifndef RTB_SM_LEAF_BURST
+#define RTB_SM_LEAF_BURST 1000 // triangle tests per visit of the LEAF state
+#endif
+
+enum { SM_STEP = 0, SM_LEAF = 1, SM_SHADE = 2, SM_DONE = 3 };
+
+#ifndef RTB_SM_MIN_CTAS
+#define RTB_SM_MIN_CTAS 6
+#endif
+
+template <class Probe, bool GRID>
+__global__ void __launch_bounds__(RTB_CTA_THREADS, GRID ? RTB_CHAIN_MIN_CTAS : RTB_SM_MIN_CTAS)
+k_whitted_chain_sm(const __grid_constant__ DScene S, const __grid_constant__ FrameParams F, float *__restrict__ out,
+                   Counters *__restrict__ counters)
+{
+    int x, lr, y;
+    unsigned int tile;
+    const long long t_start = clock64();
+    const bool active = pixelOfThread(F, x, lr, y, tile);
+    unsigned int rays = 0;
+    Probe pr;
+    // Who runs this kernel?  Grids: every tile (measured 1.75x faster than the per-ray walk on the whole
+    // frame).  k-d trees: the per-ray walk (k_whitted_chain) issues ~15 % fewer instructions, so it renders
+    // the bulk of the frame; this kernel is launched next to it on a second stream and takes only the
+    // latency-critical tiles, i.e. the first *n_heavy entries of the heaviest-first order.
+    if (!GRID)
+    {
+        const unsigned int warpIndex = blockIdx.x * (RTB_CTA_THREADS / 32) + (threadIdx.x >> 5);
+        if (warpIndex >= __ldg(F.n_heavy)) return;
+    }
+    if (active)
+    {
+        const float dx = 1.0f / F.height, dy = 1.0f / F.height;
+        const float sx = (x + 0.5f) * dx, sy = 1 - (y + 0.5f) * dy;
+        Ray r = generateRay(F.cam, sx, sy);
+        float4 fold[RTB_MAX_DEPTH + 1];
+        int4 stack[GRID ? 1 : RTB_KD_STACK];
+        int nfold = 0, depth = 0;
+        V3 c = v3(0, 0, 0);
+        const V3 zero = v3(0, 0, 0);
+
+        // ---- traversal state ----
+        int st;
+        // k-d (see kdIntersect)
+        float enT = 0, exT = 0;
+        V3 enP = zero, exP = zero;
+        int enPt = 0, exPt = 1, exNode = -1, exPrev = 0, cur = 0;
+        // grid (see gridIntersect)
+        int ci = 0, cj = 0, ck = 0;
+        float cd = 0;
+        V3 cp = zero;
+        bool px = false, py = false, pz = false;
+        // leaf / cell list
+        unsigned int li = 0, lend = 0;
+        float lo = 0, hi = 0, minD = FLT_MAX;
+        int hitTri = -1;
+        bool tunnelHit = false;
+
+        // start the accelerator walk of ray r (reference Tunnel.cpp:1171-1197 / 833-860)
+        auto beginRay = [&]() {
+            rays++;
+            tunnelHit = false;
+            hitTri = -1;
+            minD = FLT_MAX;
+            if (GRID)
+            {
+                if (r.o.x < S.g_origin.x || r.o.x > S.g_far.x || r.o.y < S.g_origin.y || r.o.y > S.g_far.y ||
+                    r.o.z < S.g_origin.z || r.o.z > S.g_far.z)
+                {
+                    float entry, exit;
+                    if (!boxIntersect(S.g_origin, S.g_extent, r, entry, exit)) { st = SM_SHADE; return; }
+                    cd = entry;
+                    cp = at(r, entry);
+                    indexInGrid(S, cp, ci, cj, ck);
+                }
+                else
+                {
+                    cp = r.o;
+                    cd = 0;
+                    indexInGrid(S, r.o, ci, cj, ck);
+                }
+                px = r.d.x > 0; py = r.d.y > 0; pz = r.d.z > 0;
+                st = SM_STEP;
+            }
+            else
+            {
+                float a, b;
+                if (!boxIntersect(S.kd_min, S.kd_size, r, a, b)) { st = SM_SHADE; return; }
+                enT = a;
+                enP = (a >= 0) ? (r.o + r.d * a) : r.o;
+                enPt = 0;
+                exPt = 1; exT = b; exP = r.o + r.d * b; exNode = -1; exPrev = 0;
+                stack[1] = make_int4(-1, __float_as_int(b), 0, 3);
+                cur = 0;
+                st = SM_STEP;
+            }
+        };
+
+        // grid: leave the current cell (Tunnel.cpp:885-966)
+        auto gridAdvance = [&]() {
+            float ddx, ddy, ddz;
+            if (px) ddx = ((S.g_origin.x + (ci + 1) * S.g_cell.x) - cp.x) / r.d.x;
+            else ddx = (cp.x - (S.g_origin.x + ci * S.g_cell.x)) / -r.d.x;
+            if (py) ddy = ((S.g_origin.y + (cj + 1) * S.g_cell.y) - cp.y) / r.d.y;
+            else ddy = (cp.y - (S.g_origin.y + cj * S.g_cell.y)) / -r.d.y;
+            if (pz) ddz = ((S.g_origin.z + (ck + 1) * S.g_cell.z) - cp.z) / r.d.z;
+            else ddz = (cp.z - (S.g_origin.z + ck * S.g_cell.z)) / -r.d.z;
+            if (ddx < ddy && ddx < ddz) { ci += px ? 1 : -1; cd += ddx; }
+            else if (ddy < ddz) { cj += py ? 1 : -1; cd += ddy; }
+            else { ck += pz ? 1 : -1; cd += ddz; }
+            cp = at(r, cd);
+            if (ci < 0 || ci > S.nx - 1 || cj < 0 || cj > S.ny - 1 || ck < 0 || ck > S.nz - 1) st = SM_SHADE; // left the grid: miss
+            else st = SM_STEP;
+        };
+
+        // k-d: the current leaf gave no hit -> pop (Tunnel.cpp:1285-1292)
+        auto kdPop = [&]() {
+            enPt = exPt; enT = exT; enP = exP;
+            cur = exNode;
+            if (cur == -1) { st = SM_SHADE; return; } // ray leaves the tree: miss
+            exPt = exPrev;
+            const int4 e = stack[exPt];
+            exNode = e.x; exT = __int_as_float(e.y); exPrev = e.w >> 2;
+            exP = kdPoint(r, exT, __int_as_float(e.z), e.w & 3);
+            st = SM_STEP;
+        };
+
+        // the list of the current leaf / cell is exhausted
+        auto listDone = [&]() {
+            if (hitTri >= 0) { tunnelHit = true; st = SM_SHADE; return; }
+            if (GRID) gridAdvance();
+            else kdPop();
+        };
+
+        beginRay();
+        while (st != SM_DONE)
+        {
+            if (st == SM_STEP)
+            {
+#pragma unroll 1
+                for (int burst = 0; burst < RTB_SM_STEP_BURST && st == SM_STEP; burst++)
+                {
+                    if (GRID)
+                    {
+                        const int cell = (ci * S.ny + cj) * S.nz + ck;
+                        pr.step(cell);
+                        const uint2 w = __ldg(S.g_words + ((unsigned int)cell >> 5));
+                        const unsigned int bit = 1u << (cell & 31);
+                        if (w.x & bit)
+                        {
+                            const unsigned int rk = w.y + __popc(w.x & (bit - 1));
+                            li = __ldg(S.g_start + rk);
+                            lend = __ldg(S.g_start + rk + 1);
+                            minD = FLT_MAX; hitTri = -1;
+                            st = SM_LEAF;
+                        }
+                        else gridAdvance();
+                    }
+                    else
+                    {
+                        const uint2 nd = __ldg(S.kd_nodes + cur);
+                        pr.step(cur);
+                        if ((nd.y & 3u) == 3u)
+                        { // leaf: scan its list with the +-0.001 window (Tunnel.cpp:1269-1280)
+                            li = nd.x;
+                            lend = nd.x + (nd.y >> 2);
+                            lo = enT - 0.001f; hi = exT + 0.001f;
+                            minD = FLT_MAX; hitTri = -1;
+                            if (li == lend) kdPop();
+                            else st = SM_LEAF;
+                        }
+                        else
+                        {
+                            const float splitVal = __uint_as_float(nd.x);
+                            const int axis = (int)(nd.y & 3u);
+                            const int right = (int)(nd.y >> 2), left = cur + 1;
+                            const float en = comp(enP, axis), ex = comp(exP, axis);
+                            int farChild = -1;
+                            bool both = false;
+                            if (en <= splitVal)
+                            {
+                                if (ex <= splitVal) cur = left;
+                                else { farChild = right; cur = left; both = true; } // (ex == split is covered by <=, line 1223)
+                            }
+                            else
+                            {
+                                if (splitVal < ex) cur = right;
+                                else { farChild = left; cur = right; both = true; }
+                            }
+                            if (both)
+                            {
+                                const float t = (splitVal - comp(r.o, axis)) / comp(r.d, axis);
+                                const int tmp = exPt++;
+                                if (exPt == enPt) exPt += 1;
+                                exPrev = tmp; exT = t; exNode = farChild;
+                                exP = kdPoint(r, t, splitVal, axis);
+                                stack[exPt] = make_int4(farChild, __float_as_int(t), __float_as_int(splitVal), axis | (tmp << 2));
+                            }
+                        }
+                    }
+                }
+            }
+            if (st == SM_LEAF)
+            {
+#pragma unroll 1
+                for (int burst = 0; burst < RTB_SM_LEAF_BURST && st == SM_LEAF; burst++)
+                {
+                    const uint32_t idx = __ldg((GRID ? S.g_tris : S.kd_tris) + li);
+                    const TriData T = loadTri(S.tri, idx);
+                    pr.tri();
+                    float t;
+                    if (triIntersectT<true>(T, r, t) && (GRID || (t >= lo && t <= hi)) && t < minD)
+                    {
+                        minD = t;
+                        hitTri = (int)idx;
+                    }
+                    if (++li == lend) listDone();
+                }
+            }
+            if (st == SM_SHADE)
+            {
+                // GeometrySet::intersect with the tunnel's result plugged in at the tunnel's position
+                Hit h;
+                const bool any = sceneIntersectWith(S, r, h, pr, [&](int &tri, float &t, V3 &n) {
+                    if (!tunnelHit) return false;
+                    tri = hitTri;
+                    t = minD;
+                    const float4 q2 = __ldg(S.tri + 3ull * (unsigned int)hitTri + 2);
+                    n = v3(q2.y, q2.z, q2.w);
+                    return true;
+                });
+                bool spawned = false;
+                if (any)
+                {
+                    const rtb_material &m = S.mats[h.mat];
+                    const V3 nl = (dot(h.n, r.d) < 0) ? h.n : h.n * -1;
+                    const V3 local = matLocal(m, r, h.pos, h.n);
+                    if (++depth <= F.setting.max_depth && depth <= RTB_MAX_DEPTH)
+                    {
+                        const V3 diffusive = (m.diffusiveness > 0) ? local : zero;
+                        const V3 term = diffusive * m.diffusiveness;
+                        if (m.reflectiveness > 0)
+                        {
+                            fold[nfold++] = make_float4(term.x, term.y, term.z, m.reflectiveness);
+                            const V3 v = r.d - nl * 2 * dot(nl, r.d);
+                            r.o = h.pos;
+                            r.d = v;
+                            spawned = true;
+                        }
+                        else c = term + zero * m.reflectiveness + zero * m.refractiveness;
+                    }
+                }
+                if (spawned) beginRay();
+                else st = SM_DONE;
+            }
+        }
+        while (nfold > 0)
+        {
+            const float4 f = fold[--nfold];
+            c = v3(f.x, f.y, f.z) + c * f.w + zero * 0.0f;
+        }
+        storePixel(F, out, x, lr, y, c, t_start, rays, pr);
+    }
+    finishWarp(F, counters, tile, t_start, rays, ProbeCounts<Probe>::tris(pr), ProbeCounts<Probe>::steps(pr));
+}
+
+} // namespace rtb

@@ -123,12 +123,20 @@ __device__ __forceinline__ TriData loadTri(const float4 *base, unsigned int idx)
 }
 __device__ __forceinline__ V3 triNormal(const TriData &t) { return v3(t.q2.y, t.q2.z, t.q2.w); }
 
-__device__ __forceinline__ bool triIntersect(const TriData &T, const Ray &ray, float &tOut)
+// ILP = false: the reference's statement order (exit after each quotient) -- fewest instructions, best
+//               when the SM is issue-bound (the bulk of a frame);
+// ILP = true : everything evaluated before one combined predicate -- best for latency-bound warps.
+// Both produce the same values and the same accept / reject decisions.
+template <bool ILP>
+__device__ __forceinline__ bool triIntersectT(const TriData &T, const Ray &ray, float &tOut)
 {
     const float m11 = T.q0.w, m21 = T.q1.x, m31 = T.q1.y; // a - b
     const float m12 = T.q1.z, m22 = T.q1.w, m32 = T.q2.x; // a - c
     const float m13 = ray.d.x, m23 = ray.d.y, m33 = ray.d.z;
     const float b1 = T.q0.x - ray.o.x, b2 = T.q0.y - ray.o.y, b3 = T.q0.z - ray.o.z;
+    if (!ILP)
+    {
+    // the reference's statement order: four determinants with an exit after each quotient
     const float detM = det3(m11, m12, m13, m21, m22, m23, m31, m32, m33);
     if (fabsf(detM) < 1e-10f) return false;
     const float t = det3(m11, m12, b1, m21, m22, b2, m31, m32, b3) / detM;
@@ -139,7 +147,25 @@ __device__ __forceinline__ bool triIntersect(const TriData &T, const Ray &ray, f
     if (gamma < -0.0001f || gamma > 1.0001f || 1 - beta - gamma < -0.0001f || 1 - beta - gamma > 1.0001f) return false;
     tOut = t;
     return true;
+    }
+    // Same values, same accept / reject decisions, but all four determinants and the three quotients
+    // are evaluated before any branch: the 48 multiplies and 20 adds are independent chains (ILP hides
+    // the 4-cycle ALU latency that dominates a lone warp's stall cycles, profiles/r01_ncu_whitted_chain.md),
+    // the reciprocal seed of det_m is shared by the three IEEE divisions, and the early exits become
+    // one predicate.  The rejects are side-effect free, so evaluating past them cannot change a result;
+    // quotients by a near-zero det_m are inf/NaN and discarded by the det test.
+    const float detM = det3(m11, m12, m13, m21, m22, m23, m31, m32, m33);
+    const float detT = det3(m11, m12, b1, m21, m22, b2, m31, m32, b3);
+    const float detB = det3(b1, m12, m13, b2, m22, m23, b3, m32, m33);
+    const float detG = det3(m11, b1, m13, m21, b2, m23, m31, b3, m33);
+    const float t = detT / detM, beta = detB / detM, gamma = detG / detM;
+    const float alpha = 1 - beta - gamma;
+    const bool reject = (fabsf(detM) < 1e-10f) | (t < 0.0005f) | (beta < -0.0001f) | (beta > 1.0001f) |
+                        (gamma < -0.0001f) | (gamma > 1.0001f) | (alpha < -0.0001f) | (alpha > 1.0001f);
+    tOut = t;
+    return !reject;
 }
+__device__ __forceinline__ bool triIntersect(const TriData &T, const Ray &ray, float &tOut) { return triIntersectT<false>(T, ray, tOut); }
 
 // nearest hit of a list of triangle references; first in list wins ties (strict <)
 template <bool WINDOW, class Probe>
@@ -390,8 +416,11 @@ __device__ bool linearIntersect(const DScene &S, const Ray &ray, int &triOut, fl
 // ---------------------------------------------------------------------------------------------
 struct Hit { int id; int mat; float t; V3 pos, n; };
 
-template <class Probe>
-__device__ bool sceneIntersect(const DScene &S, const Ray &ray, Hit &best, Probe &pr)
+// `tunnel(tri, t, n)` supplies the result of the TUNNEL geometry (a traversal, or a result computed
+// earlier by the resumable traversal of rtb_chain_sm.cuh); everything else is evaluated here in
+// insertion order with the reference's strict `<`.
+template <class Probe, class TunnelFn>
+__device__ __forceinline__ bool sceneIntersectWith(const DScene &S, const Ray &ray, Hit &best, Probe &pr, TunnelFn tunnel)
 {
     float minDistance = FLT_MAX;
     best.id = -1;
@@ -455,10 +484,7 @@ __device__ bool sceneIntersect(const DScene &S, const Ray &ray, Hit &best, Probe
             int tri = -1;
             float t;
             V3 n;
-            bool ok;
-            if (S.accel == RTB_ACCEL_REGULAR_GRID || S.accel == RTB_ACCEL_FLAT_GRID) ok = gridIntersect(S, ray, tri, t, n, pr);
-            else if (S.accel == RTB_ACCEL_KD_MEDIAN || S.accel == RTB_ACCEL_KD_SAH) ok = kdIntersect(S, ray, tri, t, n, pr);
-            else ok = linearIntersect(S, ray, tri, t, n, pr);
+            const bool ok = tunnel(tri, t, n);
             if (ok && t < minDistance)
             {
                 minDistance = t;
@@ -470,6 +496,16 @@ __device__ bool sceneIntersect(const DScene &S, const Ray &ray, Hit &best, Probe
     best.t = minDistance;
     best.pos = at(ray, minDistance);
     return true;
+}
+
+template <class Probe>
+__device__ bool sceneIntersect(const DScene &S, const Ray &ray, Hit &best, Probe &pr)
+{
+    return sceneIntersectWith(S, ray, best, pr, [&](int &tri, float &t, V3 &n) {
+        if (S.accel == RTB_ACCEL_REGULAR_GRID || S.accel == RTB_ACCEL_FLAT_GRID) return gridIntersect(S, ray, tri, t, n, pr);
+        if (S.accel == RTB_ACCEL_KD_MEDIAN || S.accel == RTB_ACCEL_KD_SAH) return kdIntersect(S, ray, tri, t, n, pr);
+        return linearIntersect(S, ray, tri, t, n, pr);
+    });
 }
 
 // ---------------------------------------------------------------------------------------------

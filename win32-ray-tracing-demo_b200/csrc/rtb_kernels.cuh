@@ -25,6 +25,8 @@ struct FrameParams
     int tiles_x, n_tiles;
     const unsigned int *order; // [n_tiles] tile ids, heaviest first; nullptr = raster order
     unsigned int *cost;        // [n_tiles] cycles >> 6 spent on each tile by this launch; may be nullptr
+    const unsigned int *n_heavy; // number of leading entries of `order` that are latency-critical tiles
+    int skip_heavy;              // k_whitted_chain leaves those entries to k_whitted_chain_sm
     unsigned long long seed;
 };
 
@@ -32,6 +34,12 @@ struct FrameParams
 #define RTB_TILE_W 8
 #define RTB_TILE_H 4
 #define RTB_COST_BUCKETS 128
+#ifndef RTB_HEAVY_BUCKETS
+#define RTB_HEAVY_BUCKETS 6 // quarter-octaves below the heaviest tile that still count as latency-critical (measured, scratch/perf2.py)
+#endif
+#ifndef RTB_HEAVY_FRACTION
+#define RTB_HEAVY_FRACTION 128 // at most 1/128 of the tiles
+#endif
 
 // warp -> tile -> (x, local row, global y); false when the thread has no pixel
 __device__ __forceinline__ bool pixelOfThread(const FrameParams &F, int &x, int &lr, int &y, unsigned int &tile)
@@ -95,18 +103,25 @@ __global__ void k_cost_histogram(const unsigned int *__restrict__ cost, int n, u
         if (h[i]) atomicAdd(&hist[i], h[i]);
 }
 
-// one warp: hist[] -> descending exclusive offsets in cursor[], hist[] cleared for the next frame
-__global__ void k_cost_offsets(unsigned int *__restrict__ hist, unsigned int *__restrict__ cursor)
+// one thread: hist[] -> descending exclusive offsets in cursor[], hist[] cleared for the next frame.
+// Also counts the "heavy" tiles: those within 8x (12 quarter-octave buckets) of the heaviest tile, capped
+// at 1/16 of the frame.  They run the latency-optimised resumable traversal (rtb_chain_sm.cuh).
+__global__ void k_cost_offsets(unsigned int *__restrict__ hist, unsigned int *__restrict__ cursor, unsigned int *__restrict__ n_heavy,
+                               int n_tiles)
 {
     if (threadIdx.x == 0)
     {
-        unsigned int run = 0;
+        int top = RTB_COST_BUCKETS - 1;
+        while (top > 0 && hist[top] == 0) top--;
+        unsigned int run = 0, heavy = 0;
         for (int b = RTB_COST_BUCKETS - 1; b >= 0; b--)
         {
             cursor[b] = run;
             run += hist[b];
+            if (b >= top - RTB_HEAVY_BUCKETS && run <= (unsigned int)n_tiles / RTB_HEAVY_FRACTION) heavy = run;
             hist[b] = 0;
         }
+        *n_heavy = heavy;
     }
 }
 
@@ -139,6 +154,61 @@ template <> struct ProbeCounts<CountProbe>
 #define RTB_CHAIN_MIN_CTAS 8 // 64 registers: measured best (5.9 ms vs 7.5 ms at 4) on the 4K SAH frame
 #endif
 
+// one pixel: walk the chain ray by ray (each ray a complete GeometrySet::intersect), then fold
+template <class Probe>
+__device__ __forceinline__ V3 chainPerRay(const DScene &S, const FrameParams &F, int x, int y, unsigned int &rays, Probe &pr)
+{
+    const float dx = 1.0f / F.height, dy = 1.0f / F.height; // MainWindow.cpp:254-255
+    const float sx = (x + 0.5f) * dx, sy = 1 - (y + 0.5f) * dy;
+    Ray r = generateRay(F.cam, sx, sy);
+    float4 fold[RTB_MAX_DEPTH + 1];
+    int n = 0, depth = 0;
+    V3 c = v3(0, 0, 0); // value returned by the innermost call
+    const V3 zero = v3(0, 0, 0);
+    while (true)
+    {
+        rays++;
+        Hit h;
+        if (!sceneIntersect(S, r, h, pr)) break; // Color::Black()
+        const rtb_material &m = S.mats[h.mat];
+        const V3 nl = (dot(h.n, r.d) < 0) ? h.n : h.n * -1;
+        const V3 local = matLocal(m, r, h.pos, h.n);
+        if (++depth > F.setting.max_depth) break;
+        if (depth > RTB_MAX_DEPTH) break;
+        const V3 diffusive = (m.diffusiveness > 0) ? local : zero;
+        const V3 term = diffusive * m.diffusiveness;
+        if (m.reflectiveness > 0)
+        {
+            fold[n++] = make_float4(term.x, term.y, term.z, m.reflectiveness);
+            const V3 v = r.d - nl * 2 * dot(nl, r.d);
+            r.o = h.pos;
+            r.d = v;
+            continue;
+        }
+        c = term + zero * m.reflectiveness + zero * m.refractiveness;
+        break;
+    }
+    while (n > 0)
+    {
+        const float4 f = fold[--n];
+        c = v3(f.x, f.y, f.z) + c * f.w + zero * 0.0f;
+    }
+    return c;
+}
+
+template <class Probe>
+__device__ __forceinline__ void storePixel(const FrameParams &F, float *out, int x, int lr, int y, V3 c, long long t_start,
+                                           unsigned int rays, const Probe &pr)
+{
+    float *o = out + 3 * pixelSlot(F, x, lr, y);
+    if (F.cost_map)
+    { // profiling aid: (thread cycles, rays, traversal steps + triangle tests) instead of the colour
+        o[0] = (float)(clock64() - t_start); o[1] = (float)rays;
+        o[2] = (float)(ProbeCounts<Probe>::tris(pr) + ProbeCounts<Probe>::steps(pr));
+    }
+    else { o[0] = c.x; o[1] = c.y; o[2] = c.z; }
+}
+
 template <class Probe>
 __global__ void __launch_bounds__(RTB_CTA_THREADS, RTB_CHAIN_MIN_CTAS)
 k_whitted_chain(const __grid_constant__ DScene S, const __grid_constant__ FrameParams F, float *__restrict__ out,
@@ -150,50 +220,11 @@ k_whitted_chain(const __grid_constant__ DScene S, const __grid_constant__ FrameP
     const bool active = pixelOfThread(F, x, lr, y, tile);
     unsigned int rays = 0;
     Probe pr;
+    if (F.skip_heavy && blockIdx.x * (RTB_CTA_THREADS / 32) + (threadIdx.x >> 5) < __ldg(F.n_heavy)) return;
     if (active)
     {
-        const float dx = 1.0f / F.height, dy = 1.0f / F.height; // MainWindow.cpp:254-255
-        const float sx = (x + 0.5f) * dx, sy = 1 - (y + 0.5f) * dy;
-        Ray r = generateRay(F.cam, sx, sy);
-        float4 fold[RTB_MAX_DEPTH + 1];
-        int n = 0, depth = 0;
-        V3 c = v3(0, 0, 0); // value returned by the innermost call
-        const V3 zero = v3(0, 0, 0);
-        while (true)
-        {
-            rays++;
-            Hit h;
-            if (!sceneIntersect(S, r, h, pr)) break; // Color::Black()
-            const rtb_material &m = S.mats[h.mat];
-            const V3 nl = (dot(h.n, r.d) < 0) ? h.n : h.n * -1;
-            const V3 local = matLocal(m, r, h.pos, h.n);
-            if (++depth > F.setting.max_depth) break;
-            if (depth > RTB_MAX_DEPTH) break;
-            const V3 diffusive = (m.diffusiveness > 0) ? local : zero;
-            const V3 term = diffusive * m.diffusiveness;
-            if (m.reflectiveness > 0)
-            {
-                fold[n++] = make_float4(term.x, term.y, term.z, m.reflectiveness);
-                const V3 v = r.d - nl * 2 * dot(nl, r.d);
-                r.o = h.pos;
-                r.d = v;
-                continue;
-            }
-            c = term + zero * m.reflectiveness + zero * m.refractiveness;
-            break;
-        }
-        while (n > 0)
-        {
-            const float4 f = fold[--n];
-            c = v3(f.x, f.y, f.z) + c * f.w + zero * 0.0f;
-        }
-        float *o = out + 3 * pixelSlot(F, x, lr, y);
-        if (F.cost_map)
-        { // profiling aid: (thread cycles, rays, traversal steps + triangle tests) instead of the colour
-            o[0] = (float)(clock64() - t_start); o[1] = (float)rays;
-            o[2] = (float)(ProbeCounts<Probe>::tris(pr) + ProbeCounts<Probe>::steps(pr));
-        }
-        else { o[0] = c.x; o[1] = c.y; o[2] = c.z; }
+        const V3 c = chainPerRay(S, F, x, y, rays, pr);
+        storePixel(F, out, x, lr, y, c, t_start, rays, pr);
     }
     finishWarp(F, counters, tile, t_start, rays, ProbeCounts<Probe>::tris(pr), ProbeCounts<Probe>::steps(pr));
 }
