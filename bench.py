@@ -208,7 +208,7 @@ def run_b200(args, wl_name):
             rtb200.unshard_device(ctx, gathered.data_ptr(), image.data_ptr(), W, H, world, ROW_BLOCK, rows_max, stream)
 
     # render kernel + heavy-tile kernel (k-d scenes, once a tile order exists) + 3 tile-order kernels (+ unshard)
-    launches_per_step = (5 if wl["algorithm"] in ("sah", "kd") else 4) + (1 if world > 1 else 0)
+    launches_per_step = (5 if wl["algorithm"] in ("sah", "kd", "fgrid") else 4) + (1 if world > 1 else 0)
 
     # ray / test / step counts of one frame (deterministic), outside the timed region
     cframe = rtb200.make_frame(W, H, samples=spp, seed=0, rank=rank, world=world, row_block=ROW_BLOCK, counters=1)

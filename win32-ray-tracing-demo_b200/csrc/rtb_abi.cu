@@ -373,17 +373,18 @@ static int launchRender(rtb_ctx *ctx, const rtb_scene *scene, FrameParams &F, fl
     F.skip_heavy = 0;
     if (F.setting.enable_monte_carlo) k_montecarlo<Probe><<<grid, RTB_CTA_THREADS, 0, stream>>>(scene->d, F, out, counters);
     else if (scene->has_refractive) k_whitted_tree<Probe><<<grid, RTB_CTA_THREADS, 0, stream>>>(scene->d, F, out, counters);
-    else if (resumable && scene->has_tunnel && grid_accel)
+    else if (resumable && scene->has_tunnel && accel == RTB_ACCEL_REGULAR_GRID)
         k_whitted_chain_sm<Probe, true><<<grid, RTB_CTA_THREADS, 0, stream>>>(scene->d, F, out, counters);
-    else if (resumable && scene->has_tunnel && kd_accel && F.order)
-    { // k-d with a known tile order: the latency-critical head of the order runs the resumable walk on the
+    else if (resumable && scene->has_tunnel && (kd_accel || grid_accel) && F.order)
+    { // a tile order is known: the latency-critical head of the order runs the resumable walk on the
       // high-priority side stream, concurrently with the per-ray walk of all other tiles
         F.skip_heavy = 1;
         const int heavyCap = F.n_tiles / RTB_HEAVY_FRACTION + 1; // upper bound of *n_heavy (k_cost_offsets)
         const dim3 hgrid((unsigned int)((heavyCap + warpsPerCta - 1) / warpsPerCta));
         CUDA_TRY(ctx, cudaEventRecord(ctx->fork, stream));
         CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->aux, ctx->fork, 0));
-        k_whitted_chain_sm<Probe, false><<<hgrid, RTB_CTA_THREADS, 0, ctx->aux>>>(scene->d, F, out, counters);
+        if (grid_accel) k_whitted_chain_sm<Probe, true><<<hgrid, RTB_CTA_THREADS, 0, ctx->aux>>>(scene->d, F, out, counters);
+        else k_whitted_chain_sm<Probe, false><<<hgrid, RTB_CTA_THREADS, 0, ctx->aux>>>(scene->d, F, out, counters);
         CUDA_TRY(ctx, cudaEventRecord(ctx->join, ctx->aux));
         k_whitted_chain<Probe><<<grid, RTB_CTA_THREADS, 0, stream>>>(scene->d, F, out, counters);
         CUDA_TRY(ctx, cudaStreamWaitEvent(stream, ctx->join, 0));

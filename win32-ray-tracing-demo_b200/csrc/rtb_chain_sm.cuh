@@ -40,11 +40,12 @@ k_whitted_chain_sm(const __grid_constant__ DScene S, const __grid_constant__ Fra
     const bool active = pixelOfThread(F, x, lr, y, tile);
     unsigned int rays = 0;
     Probe pr;
-    // Who runs this kernel?  Grids: every tile (measured 1.75x faster than the per-ray walk on the whole
-    // frame).  k-d trees: the per-ray walk (k_whitted_chain) issues ~15 % fewer instructions, so it renders
-    // the bulk of the frame; this kernel is launched next to it on a second stream and takes only the
-    // latency-critical tiles, i.e. the first *n_heavy entries of the heaviest-first order.
-    if (!GRID)
+    // Who runs this kernel?  Regular grid: every tile (measured 1.75x faster than the per-ray walk on the
+    // whole frame).  k-d trees and the flat grid: the per-ray walk (k_whitted_chain) is faster on coherent
+    // rays (~15 % fewer instructions; 2x on the flat grid's long runs of empty cells), so it renders the bulk
+    // of the frame; this kernel is launched next to it on a second stream and takes only the latency-critical
+    // tiles, i.e. the first *n_heavy entries of the heaviest-first order (F.skip_heavy).
+    if (F.skip_heavy)
     {
         const unsigned int warpIndex = blockIdx.x * (RTB_CTA_THREADS / 32) + (threadIdx.x >> 5);
         if (warpIndex >= __ldg(F.n_heavy)) return;
