@@ -336,3 +336,79 @@ def test_4k_frame_properties(ctx):
     assert rays == st["n_rays"]
     assert st["n_rays"] > 3 * w * h * 0.9  # ~3.1 rays per primary on this scene
     dev.close(); s.close()
+
+
+# ---- edge cases ----------------------------------------------------------------------------------------
+RAGGED = [dict(preset=5, algorithm="sah", segments=12, width=37, height=23),
+          dict(preset=5, algorithm="rgrid", segments=12, width=9, height=5),
+          dict(preset=4, algorithm="fgrid", segments=8, width=1, height=1),
+          dict(preset=4, algorithm="kd", segments=12, width=101, height=3),
+          dict(preset=2, width=13, height=7, setting="simple")]
+
+
+@pytest.mark.parametrize("job", RAGGED, ids=lambda j: "-".join(f"{k}{v}" for k, v in j.items()))
+def test_ragged_frame_sizes(ctx, job):
+    """Widths that are not a multiple of the 8x4 tile, single-pixel and single-row frames; each frame is
+    rendered twice so the second pass runs with the heaviest-first tile order learnt from the first."""
+    o = O.run("oracle", image=True, hits=True, seq=True, **job)
+    s, dev = _scene(ctx, job)
+    r = dev.trace_primary(s.camera, job["width"], job["height"], seq=True)
+    assert np.array_equal(r["hit_id"], o["hit_id"]) and np.array_equal(r["seq_hash"], o["seq_hash"])
+    fr = rtb200.make_frame(job["width"], job["height"])
+    a, st = dev.render(s.camera, _setting(s, job), fr)
+    b, _ = dev.render(s.camera, _setting(s, job), fr)
+    _assert_image_close(a, o["image"], str(job))
+    assert np.array_equal(_bits(a), _bits(b)) and st["n_rays"] == o["n_rays"]
+    dev.close(); s.close()
+
+
+def test_more_ranks_than_row_blocks(ctx):
+    """world larger than the number of row blocks: some ranks own nothing and render nothing."""
+    s, dev = _scene(ctx, dict(preset=5, algorithm="sah", segments=12))
+    w, h, world = 64, 20, 8  # 3 blocks of 8 rows
+    whole, st = dev.render(s.camera, s.setting, rtb200.make_frame(w, h))
+    out, rays = np.zeros_like(whole), 0
+    for rank in range(world):
+        fr = rtb200.make_frame(w, h, rank=rank, world=world, row_block=8)
+        part, pst = dev.render(s.camera, s.setting, fr)
+        ys = rtb200.shard_row_indices(h, rank, world, 8)
+        assert part.shape[0] == len(ys)
+        if len(ys):
+            out[ys] = part
+            rays += pst["n_rays"]
+    assert np.array_equal(_bits(out), _bits(whole)) and rays == st["n_rays"]
+    dev.close(); s.close()
+
+
+@pytest.mark.parametrize("max_depth", [0, 1, 2, 7])
+def test_max_depth_settings(ctx, max_depth):
+    """RenderSetting.maxDepth cuts the reflection chain exactly where the reference's `++depth > maxDepth`
+    does (MainWindow.cpp:83); the oracle has no knob for it, so check monotone ray counts and the limits."""
+    s, dev = _scene(ctx, dict(preset=5, algorithm="sah", segments=12))
+    st_ = rtb200.RenderSetting(0, max_depth, rtb200.INT_MAX, 0)
+    img, st = dev.render(s.camera, st_, rtb200.make_frame(80, 60))
+    n = 80 * 60
+    if max_depth == 0:
+        assert st["n_rays"] == n and not img.any()  # every first hit already exceeds the depth: black
+    else:
+        full, fst = dev.render(s.camera, s.setting, rtb200.make_frame(80, 60))
+        assert n <= st["n_rays"] <= fst["n_rays"]
+        assert st["n_rays"] <= n * (max_depth + 1)  # the ray that exceeds the depth is still traced (line 71-84)
+    dev.close(); s.close()
+
+
+def test_tile_order_does_not_change_results(ctx):
+    """Heaviest-first scheduling and the resumable traversal of the latency-critical tiles only change who
+    computes a pixel when: ten consecutive frames are bit-identical and so is a fresh context's first frame."""
+    job = dict(preset=5, algorithm="sah", segments=40)
+    s, dev = _scene(ctx, job)
+    fr = rtb200.make_frame(320, 240)
+    first, st0 = dev.render(s.camera, s.setting, fr)
+    for _ in range(9):
+        again, st = dev.render(s.camera, s.setting, fr)
+        assert np.array_equal(_bits(first), _bits(again)) and st["n_rays"] == st0["n_rays"]
+    ctx2 = rtb200.Context(0)
+    dev2 = ctx2.upload(s.flat)
+    fresh, _ = dev2.render(s.camera, s.setting, fr)
+    assert np.array_equal(_bits(first), _bits(fresh))
+    dev2.close(); ctx2.close(); dev.close(); s.close()
