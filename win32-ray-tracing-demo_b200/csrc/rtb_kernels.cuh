@@ -125,11 +125,30 @@ __global__ void k_cost_offsets(unsigned int *__restrict__ hist, unsigned int *__
     }
 }
 
+// Each block owns a contiguous chunk of tiles: count per bucket in shared memory, reserve the chunk's
+// range of every bucket with ONE global atomic per bucket, then place the tiles with shared-memory
+// atomics (the naive per-tile global atomic took 146 us on the 345,600 tiles of a 4K frame).
 __global__ void k_cost_scatter(const unsigned int *__restrict__ cost, int n, unsigned int *__restrict__ cursor,
                                unsigned int *__restrict__ order)
 {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-        order[atomicAdd(&cursor[costBucket(cost[i])], 1u)] = (unsigned int)i;
+    __shared__ unsigned int cnt[RTB_COST_BUCKETS], base[RTB_COST_BUCKETS];
+    const int per = (n + gridDim.x - 1) / gridDim.x;
+    const int begin = blockIdx.x * per, end = min(begin + per, n);
+    for (int i = threadIdx.x; i < RTB_COST_BUCKETS; i += blockDim.x) cnt[i] = 0;
+    __syncthreads();
+    for (int i = begin + threadIdx.x; i < end; i += blockDim.x) atomicAdd(&cnt[costBucket(cost[i])], 1u);
+    __syncthreads();
+    for (int i = threadIdx.x; i < RTB_COST_BUCKETS; i += blockDim.x)
+    {
+        base[i] = cnt[i] ? atomicAdd(&cursor[i], cnt[i]) : 0u;
+        cnt[i] = 0;
+    }
+    __syncthreads();
+    for (int i = begin + threadIdx.x; i < end; i += blockDim.x)
+    {
+        const int b = costBucket(cost[i]);
+        order[base[b] + atomicAdd(&cnt[b], 1u)] = (unsigned int)i;
+    }
 }
 
 template <class Probe> struct ProbeCounts
