@@ -273,6 +273,24 @@ def run_b200(args, wl_name):
     e2e_ms = allmax((time.perf_counter() - t1) * 1e3) / e2e_steps
     e2e_value = rays_frame / e2e_ms / 1e3
 
+    # the same call with the reference's 8-bit output stage on the GPU (3 bytes per pixel come back)
+    pinned8 = rtb200.PinnedArray(((max(rows, 1) * W * 3 + 3) // 4,))
+    host8 = pinned8.array.view(np.uint8)[: max(rows, 1) * W * 3].reshape(max(rows, 1), W, 3)
+    frame8 = rtb200.make_frame(W, H, samples=spp, seed=0, rank=rank, world=world, row_block=ROW_BLOCK, layout=rtb200.OUTPUT_RGB8)
+
+    def e2e8_step():
+        d = ctx.upload(scene.flat)
+        d.render(scene.camera, scene.setting, frame8, out=host8)
+        d.close()
+
+    e2e8_step()
+    barrier()
+    t1 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e8_step()
+    torch.cuda.synchronize()
+    e2e8_ms = allmax((time.perf_counter() - t1) * 1e3) / e2e_steps
+
     # ---- roofline of the dominant kernel (the render kernel of this rank)
     peaks, peak_kind = measured_peaks()
     pixels_rank = rows * W
@@ -347,7 +365,9 @@ def run_b200(args, wl_name):
                 "roofline": roofline, "cpu_baseline": cpu,
                 "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "ms_per_step": e2e_ms, "steps": e2e_steps,
-                        "path": "rtb_scene_upload (H2D) + rtb_render (kernel + D2H to pinned host) + rtb_scene_free per step"},
+                        "path": "rtb_scene_upload (H2D) + rtb_render (kernel + D2H of the float framebuffer to pinned host) + rtb_scene_free per step",
+                        "rgb8_output_stage": {"value": rays_frame / e2e8_ms / 1e3, "ms_per_step": e2e8_ms, "d2h_bytes_per_step": int(rows * W * 3),
+                                              "note": "same call with RTB_OUTPUT_RGB8: saturate + (int)(c*255) on the GPU as the reference's Render ends (MainWindow.cpp:305-311)"}},
                 "gpu_launches": launches_per_step * args.steps,
                 "kernel_ms_max_over_ranks": kernel_ms_max, "clocks": clocks, "others": others}
         print(json.dumps(line), flush=True)

@@ -125,7 +125,11 @@ typedef struct rtb_render_setting {
  * static across devices).  The output holds this rank's rows only, in increasing y, row-major
  * [local_row][x][3] float RGB -- unless RTB_LAYOUT_REFERENCE is set (world must be 1), which
  * gives the reference framebuffer order index = x*height + y (MainWindow.cpp:276).          */
-enum { RTB_LAYOUT_ROWMAJOR = 0, RTB_LAYOUT_REFERENCE = 1 };
+enum { RTB_LAYOUT_ROWMAJOR = 0, RTB_LAYOUT_REFERENCE = 1,
+       /* OR-able: the output buffer holds 3 BYTES per pixel (R, G, B) produced by the reference's output
+        * stage -- saturate (upper clamp only) then (int)(c * 255), MainWindow.cpp:305-311 -- instead of 3
+        * floats.  A quarter of the bytes to read back; the float framebuffer is what parity is judged on. */
+       RTB_OUTPUT_RGB8 = 4 };
 typedef struct rtb_frame {
     int32_t width, height;
     int32_t samples;      /* spp when enable_monte_carlo                                      */
@@ -176,9 +180,10 @@ int64_t rtb_scene_device_bytes(const rtb_scene *scene);
 /* Replaces `int Render(GeometrySet&, PerspectiveCamera&, RenderSetting&, ProgressCallback)`
  * (reference MainWindow.cpp:251-303, the RenderProc of Scripts.h:11-12): ray generation,
  * trace()/radiance() and the framebuffer store for this rank's rows.  `rgb_out` is a HOST
- * buffer of rtb_shard_rows(frame)*width*3 floats; the device->host copy is part of the call. */
+ * buffer of rtb_shard_rows(frame)*width*3 floats (bytes with RTB_OUTPUT_RGB8, which also runs the
+ * output stage of MainWindow.cpp:305-311); the device->host copy is part of the call.         */
 int rtb_render(rtb_ctx *ctx, const rtb_scene *scene, const rtb_camera *camera,
-               const rtb_render_setting *setting, const rtb_frame *frame, float *rgb_out,
+               const rtb_render_setting *setting, const rtb_frame *frame, void *rgb_out,
                rtb_stats *stats);
 
 /* Same, writing to a DEVICE buffer on `stream` without synchronising (stats are filled only if

@@ -17,7 +17,8 @@
 #   P7 observation hooks    REF_HOOK_* macros after Tunnel.cpp:866,1206,1266, Triangle.cpp:40,
 #                           and the scene.intersect() call of trace/radiance       (compiled out when REF_HOOKS=0)
 #   Utils.cpp (Win32) is replaced by oracle/ref/ref_utils.cpp; MainWindow.cpp is not compiled:
-#   only its lines 69-249 (trace, radiance) and 251-303 (Render's pixel loop) are lifted into a
+#   only its lines 69-249 (trace, radiance), 251-303 (Render's pixel loop) and 305-312 (the 8-bit
+#   output stage; SetPixel / RGB are stand-ins in ref_driver.cpp) are lifted into a
 #   generated include used by oracle/ref/ref_driver.cpp.
 set -euo pipefail
 
@@ -68,12 +69,14 @@ expect MainWindow.cpp 69 'Color trace(GeometrySet &scene, Ray &r, int depth'
 expect MainWindow.cpp 145 'Color radiance(GeometrySet &scene, Ray &r, int depth'
 expect MainWindow.cpp 251 'int Render(GeometrySet &scene, PerspectiveCamera &camera'
 expect MainWindow.cpp 303 'int t2 = Utils::GetTickCount();'
+expect MainWindow.cpp 311 'SetPixel(hdcBuffer, i / height, i % height, RGB(r, g, b));'
 {
     sed -n '69,249p' "$SRC/MainWindow.cpp" \
         | sed -e 's/Ray &r, int depth/Ray r, int depth/' \
               -e 's/IntersectResult result = scene.intersect(r);/IntersectResult result = scene.intersect(r); REF_HOOK_RAY();/'   # P4, P7
     sed -n '251,303p' "$SRC/MainWindow.cpp"
-    echo '    ref_render_epilogue(colors);'
+    echo '    ref_render_epilogue(colors);   // float framebuffer, before the output stage saturates it in place'
+    sed -n '305,312p' "$SRC/MainWindow.cpp"   # the output stage: saturate, (int)(c*255), SetPixel
     echo '    delete []colors;'
     echo '    return t2 - t1;'
     echo '}'

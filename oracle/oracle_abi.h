@@ -87,6 +87,8 @@ typedef struct oracle_job {
     uint64_t struct_hash;/* canonical hash of the accelerator (see rt_oracle.cpp)         */
     uint64_t tri_hash;   /* hash of the tunnel triangle stream                            */
     double *render_ms_all; /* optional [repeat]: every render's interval, in order (input ptr)   */
+    uint8_t *rgb8;       /* optional [w*h*3]: the reference's output stage -- saturate, (int)(c*255)
+                            (MainWindow.cpp:305-311) -- R,G,B bytes in framebuffer order x*height + y */
 } oracle_job;
 
 int rt_oracle_run(oracle_job *job);

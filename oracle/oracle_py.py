@@ -33,7 +33,7 @@ class OracleJob(C.Structure):
         ("n_rays", C.c_int64), ("n_tri_tests", C.c_int64), ("n_steps", C.c_int64),
         ("render_ms", C.c_double), ("prepare_ms", C.c_double),
         ("stats", C.c_int64 * 16), ("struct_hash", C.c_uint64), ("tri_hash", C.c_uint64),
-        ("render_ms_all", C.c_void_p),
+        ("render_ms_all", C.c_void_p), ("rgb8", C.c_void_p),
     ]
 
 
@@ -90,6 +90,7 @@ def run(which, preset, algorithm="linear", segments=150, width=400, height=300, 
 
     if image:
         out("rgb", np.zeros((width, height, 3), np.float32))  # reference order: [x][y]
+        out("rgb8", np.zeros((width, height, 3), np.uint8))
     if hits:
         out("hit_id", np.full(n, -2, np.int32))
         out("hit_t", np.zeros(n, np.float32))
@@ -117,6 +118,7 @@ def run(which, preset, algorithm="linear", segments=150, width=400, height=300, 
         res["tri_mat"] = res["tri_mat"][:nt]
     if image:
         res["image"] = np.ascontiguousarray(res["rgb"].transpose(1, 0, 2))  # [y][x][3]
+        res["image8"] = np.ascontiguousarray(res["rgb8"].transpose(1, 0, 2))
     for k in ("n_rays", "n_tri_tests", "n_steps", "render_ms", "prepare_ms", "struct_hash", "tri_hash"):
         res[k] = getattr(job, k)
     return res

@@ -36,6 +36,19 @@ static std::unordered_map<const void *, int> g_node_id;
 static const char *g_stl_path = "ball.stl";
 static oracle_job *g_job = nullptr;
 static float *g_rgb_out = nullptr;
+static uint8_t *g_rgb8_out = nullptr;
+
+// Win32 stand-ins for the output loop of Render() (MainWindow.cpp:305-312)
+typedef int HDC;
+typedef unsigned int COLORREF;
+static HDC hdcBuffer = 0;
+#define RGB(r, g, b) ((COLORREF)(((uint8_t)(r) | ((uint16_t)((uint8_t)(g)) << 8)) | (((uint32_t)(uint8_t)(b)) << 16)))
+static void SetPixel(HDC, int x, int y, COLORREF c)
+{
+    if (!g_rgb8_out) return;
+    uint8_t *p = g_rgb8_out + 3 * ((size_t)x * height + y);
+    p[0] = (uint8_t)(c & 0xFF); p[1] = (uint8_t)((c >> 8) & 0xFF); p[2] = (uint8_t)((c >> 16) & 0xFF);
+}
 
 const char *ref_stl_path() { return g_stl_path; }
 
@@ -235,6 +248,7 @@ static int jobRender(GeometrySet &scene, PerspectiveCamera &camera, RenderSettin
             memset(g_cnt, 0, sizeof(g_cnt));
             g_counting = true;
             g_rgb_out = (r == 0) ? job->rgb : nullptr;
+            g_rgb8_out = (r == 0) ? job->rgb8 : nullptr;
             Render(scene, camera, setting, noProgress);
             g_counting = false;
             const double ms = ref_last_tick_interval_ms();

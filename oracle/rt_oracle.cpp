@@ -1159,7 +1159,17 @@ extern "C" int rt_oracle_run(oracle_job *job)
         for (int r = 0; r < reps; r++)
         {
             const auto t0 = std::chrono::steady_clock::now();
-            render(s, job, r == 0 ? job->rgb : nullptr, &total);
+            std::vector<float> tmp;
+            float *dst = r == 0 ? job->rgb : nullptr;
+            if (r == 0 && job->rgb8 && !dst) { tmp.resize((size_t)width * height * 3); dst = tmp.data(); }
+            render(s, job, dst, &total);
+            if (r == 0 && job->rgb8)
+                for (size_t i = 0; i < (size_t)width * height * 3; i++)
+                { // MainWindow.cpp:305-311: saturate (upper clamp only), then (int)(c * 255)
+                    float c = dst[i];
+                    c = (c > 1.0f) ? 1.0f : c;
+                    job->rgb8[i] = (uint8_t)(int)(c * 255);
+                }
             const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
             if (job->render_ms_all) job->render_ms_all[r] = ms;
             if (ms < best) best = ms;

@@ -22,7 +22,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 from oracle import oracle_py as O  # noqa: E402
 
-ARRAYS = ["image", "hit_id", "hit_t", "seq_len", "seq_hash"]
+ARRAYS = ["image", "image8", "hit_id", "hit_t", "seq_len", "seq_hash"]
 
 # (name, kwargs, keep_arrays)
 JOBS = []

@@ -412,3 +412,36 @@ def test_tile_order_does_not_change_results(ctx):
     fresh, _ = dev2.render(s.camera, s.setting, fr)
     assert np.array_equal(_bits(first), _bits(fresh))
     dev2.close(); ctx2.close(); dev.close(); s.close()
+
+
+# ---- output stage: saturate -> 8 bit, BMP writer -----------------------------------
+@pytest.mark.parametrize("name", ["p4_sah_s12_80x60", "p5_rgrid_s40_160x120", "p1_simple_80x60", "p2_simple_80x60"])
+def test_rgb8_output_stage_vs_reference(ctx, name):
+    """RTB_OUTPUT_RGB8 runs the reference's output stage on the GPU (MainWindow.cpp:305-311).  A byte can
+    differ by one only where the float differs in the last ulps across a quantisation step (Phong powf)."""
+    job = META[name]["job"]
+    s, dev = _scene(ctx, job)
+    fr = rtb200.make_frame(job["width"], job["height"], layout=rtb200.OUTPUT_RGB8)
+    img8, _ = dev.render(s.camera, _setting(s, job), fr)
+    ref8 = ARR[f"{name}.image8"]
+    assert img8.dtype == np.uint8 and img8.shape == ref8.shape
+    diff = np.abs(img8.astype(np.int16) - ref8.astype(np.int16))
+    assert diff.max() <= 1 and (diff > 0).mean() < 1e-3
+    # and it is exactly the quantisation of this library's own float image
+    f32, _ = dev.render(s.camera, _setting(s, job), rtb200.make_frame(job["width"], job["height"]))
+    q = (np.minimum(f32, np.float32(1.0)) * np.float32(255)).astype(np.int32).astype(np.uint8)
+    assert np.array_equal(q, img8)
+    dev.close(); s.close()
+
+
+def test_dropin_8bit_and_bitmap(ctx, tmp_path):
+    name = "p5_sah_s40_160x120"
+    bmp = str(tmp_path / "frame.bmp")
+    img8, info = rtb200.script_run8(5, "sah", 40, 160, 120, bmp_path=bmp)
+    assert np.array_equal(img8, ARR[f"{name}.image8"]) and info["n_rays"] == META[name]["n_rays"]
+    raw = open(bmp, "rb").read()
+    assert raw[:2] == b"BM" and len(raw) == 54 + 160 * 120 * 3
+    w, h, bpp = np.frombuffer(raw[18:26], np.int32)[0], np.frombuffer(raw[18:26], np.int32)[1], np.frombuffer(raw[28:30], np.int16)[0]
+    assert (w, h, bpp) == (160, 120, 24)
+    rows = np.frombuffer(raw[54:], np.uint8).reshape(120, 160, 3)[::-1, :, ::-1]  # bottom-up BGR -> top-down RGB
+    assert np.array_equal(rows, img8)

@@ -15,7 +15,7 @@ import pytest
 
 from oracle import oracle_py as O
 
-ARRAYS = ["image", "hit_id", "hit_t", "seq_len", "seq_hash"]
+ARRAYS = ["image", "image8", "hit_id", "hit_t", "seq_len", "seq_hash"]
 
 
 def _digest(a):

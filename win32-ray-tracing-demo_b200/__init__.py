@@ -20,7 +20,7 @@ HOST_LIB = os.path.join(PKG, "librtb200_host.so")
 ALGORITHMS = {"linear": 0, "rgrid": 1, "fgrid": 2, "kd": 3, "sah": 4}
 STAT_NAMES = ["n_top", "n_tris", "grid_x", "grid_y", "grid_z", "cells_nonempty", "cell_entries",
               "cell_max", "kd_nodes", "kd_leaves", "kd_leaf_refs", "kd_max_depth"]
-LAYOUT_ROWMAJOR, LAYOUT_REFERENCE = 0, 1
+LAYOUT_ROWMAJOR, LAYOUT_REFERENCE, OUTPUT_RGB8 = 0, 1, 4
 
 
 class RtbError(RuntimeError):
@@ -167,6 +167,8 @@ def host_lib():
             getattr(lib, f).restype = C.c_uint64
         lib.rtbh_script_run.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int,
                                         C.c_char_p, vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(Stats)]
+        lib.rtbh_script_run8.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int,
+                                         C.c_char_p, vp, C.c_char_p, C.POINTER(C.c_int), C.POINTER(Stats)]
         lib.rtbh_last_error.restype = C.c_char_p
         lib.rtbh_intersect_batch.argtypes = [vp, C.c_int64, vp, vp, vp, vp, vp]
         lib.rtbh_intersect_one.argtypes = [vp, vp, vp, vp, vp, vp]
@@ -278,6 +280,22 @@ def script_run(preset, algorithm="linear", segments=150, width=400, height=300, 
     return np.ascontiguousarray(rgb.transpose(1, 0, 2)), info
 
 
+def script_run8(preset, algorithm="linear", segments=150, width=400, height=300, samples=1, seed=0, device=0,
+                stl_path=None, bmp_path=None):
+    """Drop-in path with the reference's 8-bit output stage; returns (uint8 image[y][x][3], info)."""
+    lib = host_lib()
+    rgb = np.zeros((width, height, 3), np.uint8)
+    exe, st = C.c_int(0), Stats()
+    rc = lib.rtbh_script_run8(preset, _alg(algorithm), segments, width, height, samples, seed, device,
+                              (stl_path or stl_fixture()).encode(), rgb.ctypes.data,
+                              bmp_path.encode() if bmp_path else None, C.byref(exe), C.byref(st))
+    if rc != 0:
+        raise RtbError(f"Script::Run (8-bit) failed rc={rc}: {lib.rtbh_last_error().decode()}")
+    info = st.as_dict()
+    info.update(exec_ms=exe.value)
+    return np.ascontiguousarray(rgb.transpose(1, 0, 2)), info
+
+
 # ---- device side: context + uploaded scene over the C ABI --------------------------------------
 class Context:
     def __init__(self, device=0):
@@ -363,8 +381,8 @@ class DeviceScene:
         if rows < 0:
             raise RtbError("bad frame: size / rank / world / row_block (must be a multiple of 8)")
         if out is None:
-            shape = (frame.width, frame.height, 3) if frame.layout == LAYOUT_REFERENCE else (rows, frame.width, 3)
-            out = np.zeros(shape, np.float32)
+            shape = (frame.width, frame.height, 3) if frame.layout & LAYOUT_REFERENCE else (rows, frame.width, 3)
+            out = np.zeros(shape, np.uint8 if frame.layout & OUTPUT_RGB8 else np.float32)
         st = Stats()
         self.ctx._check(self.ctx._lib.rtb_render(self.ctx._h, self._h, C.byref(camera), C.byref(setting), C.byref(frame),
                                                  out.ctypes.data, C.byref(st)), "rtb_render")

@@ -335,7 +335,8 @@ static int makeFrame(rtb_ctx *ctx, const rtb_scene *scene, const rtb_camera *cam
     const int64_t rows = rtb_shard_rows(frame);
     if (rows < 0) return fail(ctx, RTB_ERR_INVALID, "render: bad shard (rank/world/row_block; row_block must be a multiple of 8)");
     const int world = frame->world > 0 ? frame->world : 1;
-    if (frame->layout == RTB_LAYOUT_REFERENCE && world != 1)
+    if (frame->layout & ~(RTB_LAYOUT_REFERENCE | RTB_OUTPUT_RGB8)) return fail(ctx, RTB_ERR_INVALID, "render: unknown layout flags");
+    if ((frame->layout & RTB_LAYOUT_REFERENCE) && world != 1)
         return fail(ctx, RTB_ERR_INVALID, "render: the reference (column-major) layout needs the whole frame on one rank");
     if (setting->enable_monte_carlo)
     {
@@ -352,7 +353,9 @@ static int makeFrame(rtb_ctx *ctx, const rtb_scene *scene, const rtb_camera *cam
     F.cam = *cam;
     F.setting = *setting;
     F.width = frame->width; F.height = frame->height; F.samples = frame->samples;
-    F.rank = frame->rank; F.world = world; F.row_block = normRowBlock(frame); F.layout = frame->layout;
+    F.rank = frame->rank; F.world = world; F.row_block = normRowBlock(frame);
+    F.layout = frame->layout & RTB_LAYOUT_REFERENCE;
+    F.rgb8 = (frame->layout & RTB_OUTPUT_RGB8) ? 1 : 0;
     F.n_local_rows = (int)rows;
     F.tiles_x = (frame->width + RTB_TILE_W - 1) / RTB_TILE_W;
     F.n_tiles = F.tiles_x * (int)((rows + RTB_TILE_H - 1) / RTB_TILE_H);
@@ -434,7 +437,7 @@ static int renderCommon(rtb_ctx *ctx, const rtb_scene *scene, FrameParams &F, co
                         cudaStream_t stream, rtb_stats *stats, float *h_out)
 {
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    const size_t bytes = (size_t)F.n_local_rows * F.width * 3 * sizeof(float);
+    const size_t bytes = (size_t)F.n_local_rows * F.width * 3 * (F.rgb8 ? 1 : sizeof(float));
     if (F.n_local_rows == 0)
     {
         if (stats) { memset(stats, 0, sizeof(*stats)); }
@@ -482,14 +485,14 @@ static int renderCommon(rtb_ctx *ctx, const rtb_scene *scene, FrameParams &F, co
 }
 
 extern "C" int rtb_render(rtb_ctx *ctx, const rtb_scene *scene, const rtb_camera *cam, const rtb_render_setting *setting,
-                          const rtb_frame *frame, float *rgb_out, rtb_stats *stats)
+                          const rtb_frame *frame, void *rgb_out, rtb_stats *stats)
 {
     FrameParams F;
     int rc = makeFrame(ctx, scene, cam, setting, frame, F);
     if (rc != RTB_OK) return rc;
     if (!rgb_out) return fail(ctx, RTB_ERR_INVALID, "rtb_render: null output buffer");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    const size_t bytes = (size_t)F.n_local_rows * F.width * 3 * sizeof(float);
+    const size_t bytes = (size_t)F.n_local_rows * F.width * 3 * (F.rgb8 ? 1 : sizeof(float));
     if (bytes > ctx->d_frame_bytes)
     {
         if (ctx->d_frame) CUDA_TRY(ctx, cudaFree(ctx->d_frame));
@@ -498,7 +501,7 @@ extern "C" int rtb_render(rtb_ctx *ctx, const rtb_scene *scene, const rtb_camera
         CUDA_TRY(ctx, cudaMalloc(&ctx->d_frame, bytes));
         ctx->d_frame_bytes = bytes;
     }
-    return renderCommon(ctx, scene, F, frame, ctx->d_frame, ctx->stream, stats, rgb_out);
+    return renderCommon(ctx, scene, F, frame, ctx->d_frame, ctx->stream, stats, (float *)rgb_out);
 }
 
 extern "C" int rtb_render_device(rtb_ctx *ctx, const rtb_scene *scene, const rtb_camera *cam,

@@ -22,6 +22,7 @@ struct FrameParams
     int rank, world, row_block, layout;
     int n_local_rows;
     int cost_map;
+    int rgb8; // RTB_OUTPUT_RGB8
     int tiles_x, n_tiles;
     const unsigned int *order; // [n_tiles] tile ids, heaviest first; nullptr = raster order
     unsigned int *cost;        // [n_tiles] cycles >> 6 spent on each tile by this launch; may be nullptr
@@ -60,6 +61,23 @@ __device__ __forceinline__ bool pixelOfThread(const FrameParams &F, int &x, int 
 __device__ __forceinline__ size_t pixelSlot(const FrameParams &F, int x, int lr, int y)
 {
     return F.layout == RTB_LAYOUT_REFERENCE ? ((size_t)x * F.height + y) : ((size_t)lr * F.width + x);
+}
+
+// framebuffer store: float RGB, or the reference's 8-bit output stage (MainWindow.cpp:305-311)
+__device__ __forceinline__ void storeColor(const FrameParams &F, float *out, int x, int lr, int y, V3 c)
+{
+    const size_t slot = pixelSlot(F, x, lr, y);
+    if (F.rgb8)
+    {
+        unsigned char *o = reinterpret_cast<unsigned char *>(out) + 3 * slot;
+        const float r = (c.x > 1.0f) ? 1.0f : c.x, g = (c.y > 1.0f) ? 1.0f : c.y, b = (c.z > 1.0f) ? 1.0f : c.z;
+        o[0] = (unsigned char)f2i(r * 255); o[1] = (unsigned char)f2i(g * 255); o[2] = (unsigned char)f2i(b * 255);
+    }
+    else
+    {
+        float *o = out + 3 * slot;
+        o[0] = c.x; o[1] = c.y; o[2] = c.z;
+    }
 }
 
 // per-warp epilogue: record the tile's cost, add the warp's counters to the frame totals
@@ -219,13 +237,13 @@ template <class Probe>
 __device__ __forceinline__ void storePixel(const FrameParams &F, float *out, int x, int lr, int y, V3 c, long long t_start,
                                            unsigned int rays, const Probe &pr)
 {
-    float *o = out + 3 * pixelSlot(F, x, lr, y);
-    if (F.cost_map)
+    if (F.cost_map && !F.rgb8)
     { // profiling aid: (thread cycles, rays, traversal steps + triangle tests) instead of the colour
+        float *o = out + 3 * pixelSlot(F, x, lr, y);
         o[0] = (float)(clock64() - t_start); o[1] = (float)rays;
         o[2] = (float)(ProbeCounts<Probe>::tris(pr) + ProbeCounts<Probe>::steps(pr));
     }
-    else { o[0] = c.x; o[1] = c.y; o[2] = c.z; }
+    else storeColor(F, out, x, lr, y, c);
 }
 
 template <class Probe>
@@ -312,8 +330,7 @@ k_whitted_tree(const __grid_constant__ DScene S, const __grid_constant__ FramePa
                 stack[sp].w = it.w * m.reflectiveness; stack[sp].depth = depth; sp++;
             }
         }
-        float *o = out + 3 * pixelSlot(F, x, lr, y);
-        o[0] = c.x; o[1] = c.y; o[2] = c.z;
+        storeColor(F, out, x, lr, y, c);
     }
     finishWarp(F, counters, tile, t_start, rays, ProbeCounts<Probe>::tris(pr), ProbeCounts<Probe>::steps(pr));
 }
@@ -330,7 +347,7 @@ k_whitted_tree(const __grid_constant__ DScene S, const __grid_constant__ FramePa
 struct McItem { V3 o, d, T; int depth; };
 
 template <class Probe>
-__global__ void __launch_bounds__(RTB_CTA_THREADS)
+__global__ void __launch_bounds__(RTB_CTA_THREADS) // register-capped variants (4/6/8 CTAs per SM) measured slower
 k_montecarlo(const __grid_constant__ DScene S, const __grid_constant__ FrameParams F, float *__restrict__ out,
              Counters *__restrict__ counters)
 {
@@ -450,8 +467,7 @@ k_montecarlo(const __grid_constant__ DScene S, const __grid_constant__ FramePara
                 fresh = true;
             }
         }
-        float *o = out + 3 * pixelSlot(F, x, lr, y);
-        o[0] = acc.x; o[1] = acc.y; o[2] = acc.z;
+        storeColor(F, out, x, lr, y, acc);
     }
     finishWarp(F, counters, tile, t_start, rays, ProbeCounts<Probe>::tris(pr), ProbeCounts<Probe>::steps(pr));
 }

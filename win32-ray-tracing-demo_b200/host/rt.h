@@ -403,6 +403,14 @@ public:
     void configure(int width, int height, int samples, int device = 0, uint64_t seed = 0);
     static int Render(GeometrySet &scene, PerspectiveCamera &camera, RenderSetting &setting, ProgressCallback progress);
     const std::vector<float> &image() const { return image_; } // reference order: index = x*height + y
+    // Output stage of the reference's Render (MainWindow.cpp:305-311): when enabled the GPU saturates and
+    // quantises, only 3 bytes per pixel come back, and pixels() holds R,G,B in the same x*height + y order.
+    void setOutput8bit(bool on) { output8_ = on; }
+    const std::vector<unsigned char> &pixels() const { return pixels_; }
+    // 24-bit BMP of pixels() (the reference's Save-As path: MainWindow.cpp:664-708 + Utils.cpp:78-119;
+    // rows bottom-up, B,G,R; unlike the reference rows are padded to 4 bytes and biPlanes is 1, so the
+    // file is valid for every width).
+    bool saveBitmap(const char *filename) const;
     const rtb_stats &stats() const { return stats_; }
     const std::string &lastError() const { return error_; }
     rtb_ctx *context();
@@ -414,6 +422,8 @@ private:
     uint64_t seed_ = 0;
     rtb_ctx *ctx_ = nullptr;
     std::vector<float> image_;
+    std::vector<unsigned char> pixels_;
+    bool output8_ = false;
     float *pinned_ = nullptr;
     size_t pinnedFloats_ = 0;
     rtb_stats stats_;

@@ -4,6 +4,7 @@
 #include "rt.h"
 
 #include <chrono>
+#include <cstdio>
 #include <cstring>
 #include <mutex>
 
@@ -64,7 +65,7 @@ int CudaRenderer::Render(GeometrySet &scene, PerspectiveCamera &camera, RenderSe
     memset(&frame, 0, sizeof(frame));
     frame.width = self.width_; frame.height = self.height_; frame.samples = self.samples_;
     frame.seed = self.seed_; frame.rank = 0; frame.world = 1; frame.row_block = 8;
-    frame.layout = RTB_LAYOUT_REFERENCE; // Color colors[x*height + y], MainWindow.cpp:276
+    frame.layout = RTB_LAYOUT_REFERENCE | (self.output8_ ? RTB_OUTPUT_RGB8 : 0); // colors[x*height + y], MainWindow.cpp:276
     const size_t floats = (size_t)self.width_ * self.height_ * 3;
     if (floats > self.pinnedFloats_)
     { // page-locked staging buffer so the framebuffer read-back runs at full PCIe rate
@@ -79,10 +80,48 @@ int CudaRenderer::Render(GeometrySet &scene, PerspectiveCamera &camera, RenderSe
     rc = rtb_render(ctx, dev, &cam, &rs, &frame, self.pinned_, &self.stats_);
     rtb_scene_free(ctx, dev);
     if (rc != RTB_OK) { self.error_ = rtb_last_error(ctx); return -3; }
-    self.image_.assign(self.pinned_, self.pinned_ + floats);
+    if (self.output8_)
+    {
+        const unsigned char *bytes = reinterpret_cast<const unsigned char *>(self.pinned_);
+        self.pixels_.assign(bytes, bytes + floats);
+        self.image_.clear();
+    }
+    else
+    {
+        self.image_.assign(self.pinned_, self.pinned_ + floats);
+        self.pixels_.clear();
+    }
     if (progress) progress(self.height_, self.height_);
     const double ms = nowMs() - t0;
     return ms < 1.0 ? 1 : (int)(ms + 0.5);
+}
+
+bool CudaRenderer::saveBitmap(const char *filename) const
+{
+    if (pixels_.size() != (size_t)width_ * height_ * 3) return false;
+    const uint32_t rowBytes = ((uint32_t)width_ * 3 + 3) & ~3u, size = rowBytes * (uint32_t)height_;
+    unsigned char header[54];
+    memset(header, 0, sizeof(header));
+    auto put32 = [&](int at, uint32_t v) { memcpy(header + at, &v, 4); };
+    auto put16 = [&](int at, uint16_t v) { memcpy(header + at, &v, 2); };
+    put16(0, 0x4D42); put32(2, 54 + size); put32(10, 54);                  // BITMAPFILEHEADER
+    put32(14, 40); put32(18, (uint32_t)width_); put32(22, (uint32_t)height_); // BITMAPINFOHEADER
+    put16(26, 1); put16(28, 24); put32(34, size);
+    FILE *fp = fopen(filename, "wb");
+    if (!fp) return false;
+    std::vector<unsigned char> row(rowBytes, 0);
+    bool ok = fwrite(header, 1, sizeof(header), fp) == sizeof(header);
+    for (int y = height_ - 1; y >= 0 && ok; y--)
+    { // bottom-up rows, B G R (MainWindow.cpp:672-680)
+        for (int x = 0; x < width_; x++)
+        {
+            const unsigned char *p = &pixels_[3 * ((size_t)x * height_ + y)];
+            row[3 * x] = p[2]; row[3 * x + 1] = p[1]; row[3 * x + 2] = p[0];
+        }
+        ok = fwrite(row.data(), 1, rowBytes, fp) == rowBytes;
+    }
+    fclose(fp);
+    return ok;
 }
 
 // ---- GPU-served single-ray queries --------------------------------------------------------------
@@ -404,6 +443,29 @@ int rtbh_script_run(int preset, int algorithm, int segments, int width, int heig
     if (exec < 0) return exec;
     if (rgb_out) memcpy(rgb_out, r.image().data(), r.image().size() * sizeof(float));
     if (stats) *stats = r.stats();
+    return 0;
+}
+
+// Same drop-in path with the 8-bit output stage; optionally writes a BMP (Save-As).
+int rtbh_script_run8(int preset, int algorithm, int segments, int width, int height, int samples, uint64_t seed, int device,
+                     const char *stl_path, unsigned char *rgb8_out, const char *bmp_path, int *exec_ms, rtb_stats *stats)
+{
+    if (preset < 1 || preset > 5) return -1;
+    CudaRenderer &r = CudaRenderer::instance();
+    r.configure(width, height, samples, device, seed);
+    r.setOutput8bit(true);
+    Script script = *scripts[preset - 1];
+    script.tunnelSegments = segments;
+    script.samples = samples;
+    if (stl_path) script.stlPath = stl_path;
+    int prep = 0, exec = 0;
+    script.Run(CudaRenderer::Render, algorithm, nullptr, nullptr, prep, exec);
+    r.setOutput8bit(false);
+    if (exec_ms) *exec_ms = exec;
+    if (exec < 0) return exec;
+    if (rgb8_out) memcpy(rgb8_out, r.pixels().data(), r.pixels().size());
+    if (stats) *stats = r.stats();
+    if (bmp_path && !r.saveBitmap(bmp_path)) return -5;
     return 0;
 }
 
