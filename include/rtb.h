@@ -216,6 +216,16 @@ int rtb_trace_primary(rtb_ctx *ctx, const rtb_scene *scene, const rtb_camera *ca
 int rtb_intersect_rays(rtb_ctx *ctx, const rtb_scene *scene, int64_t n, const float *rays,
                        int32_t *hit_id, float *hit_t, float *position, float *normal);
 
+/* Replaces the ray loop of the reference's PerformanceTest console benchmark
+ * (src/PerformanceTest/main.cpp:29-59 `trace`, 151-162): every ray of the batch [n][6] (HOST) is
+ * mirror-reflected off whatever it hits until it reaches a PLANE geometry (the plane closing the tunnel
+ * exit), misses, or has been traced max_depth times (reference: 200).  Outputs (HOST, any may be NULL):
+ * reached (1 = stopped on a plane), depth (hits counted), hit id and position of the last hit,
+ * the total number of rays traced and the kernel's CUDA-event time.                                   */
+int rtb_bounce_rays(rtb_ctx *ctx, const rtb_scene *scene, int64_t n, const float *rays, int32_t max_depth,
+                    int32_t *reached, int32_t *depth, int32_t *last_id, float *last_pos, int64_t *total_rays,
+                    float *kernel_ms);
+
 #ifdef __cplusplus
 }
 #endif

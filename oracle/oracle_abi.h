@@ -94,6 +94,33 @@ typedef struct oracle_job {
 int rt_oracle_run(oracle_job *job);
 int ref_run(oracle_job *job);
 
+/* The "application independent" traversal benchmark of the reference's PerformanceTest console program
+ * (src/PerformanceTest/main.cpp:29-59,127-162): a tunnel of radius `radius` / angle `angle` tessellated
+ * arch_seg x path_seg, a plane closing its exit (added AFTER the tunnel), rays from the PT camera
+ * (eye (0,25,5), PerformanceTest/Camera.cpp:15-21) at the given (x, y) in [0,1]^2 -- the reference draws
+ * them with rand() -- each mirror-reflected until it hits the exit plane, misses, or exceeds max_depth.
+ * PerformanceTest's Triangle / Plane / Grid sources equal RayTracingOpt's except for a `type` tag, so
+ * libref.so runs this workload on the reference's own intersection code (grid, k-d median, SAH of
+ * RayTracingOpt; PerformanceTest's event-sweep SAH builder is not part of this build).                 */
+typedef struct oracle_bounce_job {
+    float radius, angle;
+    int32_t arch_seg, path_seg;
+    int32_t algorithm;     /* as oracle_job                                                  */
+    int32_t n;             /* rays                                                           */
+    int32_t max_depth;     /* reference: 200                                                 */
+    int32_t threads;       /* <= 0: all; the reference loop is single-threaded (1)           */
+    const float *xy;       /* [n][2] camera sample coordinates                               */
+    int32_t *reached;      /* [n] 1 = stopped on the exit plane, 0 = miss / depth exceeded   */
+    int32_t *depth;        /* [n] rays traced for this sample                                */
+    int32_t *last_id;      /* [n] hit id of the last intersection (-1 miss)                  */
+    float *last_pos;       /* [n][3] position of the last hit                                */
+    int64_t total_rays;
+    double trace_ms, prepare_ms;
+} oracle_bounce_job;
+
+int rt_oracle_bounce(oracle_bounce_job *job);
+int ref_bounce(oracle_bounce_job *job);
+
 #ifdef __cplusplus
 }
 #endif

@@ -122,3 +122,33 @@ def run(which, preset, algorithm="linear", segments=150, width=400, height=300, 
     for k in ("n_rays", "n_tri_tests", "n_steps", "render_ms", "prepare_ms", "struct_hash", "tri_hash"):
         res[k] = getattr(job, k)
     return res
+
+
+class BounceJob(C.Structure):
+    _fields_ = [("radius", C.c_float), ("angle", C.c_float), ("arch_seg", C.c_int32), ("path_seg", C.c_int32),
+                ("algorithm", C.c_int32), ("n", C.c_int32), ("max_depth", C.c_int32), ("threads", C.c_int32),
+                ("xy", C.c_void_p), ("reached", C.c_void_p), ("depth", C.c_void_p), ("last_id", C.c_void_p),
+                ("last_pos", C.c_void_p), ("total_rays", C.c_int64), ("trace_ms", C.c_double), ("prepare_ms", C.c_double)]
+
+
+def bounce(which, xy, radius=2000.0, angle=1.5708, arch_seg=150, path_seg=150, algorithm="sah", max_depth=200, threads=0):
+    """PerformanceTest workload (oracle_abi.h: oracle_bounce_job) through 'oracle' or 'ref' / 'ref_timing'."""
+    path, _ = _LIBS[which]
+    if which == "oracle" and not os.path.exists(path):
+        build_oracle()
+    lib = C.CDLL(path)
+    fn = getattr(lib, "rt_oracle_bounce" if which == "oracle" else "ref_bounce")
+    fn.argtypes = [C.POINTER(BounceJob)]
+    fn.restype = C.c_int
+    xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+    n = xy.shape[0]
+    out = {"reached": np.zeros(n, np.int32), "depth": np.zeros(n, np.int32), "last_id": np.zeros(n, np.int32),
+           "last_pos": np.zeros((n, 3), np.float32)}
+    job = BounceJob(radius, angle, arch_seg, path_seg, ALGORITHMS[algorithm] if isinstance(algorithm, str) else algorithm,
+                    n, max_depth, threads, xy.ctypes.data, out["reached"].ctypes.data, out["depth"].ctypes.data,
+                    out["last_id"].ctypes.data, out["last_pos"].ctypes.data, 0, 0.0, 0.0)
+    rc = fn(C.byref(job))
+    if rc != 0:
+        raise RuntimeError(f"{which} bounce job failed rc={rc}")
+    out.update(total_rays=job.total_rays, trace_ms=job.trace_ms, prepare_ms=job.prepare_ms)
+    return out

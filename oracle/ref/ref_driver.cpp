@@ -13,6 +13,9 @@
 #include "Tunnel.h"
 #include "Triangle.h"
 #include "Utils.h"
+#include "Plane.h"
+#include "TunnelGenerator.h"
+#include "SolidColorMaterial.h"
 #include "oracle_abi.h"
 
 #define erand48 ref_erand48
@@ -291,5 +294,78 @@ extern "C" int ref_run(oracle_job *job)
     (void)t0;
     job->prepare_ms = prepare;
     g_job = nullptr;
+    return 0;
+}
+
+// ---- PerformanceTest workload on the reference's own classes (see oracle_abi.h) -----------------
+// The scene and the ray loop follow src/PerformanceTest/main.cpp:29-81,143-162; every intersection is
+// the reference's GeometrySet / Tunnel / Triangle / Plane code.
+extern "C" int ref_bounce(oracle_bounce_job *job)
+{
+    static std::mutex once;
+    std::lock_guard<std::mutex> guard(once);
+    if (!job || job->n < 0 || job->algorithm < 0 || job->algorithm > 4 || !job->xy) return -1;
+    GeometrySet scene;
+    TunnelGenerator g;
+    Ptr<Material> dummy(new SolidColorMaterial(Color::Black(), Color::Black(), 1, 0, 0));
+    g.create(50, 25, 25, job->radius, job->angle, job->arch_seg, job->path_seg, scene, dummy, dummy,
+             (Tunnel::Algorithm)job->algorithm);
+    Tunnel *tunnel = (Tunnel *)scene.last();
+    Vector normal(sin(job->angle), 0, -cos(job->angle));   // main.cpp:75
+    float distance = job->radius * sin(job->angle);        // main.cpp:76
+    Plane *plane = new Plane(normal, distance);
+    plane->material = dummy;
+    scene.add(plane);
+    const auto t0 = std::chrono::steady_clock::now();
+    tunnel->init();
+    job->prepare_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+
+    std::unordered_map<const Geometry *, int> geomId;
+    geomId[tunnel] = 0;
+    geomId[plane] = 1;
+    int k = 0;
+    for (size_t s = 0; s < tunnel->surface.size(); s++)
+        for (size_t j = 0; j < tunnel->surface[s].size(); j++, k++) geomId[tunnel->surface[s][j]] = 2 + k;
+
+    // PerformanceTest/Camera.cpp:5-21
+    Vector front(0, 0, -1), upIn(0, 1, 0);
+    front.norm();
+    Vector right = front.cross(upIn).norm();
+    Vector up = right.cross(front).norm();
+    Point eye(0, 25, 5);
+    long long total = 0;
+    omp_set_num_threads(job->threads > 0 ? job->threads : omp_get_num_procs());
+    const auto t1 = std::chrono::steady_clock::now();
+#pragma omp parallel for schedule(dynamic, 16) reduction(+ : total)
+    for (int i = 0; i < job->n; i++)
+    {
+        const float x = job->xy[2 * i], y = job->xy[2 * i + 1];
+        Vector r = right * ((x - 0.5f) * 1.274f);
+        Vector u = up * ((y - 0.5f) * 1.0f);
+        Vector dir = (front + r + u).norm();
+        Ray ray(eye, dir);
+        int depth = 0, reached = 0, lastId = -1;
+        Point lastPos(0, 0, 0);
+        while (true)
+        { // main.cpp:29-59, recursion unrolled
+            IntersectResult result = scene.intersect(ray);
+            total++;
+            if (!result.hit) { lastId = -1; break; }
+            lastId = geomId[result.geometry];
+            lastPos = result.position;
+            Vector &n = result.normal;
+            Vector nl = (n.dot(ray.direction) < 0) ? n : n * -1;
+            if (++depth > job->max_depth) break;
+            if (result.geometry == plane) { reached = 1; break; }
+            Vector v = ray.direction - nl * 2 * nl.dot(ray.direction);
+            ray = Ray(result.position, v);
+        }
+        if (job->reached) job->reached[i] = reached;
+        if (job->depth) job->depth[i] = depth;
+        if (job->last_id) job->last_id[i] = lastId;
+        if (job->last_pos) { job->last_pos[3 * i] = lastPos.x; job->last_pos[3 * i + 1] = lastPos.y; job->last_pos[3 * i + 2] = lastPos.z; }
+    }
+    job->trace_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count();
+    job->total_rays = total;
     return 0;
 }

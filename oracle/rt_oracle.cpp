@@ -1050,6 +1050,66 @@ void hashKd(const TunnelO &T, int node, uint64_t &h)
 
 } // namespace
 
+// ------------------------------------------------------------------------------------------
+// PerformanceTest console benchmark -- reference src/PerformanceTest/main.cpp:29-59 (trace),
+// 61-81 (scene), 143-162 (ray loop), Camera.cpp:15-21
+// ------------------------------------------------------------------------------------------
+extern "C" int rt_oracle_bounce(oracle_bounce_job *job)
+{
+    if (!job || job->n < 0 || job->algorithm < 0 || job->algorithm > 4 || !job->xy) return -1;
+    Scene s;
+    s.hasTunnel = true;
+    const int dummy = addMat(s, solid(v3(0, 0, 0), v3(0, 0, 0), 1, 0, 0));
+    s.tunnel.algorithm = job->algorithm;
+    generateTunnel(s.tunnel, 50, 25, 25, job->radius, job->angle, job->arch_seg, job->path_seg, dummy, dummy);
+    Prim p; memset(&p, 0, sizeof(p));
+    p.type = PRIM_TUNNEL;
+    s.prims.push_back(p);
+    // exit plane, main.cpp:71-78
+    const V3 normal = v3(sinf(job->angle), 0, -cosf(job->angle));
+    addPlane(s, normal, job->radius * sinf(job->angle), dummy);
+    const auto t0 = std::chrono::steady_clock::now();
+    if (job->algorithm == 1 || job->algorithm == 2) initGrid(s.tunnel);
+    else if (job->algorithm == 3 || job->algorithm == 4) initKd(s.tunnel);
+    job->prepare_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    // PT camera: eye (0,25,5), front (0,0,-1), up (0,1,0); Camera.cpp:5-13
+    V3 front = normalize(v3(0, 0, -1));
+    const V3 right = normalize(cross(front, v3(0, 1, 0)));
+    const V3 up = normalize(cross(right, front));
+    const V3 eye = v3(0, 25, 5);
+    long long total = 0;
+    omp_set_num_threads(job->threads > 0 ? job->threads : omp_get_num_procs());
+    const auto t1 = std::chrono::steady_clock::now();
+#pragma omp parallel for schedule(dynamic, 16) reduction(+ : total)
+    for (int i = 0; i < job->n; i++)
+    {
+        const float x = job->xy[2 * i], y = job->xy[2 * i + 1];
+        const V3 r = right * ((x - 0.5f) * 1.274f), u = up * ((y - 0.5f) * 1.0f); // Camera.cpp:17-18
+        RayO ray = {eye, normalize(front + r + u)};
+        int depth = 0, reached = 0, lastId = -1;
+        V3 lastPos = v3(0, 0, 0);
+        while (true)
+        { // main.cpp:29-59
+            const Hit h = sceneIntersect(s, ray, nullptr);
+            total++;
+            if (!h.hit) { lastId = -1; break; }
+            lastId = h.id; lastPos = h.pos;
+            const V3 nl = (dot(h.n, ray.d) < 0) ? h.n : h.n * -1;
+            if (++depth > job->max_depth) break;
+            if (s.prims[h.id < (int)s.prims.size() ? h.id : 0].type == PRIM_PLANE && h.id < (int)s.prims.size()) { reached = 1; break; }
+            const V3 v = ray.d - nl * 2 * dot(nl, ray.d);
+            ray.o = h.pos; ray.d = v;
+        }
+        if (job->reached) job->reached[i] = reached;
+        if (job->depth) job->depth[i] = depth;
+        if (job->last_id) job->last_id[i] = lastId;
+        if (job->last_pos) { job->last_pos[3 * i] = lastPos.x; job->last_pos[3 * i + 1] = lastPos.y; job->last_pos[3 * i + 2] = lastPos.z; }
+    }
+    job->trace_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count();
+    job->total_rays = total;
+    return 0;
+}
+
 extern "C" int rt_oracle_run(oracle_job *job)
 {
     if (!job || job->preset < 1 || job->preset > 5) return -1;

@@ -70,3 +70,18 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def bounce_golden():
+    """tests/golden/bounce_golden.npz: the PerformanceTest ray loop on the reference's classes (ref_bounce)."""
+    xy = np.random.default_rng(21).random((300, 2), dtype=np.float32)
+    out = {"xy": xy}
+    for alg in ("rgrid", "sah"):
+        a = O.bounce("ref", xy, 2000.0, 1.5708, 30, 30, alg)
+        for k in ("reached", "depth", "last_id", "last_pos"):
+            out[f"{alg}.{k}"] = a[k]
+    np.savez_compressed(os.path.join(HERE, "bounce_golden.npz"), **out)
+
+
+if __name__ == "__main__":
+    bounce_golden()

@@ -445,3 +445,21 @@ def test_dropin_8bit_and_bitmap(ctx, tmp_path):
     assert (w, h, bpp) == (160, 120, 24)
     rows = np.frombuffer(raw[54:], np.uint8).reshape(120, 160, 3)[::-1, :, ::-1]  # bottom-up BGR -> top-down RGB
     assert np.array_equal(rows, img8)
+
+
+# ---- PerformanceTest console benchmark ---------------------------------------------
+@pytest.mark.parametrize("alg", ["rgrid", "fgrid", "kd", "sah", "linear"])
+def test_performance_test_bounce_workload(ctx, alg):
+    """src/PerformanceTest/main.cpp: random camera rays mirror-bounced through the tunnel until they hit
+    the plane at its exit (<= 200 reflections).  Bit-exact against the oracle (itself bit-exact against
+    the reference's classes, tests/test_oracle.py): reached flag, depth, last hit id and position per
+    ray; and the reference's own assertion -- no ray may miss (main.cpp:158-161)."""
+    rng = np.random.default_rng(11)
+    n, seg = (64, 10) if alg == "linear" else (500, 30)
+    xy = rng.random((n, 2), dtype=np.float32)
+    o = O.bounce("oracle", xy, 2000.0, 1.5708, seg, seg, alg)
+    g = rtb200.perf_test(xy, 2000.0, 1.5708, seg, seg, alg)
+    for k in ("reached", "depth", "last_id"):
+        assert np.array_equal(g[k], o[k]), k
+    assert np.array_equal(_bits(g["last_pos"]), _bits(o["last_pos"]))
+    assert g["total_rays"] == o["total_rays"] and g["reached"].all()

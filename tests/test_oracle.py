@@ -85,3 +85,25 @@ def test_counter_rng_mode_is_unbiased_vs_erand48():
     a = O.run("oracle", 1, width=48, height=36, samples=64, image=True, rng=0)["image"]
     b = O.run("oracle", 1, width=48, height=36, samples=64, image=True, rng=1, seed=7)["image"]
     assert abs(a.mean() - b.mean()) / a.mean() < 0.02
+
+
+@pytest.mark.skipif(not O.available("ref"), reason="oracle/_ref/libref.so not built (no /root/reference)")
+@pytest.mark.parametrize("alg", ["rgrid", "fgrid", "kd", "sah"])
+def test_bounce_workload_oracle_matches_ref(alg):
+    """PerformanceTest ray loop (main.cpp:29-59) on the reference's own intersection classes."""
+    xy = np.random.default_rng(3).random((150, 2), dtype=np.float32)
+    a = O.bounce("ref", xy, 2000.0, 1.5708, 24, 24, alg)
+    b = O.bounce("oracle", xy, 2000.0, 1.5708, 24, 24, alg)
+    for k in ("reached", "depth", "last_id", "last_pos"):
+        assert np.array_equal(a[k].view(np.uint8), b[k].view(np.uint8)), k
+    assert a["total_rays"] == b["total_rays"] and a["reached"].all()
+
+
+def test_bounce_workload_golden():
+    """Fixture recorded from libref.so (tests/golden/bounce_golden.npz)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "bounce_golden.npz"))
+    for alg in ("rgrid", "sah"):
+        b = O.bounce("oracle", g["xy"], 2000.0, 1.5708, 30, 30, alg)
+        for k in ("reached", "depth", "last_id", "last_pos"):
+            assert np.array_equal(b[k].view(np.uint8), g[f"{alg}.{k}"].view(np.uint8)), (alg, k)

@@ -102,7 +102,7 @@ class Stats(C.Structure):
 ABI_SYMBOLS = ["rtb_init", "rtb_shutdown", "rtb_last_error", "rtb_abi_version", "rtb_shard_rows",
                "rtb_host_alloc", "rtb_host_free",
                "rtb_scene_upload", "rtb_scene_free", "rtb_scene_device_bytes", "rtb_render",
-               "rtb_render_device", "rtb_unshard_device", "rtb_trace_primary", "rtb_intersect_rays"]
+               "rtb_render_device", "rtb_unshard_device", "rtb_trace_primary", "rtb_intersect_rays", "rtb_bounce_rays"]
 
 _cuda = None
 _host = None
@@ -169,6 +169,8 @@ def host_lib():
                                         C.c_char_p, vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(Stats)]
         lib.rtbh_script_run8.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int,
                                          C.c_char_p, vp, C.c_char_p, C.POINTER(C.c_int), C.POINTER(Stats)]
+        lib.rtbh_perf_test.argtypes = [C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, vp, vp, vp,
+                                       C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
         lib.rtbh_last_error.restype = C.c_char_p
         lib.rtbh_intersect_batch.argtypes = [vp, C.c_int64, vp, vp, vp, vp, vp]
         lib.rtbh_intersect_one.argtypes = [vp, vp, vp, vp, vp, vp]
@@ -294,6 +296,22 @@ def script_run8(preset, algorithm="linear", segments=150, width=400, height=300,
     info = st.as_dict()
     info.update(exec_ms=exe.value)
     return np.ascontiguousarray(rgb.transpose(1, 0, 2)), info
+
+
+def perf_test(xy, radius=2000.0, angle=1.5708, arch_seg=150, path_seg=150, algorithm="sah", max_depth=200):
+    """The reference's PerformanceTest console benchmark on the GPU (host C++: rt::PerformanceTest)."""
+    xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+    n = xy.shape[0]
+    out = {"reached": np.zeros(n, np.int32), "depth": np.zeros(n, np.int32), "last_id": np.zeros(n, np.int32),
+           "last_pos": np.zeros((n, 3), np.float32)}
+    total, b, pre, tr = C.c_int64(0), C.c_double(0), C.c_double(0), C.c_double(0)
+    rc = host_lib().rtbh_perf_test(radius, angle, arch_seg, path_seg, _alg(algorithm), n, xy.ctypes.data, max_depth,
+                                   out["reached"].ctypes.data, out["depth"].ctypes.data, out["last_id"].ctypes.data,
+                                   out["last_pos"].ctypes.data, C.byref(total), C.byref(b), C.byref(pre), C.byref(tr))
+    if rc != 0:
+        raise RtbError(f"PerformanceTest failed rc={rc}: {host_lib().rtbh_last_error().decode()}")
+    out.update(total_rays=total.value, build_ms=b.value, preprocess_ms=pre.value, trace_ms=tr.value)
+    return out
 
 
 # ---- device side: context + uploaded scene over the C ABI --------------------------------------

@@ -611,3 +611,40 @@ extern "C" int rtb_intersect_rays(rtb_ctx *ctx, const rtb_scene *scene, int64_t 
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return RTB_OK;
 }
+
+extern "C" int rtb_bounce_rays(rtb_ctx *ctx, const rtb_scene *scene, int64_t n, const float *rays, int32_t max_depth,
+                               int32_t *reached, int32_t *depth, int32_t *last_id, float *last_pos, int64_t *total_rays,
+                               float *kernel_ms)
+{
+    if (!ctx || !scene || n < 0 || (n > 0 && !rays) || max_depth < 0) return fail(ctx, RTB_ERR_INVALID, "rtb_bounce_rays: bad argument");
+    if (total_rays) *total_rays = 0;
+    if (kernel_ms) *kernel_ms = 0;
+    if (n == 0) return RTB_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    DevBuf<float> d_rays, d_pos;
+    DevBuf<int> d_ok, d_depth, d_id;
+    CUDA_TRY(ctx, d_rays.alloc((size_t)n * 6));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_rays.p, rays, (size_t)n * 6 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    if (reached) CUDA_TRY(ctx, d_ok.alloc((size_t)n));
+    if (depth) CUDA_TRY(ctx, d_depth.alloc((size_t)n));
+    if (last_id) CUDA_TRY(ctx, d_id.alloc((size_t)n));
+    if (last_pos) CUDA_TRY(ctx, d_pos.alloc((size_t)n * 3));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(Counters), ctx->stream));
+    const unsigned int blocks = (unsigned int)((n + RTB_CTA_THREADS - 1) / RTB_CTA_THREADS);
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+    k_bounce_rays<<<blocks, RTB_CTA_THREADS, 0, ctx->stream>>>(scene->d, (long long)n, d_rays.p, max_depth, d_ok.p, d_depth.p, d_id.p,
+                                                               d_pos.p, &ctx->d_counters->rays);
+    CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+    CUDA_TRY(ctx, cudaEventRecord(scene->last_use, ctx->stream));
+    if (reached) CUDA_TRY(ctx, cudaMemcpyAsync(reached, d_ok.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (depth) CUDA_TRY(ctx, cudaMemcpyAsync(depth, d_depth.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (last_id) CUDA_TRY(ctx, cudaMemcpyAsync(last_id, d_id.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (last_pos) CUDA_TRY(ctx, cudaMemcpyAsync(last_pos, d_pos.p, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    unsigned long long total = 0;
+    CUDA_TRY(ctx, cudaMemcpyAsync(&total, &ctx->d_counters->rays, sizeof(total), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (total_rays) *total_rays = (int64_t)total;
+    if (kernel_ms) CUDA_TRY(ctx, cudaEventElapsedTime(kernel_ms, ctx->ev[1], ctx->ev[2]));
+    return RTB_OK;
+}

@@ -414,7 +414,7 @@ __device__ bool linearIntersect(const DScene &S, const Ray &ray, int &triOut, fl
 // ---------------------------------------------------------------------------------------------
 // GeometrySet::intersect -- reference GeometrySet.cpp:95-110 (+ Plane.cpp:9-34, Sphere.cpp:10-37)
 // ---------------------------------------------------------------------------------------------
-struct Hit { int id; int mat; float t; V3 pos, n; };
+struct Hit { int id; int mat; int prim_type; float t; V3 pos, n; };
 
 // `tunnel(tri, t, n)` supplies the result of the TUNNEL geometry (a traversal, or a result computed
 // earlier by the resumable traversal of rtb_chain_sm.cuh); everything else is evaluated here in
@@ -439,7 +439,7 @@ __device__ __forceinline__ bool sceneIntersectWith(const DScene &S, const Ray &r
                 if (distance >= 0.0005f && distance < minDistance)
                 {
                     minDistance = distance;
-                    best.id = P.base_id; best.mat = P.material; best.n = normal;
+                    best.id = P.base_id; best.mat = P.material; best.n = normal; best.prim_type = RTB_PRIM_PLANE;
                 }
             }
         }
@@ -459,7 +459,7 @@ __device__ __forceinline__ bool sceneIntersectWith(const DScene &S, const Ray &r
                     if (distance < minDistance)
                     {
                         minDistance = distance;
-                        best.id = P.base_id; best.mat = P.material;
+                        best.id = P.base_id; best.mat = P.material; best.prim_type = RTB_PRIM_SPHERE;
                         best.n = normalize(at(ray, distance) - center);
                     }
                 }
@@ -475,7 +475,7 @@ __device__ __forceinline__ bool sceneIntersectWith(const DScene &S, const Ray &r
                 if (triIntersect(T, ray, t) && t < minDistance)
                 {
                     minDistance = t;
-                    best.id = P.base_id + k; best.mat = P.material; best.n = triNormal(T);
+                    best.id = P.base_id + k; best.mat = P.material; best.n = triNormal(T); best.prim_type = RTB_PRIM_TRIANGLES;
                 }
             }
         }
@@ -488,7 +488,7 @@ __device__ __forceinline__ bool sceneIntersectWith(const DScene &S, const Ray &r
             if (ok && t < minDistance)
             {
                 minDistance = t;
-                best.id = S.n_top + tri; best.mat = __ldg(S.tri_material + tri); best.n = n;
+                best.id = S.n_top + tri; best.mat = __ldg(S.tri_material + tri); best.n = n; best.prim_type = RTB_PRIM_TUNNEL;
             }
         }
     }

@@ -519,6 +519,47 @@ k_intersect_rays(const __grid_constant__ DScene S, long long n, const float *__r
 }
 
 // ---------------------------------------------------------------------------------------------
+// PerformanceTest workload (reference src/PerformanceTest/main.cpp:29-59): mirror-reflect each ray until
+// it hits a PLANE geometry (the plane closing the tunnel exit), misses, or exceeds max_depth.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(RTB_CTA_THREADS)
+k_bounce_rays(const __grid_constant__ DScene S, long long n, const float *__restrict__ rays, int max_depth,
+              int *__restrict__ reached, int *__restrict__ depth_out, int *__restrict__ last_id, float *__restrict__ last_pos,
+              unsigned long long *__restrict__ total_rays)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned int traced = 0;
+    if (i < n)
+    {
+        Ray r;
+        r.o = v3(rays[6 * i], rays[6 * i + 1], rays[6 * i + 2]);
+        r.d = v3(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]);
+        NoProbe pr;
+        int depth = 0, ok = 0, id = -1;
+        V3 pos = v3(0, 0, 0);
+        while (true)
+        {
+            Hit h;
+            traced++;
+            if (!sceneIntersect(S, r, h, pr)) { id = -1; break; }
+            id = h.id; pos = h.pos;
+            const V3 nl = (dot(h.n, r.d) < 0) ? h.n : h.n * -1;
+            if (++depth > max_depth) break;
+            if (h.prim_type == RTB_PRIM_PLANE) { ok = 1; break; }
+            const V3 v = r.d - nl * 2 * dot(nl, r.d);
+            r.o = h.pos;
+            r.d = v;
+        }
+        if (reached) reached[i] = ok;
+        if (depth_out) depth_out[i] = depth;
+        if (last_id) last_id[i] = id;
+        if (last_pos) { last_pos[3 * i] = pos.x; last_pos[3 * i + 1] = pos.y; last_pos[3 * i + 2] = pos.z; }
+    }
+    traced = __reduce_add_sync(0xffffffffu, traced);
+    if ((threadIdx.x & 31) == 0 && traced) atomicAdd(total_rays, (unsigned long long)traced);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Un-shard: after the NCCL all-gather the frame lives as [world][rows_per_rank][width][3] in
 // block-cyclic row order; this puts it back into image row order [height][width][3].
 // Pure 128-bit copies when width*3 floats is a multiple of 4 (every 4:3 frame is).

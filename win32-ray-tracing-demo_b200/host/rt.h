@@ -365,6 +365,27 @@ struct RenderSetting
     rtb_render_setting flatten() const { return {enableMonteCarlo ? 1 : 0, maxDepth, terminationDepth, singleTracingDepth}; }
 };
 
+// ---- PerformanceTest (src/PerformanceTest): its camera and its benchmark, GPU-served -------------------
+class Camera
+{ // PerformanceTest/Camera.h:7-20 -- fixed 1.274 x 1.0 image plane, no fov / ratio / forward
+    Point eye;
+    Vector front, up, right;
+public:
+    Camera(const Point &eye, Vector front, const Vector &up);
+    Ray generateRay(float x, float y) const;
+};
+
+struct PerformanceTest
+{ // PerformanceTest/main.cpp: tunnel + exit plane, N rays bounced to the exit (<= 200 reflections)
+    GeometrySet scene;
+    Tunnel *tunnel = nullptr;
+    double buildMs = 0, preprocessMs = 0;
+    bool build(float pathRadius, float pathAngle, int archSeg, int pathSeg, Tunnel::Algorithm algorithm); // main.cpp:61-81,134-140
+    // xy: n camera samples in [0,1]^2 (the reference draws them with rand()); returns the trace kernel's ms, < 0 on error
+    double run(const float *xy, int n, int maxDepth, int32_t *reached, int32_t *depth, int32_t *lastId, float *lastPos,
+               int64_t *totalRays);
+};
+
 // ---- render entry point and scene scripts (Scripts.h) -----------------------------------------
 typedef void (*LogCallback)(const char *str);
 typedef void (*ProgressCallback)(int cur, int total);

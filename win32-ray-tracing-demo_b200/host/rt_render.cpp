@@ -189,12 +189,75 @@ bool GeometrySet::intersectBatch(const float *rays, int64_t n, int32_t *hitId, f
     return rc == RTB_OK;
 }
 
-// ---- preset scene scripts (reference Scripts.cpp:22-278) ----------------------------------------
+// ---- PerformanceTest ------------------------------------------------------------------------------------
 static Ptr<Material> solid(const Color &local, const Color &emission, float d, float r, float t)
 {
     return Ptr<Material>(new SolidColorMaterial(local, emission, d, r, t));
 }
 
+Camera::Camera(const Point &eye, Vector front, const Vector &up)
+{ // PerformanceTest/Camera.cpp:5-13
+    this->eye = eye;
+    this->front = front.norm();
+    this->right = front.cross(up).norm();
+    this->up = right.cross(front).norm();
+}
+
+Ray Camera::generateRay(float x, float y) const
+{ // PerformanceTest/Camera.cpp:15-21
+    const Vector r = right * ((x - 0.5f) * 1.274f);
+    const Vector u = up * ((y - 0.5f) * 1.0f);
+    Vector dir = front + r + u;
+    dir.norm();
+    return Ray(eye, dir);
+}
+
+bool PerformanceTest::build(float pathRadius, float pathAngle, int archSeg, int pathSeg, Tunnel::Algorithm algorithm)
+{
+    const double t0 = nowMs();
+    scene.clear();
+    TunnelGenerator g;
+    Ptr<Material> plain = solid(Color::Black(), Color::Black(), 1, 0, 0); // PerformanceTest has no materials
+    g.create(50, 25, 25, pathRadius, pathAngle, archSeg, pathSeg, scene, plain, plain, algorithm);
+    tunnel = static_cast<Tunnel *>(scene.last());
+    // the plane at the exit of the tunnel, main.cpp:71-78
+    const Vector normal(std::sin(pathAngle), 0, -std::cos(pathAngle));
+    Plane *exitPlane = new Plane(normal, pathRadius * std::sin(pathAngle));
+    exitPlane->material = plain;
+    scene.add(exitPlane);
+    buildMs = nowMs() - t0;
+    const double t1 = nowMs();
+    tunnel->init();
+    preprocessMs = nowMs() - t1;
+    return true;
+}
+
+double PerformanceTest::run(const float *xy, int n, int maxDepth, int32_t *reached, int32_t *depth, int32_t *lastId,
+                            float *lastPos, int64_t *totalRays)
+{
+    rtb_ctx *ctx = CudaRenderer::instance().context();
+    if (!ctx) return -1;
+    const Camera camera(Point(0, 25, 5), Vector(0, 0, -1), Vector(0, 1, 0)); // main.cpp:143-147
+    std::vector<float> rays((size_t)n * 6);
+    for (int i = 0; i < n; i++)
+    {
+        const Ray r = camera.generateRay(xy[2 * i], xy[2 * i + 1]);
+        float *o = &rays[6 * (size_t)i];
+        o[0] = r.origin.x; o[1] = r.origin.y; o[2] = r.origin.z;
+        o[3] = r.direction.x; o[4] = r.direction.y; o[5] = r.direction.z;
+    }
+    FlatScene flat;
+    scene.flatten(flat);
+    flat.finish();
+    rtb_scene *dev = nullptr;
+    if (rtb_scene_upload(ctx, &flat.view, &dev) != RTB_OK) return -2;
+    float ms = 0;
+    const int rc = rtb_bounce_rays(ctx, dev, n, rays.data(), maxDepth, reached, depth, lastId, lastPos, totalRays, &ms);
+    rtb_scene_free(ctx, dev);
+    return rc == RTB_OK ? (double)ms : -3.0;
+}
+
+// ---- preset scene scripts (reference Scripts.cpp:22-278) ----------------------------------------
 static void addCornellBox(GeometrySet &scene)
 { // the smallpt box of presets 2 and 3: six planes and the r=600 light sphere
     const struct { Vector n; float d; Color c; } walls[6] = {
@@ -467,6 +530,21 @@ int rtbh_script_run8(int preset, int algorithm, int segments, int width, int hei
     if (stats) *stats = r.stats();
     if (bmp_path && !r.saveBitmap(bmp_path)) return -5;
     return 0;
+}
+
+// PerformanceTest console benchmark: `PerformanceTest radius angle archSeg pathSeg N algorithm` (main.cpp:83-125)
+int rtbh_perf_test(float radius, float angle, int arch_seg, int path_seg, int algorithm, int n, const float *xy, int max_depth,
+                   int32_t *reached, int32_t *depth, int32_t *last_id, float *last_pos, int64_t *total_rays,
+                   double *build_ms, double *preprocess_ms, double *trace_ms)
+{
+    if (algorithm < 0 || algorithm > 4) return -1;
+    PerformanceTest pt;
+    pt.build(radius, angle, arch_seg, path_seg, (Tunnel::Algorithm)algorithm);
+    const double ms = pt.run(xy, n, max_depth, reached, depth, last_id, last_pos, total_rays);
+    if (build_ms) *build_ms = pt.buildMs;
+    if (preprocess_ms) *preprocess_ms = pt.preprocessMs;
+    if (trace_ms) *trace_ms = ms;
+    return ms < 0 ? (int)ms : 0;
 }
 
 const char *rtbh_last_error() { return CudaRenderer::instance().lastError().c_str(); }
