@@ -12,6 +12,21 @@
 
 #include "rtb_chain_sm.cuh"
 
+#ifndef RTB_SPLIT_MAX_TILES
+#define RTB_SPLIT_MAX_TILES 131072 // shards up to 4.2 Mpixel walk their latency-critical tiles with 4 warps each
+#endif
+#ifndef RTB_HEAVY_BUCKETS_SMALL
+#define RTB_HEAVY_BUCKETS_SMALL 6   // the latency-critical set itself stays the same (widening it to 8 / 12 / 16
+#endif
+#ifndef RTB_HEAVY_FRACTION_SMALL
+#define RTB_HEAVY_FRACTION_SMALL 128 //    quarter-octaves and 1/32 .. 1/8 of the shard measured slower)
+#endif
+static int splitMaxTiles()
+{
+    static const int v = getenv("RTB_SPLIT_MAX_TILES") ? atoi(getenv("RTB_SPLIT_MAX_TILES")) : RTB_SPLIT_MAX_TILES;
+    return v;
+}
+
 using namespace rtb;
 
 struct rtb_ctx
@@ -382,12 +397,20 @@ static int launchRender(rtb_ctx *ctx, const rtb_scene *scene, FrameParams &F, fl
     { // a tile order is known: the latency-critical head of the order runs the resumable walk on the
       // high-priority side stream, concurrently with the per-ray walk of all other tiles
         F.skip_heavy = 1;
-        const int heavyCap = F.n_tiles / RTB_HEAVY_FRACTION + 1; // upper bound of *n_heavy (k_cost_offsets)
+        const bool smallShard = F.n_tiles <= splitMaxTiles();
+        const int heavyCap = F.n_tiles / (smallShard ? RTB_HEAVY_FRACTION_SMALL : RTB_HEAVY_FRACTION) + 1; // upper bound of *n_heavy
         const dim3 hgrid((unsigned int)((heavyCap + warpsPerCta - 1) / warpsPerCta));
         CUDA_TRY(ctx, cudaEventRecord(ctx->fork, stream));
         CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->aux, ctx->fork, 0));
-        if (grid_accel) k_whitted_chain_sm<Probe, true><<<hgrid, RTB_CTA_THREADS, 0, ctx->aux>>>(scene->d, F, out, counters);
-        else k_whitted_chain_sm<Probe, false><<<hgrid, RTB_CTA_THREADS, 0, ctx->aux>>>(scene->d, F, out, counters);
+        // Small shards (multi-GPU ranks, small frames) are bound by the latency of the heaviest chains, not by
+        // issue slots: there each latency-critical tile is walked by 4 warps of 8 lanes (less per-step waiting
+        // inside a warp, 4x the warps in flight).  On a big shard the extra warp-instructions would cost more
+        // than the shorter tail saves.
+        FrameParams H = F;
+        H.split4 = smallShard ? 1 : 0;
+        const dim3 sgrid(H.split4 ? (unsigned int)heavyCap : hgrid.x);
+        if (grid_accel) k_whitted_chain_sm<Probe, true><<<sgrid, RTB_CTA_THREADS, 0, ctx->aux>>>(scene->d, H, out, counters);
+        else k_whitted_chain_sm<Probe, false><<<sgrid, RTB_CTA_THREADS, 0, ctx->aux>>>(scene->d, H, out, counters);
         CUDA_TRY(ctx, cudaEventRecord(ctx->join, ctx->aux));
         k_whitted_chain<Probe><<<grid, RTB_CTA_THREADS, 0, stream>>>(scene->d, F, out, counters);
         CUDA_TRY(ctx, cudaStreamWaitEvent(stream, ctx->join, 0));
@@ -447,6 +470,7 @@ static int renderCommon(rtb_ctx *ctx, const rtb_scene *scene, FrameParams &F, co
     if (rc != RTB_OK) return rc;
     if (stats || h_out) CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], stream));
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(Counters), stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_cost, 0, (size_t)F.n_tiles * sizeof(unsigned int), stream));
     if (stats) CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], stream));
     CUDA_TRY(ctx, cudaPeekAtLastError()); // anything stale is reported here, not blamed on the launch
     if (frame->counters) rc = launchRender<CountProbe>(ctx, scene, F, d_out, ctx->d_counters, stream);
@@ -459,7 +483,10 @@ static int renderCommon(rtb_ctx *ctx, const rtb_scene *scene, FrameParams &F, co
         int blocks = (F.n_tiles + 1023) / 1024;
         if (blocks > 296) blocks = 296;
         k_cost_histogram<<<blocks, 256, 0, stream>>>(ctx->d_cost, F.n_tiles, ctx->d_hist);
-        k_cost_offsets<<<1, 32, 0, stream>>>(ctx->d_hist, ctx->d_cursor, ctx->d_heavy, F.n_tiles);
+        const bool smallShard = F.n_tiles <= splitMaxTiles();
+        k_cost_offsets<<<1, 32, 0, stream>>>(ctx->d_hist, ctx->d_cursor, ctx->d_heavy, F.n_tiles,
+                                             smallShard ? RTB_HEAVY_BUCKETS_SMALL : RTB_HEAVY_BUCKETS,
+                                             smallShard ? RTB_HEAVY_FRACTION_SMALL : RTB_HEAVY_FRACTION);
         k_cost_scatter<<<blocks, 256, 0, stream>>>(ctx->d_cost, F.n_tiles, ctx->d_cursor, ctx->d_order);
         CUDA_TRY(ctx, cudaGetLastError());
         ctx->order_valid = true;

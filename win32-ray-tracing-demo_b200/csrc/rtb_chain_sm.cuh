@@ -48,7 +48,7 @@ k_whitted_chain_sm(const __grid_constant__ DScene S, const __grid_constant__ Fra
     if (F.skip_heavy)
     {
         const unsigned int warpIndex = blockIdx.x * (RTB_CTA_THREADS / 32) + (threadIdx.x >> 5);
-        if (warpIndex >= __ldg(F.n_heavy)) return;
+        if ((F.split4 ? (warpIndex >> 2) : warpIndex) >= __ldg(F.n_heavy)) return;
     }
     if (active)
     {

@@ -28,6 +28,7 @@ struct FrameParams
     unsigned int *cost;        // [n_tiles] cycles >> 6 spent on each tile by this launch; may be nullptr
     const unsigned int *n_heavy; // number of leading entries of `order` that are latency-critical tiles
     int skip_heavy;              // k_whitted_chain leaves those entries to k_whitted_chain_sm
+    int split4;                  // this launch gives every tile to 4 warps of 8 lanes (one tile row each)
     unsigned long long seed;
 };
 
@@ -47,12 +48,14 @@ __device__ __forceinline__ bool pixelOfThread(const FrameParams &F, int &x, int 
 {
     const unsigned int w = blockIdx.x * (RTB_CTA_THREADS / 32) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
+    const unsigned int item = F.split4 ? (w >> 2) : w; // index into the tile order
     tile = 0;
-    if (w >= (unsigned int)F.n_tiles) return false;
-    tile = F.order ? __ldg(F.order + w) : w;
+    if (item >= (unsigned int)F.n_tiles) return false;
+    tile = F.order ? __ldg(F.order + item) : item;
     const int ty = tile / F.tiles_x, tx = tile - ty * F.tiles_x;
+    if (F.split4 && lane >= 8) return false; // 8 active lanes: row (w & 3) of the tile
     x = tx * RTB_TILE_W + (lane & 7);
-    lr = ty * RTB_TILE_H + (lane >> 3);
+    lr = ty * RTB_TILE_H + (F.split4 ? (int)(w & 3u) : (lane >> 3));
     const int lb = lr / F.row_block;
     y = (lb * F.world + F.rank) * F.row_block + (lr - lb * F.row_block);
     return x < F.width && lr < F.n_local_rows && y < F.height;
@@ -91,10 +94,10 @@ __device__ __forceinline__ void finishWarp(const FrameParams &F, Counters *g, un
     if ((threadIdx.x & 31) == 0)
     {
         const unsigned int w = blockIdx.x * (RTB_CTA_THREADS / 32) + (threadIdx.x >> 5);
-        if (F.cost && w < (unsigned int)F.n_tiles)
-        {
+        if (F.cost && (F.split4 ? (w >> 2) : w) < (unsigned int)F.n_tiles)
+        { // max: a tile rendered by 4 warps costs what its slowest warp took (the buffer is zeroed per frame)
             const long long dt = (clock64() - t_start) >> 6;
-            F.cost[tile] = dt > 0xffffffffll ? 0xffffffffu : (unsigned int)dt;
+            atomicMax(&F.cost[tile], dt > 0xffffffffll ? 0xffffffffu : (unsigned int)dt);
         }
         if (rays) atomicAdd(&g->rays, (unsigned long long)rays);
         if (tris) atomicAdd(&g->tris, (unsigned long long)tris);
@@ -125,7 +128,7 @@ __global__ void k_cost_histogram(const unsigned int *__restrict__ cost, int n, u
 // Also counts the "heavy" tiles: those within 8x (12 quarter-octave buckets) of the heaviest tile, capped
 // at 1/16 of the frame.  They run the latency-optimised resumable traversal (rtb_chain_sm.cuh).
 __global__ void k_cost_offsets(unsigned int *__restrict__ hist, unsigned int *__restrict__ cursor, unsigned int *__restrict__ n_heavy,
-                               int n_tiles)
+                               int n_tiles, int heavy_buckets, int heavy_fraction)
 {
     if (threadIdx.x == 0)
     {
@@ -136,7 +139,7 @@ __global__ void k_cost_offsets(unsigned int *__restrict__ hist, unsigned int *__
         {
             cursor[b] = run;
             run += hist[b];
-            if (b >= top - RTB_HEAVY_BUCKETS && run <= (unsigned int)n_tiles / RTB_HEAVY_FRACTION) heavy = run;
+            if (b >= top - heavy_buckets && run <= (unsigned int)n_tiles / heavy_fraction) heavy = run;
             hist[b] = 0;
         }
         *n_heavy = heavy;
