@@ -44,7 +44,7 @@ WORKLOADS = {
                        desc="preset 5, k-d SAH, Whitted, demo default 400x300, 1 spp"),
 }
 EXTRAS = ["p5_rgrid_4k", "p5_kd_4k", "p5_fgrid_4k", "p4_sah_4k", "p2_smallpt_64"]
-ROW_BLOCK = 16
+ROW_BLOCK = int(os.environ.get("RTB_ROW_BLOCK", "16"))  # rows per dealt block (multiple of 8)
 METRIC = "Mrays/s on tunnel scenes (grid/k-d tree) at 1/2/4/8 B200 vs CPU render secs"
 
 

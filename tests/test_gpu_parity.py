@@ -414,6 +414,26 @@ def test_tile_order_does_not_change_results(ctx):
     dev2.close(); ctx2.close(); dev.close(); s.close()
 
 
+@pytest.mark.parametrize("alg", ["sah", "kd", "rgrid", "fgrid"])
+def test_three_kernel_tiers_agree(ctx, alg):
+    """Once a tile order exists a frame is shared by three kernels (warp-per-pixel for the heaviest tiles,
+    resumable walk for the latency-critical ones, per-ray walk for the rest).  Frames 2..4 must reproduce
+    frame 1 (rendered by one kernel in raster order) bit for bit, with identical ray / triangle-test /
+    traversal-step totals -- and those totals are the oracle's."""
+    job = dict(preset=5, algorithm=alg, segments=40, width=256, height=192)
+    o = O.run("oracle", image=True, **job)
+    s, dev = _scene(ctx, job)
+    fr = rtb200.make_frame(256, 192, counters=1)
+    first, st0 = dev.render(s.camera, s.setting, fr)
+    assert (st0["n_rays"], st0["n_tri_tests"], st0["n_steps"]) == (o["n_rays"], o["n_tri_tests"], o["n_steps"])
+    for _ in range(3):
+        again, st = dev.render(s.camera, s.setting, fr)
+        assert np.array_equal(_bits(first), _bits(again))
+        assert (st["n_rays"], st["n_tri_tests"], st["n_steps"]) == (st0["n_rays"], st0["n_tri_tests"], st0["n_steps"])
+        assert st["n_launches"] >= 5  # at least two render kernels + the three tile-order kernels
+    dev.close(); s.close()
+
+
 # ---- output stage (SURVEY 8f rank 4): saturate -> 8 bit, BMP writer -----------------------------------
 @pytest.mark.parametrize("name", ["p4_sah_s12_80x60", "p5_rgrid_s40_160x120", "p1_simple_80x60", "p2_simple_80x60"])
 def test_rgb8_output_stage_vs_reference(ctx, name):

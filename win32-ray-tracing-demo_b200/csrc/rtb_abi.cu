@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "rtb_chain_sm.cuh"
+#include "rtb_chain_wide.cuh"
 
 #ifndef RTB_SPLIT_MAX_TILES
 #define RTB_SPLIT_MAX_TILES 131072 // shards up to 4.2 Mpixel walk their latency-critical tiles with 4 warps each
@@ -26,8 +27,51 @@ static int splitMaxTiles()
     static const int v = getenv("RTB_SPLIT_MAX_TILES") ? atoi(getenv("RTB_SPLIT_MAX_TILES")) : RTB_SPLIT_MAX_TILES;
     return v;
 }
+// Warp-per-pixel tier (rtb_chain_wide.cuh): how many of the heaviest tiles it takes (wideCount below).
+static double tunable(const char *name, double dflt)
+{
+    const char *v = getenv(name);
+    return v ? atof(v) : dflt;
+}
+// A warp-per-pixel tile costs 2x (regular grid: long cell lists, the lanes are busy) to 4x (k-d trees: 32 lanes
+// repeat the node walk) the SM time of the same tile in the throughput kernels and finishes 8-16x sooner, so it
+// pays exactly where a frame is bound by the latency of its heaviest chains and not by throughput
+// (measured, gpurun_out/sweep2.log, one B200, preset 5, kernel ms without -> with the tier):
+//   small frames (400x300):           SAH 1.42 -> 0.49, k-d median 3.55 -> 1.22, regular grid 8.48 -> 0.83
+//   regular grid, 1/8 shard of 4K:    worst shard 10.8 -> 4.3;   whole 4K frame 15.6 -> 14.4
+//                                     (preset 5's 400x5x400 grid: 33 triangles per occupied cell, `long_lists`; preset 4's
+//                                     350x166x400 grid has 4 per cell and 265 cells per ray -- it behaves like the k-d rows)
+//   k-d trees, 4K frame or its shards: no gain (the cost distribution is flat: ~1 % of the tiles are within 2x
+//                                      of the heaviest, far too many to render this way) -> tier off.
+#define RTB_SMALL_FRAME_TILES 16384 // up to 0.5 Mpixel
+static int wideCount(int n_tiles, bool long_lists)
+{
+    static const int cap = (int)tunable("RTB_WIDE_CAP", -1), fraction = (int)tunable("RTB_WIDE_FRACTION", 32); // tuning overrides
+    if (cap >= 0) return n_tiles / (fraction < 1 ? 1 : fraction) < cap ? n_tiles / (fraction < 1 ? 1 : fraction) : cap;
+    if (n_tiles <= RTB_SMALL_FRAME_TILES) return n_tiles / (long_lists ? 16 : 32);
+    if (long_lists) return n_tiles <= RTB_SPLIT_MAX_TILES ? (n_tiles / 32 < 1184 ? n_tiles / 32 : 1184) : 148;
+    return 0;
+}
+static int heavyBucketsSmall() { static const int v = (int)tunable("RTB_HEAVY_BUCKETS_SMALL", RTB_HEAVY_BUCKETS_SMALL); return v; }
+static int heavyFractionSmall() { static const int v = (int)tunable("RTB_HEAVY_FRACTION_SMALL", RTB_HEAVY_FRACTION_SMALL); return v < 1 ? 1 : v; }
+// Size limit of the resumable-walk tier.  Small frames have none: there the warp-per-pixel tier takes the heavy
+// tiles and a third kernel in between measured slower (k-d median 400x300: 1.4 ms without, 2.2 ms with).
+static int heavyLimit(int n_tiles)
+{
+    static const int forced = (int)tunable("RTB_HEAVY_LIMIT", -1);
+    if (forced >= 0) return forced;
+    if (n_tiles <= RTB_SMALL_FRAME_TILES) return 0;
+    return n_tiles / (n_tiles <= splitMaxTiles() ? heavyFractionSmall() : RTB_HEAVY_FRACTION);
+}
 
 using namespace rtb;
+
+struct OrderKey
+{
+    long long v[10];
+    unsigned long long scene_signature; // content signature (rtb_scene_upload): a re-upload of the same scene keeps the order
+    rtb_camera cam;
+};
 
 struct rtb_ctx
 {
@@ -43,7 +87,7 @@ struct rtb_ctx
     unsigned int *d_cost = nullptr, *d_order = nullptr, *d_hist = nullptr, *d_cursor = nullptr, *d_heavy = nullptr;
     size_t tile_capacity = 0;
     bool order_valid = false;
-    long long order_key[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    OrderKey order_key = {};
     std::string error;
 };
 
@@ -55,7 +99,46 @@ struct rtb_scene
     bool has_refractive = false;
     bool has_tunnel = false;
     cudaEvent_t last_use = nullptr; // recorded after every launch that reads the scene
+    bool long_lists = false; // regular grid with >= 16 triangle references per occupied cell (tier policy, wideCount)
+    unsigned long long signature = 0; // sampled content hash, identifies "the same scene again" for the tile-order cache
 };
+
+// FNV-1a over the small records and a strided sample of the big streams: microseconds, and a collision costs
+// nothing but a stale tile order (scheduling only)
+static unsigned long long fnv(unsigned long long h, const void *p, size_t bytes)
+{
+    const unsigned char *b = (const unsigned char *)p;
+    for (size_t i = 0; i < bytes; i++) h = (h ^ b[i]) * 0x100000001b3ull;
+    return h;
+}
+template <class T> static unsigned long long fnvSampled(unsigned long long h, const T *p, size_t n)
+{
+    if (!p || n == 0) return fnv(h, &n, sizeof(n));
+    const size_t step = n / 509 + 1;
+    for (size_t i = 0; i < n; i += step) h = fnv(h, p + i, sizeof(T));
+    h = fnv(h, p + (n - 1), sizeof(T));
+    return fnv(h, &n, sizeof(n));
+}
+static unsigned long long sceneSignature(const rtb_flat_scene *f)
+{
+    unsigned long long h = 0xcbf29ce484222325ull;
+    h = fnv(h, f->prims, sizeof(rtb_prim) * (size_t)f->n_prims);
+    h = fnv(h, f->materials, sizeof(rtb_material) * (size_t)f->n_materials);
+    h = fnv(h, &f->accel, sizeof(f->accel));
+    h = fnvSampled(h, f->loose_tri, f->loose_tri ? (size_t)f->n_loose * 12 : 0);
+    h = fnvSampled(h, f->tri, f->tri ? (size_t)f->n_tris * 12 : 0);
+    if (f->accel == RTB_ACCEL_REGULAR_GRID || f->accel == RTB_ACCEL_FLAT_GRID)
+    {
+        h = fnv(h, f->grid_origin, sizeof(f->grid_origin)); h = fnv(h, f->grid_cell, sizeof(f->grid_cell)); h = fnv(h, f->grid_dims, sizeof(f->grid_dims));
+        h = fnvSampled(h, f->grid_cell_tris, (size_t)f->n_cell_refs);
+    }
+    else if (f->accel == RTB_ACCEL_KD_MEDIAN || f->accel == RTB_ACCEL_KD_SAH)
+    {
+        h = fnvSampled(h, f->kd_nodes, (size_t)f->n_kd_nodes);
+        h = fnvSampled(h, f->kd_leaf_tris, (size_t)f->n_kd_refs);
+    }
+    return h;
+}
 
 static std::string g_error;
 static std::mutex g_error_mutex;
@@ -319,6 +402,8 @@ extern "C" int rtb_scene_upload(rtb_ctx *ctx, const rtb_flat_scene *f, rtb_scene
             return bail(fail(ctx, RTB_ERR_UNSUPPORTED, "rtb_scene_upload: accelerator outside the hot path (convex variants are out of scope)"));
     }
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    s->signature = sceneSignature(f);
+    s->long_lists = s->has_tunnel && f->accel == RTB_ACCEL_REGULAR_GRID && f->n_cells_used > 0 && f->n_cell_refs >= 16 * f->n_cells_used;
     *out = s;
     return RTB_OK;
 }
@@ -375,13 +460,16 @@ static int makeFrame(rtb_ctx *ctx, const rtb_scene *scene, const rtb_camera *cam
     F.tiles_x = (frame->width + RTB_TILE_W - 1) / RTB_TILE_W;
     F.n_tiles = F.tiles_x * (int)((rows + RTB_TILE_H - 1) / RTB_TILE_H);
     F.cost_map = frame->counters == 2;
+    F.warps_per_cta = RTB_CTA_THREADS / 32;
     F.seed = frame->seed;
     return RTB_OK;
 }
 
 template <class Probe>
-static int launchRender(rtb_ctx *ctx, const rtb_scene *scene, FrameParams &F, float *out, Counters *counters, cudaStream_t stream)
+static int launchRender(rtb_ctx *ctx, const rtb_scene *scene, FrameParams &F, float *out, Counters *counters, cudaStream_t stream,
+                        int &n_kernels)
 {
+    n_kernels = 1;
     const int warpsPerCta = RTB_CTA_THREADS / 32;
     const dim3 grid((unsigned int)((F.n_tiles + warpsPerCta - 1) / warpsPerCta));
     static const bool resumable = !(getenv("RTB_CHAIN_SM") && atoi(getenv("RTB_CHAIN_SM")) == 0); // A/B switch for profiling
@@ -389,38 +477,72 @@ static int launchRender(rtb_ctx *ctx, const rtb_scene *scene, FrameParams &F, fl
     const bool grid_accel = accel == RTB_ACCEL_REGULAR_GRID || accel == RTB_ACCEL_FLAT_GRID;
     const bool kd_accel = accel == RTB_ACCEL_KD_MEDIAN || accel == RTB_ACCEL_KD_SAH;
     F.skip_heavy = 0;
+    F.record_cost = 1;
     if (F.setting.enable_monte_carlo) k_montecarlo<Probe><<<grid, RTB_CTA_THREADS, 0, stream>>>(scene->d, F, out, counters);
     else if (scene->has_refractive) k_whitted_tree<Probe><<<grid, RTB_CTA_THREADS, 0, stream>>>(scene->d, F, out, counters);
-    else if (resumable && scene->has_tunnel && accel == RTB_ACCEL_REGULAR_GRID)
-        k_whitted_chain_sm<Probe, true><<<grid, RTB_CTA_THREADS, 0, stream>>>(scene->d, F, out, counters);
     else if (resumable && scene->has_tunnel && (kd_accel || grid_accel) && F.order)
-    { // a tile order is known: the latency-critical head of the order runs the resumable walk on the
-      // high-priority side stream, concurrently with the per-ray walk of all other tiles
-        F.skip_heavy = 1;
+    { // A tile order is known.  Three kernels share the frame, all launched at once:
+      //   order[0 .. n_wide)         the very heaviest tiles: one warp per pixel        (side stream, high priority)
+      //   order[n_wide .. n_heavy)   latency-critical tiles: resumable per-lane walk    (side stream, high priority)
+      //   order[n_heavy .. n_tiles)  everything else: per-ray walk                      (caller's stream)
+      // The regular grid renders ALL remaining tiles with the resumable walk (1.75x faster than per-ray there).
         const bool smallShard = F.n_tiles <= splitMaxTiles();
-        const int heavyCap = F.n_tiles / (smallShard ? RTB_HEAVY_FRACTION_SMALL : RTB_HEAVY_FRACTION) + 1; // upper bound of *n_heavy
-        const dim3 hgrid((unsigned int)((heavyCap + warpsPerCta - 1) / warpsPerCta));
+        const int heavyCap = heavyLimit(F.n_tiles) + wideCount(F.n_tiles, scene->long_lists); // upper bound of the device-side count
         CUDA_TRY(ctx, cudaEventRecord(ctx->fork, stream));
         CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->aux, ctx->fork, 0));
-        // Small shards (multi-GPU ranks, small frames) are bound by the latency of the heaviest chains, not by
-        // issue slots: there each latency-critical tile is walked by 4 warps of 8 lanes (less per-step waiting
-        // inside a warp, 4x the warps in flight).  On a big shard the extra warp-instructions would cost more
-        // than the shorter tail saves.
-        FrameParams H = F;
-        H.split4 = smallShard ? 1 : 0;
-        const dim3 sgrid(H.split4 ? (unsigned int)heavyCap : hgrid.x);
-        if (grid_accel) k_whitted_chain_sm<Probe, true><<<sgrid, RTB_CTA_THREADS, 0, ctx->aux>>>(scene->d, H, out, counters);
-        else k_whitted_chain_sm<Probe, false><<<sgrid, RTB_CTA_THREADS, 0, ctx->aux>>>(scene->d, H, out, counters);
-        CUDA_TRY(ctx, cudaEventRecord(ctx->join, ctx->aux));
-        k_whitted_chain<Probe><<<grid, RTB_CTA_THREADS, 0, stream>>>(scene->d, F, out, counters);
-        CUDA_TRY(ctx, cudaStreamWaitEvent(stream, ctx->join, 0));
+        const int nWide = wideCount(F.n_tiles, scene->long_lists);
+        F.n_wide = (unsigned int)nWide;
+        F.heavy_cap = (unsigned int)heavyCap;
+        if (nWide > 0)
+        {
+            FrameParams Wd = F;
+            Wd.record_cost = 0;
+            Wd.warps_per_cta = warpsPerCta;
+            const dim3 wgrid(((unsigned int)nWide * 32u + warpsPerCta - 1) / warpsPerCta);
+            k_whitted_chain_wide<Probe><<<wgrid, RTB_CTA_THREADS, 0, ctx->aux>>>(scene->d, Wd, out, counters);
+            n_kernels++;
+        }
+        if (accel == RTB_ACCEL_REGULAR_GRID)
+        { // one resumable launch for everything after the wide tiles
+            FrameParams H = F;
+            H.after_wide = 1;
+            k_whitted_chain_sm<Probe, true><<<grid, RTB_CTA_THREADS, 0, stream>>>(scene->d, H, out, counters); // records: it is this frame's throughput kernel
+            CUDA_TRY(ctx, cudaEventRecord(ctx->join, ctx->aux));
+            CUDA_TRY(ctx, cudaStreamWaitEvent(stream, ctx->join, 0));
+        }
+        else
+        {
+            // Small shards (multi-GPU ranks, small frames) are bound by the latency of the heaviest chains, not by
+            // issue slots: there each latency-critical tile is walked by 4 warps of 8 lanes (less per-step waiting
+            // inside a warp, 4x the warps in flight).  On a big shard the extra warp-instructions would cost more
+            // than the shorter tail saves.
+            FrameParams H = F;
+            H.skip_heavy = 1;
+            H.after_wide = 1;
+            H.split4 = smallShard ? 1 : 0;
+            H.record_cost = 0;
+            if (heavyLimit(F.n_tiles) > 0)
+            {
+                const unsigned int heavyWarps = (unsigned int)heavyLimit(F.n_tiles) * (H.split4 ? 4u : 1u);
+                const dim3 sgrid((heavyWarps + warpsPerCta - 1) / warpsPerCta);
+                if (grid_accel) k_whitted_chain_sm<Probe, true><<<sgrid, RTB_CTA_THREADS, 0, ctx->aux>>>(scene->d, H, out, counters);
+                else k_whitted_chain_sm<Probe, false><<<sgrid, RTB_CTA_THREADS, 0, ctx->aux>>>(scene->d, H, out, counters);
+                n_kernels++;
+            }
+            CUDA_TRY(ctx, cudaEventRecord(ctx->join, ctx->aux));
+            F.skip_heavy = 1;
+            k_whitted_chain<Probe><<<grid, RTB_CTA_THREADS, 0, stream>>>(scene->d, F, out, counters);
+            CUDA_TRY(ctx, cudaStreamWaitEvent(stream, ctx->join, 0));
+        }
     }
+    else if (resumable && scene->has_tunnel && accel == RTB_ACCEL_REGULAR_GRID)
+        k_whitted_chain_sm<Probe, true><<<grid, RTB_CTA_THREADS, 0, stream>>>(scene->d, F, out, counters);
     else k_whitted_chain<Probe><<<grid, RTB_CTA_THREADS, 0, stream>>>(scene->d, F, out, counters);
     return RTB_OK;
 }
 
 // Attach the tile order learnt from the previous frame of the same geometry (if any) and the cost buffer
-static int prepareTileOrder(rtb_ctx *ctx, FrameParams &F)
+static int prepareTileOrder(rtb_ctx *ctx, const rtb_scene *scene, FrameParams &F)
 {
     if ((size_t)F.n_tiles > ctx->tile_capacity)
     {
@@ -444,11 +566,18 @@ static int prepareTileOrder(rtb_ctx *ctx, FrameParams &F)
         CUDA_TRY(ctx, cudaMalloc(&ctx->d_heavy, sizeof(unsigned int)));
         CUDA_TRY(ctx, cudaMemset(ctx->d_heavy, 0, sizeof(unsigned int)));
     }
-    const long long key[8] = {F.width, F.height, F.rank, F.world, F.row_block, F.layout, F.setting.enable_monte_carlo, F.n_tiles};
-    if (memcmp(key, ctx->order_key, sizeof(key)) != 0)
+    // The order (and the per-tile costs behind it) belongs to one view of one scene: frame geometry, scene,
+    // camera and depth setting.  Anything else starts over with a raster-order frame that measures every tile.
+    OrderKey key;
+    memset(&key, 0, sizeof(key));
+    key.v[0] = F.width; key.v[1] = F.height; key.v[2] = F.rank; key.v[3] = F.world; key.v[4] = F.row_block; key.v[5] = F.layout;
+    key.v[6] = F.setting.enable_monte_carlo; key.v[7] = F.n_tiles; key.v[8] = F.setting.max_depth; key.v[9] = F.samples;
+    key.scene_signature = scene->signature;
+    key.cam = F.cam;
+    if (memcmp(&key, &ctx->order_key, sizeof(key)) != 0)
     {
         ctx->order_valid = false;
-        memcpy(ctx->order_key, key, sizeof(key));
+        memcpy(&ctx->order_key, &key, sizeof(key));
     }
     F.order = ctx->order_valid ? ctx->d_order : nullptr;
     F.cost = ctx->d_cost;
@@ -466,15 +595,15 @@ static int renderCommon(rtb_ctx *ctx, const rtb_scene *scene, FrameParams &F, co
         if (stats) { memset(stats, 0, sizeof(*stats)); }
         return RTB_OK;
     }
-    int rc = prepareTileOrder(ctx, F);
+    int rc = prepareTileOrder(ctx, scene, F);
     if (rc != RTB_OK) return rc;
     if (stats || h_out) CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], stream));
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(Counters), stream));
-    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_cost, 0, (size_t)F.n_tiles * sizeof(unsigned int), stream));
     if (stats) CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], stream));
     CUDA_TRY(ctx, cudaPeekAtLastError()); // anything stale is reported here, not blamed on the launch
-    if (frame->counters) rc = launchRender<CountProbe>(ctx, scene, F, d_out, ctx->d_counters, stream);
-    else rc = launchRender<NoProbe>(ctx, scene, F, d_out, ctx->d_counters, stream);
+    int n_kernels = 1;
+    if (frame->counters) rc = launchRender<CountProbe>(ctx, scene, F, d_out, ctx->d_counters, stream, n_kernels);
+    else rc = launchRender<NoProbe>(ctx, scene, F, d_out, ctx->d_counters, stream, n_kernels);
     if (rc != RTB_OK) return rc;
     CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cudaEventRecord(scene->last_use, stream));
@@ -485,8 +614,8 @@ static int renderCommon(rtb_ctx *ctx, const rtb_scene *scene, FrameParams &F, co
         k_cost_histogram<<<blocks, 256, 0, stream>>>(ctx->d_cost, F.n_tiles, ctx->d_hist);
         const bool smallShard = F.n_tiles <= splitMaxTiles();
         k_cost_offsets<<<1, 32, 0, stream>>>(ctx->d_hist, ctx->d_cursor, ctx->d_heavy, F.n_tiles,
-                                             smallShard ? RTB_HEAVY_BUCKETS_SMALL : RTB_HEAVY_BUCKETS,
-                                             smallShard ? RTB_HEAVY_FRACTION_SMALL : RTB_HEAVY_FRACTION);
+                                             smallShard ? heavyBucketsSmall() : RTB_HEAVY_BUCKETS,
+                                             heavyLimit(F.n_tiles), wideCount(F.n_tiles, scene->long_lists));
         k_cost_scatter<<<blocks, 256, 0, stream>>>(ctx->d_cost, F.n_tiles, ctx->d_cursor, ctx->d_order);
         CUDA_TRY(ctx, cudaGetLastError());
         ctx->order_valid = true;
@@ -505,7 +634,7 @@ static int renderCommon(rtb_ctx *ctx, const rtb_scene *scene, FrameParams &F, co
             stats->n_local_rows = F.n_local_rows;
             CUDA_TRY(ctx, cudaEventElapsedTime(&stats->kernel_ms, ctx->ev[1], ctx->ev[2]));
             CUDA_TRY(ctx, cudaEventElapsedTime(&stats->total_ms, ctx->ev[0], ctx->ev[3]));
-            stats->n_launches = F.skip_heavy ? 5 : 4; // render (+ heavy-tile kernel) + 3 tile-order kernels
+            stats->n_launches = n_kernels + 3; // render kernel(s) + 3 tile-order kernels
         }
     }
     return RTB_OK;
@@ -593,6 +722,7 @@ extern "C" int rtb_trace_primary(rtb_ctx *ctx, const rtb_scene *scene, const rtb
     F.cam = *cam; F.width = width; F.height = height; F.rank = 0; F.world = 1; F.row_block = 8; F.n_local_rows = height;
     F.tiles_x = (width + RTB_TILE_W - 1) / RTB_TILE_W;
     F.n_tiles = F.tiles_x * ((height + RTB_TILE_H - 1) / RTB_TILE_H);
+    F.warps_per_cta = RTB_CTA_THREADS / 32;
     const size_t n = (size_t)width * height;
     DevBuf<int> d_id, d_len, d_buf;
     DevBuf<float> d_t;

@@ -47,8 +47,8 @@ k_whitted_chain_sm(const __grid_constant__ DScene S, const __grid_constant__ Fra
     // tiles, i.e. the first *n_heavy entries of the heaviest-first order (F.skip_heavy).
     if (F.skip_heavy)
     {
-        const unsigned int warpIndex = blockIdx.x * (RTB_CTA_THREADS / 32) + (threadIdx.x >> 5);
-        if ((F.split4 ? (warpIndex >> 2) : warpIndex) >= __ldg(F.n_heavy)) return;
+        const unsigned int warpIndex = blockIdx.x * (unsigned int)F.warps_per_cta + (threadIdx.x >> 5);
+        if ((F.split4 ? (warpIndex >> 2) : warpIndex) + (F.after_wide ? F.n_wide : 0u) >= heavyCount(F)) return;
     }
     if (active)
     {

@@ -168,31 +168,75 @@ __device__ __forceinline__ bool triIntersectT(const TriData &T, const Ray &ray, 
 __device__ __forceinline__ bool triIntersect(const TriData &T, const Ray &ray, float &tOut) { return triIntersectT<false>(T, ray, tOut); }
 
 // nearest hit of a list of triangle references; first in list wins ties (strict <)
-template <bool WINDOW, class Probe>
+// WIDE = false: one lane walks the list (the lanes of a warp hold different rays).
+// WIDE = true : the whole warp holds ONE ray (rtb_chain_wide.cuh) and tests 32 triangles of the list at a
+//               time, one per lane; the nearest accepted hit is found with a warp min-reduction, ties go to
+//               the earliest list position as in the sequential scan.  Every lane returns the same result.
+template <bool WINDOW, bool WIDE, class Probe>
 __device__ __forceinline__ bool nearestInList(const DScene &S, const uint32_t *refs, uint32_t first, uint32_t last,
                                               const Ray &ray, float lo, float hi, int &triOut, float &tOut,
                                               V3 &nOut, Probe &pr)
 {
     float minDistance = FLT_MAX;
     bool found = false;
-    for (uint32_t i = first; i < last; i++)
+    if constexpr (WIDE)
     {
-        const uint32_t idx = __ldg(refs + i);
-        const TriData T = loadTri(S.tri, idx);
-        pr.tri();
-        float t;
-        if (!triIntersect(T, ray, t)) continue;
-        if (WINDOW && !(t >= lo && t <= hi)) continue;
-        if (t < minDistance)
+        const uint32_t lane = threadIdx.x & 31u;
+        for (uint32_t base = first; base < last; base += 32)
         {
-            minDistance = t;
-            triOut = (int)idx;
-            nOut = triNormal(T);
-            found = true;
+            const uint32_t i = base + lane;
+            float t = FLT_MAX;
+            uint32_t idx = 0;
+            bool ok = false;
+            if (i < last)
+            {
+                idx = __ldg(refs + i);
+                const TriData T = loadTri(S.tri, idx);
+                pr.tri();
+                ok = triIntersectT<true>(T, ray, t);
+                if (WINDOW) ok = ok && (t >= lo && t <= hi);
+                ok = ok && t < FLT_MAX; // an accepted t is >= 0.0005; inf / NaN never become a hit in the reference either
+            }
+            // accepted distances are positive floats: their bit patterns order like the values
+            const uint32_t key = ok ? __float_as_uint(t) : 0xffffffffu;
+            const uint32_t best = __reduce_min_sync(0xffffffffu, key);
+            if (best != 0xffffffffu && __uint_as_float(best) < minDistance)
+            { // strict <: an equal distance in a later group of 32 does not replace the earlier one
+                const uint32_t who = __ffs(__ballot_sync(0xffffffffu, key == best)) - 1; // earliest list position
+                minDistance = __uint_as_float(best);
+                triOut = (int)__shfl_sync(0xffffffffu, idx, who);
+                found = true;
+            }
         }
+        if (found)
+        {
+            const float4 q2 = __ldg(S.tri + 3ull * (unsigned int)triOut + 2);
+            nOut = v3(q2.y, q2.z, q2.w);
+        }
+        tOut = minDistance;
+        return found;
     }
-    tOut = minDistance;
-    return found;
+    else
+    {
+        for (uint32_t i = first; i < last; i++)
+        {
+            const uint32_t idx = __ldg(refs + i);
+            const TriData T = loadTri(S.tri, idx);
+            pr.tri();
+            float t;
+            if (!triIntersect(T, ray, t)) continue;
+            if (WINDOW && !(t >= lo && t <= hi)) continue;
+            if (t < minDistance)
+            {
+                minDistance = t;
+                triOut = (int)idx;
+                nOut = triNormal(T);
+                found = true;
+            }
+        }
+        tOut = minDistance;
+        return found;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -262,7 +306,7 @@ __device__ __forceinline__ void indexInGrid(const DScene &S, V3 p, int &i, int &
     if (k > S.nz - 1) k = S.nz - 1;
 }
 
-template <class Probe>
+template <bool WIDE, class Probe>
 __device__ bool gridIntersect(const DScene &S, const Ray &ray, int &triOut, float &tOut, V3 &nOut, Probe &pr)
 {
     int ci, cj, ck;
@@ -294,7 +338,7 @@ __device__ bool gridIntersect(const DScene &S, const Ray &ray, int &triOut, floa
         {
             const unsigned int r = w.y + __popc(w.x & (bit - 1));
             const uint32_t first = __ldg(S.g_start + r), last = __ldg(S.g_start + r + 1);
-            if (nearestInList<false>(S, S.g_tris, first, last, ray, 0.f, 0.f, triOut, tOut, nOut, pr)) return true;
+            if (nearestInList<false, WIDE>(S, S.g_tris, first, last, ray, 0.f, 0.f, triOut, tOut, nOut, pr)) return true;
         }
         // distance to the exit plane of the current cell on each axis; cell corners are recomputed
         // from the integer indices every step (Tunnel.cpp:885-938); IEEE inf/NaN semantics kept
@@ -331,7 +375,7 @@ __device__ __forceinline__ V3 kdPoint(const Ray &ray, float t, float split, int 
     return p;
 }
 
-template <class Probe>
+template <bool WIDE, class Probe>
 __device__ bool kdIntersect(const DScene &S, const Ray &ray, int &triOut, float &tOut, V3 &nOut, Probe &pr)
 {
     float a, b;
@@ -380,7 +424,7 @@ __device__ bool kdIntersect(const DScene &S, const Ray &ray, int &triOut, float 
         }
         pr.step(cur);
         const uint32_t first = nd.x, count = nd.y >> 2;
-        if (count && nearestInList<true>(S, S.kd_tris, first, first + count, ray, enT - 0.001f, exT + 0.001f,
+        if (count && nearestInList<true, WIDE>(S, S.kd_tris, first, first + count, ray, enT - 0.001f, exT + 0.001f,
                                          triOut, tOut, nOut, pr))
             return true;
         // pop: the signed distance intervals are adjacent
@@ -502,8 +546,8 @@ template <class Probe>
 __device__ bool sceneIntersect(const DScene &S, const Ray &ray, Hit &best, Probe &pr)
 {
     return sceneIntersectWith(S, ray, best, pr, [&](int &tri, float &t, V3 &n) {
-        if (S.accel == RTB_ACCEL_REGULAR_GRID || S.accel == RTB_ACCEL_FLAT_GRID) return gridIntersect(S, ray, tri, t, n, pr);
-        if (S.accel == RTB_ACCEL_KD_MEDIAN || S.accel == RTB_ACCEL_KD_SAH) return kdIntersect(S, ray, tri, t, n, pr);
+        if (S.accel == RTB_ACCEL_REGULAR_GRID || S.accel == RTB_ACCEL_FLAT_GRID) return gridIntersect<false>(S, ray, tri, t, n, pr);
+        if (S.accel == RTB_ACCEL_KD_MEDIAN || S.accel == RTB_ACCEL_KD_SAH) return kdIntersect<false>(S, ray, tri, t, n, pr);
         return linearIntersect(S, ray, tri, t, n, pr);
     });
 }

@@ -25,12 +25,31 @@ struct FrameParams
     int rgb8; // RTB_OUTPUT_RGB8
     int tiles_x, n_tiles;
     const unsigned int *order; // [n_tiles] tile ids, heaviest first; nullptr = raster order
-    unsigned int *cost;        // [n_tiles] cycles >> 6 spent on each tile by this launch; may be nullptr
-    const unsigned int *n_heavy; // number of leading entries of `order` that are latency-critical tiles
-    int skip_heavy;              // k_whitted_chain leaves those entries to k_whitted_chain_sm
+    unsigned int *cost;        // [n_tiles] cycles >> 6 the throughput kernel last spent on each tile; may be nullptr
+    const unsigned int *n_heavy; // number of leading entries of `order` that are latency-critical tiles (device value,
+                                 // written by k_cost_offsets of the previous frame); use heavyCount()
+    unsigned int n_wide;         // how many of those (the very heaviest) go to k_whitted_chain_wide (host value)
+    unsigned int heavy_cap;      // upper bound of the latency-critical head the launch grids were sized for (host value)
+    int skip_heavy;              // k_whitted_chain leaves those entries to k_whitted_chain_sm / _wide
+    int record_cost;             // this launch records the cycles each of its tiles took (FrameParams::cost).  Only the
+                                 // throughput kernel does: a tile rendered by a latency-optimised variant keeps the cost
+                                 // it had when the throughput kernel last rendered it, so its rank -- and with it the
+                                 // tier it is rendered by -- is stable from frame to frame (a cost recorded by a faster
+                                 // variant would drop the tile out of its tier on the next frame, and back, forever)
     int split4;                  // this launch gives every tile to 4 warps of 8 lanes (one tile row each)
+    int after_wide;              // this launch (k_whitted_chain_sm) starts at order[n_heavy[1]]
+    int warps_per_cta;           // blockDim / 32
     unsigned long long seed;
 };
+
+// Every kernel of a frame derives the tier boundaries from this one function, so each tile is rendered exactly
+// once whatever the previous frame (possibly of another scene with the same frame geometry) left in *n_heavy
+__device__ __forceinline__ unsigned int heavyCount(const FrameParams &F)
+{
+    unsigned int h = __ldg(F.n_heavy);
+    if (h > F.heavy_cap) h = F.heavy_cap;
+    return h < F.n_wide ? F.n_wide : h;
+}
 
 #define RTB_CTA_THREADS 128 // 4 warp tiles per CTA: small CTAs retire (and free registers) early
 #define RTB_TILE_W 8
@@ -46,10 +65,11 @@ struct FrameParams
 // warp -> tile -> (x, local row, global y); false when the thread has no pixel
 __device__ __forceinline__ bool pixelOfThread(const FrameParams &F, int &x, int &lr, int &y, unsigned int &tile)
 {
-    const unsigned int w = blockIdx.x * (RTB_CTA_THREADS / 32) + (threadIdx.x >> 5);
+    const unsigned int w = blockIdx.x * (unsigned int)F.warps_per_cta + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
-    const unsigned int item = F.split4 ? (w >> 2) : w; // index into the tile order
-    tile = 0;
+    unsigned int item = F.split4 ? (w >> 2) : w; // index into the tile order
+    if (F.after_wide) item += F.n_wide; // k_whitted_chain_sm: its tiles follow the wide kernel's
+    tile = 0xffffffffu; // no tile: finishWarp records no cost
     if (item >= (unsigned int)F.n_tiles) return false;
     tile = F.order ? __ldg(F.order + item) : item;
     const int ty = tile / F.tiles_x, tx = tile - ty * F.tiles_x;
@@ -93,11 +113,10 @@ __device__ __forceinline__ void finishWarp(const FrameParams &F, Counters *g, un
     steps = __reduce_add_sync(0xffffffffu, steps);
     if ((threadIdx.x & 31) == 0)
     {
-        const unsigned int w = blockIdx.x * (RTB_CTA_THREADS / 32) + (threadIdx.x >> 5);
-        if (F.cost && (F.split4 ? (w >> 2) : w) < (unsigned int)F.n_tiles)
-        { // max: a tile rendered by 4 warps costs what its slowest warp took (the buffer is zeroed per frame)
+        if (F.record_cost && F.cost && tile != 0xffffffffu)
+        {
             const long long dt = (clock64() - t_start) >> 6;
-            atomicMax(&F.cost[tile], dt > 0xffffffffll ? 0xffffffffu : (unsigned int)dt);
+            F.cost[tile] = dt > 0xffffffffll ? 0xffffffffu : (unsigned int)dt; // one warp per tile in the recording launches
         }
         if (rays) atomicAdd(&g->rays, (unsigned long long)rays);
         if (tris) atomicAdd(&g->tris, (unsigned long long)tris);
@@ -125,24 +144,34 @@ __global__ void k_cost_histogram(const unsigned int *__restrict__ cost, int n, u
 }
 
 // one thread: hist[] -> descending exclusive offsets in cursor[], hist[] cleared for the next frame.
-// Also counts the "heavy" tiles: those within 8x (12 quarter-octave buckets) of the heaviest tile, capped
-// at 1/16 of the frame.  They run the latency-optimised resumable traversal (rtb_chain_sm.cuh).
+// Also sizes the two latency-critical sets at the head of the order:
+//   (host)      the `wide_count` heaviest tiles: one warp per PIXEL with warp-parallel leaf tests
+//               (rtb_chain_wide.cuh).  Their recorded costs are scaled up generously (FrameParams::cost_scale),
+//               so a tile that is in the set stays in it until it really becomes light;
+//   n_heavy[0]  those plus the tiles within `heavy_buckets` quarter-octaves of the heaviest tile that is NOT in
+//               the first set, at most heavy_limit of them: resumable
+//               traversal (rtb_chain_sm.cuh).
 __global__ void k_cost_offsets(unsigned int *__restrict__ hist, unsigned int *__restrict__ cursor, unsigned int *__restrict__ n_heavy,
-                               int n_tiles, int heavy_buckets, int heavy_fraction)
+                               int n_tiles, int heavy_buckets, int heavy_limit, int wide_count)
 {
     if (threadIdx.x == 0)
     {
-        int top = RTB_COST_BUCKETS - 1;
-        while (top > 0 && hist[top] == 0) top--;
-        unsigned int run = 0, heavy = 0;
+        const unsigned int wide = (unsigned int)min(wide_count, n_tiles);
+        unsigned int run = 0, heavy = wide;
+        int top2 = -1; // bucket of the heaviest tile outside the wide set
         for (int b = RTB_COST_BUCKETS - 1; b >= 0; b--)
         {
             cursor[b] = run;
             run += hist[b];
-            if (b >= top - heavy_buckets && run <= (unsigned int)n_tiles / heavy_fraction) heavy = run;
+            if (top2 < 0 && run > wide) top2 = b;
+            if (top2 >= 0 && b >= top2 - heavy_buckets) heavy = run;
             hist[b] = 0;
         }
-        *n_heavy = heavy;
+        if (heavy < wide) heavy = wide;
+        // a bucket may be cut: with whole buckets only, a well-filled bucket at the top (flat cost distributions)
+        // would leave no latency-critical set at all
+        if (heavy - wide > (unsigned int)heavy_limit) heavy = wide + (unsigned int)heavy_limit;
+        n_heavy[0] = heavy;
     }
 }
 
@@ -194,9 +223,9 @@ template <> struct ProbeCounts<CountProbe>
 #define RTB_CHAIN_MIN_CTAS 8 // 64 registers: measured best (5.9 ms vs 7.5 ms at 4) on the 4K SAH frame
 #endif
 
-// one pixel: walk the chain ray by ray (each ray a complete GeometrySet::intersect), then fold
-template <class Probe>
-__device__ __forceinline__ V3 chainPerRay(const DScene &S, const FrameParams &F, int x, int y, unsigned int &rays, Probe &pr)
+// one pixel: walk the chain ray by ray (each ray a complete GeometrySet::intersect, `isect`), then fold
+template <class Probe, class Isect>
+__device__ __forceinline__ V3 chainWith(const DScene &S, const FrameParams &F, int x, int y, unsigned int &rays, Probe &pr, Isect isect)
 {
     const float dx = 1.0f / F.height, dy = 1.0f / F.height; // MainWindow.cpp:254-255
     const float sx = (x + 0.5f) * dx, sy = 1 - (y + 0.5f) * dy;
@@ -209,7 +238,7 @@ __device__ __forceinline__ V3 chainPerRay(const DScene &S, const FrameParams &F,
     {
         rays++;
         Hit h;
-        if (!sceneIntersect(S, r, h, pr)) break; // Color::Black()
+        if (!isect(r, h)) break; // Color::Black()
         const rtb_material &m = S.mats[h.mat];
         const V3 nl = (dot(h.n, r.d) < 0) ? h.n : h.n * -1;
         const V3 local = matLocal(m, r, h.pos, h.n);
@@ -237,6 +266,12 @@ __device__ __forceinline__ V3 chainPerRay(const DScene &S, const FrameParams &F,
 }
 
 template <class Probe>
+__device__ __forceinline__ V3 chainPerRay(const DScene &S, const FrameParams &F, int x, int y, unsigned int &rays, Probe &pr)
+{
+    return chainWith(S, F, x, y, rays, pr, [&](const Ray &r, Hit &h) { return sceneIntersect(S, r, h, pr); });
+}
+
+template <class Probe>
 __device__ __forceinline__ void storePixel(const FrameParams &F, float *out, int x, int lr, int y, V3 c, long long t_start,
                                            unsigned int rays, const Probe &pr)
 {
@@ -260,7 +295,7 @@ k_whitted_chain(const __grid_constant__ DScene S, const __grid_constant__ FrameP
     const bool active = pixelOfThread(F, x, lr, y, tile);
     unsigned int rays = 0;
     Probe pr;
-    if (F.skip_heavy && blockIdx.x * (RTB_CTA_THREADS / 32) + (threadIdx.x >> 5) < __ldg(F.n_heavy)) return;
+    if (F.skip_heavy && blockIdx.x * (unsigned int)F.warps_per_cta + (threadIdx.x >> 5) < heavyCount(F)) return;
     if (active)
     {
         const V3 c = chainPerRay(S, F, x, y, rays, pr);
