@@ -43,8 +43,11 @@ WORKLOADS = {
     "p5_sah_400": dict(preset=5, algorithm="sah", segments=150, width=400, height=300, samples=1,
                        desc="preset 5, k-d SAH, Whitted, demo default 400x300, 1 spp"),
 }
-EXTRAS = ["p5_rgrid_4k", "p5_kd_4k", "p5_fgrid_4k", "p4_sah_4k", "p2_smallpt_64"]
-ROW_BLOCK = int(os.environ.get("RTB_ROW_BLOCK", "16"))  # rows per dealt block (multiple of 8)
+WORKLOADS["p5_rgrid_400"] = dict(WORKLOADS["p5_rgrid_4k"], width=400, height=300,
+                                 desc="preset 5, regular grid 400x5x400, Whitted, demo default 400x300, 1 spp")
+# p5_*_400 is the frame the reference arm / cpu_baseline renders on the host cores: same scene, camera, size
+EXTRAS = ["p5_rgrid_4k", "p5_kd_4k", "p5_fgrid_4k", "p4_sah_4k", "p2_smallpt_64", "p5_sah_400", "p5_rgrid_400"]
+ROW_BLOCK = int(os.environ.get("RTB_ROW_BLOCK", "8"))  # rows per dealt block (multiple of 8)
 METRIC = "Mrays/s on tunnel scenes (grid/k-d tree) at 1/2/4/8 B200 vs CPU render secs"
 
 
@@ -155,8 +158,9 @@ def run_b200(args, wl_name):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
+        # stdout carries the one JSON line: NCCL's own output (its version banner is printed to stdout at every
+        # debug level above NONE) goes to a file unless the caller asked for something else
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/rtb200_nccl.%h.%p.log")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev_t = torch.device("cuda", local)
 
@@ -207,8 +211,6 @@ def run_b200(args, wl_name):
             dist.all_gather_into_tensor(gathered.view(world * rows_max, W, 3), local_buf)
             rtb200.unshard_device(ctx, gathered.data_ptr(), image.data_ptr(), W, H, world, ROW_BLOCK, rows_max, stream)
 
-    # render kernel + heavy-tile kernel (k-d scenes, once a tile order exists) + 3 tile-order kernels (+ unshard)
-    launches_per_step = (5 if wl["algorithm"] in ("sah", "kd", "fgrid") else 4) + (1 if world > 1 else 0)
 
     # ray / test / step counts of one frame (deterministic), outside the timed region
     cframe = rtb200.make_frame(W, H, samples=spp, seed=0, rank=rank, world=world, row_block=ROW_BLOCK, counters=1)
@@ -224,6 +226,10 @@ def run_b200(args, wl_name):
 
     # kernel-only duration of this rank's render launch (CUDA events on the launching stream)
     kst = dscene.render_device(scene.camera, scene.setting, frame, tmp.data_ptr(), stream, want_stats=True)
+    # kernels of this library per step, as counted by the library for this frame (rtb_stats.n_launches): the render
+    # kernels (1-3: per-ray walk, resumable walk of the latency-critical tiles, warp-per-pixel walk of the heaviest
+    # tiles) + 3 tile-order kernels, + the unshard kernel at N > 1
+    launches_per_step = int(kst["n_launches"]) + (1 if world > 1 else 0)
 
     sampler = ClockSampler(local) if rank == 0 else None
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -330,7 +336,7 @@ def run_b200(args, wl_name):
                 f2 = rtb200.make_frame(o["width"], o["height"], samples=o["samples"])
                 d2.render_device(s2.camera, s2.setting, f2, buf.data_ptr(), stream, want_stats=True)
                 best = None
-                for _ in range(3):
+                for _ in range(5):
                     st = d2.render_device(s2.camera, s2.setting, f2, buf.data_ptr(), stream, want_stats=True)
                     best = st if best is None or st["kernel_ms"] < best["kernel_ms"] else best
                 others[name] = {"Mrays/s": best["n_rays"] / best["kernel_ms"] / 1e3, "ms": best["kernel_ms"],
@@ -365,7 +371,7 @@ def run_b200(args, wl_name):
                 "roofline": roofline, "cpu_baseline": cpu,
                 "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "ms_per_step": e2e_ms, "steps": e2e_steps,
-                        "path": "rtb_scene_upload (H2D) + rtb_render (kernel + D2H of the float framebuffer to pinned host) + rtb_scene_free per step",
+                        "path": "rtb_scene_upload (H2D) + rtb_render (kernels store the float framebuffer straight into the caller's page-locked host buffer over PCIe; pageable buffers take a device frame + D2H copy) + rtb_scene_free per step",
                         "rgb8_output_stage": {"value": rays_frame / e2e8_ms / 1e3, "ms_per_step": e2e8_ms, "d2h_bytes_per_step": int(rows * W * 3),
                                               "note": "same call with RTB_OUTPUT_RGB8: saturate + (int)(c*255) on the GPU as the reference's Render ends (MainWindow.cpp:305-311)"}},
                 "gpu_launches": launches_per_step * args.steps,
