@@ -1,0 +1,338 @@
+// rtb_chain_oct.cuh -- Whitted reflection chains, EIGHT LANES PER PIXEL (sm_100a).
+//
+// Same arithmetic and same results as k_whitted_chain (rtb_kernels.cuh): the k-d walk is reference
+// Tunnel.cpp:1163-1297, the grid walk Tunnel.cpp:819-970, shading MainWindow.cpp:69-143.
+//
+// A warp is four groups of eight lanes; a group owns one pixel at a time.  The eight lanes of a group hold the
+// same ray and the same traversal state (they repeat the scalar work: accelerator steps, shading) and test
+// EIGHT triangles of the current leaf / cell list at once, one per lane; a 3-step butterfly inside the group
+// finds the nearest accepted hit, ties going to the earliest list position as in the reference's scan.
+// The four groups run the resumable state machine of rtb_chain_sm.cuh independently (NEXT pixel / accelerator
+// STEP / list round LEAF / SHADE), so a group that finishes a ray starts its next one at once.
+//
+// Why: nothing in a reflection chain is parallel except the triangle tests of one list.  With one lane per
+// pixel a chain is (steps + tests) serial latencies; here it is (steps + tests / 8), for ~2x the warp
+// instructions of the per-ray kernel on a k-d tree (the eight lanes repeat the node walk) -- against 8x the
+// latency gain and ~4-8x the instructions of the warp-per-pixel kernel (rtb_chain_wide.cuh).  That makes it the
+// right tool for the MANY moderately heavy tiles of a multi-GPU shard: on the tunnel frames ~1 % of the tiles
+// are within 2x of the heaviest one, far too many for a warp per pixel, and a shard is bound by their latency.
+// Measured (one B200, kernel ms, gpurun_out/sweep5.log / sweep6.log): worst 1/8 shard of the 4K frame
+// SAH 1.99 -> 1.42, k-d median 4.48 -> 3.41, preset 4 SAH 1.80 -> 1.44; 1280x960 SAH 1.78 -> 1.44.
+// Rejected on measurement: as the tier of a whole 4K frame (throughput-bound: 6.01 -> 6.85 ms) and, with eight
+// pixels per group (F.oct_pixels = 8), as the throughput kernel of the regular grid (14.4 -> 60 ms).
+#pragma once
+#include "rtb_kernels.cuh"
+#include "rtb_chain_sm.cuh"
+
+namespace rtb {
+
+enum { OCT_NEXT = 4 };
+
+#ifndef RTB_OCT_MIN_CTAS
+#define RTB_OCT_MIN_CTAS 5
+#endif
+
+// F.oct_pixels = 8: one warp per tile, group g renders row g of the tile (8 pixels, one after the other);
+// F.oct_pixels = 1: eight warps per tile, warp (w & 7) group g renders pixel (w & 7) * 4 + g.
+template <class Probe, bool GRID>
+__global__ void __launch_bounds__(RTB_CTA_THREADS, RTB_OCT_MIN_CTAS)
+k_whitted_chain_oct(const __grid_constant__ DScene S, const __grid_constant__ FrameParams F, float *__restrict__ out,
+                    Counters *__restrict__ counters)
+{
+    const long long t_start = clock64();
+    const unsigned int w = blockIdx.x * (RTB_CTA_THREADS / 32) + (threadIdx.x >> 5);
+    const unsigned int lane = threadIdx.x & 31u, g = lane >> 3, sub = lane & 7u;
+    const int P = F.oct_pixels;
+    unsigned int item = (P == 8 ? w : (w >> 3)) + F.item_base;
+    if (item >= F.item_end || item >= (unsigned int)F.n_tiles) return; // warp-uniform
+    if (F.item_end_dev && item >= heavyCount(F)) return;
+    const unsigned int tile = F.order ? __ldg(F.order + item) : item;
+    const int ty = tile / F.tiles_x, tx = tile - ty * F.tiles_x;
+
+    unsigned int rays = 0;
+    Probe prTop, pr; // prTop: work all eight lanes repeat (top-level geometries); pr: the tunnel walk
+
+    const V3 zero = v3(0, 0, 0);
+    float4 fold[RTB_MAX_DEPTH + 1];
+    int4 stack[GRID ? 1 : RTB_KD_STACK];
+    int nfold = 0, depth = 0;
+    V3 c = zero;
+    Ray r;
+    r.o = zero; r.d = v3(0, 0, 1);
+    int x = 0, lr = 0, y = 0, k = -1;
+
+    int st = OCT_NEXT;
+    // k-d (see kdIntersect)
+    float enT = 0, exT = 0;
+    V3 enP = zero, exP = zero;
+    int enPt = 0, exPt = 1, exNode = -1, exPrev = 0, cur = 0;
+    // grid (see gridIntersect)
+    int ci = 0, cj = 0, ck = 0;
+    float cd = 0;
+    V3 cp = zero;
+    bool px = false, py = false, pz = false;
+    // list
+    unsigned int li = 0, lend = 0;
+    float lo = 0, hi = 0, minD = FLT_MAX;
+    int hitTri = -1;
+    bool tunnelHit = false;
+
+    auto beginRay = [&]() {
+        rays++;
+        tunnelHit = false;
+        hitTri = -1;
+        minD = FLT_MAX;
+        if (GRID)
+        {
+            if (r.o.x < S.g_origin.x || r.o.x > S.g_far.x || r.o.y < S.g_origin.y || r.o.y > S.g_far.y ||
+                r.o.z < S.g_origin.z || r.o.z > S.g_far.z)
+            {
+                float entry, exit;
+                if (!boxIntersect(S.g_origin, S.g_extent, r, entry, exit)) { st = SM_SHADE; return; }
+                cd = entry;
+                cp = at(r, entry);
+                indexInGrid(S, cp, ci, cj, ck);
+            }
+            else
+            {
+                cp = r.o;
+                cd = 0;
+                indexInGrid(S, r.o, ci, cj, ck);
+            }
+            px = r.d.x > 0; py = r.d.y > 0; pz = r.d.z > 0;
+            st = SM_STEP;
+        }
+        else
+        {
+            float a, b;
+            if (!boxIntersect(S.kd_min, S.kd_size, r, a, b)) { st = SM_SHADE; return; }
+            enT = a;
+            enP = (a >= 0) ? (r.o + r.d * a) : r.o;
+            enPt = 0;
+            exPt = 1; exT = b; exP = r.o + r.d * b; exNode = -1; exPrev = 0;
+            stack[1] = make_int4(-1, __float_as_int(b), 0, 3);
+            cur = 0;
+            st = SM_STEP;
+        }
+    };
+    auto gridAdvance = [&]() { // Tunnel.cpp:885-966
+        float ddx, ddy, ddz;
+        if (px) ddx = ((S.g_origin.x + (ci + 1) * S.g_cell.x) - cp.x) / r.d.x;
+        else ddx = (cp.x - (S.g_origin.x + ci * S.g_cell.x)) / -r.d.x;
+        if (py) ddy = ((S.g_origin.y + (cj + 1) * S.g_cell.y) - cp.y) / r.d.y;
+        else ddy = (cp.y - (S.g_origin.y + cj * S.g_cell.y)) / -r.d.y;
+        if (pz) ddz = ((S.g_origin.z + (ck + 1) * S.g_cell.z) - cp.z) / r.d.z;
+        else ddz = (cp.z - (S.g_origin.z + ck * S.g_cell.z)) / -r.d.z;
+        if (ddx < ddy && ddx < ddz) { ci += px ? 1 : -1; cd += ddx; }
+        else if (ddy < ddz) { cj += py ? 1 : -1; cd += ddy; }
+        else { ck += pz ? 1 : -1; cd += ddz; }
+        cp = at(r, cd);
+        if (ci < 0 || ci > S.nx - 1 || cj < 0 || cj > S.ny - 1 || ck < 0 || ck > S.nz - 1) st = SM_SHADE;
+        else st = SM_STEP;
+    };
+    auto kdPop = [&]() { // Tunnel.cpp:1285-1292
+        enPt = exPt; enT = exT; enP = exP;
+        cur = exNode;
+        if (cur == -1) { st = SM_SHADE; return; }
+        exPt = exPrev;
+        const int4 e = stack[exPt];
+        exNode = e.x; exT = __int_as_float(e.y); exPrev = e.w >> 2;
+        exP = kdPoint(r, exT, __int_as_float(e.z), e.w & 3);
+        st = SM_STEP;
+    };
+    auto listDone = [&]() {
+        if (hitTri >= 0) { tunnelHit = true; st = SM_SHADE; return; }
+        if (GRID) gridAdvance();
+        else kdPop();
+    };
+
+    while (true)
+    {
+        // all 32 lanes are here together: the loop condition below is warp-uniform
+        const unsigned int leafMask = __ballot_sync(0xffffffffu, st == SM_LEAF);
+        if (__all_sync(0xffffffffu, st == SM_DONE)) break;
+
+        if (st == OCT_NEXT)
+        { // the group's next pixel
+            k++;
+            if (k >= P) st = SM_DONE;
+            else
+            {
+                const unsigned int p = (P == 8) ? (g * 8u + (unsigned int)k) : ((w & 7u) * 4u + g);
+                x = tx * RTB_TILE_W + (int)(p & 7u);
+                lr = ty * RTB_TILE_H + (int)(p >> 3);
+                const int lb = lr / F.row_block;
+                y = (lb * F.world + F.rank) * F.row_block + (lr - lb * F.row_block);
+                if (x < F.width && lr < F.n_local_rows && y < F.height)
+                {
+                    const float dx = 1.0f / F.height, dy = 1.0f / F.height;
+                    const float sx = (x + 0.5f) * dx, sy = 1 - (y + 0.5f) * dy;
+                    r = generateRay(F.cam, sx, sy);
+                    nfold = 0; depth = 0; c = zero;
+                    beginRay();
+                }
+            }
+        }
+        if (st == SM_STEP)
+        {
+#pragma unroll 1
+            while (st == SM_STEP)
+            {
+                if (GRID)
+                {
+                    const int cell = (ci * S.ny + cj) * S.nz + ck;
+                    pr.step(cell);
+                    const uint2 wd = __ldg(S.g_words + ((unsigned int)cell >> 5));
+                    const unsigned int bit = 1u << (cell & 31);
+                    if (wd.x & bit)
+                    {
+                        const unsigned int rk = wd.y + __popc(wd.x & (bit - 1));
+                        li = __ldg(S.g_start + rk);
+                        lend = __ldg(S.g_start + rk + 1);
+                        minD = FLT_MAX; hitTri = -1;
+                        st = SM_LEAF;
+                    }
+                    else gridAdvance();
+                }
+                else
+                {
+                    const uint2 nd = __ldg(S.kd_nodes + cur);
+                    pr.step(cur);
+                    if ((nd.y & 3u) == 3u)
+                    {
+                        li = nd.x;
+                        lend = nd.x + (nd.y >> 2);
+                        lo = enT - 0.001f; hi = exT + 0.001f;
+                        minD = FLT_MAX; hitTri = -1;
+                        if (li == lend) kdPop();
+                        else st = SM_LEAF;
+                    }
+                    else
+                    {
+                        const float splitVal = __uint_as_float(nd.x);
+                        const int axis = (int)(nd.y & 3u);
+                        const int right = (int)(nd.y >> 2), left = cur + 1;
+                        const float en = comp(enP, axis), ex = comp(exP, axis);
+                        int farChild = -1;
+                        bool both = false;
+                        if (en <= splitVal)
+                        {
+                            if (ex <= splitVal) cur = left;
+                            else { farChild = right; cur = left; both = true; }
+                        }
+                        else
+                        {
+                            if (splitVal < ex) cur = right;
+                            else { farChild = left; cur = right; both = true; }
+                        }
+                        if (both)
+                        {
+                            const float t = (splitVal - comp(r.o, axis)) / comp(r.d, axis);
+                            const int tmp = exPt++;
+                            if (exPt == enPt) exPt += 1;
+                            exPrev = tmp; exT = t; exNode = farChild;
+                            exP = kdPoint(r, t, splitVal, axis);
+                            stack[exPt] = make_int4(farChild, __float_as_int(t), __float_as_int(splitVal), axis | (tmp << 2));
+                        }
+                    }
+                }
+            }
+        }
+        if ((leafMask >> lane) & 1u)
+        { // one round: eight triangles of the list, one per lane (the group was in LEAF at the top of this iteration)
+            const unsigned int i = li + sub;
+            float t = FLT_MAX;
+            unsigned int idx = 0;
+            bool ok = false;
+            if (i < lend)
+            {
+                idx = __ldg((GRID ? S.g_tris : S.kd_tris) + i);
+                const TriData T = loadTri(S.tri, idx);
+                pr.tri();
+                ok = triIntersectT<true>(T, r, t);
+                if (!GRID) ok = ok && (t >= lo && t <= hi);
+                ok = ok && t < FLT_MAX; // accepted distances are >= 0.0005; inf / NaN never become a hit in the reference either
+            }
+            const unsigned int key = ok ? __float_as_uint(t) : 0xffffffffu; // positive floats order like their bit patterns
+            unsigned int best = key;
+            best = min(best, __shfl_xor_sync(leafMask, best, 1));
+            best = min(best, __shfl_xor_sync(leafMask, best, 2));
+            best = min(best, __shfl_xor_sync(leafMask, best, 4));
+            const unsigned int eq = (__ballot_sync(leafMask, ok && key == best) >> (g * 8u)) & 0xffu;
+            const unsigned int winner = eq ? (unsigned int)(__ffs(eq) - 1) : 0u; // earliest list position among equal distances
+            const unsigned int idxW = __shfl_sync(leafMask, idx, g * 8u + winner);
+            if (eq && __uint_as_float(best) < minD)
+            { // strict <: an equal distance in a later round does not replace the earlier one
+                minD = __uint_as_float(best);
+                hitTri = (int)idxW;
+            }
+            li += 8;
+            if (li >= lend) listDone();
+        }
+        if (st == SM_SHADE)
+        {
+            Hit h;
+            const bool any = sceneIntersectWith(S, r, h, prTop, [&](int &tri, float &t, V3 &n) {
+                if (!tunnelHit) return false;
+                tri = hitTri;
+                t = minD;
+                const float4 q2 = __ldg(S.tri + 3ull * (unsigned int)hitTri + 2);
+                n = v3(q2.y, q2.z, q2.w);
+                return true;
+            });
+            bool spawned = false;
+            if (any)
+            {
+                const rtb_material &m = S.mats[h.mat];
+                const V3 nl = (dot(h.n, r.d) < 0) ? h.n : h.n * -1;
+                const V3 local = matLocal(m, r, h.pos, h.n);
+                if (++depth <= F.setting.max_depth && depth <= RTB_MAX_DEPTH)
+                {
+                    const V3 diffusive = (m.diffusiveness > 0) ? local : zero;
+                    const V3 term = diffusive * m.diffusiveness;
+                    if (m.reflectiveness > 0)
+                    {
+                        fold[nfold++] = make_float4(term.x, term.y, term.z, m.reflectiveness);
+                        const V3 v = r.d - nl * 2 * dot(nl, r.d);
+                        r.o = h.pos;
+                        r.d = v;
+                        spawned = true;
+                    }
+                    else c = term + zero * m.reflectiveness + zero * m.refractiveness;
+                }
+            }
+            if (spawned) beginRay();
+            else
+            { // fold innermost-first, store, next pixel
+                while (nfold > 0)
+                {
+                    const float4 f = fold[--nfold];
+                    c = v3(f.x, f.y, f.z) + c * f.w + zero * 0.0f;
+                }
+                if (sub == 0) storePixel(F, out, x, lr, y, c, t_start, rays, pr);
+                st = OCT_NEXT;
+            }
+        }
+    }
+    // counters: rays, accelerator steps and top-level tests are identical on a group's eight lanes (sub 0 counts);
+    // the list tests are distinct per lane
+    unsigned int tris = ProbeCounts<Probe>::tris(pr) + (sub == 0 ? ProbeCounts<Probe>::tris(prTop) : 0u);
+    unsigned int steps = sub == 0 ? ProbeCounts<Probe>::steps(pr) : 0u;
+    unsigned int nr = sub == 0 ? rays : 0u;
+    tris = __reduce_add_sync(0xffffffffu, tris);
+    steps = __reduce_add_sync(0xffffffffu, steps);
+    nr = __reduce_add_sync(0xffffffffu, nr);
+    if (lane == 0)
+    {
+        if (F.record_cost && F.cost)
+        {
+            const long long dt = (clock64() - t_start) >> 6;
+            F.cost[tile] = dt > 0xffffffffll ? 0xffffffffu : (unsigned int)dt;
+        }
+        if (nr) atomicAdd(&counters->rays, (unsigned long long)nr);
+        if (tris) atomicAdd(&counters->tris, (unsigned long long)tris);
+        if (steps) atomicAdd(&counters->steps, (unsigned long long)steps);
+    }
+}
+
+} // namespace rtb
