@@ -119,6 +119,17 @@ def cpu_reference(wl, width, height, repeat, warmup=0):
     return dict(kind=kind, cores=cores, rays=int(counted["n_rays"]), ms=times, prepare_ms=float(r["prepare_ms"]))
 
 
+_JSON_FD = None
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def run_reference(args, wl_name):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -141,7 +152,7 @@ def run_reference(args, wl_name):
                              "render_s": ms / 1e3, "prepare_s": res["prepare_ms"] / 1e3},
             "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---- the B200 arm ----------------------------------------------------------------------------------
@@ -158,9 +169,6 @@ def run_b200(args, wl_name):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        # stdout carries the one JSON line: NCCL's own output (its version banner is printed to stdout at every
-        # debug level above NONE) goes to a file unless the caller asked for something else
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/rtb200_nccl.%h.%p.log")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev_t = torch.device("cuda", local)
 
@@ -376,7 +384,7 @@ def run_b200(args, wl_name):
                                               "note": "same call with RTB_OUTPUT_RGB8: saturate + (int)(c*255) on the GPU as the reference's Render ends (MainWindow.cpp:305-311)"}},
                 "gpu_launches": launches_per_step * args.steps,
                 "kernel_ms_max_over_ranks": kernel_ms_max, "clocks": clocks, "others": others}
-        print(json.dumps(line), flush=True)
+        emit(line)
     dscene.close(); scene.close(); ctx.close()
     if dist:
         dist.barrier()
@@ -393,6 +401,12 @@ def main():
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly one JSON line: file descriptor 1 is pointed at stderr for the duration of the run
+    # (NCCL prints its version banner to stdout whatever NCCL_DEBUG_FILE says) and emit() writes to the saved one
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args, args.workload)
     else:

@@ -503,22 +503,13 @@ static int launchRender(rtb_ctx *ctx, const rtb_scene *scene, FrameParams &F, fl
             k_whitted_chain_wide<Probe><<<wgrid, RTB_CTA_THREADS, 0, ctx->aux>>>(scene->d, Wd, out, counters);
             n_kernels++;
         }
-        // k_whitted_chain_oct: measured (gpurun_out/sweep5.log) as the latency tier of small k-d shards -- worst 1/8
-        // shard of the 4K frame SAH 1.99 -> 1.45 ms, k-d median 4.48 -> 3.41, 1280x960 SAH 1.78 -> 1.44 -- but slower
-        // as the tier of a whole 4K frame (6.01 -> 6.85, throughput-bound) and 4x slower than the resumable walk as
-        // the throughput kernel of the regular grid (RTB_OCT_RGRID, kept as a switch).
-        static const int octRgrid = (int)tunable("RTB_OCT_RGRID", 0), octTierForced = (int)tunable("RTB_OCT_TIER", -1);
+        // k_whitted_chain_oct is the latency tier of small k-d shards: worst 1/8 shard of the 4K frame SAH 1.99 -> 1.42 ms,
+        // k-d median 4.48 -> 3.41, 1280x960 SAH 1.78 -> 1.44 (gpurun_out/sweep5.log, sweep6.log).  Not for a whole 4K
+        // frame (throughput-bound: 6.01 -> 6.85 ms) and not for the grids (flat grid 3.20 -> 3.30, regular grid: no gain
+        // next to the warp-per-pixel tier, sweep7.log): those keep the resumable walk.
+        static const int octTierForced = (int)tunable("RTB_OCT_TIER", -1);
         const int octTier = octTierForced >= 0 ? octTierForced : (smallShard && kd_accel);
-        if (accel == RTB_ACCEL_REGULAR_GRID && octRgrid)
-        { // eight lanes per pixel for everything after the wide tiles
-            FrameParams H = F;
-            H.item_base = F.n_wide; H.item_end = (unsigned int)F.n_tiles; H.item_end_dev = 0; H.oct_pixels = 8;
-            const dim3 ogrid((unsigned int)((F.n_tiles - nWide + warpsPerCta - 1) / warpsPerCta));
-            k_whitted_chain_oct<Probe, true><<<ogrid, RTB_CTA_THREADS, 0, stream>>>(scene->d, H, out, counters); // records: it is this frame's throughput kernel
-            CUDA_TRY(ctx, cudaEventRecord(ctx->join, ctx->aux));
-            CUDA_TRY(ctx, cudaStreamWaitEvent(stream, ctx->join, 0));
-        }
-        else if (accel == RTB_ACCEL_REGULAR_GRID)
+        if (accel == RTB_ACCEL_REGULAR_GRID)
         { // one resumable launch for everything after the wide tiles
             FrameParams H = F;
             H.after_wide = 1;
@@ -540,7 +531,7 @@ static int launchRender(rtb_ctx *ctx, const rtb_scene *scene, FrameParams &F, fl
             if (heavyLimit(F.n_tiles) > 0 && octTier)
             { // eight lanes per pixel, eight warps per tile
                 H.skip_heavy = 0; H.after_wide = 0; H.split4 = 0;
-                H.item_base = F.n_wide; H.item_end = F.n_wide + (unsigned int)heavyLimit(F.n_tiles); H.item_end_dev = 1; H.oct_pixels = 1;
+                H.item_base = F.n_wide; H.item_end = F.n_wide + (unsigned int)heavyLimit(F.n_tiles);
                 const dim3 ogrid(((unsigned int)heavyLimit(F.n_tiles) * 8u + warpsPerCta - 1) / warpsPerCta);
                 if (grid_accel) k_whitted_chain_oct<Probe, true><<<ogrid, RTB_CTA_THREADS, 0, ctx->aux>>>(scene->d, H, out, counters);
                 else k_whitted_chain_oct<Probe, false><<<ogrid, RTB_CTA_THREADS, 0, ctx->aux>>>(scene->d, H, out, counters);

@@ -19,7 +19,7 @@
 // Measured (one B200, kernel ms, gpurun_out/sweep5.log / sweep6.log): worst 1/8 shard of the 4K frame
 // SAH 1.99 -> 1.42, k-d median 4.48 -> 3.41, preset 4 SAH 1.80 -> 1.44; 1280x960 SAH 1.78 -> 1.44.
 // Rejected on measurement: as the tier of a whole 4K frame (throughput-bound: 6.01 -> 6.85 ms) and, with eight
-// pixels per group (F.oct_pixels = 8), as the throughput kernel of the regular grid (14.4 -> 60 ms).
+// pixels per group and one warp per tile, as the throughput kernel of the regular grid (14.4 -> 60 ms).
 #pragma once
 #include "rtb_kernels.cuh"
 #include "rtb_chain_sm.cuh"
@@ -32,8 +32,7 @@ enum { OCT_NEXT = 4 };
 #define RTB_OCT_MIN_CTAS 5
 #endif
 
-// F.oct_pixels = 8: one warp per tile, group g renders row g of the tile (8 pixels, one after the other);
-// F.oct_pixels = 1: eight warps per tile, warp (w & 7) group g renders pixel (w & 7) * 4 + g.
+// Eight warps per tile: group g of warp (w & 7) renders pixel (w & 7) * 4 + g of the tile.
 template <class Probe, bool GRID>
 __global__ void __launch_bounds__(RTB_CTA_THREADS, RTB_OCT_MIN_CTAS)
 k_whitted_chain_oct(const __grid_constant__ DScene S, const __grid_constant__ FrameParams F, float *__restrict__ out,
@@ -42,10 +41,8 @@ k_whitted_chain_oct(const __grid_constant__ DScene S, const __grid_constant__ Fr
     const long long t_start = clock64();
     const unsigned int w = blockIdx.x * (RTB_CTA_THREADS / 32) + (threadIdx.x >> 5);
     const unsigned int lane = threadIdx.x & 31u, g = lane >> 3, sub = lane & 7u;
-    const int P = F.oct_pixels;
-    unsigned int item = (P == 8 ? w : (w >> 3)) + F.item_base;
-    if (item >= F.item_end || item >= (unsigned int)F.n_tiles) return; // warp-uniform
-    if (F.item_end_dev && item >= heavyCount(F)) return;
+    const unsigned int item = (w >> 3) + F.item_base;
+    if (item >= F.item_end || item >= (unsigned int)F.n_tiles || item >= heavyCount(F)) return; // warp-uniform
     const unsigned int tile = F.order ? __ldg(F.order + item) : item;
     const int ty = tile / F.tiles_x, tx = tile - ty * F.tiles_x;
 
@@ -155,10 +152,10 @@ k_whitted_chain_oct(const __grid_constant__ DScene S, const __grid_constant__ Fr
         if (st == OCT_NEXT)
         { // the group's next pixel
             k++;
-            if (k >= P) st = SM_DONE;
+            if (k >= 1) st = SM_DONE;
             else
             {
-                const unsigned int p = (P == 8) ? (g * 8u + (unsigned int)k) : ((w & 7u) * 4u + g);
+                const unsigned int p = (w & 7u) * 4u + g;
                 x = tx * RTB_TILE_W + (int)(p & 7u);
                 lr = ty * RTB_TILE_H + (int)(p >> 3);
                 const int lb = lr / F.row_block;
@@ -324,11 +321,7 @@ k_whitted_chain_oct(const __grid_constant__ DScene S, const __grid_constant__ Fr
     nr = __reduce_add_sync(0xffffffffu, nr);
     if (lane == 0)
     {
-        if (F.record_cost && F.cost)
-        {
-            const long long dt = (clock64() - t_start) >> 6;
-            F.cost[tile] = dt > 0xffffffffll ? 0xffffffffu : (unsigned int)dt;
-        }
+        // no cost is recorded: the tile keeps the cost the throughput kernel measured (FrameParams::record_cost)
         if (nr) atomicAdd(&counters->rays, (unsigned long long)nr);
         if (tris) atomicAdd(&counters->tris, (unsigned long long)tris);
         if (steps) atomicAdd(&counters->steps, (unsigned long long)steps);

@@ -37,12 +37,10 @@ struct FrameParams
                                  // tier it is rendered by -- is stable from frame to frame (a cost recorded by a faster
                                  // variant would drop the tile out of its tier on the next frame, and back, forever)
     int split4;                  // this launch gives every tile to 4 warps of 8 lanes (one tile row each)
-    int after_wide;              // this launch (k_whitted_chain_sm) starts at order[n_heavy[1]]
+    int after_wide;              // this launch (k_whitted_chain_sm) starts at order[n_wide]
     int warps_per_cta;           // blockDim / 32
-    // k_whitted_chain_oct (rtb_chain_oct.cuh): entries [item_base, item_end) of the order, cut at heavyCount() when
-    // item_end_dev; oct_pixels = 8 (one warp per tile) or 1 (eight warps per tile)
+    // k_whitted_chain_oct (rtb_chain_oct.cuh): entries [item_base, min(item_end, heavyCount())) of the order
     unsigned int item_base, item_end;
-    int item_end_dev, oct_pixels;
     unsigned long long seed;
 };
 
