@@ -104,3 +104,28 @@ build_variant() { # <hooks 0|1> <output>
 build_variant 1 "$OUT/libref.so"
 build_variant 0 "$OUT/libref_timing.so"
 echo "built $OUT/libref.so $OUT/libref_timing.so"
+
+# ---- PerformanceTest (src/PerformanceTest): its own sources + ref/ref_pt_driver.cpp -> libref_pt.so ----------
+# main.cpp (console front end) and Utils.cpp (Win32) are replaced by the driver; two mechanical patches, both the
+# MSVC-dialect kind already applied to RayTracingOpt above (P1, P3), none touching arithmetic.
+PT="$REF/src/PerformanceTest"
+if [ -d "$PT" ]; then
+    mkdir -p "$TMP/pt"
+    cp "$PT"/*.h "$PT"/*.cpp "$TMP/pt/"
+    rm -f "$TMP/pt/main.cpp" "$TMP/pt/Utils.cpp"
+    expect_pt() { sed -n "${2}p" "$PT/$1" | grep -qF -- "$3" || { echo "build_ref.sh: PerformanceTest/$1:$2 does not contain '$3'" >&2; exit 4; }; }
+    expect_pt RayContext.h 10 'struct RayContext() :'
+    sed -i '10s/struct RayContext() :/RayContext() :/' "$TMP/pt/RayContext.h"
+    expect_pt ConvexAcc.cpp 23 'intersectWithPolygonAtOrigin(Ray(newOrigin, newDir), distance)'
+    sed -i '23s/.*/    Ray refTmpRay(newOrigin, newDir); bool intersect = intersectWithPolygonAtOrigin(refTmpRay, distance);/' "$TMP/pt/ConvexAcc.cpp"
+    PTFLAGS="-O2 -std=c++14 -fopenmp -fpermissive -w -Wno-narrowing -ffp-contract=off -fPIC -include $HERE/ref/compat.h -I$TMP/pt -I$HERE"
+    ptobjs=()
+    for f in "$TMP"/pt/*.cpp; do
+        g++ $PTFLAGS -c "$f" -o "${f%.cpp}.o" &
+        ptobjs+=("${f%.cpp}.o")
+    done
+    g++ $PTFLAGS -c "$HERE/ref/ref_pt_driver.cpp" -o "$TMP/pt/ref_pt_driver.o" &
+    wait
+    g++ -shared -fopenmp -o "$OUT/libref_pt.so" "${ptobjs[@]}" "$TMP/pt/ref_pt_driver.o"
+    echo "built $OUT/libref_pt.so"
+fi

@@ -101,7 +101,8 @@ int ref_run(oracle_job *job);
  * them with rand() -- each mirror-reflected until it hits the exit plane, misses, or exceeds max_depth.
  * PerformanceTest's Triangle / Plane / Grid sources equal RayTracingOpt's except for a `type` tag, so
  * libref.so runs this workload on the reference's own intersection code (grid, k-d median, SAH of
- * RayTracingOpt; PerformanceTest's event-sweep SAH builder is not part of this build).                 */
+ * RayTracingOpt); libref_pt.so is built from PerformanceTest's own sources (its accelerator classes
+ * GridAcc / KdTreeAcc with the event-sweep SAH builder) and runs main.cpp's trace on them.               */
 typedef struct oracle_bounce_job {
     float radius, angle;
     int32_t arch_seg, path_seg;
@@ -116,10 +117,20 @@ typedef struct oracle_bounce_job {
     float *last_pos;       /* [n][3] position of the last hit                                */
     int64_t total_rays;
     double trace_ms, prepare_ms;
+    /* 0 = the tunnel generator and builders of RayTracingOpt (TunnelGenerator.cpp: rings turned by the segment
+     * direction; Tunnel.cpp: 99-candidate SAH); 1 = those of PerformanceTest itself (TunnelGenerator.cpp:243-279:
+     * rings turned by the averaged directions of the adjoining segments; KdTreeAcc.cpp: event-sweep SAH with
+     * automatic termination, cost = 1 + 1.5 * (...), leaf when cost > 1.5 * n).  The two programs share
+     * everything else on this path (cross section, median split, grids, traversal, intersection).          */
+    int32_t pt_builders;
+    int32_t pad_;
+    int64_t stats[16];     /* ORACLE_STAT_*: k-d tree sizes of the accelerator that was built               */
+    uint64_t struct_hash;  /* same hash as oracle_job.struct_hash (k-d trees)                                */
 } oracle_bounce_job;
 
 int rt_oracle_bounce(oracle_bounce_job *job);
-int ref_bounce(oracle_bounce_job *job);
+int ref_bounce(oracle_bounce_job *job);    /* libref.so: RayTracingOpt classes (pt_builders must be 0)       */
+int ref_pt_bounce(oracle_bounce_job *job); /* libref_pt.so: the PerformanceTest sources themselves           */
 
 #ifdef __cplusplus
 }

@@ -41,6 +41,7 @@ _LIBS = {
     "oracle": (os.path.join(HERE, "librt_oracle.so"), "rt_oracle_run"),
     "ref": (os.path.join(HERE, "_ref", "libref.so"), "ref_run"),
     "ref_timing": (os.path.join(HERE, "_ref", "libref_timing.so"), "ref_run"),
+    "ref_pt": (os.path.join(HERE, "_ref", "libref_pt.so"), "ref_pt_bounce"),
 }
 _loaded = {}
 
@@ -128,16 +129,19 @@ class BounceJob(C.Structure):
     _fields_ = [("radius", C.c_float), ("angle", C.c_float), ("arch_seg", C.c_int32), ("path_seg", C.c_int32),
                 ("algorithm", C.c_int32), ("n", C.c_int32), ("max_depth", C.c_int32), ("threads", C.c_int32),
                 ("xy", C.c_void_p), ("reached", C.c_void_p), ("depth", C.c_void_p), ("last_id", C.c_void_p),
-                ("last_pos", C.c_void_p), ("total_rays", C.c_int64), ("trace_ms", C.c_double), ("prepare_ms", C.c_double)]
+                ("last_pos", C.c_void_p), ("total_rays", C.c_int64), ("trace_ms", C.c_double), ("prepare_ms", C.c_double),
+                ("pt_builders", C.c_int32), ("pad_", C.c_int32), ("stats", C.c_int64 * 16), ("struct_hash", C.c_uint64)]
 
 
-def bounce(which, xy, radius=2000.0, angle=1.5708, arch_seg=150, path_seg=150, algorithm="sah", max_depth=200, threads=0):
-    """PerformanceTest workload (oracle_abi.h: oracle_bounce_job) through 'oracle' or 'ref' / 'ref_timing'."""
+def bounce(which, xy, radius=2000.0, angle=1.5708, arch_seg=150, path_seg=150, algorithm="sah", max_depth=200, threads=0,
+           pt_builders=False):
+    """PerformanceTest workload (oracle_abi.h: oracle_bounce_job) through 'oracle', 'ref' / 'ref_timing' (RayTracingOpt
+    classes) or 'ref_pt' (the PerformanceTest sources themselves; always its own builders)."""
     path, _ = _LIBS[which]
     if which == "oracle" and not os.path.exists(path):
         build_oracle()
     lib = C.CDLL(path)
-    fn = getattr(lib, "rt_oracle_bounce" if which == "oracle" else "ref_bounce")
+    fn = getattr(lib, {"oracle": "rt_oracle_bounce", "ref_pt": "ref_pt_bounce"}.get(which, "ref_bounce"))
     fn.argtypes = [C.POINTER(BounceJob)]
     fn.restype = C.c_int
     xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
@@ -146,9 +150,10 @@ def bounce(which, xy, radius=2000.0, angle=1.5708, arch_seg=150, path_seg=150, a
            "last_pos": np.zeros((n, 3), np.float32)}
     job = BounceJob(radius, angle, arch_seg, path_seg, ALGORITHMS[algorithm] if isinstance(algorithm, str) else algorithm,
                     n, max_depth, threads, xy.ctypes.data, out["reached"].ctypes.data, out["depth"].ctypes.data,
-                    out["last_id"].ctypes.data, out["last_pos"].ctypes.data, 0, 0.0, 0.0)
+                    out["last_id"].ctypes.data, out["last_pos"].ctypes.data, 0, 0.0, 0.0, 1 if pt_builders else 0, 0)
     rc = fn(C.byref(job))
     if rc != 0:
         raise RuntimeError(f"{which} bounce job failed rc={rc}")
-    out.update(total_rays=job.total_rays, trace_ms=job.trace_ms, prepare_ms=job.prepare_ms)
+    out.update(total_rays=job.total_rays, trace_ms=job.trace_ms, prepare_ms=job.prepare_ms, struct_hash=int(job.struct_hash),
+               stats={k: int(job.stats[i]) for i, k in enumerate(STAT_NAMES)})
     return out

@@ -314,6 +314,7 @@ struct KdNodeO { int axis; float split; int left, right; std::vector<int> list; 
 
 struct TunnelO
 {
+    bool ptBuilders = false; // PerformanceTest's KdTreeAcc builder (event-sweep SAH + automatic termination)
     int algorithm;
     std::vector<Tri> tris; // surface[seg][j] flattened in (seg, j) order
     // grid (Tunnel.h:51-67)
@@ -370,8 +371,11 @@ inline Tri makeTri(V3 a, V3 b, V3 c, int mat)
     return t;
 }
 
+// `pt`: the generator of the PerformanceTest program (src/PerformanceTest/TunnelGenerator.cpp:176-342).  Same cross
+// section and path; the ring at path vertex i is turned by the angle of the AVERAGED directions of the two
+// segments meeting there (its "normal vectors", lines 243-279) instead of the segment's own direction + delta.
 void generateTunnel(TunnelO &T, float rectWidth, float rectHeight, float archHeight, float pathRadius,
-                    float pathAngle, int archSegments, int pathSegments, int groundMat, int wallMat)
+                    float pathAngle, int archSegments, int pathSegments, int groundMat, int wallMat, bool pt = false)
 { // TunnelGenerator.cpp:197-366
     std::vector<V3> cs;
     cs.push_back(v3(rectWidth * 0.5f, 0.0f, 0.0f));
@@ -383,6 +387,27 @@ void generateTunnel(TunnelO &T, float rectWidth, float rectHeight, float archHei
     cs.push_back(v3(-rectWidth * 0.5f, 0.0f, 0.0f));
 
     std::vector<std::vector<Tri>> surface(pathSegments);
+    std::vector<V3> nvs; // PerformanceTest only
+    if (pt)
+    {
+        const int N = pathSegments;
+        std::vector<V3> path(N + 1);
+        for (int i = 0; i <= N; i++)
+        {
+            const float theta = pathAngle * i / pathSegments;
+            path[i] = v3(pathRadius * (1.0f - cosf(theta)), 0.0f, -pathRadius * sinf(theta));
+        }
+        for (int i = 1; i <= N; i++)
+        {
+            const V3 dir = normalize(path[i] - path[i - 1]);
+            V3 prevDir = dir, nextDir = dir;
+            if (i > 1) prevDir = normalize(path[i - 1] - path[i - 2]);
+            if (i < N) nextDir = normalize(path[i + 1] - path[i]);
+            const V3 v1 = normalize((prevDir + dir) * 0.5f), v2 = normalize((dir + nextDir) * 0.5f);
+            if (i == 1) nvs.push_back(v1);
+            nvs.push_back(v2);
+        }
+    }
 #pragma omp parallel for schedule(dynamic, 1)
     for (int i = 0; i < pathSegments; i++)
     {
@@ -392,8 +417,13 @@ void generateTunnel(TunnelO &T, float rectWidth, float rectHeight, float archHei
         const V3 p2 = v3(pathRadius * (1.0f - cosf(theta2)), 0.0f, -pathRadius * sinf(theta2));
         const float delta = (i == pathSegments - 1) ? 0 : pathAngle / pathSegments;
         const V3 fwd = v3(0, 0, -1), seg = p2 - p1;
-        const float offsetAngle1 = acosf(dot(fwd, seg) * (1.0f / (length(fwd) * length(seg)))); // Vector.cpp:88-91
-        const float offsetAngle2 = offsetAngle1 + delta;
+        float offsetAngle1 = acosf(dot(fwd, seg) * (1.0f / (length(fwd) * length(seg)))); // Vector.cpp:88-91
+        float offsetAngle2 = offsetAngle1 + delta;
+        if (pt)
+        {
+            offsetAngle1 = acosf(dot(fwd, nvs[i]) * (1.0f / (length(fwd) * length(nvs[i]))));
+            offsetAngle2 = acosf(dot(fwd, nvs[i + 1]) * (1.0f / (length(fwd) * length(nvs[i + 1]))));
+        }
         std::vector<V3> front, rear;
         for (size_t j = 0; j < cs.size(); j++)
         {
@@ -516,8 +546,61 @@ float splitSAH(TunnelO &T, int node, const std::vector<int> &list, int &bestAxis
     return minSplit;
 }
 
+// PerformanceTest/KdTreeAcc.cpp:177-274: exact SAH by a sweep over the sorted bounding-box events of every
+// axis.  Events sort by (position, type) with End < Planar < Start (KdTreeAcc.cpp:32-36); equal keys are
+// interchangeable, so std::sort's instability cannot change a count.  Cost = 1 + 1.5 * ((SAL/SA) * NL +
+// (SAR/SA) * (NR + NP)), first strict minimum wins (axis 0 -> 2, positions ascending).
+struct SweepEvent { float position; int type; }; // type: 0 End, 1 Planar, 2 Start
+inline bool sweepLess(const SweepEvent &a, const SweepEvent &b)
+{
+    return (a.position < b.position) || ((a.position == b.position) && a.type < b.type);
+}
+
+float splitSAHSweep(TunnelO &T, int node, const std::vector<int> &list, int &bestAxis, float &minSAH)
+{
+    minSAH = FLT_MAX;
+    float minPosition = 0;
+    const V3 mn = T.nodes[node].mn, mx = T.nodes[node].mx;
+    for (int axis = 0; axis < 3; axis++)
+    {
+        std::vector<SweepEvent> events;
+        events.reserve(2 * list.size());
+        for (size_t i = 0; i < list.size(); i++)
+        {
+            V3 a, b; triBounds(T.tris[list[i]], a, b);
+            if (comp(a, axis) == comp(b, axis)) events.push_back(SweepEvent{comp(a, axis), 1});
+            else { events.push_back(SweepEvent{comp(a, axis), 2}); events.push_back(SweepEvent{comp(b, axis), 0}); }
+        }
+        std::sort(events.begin(), events.end(), sweepLess);
+        int NL = 0, NP = 0, NR = (int)list.size();
+        for (size_t i = 0; i < events.size();)
+        {
+            const float position = events[i].position;
+            int PS = 0, PE = 0, PP = 0;
+            while (i < events.size() && events[i].position == position && events[i].type == 0) { PE += 1; i += 1; }
+            while (i < events.size() && events[i].position == position && events[i].type == 1) { PP += 1; i += 1; }
+            while (i < events.size() && events[i].position == position && events[i].type == 2) { PS += 1; i += 1; }
+            NP = PP; NR -= PP; NR -= PE;
+            const int nextAxis = (axis + 1) % 3, prevAxis = (axis + 2) % 3;
+            const V3 boxSize = mx - mn;
+            const float width = comp(mx, axis) - comp(mn, axis);
+            const float leftWidth = position - comp(mn, axis);
+            const float rightWidth = comp(mx, axis) - position;
+            const float height = comp(boxSize, nextAxis);
+            const float depth = comp(boxSize, prevAxis);
+            const float SAL = leftWidth * height + leftWidth * depth + height * depth;
+            const float SAR = rightWidth * height + rightWidth * depth + height * depth;
+            const float SA = width * height + width * depth + height * depth;
+            const float SAH = 1 + 1.5f * ((SAL / SA) * NL + SAR / SA * (NR + NP));
+            if (SAH < minSAH) { minSAH = SAH; minPosition = position; bestAxis = axis; }
+            NL += PS; NL += PP; NP = 0;
+        }
+    }
+    return minPosition;
+}
+
 void buildKd(TunnelO &T, int node, std::vector<int> &list, int depth)
-{ // Tunnel.cpp:546-638
+{ // Tunnel.cpp:546-638; PerformanceTest/KdTreeAcc.cpp:38-144 when T.ptBuilders
     if (depth > T.maxDepth) T.maxDepth = depth;
     if (list.size() <= 8 || depth > 18)
     {
@@ -532,6 +615,21 @@ void buildKd(TunnelO &T, int node, std::vector<int> &list, int depth)
     int axis = 0;
     float median;
     if (T.algorithm == 3) { axis = depth % 3; median = splitMedian(T, axis, list); }
+    else if (T.ptBuilders)
+    {
+        float sah;
+        median = splitSAHSweep(T, node, list, axis, sah);
+        if (sah > 1.5f * list.size())
+        { // automatic termination, KdTreeAcc.cpp:77-88
+            T.nodes[node].axis = 3;
+            T.nodes[node].split = 0.0f;
+            T.nodes[node].left = T.nodes[node].right = -1;
+            T.nodes[node].list = list;
+            T.leaves++;
+            T.leafRefs += (long long)list.size();
+            return;
+        }
+    }
     else median = splitSAH(T, node, list, axis);
     std::vector<int> leftPart, rightPart;
     for (size_t i = 0; i < list.size(); i++)
@@ -1061,7 +1159,8 @@ extern "C" int rt_oracle_bounce(oracle_bounce_job *job)
     s.hasTunnel = true;
     const int dummy = addMat(s, solid(v3(0, 0, 0), v3(0, 0, 0), 1, 0, 0));
     s.tunnel.algorithm = job->algorithm;
-    generateTunnel(s.tunnel, 50, 25, 25, job->radius, job->angle, job->arch_seg, job->path_seg, dummy, dummy);
+    s.tunnel.ptBuilders = job->pt_builders != 0;
+    generateTunnel(s.tunnel, 50, 25, 25, job->radius, job->angle, job->arch_seg, job->path_seg, dummy, dummy, job->pt_builders != 0);
     Prim p; memset(&p, 0, sizeof(p));
     p.type = PRIM_TUNNEL;
     s.prims.push_back(p);
@@ -1072,6 +1171,45 @@ extern "C" int rt_oracle_bounce(oracle_bounce_job *job)
     if (job->algorithm == 1 || job->algorithm == 2) initGrid(s.tunnel);
     else if (job->algorithm == 3 || job->algorithm == 4) initKd(s.tunnel);
     job->prepare_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    memset(job->stats, 0, sizeof(job->stats));
+    job->struct_hash = 0;
+    job->stats[ORACLE_STAT_N_TRIS] = (int64_t)s.tunnel.tris.size();
+    if (job->algorithm == 1 || job->algorithm == 2)
+    {
+        const TunnelO &T = s.tunnel;
+        uint64_t h = H0;
+        hmix(h, 0x47524944u);
+        hmix(h, (uint32_t)T.nx); hmix(h, (uint32_t)T.ny); hmix(h, (uint32_t)T.nz);
+        hmix(h, fbits(T.origin.x)); hmix(h, fbits(T.origin.y)); hmix(h, fbits(T.origin.z));
+        hmix(h, fbits(T.csx)); hmix(h, fbits(T.csy)); hmix(h, fbits(T.csz));
+        job->stats[ORACLE_STAT_GRID_X] = T.nx; job->stats[ORACLE_STAT_GRID_Y] = T.ny; job->stats[ORACLE_STAT_GRID_Z] = T.nz;
+        for (size_t c = 0; c < T.cells.size(); c++)
+        {
+            const std::vector<int> &l = T.cells[c];
+            if (l.empty()) continue;
+            job->stats[ORACLE_STAT_CELLS_NONEMPTY]++;
+            job->stats[ORACLE_STAT_CELL_ENTRIES] += (int64_t)l.size();
+            if ((int64_t)l.size() > job->stats[ORACLE_STAT_CELL_MAX]) job->stats[ORACLE_STAT_CELL_MAX] = (int64_t)l.size();
+            hmix(h, (uint32_t)c); hmix(h, (uint32_t)l.size());
+            for (size_t i = 0; i < l.size(); i++) hmix(h, (uint32_t)l[i]);
+        }
+        job->struct_hash = h;
+    }
+    if (job->algorithm == 3 || job->algorithm == 4)
+    {
+        const TunnelO &T = s.tunnel;
+        uint64_t h = H0;
+        hmix(h, 0x4b445452u);
+        hmix(h, fbits(T.nodes[0].mn.x)); hmix(h, fbits(T.nodes[0].mn.y)); hmix(h, fbits(T.nodes[0].mn.z));
+        hmix(h, fbits(T.nodes[0].mx.x)); hmix(h, fbits(T.nodes[0].mx.y)); hmix(h, fbits(T.nodes[0].mx.z));
+        hashKd(T, 0, h);
+        job->struct_hash = h;
+        job->stats[ORACLE_STAT_N_TRIS] = (int64_t)T.tris.size();
+        job->stats[ORACLE_STAT_KD_NODES] = (int64_t)T.nodes.size();
+        job->stats[ORACLE_STAT_KD_LEAVES] = T.leaves;
+        job->stats[ORACLE_STAT_KD_LEAF_REFS] = T.leafRefs;
+        job->stats[ORACLE_STAT_KD_MAX_DEPTH] = T.maxDepth;
+    }
     // PT camera: eye (0,25,5), front (0,0,-1), up (0,1,0); Camera.cpp:5-13
     V3 front = normalize(v3(0, 0, -1));
     const V3 right = normalize(cross(front, v3(0, 1, 0)));

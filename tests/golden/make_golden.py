@@ -83,5 +83,32 @@ def bounce_golden():
     np.savez_compressed(os.path.join(HERE, "bounce_golden.npz"), **out)
 
 
+PT_CASES = {  # name -> (radius, angle, arch_seg, path_seg): the tunnels of the PerformanceTest program
+    "r2000_s30": (2000.0, 1.5708, 30, 30),
+    "r100_a75_s24x12": (100.0, 1.309, 24, 12),
+}
+
+
+def bounce_pt_golden():
+    """tests/golden/bounce_pt_golden.{npz,json}: the PerformanceTest program itself (libref_pt.so: its generator, its
+    GridAcc / KdTreeAcc builders incl. the event-sweep SAH, its trace): per-ray results, k-d tree sizes and hashes;
+    plus the full-size trees (150 x 150, radius 5000) -- structure only."""
+    xy = np.random.default_rng(22).random((300, 2), dtype=np.float32)
+    out, meta = {"xy": xy}, {}
+    for name, (radius, angle, aseg, pseg) in PT_CASES.items():
+        for alg in ("rgrid", "fgrid", "kd", "sah"):
+            a = O.bounce("ref_pt", xy, radius, angle, aseg, pseg, alg)
+            for k in ("reached", "depth", "last_id", "last_pos"):
+                out[f"{name}.{alg}.{k}"] = a[k]
+            meta[f"{name}.{alg}"] = {"stats": a["stats"], "struct_hash": f"{a['struct_hash']:016x}", "total_rays": a["total_rays"]}
+    for alg in ("kd", "sah"):
+        a = O.bounce("ref_pt", xy[:4], 5000.0, 1.5707964, 150, 150, alg)
+        meta[f"r5000_s150.{alg}"] = {"stats": a["stats"], "struct_hash": f"{a['struct_hash']:016x}"}
+    np.savez_compressed(os.path.join(HERE, "bounce_pt_golden.npz"), **out)
+    with open(os.path.join(HERE, "bounce_pt_golden.json"), "w") as f:
+        json.dump(meta, f, indent=1, sort_keys=True)
+
+
 if __name__ == "__main__":
     bounce_golden()
+    bounce_pt_golden()

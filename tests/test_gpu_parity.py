@@ -477,9 +477,21 @@ def test_performance_test_bounce_workload(ctx, alg):
     rng = np.random.default_rng(11)
     n, seg = (64, 10) if alg == "linear" else (500, 30)
     xy = rng.random((n, 2), dtype=np.float32)
-    o = O.bounce("oracle", xy, 2000.0, 1.5708, seg, seg, alg)
+    o = O.bounce("oracle", xy, 2000.0, 1.5708, seg, seg, alg, pt_builders=True)  # that program's own generator / builders
     g = rtb200.perf_test(xy, 2000.0, 1.5708, seg, seg, alg)
     for k in ("reached", "depth", "last_id"):
         assert np.array_equal(g[k], o[k]), k
     assert np.array_equal(_bits(g["last_pos"]), _bits(o["last_pos"]))
     assert g["total_rays"] == o["total_rays"] and g["reached"].all()
+
+
+@pytest.mark.parametrize("case", ["r2000_s30", "r100_a75_s24x12"])
+def test_performance_test_program_golden(ctx, case):
+    """The same workload against fixtures recorded from the compiled PerformanceTest sources themselves
+    (oracle/_ref/libref_pt.so -> tests/golden/bounce_pt_golden.npz): grids, median tree, event-sweep SAH tree."""
+    cases = {"r2000_s30": (2000.0, 1.5708, 30, 30), "r100_a75_s24x12": (100.0, 1.309, 24, 12)}
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "bounce_pt_golden.npz"))
+    for alg in ("rgrid", "kd", "sah"):
+        g = rtb200.perf_test(gold["xy"], *cases[case], alg)
+        for k in ("reached", "depth", "last_id", "last_pos"):
+            assert np.array_equal(_bits(g[k]), _bits(gold[f"{case}.{alg}.{k}"])), (alg, k)

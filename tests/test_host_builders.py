@@ -115,3 +115,22 @@ def test_shard_rows_partition_the_frame():
                 assert rtb200.shard_rows(fr) == len(ys)
                 seen.extend(ys.tolist())
             assert sorted(seen) == list(range(h))
+
+
+def test_performance_test_program_builders_match_reference():
+    """rt::PerformanceTest builds its tunnel with that program's own generator and k-d builder (event-sweep SAH with
+    automatic termination): triangle count, grid / tree sizes and structure hashes equal what the compiled
+    src/PerformanceTest sources produce (tests/golden/bounce_pt_golden.json, recorded from libref_pt.so)."""
+    with open(os.path.join(os.path.dirname(__file__), "golden", "bounce_pt_golden.json")) as f:
+        meta = json.load(f)
+    cases = {"r2000_s30": (2000.0, 1.5708, 30, 30), "r100_a75_s24x12": (100.0, 1.309, 24, 12), "r5000_s150": (5000.0, 1.5707964, 150, 150)}
+    for name, m in sorted(meta.items()):
+        case, alg = name.split(".")
+        if alg == "fgrid" and case != "r2000_s30":
+            continue
+        s = rtb200.PerfScene(*cases[case], alg)
+        st = s.stats()
+        for k in ("n_tris", "grid_x", "grid_y", "grid_z", "cells_nonempty", "cell_entries", "cell_max", "kd_nodes", "kd_leaves", "kd_leaf_refs", "kd_max_depth"):
+            assert st[k] == m["stats"][k], (name, k)
+        assert f"{s.struct_hash():016x}" == m["struct_hash"], name
+        s.close()

@@ -107,3 +107,54 @@ def test_bounce_workload_golden():
         b = O.bounce("oracle", g["xy"], 2000.0, 1.5708, 30, 30, alg)
         for k in ("reached", "depth", "last_id", "last_pos"):
             assert np.array_equal(b[k].view(np.uint8), g[f"{alg}.{k}"].view(np.uint8)), (alg, k)
+
+
+# ---- the PerformanceTest PROGRAM itself (its own tunnel generator and accelerator builders) ----------------
+PT_CASES = {"r2000_s30": (2000.0, 1.5708, 30, 30), "r100_a75_s24x12": (100.0, 1.309, 24, 12)}
+
+
+@pytest.mark.skipif(not O.available("ref_pt"), reason="oracle/_ref/libref_pt.so not built (no /root/reference)")
+@pytest.mark.parametrize("alg", ["linear", "rgrid", "fgrid", "kd", "sah"])
+def test_pt_program_oracle_matches_ref_pt(alg):
+    """oracle (pt_builders) == src/PerformanceTest compiled as it is: tunnel generator (TunnelGenerator.cpp:243-279),
+    GridAcc, KdTreeAcc median and event-sweep SAH with automatic termination (KdTreeAcc.cpp:38-274) -- structure
+    hash, tree sizes and every per-ray result of main.cpp's trace."""
+    xy = np.random.default_rng(5).random((200, 2), dtype=np.float32)
+    a = O.bounce("ref_pt", xy, 1000.0, 1.5707964, 40, 40, alg)
+    b = O.bounce("oracle", xy, 1000.0, 1.5707964, 40, 40, alg, pt_builders=True)
+    assert a["struct_hash"] == b["struct_hash"] and a["stats"] == b["stats"]
+    for k in ("reached", "depth", "last_id", "last_pos"):
+        assert np.array_equal(a[k].view(np.uint8), b[k].view(np.uint8)), k
+    assert a["total_rays"] == b["total_rays"] and a["reached"].all()
+
+
+@pytest.mark.parametrize("case", sorted(PT_CASES))
+def test_pt_program_golden(case):
+    """Fixtures recorded from libref_pt.so (tests/golden/bounce_pt_golden.{npz,json}, make_golden.py)."""
+    import json
+    import os
+    here = os.path.join(os.path.dirname(__file__), "golden")
+    g = np.load(os.path.join(here, "bounce_pt_golden.npz"))
+    with open(os.path.join(here, "bounce_pt_golden.json")) as f:
+        meta = json.load(f)
+    radius, angle, aseg, pseg = PT_CASES[case]
+    for alg in ("rgrid", "kd", "sah") + (("fgrid",) if case == "r2000_s30" else ()):
+        b = O.bounce("oracle", g["xy"], radius, angle, aseg, pseg, alg, pt_builders=True)
+        m = meta[f"{case}.{alg}"]
+        assert f"{b['struct_hash']:016x}" == m["struct_hash"] and b["stats"] == m["stats"] and b["total_rays"] == m["total_rays"]
+        for k in ("reached", "depth", "last_id", "last_pos"):
+            assert np.array_equal(b[k].view(np.uint8), g[f"{case}.{alg}.{k}"].view(np.uint8)), (alg, k)
+
+
+def test_pt_program_full_size_trees_golden():
+    """The 150 x 150 tunnel of radius 5000: median tree 243,773 nodes, event-sweep SAH tree 67,333 nodes / 33,667 leaves /
+    372,819 references -- sizes and hashes of the trees src/PerformanceTest builds."""
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "bounce_pt_golden.json")) as f:
+        meta = json.load(f)
+    xy = np.full((2, 2), 0.5, np.float32)
+    for alg in ("kd", "sah"):
+        b = O.bounce("oracle", xy, 5000.0, 1.5707964, 150, 150, alg, pt_builders=True)
+        m = meta[f"r5000_s150.{alg}"]
+        assert f"{b['struct_hash']:016x}" == m["struct_hash"] and b["stats"] == m["stats"]

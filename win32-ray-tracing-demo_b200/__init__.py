@@ -149,6 +149,8 @@ def host_lib():
         vp = C.c_void_p
         lib.rtbh_preset_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_char_p]
         lib.rtbh_preset_create.restype = vp
+        lib.rtbh_perf_scene_create.argtypes = [C.c_float, C.c_float, C.c_int, C.c_int, C.c_int]
+        lib.rtbh_perf_scene_create.restype = vp
         lib.rtbh_free.argtypes = [vp]
         lib.rtbh_flat.argtypes = [vp]
         lib.rtbh_flat.restype = C.POINTER(FlatScene)
@@ -264,6 +266,21 @@ class PresetScene:
         pos, nrm = np.zeros(3, np.float32), np.zeros(3, np.float32)
         host_lib().rtbh_intersect_one(self._h, ray.ctypes.data, C.byref(hid), C.byref(ht), pos.ctypes.data, nrm.ctypes.data)
         return hid.value, ht.value, pos, nrm
+
+
+class PerfScene(PresetScene):
+    """The scene of the reference's PerformanceTest program (tunnel built by that program's own generator and
+    k-d builder + the plane closing its exit), built and flattened by the C++ host library."""
+
+    def __init__(self, radius=2000.0, angle=1.5708, arch_seg=150, path_seg=150, algorithm="sah"):
+        lib = host_lib()
+        self.preset, self.algorithm, self.segments = 0, algorithm, path_seg
+        self._h = lib.rtbh_perf_scene_create(radius, angle, arch_seg, path_seg, _alg(algorithm))
+        if not self._h:
+            raise RtbError("rtbh_perf_scene_create failed (bad algorithm / tessellation)")
+        self.flat = lib.rtbh_flat(self._h)
+        self.camera = lib.rtbh_camera(self._h).contents
+        self.setting = lib.rtbh_setting(self._h).contents
 
 
 def script_run(preset, algorithm="linear", segments=150, width=400, height=300, samples=1, seed=0, device=0,

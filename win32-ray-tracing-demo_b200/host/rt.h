@@ -292,6 +292,9 @@ public:
     int kdLeafSize = 8;       // Tunnel.cpp:550
     int kdMaxDepth = 18;
     int sahCandidates = 100;  // Tunnel.cpp:679
+    // KdTreeSAH builds with PerformanceTest's builder (KdTreeAcc.cpp: event-sweep SAH + automatic termination)
+    // instead of RayTracingOpt's 99-candidate one; set by TunnelGenerator::performanceTestVariant
+    bool performanceTestBuilders = false;
 
     // Reference Tunnel.cpp:116-133: builds the accelerator selected by `algorithm`.
     void init();
@@ -324,6 +327,10 @@ private:
 class TunnelGenerator
 {
 public:
+    // false: RayTracingOpt's generator (rings turned by their segment's direction, TunnelGenerator.cpp:262-290);
+    // true:  PerformanceTest's (rings turned by the averaged directions of the adjoining segments,
+    //        src/PerformanceTest/TunnelGenerator.cpp:243-279) and its k-d builder -- the two programs differ there
+    bool performanceTestVariant = false;
     // Reference TunnelGenerator.cpp:197-366.
     bool create(float rectWidth, float rectHeight, float archHeight, float pathRadius, float pathAngle,
                 int archSegments, int pathSegments, GeometrySet &scene, Ptr<Material> groundMaterial,
@@ -381,6 +388,8 @@ struct PerformanceTest
     Tunnel *tunnel = nullptr;
     double buildMs = 0, preprocessMs = 0;
     bool build(float pathRadius, float pathAngle, int archSeg, int pathSeg, Tunnel::Algorithm algorithm); // main.cpp:61-81,134-140
+    static Tunnel *buildScene(GeometrySet &scene, float pathRadius, float pathAngle, int archSeg, int pathSeg,
+                              Tunnel::Algorithm algorithm); // the scene alone, accelerator not yet built
     // xy: n camera samples in [0,1]^2 (the reference draws them with rand()); returns the trace kernel's ms, < 0 on error
     double run(const float *xy, int n, int maxDepth, int32_t *reached, int32_t *depth, int32_t *lastId, float *lastPos,
                int64_t *totalRays);

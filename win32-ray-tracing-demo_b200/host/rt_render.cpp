@@ -212,19 +212,27 @@ Ray Camera::generateRay(float x, float y) const
     return Ray(eye, dir);
 }
 
-bool PerformanceTest::build(float pathRadius, float pathAngle, int archSeg, int pathSeg, Tunnel::Algorithm algorithm)
+// main.cpp:61-81: the tunnel (that program's own generator and k-d builder) and the plane closing its exit
+Tunnel *PerformanceTest::buildScene(GeometrySet &scene, float pathRadius, float pathAngle, int archSeg, int pathSeg,
+                                    Tunnel::Algorithm algorithm)
 {
-    const double t0 = nowMs();
     scene.clear();
     TunnelGenerator g;
+    g.performanceTestVariant = true;
     Ptr<Material> plain = solid(Color::Black(), Color::Black(), 1, 0, 0); // PerformanceTest has no materials
     g.create(50, 25, 25, pathRadius, pathAngle, archSeg, pathSeg, scene, plain, plain, algorithm);
-    tunnel = static_cast<Tunnel *>(scene.last());
-    // the plane at the exit of the tunnel, main.cpp:71-78
-    const Vector normal(std::sin(pathAngle), 0, -std::cos(pathAngle));
+    Tunnel *tunnel = static_cast<Tunnel *>(scene.last());
+    const Vector normal(std::sin(pathAngle), 0, -std::cos(pathAngle)); // main.cpp:71-78
     Plane *exitPlane = new Plane(normal, pathRadius * std::sin(pathAngle));
     exitPlane->material = plain;
     scene.add(exitPlane);
+    return tunnel;
+}
+
+bool PerformanceTest::build(float pathRadius, float pathAngle, int archSeg, int pathSeg, Tunnel::Algorithm algorithm)
+{
+    const double t0 = nowMs();
+    tunnel = buildScene(scene, pathRadius, pathAngle, archSeg, pathSeg, algorithm);
     buildMs = nowMs() - t0;
     const double t1 = nowMs();
     tunnel->init();
@@ -397,6 +405,26 @@ rtbh_scene *rtbh_preset_create(int preset, int algorithm, int segments, const ch
     h->cam = h->camera->flatten();
     h->rs = h->setting.flatten();
     if (preset >= 4) h->tunnel = static_cast<Tunnel *>(h->scene.last());
+    return h;
+}
+// The PerformanceTest scene (tunnel + exit plane, src/PerformanceTest/main.cpp:61-81) built and flattened; the
+// handle serves the same queries as a preset's (stats, hashes, flat view) -- no camera / setting of its own.
+rtbh_scene *rtbh_perf_scene_create(float radius, float angle, int arch_seg, int path_seg, int algorithm)
+{
+    if (algorithm < 0 || algorithm > 4 || arch_seg < 1 || path_seg < 1) return nullptr;
+    rtbh_scene *h = new rtbh_scene();
+    const double t0 = nowMs();
+    h->tunnel = PerformanceTest::buildScene(h->scene, radius, angle, arch_seg, path_seg, (Tunnel::Algorithm)algorithm);
+    const double t1 = nowMs();
+    h->tunnel->init();
+    h->prepareMs = (int)(nowMs() - t1);
+    h->buildMs = nowMs() - t0;
+    h->scene.flatten(h->flat);
+    h->flat.finish();
+    h->camera.reset(new PerspectiveCamera(Point(0, 25, 5), Vector(0, 0, -1), Vector(0, 1, 0), 1.274f, 53.13f, 0.0f));
+    h->setting = RenderSetting::Simple();
+    h->cam = h->camera->flatten();
+    h->rs = h->setting.flatten();
     return h;
 }
 void rtbh_free(rtbh_scene *h) { delete h; }

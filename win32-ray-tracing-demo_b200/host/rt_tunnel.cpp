@@ -110,13 +110,35 @@ bool TunnelGenerator::create(float rectWidth, float rectHeight, float archHeight
     for (int i = 0; i < pathSegments; i++) tunnel->path.push_back(pathPoint(i + 1));
     tunnel->surface.assign(pathSegments, std::vector<TunnelTriangle>());
 
+    // PerformanceTest's generator (src/PerformanceTest/TunnelGenerator.cpp:243-279) turns the ring at path vertex i
+    // by the angle of the averaged directions of the two segments that meet there
+    std::vector<Vector> ringNormal;
+    if (performanceTestVariant)
+    {
+        const int N = pathSegments;
+        for (int i = 1; i <= N; i++)
+        {
+            const Vector dir = Vector(tunnel->path[i - 1], tunnel->path[i]).norm();
+            const Vector prevDir = i > 1 ? Vector(tunnel->path[i - 2], tunnel->path[i - 1]).norm() : dir;
+            const Vector nextDir = i < N ? Vector(tunnel->path[i], tunnel->path[i + 1]).norm() : dir;
+            if (i == 1) ringNormal.push_back(((prevDir + dir) * 0.5f).norm());
+            ringNormal.push_back(((dir + nextDir) * 0.5f).norm());
+        }
+        tunnel->performanceTestBuilders = true;
+    }
+
 #pragma omp parallel for schedule(dynamic, 1)
     for (int i = 0; i < pathSegments; i++)
     {
         const Point p1 = pathPoint(i), p2 = pathPoint(i + 1);
         const float delta = (i == pathSegments - 1) ? 0 : pathAngle / pathSegments;
-        const float angle1 = Vector(0, 0, -1).angleTo(Vector(p1, p2));
-        const float angle2 = angle1 + delta;
+        float angle1 = Vector(0, 0, -1).angleTo(Vector(p1, p2));
+        float angle2 = angle1 + delta;
+        if (performanceTestVariant)
+        {
+            angle1 = Vector(0, 0, -1).angleTo(ringNormal[i]);
+            angle2 = Vector(0, 0, -1).angleTo(ringNormal[i + 1]);
+        }
         // place the section at both ends of the segment: rotate about y, then translate (296-307)
         auto place = [&](float angle, const Point &at, Ring &ring) {
             for (const Point &p : section)
@@ -293,12 +315,12 @@ struct BuildNode
 struct KdBuilder
 {
     const std::vector<TunnelTriangle> &tris;
-    bool sah;
+    bool sah, sweep;
     int leafSize, maxDepth, candidates;
     std::vector<float> lo[3], hi[3], centroid[3]; // per-triangle extent / centroid per axis
 
-    KdBuilder(const std::vector<TunnelTriangle> &t, bool sah, int leafSize, int maxDepth, int candidates)
-        : tris(t), sah(sah), leafSize(leafSize), maxDepth(maxDepth), candidates(candidates)
+    KdBuilder(const std::vector<TunnelTriangle> &t, bool sah, bool sweep, int leafSize, int maxDepth, int candidates)
+        : tris(t), sah(sah), sweep(sweep), leafSize(leafSize), maxDepth(maxDepth), candidates(candidates)
     {
         for (int a = 0; a < 3; a++)
         {
@@ -359,8 +381,57 @@ struct KdBuilder
         return minSplit;
     }
 
+    // PerformanceTest/KdTreeAcc.cpp:177-274: the exact SAH, cost = 1 + 1.5 * ((SAL/SA) * NL + (SAR/SA) * (NR + NP)),
+    // evaluated at every bounding-box boundary of the node's triangles, first strict minimum wins (axis 0 -> 2,
+    // positions ascending).  The reference sorts one list of {End, Planar, Start} events per axis; the counts it
+    // derives at a position p are  PE = #{hi == p}, PS = #{lo == p} over the triangles with lo < hi, and
+    // PP = #{lo == hi == p}, so three sorted position arrays merged in step give the same sweep.
+    float splitSAHSweep(const float mn[3], const float mx[3], const std::vector<uint32_t> &list, int &bestAxis, float &minSAH) const
+    {
+        minSAH = FLT_MAX;
+        float minPosition = 0;
+        std::vector<float> starts, ends, planars;
+        for (int axis = 0; axis < 3; axis++)
+        {
+            starts.clear(); ends.clear(); planars.clear();
+            for (uint32_t t : list)
+            {
+                if (lo[axis][t] == hi[axis][t]) planars.push_back(lo[axis][t]);
+                else { starts.push_back(lo[axis][t]); ends.push_back(hi[axis][t]); }
+            }
+            std::sort(starts.begin(), starts.end());
+            std::sort(ends.begin(), ends.end());
+            std::sort(planars.begin(), planars.end());
+            const int nextAxis = (axis + 1) % 3, prevAxis = (axis + 2) % 3;
+            const float width = mx[axis] - mn[axis], height = mx[nextAxis] - mn[nextAxis], depth = mx[prevAxis] - mn[prevAxis];
+            const float SA = width * height + width * depth + height * depth;
+            size_t is = 0, ie = 0, ip = 0;
+            int NL = 0, NR = (int)list.size();
+            while (is < starts.size() || ie < ends.size() || ip < planars.size())
+            {
+                float position = FLT_MAX;
+                if (is < starts.size()) position = std::min(position, starts[is]);
+                if (ie < ends.size()) position = std::min(position, ends[ie]);
+                if (ip < planars.size()) position = std::min(position, planars[ip]);
+                int PS = 0, PE = 0, PP = 0;
+                while (ie < ends.size() && ends[ie] == position) { PE++; ie++; }
+                while (ip < planars.size() && planars[ip] == position) { PP++; ip++; }
+                while (is < starts.size() && starts[is] == position) { PS++; is++; }
+                const int NP = PP;
+                NR -= PP; NR -= PE;
+                const float leftWidth = position - mn[axis], rightWidth = mx[axis] - position;
+                const float SAL = leftWidth * height + leftWidth * depth + height * depth;
+                const float SAR = rightWidth * height + rightWidth * depth + height * depth;
+                const float cost = 1 + 1.5f * ((SAL / SA) * NL + SAR / SA * (NR + NP));
+                if (cost < minSAH) { minSAH = cost; minPosition = position; bestAxis = axis; }
+                NL += PS; NL += PP;
+            }
+        }
+        return minPosition;
+    }
+
     void build(BuildNode *node, std::vector<uint32_t> &list, const float mn[3], const float mx[3], int depth) const
-    { // reference Tunnel.cpp:546-638
+    { // reference Tunnel.cpp:546-638; PerformanceTest/KdTreeAcc.cpp:38-144 when `sweep`
         if ((int)list.size() <= leafSize || depth > maxDepth)
         {
             node->axis = 3;
@@ -369,7 +440,18 @@ struct KdBuilder
         }
         int axis = depth % 3;
         float split;
-        if (sah) split = splitSAH(mn, mx, list, axis);
+        if (sah && sweep)
+        {
+            float cost;
+            split = splitSAHSweep(mn, mx, list, axis, cost);
+            if (cost > 1.5f * list.size())
+            { // automatic termination (KdTreeAcc.cpp:77-88): splitting would cost more than testing the whole list
+                node->axis = 3;
+                node->list = list;
+                return;
+            }
+        }
+        else if (sah) split = splitSAH(mn, mx, list, axis);
         else split = splitMedian(axis, list);
         node->axis = axis;
         node->split = split;
@@ -426,7 +508,7 @@ void Tunnel::initKdTree(const std::vector<TunnelTriangle> &tris)
 { // reference Tunnel.cpp:467-517
     const Bounds b = sceneBounds(tris);
     for (int a = 0; a < 3; a++) { kdMin_[a] = b.mn[a]; kdMax_[a] = b.mx[a]; }
-    KdBuilder builder(tris, algorithm == KdTreeSAH, kdLeafSize, kdMaxDepth, sahCandidates);
+    KdBuilder builder(tris, algorithm == KdTreeSAH, performanceTestBuilders, kdLeafSize, kdMaxDepth, sahCandidates);
     std::vector<uint32_t> list(tris.size());
     for (size_t i = 0; i < list.size(); i++) list[i] = (uint32_t)i;
     BuildNode root;
