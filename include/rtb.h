@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define RTB_ABI_VERSION 1
+#define RTB_ABI_VERSION 2
 
 typedef enum rtb_status {
     RTB_OK = 0,
@@ -72,7 +72,9 @@ enum { RTB_ACCEL_LINEAR = 0,       /* Tunnel.cpp:786-804  */
        RTB_ACCEL_REGULAR_GRID = 1, /* Tunnel.cpp:346-465 (uniform cell = maxExtent/399), 819-970 */
        RTB_ACCEL_FLAT_GRID = 2,    /* 400^3 anisotropic cells                                  */
        RTB_ACCEL_KD_MEDIAN = 3,    /* Tunnel.cpp:546-669, 1163-1297                            */
-       RTB_ACCEL_KD_SAH = 4 };     /* Tunnel.cpp:671-784                                       */
+       RTB_ACCEL_KD_SAH = 4,       /* Tunnel.cpp:671-784                                       */
+       RTB_ACCEL_CONVEX = 5,        /* PerformanceTest/ConvexAcc.cpp (Tunnel.cpp:972-1161): polygon-to-polygon walk,  */
+       RTB_ACCEL_CONVEX_SIMPLE = 6 }; /* first accepted triangle of the wall segment, table-ordered / list-ordered     */
 
 /* 8-byte k-d node, nodes stored in pre-order (left child = index + 1).
  *   inner: a = float bits of the split position, b = (right_child_index << 2) | axis (0,1,2)
@@ -103,6 +105,17 @@ typedef struct rtb_flat_scene {
     float kd_min[3], kd_max[3];                                 /* root box                   */
     int32_t n_kd_nodes;   const rtb_kdnode *kd_nodes;
     int64_t n_kd_refs;    const uint32_t *kd_leaf_tris;
+    /* convex accelerator (RTB_ACCEL_CONVEX*): reference PerformanceTest/ConvexAcc.h:8-28.  The tunnel is n_cx_path - 1
+     * segments of 2 * n_cx_edges triangles each (tri order = surface[seg][j]).                                        */
+    int32_t n_cx_path;    const float *cx_frames;  /* [n_cx_path][8]: path vertex xyz, ring normal xyz, cos / sin of the
+                                                       rotation that maps the ring's plane to z = 0 (ConvexAcc.cpp:12-18;
+                                                       host cosf / sinf / atan2f, as the reference evaluates them)        */
+    int32_t n_cx_edges;   const float *cx_edges;   /* [n_cx_edges][3]: A, B, C of A*x + B*y + C > 0 (ConvexAcc.cpp:183-214) */
+    float cx_width, cx_height;                      /* bounding rectangle of the cross section (Tunnel.h:19-20)              */
+    const uint8_t *cx_cell_status;                  /* [100*100] 0 Hit, 1 Partial, 2 Miss (ConvexAcc.cpp:216-247)            */
+    const int16_t *cx_cell_range;                   /* [100*100][2] first / last edge to test in a Partial cell              */
+    const uint16_t *cx_order;                       /* RTB_ACCEL_CONVEX: [100][360][2*n_cx_edges] triangle order per
+                                                       (height, angle) bin (ConvexAcc.cpp:249-270)                           */
 } rtb_flat_scene;
 
 /* ---- camera: reference Camera.h:7-23; the derived fields are computed on the host exactly as

@@ -16,7 +16,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 STAT_NAMES = ["n_top", "n_tris", "grid_x", "grid_y", "grid_z", "cells_nonempty", "cell_entries",
               "cell_max", "kd_nodes", "kd_leaves", "kd_leaf_refs", "kd_max_depth"]
-ALGORITHMS = {"linear": 0, "rgrid": 1, "fgrid": 2, "kd": 3, "sah": 4}
+ALGORITHMS = {"linear": 0, "rgrid": 1, "fgrid": 2, "kd": 3, "sah": 4, "convex": 5, "convexsimple": 6}
 SETTINGS = {"preset": 0, "simple": 1, "default": 2, "highspeed": 3, "highquality": 4}
 
 

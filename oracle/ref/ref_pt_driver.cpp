@@ -110,6 +110,33 @@ extern "C" int ref_pt_bounce(oracle_bounce_job *job)
         }
         job->struct_hash = h;
     }
+    if (tunnel->accConvex)
+    { // the convex accelerator's tables (ConvexAcc.h:24-27) + the per-polygon frames intersectWithPolygon derives
+        ConvexAcc *X = tunnel->accConvex;
+        uint64_t h = 0xcbf29ce484222325ull;
+        hmix(h, 0x43565800u);
+        hmix(h, (uint32_t)tunnel->path.size()); hmix(h, (uint32_t)tunnel->crossSection.vertices.size());
+        hmix(h, fbits(tunnel->width)); hmix(h, fbits(tunnel->height));
+        for (size_t i = 0; i < tunnel->path.size(); i++)
+        {
+            Point p = tunnel->path[i];
+            Vector n = tunnel->nvs[i];
+            float theta = PI - atan2(n.x, n.z); // ConvexAcc.cpp:14
+            const float v[8] = {p.x, p.y, p.z, n.x, n.y, n.z, cos(theta), sin(theta)};
+            for (int q = 0; q < 8; q++) hmix(h, fbits(v[q]));
+        }
+        for (size_t e = 0; e < X->edgeParams.size(); e++) { hmix(h, fbits(X->edgeParams[e].A)); hmix(h, fbits(X->edgeParams[e].B)); hmix(h, fbits(X->edgeParams[e].C)); }
+        for (int i = 0; i < 100; i++)
+            for (int j = 0; j < 100; j++)
+                hmix(h, X->intersectionTable[i][j] == ConvexAcc::Hit ? 0u : (X->intersectionTable[i][j] == ConvexAcc::Partial ? 1u : 2u));
+        for (int i = 0; i < 100; i++)
+            for (int j = 0; j < 100; j++) { hmix(h, (uint32_t)(uint16_t)X->edgeRangeTable[i][j].start); hmix(h, (uint32_t)(uint16_t)X->edgeRangeTable[i][j].end); }
+        if (tunnel->algorithm == Tunnel::Convex)
+            for (int y = 0; y < 100; y++)
+                for (int a = 0; a < 360; a++)
+                    for (size_t k = 0; k < X->intersectionTableYAxis[y][a].size(); k++) hmix(h, (uint32_t)X->intersectionTableYAxis[y][a][k]);
+        job->struct_hash = h;
+    }
     if (tunnel->accKdTree && tunnel->accKdTree->root)
     {
         KdTreeAcc::KdNode *root = tunnel->accKdTree->root;

@@ -23,6 +23,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <vector>
 #include <omp.h>
 
@@ -323,7 +324,16 @@ struct TunnelO
     // k-d tree (Tunnel.h:75-93); nodes are stored in creation = pre-order
     std::vector<KdNodeO> nodes;
     int leaves; long long leafRefs; int maxDepth;
+    // convex accelerator (PerformanceTest/ConvexAcc.h): cross section, path, ring normals, tables
+    float width = 0, height = 0;
+    int trisPerSegment = 0;
+    std::vector<V3> cs, path, nvs;
+    std::vector<V3> edge;                 // {A, B, C}: A * x + B * y + C > 0 inside
+    std::vector<unsigned char> cellStatus; // [100][100]: 0 Hit, 1 Partial, 2 Miss
+    std::vector<short> cellRange;          // [100][100][2]
+    std::vector<unsigned short> yAxis;     // [100][360][2 * edges]
 };
+struct RayCtx { bool inTunnel; int segment; }; // RayContext.h:5-13
 
 bool ringConvexity(const std::vector<V3> &front, const std::vector<V3> &rear, std::vector<int> &conn)
 { // TunnelGenerator.cpp:6-176 createPolyhedron; conn: 0 BC, 1 AD, 2 Both, 3 Invalid
@@ -445,6 +455,15 @@ void generateTunnel(TunnelO &T, float rectWidth, float rectHeight, float archHei
     }
     T.tris.clear();
     for (int i = 0; i < pathSegments; i++) T.tris.insert(T.tris.end(), surface[i].begin(), surface[i].end());
+    T.width = rectWidth; T.height = rectHeight + archHeight;
+    T.cs = cs; T.nvs = nvs;
+    T.trisPerSegment = 2 * (int)cs.size();
+    T.path.clear();
+    for (int i = 0; i <= pathSegments; i++)
+    {
+        const float theta = pathAngle * i / pathSegments;
+        T.path.push_back(v3(pathRadius * (1.0f - cosf(theta)), 0.0f, -pathRadius * sinf(theta)));
+    }
 }
 
 void tunnelBounds(const TunnelO &T, V3 &mn, V3 &mx)
@@ -794,6 +813,211 @@ bool linearIntersect(const TunnelO &T, const RayO &ray, int &triOut, float &tOut
 // Scene, camera, settings -- GeometrySet.cpp, Camera.cpp:4-26, RenderSetting.h:40-78
 // ------------------------------------------------------------------------------------------
 enum { PRIM_PLANE = 0, PRIM_SPHERE = 1, PRIM_TRIANGLE = 2, PRIM_TUNNEL = 3 };
+// ------------------------------------------------------------------------------------------
+// Convex accelerator -- PerformanceTest/ConvexAcc.cpp (the author's own method): the tunnel is a chain
+// of convex polyhedra between consecutive cross-section polygons; a ray inside walks from polygon to
+// polygon (a 2D point-in-convex-polygon test through a 100x100 lookup table) until it leaves through a
+// wall, where it tests that segment's triangles -- all of them in list order (ConvexSimple) or in the
+// order of a (height, angle) table (Convex) -- and returns the FIRST accepted one, not the nearest.
+// ------------------------------------------------------------------------------------------
+enum { CONVEX_TABLE = 100 };
+inline int f2i(float f) { return (f >= -2147483648.0f && f < 2147483648.0f) ? (int)f : (int)0x80000000; } // cvttss2si
+
+inline bool convexCorner(const TunnelO &T, float x, float y)
+{ // ConvexAcc.cpp:103-118: inside all edges (with the 0.0001 leak margin)
+    for (size_t j = 0; j < T.edge.size(); j++)
+        if (T.edge[j].x * x + T.edge[j].y * y + T.edge[j].z < 0.0001f) return false;
+    return true;
+}
+
+void initConvex(TunnelO &T)
+{ // ConvexAcc.cpp:181-271
+    const size_t n = T.cs.size();
+    T.edge.clear();
+    for (size_t i = 0; i < n; i++)
+    {
+        const V3 p1 = T.cs[i], p2 = T.cs[(i + 1) % n];
+        T.edge.push_back(v3(p1.y - p2.y, p2.x - p1.x, p1.x * p2.y - p2.x * p1.y));
+    }
+    T.cellStatus.assign(CONVEX_TABLE * CONVEX_TABLE, 2);
+    T.cellRange.assign(CONVEX_TABLE * CONVEX_TABLE * 2, -1);
+    for (int i = 0; i < CONVEX_TABLE; i++)
+        for (int j = 0; j < CONVEX_TABLE; j++)
+        {
+            const float cellWidth = T.width / (CONVEX_TABLE - 1.0f), cellHeight = T.height / (CONVEX_TABLE - 1.0f);
+            const float cx = i * cellWidth - T.width / 2, cy = j * cellHeight;
+            const float px[4] = {cx + -cellWidth / 2, cx + cellWidth / 2, cx + -cellWidth / 2, cx + cellWidth / 2};
+            const float py[4] = {cy + -cellHeight / 2, cy + -cellHeight / 2, cy + cellHeight / 2, cy + cellHeight / 2};
+            int hit = 0;
+            for (int c = 0; c < 4; c++) hit += convexCorner(T, px[c], py[c]) ? 1 : 0;
+            short mn = -1, mx = -1;
+            unsigned char status;
+            if (hit == 4) status = 0;
+            else if (hit == 0) status = 2;
+            else
+            { // Partial: the range of edges that may cross the cell (ConvexAcc.cpp:136-176)
+                status = 1;
+                mn = SHRT_MAX; mx = SHRT_MIN;
+                for (size_t e = 0; e < n; e++)
+                {
+                    const V3 start = T.cs[e], end = T.cs[(e + 1) % n];
+                    float sd[4];
+                    for (int c = 0; c < 4; c++) sd[c] = T.edge[e].x * px[c] + T.edge[e].y * py[c] + T.edge[e].z;
+                    if ((sd[0] > 0.0001 && sd[1] > 0.0001 && sd[2] > 0.0001 && sd[3] > 0.0001) ||
+                        (sd[0] < -0.0001 && sd[1] < -0.0001 && sd[2] < -0.0001 && sd[3] < -0.0001)) continue; // double compares
+                    if (start.x > px[3] && end.x > px[3]) continue;
+                    if (start.x < px[0] && end.x < px[0]) continue;
+                    if (start.y > py[3] && end.y > py[3]) continue;
+                    if (start.y < py[0] && end.y < py[0]) continue;
+                    if ((short)e > mx) mx = (short)e;
+                    if ((short)e < mn) mn = (short)e;
+                }
+            }
+            T.cellStatus[i * CONVEX_TABLE + j] = status;
+            T.cellRange[(i * CONVEX_TABLE + j) * 2] = mn;
+            T.cellRange[(i * CONVEX_TABLE + j) * 2 + 1] = mx;
+        }
+    T.yAxis.clear();
+    if (T.algorithm != 5) return;
+    T.yAxis.resize((size_t)100 * 360 * 2 * n);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int y = 0; y < 100; y++)
+        for (int iAngle = 0; iAngle < 360; iAngle++)
+        { // ConvexAcc.cpp:236-270: edges ordered by how far (in angle) they are from the ray (0, height*(y+.5)/100) + angle
+            const float ty = T.height * (y + 0.5f) / 100.0f;
+            const float targetAngle = iAngle / 360.0f * PI_F * 2;
+            std::multimap<float, int> mapping;
+            for (size_t e = 0; e < n; e++)
+            {
+                const V3 p1 = T.cs[e], p2 = T.cs[(e + 1) % n];
+                const V3 v1 = v3(p1.x - 0, p1.y - ty, p1.z - 0), v2 = v3(p2.x - 0, p2.y - ty, p2.z - 0);
+                const V3 v = v3(cosf(targetAngle), sinf(targetAngle), 0);
+                float delta;
+                if (v1.x * v.y - v1.y * v.x > 0 && v.x * v2.y - v.y * v2.x > 0) delta = 0;
+                else
+                {
+                    const float mxp = (p1.x + p2.x) / 2, myp = (p1.y + p2.y) / 2;
+                    const float angle = atan2f(myp - ty, mxp - 0.0f);
+                    delta = targetAngle - angle;
+                    delta = (delta > PI_F) ? delta - 2 * PI_F : delta;
+                    delta = fabsf(delta);
+                }
+                mapping.insert(std::multimap<float, int>::value_type(delta, (int)e));
+            }
+            unsigned short *row = &T.yAxis[((size_t)y * 360 + iAngle) * 2 * n];
+            size_t k = 0;
+            for (std::multimap<float, int>::iterator it = mapping.begin(); it != mapping.end(); ++it)
+            {
+                row[k++] = (unsigned short)(it->second * 2);
+                row[k++] = (unsigned short)(it->second * 2 + 1);
+            }
+        }
+}
+
+// ConvexAcc.cpp:37-84; `distance` is only written when the ray crosses the polygon's plane
+inline bool convexAtOrigin(const TunnelO &T, V3 o, V3 d, float &distance)
+{
+    if (o.z * d.z >= 0) return false;
+    distance = (0 - o.z) / d.z;
+    const V3 p = o + d * distance;
+    const float cellWidth = T.width / (CONVEX_TABLE - 1.0f), cellHeight = T.height / (CONVEX_TABLE - 1.0f);
+    int i = f2i((p.x + T.width / 2) / cellWidth + 0.5f), j = f2i(p.y / cellHeight + 0.5f);
+    i = std::max(i, 0); j = std::max(j, 0);
+    i = std::min(i, CONVEX_TABLE - 1); j = std::min(j, CONVEX_TABLE - 1);
+    const unsigned char st = T.cellStatus[i * CONVEX_TABLE + j];
+    if (st == 0) return true;
+    if (st == 2) return false;
+    const int begin = T.cellRange[(i * CONVEX_TABLE + j) * 2], end = T.cellRange[(i * CONVEX_TABLE + j) * 2 + 1];
+    for (int e = begin; e <= end; e++)
+        if (T.edge[e].x * p.x + T.edge[e].y * p.y + T.edge[e].z < 0.0001f) return false;
+    return true;
+}
+
+// ConvexAcc.cpp:7-35: bring the ray into the frame of polygon `index` (rotation about y + translation)
+inline bool convexPolygon(const TunnelO &T, const RayO &ray, int index, V3 &origin, V3 &dir, float &distance)
+{
+    const V3 p = T.path[index], n = T.nvs[index];
+    const float theta = PI_F - atan2f(n.x, n.z);
+    const float c = cosf(theta), s = sinf(theta);
+    const V3 q = v3(ray.o.x + (0 - p.x), ray.o.y + (0 - p.y), ray.o.z + (0 - p.z));
+    V3 newOrigin = v3(c * q.x + 0 * q.y + s * q.z, 0 * q.x + 1 * q.y + 0 * q.z, -s * q.x + 0 * q.y + c * q.z);
+    V3 newDir = v3(c * ray.d.x + 0 * ray.d.y + s * ray.d.z, 0 * ray.d.x + 1 * ray.d.y + 0 * ray.d.z, -s * ray.d.x + 0 * ray.d.y + c * ray.d.z);
+    const bool hit = convexAtOrigin(T, newOrigin, newDir, distance);
+    if (!hit)
+    {
+        newOrigin.z = 0;
+        newDir.z = 0;
+        newDir = normalize(newDir);
+        origin = newOrigin;
+        dir = newDir;
+    }
+    return hit;
+}
+
+bool linearIntersect(const TunnelO &T, const RayO &ray, int &triOut, float &tOut, Probe *pr);
+
+// ConvexAcc.cpp:273-415.  Returns the first accepted triangle of the wall segment the ray leaves through.
+bool convexIntersect(const TunnelO &T, const RayO &ray, RayCtx &ctx, int &triOut, float &tOut, Probe *pr)
+{
+    RayO adv = ray;
+    float distance = 0; // uninitialised in the reference; only read after a call that wrote it, except through
+                        // the stale-value path described at convexAtOrigin
+    const int N = (int)T.path.size() - 1;
+    if (!ctx.inTunnel)
+    {
+        V3 no, nd;
+        if (convexPolygon(T, ray, 0, no, nd, distance) && dot(ray.d, T.nvs[0]) > 0)
+        {
+            ctx.inTunnel = true; ctx.segment = 0;
+            adv.o = at(ray, distance); adv.d = ray.d;
+        }
+        else if (convexPolygon(T, ray, N, no, nd, distance) && dot(ray.d, T.nvs[N]) < 0)
+        {
+            ctx.inTunnel = true; ctx.segment = N - 1;
+            adv.o = at(ray, distance); adv.d = ray.d;
+        }
+        else return linearIntersect(T, ray, triOut, tOut, pr);
+    }
+    const int begin = ctx.segment;
+    if (!(dot(ray.d, T.nvs[begin]) > 0)) return false; // "Backward": unimplemented in the reference (lines 405-410)
+    for (int i = begin + 1; i <= N; i++)
+    {
+        V3 no, nd;
+        if (!convexPolygon(T, adv, i, no, nd, distance))
+        { // leaves through the wall of segment i - 1
+            const int base = (i - 1) * T.trisPerSegment;
+            if (T.algorithm == 6)
+            {
+                for (int j = 0; j < T.trisPerSegment; j++)
+                {
+                    float t;
+                    if (triIntersect(T.tris[base + j], ray, t, pr)) { ctx.segment = i - 1; triOut = base + j; tOut = t; return true; }
+                }
+            }
+            else
+            {
+                const float y = no.y - no.x * nd.y / nd.x;
+                int index = f2i(99.0f * y / T.height + 0.5f);
+                index = std::max(0, index); index = std::min(99, index);
+                float fAngle = atan2f(nd.y, nd.x);
+                fAngle = (fAngle < 0) ? fAngle + PI_F * 2 : fAngle;
+                int iAngle = f2i(fAngle / PI_F * 180.0f + 0.5f) % 360;
+                iAngle = std::max(0, iAngle); iAngle = std::min(359, iAngle);
+                const unsigned short *row = &T.yAxis[((size_t)index * 360 + iAngle) * T.trisPerSegment];
+                for (int j = 0; j < T.trisPerSegment; j++)
+                {
+                    float t;
+                    if (triIntersect(T.tris[base + row[j]], ray, t, pr)) { ctx.segment = i - 1; triOut = base + row[j]; tOut = t; return true; }
+                }
+                adv.o = at(adv, distance);
+            }
+        }
+        else adv.o = at(adv, distance);
+    }
+    ctx.inTunnel = false;
+    return false;
+}
+
 struct Prim { int type; PlaneO plane; SphereO sphere; Tri tri; int mat; };
 
 struct Camera { V3 eye, front, up, right; float ratio, xcenter, fov, fovScale, forward; };
@@ -935,7 +1159,7 @@ bool buildPreset(Scene &s, const oracle_job *job)
     return true;
 }
 
-Hit sceneIntersect(const Scene &s, const RayO &ray, Probe *pr)
+Hit sceneIntersect(const Scene &s, const RayO &ray, Probe *pr, RayCtx *ctx = nullptr)
 { // GeometrySet.cpp:95-110 (strict <, insertion order) + Tunnel.cpp:1299-1309 dispatch
     if (pr && pr->cnt) pr->cnt->rays++;
     Hit best; memset(&best, 0, sizeof(best));
@@ -964,6 +1188,11 @@ Hit sceneIntersect(const Scene &s, const RayO &ray, Probe *pr)
             const TunnelO &T = s.tunnel;
             if (T.algorithm == 1 || T.algorithm == 2) ok = gridIntersect(T, ray, tri, t, pr);
             else if (T.algorithm == 3 || T.algorithm == 4) ok = kdIntersect(T, ray, tri, t, pr);
+            else if (T.algorithm == 5 || T.algorithm == 6)
+            { // the ray's context is mutated by the tunnel whatever the other geometries return (Ray.h:11-16)
+                RayCtx fresh = {false, -1};
+                ok = convexIntersect(T, ray, ctx ? *ctx : fresh, tri, t, pr);
+            }
             else ok = linearIntersect(T, ray, tri, t, pr);
             if (ok) { h.hit = true; h.id = nTop + tri; h.t = t; h.pos = at(ray, t); h.n = T.tris[tri].n; h.mat = T.tris[tri].mat; }
         }
@@ -1154,7 +1383,8 @@ void hashKd(const TunnelO &T, int node, uint64_t &h)
 // ------------------------------------------------------------------------------------------
 extern "C" int rt_oracle_bounce(oracle_bounce_job *job)
 {
-    if (!job || job->n < 0 || job->algorithm < 0 || job->algorithm > 4 || !job->xy) return -1;
+    if (!job || job->n < 0 || job->algorithm < 0 || job->algorithm > 6 || !job->xy) return -1;
+    if (job->algorithm > 4 && !job->pt_builders) return -1; // the convex accelerator needs that program's ring normals
     Scene s;
     s.hasTunnel = true;
     const int dummy = addMat(s, solid(v3(0, 0, 0), v3(0, 0, 0), 1, 0, 0));
@@ -1170,6 +1400,7 @@ extern "C" int rt_oracle_bounce(oracle_bounce_job *job)
     const auto t0 = std::chrono::steady_clock::now();
     if (job->algorithm == 1 || job->algorithm == 2) initGrid(s.tunnel);
     else if (job->algorithm == 3 || job->algorithm == 4) initKd(s.tunnel);
+    else if (job->algorithm == 5 || job->algorithm == 6) initConvex(s.tunnel);
     job->prepare_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     memset(job->stats, 0, sizeof(job->stats));
     job->struct_hash = 0;
@@ -1193,6 +1424,25 @@ extern "C" int rt_oracle_bounce(oracle_bounce_job *job)
             hmix(h, (uint32_t)c); hmix(h, (uint32_t)l.size());
             for (size_t i = 0; i < l.size(); i++) hmix(h, (uint32_t)l[i]);
         }
+        job->struct_hash = h;
+    }
+    if (job->algorithm == 5 || job->algorithm == 6)
+    { // the convex accelerator's tables
+        const TunnelO &T = s.tunnel;
+        uint64_t h = H0;
+        hmix(h, 0x43565800u);
+        hmix(h, (uint32_t)T.path.size()); hmix(h, (uint32_t)T.cs.size());
+        hmix(h, fbits(T.width)); hmix(h, fbits(T.height));
+        for (size_t i = 0; i < T.path.size(); i++)
+        {
+            const float theta = PI_F - atan2f(T.nvs[i].x, T.nvs[i].z);
+            const float v[8] = {T.path[i].x, T.path[i].y, T.path[i].z, T.nvs[i].x, T.nvs[i].y, T.nvs[i].z, cosf(theta), sinf(theta)};
+            for (int q = 0; q < 8; q++) hmix(h, fbits(v[q]));
+        }
+        for (size_t e = 0; e < T.edge.size(); e++) { hmix(h, fbits(T.edge[e].x)); hmix(h, fbits(T.edge[e].y)); hmix(h, fbits(T.edge[e].z)); }
+        for (size_t i = 0; i < T.cellStatus.size(); i++) hmix(h, T.cellStatus[i]);
+        for (size_t i = 0; i < T.cellRange.size(); i++) hmix(h, (uint32_t)(uint16_t)T.cellRange[i]);
+        for (size_t i = 0; i < T.yAxis.size(); i++) hmix(h, T.yAxis[i]);
         job->struct_hash = h;
     }
     if (job->algorithm == 3 || job->algorithm == 4)
@@ -1226,9 +1476,10 @@ extern "C" int rt_oracle_bounce(oracle_bounce_job *job)
         RayO ray = {eye, normalize(front + r + u)};
         int depth = 0, reached = 0, lastId = -1;
         V3 lastPos = v3(0, 0, 0);
+        RayCtx ctx = {false, -1}; // newRay.context = r.context, main.cpp:57
         while (true)
         { // main.cpp:29-59
-            const Hit h = sceneIntersect(s, ray, nullptr);
+            const Hit h = sceneIntersect(s, ray, nullptr, &ctx);
             total++;
             if (!h.hit) { lastId = -1; break; }
             lastId = h.id; lastPos = h.pos;

@@ -91,17 +91,17 @@ PT_CASES = {  # name -> (radius, angle, arch_seg, path_seg): the tunnels of the 
 
 def bounce_pt_golden():
     """tests/golden/bounce_pt_golden.{npz,json}: the PerformanceTest program itself (libref_pt.so: its generator, its
-    GridAcc / KdTreeAcc builders incl. the event-sweep SAH, its trace): per-ray results, k-d tree sizes and hashes;
+    GridAcc / KdTreeAcc / ConvexAcc builders incl. the event-sweep SAH, its trace): per-ray results, structure sizes and hashes;
     plus the full-size trees (150 x 150, radius 5000) -- structure only."""
     xy = np.random.default_rng(22).random((300, 2), dtype=np.float32)
     out, meta = {"xy": xy}, {}
     for name, (radius, angle, aseg, pseg) in PT_CASES.items():
-        for alg in ("rgrid", "fgrid", "kd", "sah"):
+        for alg in ("rgrid", "fgrid", "kd", "sah", "convex", "convexsimple"):
             a = O.bounce("ref_pt", xy, radius, angle, aseg, pseg, alg)
             for k in ("reached", "depth", "last_id", "last_pos"):
                 out[f"{name}.{alg}.{k}"] = a[k]
             meta[f"{name}.{alg}"] = {"stats": a["stats"], "struct_hash": f"{a['struct_hash']:016x}", "total_rays": a["total_rays"]}
-    for alg in ("kd", "sah"):
+    for alg in ("kd", "sah", "convex", "convexsimple"):
         a = O.bounce("ref_pt", xy[:4], 5000.0, 1.5707964, 150, 150, alg)
         meta[f"r5000_s150.{alg}"] = {"stats": a["stats"], "struct_hash": f"{a['struct_hash']:016x}"}
     np.savez_compressed(os.path.join(HERE, "bounce_pt_golden.npz"), **out)

@@ -27,7 +27,7 @@ def test_header_symbols_exported():
 
 def test_abi_version_and_struct_sizes():
     lib = rtb200.cuda_lib()
-    assert lib.rtb_abi_version() == 1
+    assert lib.rtb_abi_version() == 2
     assert C.sizeof(rtb200.Material) == 64 and C.sizeof(rtb200.Prim) == 48
     assert C.sizeof(rtb200.KdNode) == 8 and C.sizeof(rtb200.CellWord) == 8
 

@@ -467,6 +467,38 @@ def test_dropin_8bit_and_bitmap(ctx, tmp_path):
     assert np.array_equal(rows, img8)
 
 
+# ---- PerformanceTest console benchmark and convex accelerators (rank 3) --------------
+@pytest.mark.parametrize("alg", ["convex", "convexsimple"])
+def test_convex_accelerators_vs_oracle(ctx, alg):
+    """Convex / ConvexSimple (PerformanceTest/ConvexAcc.cpp) on 4,000 rays of the full-size 150 x 150 tunnel, bit-exact
+    against the oracle (itself bit-exact against the compiled reference): reached, depth, last hit id / position."""
+    xy = np.random.default_rng(17).random((4000, 2), dtype=np.float32)
+    o = O.bounce("oracle", xy, 2000.0, 1.5708, 150, 150, alg, pt_builders=True)
+    g = rtb200.perf_test(xy, 2000.0, 1.5708, 150, 150, alg)
+    for k in ("reached", "depth", "last_id"):
+        assert np.array_equal(g[k], o[k]), (k, int((g[k] != o[k]).sum()))
+    assert np.array_equal(_bits(g["last_pos"]), _bits(o["last_pos"]))
+    assert g["total_rays"] == o["total_rays"]
+
+
+def test_convex_accelerator_renders_and_single_rays(ctx):
+    """The convex accelerator behind the other entry points: a Whitted frame (the context travels down the reflection
+    chain) equals the per-ray API applied bounce by bounce is not required -- here: the frame is deterministic, finite,
+    and primary hits agree with the SAH tree wherever both report the nearest triangle (the convex walk returns the
+    first accepted triangle of the wall segment, which for a ray inside a convex segment is the only one)."""
+    sc = rtb200.PerfScene(2000.0, 1.5708, 60, 60, "convex")
+    ss = rtb200.PerfScene(2000.0, 1.5708, 60, 60, "sah")
+    dc, ds = ctx.upload(sc.flat), ctx.upload(ss.flat)
+    a = dc.trace_primary(sc.camera, 160, 120)
+    b = ds.trace_primary(ss.camera, 160, 120)
+    agree = (a["hit_id"] == b["hit_id"]).mean()
+    assert agree > 0.999, agree
+    img1, st1 = dc.render(sc.camera, sc.setting, rtb200.make_frame(160, 120))
+    img2, st2 = dc.render(sc.camera, sc.setting, rtb200.make_frame(160, 120))
+    assert np.isfinite(img1).all() and np.array_equal(_bits(img1), _bits(img2)) and st1["n_rays"] == st2["n_rays"]
+    dc.close(); ds.close(); sc.close(); ss.close()
+
+
 # ---- PerformanceTest console benchmark (SURVEY 8f rank 1) ---------------------------------------------
 @pytest.mark.parametrize("alg", ["rgrid", "fgrid", "kd", "sah", "linear"])
 def test_performance_test_bounce_workload(ctx, alg):
@@ -488,10 +520,11 @@ def test_performance_test_bounce_workload(ctx, alg):
 @pytest.mark.parametrize("case", ["r2000_s30", "r100_a75_s24x12"])
 def test_performance_test_program_golden(ctx, case):
     """The same workload against fixtures recorded from the compiled PerformanceTest sources themselves
-    (oracle/_ref/libref_pt.so -> tests/golden/bounce_pt_golden.npz): grids, median tree, event-sweep SAH tree."""
+    (oracle/_ref/libref_pt.so -> tests/golden/bounce_pt_golden.npz): grids, median tree, event-sweep SAH tree and the
+    convex accelerators (first accepted triangle of the wall segment, ray context carried over bounces)."""
     cases = {"r2000_s30": (2000.0, 1.5708, 30, 30), "r100_a75_s24x12": (100.0, 1.309, 24, 12)}
     gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "bounce_pt_golden.npz"))
-    for alg in ("rgrid", "kd", "sah"):
+    for alg in ("rgrid", "kd", "sah", "convex", "convexsimple"):
         g = rtb200.perf_test(gold["xy"], *cases[case], alg)
         for k in ("reached", "depth", "last_id", "last_pos"):
             assert np.array_equal(_bits(g[k]), _bits(gold[f"{case}.{alg}.{k}"])), (alg, k)

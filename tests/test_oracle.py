@@ -114,11 +114,12 @@ PT_CASES = {"r2000_s30": (2000.0, 1.5708, 30, 30), "r100_a75_s24x12": (100.0, 1.
 
 
 @pytest.mark.skipif(not O.available("ref_pt"), reason="oracle/_ref/libref_pt.so not built (no /root/reference)")
-@pytest.mark.parametrize("alg", ["linear", "rgrid", "fgrid", "kd", "sah"])
+@pytest.mark.parametrize("alg", ["linear", "rgrid", "fgrid", "kd", "sah", "convex", "convexsimple"])
 def test_pt_program_oracle_matches_ref_pt(alg):
     """oracle (pt_builders) == src/PerformanceTest compiled as it is: tunnel generator (TunnelGenerator.cpp:243-279),
-    GridAcc, KdTreeAcc median and event-sweep SAH with automatic termination (KdTreeAcc.cpp:38-274) -- structure
-    hash, tree sizes and every per-ray result of main.cpp's trace."""
+    GridAcc, KdTreeAcc median and event-sweep SAH with automatic termination (KdTreeAcc.cpp:38-274), ConvexAcc tables
+    and polygon walk with the ray context carried over the bounces (ConvexAcc.cpp) -- structure hash, sizes and every
+    per-ray result of main.cpp's trace."""
     xy = np.random.default_rng(5).random((200, 2), dtype=np.float32)
     a = O.bounce("ref_pt", xy, 1000.0, 1.5707964, 40, 40, alg)
     b = O.bounce("oracle", xy, 1000.0, 1.5707964, 40, 40, alg, pt_builders=True)
@@ -138,7 +139,7 @@ def test_pt_program_golden(case):
     with open(os.path.join(here, "bounce_pt_golden.json")) as f:
         meta = json.load(f)
     radius, angle, aseg, pseg = PT_CASES[case]
-    for alg in ("rgrid", "kd", "sah") + (("fgrid",) if case == "r2000_s30" else ()):
+    for alg in ("rgrid", "kd", "sah", "convex", "convexsimple") + (("fgrid",) if case == "r2000_s30" else ()):
         b = O.bounce("oracle", g["xy"], radius, angle, aseg, pseg, alg, pt_builders=True)
         m = meta[f"{case}.{alg}"]
         assert f"{b['struct_hash']:016x}" == m["struct_hash"] and b["stats"] == m["stats"] and b["total_rays"] == m["total_rays"]
@@ -154,7 +155,7 @@ def test_pt_program_full_size_trees_golden():
     with open(os.path.join(os.path.dirname(__file__), "golden", "bounce_pt_golden.json")) as f:
         meta = json.load(f)
     xy = np.full((2, 2), 0.5, np.float32)
-    for alg in ("kd", "sah"):
+    for alg in ("kd", "sah", "convex", "convexsimple"):
         b = O.bounce("oracle", xy, 5000.0, 1.5707964, 150, 150, alg, pt_builders=True)
         m = meta[f"r5000_s150.{alg}"]
         assert f"{b['struct_hash']:016x}" == m["struct_hash"] and b["stats"] == m["stats"]

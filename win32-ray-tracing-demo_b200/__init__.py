@@ -17,7 +17,7 @@ ROOT = os.path.dirname(PKG)
 CUDA_LIB = os.path.join(PKG, "librtb200.so")
 HOST_LIB = os.path.join(PKG, "librtb200_host.so")
 
-ALGORITHMS = {"linear": 0, "rgrid": 1, "fgrid": 2, "kd": 3, "sah": 4}
+ALGORITHMS = {"linear": 0, "rgrid": 1, "fgrid": 2, "kd": 3, "sah": 4, "convex": 5, "convexsimple": 6}
 STAT_NAMES = ["n_top", "n_tris", "grid_x", "grid_y", "grid_z", "cells_nonempty", "cell_entries",
               "cell_max", "kd_nodes", "kd_leaves", "kd_leaf_refs", "kd_max_depth"]
 LAYOUT_ROWMAJOR, LAYOUT_REFERENCE, OUTPUT_RGB8 = 0, 1, 4
@@ -63,6 +63,11 @@ class FlatScene(C.Structure):
         ("kd_min", C.c_float * 3), ("kd_max", C.c_float * 3),
         ("n_kd_nodes", C.c_int32), ("kd_nodes", C.POINTER(KdNode)),
         ("n_kd_refs", C.c_int64), ("kd_leaf_tris", C.POINTER(C.c_uint32)),
+        ("n_cx_path", C.c_int32), ("cx_frames", C.POINTER(C.c_float)),
+        ("n_cx_edges", C.c_int32), ("cx_edges", C.POINTER(C.c_float)),
+        ("cx_width", C.c_float), ("cx_height", C.c_float),
+        ("cx_cell_status", C.POINTER(C.c_uint8)), ("cx_cell_range", C.POINTER(C.c_int16)),
+        ("cx_order", C.POINTER(C.c_uint16)),
     ]
 
 

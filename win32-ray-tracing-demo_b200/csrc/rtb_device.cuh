@@ -71,7 +71,19 @@ struct DScene
     V3 kd_min, kd_size; // Grid(near, far): pos = near, size = far - near (Grid.cpp:13-17)
     const uint2 *kd_nodes;
     const uint32_t *kd_tris;
+    // convex accelerator (include/rtb.h: cx_*)
+    int cx_n_path, cx_n_edges;
+    float cx_width, cx_height;
+    const float *cx_frames;
+    const float *cx_edges;
+    const uint8_t *cx_status;
+    const short *cx_range;
+    const uint16_t *cx_order;
 };
+
+// Ray::context (reference Ray.h:11-16, RayContext.h:5-13): written by the convex accelerator, copied to the
+// reflected ray by trace() (MainWindow.cpp:105, PerformanceTest/main.cpp:57)
+struct RayCtx { int inTunnel, segment; };
 
 struct Counters { unsigned long long rays, tris, steps; };
 
@@ -456,6 +468,118 @@ __device__ bool linearIntersect(const DScene &S, const Ray &ray, int &triOut, fl
 }
 
 // ---------------------------------------------------------------------------------------------
+// Convex accelerator -- reference PerformanceTest/ConvexAcc.cpp:7-84, 273-415 (Tunnel.cpp:972-1161).
+// A ray inside the tunnel walks from cross-section polygon to polygon (point-in-convex-polygon through the
+// 100 x 100 table) until it leaves through the wall of a segment, then tries that segment's triangles in
+// list order (ConvexSimple) or in the order of the (height, direction) table (Convex) and returns the FIRST
+// accepted one.  All tables come from the host (rtb_scene_upload); what runs here is float arithmetic in the
+// reference's order plus one atan2f per wall exit (CUDA's differs from glibc's in the last ulps: it can
+// select the neighbouring direction bin only when the angle sits on a bin boundary to within those ulps).
+// ---------------------------------------------------------------------------------------------
+#define RTB_CX_TABLE 100
+__device__ __forceinline__ bool convexAtOrigin(const DScene &S, V3 o, V3 d, float &distance)
+{
+    if (o.z * d.z >= 0) return false;
+    distance = (0 - o.z) / d.z;
+    const V3 p = o + d * distance;
+    const float cellWidth = S.cx_width / (RTB_CX_TABLE - 1.0f), cellHeight = S.cx_height / (RTB_CX_TABLE - 1.0f);
+    int i = f2i((p.x + S.cx_width / 2) / cellWidth + 0.5f), j = f2i(p.y / cellHeight + 0.5f);
+    i = max(i, 0); j = max(j, 0);
+    i = min(i, RTB_CX_TABLE - 1); j = min(j, RTB_CX_TABLE - 1);
+    const int cell = i * RTB_CX_TABLE + j;
+    const unsigned int st = __ldg(S.cx_status + cell);
+    if (st == 0) return true;
+    if (st == 2) return false;
+    const int begin = __ldg(S.cx_range + 2 * cell), end = __ldg(S.cx_range + 2 * cell + 1);
+    for (int e = begin; e <= end; e++)
+        if (__ldg(S.cx_edges + 3 * e) * p.x + __ldg(S.cx_edges + 3 * e + 1) * p.y + __ldg(S.cx_edges + 3 * e + 2) < 0.0001f) return false;
+    return true;
+}
+
+__device__ __forceinline__ bool convexPolygon(const DScene &S, const Ray &ray, int index, V3 &origin, V3 &dir, float &distance)
+{
+    const float *f = S.cx_frames + 8 * index;
+    const float c = __ldg(f + 6), s = __ldg(f + 7);
+    const V3 q = v3(ray.o.x + (0 - __ldg(f)), ray.o.y + (0 - __ldg(f + 1)), ray.o.z + (0 - __ldg(f + 2)));
+    V3 newOrigin = v3(c * q.x + 0 * q.y + s * q.z, 0 * q.x + 1 * q.y + 0 * q.z, -s * q.x + 0 * q.y + c * q.z);
+    V3 newDir = v3(c * ray.d.x + 0 * ray.d.y + s * ray.d.z, 0 * ray.d.x + 1 * ray.d.y + 0 * ray.d.z, -s * ray.d.x + 0 * ray.d.y + c * ray.d.z);
+    const bool hit = convexAtOrigin(S, newOrigin, newDir, distance);
+    if (!hit)
+    {
+        newOrigin.z = 0;
+        newDir.z = 0;
+        origin = newOrigin;
+        dir = normalize(newDir);
+    }
+    return hit;
+}
+
+template <class Probe>
+__device__ bool convexIntersect(const DScene &S, const Ray &ray, RayCtx &ctx, int &triOut, float &tOut, V3 &nOut, Probe &pr)
+{
+    Ray adv = ray;
+    float distance = 0;
+    const int N = S.cx_n_path - 1;
+    const int perSegment = 2 * S.cx_n_edges;
+    auto ringNormal = [&](int i) { return v3(__ldg(S.cx_frames + 8 * i + 3), __ldg(S.cx_frames + 8 * i + 4), __ldg(S.cx_frames + 8 * i + 5)); };
+    if (!ctx.inTunnel)
+    {
+        V3 no, nd;
+        if (convexPolygon(S, ray, 0, no, nd, distance) && dot(ray.d, ringNormal(0)) > 0)
+        { // through the entrance
+            ctx.inTunnel = 1; ctx.segment = 0;
+            adv.o = at(ray, distance);
+        }
+        else if (convexPolygon(S, ray, N, no, nd, distance) && dot(ray.d, ringNormal(N)) < 0)
+        { // through the exit
+            ctx.inTunnel = 1; ctx.segment = N - 1;
+            adv.o = at(ray, distance);
+        }
+        else return linearIntersect(S, ray, triOut, tOut, nOut, pr); // starts outside and never enters
+    }
+    const int begin = ctx.segment;
+    if (!(dot(ray.d, ringNormal(begin)) > 0)) return false; // "Backward" is unimplemented in the reference (ConvexAcc.cpp:405-410)
+    for (int i = begin + 1; i <= N; i++)
+    {
+        V3 no, nd;
+        if (!convexPolygon(S, adv, i, no, nd, distance))
+        { // the ray leaves through the wall of segment i - 1
+            const int base = (i - 1) * perSegment;
+            const uint16_t *row = nullptr;
+            if (S.accel == RTB_ACCEL_CONVEX)
+            {
+                const float y = no.y - no.x * nd.y / nd.x;
+                int index = f2i(99.0f * y / S.cx_height + 0.5f);
+                index = max(0, index); index = min(99, index);
+                const float PI_F = 3.14159265359f;
+                float fAngle = atan2f(nd.y, nd.x);
+                fAngle = (fAngle < 0) ? fAngle + PI_F * 2 : fAngle;
+                int iAngle = f2i(fAngle / PI_F * 180.0f + 0.5f) % 360;
+                iAngle = max(0, iAngle); iAngle = min(359, iAngle);
+                row = S.cx_order + ((size_t)index * 360 + iAngle) * perSegment;
+            }
+            for (int j = 0; j < perSegment; j++)
+            {
+                const int idx = base + (row ? (int)__ldg(row + j) : j);
+                const TriData T = loadTri(S.tri, idx);
+                pr.tri();
+                float t;
+                if (triIntersect(T, ray, t))
+                {
+                    ctx.segment = i - 1;
+                    triOut = idx; tOut = t; nOut = triNormal(T);
+                    return true;
+                }
+            }
+            if (S.accel == RTB_ACCEL_CONVEX) adv.o = at(adv, distance); // ConvexSimple does not advance here (lines 358-371)
+        }
+        else adv.o = at(adv, distance);
+    }
+    ctx.inTunnel = 0;
+    return false;
+}
+
+// ---------------------------------------------------------------------------------------------
 // GeometrySet::intersect -- reference GeometrySet.cpp:95-110 (+ Plane.cpp:9-34, Sphere.cpp:10-37)
 // ---------------------------------------------------------------------------------------------
 struct Hit { int id; int mat; int prim_type; float t; V3 pos, n; };
@@ -543,13 +667,22 @@ __device__ __forceinline__ bool sceneIntersectWith(const DScene &S, const Ray &r
 }
 
 template <class Probe>
-__device__ bool sceneIntersect(const DScene &S, const Ray &ray, Hit &best, Probe &pr)
+__device__ bool sceneIntersect(const DScene &S, const Ray &ray, Hit &best, Probe &pr, RayCtx &ctx)
 {
     return sceneIntersectWith(S, ray, best, pr, [&](int &tri, float &t, V3 &n) {
         if (S.accel == RTB_ACCEL_REGULAR_GRID || S.accel == RTB_ACCEL_FLAT_GRID) return gridIntersect<false>(S, ray, tri, t, n, pr);
         if (S.accel == RTB_ACCEL_KD_MEDIAN || S.accel == RTB_ACCEL_KD_SAH) return kdIntersect<false>(S, ray, tri, t, n, pr);
+        if (S.accel == RTB_ACCEL_CONVEX || S.accel == RTB_ACCEL_CONVEX_SIMPLE) return convexIntersect(S, ray, ctx, tri, t, n, pr);
         return linearIntersect(S, ray, tri, t, n, pr);
     });
+}
+// a ray generated by the camera or by a caller carries a fresh context
+template <class Probe>
+__device__ bool sceneIntersect(const DScene &S, const Ray &ray, Hit &best, Probe &pr)
+{
+    RayCtx ctx;
+    ctx.inTunnel = 0; ctx.segment = -1;
+    return sceneIntersect(S, ray, best, pr, ctx);
 }
 
 // ---------------------------------------------------------------------------------------------

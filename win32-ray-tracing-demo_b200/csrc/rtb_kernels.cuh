@@ -270,7 +270,9 @@ __device__ __forceinline__ V3 chainWith(const DScene &S, const FrameParams &F, i
 template <class Probe>
 __device__ __forceinline__ V3 chainPerRay(const DScene &S, const FrameParams &F, int x, int y, unsigned int &rays, Probe &pr)
 {
-    return chainWith(S, F, x, y, rays, pr, [&](const Ray &r, Hit &h) { return sceneIntersect(S, r, h, pr); });
+    RayCtx ctx; // carried along the chain: trace() copies it to the reflected ray (MainWindow.cpp:105)
+    ctx.inTunnel = 0; ctx.segment = -1;
+    return chainWith(S, F, x, y, rays, pr, [&](const Ray &r, Hit &h) { return sceneIntersect(S, r, h, pr, ctx); });
 }
 
 template <class Probe>
@@ -577,11 +579,13 @@ k_bounce_rays(const __grid_constant__ DScene S, long long n, const float *__rest
         NoProbe pr;
         int depth = 0, ok = 0, id = -1;
         V3 pos = v3(0, 0, 0);
+        RayCtx ctx; // newRay.context = r.context, PerformanceTest/main.cpp:57
+        ctx.inTunnel = 0; ctx.segment = -1;
         while (true)
         {
             Hit h;
             traced++;
-            if (!sceneIntersect(S, r, h, pr)) { id = -1; break; }
+            if (!sceneIntersect(S, r, h, pr, ctx)) { id = -1; break; }
             id = h.id; pos = h.pos;
             const V3 nl = (dot(h.n, r.d) < 0) ? h.n : h.n * -1;
             if (++depth > max_depth) break;

@@ -194,6 +194,10 @@ struct FlatScene
     std::vector<uint32_t> gridCellStart, gridCellTris;
     std::vector<rtb_kdnode> kdNodes;
     std::vector<uint32_t> kdLeafTris;
+    std::vector<float> cxFrames, cxEdges;  // convex accelerator (include/rtb.h: cx_*)
+    std::vector<uint8_t> cxCellStatus;
+    std::vector<int16_t> cxCellRange;
+    std::vector<uint16_t> cxOrder;
     rtb_flat_scene view; // pointers into the vectors above; refreshed by finish()
     int nTop = 0;
     FlatScene();
@@ -284,6 +288,8 @@ public:
     Algorithm algorithm = Linear;
     float height = 0, width = 0;
     std::vector<Point> path;
+    std::vector<Point> crossSection;                  // the polygon at the origin, Tunnel.h:11
+    std::vector<Vector> ringNormals;                  // PerformanceTest/Tunnel.h:16 `nvs` (that program's generator only)
     std::vector<std::vector<TunnelTriangle>> surface; // [segment][j], reference Tunnel.h:13
     Ptr<Material> groundMaterial, wallMaterial;
 
@@ -319,6 +325,11 @@ private:
     float kdMin_[3] = {0, 0, 0}, kdMax_[3] = {0, 0, 0};
     std::vector<rtb_kdnode> kdNodes_;
     std::vector<uint32_t> kdLeafTris_;
+    std::vector<float> cxFrames_, cxEdges_;
+    std::vector<uint8_t> cxCellStatus_;
+    std::vector<int16_t> cxCellRange_;
+    std::vector<uint16_t> cxOrder_;
+    void initConvex();
     void collect(std::vector<TunnelTriangle> &flat) const;
     void initGrid(const std::vector<TunnelTriangle> &tris);
     void initKdTree(const std::vector<TunnelTriangle> &tris);

@@ -411,7 +411,7 @@ rtbh_scene *rtbh_preset_create(int preset, int algorithm, int segments, const ch
 // handle serves the same queries as a preset's (stats, hashes, flat view) -- no camera / setting of its own.
 rtbh_scene *rtbh_perf_scene_create(float radius, float angle, int arch_seg, int path_seg, int algorithm)
 {
-    if (algorithm < 0 || algorithm > 4 || arch_seg < 1 || path_seg < 1) return nullptr;
+    if (algorithm < 0 || algorithm > 6 || arch_seg < 1 || path_seg < 1) return nullptr;
     rtbh_scene *h = new rtbh_scene();
     const double t0 = nowMs();
     h->tunnel = PerformanceTest::buildScene(h->scene, radius, angle, arch_seg, path_seg, (Tunnel::Algorithm)algorithm);
@@ -494,6 +494,20 @@ uint64_t rtbh_struct_hash(const rtbh_scene *h)
         }
         return x;
     }
+    if (f.accel == RTB_ACCEL_CONVEX || f.accel == RTB_ACCEL_CONVEX_SIMPLE)
+    { // convex accelerator tables, same convention as oracle/rt_oracle.cpp and oracle/ref/ref_pt_driver.cpp
+        if (!f.cx_frames) return 0;
+        hmix(x, 0x43565800u);
+        hmix(x, (uint32_t)f.n_cx_path); hmix(x, (uint32_t)f.n_cx_edges);
+        hmix(x, fbits(f.cx_width)); hmix(x, fbits(f.cx_height));
+        for (int i = 0; i < f.n_cx_path * 8; i++) hmix(x, fbits(f.cx_frames[i]));
+        for (int i = 0; i < f.n_cx_edges * 3; i++) hmix(x, fbits(f.cx_edges[i]));
+        for (int i = 0; i < 100 * 100; i++) hmix(x, f.cx_cell_status[i]);
+        for (int i = 0; i < 100 * 100 * 2; i++) hmix(x, (uint32_t)(uint16_t)f.cx_cell_range[i]);
+        if (f.accel == RTB_ACCEL_CONVEX)
+            for (int64_t i = 0; i < (int64_t)100 * 360 * 2 * f.n_cx_edges; i++) hmix(x, f.cx_order[i]);
+        return x;
+    }
     if (f.accel == RTB_ACCEL_KD_MEDIAN || f.accel == RTB_ACCEL_KD_SAH)
     {
         hmix(x, 0x4b445452u);
@@ -565,7 +579,7 @@ int rtbh_perf_test(float radius, float angle, int arch_seg, int path_seg, int al
                    int32_t *reached, int32_t *depth, int32_t *last_id, float *last_pos, int64_t *total_rays,
                    double *build_ms, double *preprocess_ms, double *trace_ms)
 {
-    if (algorithm < 0 || algorithm > 4) return -1;
+    if (algorithm < 0 || algorithm > 6) return -1;
     PerformanceTest pt;
     pt.build(radius, angle, arch_seg, path_seg, (Tunnel::Algorithm)algorithm);
     const double ms = pt.run(xy, n, max_depth, reached, depth, last_id, last_pos, total_rays);

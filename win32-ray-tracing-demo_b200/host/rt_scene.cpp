@@ -83,13 +83,19 @@ void FlatScene::finish()
     view.n_cell_refs = (int64_t)gridCellTris.size(); view.grid_cell_tris = gridCellTris.empty() ? nullptr : gridCellTris.data();
     view.n_kd_nodes = (int32_t)kdNodes.size(); view.kd_nodes = kdNodes.empty() ? nullptr : kdNodes.data();
     view.n_kd_refs = (int64_t)kdLeafTris.size(); view.kd_leaf_tris = kdLeafTris.empty() ? nullptr : kdLeafTris.data();
+    view.n_cx_path = (int32_t)(cxFrames.size() / 8); view.cx_frames = cxFrames.empty() ? nullptr : cxFrames.data();
+    view.n_cx_edges = (int32_t)(cxEdges.size() / 3); view.cx_edges = cxEdges.empty() ? nullptr : cxEdges.data();
+    view.cx_cell_status = cxCellStatus.empty() ? nullptr : cxCellStatus.data();
+    view.cx_cell_range = cxCellRange.empty() ? nullptr : cxCellRange.data();
+    view.cx_order = cxOrder.empty() ? nullptr : cxOrder.data();
 }
 
 size_t FlatScene::hostBytes() const
 {
     return prims.size() * sizeof(rtb_prim) + materials.size() * sizeof(rtb_material) + (looseTri.size() + tri.size()) * 4 +
            triMaterial.size() * 4 + gridWords.size() * sizeof(rtb_cellword) + (gridCellStart.size() + gridCellTris.size()) * 4 +
-           kdNodes.size() * sizeof(rtb_kdnode) + kdLeafTris.size() * 4;
+           kdNodes.size() * sizeof(rtb_kdnode) + kdLeafTris.size() * 4 + (cxFrames.size() + cxEdges.size()) * 4 +
+           cxCellStatus.size() + cxCellRange.size() * 2 + cxOrder.size() * 2;
 }
 
 // ---- geometries -------------------------------------------------------------------------------

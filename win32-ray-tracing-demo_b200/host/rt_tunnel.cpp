@@ -125,7 +125,9 @@ bool TunnelGenerator::create(float rectWidth, float rectHeight, float archHeight
             ringNormal.push_back(((dir + nextDir) * 0.5f).norm());
         }
         tunnel->performanceTestBuilders = true;
+        tunnel->ringNormals = ringNormal;
     }
+    tunnel->crossSection = section;
 
 #pragma omp parallel for schedule(dynamic, 1)
     for (int i = 0; i < pathSegments; i++)
@@ -218,11 +220,120 @@ void Tunnel::init()
     std::vector<TunnelTriangle> tris;
     collect(tris);
     gridWords_.clear(); gridCellStart_.clear(); gridCellTris_.clear(); kdNodes_.clear(); kdLeafTris_.clear();
+    cxFrames_.clear(); cxEdges_.clear(); cxCellStatus_.clear(); cxCellRange_.clear(); cxOrder_.clear();
     stats = BuildStats();
     if (algorithm == RegularGrid || algorithm == FlatGrid) initGrid(tris);
     else if (algorithm == KdTreeStandard || algorithm == KdTreeSAH) initKdTree(tris);
+    else if (algorithm == Convex || algorithm == ConvexSimple) initConvex();
     built_ = true;
     invalidate();
+}
+
+// ---- convex accelerator tables (reference PerformanceTest/ConvexAcc.cpp:181-271) ------------------
+// Everything the device walk needs is a table built here with the host's libm, evaluated exactly as the
+// reference evaluates it (per intersect call, from the same inputs): per path vertex the rotation that maps
+// its ring onto the plane z = 0; the half-plane form of the cross-section edges; a 100 x 100 lookup over the
+// cross-section's bounding rectangle saying whether a cell is inside, outside or which edges cut it; and, for
+// Convex, the order in which a wall segment's triangles are tried for each of 100 heights x 360 directions.
+void Tunnel::initConvex()
+{
+    const size_t n = crossSection.size(), nPath = path.size();
+    if (n < 3 || nPath < 2 || ringNormals.size() != nPath) return; // flatten() emits no tables; the upload rejects the scene
+    cxFrames_.resize(nPath * 8);
+    for (size_t i = 0; i < nPath; i++)
+    {
+        const Vector &nv = ringNormals[i];
+        const float theta = PI - std::atan2(nv.x, nv.z); // ConvexAcc.cpp:14
+        float *f = &cxFrames_[i * 8];
+        f[0] = path[i].x; f[1] = path[i].y; f[2] = path[i].z;
+        f[3] = nv.x; f[4] = nv.y; f[5] = nv.z;
+        f[6] = std::cos(theta); f[7] = std::sin(theta);
+    }
+    cxEdges_.resize(n * 3);
+    for (size_t e = 0; e < n; e++)
+    { // inside <=> A*x + B*y + C > 0 for the counter-clockwise polygon
+        const Point &p1 = crossSection[e], &p2 = crossSection[(e + 1) % n];
+        cxEdges_[3 * e] = p1.y - p2.y;
+        cxEdges_[3 * e + 1] = p2.x - p1.x;
+        cxEdges_[3 * e + 2] = p1.x * p2.y - p2.x * p1.y;
+    }
+    auto side = [&](size_t e, float x, float y) { return cxEdges_[3 * e] * x + cxEdges_[3 * e + 1] * y + cxEdges_[3 * e + 2]; };
+    auto inside = [&](float x, float y) {
+        for (size_t e = 0; e < n; e++)
+            if (side(e, x, y) < 0.0001f) return false;
+        return true;
+    };
+    const int R = 100;
+    cxCellStatus_.assign((size_t)R * R, 2);
+    cxCellRange_.assign((size_t)R * R * 2, -1);
+    const float cellW = width / (R - 1.0f), cellH = height / (R - 1.0f);
+    for (int i = 0; i < R; i++)
+        for (int j = 0; j < R; j++)
+        {
+            const float cx = i * cellW - width / 2, cy = j * cellH;
+            const float x0 = cx + -cellW / 2, x1 = cx + cellW / 2, y0 = cy + -cellH / 2, y1 = cy + cellH / 2;
+            const float xs[4] = {x0, x1, x0, x1}, ys[4] = {y0, y0, y1, y1};
+            int cornersInside = 0;
+            for (int c = 0; c < 4; c++) cornersInside += inside(xs[c], ys[c]) ? 1 : 0;
+            const size_t cell = (size_t)i * R + j;
+            if (cornersInside == 4) { cxCellStatus_[cell] = 0; continue; }
+            if (cornersInside == 0) { cxCellStatus_[cell] = 2; continue; }
+            cxCellStatus_[cell] = 1;
+            int first = SHRT_MAX, last = SHRT_MIN;
+            for (size_t e = 0; e < n; e++)
+            {
+                float sd[4];
+                for (int c = 0; c < 4; c++) sd[c] = side(e, xs[c], ys[c]);
+                // the reference compares against the double literal 0.0001 here (ConvexAcc.cpp:152-153)
+                const bool allLeft = sd[0] > 0.0001 && sd[1] > 0.0001 && sd[2] > 0.0001 && sd[3] > 0.0001;
+                const bool allRight = sd[0] < -0.0001 && sd[1] < -0.0001 && sd[2] < -0.0001 && sd[3] < -0.0001;
+                if (allLeft || allRight) continue;
+                const Point &a = crossSection[e], &b = crossSection[(e + 1) % n];
+                if ((a.x > x1 && b.x > x1) || (a.x < x0 && b.x < x0) || (a.y > y1 && b.y > y1) || (a.y < y0 && b.y < y0)) continue;
+                first = std::min(first, (int)e);
+                last = std::max(last, (int)e);
+            }
+            cxCellRange_[cell * 2] = (int16_t)first;
+            cxCellRange_[cell * 2 + 1] = (int16_t)last;
+        }
+    if (algorithm != Convex) return;
+    // order of the edges by their angular distance from the 2D ray (0, height*(y+0.5)/100) + direction iAngle degrees;
+    // the reference fills a multimap (equal keys keep insertion order) = a stable sort by that distance
+    cxOrder_.resize((size_t)100 * 360 * 2 * n);
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int y = 0; y < 100; y++)
+    {
+        std::vector<std::pair<float, int>> keyed(n);
+        for (int iAngle = 0; iAngle < 360; iAngle++)
+        {
+            const float ty = height * (y + 0.5f) / 100.0f;
+            const float target = iAngle / 360.0f * PI * 2;
+            const float vx = std::cos(target), vy = std::sin(target);
+            for (size_t e = 0; e < n; e++)
+            {
+                const Point &p1 = crossSection[e], &p2 = crossSection[(e + 1) % n];
+                const float ax = p1.x - 0, ay = p1.y - ty, bx = p2.x - 0, by = p2.y - ty;
+                float delta;
+                if (ax * vy - ay * vx > 0 && vx * by - vy * bx > 0) delta = 0; // the ray passes between the edge's end points
+                else
+                {
+                    const float mx = (p1.x + p2.x) / 2, my = (p1.y + p2.y) / 2;
+                    const float angle = std::atan2(my - ty, mx - 0.0f);
+                    delta = target - angle;
+                    delta = (delta > PI) ? delta - 2 * PI : delta;
+                    delta = std::fabs(delta);
+                }
+                keyed[e] = std::make_pair(delta, (int)e);
+            }
+            std::stable_sort(keyed.begin(), keyed.end(), [](const std::pair<float, int> &a, const std::pair<float, int> &b) { return a.first < b.first; });
+            uint16_t *row = &cxOrder_[((size_t)y * 360 + iAngle) * 2 * n];
+            for (size_t k = 0; k < n; k++)
+            {
+                row[2 * k] = (uint16_t)(keyed[k].second * 2);
+                row[2 * k + 1] = (uint16_t)(keyed[k].second * 2 + 1);
+            }
+        }
+    }
 }
 
 void Tunnel::initGrid(const std::vector<TunnelTriangle> &tris)
@@ -547,6 +658,8 @@ void Tunnel::flatten(FlatScene &out) const
     out.gridCellTris = gridCellTris_;
     out.kdNodes = kdNodes_;
     out.kdLeafTris = kdLeafTris_;
+    out.cxFrames = cxFrames_; out.cxEdges = cxEdges_; out.cxCellStatus = cxCellStatus_; out.cxCellRange = cxCellRange_; out.cxOrder = cxOrder_;
+    f.cx_width = width; f.cx_height = height;
 }
 
 } // namespace rt
