@@ -98,6 +98,10 @@ typedef struct rtb_flat_scene {
     /* grid (RTB_ACCEL_REGULAR_GRID / FLAT_GRID): reference Tunnel.h:51-67 */
     float grid_origin[3], grid_cell[3];
     int32_t grid_dims[3];
+    int32_t grid_build_resolution; /* > 1 with grid_words == NULL: the library builds the grid ON THE DEVICE from `tri`
+                                      with the reference's rules (Tunnel.cpp:346-465; 400 in the reference): REGULAR
+                                      cuts the longest extent into resolution - 1 cubic cells, FLAT every extent;
+                                      grid_origin / grid_cell / grid_dims and the three arrays below are ignored        */
     int64_t n_cellwords;  const rtb_cellword *grid_words;      /* ceil(nx*ny*nz / 32)        */
     int64_t n_cells_used; const uint32_t *grid_cell_start;     /* [n_cells_used + 1]         */
     int64_t n_cell_refs;  const uint32_t *grid_cell_tris;      /* [n_cell_refs]              */
@@ -189,6 +193,10 @@ int64_t rtb_shard_rows(const rtb_frame *frame);
 int rtb_scene_upload(rtb_ctx *ctx, const rtb_flat_scene *flat, rtb_scene **scene);
 int rtb_scene_free(rtb_ctx *ctx, rtb_scene *scene);
 int64_t rtb_scene_device_bytes(const rtb_scene *scene);
+/* Inspection: canonical structure hash of the grid resident on the device (the arrays are read back), the hash
+ * tests/golden and the host API use for grids; stats = {dims x, y, z, occupied cells, triangle references, longest
+ * cell list}.  RTB_ERR_UNSUPPORTED for other accelerators.                                                          */
+int rtb_scene_grid_hash(rtb_ctx *ctx, const rtb_scene *scene, uint64_t *hash, int64_t stats[6]);
 
 /* Replaces `int Render(GeometrySet&, PerspectiveCamera&, RenderSetting&, ProgressCallback)`
  * (reference MainWindow.cpp:251-303, the RenderProc of Scripts.h:11-12): ray generation,

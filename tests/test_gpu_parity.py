@@ -434,6 +434,54 @@ def test_three_kernel_tiers_agree(ctx, alg):
     dev.close(); s.close()
 
 
+def test_moving_camera_keeps_results_exact(ctx):
+    """A camera move reuses the previous frame's tile order for one frame (without the latency tiers); the image of
+    every frame equals what a fresh context renders for that camera."""
+    job = dict(preset=5, algorithm="sah", segments=40)
+    s, dev = _scene(ctx, job)
+    fr = rtb200.make_frame(256, 192)
+    for step in range(4):
+        cam = type(s.camera).from_buffer_copy(s.camera)
+        cam.eye[0] += 0.75 * step
+        cam.eye[2] -= 1.5 * step
+        ctx2 = rtb200.Context(0)  # no history: raster order, one kernel
+        dev2 = ctx2.upload(s.flat)
+        ref, st2 = dev2.render(cam, s.setting, fr)
+        dev2.close(); ctx2.close()
+        for _ in range(2):  # moved frame (order only), then the same view again (tiers)
+            img, st = dev.render(cam, s.setting, fr)
+            assert np.array_equal(_bits(img), _bits(ref)) and st["n_rays"] == st2["n_rays"]
+    dev.close(); s.close()
+
+
+# ---- GPU-side grid builder (SURVEY 8f rank 2) ----------------------------------------------------------
+@pytest.mark.parametrize("job", [dict(preset=5, algorithm="rgrid", segments=150), dict(preset=5, algorithm="fgrid", segments=150),
+                                 dict(preset=4, algorithm="rgrid", segments=40), dict(preset=4, algorithm="fgrid", segments=12)],
+                         ids=lambda j: f"p{j['preset']}_{j['algorithm']}_s{j['segments']}")
+def test_grid_built_on_device_is_identical(ctx, job):
+    """rtb_scene_upload without grid arrays (grid_build_resolution = 400) builds the grid on the device: dims, occupied
+    cells, references, longest list and the canonical structure hash equal the host builder's (= the reference's,
+    tests/test_host_builders.py), and the rendered frame is bit-identical."""
+    host = PresetScene(job["preset"], job["algorithm"], job["segments"])
+    rtb200.set_grid_on_device(True)
+    try:
+        lazy = PresetScene(job["preset"], job["algorithm"], job["segments"])
+    finally:
+        rtb200.set_grid_on_device(False)
+    assert lazy.flat.contents.grid_build_resolution == 400 and not lazy.flat.contents.grid_words
+    dh, dl = ctx.upload(host.flat), ctx.upload(lazy.flat)
+    hh, sh = dh.grid_hash()
+    hl, sl = dl.grid_hash()
+    st = host.stats()
+    assert hl == hh == host.struct_hash()
+    assert sl == sh and {k: st[k] for k in sl} == sl
+    fr = rtb200.make_frame(160, 120)
+    a, sa = dh.render(host.camera, host.setting, fr)
+    b, sb = dl.render(lazy.camera, lazy.setting, fr)
+    assert np.array_equal(_bits(a), _bits(b)) and sa["n_rays"] == sb["n_rays"]
+    dh.close(); dl.close(); host.close(); lazy.close()
+
+
 # ---- output stage (SURVEY 8f rank 4): saturate -> 8 bit, BMP writer -----------------------------------
 @pytest.mark.parametrize("name", ["p4_sah_s12_80x60", "p5_rgrid_s40_160x120", "p1_simple_80x60", "p2_simple_80x60"])
 def test_rgb8_output_stage_vs_reference(ctx, name):

@@ -57,6 +57,7 @@ class FlatScene(C.Structure):
         ("n_tris", C.c_int32), ("tri", C.POINTER(C.c_float)), ("tri_material", C.POINTER(C.c_int32)),
         ("accel", C.c_int32),
         ("grid_origin", C.c_float * 3), ("grid_cell", C.c_float * 3), ("grid_dims", C.c_int32 * 3),
+        ("grid_build_resolution", C.c_int32),
         ("n_cellwords", C.c_int64), ("grid_words", C.POINTER(CellWord)),
         ("n_cells_used", C.c_int64), ("grid_cell_start", C.POINTER(C.c_uint32)),
         ("n_cell_refs", C.c_int64), ("grid_cell_tris", C.POINTER(C.c_uint32)),
@@ -106,7 +107,7 @@ class Stats(C.Structure):
 
 ABI_SYMBOLS = ["rtb_init", "rtb_shutdown", "rtb_last_error", "rtb_abi_version", "rtb_shard_rows",
                "rtb_host_alloc", "rtb_host_free",
-               "rtb_scene_upload", "rtb_scene_free", "rtb_scene_device_bytes", "rtb_render",
+               "rtb_scene_upload", "rtb_scene_free", "rtb_scene_device_bytes", "rtb_scene_grid_hash", "rtb_render",
                "rtb_render_device", "rtb_unshard_device", "rtb_trace_primary", "rtb_intersect_rays", "rtb_bounce_rays"]
 
 _cuda = None
@@ -133,6 +134,8 @@ def cuda_lib():
         lib.rtb_scene_free.argtypes = [vp, vp]
         lib.rtb_scene_device_bytes.argtypes = [vp]
         lib.rtb_scene_device_bytes.restype = i64
+        lib.rtb_scene_grid_hash.argtypes = [vp, vp, C.POINTER(C.c_uint64), C.POINTER(C.c_int64)]
+        lib.rtb_scene_grid_hash.restype = C.c_int
         lib.rtb_render.argtypes = [vp, vp, C.POINTER(Camera), C.POINTER(RenderSetting), C.POINTER(Frame), vp,
                                    C.POINTER(Stats)]
         lib.rtb_render_device.argtypes = [vp, vp, C.POINTER(Camera), C.POINTER(RenderSetting), C.POINTER(Frame),
@@ -271,6 +274,11 @@ class PresetScene:
         pos, nrm = np.zeros(3, np.float32), np.zeros(3, np.float32)
         host_lib().rtbh_intersect_one(self._h, ray.ctypes.data, C.byref(hid), C.byref(ht), pos.ctypes.data, nrm.ctypes.data)
         return hid.value, ht.value, pos, nrm
+
+
+def set_grid_on_device(on):
+    """Tunnels built from now on leave RegularGrid / FlatGrid to the device builder of rtb_scene_upload."""
+    host_lib().rtbh_set_grid_on_device(1 if on else 0)
 
 
 class PerfScene(PresetScene):
@@ -414,6 +422,12 @@ class DeviceScene:
     @property
     def device_bytes(self):
         return int(self.ctx._lib.rtb_scene_device_bytes(self._h))
+
+    def grid_hash(self):
+        """(canonical structure hash, {dims, occupied cells, references, longest list}) of the grid on the device."""
+        h, st = C.c_uint64(0), (C.c_int64 * 6)()
+        self.ctx._check(self.ctx._lib.rtb_scene_grid_hash(self.ctx._h, self._h, C.byref(h), st), "rtb_scene_grid_hash")
+        return int(h.value), dict(grid_x=st[0], grid_y=st[1], grid_z=st[2], cells_nonempty=st[3], cell_entries=st[4], cell_max=st[5])
 
     def render(self, camera, setting, frame, out=None):
         """rtb_render with HOST buffers; returns (rows x width x 3 float32 | reference-order array, stats)."""

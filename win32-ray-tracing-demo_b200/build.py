@@ -33,7 +33,7 @@ def _nvcc():
 
 
 def build_cuda(force=False, verbose=False):
-    src = [os.path.join(PKG, "csrc", f) for f in ("rtb_abi.cu", "rtb_chain_sm.cuh", "rtb_chain_wide.cuh", "rtb_chain_oct.cuh", "rtb_kernels.cuh", "rtb_device.cuh")]
+    src = [os.path.join(PKG, "csrc", f) for f in ("rtb_abi.cu", "rtb_chain_sm.cuh", "rtb_chain_wide.cuh", "rtb_chain_oct.cuh", "rtb_build_grid.cuh", "rtb_kernels.cuh", "rtb_device.cuh")]
     src.append(os.path.join(ROOT, "include", "rtb.h"))
     if not force and _newer(CUDA_LIB, src):
         return CUDA_LIB

@@ -13,6 +13,7 @@
 #include "rtb_chain_sm.cuh"
 #include "rtb_chain_wide.cuh"
 #include "rtb_chain_oct.cuh"
+#include "rtb_build_grid.cuh"
 
 #ifndef RTB_SPLIT_MAX_TILES
 #define RTB_SPLIT_MAX_TILES 131072 // shards up to 4.2 Mpixel walk their latency-critical tiles with 4 warps each
@@ -88,6 +89,7 @@ struct rtb_ctx
     unsigned int *d_cost = nullptr, *d_order = nullptr, *d_hist = nullptr, *d_cursor = nullptr, *d_heavy = nullptr;
     size_t tile_capacity = 0;
     bool order_valid = false;
+    bool tiers_ok = true; // false: this frame uses the order but not the latency tiers (camera moved)
     OrderKey order_key = {};
     std::string error;
 };
@@ -100,6 +102,7 @@ struct rtb_scene
     bool has_refractive = false;
     bool has_tunnel = false;
     cudaEvent_t last_use = nullptr; // recorded after every launch that reads the scene
+    int64_t grid_cells_used = 0, grid_refs = 0, grid_words = 0;
     bool long_lists = false; // regular grid with >= 16 triangle references per occupied cell (tier policy, wideCount)
     unsigned long long signature = 0; // sampled content hash, identifies "the same scene again" for the tile-order cache
 };
@@ -126,6 +129,7 @@ static unsigned long long sceneSignature(const rtb_flat_scene *f)
     h = fnv(h, f->prims, sizeof(rtb_prim) * (size_t)f->n_prims);
     h = fnv(h, f->materials, sizeof(rtb_material) * (size_t)f->n_materials);
     h = fnv(h, &f->accel, sizeof(f->accel));
+    h = fnv(h, &f->grid_build_resolution, sizeof(f->grid_build_resolution));
     h = fnvSampled(h, f->loose_tri, f->loose_tri ? (size_t)f->n_loose * 12 : 0);
     h = fnvSampled(h, f->tri, f->tri ? (size_t)f->n_tris * 12 : 0);
     if (f->accel == RTB_ACCEL_REGULAR_GRID || f->accel == RTB_ACCEL_FLAT_GRID)
@@ -294,6 +298,134 @@ static int kdDepth(const rtb_kdnode *nodes, int n, int node, int depth, int &max
     return kdDepth(nodes, n, right, depth + 1, maxDepth, visited);
 }
 
+// ---- grid built on the device (rtb_build_grid.cuh) ------------------------------------------------------------
+template <class T> static int deviceArray(rtb_ctx *ctx, rtb_scene *s, size_t n, T **dev, bool keep)
+{
+    void *p = nullptr;
+    CUDA_TRY(ctx, cudaMallocAsync(&p, (n ? n : 1) * sizeof(T), ctx->stream));
+    if (keep) { s->allocs.push_back(p); s->bytes += (int64_t)(n * sizeof(T)); }
+    *dev = (T *)p;
+    return RTB_OK;
+}
+
+static int buildGridOnDevice(rtb_ctx *ctx, rtb_scene *s, const rtb_flat_scene *f)
+{
+    DScene &d = s->d;
+    const int n = f->n_tris, R = f->grid_build_resolution;
+    cudaStream_t st = ctx->stream;
+    std::vector<void *> temps;
+    auto temp = [&](size_t bytes, void **p) { cudaError_t e = cudaMallocAsync(p, bytes ? bytes : 1, st); if (e == cudaSuccess) temps.push_back(*p); return e; };
+    auto cleanup = [&]() { for (void *p : temps) cudaFreeAsync(p, st); };
+#define GRID_TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return fail(ctx, RTB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
+    float *d_raw = nullptr, *d_bounds = nullptr;
+    GRID_TRY(temp((size_t)n * 12 * sizeof(float), (void **)&d_raw));
+    GRID_TRY(cudaMemcpyAsync(d_raw, f->tri, (size_t)n * 12 * sizeof(float), cudaMemcpyHostToDevice, st));
+    GRID_TRY(temp(6 * sizeof(float), (void **)&d_bounds));
+    const float init[6] = {FLT_MAX, FLT_MAX, FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
+    GRID_TRY(cudaMemcpyAsync(d_bounds, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    k_grid_bounds<<<148, 256, 0, st>>>(d_raw, n, d_bounds);
+    float b[6];
+    GRID_TRY(cudaMemcpyAsync(b, d_bounds, sizeof(b), cudaMemcpyDeviceToHost, st));
+    GRID_TRY(cudaStreamSynchronize(st));
+
+    // sizing with the reference's float expressions (Tunnel.cpp:372-404)
+    GridSizing G;
+    const float width = b[3] - b[0], height = b[4] - b[1], depth = b[5] - b[2];
+    if (f->accel == RTB_ACCEL_REGULAR_GRID)
+    {
+        const float maxLength = std::max(std::max(width, height), depth);
+        const float size = maxLength / (R - 1);
+        for (int a = 0; a < 3; a++) { G.cell[a] = size; G.origin[a] = b[a] - size / 2; }
+        G.dims[0] = (int)(width / size + 1.5f); G.dims[1] = (int)(height / size + 1.5f); G.dims[2] = (int)(depth / size + 1.5f);
+    }
+    else
+    {
+        G.cell[0] = width / (R - 1); G.cell[1] = height / (R - 1); G.cell[2] = depth / (R - 1);
+        for (int a = 0; a < 3; a++) { G.origin[a] = b[a] - G.cell[a] / 2; G.dims[a] = R; }
+    }
+    const int64_t cells = (int64_t)G.dims[0] * G.dims[1] * G.dims[2];
+    if (G.dims[0] <= 0 || G.dims[1] <= 0 || G.dims[2] <= 0 || cells > 0x7fffffffLL || !(G.cell[0] > 0) || !(G.cell[1] > 0) || !(G.cell[2] > 0))
+    {
+        cleanup();
+        return fail(ctx, RTB_ERR_INVALID, "rtb_scene_upload: degenerate tunnel bounds, cannot size the grid");
+    }
+    const int64_t nWords = (cells + 31) / 32;
+
+    // count -> scan -> emit -> sort
+    unsigned int *d_count = nullptr, *d_offset = nullptr;
+    GRID_TRY(temp((size_t)(n + 1) * sizeof(unsigned int), (void **)&d_count));
+    GRID_TRY(temp((size_t)(n + 1) * sizeof(unsigned int), (void **)&d_offset));
+    GRID_TRY(cudaMemsetAsync(d_count, 0, (size_t)(n + 1) * sizeof(unsigned int), st));
+    const int tb = 256, nb = (n + tb - 1) / tb;
+    k_grid_count<<<nb, tb, 0, st>>>(d_raw, n, G, d_count);
+    void *d_tmp = nullptr;
+    size_t tmpBytes = 0, need = 0;
+    GRID_TRY(cub::DeviceScan::ExclusiveSum(nullptr, need, d_count, d_offset, n + 1, st));
+    tmpBytes = need;
+    GRID_TRY(temp(tmpBytes, &d_tmp));
+    GRID_TRY(cub::DeviceScan::ExclusiveSum(d_tmp, tmpBytes, d_count, d_offset, n + 1, st));
+    unsigned int total = 0;
+    GRID_TRY(cudaMemcpyAsync(&total, d_offset + n, sizeof(total), cudaMemcpyDeviceToHost, st));
+    GRID_TRY(cudaStreamSynchronize(st));
+    if (total == 0 || total > 0x7fffffffu) { cleanup(); return fail(ctx, RTB_ERR_INVALID, "rtb_scene_upload: grid reference count out of range"); }
+    unsigned long long *d_keys = nullptr, *d_sorted = nullptr;
+    GRID_TRY(temp((size_t)total * sizeof(unsigned long long), (void **)&d_keys));
+    GRID_TRY(temp((size_t)total * sizeof(unsigned long long), (void **)&d_sorted));
+    k_grid_emit<<<nb, tb, 0, st>>>(d_raw, n, G, d_offset, d_keys);
+    int cellBits = 1;
+    while ((1ll << cellBits) < cells) cellBits++;
+    void *d_tmp2 = nullptr;
+    GRID_TRY(cub::DeviceRadixSort::SortKeys(nullptr, need, d_keys, d_sorted, (int)total, 0, 32 + cellBits, st));
+    GRID_TRY(temp(need, &d_tmp2));
+    GRID_TRY(cub::DeviceRadixSort::SortKeys(d_tmp2, need, d_keys, d_sorted, (int)total, 0, 32 + cellBits, st));
+
+    // directory
+    uint2 *d_words = nullptr;
+    uint32_t *d_cell_tris = nullptr, *d_cell_start = nullptr;
+    int rc;
+    if ((rc = deviceArray(ctx, s, (size_t)nWords, &d_words, true)) != RTB_OK) { cleanup(); return rc; }
+    if ((rc = deviceArray(ctx, s, (size_t)total, &d_cell_tris, true)) != RTB_OK) { cleanup(); return rc; }
+    GRID_TRY(cudaMemsetAsync(d_words, 0, (size_t)nWords * sizeof(uint2), st));
+    unsigned int *d_head = nullptr, *d_rank = nullptr;
+    GRID_TRY(temp((size_t)(total + 1) * sizeof(unsigned int), (void **)&d_head));
+    GRID_TRY(temp((size_t)(total + 1) * sizeof(unsigned int), (void **)&d_rank));
+    GRID_TRY(cudaMemsetAsync(d_head + total, 0, sizeof(unsigned int), st));
+    const unsigned int eb = (total + tb - 1) / tb;
+    k_grid_heads<<<eb, tb, 0, st>>>(d_sorted, total, d_cell_tris, d_head, d_words);
+    void *d_tmp3 = nullptr;
+    GRID_TRY(cub::DeviceScan::ExclusiveSum(nullptr, need, d_head, d_rank, (int)total + 1, st));
+    GRID_TRY(temp(need, &d_tmp3));
+    GRID_TRY(cub::DeviceScan::ExclusiveSum(d_tmp3, need, d_head, d_rank, (int)total + 1, st));
+    unsigned int nRuns = 0;
+    GRID_TRY(cudaMemcpyAsync(&nRuns, d_rank + total, sizeof(nRuns), cudaMemcpyDeviceToHost, st));
+    GRID_TRY(cudaStreamSynchronize(st));
+    if ((rc = deviceArray(ctx, s, (size_t)nRuns + 1, &d_cell_start, true)) != RTB_OK) { cleanup(); return rc; }
+    k_grid_starts<<<eb, tb, 0, st>>>(d_head, d_rank, total, d_cell_start, nRuns);
+    unsigned int *d_pop = nullptr, *d_wrank = nullptr;
+    GRID_TRY(temp((size_t)nWords * sizeof(unsigned int), (void **)&d_pop));
+    GRID_TRY(temp((size_t)nWords * sizeof(unsigned int), (void **)&d_wrank));
+    const unsigned int wb = (unsigned int)((nWords + tb - 1) / tb);
+    k_grid_word_pop<<<wb, tb, 0, st>>>(d_words, nWords, d_pop);
+    void *d_tmp4 = nullptr;
+    GRID_TRY(cub::DeviceScan::ExclusiveSum(nullptr, need, d_pop, d_wrank, (int)nWords, st));
+    GRID_TRY(temp(need, &d_tmp4));
+    GRID_TRY(cub::DeviceScan::ExclusiveSum(d_tmp4, need, d_pop, d_wrank, (int)nWords, st));
+    k_grid_word_rank<<<wb, tb, 0, st>>>(d_words, nWords, d_wrank);
+    GRID_TRY(cudaGetLastError());
+    cleanup();
+    GRID_TRY(cudaStreamSynchronize(st));
+#undef GRID_TRY
+
+    d.g_origin = {G.origin[0], G.origin[1], G.origin[2]};
+    d.g_cell = {G.cell[0], G.cell[1], G.cell[2]};
+    d.nx = G.dims[0]; d.ny = G.dims[1]; d.nz = G.dims[2];
+    d.g_extent = {d.g_cell.x * d.nx, d.g_cell.y * d.ny, d.g_cell.z * d.nz};
+    d.g_far = {d.g_origin.x + d.g_extent.x, d.g_origin.y + d.g_extent.y, d.g_origin.z + d.g_extent.z};
+    d.g_words = d_words; d.g_start = d_cell_start; d.g_tris = d_cell_tris;
+    s->grid_cells_used = nRuns; s->grid_refs = total; s->grid_words = nWords;
+    return RTB_OK;
+}
+
 extern "C" int rtb_scene_upload(rtb_ctx *ctx, const rtb_flat_scene *f, rtb_scene **out)
 {
     if (!ctx || !f || !out) return fail(ctx, RTB_ERR_INVALID, "rtb_scene_upload: null argument");
@@ -354,7 +486,12 @@ extern "C" int rtb_scene_upload(rtb_ctx *ctx, const rtb_flat_scene *f, rtb_scene
         d.n_tris = f->n_tris;
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
 
-        if (f->accel == RTB_ACCEL_REGULAR_GRID || f->accel == RTB_ACCEL_FLAT_GRID)
+        if ((f->accel == RTB_ACCEL_REGULAR_GRID || f->accel == RTB_ACCEL_FLAT_GRID) && !f->grid_words && f->grid_build_resolution > 1)
+        { // no grid arrays, a resolution: build it here, on the device
+            if (f->n_tris <= 0) return bail(fail(ctx, RTB_ERR_INVALID, "rtb_scene_upload: a grid needs triangles"));
+            if ((rc = buildGridOnDevice(ctx, s, f)) != RTB_OK) return bail(rc);
+        }
+        else if (f->accel == RTB_ACCEL_REGULAR_GRID || f->accel == RTB_ACCEL_FLAT_GRID)
         {
             const int64_t cells = (int64_t)f->grid_dims[0] * f->grid_dims[1] * f->grid_dims[2];
             if (f->grid_dims[0] <= 0 || f->grid_dims[1] <= 0 || f->grid_dims[2] <= 0 || cells > 0x7fffffffLL ||
@@ -375,6 +512,7 @@ extern "C" int rtb_scene_upload(rtb_ctx *ctx, const rtb_flat_scene *f, rtb_scene
             d.g_words = words;
             if ((rc = uploadArray(ctx, s, f->grid_cell_start, (size_t)f->n_cells_used + 1, &d.g_start)) != RTB_OK) return bail(rc);
             if ((rc = uploadArray(ctx, s, f->grid_cell_tris, (size_t)f->n_cell_refs, &d.g_tris)) != RTB_OK) return bail(rc);
+            s->grid_cells_used = f->n_cells_used; s->grid_refs = f->n_cell_refs; s->grid_words = f->n_cellwords;
         }
         else if (f->accel == RTB_ACCEL_KD_MEDIAN || f->accel == RTB_ACCEL_KD_SAH)
         {
@@ -430,7 +568,7 @@ extern "C" int rtb_scene_upload(rtb_ctx *ctx, const rtb_flat_scene *f, rtb_scene
     }
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     s->signature = sceneSignature(f);
-    s->long_lists = s->has_tunnel && f->accel == RTB_ACCEL_REGULAR_GRID && f->n_cells_used > 0 && f->n_cell_refs >= 16 * f->n_cells_used;
+    s->long_lists = s->has_tunnel && f->accel == RTB_ACCEL_REGULAR_GRID && s->grid_cells_used > 0 && s->grid_refs >= 16 * s->grid_cells_used;
     *out = s;
     return RTB_OK;
 }
@@ -452,6 +590,48 @@ extern "C" int rtb_scene_free(rtb_ctx *ctx, rtb_scene *s)
 }
 
 extern "C" int64_t rtb_scene_device_bytes(const rtb_scene *s) { return s ? s->bytes : 0; }
+
+extern "C" int rtb_scene_grid_hash(rtb_ctx *ctx, const rtb_scene *s, uint64_t *hash, int64_t stats[6])
+{
+    if (!ctx || !s || !hash) return fail(ctx, RTB_ERR_INVALID, "rtb_scene_grid_hash: null argument");
+    const DScene &d = s->d;
+    if (!s->has_tunnel || (d.accel != RTB_ACCEL_REGULAR_GRID && d.accel != RTB_ACCEL_FLAT_GRID))
+        return fail(ctx, RTB_ERR_UNSUPPORTED, "rtb_scene_grid_hash: the scene has no grid");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    std::vector<uint2> words((size_t)s->grid_words);
+    std::vector<uint32_t> start((size_t)s->grid_cells_used + 1), tris((size_t)s->grid_refs);
+    CUDA_TRY(ctx, cudaMemcpyAsync(words.data(), d.g_words, words.size() * sizeof(uint2), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(start.data(), d.g_start, start.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(tris.data(), d.g_tris, tris.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    auto mix = [](uint64_t &h, uint32_t v) { h = (h ^ v) * 0x100000001b3ull; };
+    auto bits = [](float v) { uint32_t u; memcpy(&u, &v, 4); return u; };
+    uint64_t x = 0xcbf29ce484222325ull;
+    mix(x, 0x47524944u);
+    mix(x, (uint32_t)d.nx); mix(x, (uint32_t)d.ny); mix(x, (uint32_t)d.nz);
+    mix(x, bits(d.g_origin.x)); mix(x, bits(d.g_origin.y)); mix(x, bits(d.g_origin.z));
+    mix(x, bits(d.g_cell.x)); mix(x, bits(d.g_cell.y)); mix(x, bits(d.g_cell.z));
+    int64_t longest = 0;
+    for (size_t w = 0; w < words.size(); w++)
+    {
+        uint32_t b = words[w].x, r = words[w].y;
+        while (b)
+        {
+            const int bit = __builtin_ctz(b);
+            b &= b - 1;
+            if ((size_t)r + 1 >= start.size()) return fail(ctx, RTB_ERR_INVALID, "rtb_scene_grid_hash: inconsistent cell directory");
+            const uint32_t first = start[r], last = start[r + 1];
+            mix(x, (uint32_t)(w * 32 + bit));
+            mix(x, last - first);
+            for (uint32_t e = first; e < last; e++) mix(x, tris[e]);
+            if ((int64_t)(last - first) > longest) longest = last - first;
+            r++;
+        }
+    }
+    *hash = x;
+    if (stats) { stats[0] = d.nx; stats[1] = d.ny; stats[2] = d.nz; stats[3] = s->grid_cells_used; stats[4] = s->grid_refs; stats[5] = longest; }
+    return RTB_OK;
+}
 
 // ---- render -----------------------------------------------------------------------------------
 static int makeFrame(rtb_ctx *ctx, const rtb_scene *scene, const rtb_camera *cam, const rtb_render_setting *setting,
@@ -507,7 +687,7 @@ static int launchRender(rtb_ctx *ctx, const rtb_scene *scene, FrameParams &F, fl
     F.record_cost = 1;
     if (F.setting.enable_monte_carlo) k_montecarlo<Probe><<<grid, RTB_CTA_THREADS, 0, stream>>>(scene->d, F, out, counters);
     else if (scene->has_refractive) k_whitted_tree<Probe><<<grid, RTB_CTA_THREADS, 0, stream>>>(scene->d, F, out, counters);
-    else if (resumable && scene->has_tunnel && (kd_accel || grid_accel) && F.order)
+    else if (resumable && scene->has_tunnel && (kd_accel || grid_accel) && F.order && ctx->tiers_ok)
     { // A tile order is known.  Three kernels share the frame, all launched at once:
       //   order[0 .. n_wide)         the very heaviest tiles: one warp per pixel        (side stream, high priority)
       //   order[n_wide .. n_heavy)   latency-critical tiles: resumable per-lane walk    (side stream, high priority)
@@ -609,16 +789,24 @@ static int prepareTileOrder(rtb_ctx *ctx, const rtb_scene *scene, FrameParams &F
         CUDA_TRY(ctx, cudaMemset(ctx->d_heavy, 0, sizeof(unsigned int)));
     }
     // The order (and the per-tile costs behind it) belongs to one view of one scene: frame geometry, scene,
-    // camera and depth setting.  Anything else starts over with a raster-order frame that measures every tile.
+    // camera and depth setting.  A camera move keeps the order for one frame without the tiers (below); anything
+    // else starts over with a raster-order frame that measures every tile.
     OrderKey key;
     memset(&key, 0, sizeof(key));
     key.v[0] = F.width; key.v[1] = F.height; key.v[2] = F.rank; key.v[3] = F.world; key.v[4] = F.row_block; key.v[5] = F.layout;
     key.v[6] = F.setting.enable_monte_carlo; key.v[7] = F.n_tiles; key.v[8] = F.setting.max_depth; key.v[9] = F.samples;
     key.scene_signature = scene->signature;
     key.cam = F.cam;
+    ctx->tiers_ok = true;
     if (memcmp(&key, &ctx->order_key, sizeof(key)) != 0)
     {
-        ctx->order_valid = false;
+        OrderKey sameView = key;
+        sameView.cam = ctx->order_key.cam;
+        if (memcmp(&sameView, &ctx->order_key, sizeof(key)) == 0)
+            ctx->tiers_ok = false; // only the camera moved: the last order is still a good guess (temporal coherence), but
+                                   // every tile is rendered and re-measured by the throughput kernel this frame
+        else
+            ctx->order_valid = false;
         memcpy(&ctx->order_key, &key, sizeof(key));
     }
     F.order = ctx->order_valid ? ctx->d_order : nullptr;

@@ -301,6 +301,11 @@ public:
     // KdTreeSAH builds with PerformanceTest's builder (KdTreeAcc.cpp: event-sweep SAH + automatic termination)
     // instead of RayTracingOpt's 99-candidate one; set by TunnelGenerator::performanceTestVariant
     bool performanceTestBuilders = false;
+    // RegularGrid / FlatGrid: leave the grid to the device builder (rtb_scene_upload, include/rtb.h:
+    // grid_build_resolution) instead of building it here; init() then only records the request.  The default for
+    // newly generated tunnels is Tunnel::gridOnDeviceDefault (false: host build, needed for host-side statistics).
+    bool gridOnDevice = false;
+    static bool gridOnDeviceDefault;
 
     // Reference Tunnel.cpp:116-133: builds the accelerator selected by `algorithm`.
     void init();

@@ -427,6 +427,8 @@ rtbh_scene *rtbh_perf_scene_create(float radius, float angle, int arch_seg, int 
     h->rs = h->setting.flatten();
     return h;
 }
+// tunnels generated from now on leave their grid to the device builder (Tunnel::gridOnDevice)
+void rtbh_set_grid_on_device(int on) { Tunnel::gridOnDeviceDefault = on != 0; }
 void rtbh_free(rtbh_scene *h) { delete h; }
 const rtb_flat_scene *rtbh_flat(const rtbh_scene *h) { return &h->flat.view; }
 const rtb_camera *rtbh_camera(const rtbh_scene *h) { return &h->cam; }

@@ -86,6 +86,7 @@ bool TunnelGenerator::create(float rectWidth, float rectHeight, float archHeight
                              Ptr<Material> wallMaterial, Tunnel::Algorithm algorithm)
 {
     Tunnel *tunnel = new Tunnel();
+    tunnel->gridOnDevice = Tunnel::gridOnDeviceDefault;
     tunnel->height = rectHeight + archHeight;
     tunnel->width = rectWidth;
     tunnel->algorithm = algorithm;
@@ -174,6 +175,8 @@ bool TunnelGenerator::create(float rectWidth, float rectHeight, float archHeight
 }
 
 // ---- Tunnel ------------------------------------------------------------------------------------
+bool Tunnel::gridOnDeviceDefault = false;
+
 size_t Tunnel::triangleCount() const
 {
     size_t n = 0;
@@ -222,7 +225,8 @@ void Tunnel::init()
     gridWords_.clear(); gridCellStart_.clear(); gridCellTris_.clear(); kdNodes_.clear(); kdLeafTris_.clear();
     cxFrames_.clear(); cxEdges_.clear(); cxCellStatus_.clear(); cxCellRange_.clear(); cxOrder_.clear();
     stats = BuildStats();
-    if (algorithm == RegularGrid || algorithm == FlatGrid) initGrid(tris);
+    if ((algorithm == RegularGrid || algorithm == FlatGrid) && gridOnDevice) { /* built by rtb_scene_upload */ }
+    else if (algorithm == RegularGrid || algorithm == FlatGrid) initGrid(tris);
     else if (algorithm == KdTreeStandard || algorithm == KdTreeSAH) initKdTree(tris);
     else if (algorithm == Convex || algorithm == ConvexSimple) initConvex();
     built_ = true;
@@ -660,6 +664,7 @@ void Tunnel::flatten(FlatScene &out) const
     out.kdLeafTris = kdLeafTris_;
     out.cxFrames = cxFrames_; out.cxEdges = cxEdges_; out.cxCellStatus = cxCellStatus_; out.cxCellRange = cxCellRange_; out.cxOrder = cxOrder_;
     f.cx_width = width; f.cx_height = height;
+    f.grid_build_resolution = ((algorithm == RegularGrid || algorithm == FlatGrid) && gridOnDevice) ? gridResolution : 0;
 }
 
 } // namespace rt
