@@ -116,8 +116,14 @@ typedef struct rtb_flat_scene {
                                                        host cosf / sinf / atan2f, as the reference evaluates them)        */
     int32_t n_cx_edges;   const float *cx_edges;   /* [n_cx_edges][3]: A, B, C of A*x + B*y + C > 0 (ConvexAcc.cpp:183-214) */
     float cx_width, cx_height;                      /* bounding rectangle of the cross section (Tunnel.h:19-20)              */
-    const uint8_t *cx_cell_status;                  /* [100*100] 0 Hit, 1 Partial, 2 Miss (ConvexAcc.cpp:216-247)            */
-    const int16_t *cx_cell_range;                   /* [100*100][2] first / last edge to test in a Partial cell              */
+    int32_t cx_table_size;                          /* T: cells per side of the lookup over the cross section's bounding
+                                                       rectangle -- 100 in PerformanceTest (ConvexAcc.h:12), 400 in
+                                                       RayTracingOpt (Tunnel.cpp:255-284)                                     */
+    int32_t cx_round_bins;                          /* direction bin of the order table: 1 = (int)(deg + 0.5) % 360
+                                                       (ConvexAcc.cpp:372), 0 = (int)deg (Tunnel.cpp:1042)                    */
+    const uint8_t *cx_cell_status;                  /* [T*T] 0 Hit, 1 Partial, 2 Miss (ConvexAcc.cpp:216-247)                */
+    const int16_t *cx_cell_range;                   /* [T*T][2] first / last edge to test in a Partial cell (RayTracingOpt
+                                                       tests them all: 0 .. n_cx_edges - 1)                                   */
     const uint16_t *cx_order;                       /* RTB_ACCEL_CONVEX: [100][360][2*n_cx_edges] triangle order per
                                                        (height, angle) bin (ConvexAcc.cpp:249-270)                           */
 } rtb_flat_scene;

@@ -190,6 +190,38 @@ static int jobRender(GeometrySet &scene, PerspectiveCamera &camera, RenderSettin
             }
             job->struct_hash = h;
         }
+        else if (tunnel->algorithm == Tunnel::Convex || tunnel->algorithm == Tunnel::ConvexSimple)
+        { // convex tables, convention of oracle/rt_oracle.cpp: hashConvex (a Partial cell tests every edge here)
+            uint64_t h = H0;
+            hmix(h, 0x43565800u);
+            hmix(h, (uint32_t)tunnel->path.size()); hmix(h, (uint32_t)tunnel->crossSection.vertices.size());
+            hmix(h, fbits(tunnel->width)); hmix(h, fbits(tunnel->height));
+            for (size_t i = 0; i < tunnel->path.size(); i++)
+            {
+                Point p = tunnel->path[i];
+                Vector n = tunnel->nvs[i];
+                float theta = PI - atan2(n.x, n.z); // Tunnel.cpp:37
+                const float v[8] = {p.x, p.y, p.z, n.x, n.y, n.z, cos(theta), sin(theta)};
+                for (int q = 0; q < 8; q++) hmix(h, fbits(v[q]));
+            }
+            const int nEdges = (int)tunnel->edgeParams.size();
+            for (int e = 0; e < nEdges; e++) { hmix(h, fbits(tunnel->edgeParams[e].A)); hmix(h, fbits(tunnel->edgeParams[e].B)); hmix(h, fbits(tunnel->edgeParams[e].C)); }
+            for (int i = 0; i < 400; i++)
+                for (int j = 0; j < 400; j++)
+                    hmix(h, tunnel->intersectionTable[i][j] == Tunnel::Hit ? 0u : (tunnel->intersectionTable[i][j] == Tunnel::Partial ? 1u : 2u));
+            for (int i = 0; i < 400; i++)
+                for (int j = 0; j < 400; j++)
+                {
+                    const bool partial = tunnel->intersectionTable[i][j] == Tunnel::Partial;
+                    hmix(h, (uint32_t)(uint16_t)(short)(partial ? 0 : -1));
+                    hmix(h, (uint32_t)(uint16_t)(short)(partial ? nEdges - 1 : -1));
+                }
+            if (tunnel->algorithm == Tunnel::Convex)
+                for (int y = 0; y < 100; y++)
+                    for (int a = 0; a < 360; a++)
+                        for (size_t k = 0; k < tunnel->intersectionTableYAxis[y][a].size(); k++) hmix(h, (uint32_t)tunnel->intersectionTableYAxis[y][a][k]);
+            job->struct_hash = h;
+        }
         else if (tunnel->root)
         {
             uint64_t h = H0;
@@ -274,7 +306,7 @@ extern "C" int ref_run(oracle_job *job)
     static std::mutex once;
     std::lock_guard<std::mutex> guard(once);
     if (!job || job->preset < 1 || job->preset > 5) return -1;
-    if (job->algorithm < 0 || job->algorithm > 4) return -2; // convex variants are out of scope
+    if (job->algorithm < 0 || job->algorithm > 6) return -2; // 5, 6: Tunnel::fastIntersect (Convex / ConvexSimple)
     if (job->width <= 0 || job->height <= 0) return -3;
     g_job = job;
     g_stl_path = job->stl_path ? job->stl_path : "ball.stl";

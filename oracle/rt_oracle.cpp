@@ -332,6 +332,8 @@ struct TunnelO
     std::vector<unsigned char> cellStatus; // [100][100]: 0 Hit, 1 Partial, 2 Miss
     std::vector<short> cellRange;          // [100][100][2]
     std::vector<unsigned short> yAxis;     // [100][360][2 * edges]
+    int cxTable = 100;                     // cells per side of the lookup table
+    bool cxRoundBins = true;               // direction bin: (int)(deg + 0.5) % 360 (PerformanceTest) or (int)deg (RayTracingOpt)
 };
 struct RayCtx { bool inTunnel; int segment; }; // RayContext.h:5-13
 
@@ -820,7 +822,7 @@ enum { PRIM_PLANE = 0, PRIM_SPHERE = 1, PRIM_TRIANGLE = 2, PRIM_TUNNEL = 3 };
 // wall, where it tests that segment's triangles -- all of them in list order (ConvexSimple) or in the
 // order of a (height, angle) table (Convex) -- and returns the FIRST accepted one, not the nearest.
 // ------------------------------------------------------------------------------------------
-enum { CONVEX_TABLE = 100 };
+// table resolution: 100 in PerformanceTest/ConvexAcc.h:12, 400 in RayTracingOpt (Tunnel.cpp:255-284)
 inline int f2i(float f) { return (f >= -2147483648.0f && f < 2147483648.0f) ? (int)f : (int)0x80000000; } // cvttss2si
 
 inline bool convexCorner(const TunnelO &T, float x, float y)
@@ -831,8 +833,20 @@ inline bool convexCorner(const TunnelO &T, float x, float y)
 }
 
 void initConvex(TunnelO &T)
-{ // ConvexAcc.cpp:181-271
+{ // PerformanceTest/ConvexAcc.cpp:181-271; RayTracingOpt/Tunnel.cpp:135-344 when !T.ptBuilders
     const size_t n = T.cs.size();
+    T.cxTable = T.ptBuilders ? 100 : 400;
+    T.cxRoundBins = T.ptBuilders;
+    if (!T.ptBuilders)
+    { // RayTracingOpt derives the ring normals here: the direction of the segment that starts at the vertex (Tunnel.cpp:139-150)
+        T.nvs.clear();
+        for (size_t i = 0; i < T.path.size(); i++)
+        {
+            if (i + 1 < T.path.size()) T.nvs.push_back(normalize(T.path[i + 1] - T.path[i]));
+            else T.nvs.push_back(normalize((T.path[i] + (T.path[i] - T.path[i - 1])) - T.path[i]));
+        }
+    }
+    const int CONVEX_TABLE = T.cxTable;
     T.edge.clear();
     for (size_t i = 0; i < n; i++)
     {
@@ -873,6 +887,7 @@ void initConvex(TunnelO &T)
                     if ((short)e < mn) mn = (short)e;
                 }
             }
+            if (status == 1 && !T.ptBuilders) { mn = 0; mx = (short)(n - 1); } // RayTracingOpt tests every edge (inPolygon, Tunnel.cpp:102-114)
             T.cellStatus[i * CONVEX_TABLE + j] = status;
             T.cellRange[(i * CONVEX_TABLE + j) * 2] = mn;
             T.cellRange[(i * CONVEX_TABLE + j) * 2 + 1] = mx;
@@ -920,6 +935,7 @@ inline bool convexAtOrigin(const TunnelO &T, V3 o, V3 d, float &distance)
     if (o.z * d.z >= 0) return false;
     distance = (0 - o.z) / d.z;
     const V3 p = o + d * distance;
+    const int CONVEX_TABLE = T.cxTable;
     const float cellWidth = T.width / (CONVEX_TABLE - 1.0f), cellHeight = T.height / (CONVEX_TABLE - 1.0f);
     int i = f2i((p.x + T.width / 2) / cellWidth + 0.5f), j = f2i(p.y / cellHeight + 0.5f);
     i = std::max(i, 0); j = std::max(j, 0);
@@ -1001,7 +1017,7 @@ bool convexIntersect(const TunnelO &T, const RayO &ray, RayCtx &ctx, int &triOut
                 index = std::max(0, index); index = std::min(99, index);
                 float fAngle = atan2f(nd.y, nd.x);
                 fAngle = (fAngle < 0) ? fAngle + PI_F * 2 : fAngle;
-                int iAngle = f2i(fAngle / PI_F * 180.0f + 0.5f) % 360;
+                int iAngle = T.cxRoundBins ? f2i(fAngle / PI_F * 180.0f + 0.5f) % 360 : f2i(fAngle / PI_F * 180.0f);
                 iAngle = std::max(0, iAngle); iAngle = std::min(359, iAngle);
                 const unsigned short *row = &T.yAxis[((size_t)index * 360 + iAngle) * T.trisPerSegment];
                 for (int j = 0; j < T.trisPerSegment; j++)
@@ -1229,9 +1245,9 @@ inline Fresnel refraction(const RayO &r, V3 p, V3 n, V3 nl, float nt)
     return f;
 }
 
-V3 trace(const Scene &s, RayO r, int depth, Probe *pr)
+V3 trace(const Scene &s, RayO r, int depth, Probe *pr, RayCtx ctx = RayCtx{false, -1})
 {
-    const Hit res = sceneIntersect(s, r, pr);
+    const Hit res = sceneIntersect(s, r, pr, &ctx);
     if (!res.hit) return v3(0, 0, 0);
     const Mat &m = s.mats[res.mat];
     const V3 p = res.pos, n = res.n;
@@ -1244,7 +1260,7 @@ V3 trace(const Scene &s, RayO r, int depth, Probe *pr)
     if (m.reflectiveness > 0)
     {
         RayO nr = {p, r.d - nl * 2 * dot(nl, r.d)};
-        reflective = trace(s, nr, depth, pr);
+        reflective = trace(s, nr, depth, pr, ctx); // newRay.context = r.context, MainWindow.cpp:105
     }
     if (m.refractiveness > 0)
     {
@@ -1375,6 +1391,26 @@ void hashKd(const TunnelO &T, int node, uint64_t &h)
     hashKd(T, n.right, h);
 }
 
+// convex accelerator tables: frames (path vertex, ring normal, cos / sin of the ring rotation), edges, cell table, order table
+uint64_t hashConvex(const TunnelO &T)
+{
+    uint64_t h = H0;
+    hmix(h, 0x43565800u);
+    hmix(h, (uint32_t)T.path.size()); hmix(h, (uint32_t)T.cs.size());
+    hmix(h, fbits(T.width)); hmix(h, fbits(T.height));
+    for (size_t i = 0; i < T.path.size(); i++)
+    {
+        const float theta = PI_F - atan2f(T.nvs[i].x, T.nvs[i].z);
+        const float v[8] = {T.path[i].x, T.path[i].y, T.path[i].z, T.nvs[i].x, T.nvs[i].y, T.nvs[i].z, cosf(theta), sinf(theta)};
+        for (int q = 0; q < 8; q++) hmix(h, fbits(v[q]));
+    }
+    for (size_t e = 0; e < T.edge.size(); e++) { hmix(h, fbits(T.edge[e].x)); hmix(h, fbits(T.edge[e].y)); hmix(h, fbits(T.edge[e].z)); }
+    for (size_t i = 0; i < T.cellStatus.size(); i++) hmix(h, T.cellStatus[i]);
+    for (size_t i = 0; i < T.cellRange.size(); i++) hmix(h, (uint32_t)(uint16_t)T.cellRange[i]);
+    for (size_t i = 0; i < T.yAxis.size(); i++) hmix(h, T.yAxis[i]);
+    return h;
+}
+
 } // namespace
 
 // ------------------------------------------------------------------------------------------
@@ -1426,25 +1462,7 @@ extern "C" int rt_oracle_bounce(oracle_bounce_job *job)
         }
         job->struct_hash = h;
     }
-    if (job->algorithm == 5 || job->algorithm == 6)
-    { // the convex accelerator's tables
-        const TunnelO &T = s.tunnel;
-        uint64_t h = H0;
-        hmix(h, 0x43565800u);
-        hmix(h, (uint32_t)T.path.size()); hmix(h, (uint32_t)T.cs.size());
-        hmix(h, fbits(T.width)); hmix(h, fbits(T.height));
-        for (size_t i = 0; i < T.path.size(); i++)
-        {
-            const float theta = PI_F - atan2f(T.nvs[i].x, T.nvs[i].z);
-            const float v[8] = {T.path[i].x, T.path[i].y, T.path[i].z, T.nvs[i].x, T.nvs[i].y, T.nvs[i].z, cosf(theta), sinf(theta)};
-            for (int q = 0; q < 8; q++) hmix(h, fbits(v[q]));
-        }
-        for (size_t e = 0; e < T.edge.size(); e++) { hmix(h, fbits(T.edge[e].x)); hmix(h, fbits(T.edge[e].y)); hmix(h, fbits(T.edge[e].z)); }
-        for (size_t i = 0; i < T.cellStatus.size(); i++) hmix(h, T.cellStatus[i]);
-        for (size_t i = 0; i < T.cellRange.size(); i++) hmix(h, (uint32_t)(uint16_t)T.cellRange[i]);
-        for (size_t i = 0; i < T.yAxis.size(); i++) hmix(h, T.yAxis[i]);
-        job->struct_hash = h;
-    }
+    if (job->algorithm == 5 || job->algorithm == 6) job->struct_hash = hashConvex(s.tunnel);
     if (job->algorithm == 3 || job->algorithm == 4)
     {
         const TunnelO &T = s.tunnel;
@@ -1502,7 +1520,7 @@ extern "C" int rt_oracle_bounce(oracle_bounce_job *job)
 extern "C" int rt_oracle_run(oracle_job *job)
 {
     if (!job || job->preset < 1 || job->preset > 5) return -1;
-    if (job->algorithm < 0 || job->algorithm > 4) return -2;
+    if (job->algorithm < 0 || job->algorithm > 6) return -2;
     if (job->width <= 0 || job->height <= 0) return -3;
     Scene s;
     if (!buildPreset(s, job)) return -4;
@@ -1518,6 +1536,7 @@ extern "C" int rt_oracle_run(oracle_job *job)
         const auto t0 = std::chrono::steady_clock::now();
         if (T.algorithm == 1 || T.algorithm == 2) initGrid(T);
         else if (T.algorithm == 3 || T.algorithm == 4) initKd(T);
+        else if (T.algorithm == 5 || T.algorithm == 6) initConvex(T);
         job->prepare_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         job->stats[ORACLE_STAT_N_TRIS] = (int64_t)T.tris.size();
         uint64_t th = H0;
@@ -1552,6 +1571,7 @@ extern "C" int rt_oracle_run(oracle_job *job)
             }
             job->struct_hash = h;
         }
+        else if (T.algorithm == 5 || T.algorithm == 6) job->struct_hash = hashConvex(T);
         else if (T.algorithm == 3 || T.algorithm == 4)
         {
             uint64_t h = H0;

@@ -109,6 +109,27 @@ def bounce_pt_golden():
         json.dump(meta, f, indent=1, sort_keys=True)
 
 
+CONVEX_JOBS = {  # RayTracingOpt's own convex walk (Tunnel::fastIntersect) behind the preset scenes
+    "p5_convex_s40_160x120": dict(preset=5, algorithm="convex", segments=40, width=160, height=120),
+    "p5_convexsimple_s40_160x120": dict(preset=5, algorithm="convexsimple", segments=40, width=160, height=120),
+    "p4_convex_s24_160x120": dict(preset=4, algorithm="convex", segments=24, width=160, height=120),
+}
+
+
+def convex_golden():
+    """tests/golden/convex_golden.{npz,json}: presets 4 / 5 rendered by libref.so with Tunnel::Convex / ConvexSimple."""
+    arrays, meta = {}, {}
+    for name, job in CONVEX_JOBS.items():
+        r = O.run("ref", image=True, hits=True, **job)
+        for k in ("hit_id", "hit_t", "image"):
+            arrays[f"{name}.{k}"] = r[k]
+        meta[name] = {"job": job, "n_rays": r["n_rays"], "n_tri_tests": r["n_tri_tests"], "struct_hash": f"{r['struct_hash']:016x}"}
+    np.savez_compressed(os.path.join(HERE, "convex_golden.npz"), **arrays)
+    with open(os.path.join(HERE, "convex_golden.json"), "w") as f:
+        json.dump(meta, f, indent=1, sort_keys=True)
+
+
 if __name__ == "__main__":
     bounce_golden()
     bounce_pt_golden()
+    convex_golden()

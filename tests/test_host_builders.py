@@ -134,3 +134,16 @@ def test_performance_test_program_builders_match_reference():
             assert st[k] == m["stats"][k], (name, k)
         assert f"{s.struct_hash():016x}" == m["struct_hash"], name
         s.close()
+
+
+def test_convex_tables_of_presets_match_reference():
+    """RayTracingOpt's convex tables (400 x 400 cell table, ring normals from the path, order table) built by the host API."""
+    with open(os.path.join(os.path.dirname(__file__), "golden", "convex_golden.json")) as f:
+        meta = json.load(f)
+    for name, m in sorted(meta.items()):
+        j = m["job"]
+        s = PresetScene(j["preset"], j["algorithm"], j["segments"])
+        assert f"{s.struct_hash():016x}" == m["struct_hash"], name
+        f_ = s.flat.contents
+        assert (f_.cx_table_size, f_.cx_round_bins) == (400, 0)
+        s.close()

@@ -159,3 +159,37 @@ def test_pt_program_full_size_trees_golden():
         b = O.bounce("oracle", xy, 5000.0, 1.5707964, 150, 150, alg, pt_builders=True)
         m = meta[f"r5000_s150.{alg}"]
         assert f"{b['struct_hash']:016x}" == m["struct_hash"] and b["stats"] == m["stats"]
+
+
+# ---- RayTracingOpt's convex walk (Tunnel::fastIntersect, Tunnel.cpp:135-344, 972-1161) behind the presets -----
+def _convex_meta():
+    import json
+    import os
+    here = os.path.join(os.path.dirname(__file__), "golden")
+    with open(os.path.join(here, "convex_golden.json")) as f:
+        return json.load(f), np.load(os.path.join(here, "convex_golden.npz"))
+
+
+@pytest.mark.parametrize("name", ["p5_convex_s40_160x120", "p5_convexsimple_s40_160x120", "p4_convex_s24_160x120"])
+def test_convex_presets_golden(name):
+    """Fixtures recorded from libref.so: table hash, primary hit ids / distances, Whitted image (the ray context travels
+    down the reflection chain), ray and triangle-test totals -- all bit-identical."""
+    meta, arr = _convex_meta()
+    m = meta[name]
+    o = O.run("oracle", image=True, hits=True, **m["job"])
+    assert f"{o['struct_hash']:016x}" == m["struct_hash"]
+    assert (o["n_rays"], o["n_tri_tests"]) == (m["n_rays"], m["n_tri_tests"])
+    assert np.array_equal(o["hit_id"], arr[f"{name}.hit_id"])
+    assert np.array_equal(o["hit_t"].view(np.uint32), arr[f"{name}.hit_t"].view(np.uint32))
+    assert np.array_equal(o["image"].view(np.uint32), arr[f"{name}.image"].view(np.uint32))
+
+
+@pytest.mark.skipif(not O.available("ref"), reason="oracle/_ref/libref.so not built (no /root/reference)")
+@pytest.mark.parametrize("alg", ["convex", "convexsimple"])
+def test_convex_presets_oracle_matches_ref(alg):
+    job = dict(preset=5, algorithm=alg, segments=30, width=96, height=72)
+    a = O.run("ref", image=True, hits=True, **job)
+    b = O.run("oracle", image=True, hits=True, **job)
+    assert a["struct_hash"] == b["struct_hash"] and a["n_rays"] == b["n_rays"]
+    for k in ("hit_id", "hit_t", "image"):
+        assert np.array_equal(a[k].view(np.uint8), b[k].view(np.uint8)), k

@@ -67,6 +67,7 @@ class FlatScene(C.Structure):
         ("n_cx_path", C.c_int32), ("cx_frames", C.POINTER(C.c_float)),
         ("n_cx_edges", C.c_int32), ("cx_edges", C.POINTER(C.c_float)),
         ("cx_width", C.c_float), ("cx_height", C.c_float),
+        ("cx_table_size", C.c_int32), ("cx_round_bins", C.c_int32),
         ("cx_cell_status", C.POINTER(C.c_uint8)), ("cx_cell_range", C.POINTER(C.c_int16)),
         ("cx_order", C.POINTER(C.c_uint16)),
     ]

@@ -541,12 +541,14 @@ extern "C" int rtb_scene_upload(rtb_ctx *ctx, const rtb_flat_scene *f, rtb_scene
         {
             const int64_t perSegment = 2 * (int64_t)f->n_cx_edges;
             if (f->n_cx_path < 2 || f->n_cx_edges < 3 || f->n_cx_edges > 32767 || !f->cx_frames || !f->cx_edges || !f->cx_cell_status ||
-                !f->cx_cell_range || (f->accel == RTB_ACCEL_CONVEX && !f->cx_order) || !(f->cx_width > 0) || !(f->cx_height > 0))
+                !f->cx_cell_range || (f->accel == RTB_ACCEL_CONVEX && !f->cx_order) || !(f->cx_width > 0) || !(f->cx_height > 0) ||
+                f->cx_table_size < 2 || f->cx_table_size > 4096)
                 return bail(fail(ctx, RTB_ERR_INVALID, "rtb_scene_upload: convex accelerator tables missing (the tunnel needs ring normals: "
                                                        "PerformanceTest's generator)"));
             if ((int64_t)f->n_tris != (f->n_cx_path - 1) * perSegment)
                 return bail(fail(ctx, RTB_ERR_INVALID, "rtb_scene_upload: convex accelerator needs (n_cx_path - 1) * 2 * n_cx_edges triangles in segment order"));
-            for (int i = 0; i < 100 * 100; i++)
+            const size_t tableCells = (size_t)f->cx_table_size * f->cx_table_size;
+            for (size_t i = 0; i < tableCells; i++)
             {
                 const int st = f->cx_cell_status[i], b = f->cx_cell_range[2 * i], e = f->cx_cell_range[2 * i + 1];
                 if (st > 2 || (st == 1 && (b < 0 || e >= f->n_cx_edges)))
@@ -556,10 +558,11 @@ extern "C" int rtb_scene_upload(rtb_ctx *ctx, const rtb_flat_scene *f, rtb_scene
                 for (int64_t i = 0; i < (int64_t)100 * 360 * perSegment; i++)
                     if (f->cx_order[i] >= perSegment) return bail(fail(ctx, RTB_ERR_INVALID, "rtb_scene_upload: bad convex order table"));
             d.cx_n_path = f->n_cx_path; d.cx_n_edges = f->n_cx_edges; d.cx_width = f->cx_width; d.cx_height = f->cx_height;
+            d.cx_table = f->cx_table_size; d.cx_round_bins = f->cx_round_bins ? 1 : 0;
             if ((rc = uploadArray(ctx, s, f->cx_frames, (size_t)f->n_cx_path * 8, &d.cx_frames)) != RTB_OK) return bail(rc);
             if ((rc = uploadArray(ctx, s, f->cx_edges, (size_t)f->n_cx_edges * 3, &d.cx_edges)) != RTB_OK) return bail(rc);
-            if ((rc = uploadArray(ctx, s, f->cx_cell_status, (size_t)100 * 100, &d.cx_status)) != RTB_OK) return bail(rc);
-            if ((rc = uploadArray(ctx, s, (const short *)f->cx_cell_range, (size_t)100 * 100 * 2, &d.cx_range)) != RTB_OK) return bail(rc);
+            if ((rc = uploadArray(ctx, s, f->cx_cell_status, tableCells, &d.cx_status)) != RTB_OK) return bail(rc);
+            if ((rc = uploadArray(ctx, s, (const short *)f->cx_cell_range, tableCells * 2, &d.cx_range)) != RTB_OK) return bail(rc);
             if (f->accel == RTB_ACCEL_CONVEX &&
                 (rc = uploadArray(ctx, s, f->cx_order, (size_t)100 * 360 * perSegment, &d.cx_order)) != RTB_OK) return bail(rc);
         }

@@ -72,7 +72,7 @@ struct DScene
     const uint2 *kd_nodes;
     const uint32_t *kd_tris;
     // convex accelerator (include/rtb.h: cx_*)
-    int cx_n_path, cx_n_edges;
+    int cx_n_path, cx_n_edges, cx_table, cx_round_bins;
     float cx_width, cx_height;
     const float *cx_frames;
     const float *cx_edges;
@@ -470,23 +470,23 @@ __device__ bool linearIntersect(const DScene &S, const Ray &ray, int &triOut, fl
 // ---------------------------------------------------------------------------------------------
 // Convex accelerator -- reference PerformanceTest/ConvexAcc.cpp:7-84, 273-415 (Tunnel.cpp:972-1161).
 // A ray inside the tunnel walks from cross-section polygon to polygon (point-in-convex-polygon through the
-// 100 x 100 table) until it leaves through the wall of a segment, then tries that segment's triangles in
+// lookup table) until it leaves through the wall of a segment, then tries that segment's triangles in
 // list order (ConvexSimple) or in the order of the (height, direction) table (Convex) and returns the FIRST
 // accepted one.  All tables come from the host (rtb_scene_upload); what runs here is float arithmetic in the
 // reference's order plus one atan2f per wall exit (CUDA's differs from glibc's in the last ulps: it can
 // select the neighbouring direction bin only when the angle sits on a bin boundary to within those ulps).
 // ---------------------------------------------------------------------------------------------
-#define RTB_CX_TABLE 100
 __device__ __forceinline__ bool convexAtOrigin(const DScene &S, V3 o, V3 d, float &distance)
 {
     if (o.z * d.z >= 0) return false;
     distance = (0 - o.z) / d.z;
     const V3 p = o + d * distance;
-    const float cellWidth = S.cx_width / (RTB_CX_TABLE - 1.0f), cellHeight = S.cx_height / (RTB_CX_TABLE - 1.0f);
+    const int table = S.cx_table; // 100 (PerformanceTest) or 400 (RayTracingOpt)
+    const float cellWidth = S.cx_width / (table - 1.0f), cellHeight = S.cx_height / (table - 1.0f);
     int i = f2i((p.x + S.cx_width / 2) / cellWidth + 0.5f), j = f2i(p.y / cellHeight + 0.5f);
     i = max(i, 0); j = max(j, 0);
-    i = min(i, RTB_CX_TABLE - 1); j = min(j, RTB_CX_TABLE - 1);
-    const int cell = i * RTB_CX_TABLE + j;
+    i = min(i, table - 1); j = min(j, table - 1);
+    const int cell = i * table + j;
     const unsigned int st = __ldg(S.cx_status + cell);
     if (st == 0) return true;
     if (st == 2) return false;
@@ -554,7 +554,7 @@ __device__ bool convexIntersect(const DScene &S, const Ray &ray, RayCtx &ctx, in
                 const float PI_F = 3.14159265359f;
                 float fAngle = atan2f(nd.y, nd.x);
                 fAngle = (fAngle < 0) ? fAngle + PI_F * 2 : fAngle;
-                int iAngle = f2i(fAngle / PI_F * 180.0f + 0.5f) % 360;
+                int iAngle = S.cx_round_bins ? f2i(fAngle / PI_F * 180.0f + 0.5f) % 360 : f2i(fAngle / PI_F * 180.0f);
                 iAngle = max(0, iAngle); iAngle = min(359, iAngle);
                 row = S.cx_order + ((size_t)index * 360 + iAngle) * perSegment;
             }

@@ -334,6 +334,7 @@ private:
     std::vector<uint8_t> cxCellStatus_;
     std::vector<int16_t> cxCellRange_;
     std::vector<uint16_t> cxOrder_;
+    int cxTable_ = 0;
     void initConvex();
     void collect(std::vector<TunnelTriangle> &flat) const;
     void initGrid(const std::vector<TunnelTriangle> &tris);

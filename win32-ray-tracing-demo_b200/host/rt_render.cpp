@@ -390,7 +390,7 @@ extern "C" {
 // Build preset `preset` (1..5, reference Scripts.cpp) with the host builders and flatten it.
 rtbh_scene *rtbh_preset_create(int preset, int algorithm, int segments, const char *stl_path)
 {
-    if (preset < 1 || preset > 5 || algorithm < 0 || algorithm > 4) return nullptr;
+    if (preset < 1 || preset > 5 || algorithm < 0 || algorithm > 6) return nullptr;
     rtbh_scene *h = new rtbh_scene();
     Script script = *scripts[preset - 1];
     script.tunnelSegments = segments;
@@ -504,8 +504,9 @@ uint64_t rtbh_struct_hash(const rtbh_scene *h)
         hmix(x, fbits(f.cx_width)); hmix(x, fbits(f.cx_height));
         for (int i = 0; i < f.n_cx_path * 8; i++) hmix(x, fbits(f.cx_frames[i]));
         for (int i = 0; i < f.n_cx_edges * 3; i++) hmix(x, fbits(f.cx_edges[i]));
-        for (int i = 0; i < 100 * 100; i++) hmix(x, f.cx_cell_status[i]);
-        for (int i = 0; i < 100 * 100 * 2; i++) hmix(x, (uint32_t)(uint16_t)f.cx_cell_range[i]);
+        const int cells = f.cx_table_size * f.cx_table_size;
+        for (int i = 0; i < cells; i++) hmix(x, f.cx_cell_status[i]);
+        for (int i = 0; i < cells * 2; i++) hmix(x, (uint32_t)(uint16_t)f.cx_cell_range[i]);
         if (f.accel == RTB_ACCEL_CONVEX)
             for (int64_t i = 0; i < (int64_t)100 * 360 * 2 * f.n_cx_edges; i++) hmix(x, f.cx_order[i]);
         return x;

@@ -242,7 +242,22 @@ void Tunnel::init()
 void Tunnel::initConvex()
 {
     const size_t n = crossSection.size(), nPath = path.size();
-    if (n < 3 || nPath < 2 || ringNormals.size() != nPath) return; // flatten() emits no tables; the upload rejects the scene
+    if (n < 3 || nPath < 2) return; // flatten() emits no tables; the upload rejects the scene
+    // The two reference programs differ in three details (RayTracingOpt/Tunnel.cpp:135-344 vs PerformanceTest/ConvexAcc.cpp):
+    // ring normals (PerformanceTest's generator averages the adjoining segments; RayTracingOpt takes the direction of
+    // the segment that starts at the vertex, here), table resolution (100 vs 400) and which edges a Partial cell
+    // tests (a precomputed range vs all of them); plus the rounding of the direction bin (flatten: cx_round_bins).
+    const bool pt = performanceTestBuilders;
+    if (!pt)
+    {
+        ringNormals.clear();
+        for (size_t i = 0; i < nPath; i++)
+        {
+            if (i + 1 < nPath) ringNormals.push_back(Vector(path[i], path[i + 1]).norm());
+            else ringNormals.push_back(Vector(path[i], path[i] + Vector(path[i - 1], path[i])).norm());
+        }
+    }
+    if (ringNormals.size() != nPath) return;
     cxFrames_.resize(nPath * 8);
     for (size_t i = 0; i < nPath; i++)
     {
@@ -267,7 +282,8 @@ void Tunnel::initConvex()
             if (side(e, x, y) < 0.0001f) return false;
         return true;
     };
-    const int R = 100;
+    const int R = pt ? 100 : 400;
+    cxTable_ = R;
     cxCellStatus_.assign((size_t)R * R, 2);
     cxCellRange_.assign((size_t)R * R * 2, -1);
     const float cellW = width / (R - 1.0f), cellH = height / (R - 1.0f);
@@ -283,6 +299,7 @@ void Tunnel::initConvex()
             if (cornersInside == 4) { cxCellStatus_[cell] = 0; continue; }
             if (cornersInside == 0) { cxCellStatus_[cell] = 2; continue; }
             cxCellStatus_[cell] = 1;
+            if (!pt) { cxCellRange_[cell * 2] = 0; cxCellRange_[cell * 2 + 1] = (int16_t)(n - 1); continue; }
             int first = SHRT_MAX, last = SHRT_MIN;
             for (size_t e = 0; e < n; e++)
             {
@@ -664,6 +681,7 @@ void Tunnel::flatten(FlatScene &out) const
     out.kdLeafTris = kdLeafTris_;
     out.cxFrames = cxFrames_; out.cxEdges = cxEdges_; out.cxCellStatus = cxCellStatus_; out.cxCellRange = cxCellRange_; out.cxOrder = cxOrder_;
     f.cx_width = width; f.cx_height = height;
+    f.cx_table_size = cxTable_; f.cx_round_bins = performanceTestBuilders ? 1 : 0;
     f.grid_build_resolution = ((algorithm == RegularGrid || algorithm == FlatGrid) && gridOnDevice) ? gridResolution : 0;
 }
 
