@@ -28,6 +28,9 @@
 #include <omp.h>
 
 #include "oracle_abi.h"
+#ifdef RTB_PRETEST_CHECK
+#include "../win32-ray-tracing-demo_b200/csrc/rtb_pretest.h"
+#endif
 
 namespace {
 
@@ -685,19 +688,60 @@ void initKd(TunnelO &T)
     buildKd(T, 0, list, 0);
 }
 
+#ifdef RTB_PRETEST_CHECK
+// Checker of the product's conservative rejection test (win32-ray-tracing-demo_b200/csrc/rtb_pretest.h), built only into
+// librt_oracle_pretest.so (make pretest; tests/test_pretest.py): the same host+device function the kernels run is
+// evaluated next to the exact test on every (ray, triangle) pair of a frame.  A "violation" is a pair the pre-test
+// rejects although the exact test would have made it the nearest hit of its list.
+struct PretestStats { long long tests, candidates, updates, violations, lists, lists1, lists2, unsure; };
+PretestStats g_pre = {0, 0, 0, 0, 0, 0, 0, 0};
+int g_pre_use_nearest = 0;
+#endif
+
 // nearest hit of a triangle list, first-in-list wins ties (strict <)
 inline bool nearestInList(const TunnelO &T, const std::vector<int> &list, const RayO &ray, float lo, float hi,
                           bool window, int &triOut, float &tOut, Probe *pr)
 {
     float minDistance = FLT_MAX;
     bool found = false;
+#ifdef RTB_PRETEST_CHECK
+    PretestStats st = {0, 0, 0, 0, 1, 0, 0, 0};
+    const float dmx = rtb_pre::dirMax(ray.d.x, ray.d.y, ray.d.z);
+    const float Lp = rtb_pre::lowBound(window ? lo : -FLT_MAX);
+    int cands = 0;
+#endif
     for (size_t i = 0; i < list.size(); i++)
     {
         float t;
+#ifdef RTB_PRETEST_CHECK
+        const Tri &K = T.tris[list[i]];
+        const float rec[9] = {K.a.x, K.a.y, K.a.z, K.b.x, K.b.y, K.b.z, K.c.x, K.c.y, K.c.z};
+        const rtb_pre::PreTri P = rtb_pre::makePreTri(rec);
+        // the kernels defer the exact test of a candidate to the end of its list, so their H is the leaf window
+        // alone (g_pre_use_nearest = 0); = 1 also feeds the nearest hit so far, the tightest H the header allows
+        const float Hp = rtb_pre::highBound(window ? hi : FLT_MAX, g_pre_use_nearest ? minDistance : FLT_MAX);
+        const bool rejected = window ? rtb_pre::sureReject<true>(P, ray.o.x, ray.o.y, ray.o.z, ray.d.x, ray.d.y, ray.d.z, dmx, Lp, Hp)
+                                     : rtb_pre::sureReject<false>(P, ray.o.x, ray.o.y, ray.o.z, ray.d.x, ray.d.y, ray.d.z, dmx, Lp, Hp);
+        st.tests++;
+        if (!rejected) { st.candidates++; cands++; }
+        // with L' = +inf the t test fires whenever it is allowed to: the call returns "the sign of det_M is certain"
+        if (!rejected && !rtb_pre::sureReject<false>(P, ray.o.x, ray.o.y, ray.o.z, ray.d.x, ray.d.y, ray.d.z, dmx, INFINITY, Hp)) st.unsure++;
+        const bool wouldUpdate = triIntersect(K, ray, t, nullptr) && !(window && !(t >= lo && t <= hi)) && t < minDistance;
+        if (wouldUpdate) st.updates++;
+        if (wouldUpdate && rejected) st.violations++;
+#endif
         if (!triIntersect(T.tris[list[i]], ray, t, pr)) continue;
         if (window && !(t >= lo && t <= hi)) continue;
         if (t < minDistance) { minDistance = t; triOut = list[i]; found = true; }
     }
+#ifdef RTB_PRETEST_CHECK
+    st.lists1 = cands >= 1; st.lists2 = cands >= 2;
+#pragma omp critical(pretest_stats)
+    {
+        g_pre.tests += st.tests; g_pre.candidates += st.candidates; g_pre.updates += st.updates;
+        g_pre.violations += st.violations; g_pre.lists += st.lists; g_pre.lists1 += st.lists1; g_pre.lists2 += st.lists2; g_pre.unsure += st.unsure;
+    }
+#endif
     tOut = minDistance;
     return found;
 }
@@ -1516,6 +1560,75 @@ extern "C" int rt_oracle_bounce(oracle_bounce_job *job)
     job->total_rays = total;
     return 0;
 }
+
+#ifdef RTB_PRETEST_CHECK
+// out[8] = tests, candidates, updates, violations, lists, lists with >= 1 candidate, lists with >= 2, candidates whose
+// det_M sign was uncertain (grazing rays); reset on read
+// Random stress of the rejection test away from the preset scenes: triangles of widely varying size and aspect,
+// rays aimed at a point of the triangle's plane close to (inside or just outside) its boundary, from near and far,
+// head-on to grazing, unit and non-unit directions.  out[4] = pairs, exact accepts, candidates, violations.
+extern "C" void rt_oracle_pretest_fuzz(uint64_t seed, long long n, long long *out)
+{
+    long long acc = 0, cand = 0, viol = 0;
+#pragma omp parallel for reduction(+ : acc, cand, viol) schedule(static)
+    for (long long i = 0; i < n; i++)
+    {
+        uint32_t ctr[4] = {(uint32_t)i, (uint32_t)(i >> 32), 0, 0}, key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)}, r[4];
+        float u[20];
+        for (int b = 0; b < 5; b++)
+        {
+            ctr[2] = (uint32_t)b;
+            philox4x32_10(ctr, key, r);
+            for (int q = 0; q < 4; q++) u[4 * b + q] = (float)((r[q] >> 8) * (1.0 / 16777216.0));
+        }
+        const float scale = powf(10.0f, -3.0f + 7.0f * u[0]);            // triangle size 1e-3 .. 1e4
+        const float aspect = powf(10.0f, -3.0f * u[1]);                   // down to 1000 : 1 slivers
+        const float offset = (u[2] < 0.5f) ? 0.0f : powf(10.0f, 5.0f * u[3]) - 1.0f; // scene offset up to 1e5
+        Tri K;
+        K.a = v3(offset + scale * (u[4] - 0.5f), offset * 0.5f + scale * (u[5] - 0.5f), scale * (u[6] - 0.5f) - offset);
+        K.b = K.a + v3(scale * (u[7] - 0.5f), scale * (u[8] - 0.5f), scale * (u[9] - 0.5f));
+        K.c = K.a + v3(scale * aspect * (u[10] - 0.5f), scale * aspect * (u[11] - 0.5f), scale * aspect * (u[12] - 0.5f));
+        K.n = v3(0, 1, 0); K.mat = 0;
+        // target point in barycentric coordinates around the boundary, half of the time within 1e-3 of an edge
+        float be = u[13] * 1.2f - 0.1f, ga = u[14] * 1.2f - 0.1f;
+        if (u[15] < 0.25f) be = (u[13] - 0.5f) * 2e-3f;
+        else if (u[15] < 0.5f) ga = (u[14] - 0.5f) * 2e-3f;
+        else if (u[15] < 0.75f) ga = 1.0f - be + (u[14] - 0.5f) * 2e-3f;
+        const V3 target = K.a + (K.b - K.a) * be + (K.c - K.a) * ga;
+        V3 dir = normalize(v3(u[16] - 0.5f, u[17] - 0.5f, u[18] - 0.5f));
+        const V3 nrm = cross(K.b - K.a, K.c - K.a);
+        if (u[19] < 0.3f)
+        { // grazing: tilt the direction into the triangle's plane
+            const float nl = length(nrm);
+            if (nl > 0) { const V3 nn = nrm * (1 / nl); dir = normalize(dir - nn * (dot(dir, nn) * (1.0f - 1e-3f * u[16]))); }
+        }
+        const float dist = scale * powf(10.0f, -2.0f + 5.0f * u[17]);    // 0.01 .. 1000 triangle sizes away
+        RayO ray;
+        ray.o = target - dir * dist;
+        ray.d = (u[18] < 0.8f) ? dir : dir * (0.25f + 3.0f * u[19]);
+        const float rec[9] = {K.a.x, K.a.y, K.a.z, K.b.x, K.b.y, K.b.z, K.c.x, K.c.y, K.c.z};
+        const rtb_pre::PreTri P = rtb_pre::makePreTri(rec);
+        const float dmx = rtb_pre::dirMax(ray.d.x, ray.d.y, ray.d.z);
+        float t;
+        const bool hit = triIntersect(K, ray, t, nullptr);
+        // windows: none, and one that just contains / just excludes the hit
+        float lo = -FLT_MAX, hi = FLT_MAX;
+        if (hit && u[12] < 0.5f) { lo = t * (1.0f - 1e-3f * (u[11] - 0.3f)); hi = t * (1.0f + 1e-3f * (u[10] - 0.3f)); }
+        const bool inWindow = hit && t >= lo && t <= hi;
+        const bool rejected = rtb_pre::sureReject(P, ray.o.x, ray.o.y, ray.o.z, ray.d.x, ray.d.y, ray.d.z, dmx,
+                                                  rtb_pre::lowBound(lo), rtb_pre::highBound(hi, FLT_MAX));
+        acc += inWindow; cand += !rejected; viol += (inWindow && rejected);
+    }
+    out[0] = n; out[1] = acc; out[2] = cand; out[3] = viol;
+}
+extern "C" void rt_oracle_pretest_mode(int use_nearest) { g_pre_use_nearest = use_nearest; }
+extern "C" void rt_oracle_pretest_stats(long long *out)
+{
+    const long long v[8] = {g_pre.tests, g_pre.candidates, g_pre.updates, g_pre.violations, g_pre.lists, g_pre.lists1, g_pre.lists2, g_pre.unsure};
+    memcpy(out, v, sizeof(v));
+    g_pre = PretestStats{0, 0, 0, 0, 0, 0, 0, 0};
+}
+#endif
 
 extern "C" int rt_oracle_run(oracle_job *job)
 {

@@ -286,6 +286,19 @@ static void packTriangles(const float *src, size_t n, std::vector<float4> &dst)
     }
 }
 
+// a,b,c (the 9 leading floats of a record) -> the stream of the conservative rejection test (rtb_pretest.h)
+static void packPreTriangles(const float *src, size_t n, std::vector<float4> &dst)
+{
+    dst.resize(3 * n);
+    for (size_t i = 0; i < n; i++)
+    {
+        const rtb_pre::PreTri p = rtb_pre::makePreTri(src + 12 * i);
+        dst[3 * i + 0] = make_float4(p.ax, p.ay, p.az, p.a1e);
+        dst[3 * i + 1] = make_float4(p.e1x, p.e1y, p.e1z, p.ee);
+        dst[3 * i + 2] = make_float4(p.e2x, p.e2y, p.e2z, 0.f);
+    }
+}
+
 static int kdDepth(const rtb_kdnode *nodes, int n, int node, int depth, int &maxDepth, int &visited)
 {
     if (node < 0 || node >= n || depth > 64) return -1;
@@ -482,6 +495,9 @@ extern "C" int rtb_scene_upload(rtb_ctx *ctx, const rtb_flat_scene *f, rtb_scene
                 return bail(fail(ctx, RTB_ERR_INVALID, "rtb_scene_upload: triangle material out of range"));
         packTriangles(f->tri, (size_t)f->n_tris, packed);
         if ((rc = uploadArray(ctx, s, packed.data(), packed.size(), &d.tri)) != RTB_OK) return bail(rc);
+        std::vector<float4> packedPre;
+        packPreTriangles(f->tri, (size_t)f->n_tris, packedPre);
+        if ((rc = uploadArray(ctx, s, packedPre.data(), packedPre.size(), &d.tri_pre)) != RTB_OK) return bail(rc);
         if ((rc = uploadArray(ctx, s, f->tri_material, (size_t)f->n_tris, &d.tri_material)) != RTB_OK) return bail(rc);
         d.n_tris = f->n_tris;
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));

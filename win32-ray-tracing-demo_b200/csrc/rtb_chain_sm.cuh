@@ -4,7 +4,8 @@
 // Tunnel.cpp:1163-1297, the grid walk Tunnel.cpp:819-970, shading MainWindow.cpp:69-143 -- but the
 // control flow is one per-lane loop over the states
 //      STEP   advance the accelerator (k-d: one inner node or leaf entry; grid: one cell)
-//      LEAF   test triangles of the current leaf / cell
+//      LEAF   scan the list of the current leaf / cell with the conservative rejection test (rtb_pretest.h)
+//      EXACT  the reference's exact test for the candidates LEAF could not reject (see nearestInList)
 //      SHADE  close the ray (top-level geometries + tunnel result), shade, fold, spawn the reflection
 // A lane that has finished a ray shades it and starts the next ray of ITS OWN chain at once instead of
 // waiting, at a per-ray reconvergence point, for the slowest traversal in the warp.  On the tunnel
@@ -23,7 +24,7 @@ namespace rtb {
 #define RTB_SM_LEAF_BURST 1000 // triangle tests per visit of the LEAF state
 #endif
 
-enum { SM_STEP = 0, SM_LEAF = 1, SM_SHADE = 2, SM_DONE = 3 };
+enum { SM_STEP = 0, SM_LEAF = 1, SM_SHADE = 2, SM_DONE = 3, SM_EXACT = 4 };
 
 #ifndef RTB_SM_MIN_CTAS
 #define RTB_SM_MIN_CTAS 6
@@ -76,6 +77,9 @@ k_whitted_chain_sm(const __grid_constant__ DScene S, const __grid_constant__ Fra
         unsigned int li = 0, lend = 0;
         float lo = 0, hi = 0, minD = FLT_MAX;
         int hitTri = -1;
+        // conservative rejection test: per-ray / per-list constants, pending candidate, end of the exact scan
+        float dmx = 0, Lp = rtb_pre::lowBound(-FLT_MAX), Hp = rtb_pre::highBound(FLT_MAX, FLT_MAX);
+        unsigned int pend = 0xffffffffu, jend = 0;
         bool tunnelHit = false;
 
         // start the accelerator walk of ray r (reference Tunnel.cpp:1171-1197 / 833-860)
@@ -84,6 +88,7 @@ k_whitted_chain_sm(const __grid_constant__ DScene S, const __grid_constant__ Fra
             tunnelHit = false;
             hitTri = -1;
             minD = FLT_MAX;
+            dmx = rtb_pre::dirMax(r.d.x, r.d.y, r.d.z);
             if (GRID)
             {
                 if (r.o.x < S.g_origin.x || r.o.x > S.g_far.x || r.o.y < S.g_origin.y || r.o.y > S.g_far.y ||
@@ -173,7 +178,7 @@ k_whitted_chain_sm(const __grid_constant__ DScene S, const __grid_constant__ Fra
                             const unsigned int rk = w.y + __popc(w.x & (bit - 1));
                             li = __ldg(S.g_start + rk);
                             lend = __ldg(S.g_start + rk + 1);
-                            minD = FLT_MAX; hitTri = -1;
+                            minD = FLT_MAX; hitTri = -1; pend = 0xffffffffu;
                             st = SM_LEAF;
                         }
                         else gridAdvance();
@@ -187,7 +192,8 @@ k_whitted_chain_sm(const __grid_constant__ DScene S, const __grid_constant__ Fra
                             li = nd.x;
                             lend = nd.x + (nd.y >> 2);
                             lo = enT - 0.001f; hi = exT + 0.001f;
-                            minD = FLT_MAX; hitTri = -1;
+                            Lp = rtb_pre::lowBound(lo); Hp = rtb_pre::highBound(hi, FLT_MAX);
+                            minD = FLT_MAX; hitTri = -1; pend = 0xffffffffu;
                             if (li == lend) kdPop();
                             else st = SM_LEAF;
                         }
@@ -228,16 +234,35 @@ k_whitted_chain_sm(const __grid_constant__ DScene S, const __grid_constant__ Fra
                 for (int burst = 0; burst < RTB_SM_LEAF_BURST && st == SM_LEAF; burst++)
                 {
                     const uint32_t idx = __ldg((GRID ? S.g_tris : S.kd_tris) + li);
-                    const TriData T = loadTri(S.tri, idx);
+                    const rtb_pre::PreTri P = loadPreTri(S.tri_pre, idx);
                     pr.tri();
+                    if (!rtb_pre::sureReject<!GRID>(P, r.o.x, r.o.y, r.o.z, r.d.x, r.d.y, r.d.z, dmx, Lp, Hp))
+                    { // candidate: its exact test waits for the end of the list, unless one is waiting already
+                        if (pend != 0xffffffffu) { jend = lend; st = SM_EXACT; }
+                        else pend = li;
+                    }
+                    if (st == SM_LEAF && ++li == lend)
+                    {
+                        if (pend != 0xffffffffu) { jend = pend + 1; st = SM_EXACT; }
+                        else listDone();
+                    }
+                }
+            }
+            if (st == SM_EXACT)
+            { // [pend, jend) in list order; entries behind li (where the fast scan stopped) are counted here
+                for (unsigned int j = pend; j < jend; j++)
+                {
+                    const uint32_t idx = __ldg((GRID ? S.g_tris : S.kd_tris) + j);
+                    const TriData T = loadTri(S.tri, idx);
+                    if (j > li) pr.tri();
                     float t;
                     if (triIntersectT<true>(T, r, t) && (GRID || (t >= lo && t <= hi)) && t < minD)
                     {
                         minD = t;
                         hitTri = (int)idx;
                     }
-                    if (++li == lend) listDone();
                 }
+                listDone();
             }
             if (st == SM_SHADE)
             {
