@@ -308,6 +308,50 @@ def test_upload_rejects_bad_scenes(ctx):
     f.accel = 5  # convex: out of scope
     with pytest.raises(rtb200.RtbError):
         ctx.upload(f)
+    # malformed accelerator / index streams are refused on the host, before anything reaches a kernel
+    import ctypes as C
+
+    def corrupted(copy_field, n, ctype, mutate):
+        f = rtb200.FlatScene.from_buffer_copy(s.flat.contents)
+        arr = (ctype * n)()
+        C.memmove(arr, getattr(s.flat.contents, copy_field), C.sizeof(arr))
+        mutate(arr)
+        setattr(f, copy_field, C.cast(arr, type(getattr(f, copy_field))))
+        return f, arr
+
+    nn, nr, nt = s.flat.contents.n_kd_nodes, s.flat.contents.n_kd_refs, s.flat.contents.n_tris
+
+    def first_inner(nodes):
+        return next(i for i in range(nn) if (nodes[i].b & 3) != 3)
+
+    def first_leaf(nodes):
+        return next(i for i in range(nn) if (nodes[i].b & 3) == 3 and (nodes[i].b >> 2) > 0)
+
+    def bad_right(nodes):  # right child not behind the left subtree
+        i = first_inner(nodes); nodes[i].b = ((i + 1) << 2) | (nodes[i].b & 3)
+
+    def right_out_of_range(nodes):
+        i = first_inner(nodes); nodes[i].b = ((nn + 5) << 2) | (nodes[i].b & 3)
+
+    def leaf_range(nodes):
+        i = first_leaf(nodes); nodes[i].a = nr
+
+    def truncated(nodes):  # the last leaf turned into an inner node: the tree never closes
+        nodes[nn - 1].b = (nn << 2) | 0
+
+    for mutate in (bad_right, right_out_of_range, leaf_range, truncated):
+        f, keep = corrupted("kd_nodes", nn, rtb200.KdNode, mutate)
+        with pytest.raises(rtb200.RtbError):
+            ctx.upload(f)
+    f, keep = corrupted("kd_leaf_tris", nr, C.c_uint32, lambda a: a.__setitem__(nr // 2, nt))
+    with pytest.raises(rtb200.RtbError):
+        ctx.upload(f)
+    f, keep = corrupted("tri_material", nt, C.c_int32, lambda a: a.__setitem__(nt - 1, -1))
+    with pytest.raises(rtb200.RtbError):
+        ctx.upload(f)
+    f, keep = corrupted("tri_material", nt, C.c_int32, lambda a: a.__setitem__(0, 99))
+    with pytest.raises(rtb200.RtbError):
+        ctx.upload(f)
     dev = ctx.upload(s.flat)
     with pytest.raises(rtb200.RtbError):
         dev.render(s.camera, s.setting, rtb200.make_frame(0, 10))

@@ -8,6 +8,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <chrono>
 #include <vector>
 
 #include "rtb_chain_sm.cuh"
@@ -91,6 +92,10 @@ struct rtb_ctx
     bool order_valid = false;
     bool tiers_ok = true; // false: this frame uses the order but not the latency tiers (camera moved)
     OrderKey order_key = {};
+    // page-locked staging ring of rtb_scene_upload: streams are packed / copied into it and leave with truly
+    // asynchronous H2D copies (a pageable source makes every cudaMemcpyAsync a staged, partly synchronous copy)
+    char *stage = nullptr;
+    size_t stage_cap = 0, stage_used = 0;
     std::string error;
 };
 
@@ -102,6 +107,7 @@ struct rtb_scene
     bool has_refractive = false;
     bool has_tunnel = false;
     cudaEvent_t last_use = nullptr; // recorded after every launch that reads the scene
+    cudaEvent_t ready = nullptr;    // recorded on ctx->stream behind the upload copies
     int64_t grid_cells_used = 0, grid_refs = 0, grid_words = 0;
     bool long_lists = false; // regular grid with >= 16 triangle references per occupied cell (tier policy, wideCount)
     unsigned long long signature = 0; // sampled content hash, identifies "the same scene again" for the tile-order cache
@@ -233,6 +239,7 @@ extern "C" int rtb_shutdown(rtb_ctx *ctx)
     if (ctx->d_hist) cudaFree(ctx->d_hist);
     if (ctx->d_cursor) cudaFree(ctx->d_cursor);
     if (ctx->d_heavy) cudaFree(ctx->d_heavy);
+    if (ctx->stage) cudaFreeHost(ctx->stage);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return RTB_OK;
@@ -255,61 +262,141 @@ extern "C" int64_t rtb_shard_rows(const rtb_frame *f)
 }
 
 // ---- scene upload -----------------------------------------------------------------------------
-template <class T>
-static int uploadArray(rtb_ctx *ctx, rtb_scene *s, const T *host, size_t n, const T **dev)
+// `bytes` of page-locked staging memory.  Copies queued from the ring read it asynchronously, so it is only reused
+// after the stream has drained (once every few uploads; the ring holds several scenes).
+static int stageReserve(rtb_ctx *ctx, size_t bytes, char **out)
+{
+    bytes = (bytes + 255) & ~(size_t)255;
+    if (ctx->stage_used + bytes > ctx->stage_cap)
+    {
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        if (bytes > ctx->stage_cap)
+        {
+            if (ctx->stage) cudaFreeHost(ctx->stage);
+            ctx->stage = nullptr; ctx->stage_cap = 0;
+            const size_t cap = bytes * 2 > ((size_t)64 << 20) ? bytes * 2 : ((size_t)64 << 20);
+            CUDA_TRY(ctx, cudaHostAlloc((void **)&ctx->stage, cap, cudaHostAllocDefault));
+            ctx->stage_cap = cap;
+        }
+        ctx->stage_used = 0;
+    }
+    *out = ctx->stage + ctx->stage_used;
+    ctx->stage_used += bytes;
+    return RTB_OK;
+}
+
+// device array of n elements; `fill(T *staging)` writes the elements into staging memory (nullptr: zero-filled)
+template <class T, class Fill>
+static int uploadWith(rtb_ctx *ctx, rtb_scene *s, size_t n, const T **dev, Fill fill, bool zero = false)
 {
     *dev = nullptr;
-    if (n == 0) n = 1; // keep pointers valid
+    const size_t count = n ? n : 1; // keep pointers valid
     void *p = nullptr;
-    CUDA_TRY(ctx, cudaMallocAsync(&p, n * sizeof(T), ctx->stream));
+    CUDA_TRY(ctx, cudaMallocAsync(&p, count * sizeof(T), ctx->stream));
     s->allocs.push_back(p);
-    s->bytes += (int64_t)(n * sizeof(T));
-    if (host) CUDA_TRY(ctx, cudaMemcpyAsync(p, host, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
-    else CUDA_TRY(ctx, cudaMemsetAsync(p, 0, n * sizeof(T), ctx->stream));
+    s->bytes += (int64_t)(count * sizeof(T));
+    if (n && !zero)
+    {
+        char *st = nullptr;
+        const int rc = stageReserve(ctx, n * sizeof(T), &st);
+        if (rc != RTB_OK) return rc;
+        fill(reinterpret_cast<T *>(st));
+        CUDA_TRY(ctx, cudaMemcpyAsync(p, st, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    else CUDA_TRY(ctx, cudaMemsetAsync(p, 0, count * sizeof(T), ctx->stream));
     *dev = (const T *)p;
     return RTB_OK;
 }
 
-// a,b,c,normal (12 floats) -> {a.xyz, e1.x} {e1.yz, e2.xy} {e2.z, n.xyz}; e1 = a - b, e2 = a - c are
-// the float subtractions reference Triangle.cpp:73-79 performs per test, done once here.
-static void packTriangles(const float *src, size_t n, std::vector<float4> &dst)
+template <class T>
+static int uploadArray(rtb_ctx *ctx, rtb_scene *s, const T *host, size_t n, const T **dev)
 {
-    dst.resize(3 * n);
-    for (size_t i = 0; i < n; i++)
+    return uploadWith<T>(ctx, s, n, dev, [&](T *st) { memcpy(st, host, n * sizeof(T)); }, host == nullptr);
+}
+
+// Triangle records (a, b, c, normal: 12 floats) -> the two device streams, one thread per triangle:
+//   exact stream  {a.xyz, e1.x} {e1.yz, e2.xy} {e2.z, n.xyz}; e1 = a - b, e2 = a - c are the float subtractions
+//                 reference Triangle.cpp:73-79 performs per test, done once here;
+//   pre stream    {a.xyz, A1 eps} {e1.xyz, E eps} {e2.xyz, 0} of the conservative rejection test (rtb_pretest.h).
+// Packing 45,900 triangles took 0.7 ms of every upload on the host; here it is one 48-byte read and two 48-byte
+// writes per thread behind the raw H2D copy.
+__global__ void k_pack_triangles(const float *__restrict__ raw, int n, float4 *__restrict__ exact, float4 *__restrict__ pre)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float t[12];
+    const float4 *src = reinterpret_cast<const float4 *>(raw) + 3 * (size_t)i;
+    const float4 r0 = src[0], r1 = src[1], r2 = src[2];
+    t[0] = r0.x; t[1] = r0.y; t[2] = r0.z; t[3] = r0.w; t[4] = r1.x; t[5] = r1.y; t[6] = r1.z; t[7] = r1.w;
+    t[8] = r2.x; t[9] = r2.y; t[10] = r2.z; t[11] = r2.w;
+    const float e1x = t[0] - t[3], e1y = t[1] - t[4], e1z = t[2] - t[5];
+    const float e2x = t[0] - t[6], e2y = t[1] - t[7], e2z = t[2] - t[8];
+    exact[3 * (size_t)i + 0] = make_float4(t[0], t[1], t[2], e1x);
+    exact[3 * (size_t)i + 1] = make_float4(e1y, e1z, e2x, e2y);
+    exact[3 * (size_t)i + 2] = make_float4(e2z, t[9], t[10], t[11]);
+    if (pre)
     {
-        const float *t = src + 12 * i;
-        const float e1x = t[0] - t[3], e1y = t[1] - t[4], e1z = t[2] - t[5];
-        const float e2x = t[0] - t[6], e2y = t[1] - t[7], e2z = t[2] - t[8];
-        dst[3 * i + 0] = make_float4(t[0], t[1], t[2], e1x);
-        dst[3 * i + 1] = make_float4(e1y, e1z, e2x, e2y);
-        dst[3 * i + 2] = make_float4(e2z, t[9], t[10], t[11]);
+        const rtb_pre::PreTri p = rtb_pre::makePreTri(t);
+        pre[3 * (size_t)i + 0] = make_float4(p.ax, p.ay, p.az, p.a1e);
+        pre[3 * (size_t)i + 1] = make_float4(p.e1x, p.e1y, p.e1z, p.ee);
+        pre[3 * (size_t)i + 2] = make_float4(p.e2x, p.e2y, p.e2z, 0.f);
     }
 }
 
-// a,b,c (the 9 leading floats of a record) -> the stream of the conservative rejection test (rtb_pretest.h)
-static void packPreTriangles(const float *src, size_t n, std::vector<float4> &dst)
+// raw records -> staging -> device (asynchronous), packed there; `pre` may be null (loose triangles: exact stream only)
+static int uploadTriangles(rtb_ctx *ctx, rtb_scene *s, const float *host, size_t n, const float4 **exact, const float4 **pre)
 {
-    dst.resize(3 * n);
-    for (size_t i = 0; i < n; i++)
-    {
-        const rtb_pre::PreTri p = rtb_pre::makePreTri(src + 12 * i);
-        dst[3 * i + 0] = make_float4(p.ax, p.ay, p.az, p.a1e);
-        dst[3 * i + 1] = make_float4(p.e1x, p.e1y, p.e1z, p.ee);
-        dst[3 * i + 2] = make_float4(p.e2x, p.e2y, p.e2z, 0.f);
-    }
+    int rc;
+    *exact = nullptr;
+    if (pre) *pre = nullptr;
+    if ((rc = uploadWith<float4>(ctx, s, 3 * n, exact, [](float4 *) {}, true)) != RTB_OK) return rc; // allocations (zeroed)
+    if (pre && (rc = uploadWith<float4>(ctx, s, 3 * n, pre, [](float4 *) {}, true)) != RTB_OK) return rc;
+    if (n == 0) return RTB_OK;
+    char *st = nullptr;
+    if ((rc = stageReserve(ctx, n * 12 * sizeof(float), &st)) != RTB_OK) return rc;
+    memcpy(st, host, n * 12 * sizeof(float));
+    void *raw = nullptr;
+    CUDA_TRY(ctx, cudaMallocAsync(&raw, n * 12 * sizeof(float), ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(raw, st, n * 12 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    k_pack_triangles<<<(unsigned int)((n + 255) / 256), 256, 0, ctx->stream>>>((const float *)raw, (int)n, const_cast<float4 *>(*exact),
+                                                                             pre ? const_cast<float4 *>(*pre) : nullptr);
+    CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, cudaFreeAsync(raw, ctx->stream));
+    return RTB_OK;
 }
 
-static int kdDepth(const rtb_kdnode *nodes, int n, int node, int depth, int &maxDepth, int &visited)
+// pre-order k-d array -> 0 when it is a well-formed tree (every inner node's right child lies behind its left
+// subtree, every node reached exactly once), maxDepth = deepest node.  One linear pass with an explicit stack of
+// pending right children: the recursive walk took 0.2 ms of every upload.
+static int kdDepth(const rtb_kdnode *nodes, int n, int &maxDepth)
 {
-    if (node < 0 || node >= n || depth > 64) return -1;
-    visited++;
-    if (depth > maxDepth) maxDepth = depth;
-    if ((nodes[node].b & 3u) == 3u) return 0;
-    const int right = (int)(nodes[node].b >> 2);
-    if (right <= node + 1) return -1;
-    if (kdDepth(nodes, n, node + 1, depth + 1, maxDepth, visited) != 0) return -1;
-    return kdDepth(nodes, n, right, depth + 1, maxDepth, visited);
+    std::vector<std::pair<int, int>> pending; // (index of a right child, its depth)
+    pending.reserve(128);
+    int depth = 0;
+    maxDepth = 0;
+    for (int i = 0; i < n; i++)
+    {
+        if (depth > 64) return -1;
+        if (depth > maxDepth) maxDepth = depth;
+        if ((nodes[i].b & 3u) == 3u)
+        { // leaf: the next node in pre-order is the nearest pending right child
+            if (pending.empty()) return i == n - 1 ? 0 : -1;
+            if (pending.back().first != i + 1) return -1;
+            depth = pending.back().second;
+            pending.pop_back();
+        }
+        else
+        {
+            const int right = (int)(nodes[i].b >> 2);
+            if (right <= i + 1 || right >= n) return -1;
+            if (!pending.empty() && right >= pending.back().first) return -1; // must end before the enclosing right child
+            pending.push_back(std::make_pair(right, depth + 1));
+            depth += 1; // the left child follows directly
+        }
+    }
+    return -1; // ran out of nodes with subtrees still open (n == 0 included)
 }
+
 
 // ---- grid built on the device (rtb_build_grid.cuh) ------------------------------------------------------------
 template <class T> static int deviceArray(rtb_ctx *ctx, rtb_scene *s, size_t n, T **dev, bool keep)
@@ -439,8 +526,28 @@ static int buildGridOnDevice(rtb_ctx *ctx, rtb_scene *s, const rtb_flat_scene *f
     return RTB_OK;
 }
 
+// RTB_UPLOAD_TIMING=1: host-side laps of rtb_scene_upload on stderr (profiling aid)
+struct UploadLaps
+{
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    std::string text;
+    UploadLaps() : on(getenv("RTB_UPLOAD_TIMING") && atoi(getenv("RTB_UPLOAD_TIMING"))), t0(std::chrono::steady_clock::now()) {}
+    void lap(const char *what)
+    {
+        if (!on) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        char buf[64];
+        snprintf(buf, sizeof(buf), " %s %.0f us;", what, std::chrono::duration<double, std::micro>(t1 - t0).count());
+        text += buf;
+        t0 = t1;
+    }
+    ~UploadLaps() { if (on) fprintf(stderr, "rtb_scene_upload:%s\n", text.c_str()); }
+};
+
 extern "C" int rtb_scene_upload(rtb_ctx *ctx, const rtb_flat_scene *f, rtb_scene **out)
 {
+    UploadLaps laps;
     if (!ctx || !f || !out) return fail(ctx, RTB_ERR_INVALID, "rtb_scene_upload: null argument");
     *out = nullptr;
     if (f->n_prims <= 0 || !f->prims) return fail(ctx, RTB_ERR_INVALID, "rtb_scene_upload: empty scene");
@@ -453,9 +560,10 @@ extern "C" int rtb_scene_upload(rtb_ctx *ctx, const rtb_flat_scene *f, rtb_scene
     rtb_scene *s = new rtb_scene();
     DScene &d = s->d;
     memset(&d, 0, sizeof(d));
-    if (cudaEventCreateWithFlags(&s->last_use, cudaEventDisableTiming) != cudaSuccess)
+    if (cudaEventCreateWithFlags(&s->last_use, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->ready, cudaEventDisableTiming) != cudaSuccess)
     {
-        delete s;
+        rtb_scene_free(ctx, s);
         return fail(ctx, RTB_ERR_CUDA, "rtb_scene_upload: cudaEventCreate failed");
     }
     d.n_prims = f->n_prims; d.n_materials = f->n_materials; d.n_top = f->n_top; d.accel = f->accel;
@@ -468,9 +576,9 @@ extern "C" int rtb_scene_upload(rtb_ctx *ctx, const rtb_flat_scene *f, rtb_scene
         if (p.type != RTB_PRIM_TUNNEL) ok = ok && p.material >= 0 && p.material < f->n_materials;
         if (p.type == RTB_PRIM_TRIANGLES) ok = ok && p.first >= 0 && p.count >= 0 && p.first + p.count <= f->n_loose && f->loose_tri;
         if (p.type == RTB_PRIM_TUNNEL) tunnels++;
-        if (!ok) { delete s; return fail(ctx, RTB_ERR_INVALID, "rtb_scene_upload: bad top-level record " + std::to_string(i)); }
+        if (!ok) { rtb_scene_free(ctx, s); return fail(ctx, RTB_ERR_INVALID, "rtb_scene_upload: bad top-level record " + std::to_string(i)); }
     }
-    if (tunnels > 1) { delete s; return fail(ctx, RTB_ERR_UNSUPPORTED, "rtb_scene_upload: one tunnel per scene"); }
+    if (tunnels > 1) { rtb_scene_free(ctx, s); return fail(ctx, RTB_ERR_UNSUPPORTED, "rtb_scene_upload: one tunnel per scene"); }
     s->has_tunnel = tunnels == 1;
     for (int i = 0; i < f->n_materials; i++)
     {
@@ -479,28 +587,28 @@ extern "C" int rtb_scene_upload(rtb_ctx *ctx, const rtb_flat_scene *f, rtb_scene
     }
 
     int rc = RTB_OK;
-    std::vector<float4> packed;
     auto bail = [&](int code) { rtb_scene_free(ctx, s); return code; };
+    laps.lap("header");
 
-    packTriangles(f->loose_tri, f->loose_tri ? (size_t)f->n_loose : 0, packed);
-    if ((rc = uploadArray(ctx, s, packed.data(), packed.size(), &d.loose)) != RTB_OK) return bail(rc);
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)); // `packed` is reused below
+    // every stream is packed / copied into the page-locked staging ring and leaves with an asynchronous copy:
+    // no intermediate synchronisation, the upload is ordered before the renders on ctx->stream
+    const size_t nLoose = f->loose_tri ? (size_t)f->n_loose : 0;
+    if ((rc = uploadTriangles(ctx, s, f->loose_tri, nLoose, &d.loose, nullptr)) != RTB_OK) return bail(rc);
 
     if (s->has_tunnel)
     {
         if (f->n_tris < 0 || (f->n_tris > 0 && (!f->tri || !f->tri_material)))
             return bail(fail(ctx, RTB_ERR_INVALID, "rtb_scene_upload: tunnel triangle streams missing"));
-        for (int i = 0; i < f->n_tris; i++)
-            if (f->tri_material[i] < 0 || f->tri_material[i] >= f->n_materials)
-                return bail(fail(ctx, RTB_ERR_INVALID, "rtb_scene_upload: triangle material out of range"));
-        packTriangles(f->tri, (size_t)f->n_tris, packed);
-        if ((rc = uploadArray(ctx, s, packed.data(), packed.size(), &d.tri)) != RTB_OK) return bail(rc);
-        std::vector<float4> packedPre;
-        packPreTriangles(f->tri, (size_t)f->n_tris, packedPre);
-        if ((rc = uploadArray(ctx, s, packedPre.data(), packedPre.size(), &d.tri_pre)) != RTB_OK) return bail(rc);
-        if ((rc = uploadArray(ctx, s, f->tri_material, (size_t)f->n_tris, &d.tri_material)) != RTB_OK) return bail(rc);
+        uint32_t maxMat = 0; // negative ids wrap to huge values
+        for (int i = 0; i < f->n_tris; i++) maxMat = (uint32_t)f->tri_material[i] > maxMat ? (uint32_t)f->tri_material[i] : maxMat;
+        if (f->n_tris > 0 && maxMat >= (uint32_t)f->n_materials)
+            return bail(fail(ctx, RTB_ERR_INVALID, "rtb_scene_upload: triangle material out of range"));
+        const size_t nTris = (size_t)f->n_tris;
+        laps.lap("loose+material check");
+        if ((rc = uploadTriangles(ctx, s, f->tri, nTris, &d.tri, &d.tri_pre)) != RTB_OK) return bail(rc);
+        if ((rc = uploadArray(ctx, s, f->tri_material, nTris, &d.tri_material)) != RTB_OK) return bail(rc);
         d.n_tris = f->n_tris;
-        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        laps.lap("triangle streams");
 
         if ((f->accel == RTB_ACCEL_REGULAR_GRID || f->accel == RTB_ACCEL_FLAT_GRID) && !f->grid_words && f->grid_build_resolution > 1)
         { // no grid arrays, a resolution: build it here, on the device
@@ -514,9 +622,10 @@ extern "C" int rtb_scene_upload(rtb_ctx *ctx, const rtb_flat_scene *f, rtb_scene
                 f->n_cellwords != (cells + 31) / 32 || !f->grid_words || !f->grid_cell_start ||
                 (f->n_cell_refs > 0 && !f->grid_cell_tris))
                 return bail(fail(ctx, RTB_ERR_INVALID, "rtb_scene_upload: inconsistent grid directory"));
-            for (int64_t i = 0; i < f->n_cell_refs; i++)
-                if (f->grid_cell_tris[i] >= (uint32_t)f->n_tris)
-                    return bail(fail(ctx, RTB_ERR_INVALID, "rtb_scene_upload: grid triangle reference out of range"));
+            uint32_t maxRef = 0;
+            for (int64_t i = 0; i < f->n_cell_refs; i++) maxRef = f->grid_cell_tris[i] > maxRef ? f->grid_cell_tris[i] : maxRef;
+            if (f->n_cell_refs > 0 && maxRef >= (uint32_t)f->n_tris)
+                return bail(fail(ctx, RTB_ERR_INVALID, "rtb_scene_upload: grid triangle reference out of range"));
             d.g_origin = {f->grid_origin[0], f->grid_origin[1], f->grid_origin[2]};
             d.g_cell = {f->grid_cell[0], f->grid_cell[1], f->grid_cell[2]};
             d.nx = f->grid_dims[0]; d.ny = f->grid_dims[1]; d.nz = f->grid_dims[2];
@@ -534,17 +643,27 @@ extern "C" int rtb_scene_upload(rtb_ctx *ctx, const rtb_flat_scene *f, rtb_scene
         {
             if (f->n_kd_nodes <= 0 || !f->kd_nodes || (f->n_kd_refs > 0 && !f->kd_leaf_tris))
                 return bail(fail(ctx, RTB_ERR_INVALID, "rtb_scene_upload: k-d tree missing"));
-            int maxDepth = 0, visited = 0;
-            if (kdDepth(f->kd_nodes, f->n_kd_nodes, 0, 0, maxDepth, visited) != 0 || visited != f->n_kd_nodes)
+            int maxDepth = 0;
+            laps.lap("pre-kd");
+            if (kdDepth(f->kd_nodes, f->n_kd_nodes, maxDepth) != 0)
                 return bail(fail(ctx, RTB_ERR_INVALID, "rtb_scene_upload: k-d nodes are not a pre-order tree"));
             if (2 * maxDepth + 2 >= RTB_KD_STACK)
                 return bail(fail(ctx, RTB_ERR_UNSUPPORTED, "rtb_scene_upload: k-d tree deeper than the 50-entry traversal stack allows"));
+            laps.lap("kdDepth");
+            // branch-free maxima (the compiler vectorises them): 69 k nodes + 380 k references per upload
+            int64_t leafEnd = 0;
             for (int i = 0; i < f->n_kd_nodes; i++)
-                if ((f->kd_nodes[i].b & 3u) == 3u && (int64_t)f->kd_nodes[i].a + (f->kd_nodes[i].b >> 2) > f->n_kd_refs)
-                    return bail(fail(ctx, RTB_ERR_INVALID, "rtb_scene_upload: k-d leaf range out of bounds"));
-            for (int64_t i = 0; i < f->n_kd_refs; i++)
-                if (f->kd_leaf_tris[i] >= (uint32_t)f->n_tris)
-                    return bail(fail(ctx, RTB_ERR_INVALID, "rtb_scene_upload: k-d triangle reference out of range"));
+            {
+                const int64_t e = ((f->kd_nodes[i].b & 3u) == 3u) ? (int64_t)f->kd_nodes[i].a + (f->kd_nodes[i].b >> 2) : 0;
+                leafEnd = e > leafEnd ? e : leafEnd;
+            }
+            if (leafEnd > f->n_kd_refs) return bail(fail(ctx, RTB_ERR_INVALID, "rtb_scene_upload: k-d leaf range out of bounds"));
+            laps.lap("leaf ranges");
+            uint32_t maxRef = 0;
+            for (int64_t i = 0; i < f->n_kd_refs; i++) maxRef = f->kd_leaf_tris[i] > maxRef ? f->kd_leaf_tris[i] : maxRef;
+            if (f->n_kd_refs > 0 && maxRef >= (uint32_t)f->n_tris)
+                return bail(fail(ctx, RTB_ERR_INVALID, "rtb_scene_upload: k-d triangle reference out of range"));
+            laps.lap("ref max");
             d.kd_min = {f->kd_min[0], f->kd_min[1], f->kd_min[2]};
             // reference Grid.cpp:13-17: Grid(near, far) keeps size = far - near
             d.kd_size = {f->kd_max[0] - f->kd_min[0], f->kd_max[1] - f->kd_min[1], f->kd_max[2] - f->kd_min[2]};
@@ -585,8 +704,12 @@ extern "C" int rtb_scene_upload(rtb_ctx *ctx, const rtb_flat_scene *f, rtb_scene
         else if (f->accel != RTB_ACCEL_LINEAR)
             return bail(fail(ctx, RTB_ERR_UNSUPPORTED, "rtb_scene_upload: unknown accelerator"));
     }
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    // no synchronisation: the copies are queued on ctx->stream ahead of anything that reads the scene; launches on
+    // another stream (rtb_render_device) wait for this event
+    laps.lap("accelerator");
+    CUDA_TRY(ctx, cudaEventRecord(s->ready, ctx->stream));
     s->signature = sceneSignature(f);
+    laps.lap("signature");
     s->long_lists = s->has_tunnel && f->accel == RTB_ACCEL_REGULAR_GRID && s->grid_cells_used > 0 && s->grid_refs >= 16 * s->grid_cells_used;
     *out = s;
     return RTB_OK;
@@ -604,6 +727,7 @@ extern "C" int rtb_scene_free(rtb_ctx *ctx, rtb_scene *s)
     else
         for (void *p : s->allocs) cudaFree(p);
     if (s->last_use) cudaEventDestroy(s->last_use);
+    if (s->ready) cudaEventDestroy(s->ready);
     delete s;
     return RTB_OK;
 }
@@ -804,8 +928,8 @@ static int prepareTileOrder(rtb_ctx *ctx, const rtb_scene *scene, FrameParams &F
         CUDA_TRY(ctx, cudaMalloc(&ctx->d_hist, RTB_COST_BUCKETS * sizeof(unsigned int)));
         CUDA_TRY(ctx, cudaMalloc(&ctx->d_cursor, RTB_COST_BUCKETS * sizeof(unsigned int)));
         CUDA_TRY(ctx, cudaMemset(ctx->d_hist, 0, RTB_COST_BUCKETS * sizeof(unsigned int)));
-        CUDA_TRY(ctx, cudaMalloc(&ctx->d_heavy, sizeof(unsigned int)));
-        CUDA_TRY(ctx, cudaMemset(ctx->d_heavy, 0, sizeof(unsigned int)));
+        CUDA_TRY(ctx, cudaMalloc(&ctx->d_heavy, 2 * sizeof(unsigned int))); // [0] latency-critical tiles, [1] floor bucket
+        CUDA_TRY(ctx, cudaMemset(ctx->d_heavy, 0, 2 * sizeof(unsigned int)));
     }
     // The order (and the per-tile costs behind it) belongs to one view of one scene: frame geometry, scene,
     // camera and depth setting.  A camera move keeps the order for one frame without the tiers (below); anything
@@ -837,6 +961,7 @@ static int prepareTileOrder(rtb_ctx *ctx, const rtb_scene *scene, FrameParams &F
 static int renderCommon(rtb_ctx *ctx, const rtb_scene *scene, FrameParams &F, const rtb_frame *frame, float *d_out,
                         cudaStream_t stream, rtb_stats *stats, float *h_out, bool sync = false)
 {
+    const bool host_frame = sync; // rtb_render's zero-copy path: d_out is the device alias of a page-locked host buffer
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     const size_t bytes = (size_t)F.n_local_rows * F.width * 3 * (F.rgb8 ? 1 : sizeof(float));
     if (F.n_local_rows == 0)
@@ -844,8 +969,12 @@ static int renderCommon(rtb_ctx *ctx, const rtb_scene *scene, FrameParams &F, co
         if (stats) { memset(stats, 0, sizeof(*stats)); }
         return RTB_OK;
     }
+    if (stream != ctx->stream) CUDA_TRY(ctx, cudaStreamWaitEvent(stream, scene->ready, 0)); // the upload ran on ctx->stream
     int rc = prepareTileOrder(ctx, scene, F);
     if (rc != RTB_OK) return rc;
+    // whole-tile 128-bit stores (storeTile): row-major frames whose 8-pixel row segments are 16-byte aligned
+    static const bool wideStore = !(getenv("RTB_WIDE_STORE") && atoi(getenv("RTB_WIDE_STORE")) == 0);
+    F.wide_store = wideStore && !F.layout && !F.cost_map && F.width % 4 == 0 && ((uintptr_t)d_out & 15u) == 0;
     if (stats || h_out || sync) CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], stream));
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(Counters), stream));
     if (stats) CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], stream));
@@ -860,12 +989,15 @@ static int renderCommon(rtb_ctx *ctx, const rtb_scene *scene, FrameParams &F, co
     { // heaviest-first order for the next frame of this geometry: counting sort of the recorded tile costs
         int blocks = (F.n_tiles + 1023) / 1024;
         if (blocks > 296) blocks = 296;
+        // frames stored straight into host memory order their light tiles by position (k_cost_offsets)
+        static const int floorDeltaHost = (int)tunable("RTB_FLOOR_DELTA_HOST", 9), floorDeltaDevice = (int)tunable("RTB_FLOOR_DELTA_DEVICE", 0);
+        const int floorDelta = host_frame ? floorDeltaHost : floorDeltaDevice;
         k_cost_histogram<<<blocks, 256, 0, stream>>>(ctx->d_cost, F.n_tiles, ctx->d_hist);
         const bool smallShard = F.n_tiles <= splitMaxTiles();
         k_cost_offsets<<<1, 32, 0, stream>>>(ctx->d_hist, ctx->d_cursor, ctx->d_heavy, F.n_tiles,
                                              smallShard ? heavyBucketsSmall() : RTB_HEAVY_BUCKETS,
-                                             heavyLimit(F.n_tiles), wideCount(F.n_tiles, scene->long_lists));
-        k_cost_scatter<<<blocks, 256, 0, stream>>>(ctx->d_cost, F.n_tiles, ctx->d_cursor, ctx->d_order);
+                                             heavyLimit(F.n_tiles), wideCount(F.n_tiles, scene->long_lists), floorDelta);
+        k_cost_scatter<<<blocks, 256, 0, stream>>>(ctx->d_cost, F.n_tiles, ctx->d_cursor, ctx->d_order, ctx->d_heavy);
         CUDA_TRY(ctx, cudaGetLastError());
         ctx->order_valid = true;
     }

@@ -51,6 +51,8 @@ k_whitted_chain_sm(const __grid_constant__ DScene S, const __grid_constant__ Fra
         const unsigned int warpIndex = blockIdx.x * (unsigned int)F.warps_per_cta + (threadIdx.x >> 5);
         if ((F.split4 ? (warpIndex >> 2) : warpIndex) + (F.after_wide ? F.n_wide : 0u) >= heavyCount(F)) return;
     }
+    __shared__ __align__(16) uint32_t stage[RTB_CTA_THREADS / 32][RTB_TILE_STAGE_WORDS];
+    V3 cOut = v3(0, 0, 0);
     if (active)
     {
         const float dx = 1.0f / F.height, dy = 1.0f / F.height;
@@ -306,8 +308,10 @@ k_whitted_chain_sm(const __grid_constant__ DScene S, const __grid_constant__ Fra
             const float4 f = fold[--nfold];
             c = v3(f.x, f.y, f.z) + c * f.w + zero * 0.0f;
         }
-        storePixel(F, out, x, lr, y, c, t_start, rays, pr);
+        cOut = c;
     }
+    // split4 launches give a tile to four warps of 8 lanes: per-pixel stores there
+    if ((F.split4 || !storeTile(F, out, tile, active, cOut, stage[threadIdx.x >> 5])) && active) storePixel(F, out, x, lr, y, cOut, t_start, rays, pr);
     finishWarp(F, counters, tile, t_start, rays, ProbeCounts<Probe>::tris(pr), ProbeCounts<Probe>::steps(pr));
 }
 

@@ -23,6 +23,7 @@ struct FrameParams
     int n_local_rows;
     int cost_map;
     int rgb8; // RTB_OUTPUT_RGB8
+    int wide_store; // row-major output, 16-byte aligned rows: full tiles leave through storeTile()
     int tiles_x, n_tiles;
     const unsigned int *order; // [n_tiles] tile ids, heaviest first; nullptr = raster order
     unsigned int *cost;        // [n_tiles] cycles >> 6 the throughput kernel last spent on each tile; may be nullptr
@@ -105,6 +106,38 @@ __device__ __forceinline__ void storeColor(const FrameParams &F, float *out, int
     }
 }
 
+// Whole-tile store of the throughput kernels.  A warp owns an 8x4 tile; written pixel by pixel each of its four
+// 96-byte row segments leaves as 3 x 8 scalar stores that touch every 32-byte sector three times -- harmless in
+// HBM, but when the kernels store straight into the caller's page-locked host frame every partial sector is its
+// own PCIe write.  Here the 96 colour floats pass through 384 bytes of shared memory and leave as 24 128-bit
+// stores, each sector written once (8-bit frames: 24 32-bit stores).  Returns false when the tile is ragged or
+// the layout is not row-major / aligned: the caller then stores per pixel.
+__device__ __forceinline__ bool storeTile(const FrameParams &F, float *out, unsigned int tile, bool active, V3 c, uint32_t *stage)
+{
+    if (!F.wide_store || !__all_sync(0xffffffffu, active)) return false;
+    const int lane = threadIdx.x & 31;
+    const int ty = tile / F.tiles_x, tx = tile - ty * F.tiles_x;
+    const int row = lane / 6, j = lane - row * 6; // lanes 0..23: row 0..3, 16-byte (4-byte) chunk 0..5 of the row segment
+    const size_t rowSlot = (size_t)(ty * RTB_TILE_H + row) * F.width + (size_t)tx * RTB_TILE_W;
+    if (F.rgb8)
+    {
+        unsigned char *sb = reinterpret_cast<unsigned char *>(stage);
+        const float r = (c.x > 1.0f) ? 1.0f : c.x, g = (c.y > 1.0f) ? 1.0f : c.y, b = (c.z > 1.0f) ? 1.0f : c.z;
+        sb[3 * lane + 0] = (unsigned char)f2i(r * 255); sb[3 * lane + 1] = (unsigned char)f2i(g * 255); sb[3 * lane + 2] = (unsigned char)f2i(b * 255);
+        __syncwarp();
+        if (lane < 24) *reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(out) + 3 * rowSlot + 4 * j) = stage[lane];
+    }
+    else
+    {
+        float *sf = reinterpret_cast<float *>(stage);
+        sf[3 * lane + 0] = c.x; sf[3 * lane + 1] = c.y; sf[3 * lane + 2] = c.z;
+        __syncwarp();
+        if (lane < 24) *reinterpret_cast<float4 *>(out + 3 * rowSlot + 4 * j) = reinterpret_cast<const float4 *>(stage)[lane];
+    }
+    return true;
+}
+#define RTB_TILE_STAGE_WORDS 96
+
 // per-warp epilogue: record the tile's cost, add the warp's counters to the frame totals
 __device__ __forceinline__ void finishWarp(const FrameParams &F, Counters *g, unsigned int tile, long long t_start,
                                            unsigned int rays, unsigned int tris, unsigned int steps)
@@ -153,17 +186,37 @@ __global__ void k_cost_histogram(const unsigned int *__restrict__ cost, int n, u
 //   n_heavy[0]  those plus the tiles within `heavy_buckets` quarter-octaves of the heaviest tile that is NOT in
 //               the first set, at most heavy_limit of them: resumable
 //               traversal (rtb_chain_sm.cuh).
+// n_heavy[1] = FLOOR BUCKET of the order: every tile in a bucket at or below it is "light" and is placed in one
+// common bucket, i.e. (nearly) in raster order instead of by cost.  With floor_delta > 0 the floor lies that many
+// quarter-octaves above the median tile (9: tiles up to ~4.8x the median are light).  Heaviest-first only matters
+// for the tiles that can stretch the end of the kernel; among the light ones raster order keeps neighbouring tiles
+// -- neighbouring framebuffer rows -- in flight together.  When the kernels store straight into the caller's
+// page-locked host frame that is what lets the 96-byte row segments of adjacent tiles combine into long PCIe
+// writes: 4K SAH frame 6.95 -> 5.79 ms with the floor, against 5.48 ms into HBM (profiles/r01_e2e_floor_bucket.log).
+// Frames rendered into device memory keep floor_delta = 0 (pure heaviest-first is 3 % faster there).
 __global__ void k_cost_offsets(unsigned int *__restrict__ hist, unsigned int *__restrict__ cursor, unsigned int *__restrict__ n_heavy,
-                               int n_tiles, int heavy_buckets, int heavy_limit, int wide_count)
+                               int n_tiles, int heavy_buckets, int heavy_limit, int wide_count, int floor_delta)
 {
     if (threadIdx.x == 0)
     {
+        int floorBucket = 0;
+        if (floor_delta > 0)
+        {
+            unsigned int below = 0;
+            int median = 0;
+            for (int b = 0; b < RTB_COST_BUCKETS; b++)
+            {
+                below += hist[b];
+                if (2u * below >= (unsigned int)n_tiles) { median = b; break; }
+            }
+            floorBucket = min(median + floor_delta, RTB_COST_BUCKETS - 1);
+        }
         const unsigned int wide = (unsigned int)min(wide_count, n_tiles);
         unsigned int run = 0, heavy = wide;
         int top2 = -1; // bucket of the heaviest tile outside the wide set
         for (int b = RTB_COST_BUCKETS - 1; b >= 0; b--)
         {
-            cursor[b] = run;
+            if (b >= floorBucket) cursor[b] = run; // buckets below the floor are placed through cursor[floorBucket]
             run += hist[b];
             if (top2 < 0 && run > wide) top2 = b;
             if (top2 >= 0 && b >= top2 - heavy_buckets) heavy = run;
@@ -174,6 +227,7 @@ __global__ void k_cost_offsets(unsigned int *__restrict__ hist, unsigned int *__
         // would leave no latency-critical set at all
         if (heavy - wide > (unsigned int)heavy_limit) heavy = wide + (unsigned int)heavy_limit;
         n_heavy[0] = heavy;
+        n_heavy[1] = (unsigned int)floorBucket;
     }
 }
 
@@ -181,14 +235,15 @@ __global__ void k_cost_offsets(unsigned int *__restrict__ hist, unsigned int *__
 // range of every bucket with ONE global atomic per bucket, then place the tiles with shared-memory
 // atomics (the naive per-tile global atomic took 146 us on the 345,600 tiles of a 4K frame).
 __global__ void k_cost_scatter(const unsigned int *__restrict__ cost, int n, unsigned int *__restrict__ cursor,
-                               unsigned int *__restrict__ order)
+                               unsigned int *__restrict__ order, const unsigned int *__restrict__ n_heavy)
 {
+    const int floor_bucket = (int)n_heavy[1]; // written by k_cost_offsets just before this launch
     __shared__ unsigned int cnt[RTB_COST_BUCKETS], base[RTB_COST_BUCKETS];
     const int per = (n + gridDim.x - 1) / gridDim.x;
     const int begin = blockIdx.x * per, end = min(begin + per, n);
     for (int i = threadIdx.x; i < RTB_COST_BUCKETS; i += blockDim.x) cnt[i] = 0;
     __syncthreads();
-    for (int i = begin + threadIdx.x; i < end; i += blockDim.x) atomicAdd(&cnt[costBucket(cost[i])], 1u);
+    for (int i = begin + threadIdx.x; i < end; i += blockDim.x) atomicAdd(&cnt[max(costBucket(cost[i]), floor_bucket)], 1u);
     __syncthreads();
     for (int i = threadIdx.x; i < RTB_COST_BUCKETS; i += blockDim.x)
     {
@@ -198,7 +253,7 @@ __global__ void k_cost_scatter(const unsigned int *__restrict__ cost, int n, uns
     __syncthreads();
     for (int i = begin + threadIdx.x; i < end; i += blockDim.x)
     {
-        const int b = costBucket(cost[i]);
+        const int b = max(costBucket(cost[i]), floor_bucket);
         order[base[b] + atomicAdd(&cnt[b], 1u)] = (unsigned int)i;
     }
 }
@@ -300,11 +355,10 @@ k_whitted_chain(const __grid_constant__ DScene S, const __grid_constant__ FrameP
     unsigned int rays = 0;
     Probe pr;
     if (F.skip_heavy && blockIdx.x * (unsigned int)F.warps_per_cta + (threadIdx.x >> 5) < heavyCount(F)) return;
-    if (active)
-    {
-        const V3 c = chainPerRay(S, F, x, y, rays, pr);
-        storePixel(F, out, x, lr, y, c, t_start, rays, pr);
-    }
+    __shared__ __align__(16) uint32_t stage[RTB_CTA_THREADS / 32][RTB_TILE_STAGE_WORDS];
+    V3 c = v3(0, 0, 0);
+    if (active) c = chainPerRay(S, F, x, y, rays, pr);
+    if (!storeTile(F, out, tile, active, c, stage[threadIdx.x >> 5]) && active) storePixel(F, out, x, lr, y, c, t_start, rays, pr);
     finishWarp(F, counters, tile, t_start, rays, ProbeCounts<Probe>::tris(pr), ProbeCounts<Probe>::steps(pr));
 }
 

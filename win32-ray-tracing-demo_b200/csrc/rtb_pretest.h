@@ -64,8 +64,10 @@ struct PreTri
     float e2x, e2y, e2z, pad;
 };
 
-// a, b, c as the 9 leading floats of the 12-float triangle record of include/rtb.h
-inline PreTri makePreTri(const float *t)
+// a, b, c as the 9 leading floats of the 12-float triangle record of include/rtb.h.  Host + device: the upload
+// packs on the GPU (k_pack_triangles), the CPU checker of tests/ on the host -- IEEE double arithmetic without
+// contraction on both sides (-fmad=false / -ffp-contract=off), hence the same constants
+RTB_PRE_FN PreTri makePreTri(const float *t)
 {
     PreTri p;
     p.ax = t[0]; p.ay = t[1]; p.az = t[2];
