@@ -253,6 +253,13 @@ int rtb_bounce_rays(rtb_ctx *ctx, const rtb_scene *scene, int64_t n, const float
                     int32_t *reached, int32_t *depth, int32_t *last_id, float *last_pos, int64_t *total_rays,
                     float *kernel_ms);
 
+/* Self-test of the list scans' rejection test (csrc/rtb_pretest.h): n random (ray, triangle) pairs -- triangles of
+ * widely varying size, slivers, rays aimed at the triangle's boundary -- are decided by the scalar function (the one
+ * tests/ checks against the oracle on the CPU) and by the packed-FP32 two-triangle variant the kernels run;
+ * *mismatches = pairs on which the two disagree (must be 0), *rejected = pairs the test rejects (so a caller can see
+ * that both outcomes occur).  No reference counterpart: diagnostic entry point.                                     */
+int rtb_selftest_pretest(rtb_ctx *ctx, int64_t n, uint64_t seed, int64_t *mismatches, int64_t *rejected);
+
 #ifdef __cplusplus
 }
 #endif

@@ -643,3 +643,18 @@ def test_performance_test_program_golden(ctx, case):
         g = rtb200.perf_test(gold["xy"], *cases[case], alg)
         for k in ("reached", "depth", "last_id", "last_pos"):
             assert np.array_equal(_bits(g[k]), _bits(gold[f"{case}.{alg}.{k}"])), (alg, k)
+
+
+@pytest.mark.gpu
+def test_packed_pretest_equals_scalar(ctx):
+    """The kernels decide two triangles per call on the packed FP32 pipe (rtb_pretest.h: sureReject2); each half must
+    take, bit for bit, the decision of the scalar sureReject that tests/test_pretest.py checks against the oracle."""
+    import ctypes as C
+    lib = rtb200.cuda_lib()
+    lib.rtb_selftest_pretest.argtypes = [C.c_void_p, C.c_int64, C.c_uint64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    mism, rej = C.c_int64(-1), C.c_int64(-1)
+    n = 20_000_000
+    rc = lib.rtb_selftest_pretest(ctx._h, n, 20261018, C.byref(mism), C.byref(rej))
+    assert rc == 0
+    assert mism.value == 0
+    assert 0.05 * n < rej.value < 0.95 * n  # both outcomes are exercised

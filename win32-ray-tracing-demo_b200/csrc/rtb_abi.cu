@@ -367,6 +367,34 @@ static int uploadTriangles(rtb_ctx *ctx, rtb_scene *s, const float *host, size_t
     return RTB_OK;
 }
 
+// Pair stream (DScene::pre2): the rejection-test records of list positions 2p and 2p + 1, interleaved component by
+// component so that the 128-bit loads of the scan deliver 64-bit register pairs for the packed FP32 instructions.
+// One thread per list position; the unused half of a trailing odd pair is zero (allocation is cleared).
+__global__ void k_pack_pairs(const uint32_t *__restrict__ refs, unsigned int n_refs, const float4 *__restrict__ tri_pre,
+                             float *__restrict__ pre2)
+{
+    const unsigned int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_refs) return;
+    const float4 *src = tri_pre + 3ull * refs[j];
+    const float4 q0 = src[0], q1 = src[1], q2 = src[2]; // {a.xyz, A1e} {e1.xyz, Ee} {e2.xyz, 0}
+    float *dst = pre2 + 24ull * (j >> 1) + (j & 1u);
+    dst[0] = q0.x; dst[2] = q0.y; dst[4] = q0.z; dst[6] = q0.w;
+    dst[8] = q1.x; dst[10] = q1.y; dst[12] = q1.z; dst[14] = q1.w;
+    dst[16] = q2.x; dst[18] = q2.y; dst[20] = q2.z; dst[22] = 0.f;
+}
+
+// builds DScene::pre2 for the reference array `refs` (device) -- queued behind the copies / kernels that produce it
+static int packPairs(rtb_ctx *ctx, rtb_scene *s, const uint32_t *refs, size_t n_refs)
+{
+    const size_t pairs = (n_refs + 1) / 2;
+    int rc = uploadWith<float4>(ctx, s, 6 * pairs, &s->d.pre2, [](float4 *) {}, true); // zero-filled allocation
+    if (rc != RTB_OK || n_refs == 0) return rc;
+    k_pack_pairs<<<(unsigned int)((n_refs + 255) / 256), 256, 0, ctx->stream>>>(refs, (unsigned int)n_refs, s->d.tri_pre,
+                                                                                reinterpret_cast<float *>(const_cast<float4 *>(s->d.pre2)));
+    CUDA_TRY(ctx, cudaGetLastError());
+    return RTB_OK;
+}
+
 // pre-order k-d array -> 0 when it is a well-formed tree (every inner node's right child lies behind its left
 // subtree, every node reached exactly once), maxDepth = deepest node.  One linear pass with an explicit stack of
 // pending right children: the recursive walk took 0.2 ms of every upload.
@@ -525,7 +553,7 @@ static int buildGridOnDevice(rtb_ctx *ctx, rtb_scene *s, const rtb_flat_scene *f
     d.g_far = {d.g_origin.x + d.g_extent.x, d.g_origin.y + d.g_extent.y, d.g_origin.z + d.g_extent.z};
     d.g_words = d_words; d.g_start = d_cell_start; d.g_tris = d_cell_tris;
     s->grid_cells_used = nRuns; s->grid_refs = total; s->grid_words = nWords;
-    return RTB_OK;
+    return packPairs(ctx, s, d_cell_tris, (size_t)total);
 }
 
 // Index / structure checks of rtb_scene_upload that scan whole streams (k-d nodes, leaf and cell references: 0.6 ms
@@ -655,6 +683,12 @@ extern "C" int rtb_scene_upload(rtb_ctx *ctx, const rtb_flat_scene *f, rtb_scene
                 (f->n_cell_refs > 0 && !f->grid_cell_tris))
                 return bail(fail(ctx, RTB_ERR_INVALID, "rtb_scene_upload: inconsistent grid directory"));
             checks.run([f]() {
+                uint32_t maxStart = 0;
+                for (int64_t i = 0; i <= f->n_cells_used; i++) maxStart = f->grid_cell_start[i] > maxStart ? f->grid_cell_start[i] : maxStart;
+                const bool bad = f->n_cells_used < 0 || (int64_t)maxStart > f->n_cell_refs;
+                return std::make_pair(bad ? (int)RTB_ERR_INVALID : (int)RTB_OK, "rtb_scene_upload: grid cell list out of range");
+            });
+            checks.run([f]() {
                 uint32_t maxRef = 0; // branch-free maximum: the compiler vectorises it (up to 6.4 M references)
                 for (int64_t i = 0; i < f->n_cell_refs; i++) maxRef = f->grid_cell_tris[i] > maxRef ? f->grid_cell_tris[i] : maxRef;
                 const bool bad = f->n_cell_refs > 0 && maxRef >= (uint32_t)f->n_tris;
@@ -671,6 +705,7 @@ extern "C" int rtb_scene_upload(rtb_ctx *ctx, const rtb_flat_scene *f, rtb_scene
             d.g_words = words;
             if ((rc = uploadArray(ctx, s, f->grid_cell_start, (size_t)f->n_cells_used + 1, &d.g_start)) != RTB_OK) return bail(rc);
             if ((rc = uploadArray(ctx, s, f->grid_cell_tris, (size_t)f->n_cell_refs, &d.g_tris)) != RTB_OK) return bail(rc);
+            if ((rc = packPairs(ctx, s, d.g_tris, (size_t)f->n_cell_refs)) != RTB_OK) return bail(rc);
             s->grid_cells_used = f->n_cells_used; s->grid_refs = f->n_cell_refs; s->grid_words = f->n_cellwords;
         }
         else if (f->accel == RTB_ACCEL_KD_MEDIAN || f->accel == RTB_ACCEL_KD_SAH)
@@ -707,6 +742,7 @@ extern "C" int rtb_scene_upload(rtb_ctx *ctx, const rtb_flat_scene *f, rtb_scene
             if ((rc = uploadArray(ctx, s, (const uint2 *)f->kd_nodes, (size_t)f->n_kd_nodes, &nodes)) != RTB_OK) return bail(rc);
             d.kd_nodes = nodes;
             if ((rc = uploadArray(ctx, s, f->kd_leaf_tris, (size_t)f->n_kd_refs, &d.kd_tris)) != RTB_OK) return bail(rc);
+            if ((rc = packPairs(ctx, s, d.kd_tris, (size_t)f->n_kd_refs)) != RTB_OK) return bail(rc);
         }
         else if (f->accel == RTB_ACCEL_CONVEX || f->accel == RTB_ACCEL_CONVEX_SIMPLE)
         {
@@ -1072,11 +1108,16 @@ extern "C" int rtb_render(rtb_ctx *ctx, const rtb_scene *scene, const rtb_camera
     { // Page-locked output buffer (rtb_host_alloc / cudaHostAlloc / cudaHostRegister): the kernels store the pixels
       // straight into it over PCIe while they render, instead of a device framebuffer and a copy after the last
       // kernel.  Measured on the 4K SAH frame (scene upload + render + frame in host memory): 9.71 -> 8.77 ms; the
-      // kernels slow down 6.06 -> 7.47 ms under PCIe back-pressure but the 2.4 ms copy is gone.  Float frames only:
-      // the 8-bit output stage writes 24-byte row segments, too small for PCIe (7.91 ms staged, 8.82 ms direct).
+      // kernels slowed down 6.06 -> 7.47 ms under PCIe back-pressure but the 2.4 ms copy was gone; with whole-tile
+      // stores and the light tiles in raster order (k_cost_offsets) the slow-down is 5.48 -> 5.75 ms.
         static const bool zerocopy = !(getenv("RTB_ZEROCOPY") && atoi(getenv("RTB_ZEROCOPY")) == 0);
         cudaPointerAttributes attr;
-        if (zerocopy && !F.cost_map && !F.rgb8 && cudaPointerGetAttributes(&attr, rgb_out) == cudaSuccess && attr.type == cudaMemoryTypeHost &&
+        // 8-bit frames too, provided the tiles leave through storeTile (row-major, width % 4 == 0): 32-bit stores of
+        // whole 24-byte row segments with the light tiles in raster order (6.72 -> 6.33 ms); written byte by byte
+        // they were slower than a device frame + copy (8.82 vs 7.91 ms)
+        static const bool zerocopy8 = !(getenv("RTB_ZEROCOPY_RGB8") && atoi(getenv("RTB_ZEROCOPY_RGB8")) == 0);
+        const bool rgb8Direct = zerocopy8 && !F.layout && F.width % 4 == 0;
+        if (zerocopy && !F.cost_map && (!F.rgb8 || rgb8Direct) && cudaPointerGetAttributes(&attr, rgb_out) == cudaSuccess && attr.type == cudaMemoryTypeHost &&
             attr.devicePointer)
             return renderCommon(ctx, scene, F, frame, (float *)attr.devicePointer, ctx->stream, stats, nullptr, true);
         cudaGetLastError(); // pageable memory: cudaPointerGetAttributes may leave an error behind on older drivers
@@ -1235,5 +1276,79 @@ extern "C" int rtb_bounce_rays(rtb_ctx *ctx, const rtb_scene *scene, int64_t n, 
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     if (total_rays) *total_rays = (int64_t)total;
     if (kernel_ms) CUDA_TRY(ctx, cudaEventElapsedTime(kernel_ms, ctx->ev[1], ctx->ev[2]));
+    return RTB_OK;
+}
+
+// ---- self-test of the packed rejection test -------------------------------------------------------------------
+__device__ __forceinline__ float selftestUniform(unsigned long long &state)
+{ // splitmix64 -> [0, 1)
+    state += 0x9e3779b97f4a7c15ull;
+    unsigned long long z = state;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    z ^= z >> 31;
+    return (float)(z >> 40) * (1.0f / 16777216.0f);
+}
+
+__device__ __forceinline__ rtb_pre::PreTri selftestTriangle(unsigned long long &st, float &scale)
+{
+    scale = powf(10.0f, -3.0f + 7.0f * selftestUniform(st));
+    const float aspect = powf(10.0f, -3.0f * selftestUniform(st));
+    const float offset = selftestUniform(st) < 0.5f ? 0.0f : powf(10.0f, 5.0f * selftestUniform(st)) - 1.0f;
+    float t[12];
+    for (int k = 0; k < 3; k++) t[k] = offset * (k == 2 ? -1.0f : 1.0f) + scale * (selftestUniform(st) - 0.5f);
+    for (int k = 0; k < 3; k++) t[3 + k] = t[k] + scale * (selftestUniform(st) - 0.5f);
+    for (int k = 0; k < 3; k++) t[6 + k] = t[k] + scale * aspect * (selftestUniform(st) - 0.5f);
+    t[9] = 0; t[10] = 1; t[11] = 0;
+    return rtb_pre::makePreTri(t);
+}
+
+__global__ void k_selftest_pretest(long long n, unsigned long long seed, unsigned long long *mismatches, unsigned long long *rejected)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long st = seed * 0x2545f4914f6cdd1dull + (unsigned long long)i * 0x9e3779b97f4a7c15ull;
+    float s0, s1;
+    const rtb_pre::PreTri A = selftestTriangle(st, s0), B = selftestTriangle(st, s1);
+    // a ray through a point near the boundary of A (B sees an unrelated ray: mostly rejects, sometimes not)
+    const float be = selftestUniform(st) * 1.2f - 0.1f, ga = (selftestUniform(st) < 0.5f) ? (selftestUniform(st) - 0.5f) * 2e-3f : selftestUniform(st) * 1.2f - 0.1f;
+    const float tx = A.ax - A.e1x * be - A.e2x * ga, ty = A.ay - A.e1y * be - A.e2y * ga, tz = A.az - A.e1z * be - A.e2z * ga;
+    float dx = selftestUniform(st) - 0.5f, dy = selftestUniform(st) - 0.5f, dz = selftestUniform(st) - 0.5f;
+    const float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz + 1e-30f);
+    dx *= inv; dy *= inv; dz *= inv;
+    const float dist = s0 * powf(10.0f, -2.0f + 5.0f * selftestUniform(st));
+    const float ox = tx - dx * dist, oy = ty - dy * dist, oz = tz - dz * dist;
+    const float dmx = rtb_pre::dirMax(dx, dy, dz);
+    const float lo = selftestUniform(st) < 0.5f ? -FLT_MAX : dist * (1.0f - 1e-3f * selftestUniform(st));
+    const float hi = selftestUniform(st) < 0.5f ? FLT_MAX : dist * (1.0f + 1e-3f * selftestUniform(st));
+    const float Lp = rtb_pre::lowBound(lo), Hp = rtb_pre::highBound(hi, FLT_MAX);
+    rtb_pre::PreTri2 P;
+    P.ax = make_float2(A.ax, B.ax); P.ay = make_float2(A.ay, B.ay); P.az = make_float2(A.az, B.az); P.a1e = make_float2(A.a1e, B.a1e);
+    P.e1x = make_float2(A.e1x, B.e1x); P.e1y = make_float2(A.e1y, B.e1y); P.e1z = make_float2(A.e1z, B.e1z); P.ee = make_float2(A.ee, B.ee);
+    P.e2x = make_float2(A.e2x, B.e2x); P.e2y = make_float2(A.e2y, B.e2y); P.e2z = make_float2(A.e2z, B.e2z);
+    bool r0, r1, q0, q1;
+    rtb_pre::sureReject2<true>(P, ox, oy, oz, dx, dy, dz, dmx, Lp, Hp, r0, r1);
+    rtb_pre::sureReject2<false>(P, ox, oy, oz, dx, dy, dz, dmx, Lp, Hp, q0, q1);
+    const bool s0h = rtb_pre::sureReject<true>(A, ox, oy, oz, dx, dy, dz, dmx, Lp, Hp), s1h = rtb_pre::sureReject<true>(B, ox, oy, oz, dx, dy, dz, dmx, Lp, Hp);
+    const bool s0l = rtb_pre::sureReject<false>(A, ox, oy, oz, dx, dy, dz, dmx, Lp, Hp), s1l = rtb_pre::sureReject<false>(B, ox, oy, oz, dx, dy, dz, dmx, Lp, Hp);
+    const unsigned int bad = (r0 != s0h) + (r1 != s1h) + (q0 != s0l) + (q1 != s1l);
+    if (bad) atomicAdd(mismatches, (unsigned long long)bad);
+    if (s0h) atomicAdd(rejected, 1ull);
+}
+
+extern "C" int rtb_selftest_pretest(rtb_ctx *ctx, int64_t n, uint64_t seed, int64_t *mismatches, int64_t *rejected)
+{
+    if (!ctx || n <= 0 || !mismatches || !rejected) return fail(ctx, RTB_ERR_INVALID, "rtb_selftest_pretest: bad argument");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    DevBuf<unsigned long long> d;
+    CUDA_TRY(ctx, d.alloc(2));
+    CUDA_TRY(ctx, cudaMemsetAsync(d.p, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    k_selftest_pretest<<<(unsigned int)((n + 255) / 256), 256, 0, ctx->stream>>>((long long)n, (unsigned long long)seed, d.p, d.p + 1);
+    CUDA_TRY(ctx, cudaGetLastError());
+    unsigned long long h[2] = {0, 0};
+    CUDA_TRY(ctx, cudaMemcpyAsync(h, d.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    *mismatches = (int64_t)h[0];
+    *rejected = (int64_t)h[1];
     return RTB_OK;
 }

@@ -81,7 +81,7 @@ k_whitted_chain_sm(const __grid_constant__ DScene S, const __grid_constant__ Fra
         int hitTri = -1;
         // conservative rejection test: per-ray / per-list constants, pending candidate, end of the exact scan
         float dmx = 0, Lp = rtb_pre::lowBound(-FLT_MAX), Hp = rtb_pre::highBound(FLT_MAX, FLT_MAX);
-        unsigned int pend = 0xffffffffu, jend = 0;
+        unsigned int pend = 0xffffffffu, jend = 0, lp = 0, counted = 0; // lp: current pair of the list [li, lend)
         bool tunnelHit = false;
 
         // start the accelerator walk of ray r (reference Tunnel.cpp:1171-1197 / 833-860)
@@ -180,8 +180,9 @@ k_whitted_chain_sm(const __grid_constant__ DScene S, const __grid_constant__ Fra
                             const unsigned int rk = w.y + __popc(w.x & (bit - 1));
                             li = __ldg(S.g_start + rk);
                             lend = __ldg(S.g_start + rk + 1);
-                            minD = FLT_MAX; hitTri = -1; pend = 0xffffffffu;
-                            st = SM_LEAF;
+                            minD = FLT_MAX; hitTri = -1; pend = 0xffffffffu; lp = li >> 1;
+                            if (li == lend) gridAdvance(); // cannot happen with a well-formed directory; the pair loop needs a non-empty list
+                            else st = SM_LEAF;
                         }
                         else gridAdvance();
                     }
@@ -195,7 +196,7 @@ k_whitted_chain_sm(const __grid_constant__ DScene S, const __grid_constant__ Fra
                             lend = nd.x + (nd.y >> 2);
                             lo = enT - 0.001f; hi = exT + 0.001f;
                             Lp = rtb_pre::lowBound(lo); Hp = rtb_pre::highBound(hi, FLT_MAX);
-                            minD = FLT_MAX; hitTri = -1; pend = 0xffffffffu;
+                            minD = FLT_MAX; hitTri = -1; pend = 0xffffffffu; lp = li >> 1;
                             if (li == lend) kdPop();
                             else st = SM_LEAF;
                         }
@@ -231,32 +232,43 @@ k_whitted_chain_sm(const __grid_constant__ DScene S, const __grid_constant__ Fra
                 }
             }
             if (st == SM_LEAF)
-            {
+            { // two list entries per iteration from the pair stream (see nearestInList)
 #pragma unroll 1
                 for (int burst = 0; burst < RTB_SM_LEAF_BURST && st == SM_LEAF; burst++)
                 {
-                    const uint32_t idx = __ldg((GRID ? S.g_tris : S.kd_tris) + li);
-                    const rtb_pre::PreTri P = loadPreTri(S.tri_pre, idx);
-                    pr.tri();
-                    if (!rtb_pre::sureReject<!GRID>(P, r.o.x, r.o.y, r.o.z, r.d.x, r.d.y, r.d.z, dmx, Lp, Hp))
+                    const rtb_pre::PreTri2 P = loadPreTri2(S.pre2, lp);
+                    const unsigned int j0 = 2u * lp, j1 = j0 + 1u;
+                    const bool in0 = j0 >= li, in1 = j1 < lend;
+                    if (in0) pr.tri();
+                    if (in1) pr.tri();
+                    bool r0, r1;
+                    rtb_pre::sureReject2<!GRID>(P, r.o.x, r.o.y, r.o.z, r.d.x, r.d.y, r.d.z, dmx, Lp, Hp, r0, r1);
+                    const bool c0 = in0 && !r0, c1 = in1 && !r1;
+                    if (c0 || c1)
                     { // candidate: its exact test waits for the end of the list, unless one is waiting already
-                        if (pend != 0xffffffffu) { jend = lend; st = SM_EXACT; }
-                        else pend = li;
+                        if (pend != 0xffffffffu || (c0 && c1))
+                        {
+                            if (pend == 0xffffffffu) pend = j0;
+                            counted = in1 ? j1 + 1u : j1;
+                            jend = lend;
+                            st = SM_EXACT;
+                        }
+                        else pend = c0 ? j0 : j1;
                     }
-                    if (st == SM_LEAF && ++li == lend)
+                    if (st == SM_LEAF && ++lp == ((lend + 1u) >> 1))
                     {
-                        if (pend != 0xffffffffu) { jend = pend + 1; st = SM_EXACT; }
+                        if (pend != 0xffffffffu) { counted = lend; jend = pend + 1; st = SM_EXACT; }
                         else listDone();
                     }
                 }
             }
             if (st == SM_EXACT)
-            { // [pend, jend) in list order; entries behind li (where the fast scan stopped) are counted here
+            { // [pend, jend) in list order; entries the fast scan has not reached are counted here
                 for (unsigned int j = pend; j < jend; j++)
                 {
                     const uint32_t idx = __ldg((GRID ? S.g_tris : S.kd_tris) + j);
                     const TriData T = loadTri(S.tri, idx);
-                    if (j > li) pr.tri();
+                    if (j >= counted) pr.tri();
                     float t;
                     if (triIntersectT<true>(T, r, t) && (GRID || (t >= lo && t <= hi)) && t < minD)
                     {

@@ -62,6 +62,10 @@ struct DScene
     // the same triangles for the conservative rejection test (rtb_pretest.h): 3 x float4 = {a.xyz, A1 eps}
     // {e1.xyz, E eps} {e2.xyz, 0}; the per-lane list scans read THIS stream and touch `tri` only for candidates
     const float4 *tri_pre;
+    // PAIR stream of the active accelerator's reference array (kd_tris or g_tris): for positions 2p and 2p + 1 six
+    // float4 with the two triangles' rejection-test records interleaved component by component (rtb_pretest.h:
+    // PreTri2, k_pack_pairs) -- what the packed FP32 scan reads, without index indirection.  null: linear / convex
+    const float4 *pre2;
     const int *tri_material;
     int n_tris;
     // grid
@@ -146,6 +150,17 @@ __device__ __forceinline__ rtb_pre::PreTri loadPreTri(const float4 *base, unsign
     t.ax = q0.x; t.ay = q0.y; t.az = q0.z; t.a1e = q0.w;
     t.e1x = q1.x; t.e1y = q1.y; t.e1z = q1.z; t.ee = q1.w;
     t.e2x = q2.x; t.e2y = q2.y; t.e2z = q2.z; t.pad = 0.f;
+    return t;
+}
+
+__device__ __forceinline__ rtb_pre::PreTri2 loadPreTri2(const float4 *base, unsigned int pair)
+{
+    const float4 *p = base + 6ull * pair;
+    const float4 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2), q3 = __ldg(p + 3), q4 = __ldg(p + 4), q5 = __ldg(p + 5);
+    rtb_pre::PreTri2 t;
+    t.ax = make_float2(q0.x, q0.y); t.ay = make_float2(q0.z, q0.w); t.az = make_float2(q1.x, q1.y); t.a1e = make_float2(q1.z, q1.w);
+    t.e1x = make_float2(q2.x, q2.y); t.e1y = make_float2(q2.z, q2.w); t.e1z = make_float2(q3.x, q3.y); t.ee = make_float2(q3.z, q3.w);
+    t.e2x = make_float2(q4.x, q4.y); t.e2y = make_float2(q4.z, q4.w); t.e2z = make_float2(q5.x, q5.y);
     return t;
 }
 
@@ -245,37 +260,52 @@ __device__ __forceinline__ bool nearestInList(const DScene &S, const uint32_t *r
     else
     {
         // Per-lane scan.  Every list entry first meets the conservative rejection test (rtb_pretest.h: the four
-        // determinants by two cross products with FMA, no division, plus an error bound -- about half the
-        // instructions of the exact test, and no data-dependent branch).  It never accepts: an entry it cannot
-        // reject is a CANDIDATE and takes the reference's exact test, so results are bit-identical.  Candidates are
-        // essentially the ray's real hits (1.06-1.6 per ray, profiles/r01_pretest_stats.md), so their exact test
-        // is DEFERRED to the end of the list: inside the loop it would be executed -- by warp union -- in most
-        // iterations for the one lane that needs it.  Should a second candidate turn up while one is pending
-        // (0.1-0.3 % of the lists) the fast loop stops and the rest of the list is scanned exactly, in order.
+        // determinants by two cross products with FMA, no division, plus an error bound; no data-dependent branch),
+        // two entries per iteration on the packed FP32 pipe, read from the pair stream (no index indirection): list
+        // positions 2p and 2p + 1 form pair p, a list that starts or ends on an odd position masks the foreign half.
+        // The test never accepts: an entry it cannot reject is a CANDIDATE and takes the reference's exact test, so
+        // results are bit-identical.  Candidates are essentially the ray's real hits (1.06-1.6 per ray,
+        // profiles/r01_pretest_stats.md), so their exact test is DEFERRED to the end of the list: inside the loop it
+        // would be executed -- by warp union -- in most iterations for the one lane that needs it.  Should a second
+        // candidate turn up while one is pending (0.1-0.3 % of the lists) the fast loop stops and the rest of the
+        // list is scanned exactly, in order.
         const float dmx = rtb_pre::dirMax(ray.d.x, ray.d.y, ray.d.z);
         const float Lp = rtb_pre::lowBound(WINDOW ? lo : -FLT_MAX);
         const float Hp = rtb_pre::highBound(WINDOW ? hi : FLT_MAX, FLT_MAX);
         uint32_t pend = 0xffffffffu;
-        uint32_t i = first;
-        for (; i < last; i++)
+        uint32_t counted = last; // list positions below `counted` have gone through pr.tri()
+        bool multi = false;      // the fast loop stopped at a second candidate
+        const uint32_t pEnd = (last + 1u) >> 1;
+        for (uint32_t p = first >> 1; p < pEnd; p++)
         {
-            const uint32_t idx = __ldg(refs + i);
-            const rtb_pre::PreTri P = loadPreTri(S.tri_pre, idx);
-            pr.tri();
-            if (rtb_pre::sureReject<WINDOW>(P, ray.o.x, ray.o.y, ray.o.z, ray.d.x, ray.d.y, ray.d.z, dmx, Lp, Hp)) continue;
-            if (pend != 0xffffffffu) break;
-            pend = i;
+            const rtb_pre::PreTri2 P = loadPreTri2(S.pre2, p);
+            const uint32_t j0 = 2u * p, j1 = j0 + 1u;
+            const bool in0 = j0 >= first, in1 = j1 < last; // j0 < last and j1 >= first always hold
+            if (in0) pr.tri();
+            if (in1) pr.tri();
+            bool r0, r1;
+            rtb_pre::sureReject2<WINDOW>(P, ray.o.x, ray.o.y, ray.o.z, ray.d.x, ray.d.y, ray.d.z, dmx, Lp, Hp, r0, r1);
+            const bool c0 = in0 && !r0, c1 = in1 && !r1;
+            if (!(c0 || c1)) continue;
+            if (pend != 0xffffffffu || (c0 && c1))
+            { // a second candidate: exact scan from the first one to the end of the list
+                if (pend == 0xffffffffu) pend = j0;
+                counted = in1 ? j1 + 1u : j1;
+                multi = true;
+                break;
+            }
+            pend = c0 ? j0 : j1;
         }
         if (pend != 0xffffffffu)
         {
-            // [pend, pend + 1) when the fast loop ran to the end, else [pend, last): entries up to i were counted
-            // above (those between pend and i are proven rejects, testing them again changes nothing)
-            const uint32_t jend = (i < last) ? last : pend + 1;
+            // [pend, pend + 1) when the fast loop ran to the end, else [pend, last): entries the fast loop proved
+            // rejects are tested again on the way, which changes nothing
+            const uint32_t jend = multi ? last : pend + 1;
             for (uint32_t j = pend; j < jend; j++)
             {
                 const uint32_t idx = __ldg(refs + j);
                 const TriData T = loadTri(S.tri, idx);
-                if (j > i) pr.tri();
+                if (j >= counted) pr.tri();
                 float t;
                 if (!triIntersect(T, ray, t)) continue;
                 if (WINDOW && !(t >= lo && t <= hi)) continue;

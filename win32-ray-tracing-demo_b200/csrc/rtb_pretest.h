@@ -145,4 +145,60 @@ RTB_PRE_FN bool sureReject(const PreTri &T, float ox, float oy, float oz, float 
     return rej & (mlo > 0.f);
 }
 
+#if defined(__CUDACC__)
+// ---------------------------------------------------------------------------------------------------------------
+// TWO triangles per call on Blackwell's packed FP32 pipe (sm_100: FFMA2 / FMUL2 / FADD2, `fma.rn.f32x2`).
+// The list scans are bound by warp-instruction ISSUE, not by the FMA pipe (36 % busy): a packed instruction does two
+// lanes' worth of IEEE arithmetic for one issue slot, the ray's components enter as broadcast scalar operands, and
+// each half is rounded exactly like the scalar operation -- the two halves of sureReject2 take, bit for bit, the
+// decisions sureReject<HIGH> takes (tests/test_gpu_parity.py::test_packed_pretest_equals_scalar), so everything the
+// CPU checker proves about the scalar function holds here.
+// Operands come from the PAIR stream: for list positions 2p and 2p + 1 of the accelerator's reference array, six
+// float4 = {ax ax' ay ay'} {az az' A1e A1e'} {e1x e1x' e1y e1y'} {e1z e1z' Ee Ee'} {e2x e2x' e2y e2y'} {e2z e2z' 0 0}
+// (k_pack_pairs): 64-bit aligned register pairs straight out of the 128-bit loads, and no index indirection.
+// ---------------------------------------------------------------------------------------------------------------
+struct PreTri2 { float2 ax, ay, az, a1e, e1x, e1y, e1z, ee, e2x, e2y, e2z; };
+
+__device__ __forceinline__ float2 pre2(float x, float y) { return make_float2(x, y); }
+__device__ __forceinline__ float2 bc(float v) { return make_float2(v, v); }             // becomes a broadcast operand
+__device__ __forceinline__ float2 neg2(float2 v) { return make_float2(-v.x, -v.y); }      // folded into operand modifiers
+__device__ __forceinline__ float2 abs2(float2 v) { return make_float2(fabsf(v.x), fabsf(v.y)); }
+
+template <bool HIGH = true>
+__device__ __forceinline__ void sureReject2(const PreTri2 &T, float ox, float oy, float oz, float dx, float dy, float dz, float dmx,
+                                            float Lp, float Hp, bool &rej0, bool &rej1)
+{
+    const float2 b1 = __fadd2_rn(T.ax, bc(-ox)), b2 = __fadd2_rn(T.ay, bc(-oy)), b3 = __fadd2_rn(T.az, bc(-oz));
+    const float2 px = __ffma2_rn(T.e2y, bc(dz), neg2(__fmul2_rn(T.e2z, bc(dy))));
+    const float2 py = __ffma2_rn(T.e2z, bc(dx), neg2(__fmul2_rn(T.e2x, bc(dz))));
+    const float2 pz = __ffma2_rn(T.e2x, bc(dy), neg2(__fmul2_rn(T.e2y, bc(dx))));
+    const float2 dM = __ffma2_rn(T.e1z, pz, __ffma2_rn(T.e1y, py, __fmul2_rn(T.e1x, px)));
+    const float2 dB = __ffma2_rn(b3, pz, __ffma2_rn(b2, py, __fmul2_rn(b1, px)));
+    const float2 qx = __ffma2_rn(b2, T.e1z, neg2(__fmul2_rn(b3, T.e1y)));
+    const float2 qy = __ffma2_rn(b3, T.e1x, neg2(__fmul2_rn(b1, T.e1z)));
+    const float2 qz = __ffma2_rn(b1, T.e1y, neg2(__fmul2_rn(b2, T.e1x)));
+    const float2 dT = __ffma2_rn(T.e2z, qz, __ffma2_rn(T.e2y, qy, __fmul2_rn(T.e2x, qx)));
+    const float2 dGn = __ffma2_rn(bc(dz), qz, __ffma2_rn(bc(dy), qy, __fmul2_rn(bc(dx), qx))); // = -detG'
+    const float2 bn = __fadd2_rn(__fadd2_rn(abs2(b1), abs2(b2)), abs2(b3));
+    const float2 kap = __fmul2_rn(bc(dmx), __ffma2_rn(T.ee, bn, T.a1e));
+    const float2 kT = __fmul2_rn(T.a1e, bn);
+    const float2 m = abs2(dM);
+    const float2 mk = __fadd2_rn(m, kap), mlo = __fadd2_rn(m, neg2(kap));
+    const float2 hiK = __ffma2_rn(bc(RTB_PRE_CH), mk, kap), cLo = __ffma2_rn(bc(RTB_PRE_CL), mk, kap); // cLo = -loK
+    const float2 hiA = __fadd2_rn(hiK, kap);
+    const float2 tLow = __fmul2_rn(bc(Lp), mlo), tHigh = __fmul2_rn(bc(Hp), mk);
+#define RTB_PRE_HALF(h, out)                                                                                                  \
+    {                                                                                                                         \
+        const uint32_t s = signOf(dM.h);                                                                                      \
+        const float Bt = xorSign(dB.h, s), Gn = xorSign(dGn.h, s) /* = -G~ */, Tt = xorSign(dT.h, s);                          \
+        bool r = (Bt < -cLo.h) | (Bt > hiK.h) | (Gn > cLo.h) | (Gn < -hiK.h) | (Bt - Gn > hiA.h) | (Tt + kT.h < tLow.h);       \
+        if (HIGH) r = r | (Tt - kT.h > tHigh.h);                                                                              \
+        out = r & (mlo.h > 0.f);                                                                                              \
+    }
+    RTB_PRE_HALF(x, rej0)
+    RTB_PRE_HALF(y, rej1)
+#undef RTB_PRE_HALF
+}
+#endif // __CUDACC__
+
 } // namespace rtb_pre
