@@ -205,7 +205,7 @@ k_whitted_chain_sm(const __grid_constant__ DScene S, const __grid_constant__ Fra
                             const float splitVal = __uint_as_float(nd.x);
                             const int axis = (int)(nd.y & 3u);
                             const int right = (int)(nd.y >> 2), left = cur + 1;
-                            const float en = comp(enP, axis), ex = comp(exP, axis);
+                            const float en = compSel(enP, axis), ex = compSel(exP, axis);
                             int farChild = -1;
                             bool both = false;
                             if (en <= splitVal)
@@ -220,7 +220,7 @@ k_whitted_chain_sm(const __grid_constant__ DScene S, const __grid_constant__ Fra
                             }
                             if (both)
                             {
-                                const float t = (splitVal - comp(r.o, axis)) / comp(r.d, axis);
+                                const float t = (splitVal - compSel(r.o, axis)) / compSel(r.d, axis);
                                 const int tmp = exPt++;
                                 if (exPt == enPt) exPt += 1;
                                 exPrev = tmp; exT = t; exNode = farChild;

@@ -34,6 +34,25 @@ __device__ __forceinline__ float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y 
 __device__ __forceinline__ V3 cross(V3 a, V3 b) { return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
 __device__ __forceinline__ V3 normalize(V3 a) { return a * (1 / sqrtf(a.x * a.x + a.y * a.y + a.z * a.z)); }
 __device__ __forceinline__ float comp(const V3 &a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
+// component by a RUN-TIME axis (the k-d walks): two selects instead of the compare-and-branch ladders the ternaries
+// above turn into when the lanes of a warp sit on nodes with different split axes (11 instructions and a
+// divergent region per pick in the SASS of the walk; 25 M inner nodes per 4K frame)
+__device__ __forceinline__ float compSel(const V3 &a, int axis)
+{
+    float r;
+    asm("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %4, 0;\n\tselp.f32 %0, %1, %2, p;\n\tsetp.eq.s32 p, %4, 2;\n\tselp.f32 %0, %3, %0, p;\n\t}"
+        : "=f"(r) : "f"(a.x), "f"(a.y), "f"(a.z), "r"(axis));
+    return r;
+}
+// v with component `axis` replaced by s (axis 3: v unchanged)
+__device__ __forceinline__ V3 withComp(V3 v, int axis, float s)
+{
+    V3 r;
+    asm("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %7, 0;\n\tselp.f32 %0, %6, %3, p;\n\tsetp.eq.s32 p, %7, 1;\n\tselp.f32 %1, %6, %4, p;\n\t"
+        "setp.eq.s32 p, %7, 2;\n\tselp.f32 %2, %6, %5, p;\n\t}"
+        : "=f"(r.x), "=f"(r.y), "=f"(r.z) : "f"(v.x), "f"(v.y), "f"(v.z), "f"(s), "r"(axis));
+    return r;
+}
 __device__ __forceinline__ V3 ld3(const float *p) { return v3(p[0], p[1], p[2]); }
 
 struct Ray { V3 o, d; };
@@ -452,11 +471,7 @@ __device__ bool gridIntersect(const DScene &S, const Ray &ray, int &triOut, floa
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ V3 kdPoint(const Ray &ray, float t, float split, int axis)
 {
-    V3 p = v3(ray.o.x + t * ray.d.x, ray.o.y + t * ray.d.y, ray.o.z + t * ray.d.z);
-    if (axis == 0) p.x = split;
-    else if (axis == 1) p.y = split;
-    else if (axis == 2) p.z = split;
-    return p;
+    return withComp(v3(ray.o.x + t * ray.d.x, ray.o.y + t * ray.d.y, ray.o.z + t * ray.d.z), axis, split);
 }
 
 template <bool WIDE, class Probe>
@@ -485,7 +500,7 @@ __device__ bool kdIntersect(const DScene &S, const Ray &ray, int &triOut, float 
             const float splitVal = __uint_as_float(nd.x);
             const int axis = (int)(nd.y & 3u);
             const int right = (int)(nd.y >> 2), left = cur + 1;
-            const float en = comp(enP, axis), ex = comp(exP, axis);
+            const float en = compSel(enP, axis), ex = compSel(exP, axis);
             int farChild;
             if (en <= splitVal)
             {
@@ -498,7 +513,7 @@ __device__ bool kdIntersect(const DScene &S, const Ray &ray, int &triOut, float 
                 if (splitVal < ex) { cur = right; nd = __ldg(S.kd_nodes + cur); continue; }
                 farChild = left; cur = right;
             }
-            const float t = (splitVal - comp(ray.o, axis)) / comp(ray.d, axis);
+            const float t = (splitVal - compSel(ray.o, axis)) / compSel(ray.d, axis);
             const int tmp = exPt++;
             if (exPt == enPt) exPt += 1;
             exPrev = tmp; exT = t; exNode = farChild;
