@@ -270,7 +270,7 @@ def run_b200(args, wl_name):
     pinned = rtb200.PinnedArray((max(rows, 1), W, 3))  # rtb_host_alloc: page-locked host framebuffer
     host_out = pinned.array
     e2e_steps = max(3, min(args.steps, 10))
-    h2d = dscene.device_bytes
+    h2d = dscene.upload_bytes  # what rtb_scene_upload copies from host memory per step
     d2h = rows * W * 3 * 4
 
     def e2e_step():
@@ -375,7 +375,7 @@ def run_b200(args, wl_name):
                            "sharding": f"tile rows, blocks of {ROW_BLOCK} rows dealt round-robin to {world} rank(s)"
                                        + ("; NCCL all_gather_into_tensor + unshard kernel every step" if world > 1 else ""),
                            "l2": "flushed between timed iterations (384 MiB memset, untimed)",
-                           "host_build_s": host_build_s, "scene_device_bytes": h2d},
+                           "host_build_s": host_build_s, "scene_device_bytes": dscene.device_bytes, "scene_upload_bytes": h2d},
                 "roofline": roofline, "cpu_baseline": cpu,
                 "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "ms_per_step": e2e_ms, "steps": e2e_steps,

@@ -199,6 +199,9 @@ int64_t rtb_shard_rows(const rtb_frame *frame);
 int rtb_scene_upload(rtb_ctx *ctx, const rtb_flat_scene *flat, rtb_scene **scene);
 int rtb_scene_free(rtb_ctx *ctx, rtb_scene *scene);
 int64_t rtb_scene_device_bytes(const rtb_scene *scene);
+/* bytes rtb_scene_upload copied from host memory for this scene (raw triangle records, materials, accelerator arrays);
+ * the packed triangle streams and the pair stream of the list scans are produced on the device                      */
+int64_t rtb_scene_upload_bytes(const rtb_scene *scene);
 /* Inspection: canonical structure hash of the grid resident on the device (the arrays are read back), the hash
  * tests/golden and the host API use for grids; stats = {dims x, y, z, occupied cells, triangle references, longest
  * cell list}.  RTB_ERR_UNSUPPORTED for other accelerators.                                                          */

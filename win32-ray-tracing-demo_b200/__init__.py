@@ -108,7 +108,7 @@ class Stats(C.Structure):
 
 ABI_SYMBOLS = ["rtb_init", "rtb_shutdown", "rtb_last_error", "rtb_abi_version", "rtb_shard_rows",
                "rtb_host_alloc", "rtb_host_free",
-               "rtb_scene_upload", "rtb_scene_free", "rtb_scene_device_bytes", "rtb_scene_grid_hash", "rtb_render",
+               "rtb_scene_upload", "rtb_scene_free", "rtb_scene_device_bytes", "rtb_scene_upload_bytes", "rtb_scene_grid_hash", "rtb_render",
                "rtb_render_device", "rtb_unshard_device", "rtb_trace_primary", "rtb_intersect_rays", "rtb_bounce_rays",
                "rtb_selftest_pretest"]
 
@@ -136,6 +136,8 @@ def cuda_lib():
         lib.rtb_scene_free.argtypes = [vp, vp]
         lib.rtb_scene_device_bytes.argtypes = [vp]
         lib.rtb_scene_device_bytes.restype = i64
+        lib.rtb_scene_upload_bytes.argtypes = [vp]
+        lib.rtb_scene_upload_bytes.restype = i64
         lib.rtb_scene_grid_hash.argtypes = [vp, vp, C.POINTER(C.c_uint64), C.POINTER(C.c_int64)]
         lib.rtb_scene_grid_hash.restype = C.c_int
         lib.rtb_render.argtypes = [vp, vp, C.POINTER(Camera), C.POINTER(RenderSetting), C.POINTER(Frame), vp,
@@ -424,6 +426,11 @@ class DeviceScene:
     @property
     def device_bytes(self):
         return int(self.ctx._lib.rtb_scene_device_bytes(self._h))
+
+    @property
+    def upload_bytes(self):
+        """bytes the upload copied from host memory (the packed / pair streams are produced on the device)"""
+        return int(self.ctx._lib.rtb_scene_upload_bytes(self._h))
 
     def grid_hash(self):
         """(canonical structure hash, {dims, occupied cells, references, longest list}) of the grid on the device."""

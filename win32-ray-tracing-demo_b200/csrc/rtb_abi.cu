@@ -105,7 +105,8 @@ struct rtb_scene
 {
     DScene d;
     std::vector<void *> allocs;
-    int64_t bytes = 0;
+    int64_t bytes = 0;     // device bytes held by the scene
+    int64_t h2d_bytes = 0; // bytes the upload copied from host memory (the rest is produced on the device)
     bool has_refractive = false;
     bool has_tunnel = false;
     cudaEvent_t last_use = nullptr; // recorded after every launch that reads the scene
@@ -304,6 +305,7 @@ static int uploadWith(rtb_ctx *ctx, rtb_scene *s, size_t n, const T **dev, Fill 
         if (rc != RTB_OK) return rc;
         fill(reinterpret_cast<T *>(st));
         CUDA_TRY(ctx, cudaMemcpyAsync(p, st, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+        s->h2d_bytes += (int64_t)(n * sizeof(T));
     }
     else CUDA_TRY(ctx, cudaMemsetAsync(p, 0, count * sizeof(T), ctx->stream));
     *dev = (const T *)p;
@@ -360,6 +362,7 @@ static int uploadTriangles(rtb_ctx *ctx, rtb_scene *s, const float *host, size_t
     void *raw = nullptr;
     CUDA_TRY(ctx, cudaMallocAsync(&raw, n * 12 * sizeof(float), ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(raw, st, n * 12 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    s->h2d_bytes += (int64_t)(n * 12 * sizeof(float));
     k_pack_triangles<<<(unsigned int)((n + 255) / 256), 256, 0, ctx->stream>>>((const float *)raw, (int)n, const_cast<float4 *>(*exact),
                                                                              pre ? const_cast<float4 *>(*pre) : nullptr);
     CUDA_TRY(ctx, cudaGetLastError());
@@ -450,6 +453,7 @@ static int buildGridOnDevice(rtb_ctx *ctx, rtb_scene *s, const rtb_flat_scene *f
     float *d_raw = nullptr, *d_bounds = nullptr;
     GRID_TRY(temp((size_t)n * 12 * sizeof(float), (void **)&d_raw));
     GRID_TRY(cudaMemcpyAsync(d_raw, f->tri, (size_t)n * 12 * sizeof(float), cudaMemcpyHostToDevice, st));
+    s->h2d_bytes += (int64_t)n * 12 * (int64_t)sizeof(float);
     GRID_TRY(temp(6 * sizeof(float), (void **)&d_bounds));
     const float init[6] = {FLT_MAX, FLT_MAX, FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
     GRID_TRY(cudaMemcpyAsync(d_bounds, init, sizeof(init), cudaMemcpyHostToDevice, st));
@@ -808,6 +812,7 @@ extern "C" int rtb_scene_free(rtb_ctx *ctx, rtb_scene *s)
 }
 
 extern "C" int64_t rtb_scene_device_bytes(const rtb_scene *s) { return s ? s->bytes : 0; }
+extern "C" int64_t rtb_scene_upload_bytes(const rtb_scene *s) { return s ? s->h2d_bytes : 0; }
 
 extern "C" int rtb_scene_grid_hash(rtb_ctx *ctx, const rtb_scene *s, uint64_t *hash, int64_t stats[6])
 {
