@@ -48,6 +48,13 @@ WORKLOADS["p5_rgrid_400"] = dict(WORKLOADS["p5_rgrid_4k"], width=400, height=300
 # p5_*_400 is the frame the reference arm / cpu_baseline renders on the host cores: same scene, camera, size
 EXTRAS = ["p5_rgrid_4k", "p5_kd_4k", "p5_fgrid_4k", "p4_sah_4k", "p2_smallpt_64", "p5_sah_400", "p5_rgrid_400"]
 ROW_BLOCK = int(os.environ.get("RTB_ROW_BLOCK", "8"))  # rows per dealt block (multiple of 8)
+# N > 1: column-block shards (rtb_frame.col_block) -- every rank renders every row and 1 / N of the 32-pixel column
+# blocks, so all ranks hold the same mix of heavy (vanishing point) and light tiles; 0 = whole-row shards
+COL_BLOCK = int(os.environ.get("RTB_COL_BLOCK", "32"))
+# ... from this many ranks on: up to 4 ranks the few heavy row blocks around the vanishing point already land on
+# different ranks (measured: N = 2 rows 10,054 vs columns 9,833 Mrays/s); at 8 ranks rows leave half the ranks without
+# them (slowest of 8 shards, one GPU: SAH 1.23 -> 1.19 ms, k-d median 4.05 -> 2.68, regular grid 4.31 -> 3.54)
+COL_MIN_WORLD = int(os.environ.get("RTB_COL_MIN_WORLD", "5"))
 METRIC = "Mrays/s on tunnel scenes (grid/k-d tree) at 1/2/4/8 B200 vs CPU render secs"
 
 
@@ -196,7 +203,9 @@ def run_b200(args, wl_name):
     host_build_s = time.perf_counter() - t0
     ctx = rtb200.Context(local)
     dscene = ctx.upload(scene.flat)
-    frame = rtb200.make_frame(W, H, samples=spp, seed=0, rank=rank, world=world, row_block=ROW_BLOCK)
+    col_block = COL_BLOCK if (world >= max(COL_MIN_WORLD, 2) and COL_BLOCK > 0 and W % (world * COL_BLOCK) == 0) else 0
+    frame = rtb200.make_frame(W, H, samples=spp, seed=0, rank=rank, world=world, row_block=ROW_BLOCK, col_block=col_block)
+    Wl = rtb200.shard_width(frame)  # width of this rank's local image
     rows = rtb200.shard_rows(frame)
     rows_max = int(allmax(rows))
     # a dedicated (non-default) torch stream: the kernels, the NCCL gather and the timing events all
@@ -207,8 +216,14 @@ def run_b200(args, wl_name):
 
     image = torch.zeros((H, W, 3), dtype=torch.float32, device=dev_t)
     if world > 1:
-        local_buf = torch.zeros((rows_max, W, 3), dtype=torch.float32, device=dev_t)
-        gathered = torch.zeros((world, rows_max, W, 3), dtype=torch.float32, device=dev_t)
+        local_buf = torch.zeros((rows_max, Wl, 3), dtype=torch.float32, device=dev_t)
+        gathered = torch.zeros((world, rows_max, Wl, 3), dtype=torch.float32, device=dev_t)
+
+    def unshard():
+        if col_block:
+            rtb200.unshard_cols_device(ctx, gathered.data_ptr(), image.data_ptr(), W, H, world, ROW_BLOCK, col_block, stream)
+        else:
+            rtb200.unshard_device(ctx, gathered.data_ptr(), image.data_ptr(), W, H, world, ROW_BLOCK, rows_max, stream)
     flush = torch.empty(384 * 1024 * 1024, dtype=torch.uint8, device=dev_t)  # > 126 MB L2
 
     def step():
@@ -216,12 +231,12 @@ def run_b200(args, wl_name):
             dscene.render_device(scene.camera, scene.setting, frame, image.data_ptr(), stream)
         else:
             dscene.render_device(scene.camera, scene.setting, frame, local_buf.data_ptr(), stream)
-            dist.all_gather_into_tensor(gathered.view(world * rows_max, W, 3), local_buf)
-            rtb200.unshard_device(ctx, gathered.data_ptr(), image.data_ptr(), W, H, world, ROW_BLOCK, rows_max, stream)
+            dist.all_gather_into_tensor(gathered.view(world * rows_max, Wl, 3), local_buf)
+            unshard()
 
 
     # ray / test / step counts of one frame (deterministic), outside the timed region
-    cframe = rtb200.make_frame(W, H, samples=spp, seed=0, rank=rank, world=world, row_block=ROW_BLOCK, counters=1)
+    cframe = rtb200.make_frame(W, H, samples=spp, seed=0, rank=rank, world=world, row_block=ROW_BLOCK, counters=1, col_block=col_block)
     tmp = local_buf if world > 1 else image
     cst = dscene.render_device(scene.camera, scene.setting, cframe, tmp.data_ptr(), stream, want_stats=True)
     rays_frame = allsum(cst["n_rays"])
@@ -255,8 +270,8 @@ def run_b200(args, wl_name):
             kev[i][0].record()
             dscene.render_device(scene.camera, scene.setting, frame, local_buf.data_ptr(), stream)
             kev[i][1].record()
-            dist.all_gather_into_tensor(gathered.view(world * rows_max, W, 3), local_buf)
-            rtb200.unshard_device(ctx, gathered.data_ptr(), image.data_ptr(), W, H, world, ROW_BLOCK, rows_max, stream)
+            dist.all_gather_into_tensor(gathered.view(world * rows_max, Wl, 3), local_buf)
+            unshard()
         ev[i][1].record()
     barrier()
     clocks = sampler.stop() if sampler else None
@@ -267,11 +282,11 @@ def run_b200(args, wl_name):
     value = rays_frame / ms_per_step / 1e3  # Mrays/s, whole job
 
     # ---- e2e: host buffers through the C ABI, H2D scene upload + D2H framebuffer inside the timed region
-    pinned = rtb200.PinnedArray((max(rows, 1), W, 3))  # rtb_host_alloc: page-locked host framebuffer
+    pinned = rtb200.PinnedArray((max(rows, 1), Wl, 3))  # rtb_host_alloc: page-locked host framebuffer
     host_out = pinned.array
     e2e_steps = max(3, min(args.steps, 10))
     h2d = dscene.upload_bytes  # what rtb_scene_upload copies from host memory per step
-    d2h = rows * W * 3 * 4
+    d2h = rows * Wl * 3 * 4
 
     def e2e_step():
         d = ctx.upload(scene.flat)
@@ -288,9 +303,9 @@ def run_b200(args, wl_name):
     e2e_value = rays_frame / e2e_ms / 1e3
 
     # the same call with the reference's 8-bit output stage on the GPU (3 bytes per pixel come back)
-    pinned8 = rtb200.PinnedArray(((max(rows, 1) * W * 3 + 3) // 4,))
-    host8 = pinned8.array.view(np.uint8)[: max(rows, 1) * W * 3].reshape(max(rows, 1), W, 3)
-    frame8 = rtb200.make_frame(W, H, samples=spp, seed=0, rank=rank, world=world, row_block=ROW_BLOCK, layout=rtb200.OUTPUT_RGB8)
+    pinned8 = rtb200.PinnedArray(((max(rows, 1) * Wl * 3 + 3) // 4,))
+    host8 = pinned8.array.view(np.uint8)[: max(rows, 1) * Wl * 3].reshape(max(rows, 1), Wl, 3)
+    frame8 = rtb200.make_frame(W, H, samples=spp, seed=0, rank=rank, world=world, row_block=ROW_BLOCK, layout=rtb200.OUTPUT_RGB8, col_block=col_block)
 
     def e2e8_step():
         d = ctx.upload(scene.flat)
@@ -307,7 +322,7 @@ def run_b200(args, wl_name):
 
     # ---- roofline of the dominant kernel (the render kernel of this rank)
     peaks, peak_kind = measured_peaks()
-    pixels_rank = rows * W
+    pixels_rank = rows * Wl
     # algorithmic bytes (DESIGN.md "Roofline"): 8 B per visited cell / k-d node, 4 B index + 36 B vertices per
     # triangle test, 12 B normal + 4 B material per ray, 12 B framebuffer store per pixel
     algo_bytes = 8 * cst["n_steps"] + 40 * cst["n_tri_tests"] + 16 * cst["n_rays"] + 12 * pixels_rank
@@ -372,7 +387,8 @@ def run_b200(args, wl_name):
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": wl_name, "description": wl["desc"], "rays_per_step": rays_frame,
                            "tri_tests_per_step": tests_frame, "traversal_steps_per_step": steps_frame,
-                           "sharding": f"tile rows, blocks of {ROW_BLOCK} rows dealt round-robin to {world} rank(s)"
+                           "sharding": (f"column blocks of {col_block} pixels, rotated every {ROW_BLOCK} rows, dealt round-robin to {world} rank(s)" if col_block
+                                        else f"tile rows, blocks of {ROW_BLOCK} rows dealt round-robin to {world} rank(s)")
                                        + ("; NCCL all_gather_into_tensor + unshard kernel every step" if world > 1 else ""),
                            "l2": "flushed between timed iterations (384 MiB memset, untimed)",
                            "host_build_s": host_build_s, "scene_device_bytes": dscene.device_bytes, "scene_upload_bytes": h2d},
@@ -380,7 +396,7 @@ def run_b200(args, wl_name):
                 "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "ms_per_step": e2e_ms, "steps": e2e_steps,
                         "path": "rtb_scene_upload (H2D) + rtb_render (kernels store the float framebuffer straight into the caller's page-locked host buffer over PCIe; pageable buffers take a device frame + D2H copy) + rtb_scene_free per step",
-                        "rgb8_output_stage": {"value": rays_frame / e2e8_ms / 1e3, "ms_per_step": e2e8_ms, "d2h_bytes_per_step": int(rows * W * 3),
+                        "rgb8_output_stage": {"value": rays_frame / e2e8_ms / 1e3, "ms_per_step": e2e8_ms, "d2h_bytes_per_step": int(rows * Wl * 3),
                                               "note": "same call with RTB_OUTPUT_RGB8: saturate + (int)(c*255) on the GPU as the reference's Render ends (MainWindow.cpp:305-311)"}},
                 "gpu_launches": launches_per_step * args.steps,
                 "kernel_ms_max_over_ranks": kernel_ms_max, "clocks": clocks, "others": others}

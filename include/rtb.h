@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define RTB_ABI_VERSION 2
+#define RTB_ABI_VERSION 3
 
 typedef enum rtb_status {
     RTB_OK = 0,
@@ -163,6 +163,14 @@ typedef struct rtb_frame {
     int32_t counters;     /* 1: also count triangle tests / traversal steps (slower); 2: as 1 and write a
                              per-pixel cost map (thread cycles, rays, steps + tests) instead of the colour
                              (profiling aid, Whitted chain kernel only)                          */
+    int32_t col_block;    /* 0: the shard is whole rows (blocks of row_block rows dealt round-robin).  > 0 (with world
+                             > 1): COLUMN-BLOCK shard -- every rank renders every row and, of block row
+                             by = y / row_block, the column blocks bx = x / col_block with (bx + by) % world == rank;
+                             its output is a local image [height][width / world] in which local column block c holds
+                             global block c * world + (rank - by) mod world.  Multiple of 8, width a multiple of
+                             world * col_block, row-major layout.  The tunnel frames concentrate their cost around
+                             the vanishing point: narrow column blocks give every rank the same mix of tiles.
+                             (Occupies what was tail padding of this struct: zero-initialised callers get rows.)  */
 } rtb_frame;
 
 typedef struct rtb_stats {
@@ -193,6 +201,8 @@ int rtb_host_free(void *p);
 
 /* Number of rows / first-row list of a shard (pure host arithmetic; no device needed).       */
 int64_t rtb_shard_rows(const rtb_frame *frame);
+/* width of the shard's local image: frame->width, or frame->width / world for a column-block shard */
+int64_t rtb_shard_width(const rtb_frame *frame);
 
 /* Upload a flattened scene.  Replaces nothing in the reference (it has no device); it is the
  * device-side image of GeometrySet + Tunnel::grid / Tunnel::root.                           */
@@ -255,6 +265,10 @@ int rtb_intersect_rays(rtb_ctx *ctx, const rtb_scene *scene, int64_t n, const fl
 int rtb_bounce_rays(rtb_ctx *ctx, const rtb_scene *scene, int64_t n, const float *rays, int32_t max_depth,
                     int32_t *reached, int32_t *depth, int32_t *last_id, float *last_pos, int64_t *total_rays,
                     float *kernel_ms);
+
+/* As rtb_unshard_device for column-block shards (rtb_frame.col_block): `gathered` = [world][height][width / world][3]. */
+int rtb_unshard_cols_device(rtb_ctx *ctx, const void *gathered, void *image, int32_t width, int32_t height,
+                            int32_t world, int32_t row_block, int32_t col_block, void *stream);
 
 /* Self-test of the list scans' rejection test (csrc/rtb_pretest.h): n random (ray, triangle) pairs -- triangles of
  * widely varying size, slivers, rays aimed at the triangle's boundary -- are decided by the scalar function (the one

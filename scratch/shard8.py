@@ -12,6 +12,7 @@ for sc in os.environ.get("SCENES", "5sah,5kd,4sah,5rgrid").split(","):
     s = rtb200.PresetScene(int(sc[0]), sc[1:], 150)
     d = ctx.upload(s.flat)
     world = 8
-    sh = [runs(d, s, rtb200.make_frame(3840, 2880, rank=r, world=world, row_block=8), 6) for r in range(world)]
-    print(tag, sc, "world", world, "per-rank min of last 3:", " ".join("%.2f" % min(x[3:]) for x in sh), "max %.2f" % max(min(x[3:]) for x in sh), flush=True)
+    for cb in [int(c) for c in os.environ.get("COLS", "0,32").split(",")]:
+        sh = [runs(d, s, rtb200.make_frame(3840, 2880, rank=r, world=world, row_block=8, col_block=cb), 6) for r in range(world)]
+        print(tag, sc, "world", world, "col_block", cb, "per-rank min of last 3:", " ".join("%.2f" % min(x[3:]) for x in sh), "max %.2f" % max(min(x[3:]) for x in sh), flush=True)
     d.close(); s.close()

@@ -27,7 +27,8 @@ def test_header_symbols_exported():
 
 def test_abi_version_and_struct_sizes():
     lib = rtb200.cuda_lib()
-    assert lib.rtb_abi_version() == 2
+    assert lib.rtb_abi_version() == 3
+    assert C.sizeof(rtb200.Frame) == 48  # col_block took the tail padding: the size did not change with ABI 3
     assert C.sizeof(rtb200.Material) == 64 and C.sizeof(rtb200.Prim) == 48
     assert C.sizeof(rtb200.KdNode) == 8 and C.sizeof(rtb200.CellWord) == 8
 
@@ -50,3 +51,27 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle_py" not in text and "rt_oracle" not in text.replace("oracle/rt_oracle.cpp", ""), f
+
+
+def test_column_block_shards_partition_the_frame():
+    """Host arithmetic of the column-block sharding (rtb_frame.col_block): for every row the ranks' column sets are a
+    partition of the row, every rank owns width / world columns, and the block -> rank map rotates with the block row."""
+    import numpy as np
+    for (w, world, rb, cb) in [(256, 4, 8, 16), (3840, 8, 8, 32), (96, 3, 16, 8), (64, 2, 8, 32)]:
+        for y in (0, 7, 8, 9, rb * world - 1, rb * world, 1000):
+            seen = np.zeros(w, np.int32)
+            for rank in range(world):
+                xs = rtb200.shard_col_indices(w, y, rank, world, rb, cb)
+                assert len(xs) == w // world and np.all(np.diff(xs) > 0)
+                assert np.all(((xs // cb) + (y // rb)) % world == rank)
+                seen[xs] += 1
+            assert np.all(seen == 1)
+    lib = rtb200.cuda_lib()
+    fr = rtb200.make_frame(3840, 2880, rank=3, world=8, row_block=8, col_block=32)
+    assert lib.rtb_shard_rows(C.byref(fr)) == 2880 and lib.rtb_shard_width(C.byref(fr)) == 480
+    bad = rtb200.make_frame(3840, 2880, rank=3, world=8, row_block=8, col_block=12)   # not a multiple of 8
+    assert lib.rtb_shard_rows(C.byref(bad)) == -1
+    bad = rtb200.make_frame(3848, 2880, rank=3, world=8, row_block=8, col_block=32)   # width not a multiple of world * col_block
+    assert lib.rtb_shard_rows(C.byref(bad)) == -1
+    one = rtb200.make_frame(3840, 2880, rank=0, world=1, row_block=8, col_block=32)   # a single rank ignores col_block
+    assert lib.rtb_shard_rows(C.byref(one)) == 2880 and lib.rtb_shard_width(C.byref(one)) == 3840

@@ -1,6 +1,7 @@
 """N > 1 host logic on CPU (gloo, world_size 2 and 3): the tile-row shard arithmetic of include/rtb.h
 (rtb_shard_rows, block-cyclic dealing), the padded all-gather layout bench.py uses, and the row order
-rtb_unshard_device restores.  No GPU kernels run here; each rank fills its shard with a function of the
+rtb_unshard_device restores; the same for column-block shards (rtb_frame.col_block, rtb_shard_width,
+rtb_unshard_cols_device).  No GPU kernels run here; each rank fills its shard with a function of the
 global row index so the reassembled frame can be checked exactly."""
 import os
 import socket
@@ -44,6 +45,30 @@ WORKER = textwrap.dedent("""
     total = torch.tensor([rows], dtype=torch.int64)
     dist.all_reduce(total)
     assert int(total.item()) == H
+
+    # ---- column-block shards (rtb_frame.col_block): local image [H][W / world], gathered [world][H][W / world][3] ----
+    CB = 8
+    Wc = world * CB * 5
+    cframe = rtb200.make_frame(Wc, H, rank=rank, world=world, row_block=RB, col_block=CB)
+    assert rtb200.shard_rows(cframe) == H and rtb200.shard_width(cframe) == Wc // world    # C ABI
+    Wl = Wc // world
+    local = torch.zeros((H, Wl, 3), dtype=torch.float32)
+    for y in range(H):
+        gx = torch.from_numpy(rtb200.shard_col_indices(Wc, y, rank, world, RB, CB)).to(torch.float32)
+        for c in range(3):
+            local[y, :, c] = float(y) * 1000 + gx + c * 0.25
+    gathered = torch.zeros((world, H, Wl, 3), dtype=torch.float32)
+    dist.all_gather_into_tensor(gathered.view(world * H, Wl, 3), local)
+    # the permutation rtb_unshard_cols_device applies (k_unshard_cols): column block bx of row y lives on rank
+    # (bx + y // RB) %% world at local block bx // world
+    image = torch.empty((H, Wc, 3), dtype=torch.float32)
+    for y in range(H):
+        for bx in range(Wc // CB):
+            r = (bx + y // RB) %% world
+            image[y, bx * CB:(bx + 1) * CB] = gathered[r, y, (bx // world) * CB:(bx // world + 1) * CB]
+    xc = torch.arange(Wc, dtype=torch.float32)
+    expect = torch.arange(H, dtype=torch.float32)[:, None, None] * 1000 + xc[None, :, None] + torch.tensor([0, 0.25, 0.5])[None, None, :]
+    assert torch.equal(image, expect), "column-sharded frame differs"
     dist.barrier()
     if rank == 0:
         print("GLOO_OK", world, rows_max)

@@ -169,6 +169,72 @@ def test_row_shards_reassemble_bit_exact(ctx, world):
     dev.close(); s.close()
 
 
+@pytest.mark.parametrize("world,col_block,w,h,alg", [(2, 8, 160, 120, "rgrid"), (4, 16, 256, 96, "sah"), (8, 8, 192, 144, "sah"),
+                                                     (3, 16, 96, 72, "kd"), (8, 32, 512, 60, "fgrid")])
+def test_column_block_shards_reassemble_bit_exact(ctx, world, col_block, w, h, alg):
+    """Column-block sharding (rtb_frame.col_block: every rank renders every row and 1 / world of the column blocks,
+    rotated from block row to block row) is bit-identical to the whole frame -- second frames too, when the tile order
+    and the latency tiers are in play -- and the ray counts add up."""
+    s, dev = _scene(ctx, dict(preset=5, algorithm=alg, segments=24))
+    whole, st = dev.render(s.camera, s.setting, rtb200.make_frame(w, h))
+    for repeat in range(2):
+        out = np.zeros_like(whole)
+        rays = 0
+        for rank in range(world):
+            fr = rtb200.make_frame(w, h, rank=rank, world=world, row_block=8, col_block=col_block)
+            assert rtb200.shard_rows(fr) == h and rtb200.shard_width(fr) == w // world
+            part, pst = dev.render(s.camera, s.setting, fr)
+            part, pst = dev.render(s.camera, s.setting, fr)  # the second frame of a view uses the recorded tile order
+            assert part.shape == (h, w // world, 3)
+            for y in range(h):
+                out[y, rtb200.shard_col_indices(w, y, rank, world, 8, col_block)] = part[y]
+            rays += pst["n_rays"]
+        assert np.array_equal(_bits(out), _bits(whole))
+        assert rays == st["n_rays"]
+    # a width that is not a multiple of world * col_block is refused
+    with pytest.raises(rtb200.RtbError):
+        dev.render(s.camera, s.setting, rtb200.make_frame(w + 8, h, rank=0, world=world, row_block=8, col_block=col_block))
+    dev.close(); s.close()
+
+
+def test_column_block_shards_monte_carlo_and_rgb8(ctx):
+    """The counter RNG is keyed by the GLOBAL pixel, so a column-sharded Monte-Carlo frame equals the whole frame; the
+    8-bit output stage goes through the same local layout."""
+    w, h, world, cb = 128, 48, 4, 8
+    s, dev = _scene(ctx, dict(preset=2))
+    whole, _ = dev.render(s.camera, s.setting, rtb200.make_frame(w, h, samples=3, seed=11))
+    whole8, _ = dev.render(s.camera, s.setting, rtb200.make_frame(w, h, samples=3, seed=11, layout=rtb200.OUTPUT_RGB8))
+    out, out8 = np.zeros_like(whole), np.zeros_like(whole8)
+    for rank in range(world):
+        part, _ = dev.render(s.camera, s.setting, rtb200.make_frame(w, h, samples=3, seed=11, rank=rank, world=world, col_block=cb))
+        part8, _ = dev.render(s.camera, s.setting, rtb200.make_frame(w, h, samples=3, seed=11, rank=rank, world=world, col_block=cb,
+                                                                      layout=rtb200.OUTPUT_RGB8))
+        for y in range(h):
+            xs = rtb200.shard_col_indices(w, y, rank, world, 8, cb)
+            out[y, xs] = part[y]
+            out8[y, xs] = part8[y]
+    assert np.array_equal(_bits(out), _bits(whole))
+    assert np.array_equal(out8, whole8)
+    dev.close(); s.close()
+
+
+def test_unshard_cols_kernel(ctx):
+    import torch
+    w, h, world, rb, cb = 256, 72, 4, 8, 16
+    s, dev = _scene(ctx, dict(preset=4, algorithm="sah", segments=12))
+    whole, _ = dev.render(s.camera, s.setting, rtb200.make_frame(w, h))
+    gathered = torch.zeros((world, h, w // world, 3), dtype=torch.float32, device="cuda:0")
+    stream = torch.cuda.current_stream().cuda_stream
+    for rank in range(world):
+        fr = rtb200.make_frame(w, h, rank=rank, world=world, row_block=rb, col_block=cb)
+        dev.render_device(s.camera, s.setting, fr, gathered[rank].data_ptr(), stream)
+    image = torch.empty((h, w, 3), dtype=torch.float32, device="cuda:0")
+    rtb200.unshard_cols_device(ctx, gathered.data_ptr(), image.data_ptr(), w, h, world, rb, cb, stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(_bits(image.cpu().numpy()), _bits(whole))
+    dev.close(); s.close()
+
+
 def test_unshard_kernel(ctx):
     import torch
     w, h, world, rb = 96, 72, 4, 8

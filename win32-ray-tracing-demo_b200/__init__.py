@@ -94,7 +94,8 @@ SETTINGS = {  # reference RenderSetting.h:40-78
 class Frame(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("samples", C.c_int32),
                 ("seed", C.c_uint64), ("rank", C.c_int32), ("world", C.c_int32),
-                ("row_block", C.c_int32), ("layout", C.c_int32), ("counters", C.c_int32)]
+                ("row_block", C.c_int32), ("layout", C.c_int32), ("counters", C.c_int32),
+                ("col_block", C.c_int32)]
 
 
 class Stats(C.Structure):
@@ -106,7 +107,8 @@ class Stats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "pad_"}
 
 
-ABI_SYMBOLS = ["rtb_init", "rtb_shutdown", "rtb_last_error", "rtb_abi_version", "rtb_shard_rows",
+ABI_SYMBOLS = ["rtb_init", "rtb_shutdown", "rtb_last_error", "rtb_abi_version", "rtb_shard_rows", "rtb_shard_width",
+               "rtb_unshard_cols_device",
                "rtb_host_alloc", "rtb_host_free",
                "rtb_scene_upload", "rtb_scene_free", "rtb_scene_device_bytes", "rtb_scene_upload_bytes", "rtb_scene_grid_hash", "rtb_render",
                "rtb_render_device", "rtb_unshard_device", "rtb_trace_primary", "rtb_intersect_rays", "rtb_bounce_rays",
@@ -132,6 +134,8 @@ def cuda_lib():
         lib.rtb_host_free.argtypes = [vp]
         lib.rtb_shard_rows.argtypes = [C.POINTER(Frame)]
         lib.rtb_shard_rows.restype = i64
+        lib.rtb_shard_width.argtypes = [C.POINTER(Frame)]
+        lib.rtb_shard_width.restype = i64
         lib.rtb_scene_upload.argtypes = [vp, C.POINTER(FlatScene), C.POINTER(vp)]
         lib.rtb_scene_free.argtypes = [vp, vp]
         lib.rtb_scene_device_bytes.argtypes = [vp]
@@ -145,6 +149,7 @@ def cuda_lib():
         lib.rtb_render_device.argtypes = [vp, vp, C.POINTER(Camera), C.POINTER(RenderSetting), C.POINTER(Frame),
                                           vp, vp, C.POINTER(Stats)]
         lib.rtb_unshard_device.argtypes = [vp, vp, vp, i32, i32, i32, i32, i64, vp]
+        lib.rtb_unshard_cols_device.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp]
         lib.rtb_trace_primary.argtypes = [vp, vp, C.POINTER(Camera), i32, i32, vp, vp, vp, vp, vp, i32]
         lib.rtb_intersect_rays.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp]
         _cuda = lib
@@ -376,6 +381,11 @@ def unshard_device(ctx, gathered_ptr, image_ptr, width, height, world, row_block
                                            row_block, rows_per_rank, C.c_void_p(stream)), "rtb_unshard_device")
 
 
+def unshard_cols_device(ctx, gathered_ptr, image_ptr, width, height, world, row_block, col_block, stream=0):
+    ctx._check(ctx._lib.rtb_unshard_cols_device(ctx._h, C.c_void_p(gathered_ptr), C.c_void_p(image_ptr), width, height, world,
+                                                row_block, col_block, C.c_void_p(stream)), "rtb_unshard_cols_device")
+
+
 class PinnedArray:
     """float32 numpy view over page-locked host memory from rtb_host_alloc."""
 
@@ -398,8 +408,25 @@ def shard_rows(frame):
     return int(cuda_lib().rtb_shard_rows(C.byref(frame)))
 
 
-def make_frame(width, height, samples=1, seed=0, rank=0, world=1, row_block=8, layout=LAYOUT_ROWMAJOR, counters=0):
-    return Frame(width, height, samples, seed, rank, world, row_block, layout, counters)
+def shard_width(frame):
+    return int(cuda_lib().rtb_shard_width(C.byref(frame)))
+
+
+def make_frame(width, height, samples=1, seed=0, rank=0, world=1, row_block=8, layout=LAYOUT_ROWMAJOR, counters=0, col_block=0):
+    """col_block > 0 (and world > 1): column-block shard, local image [height][width / world] (include/rtb.h)."""
+    return Frame(width, height, samples, seed, rank, world, row_block, layout, counters, col_block)
+
+
+def shard_col_indices(width, y, rank, world, row_block, col_block):
+    """Global x of each local column of row y of a column-block shard: block row by = y // row_block owns the
+    column blocks bx with (bx + by) % world == rank (mirror of localToGlobal in csrc/rtb_kernels.cuh)."""
+    by = y // row_block
+    shift = (rank - by) % world
+    xs = []
+    for c in range(width // (world * col_block)):
+        bx = c * world + shift
+        xs.extend(range(bx * col_block, (bx + 1) * col_block))
+    return np.asarray(xs, np.int64)
 
 
 def shard_row_indices(height, rank, world, row_block=8):
@@ -444,7 +471,7 @@ class DeviceScene:
         if rows < 0:
             raise RtbError("bad frame: size / rank / world / row_block (must be a multiple of 8)")
         if out is None:
-            shape = (frame.width, frame.height, 3) if frame.layout & LAYOUT_REFERENCE else (rows, frame.width, 3)
+            shape = (frame.width, frame.height, 3) if frame.layout & LAYOUT_REFERENCE else (rows, shard_width(frame), 3)
             out = np.zeros(shape, np.uint8 if frame.layout & OUTPUT_RGB8 else np.float32)
         st = Stats()
         self.ctx._check(self.ctx._lib.rtb_render(self.ctx._h, self._h, C.byref(camera), C.byref(setting), C.byref(frame),

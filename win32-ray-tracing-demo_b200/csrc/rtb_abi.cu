@@ -250,11 +250,19 @@ extern "C" int rtb_shutdown(rtb_ctx *ctx)
 
 static int normRowBlock(const rtb_frame *f) { return f->row_block > 0 ? f->row_block : 8; }
 
+// column-block sharding in effect?  (world > 1 and a column block given)
+static bool colSharded(const rtb_frame *f) { return f->col_block > 0 && f->world > 1; }
+static bool colShardOk(const rtb_frame *f)
+{
+    return f->col_block % 8 == 0 && f->width % ((int64_t)f->world * f->col_block) == 0 && !(f->layout & RTB_LAYOUT_REFERENCE);
+}
+
 extern "C" int64_t rtb_shard_rows(const rtb_frame *f)
 {
     if (!f || f->width <= 0 || f->height <= 0) return -1;
     const int world = f->world > 0 ? f->world : 1, rank = f->rank, rb = normRowBlock(f);
     if (rank < 0 || rank >= world || rb % 8 != 0) return -1;
+    if (colSharded(f)) return colShardOk(f) ? f->height : -1; // every rank renders every row
     int64_t rows = 0;
     for (int64_t b = rank; b * rb < f->height; b += world)
     {
@@ -262,6 +270,12 @@ extern "C" int64_t rtb_shard_rows(const rtb_frame *f)
         rows += y1 - y0;
     }
     return rows;
+}
+
+extern "C" int64_t rtb_shard_width(const rtb_frame *f)
+{
+    if (rtb_shard_rows(f) < 0) return -1;
+    return colSharded(f) ? f->width / f->world : f->width;
 }
 
 // ---- scene upload -----------------------------------------------------------------------------
@@ -863,7 +877,9 @@ static int makeFrame(rtb_ctx *ctx, const rtb_scene *scene, const rtb_camera *cam
     if (!ctx || !scene || !cam || !setting || !frame) return fail(ctx, RTB_ERR_INVALID, "render: null argument");
     if (frame->width <= 0 || frame->height <= 0) return fail(ctx, RTB_ERR_INVALID, "render: bad image size");
     const int64_t rows = rtb_shard_rows(frame);
-    if (rows < 0) return fail(ctx, RTB_ERR_INVALID, "render: bad shard (rank/world/row_block; row_block must be a multiple of 8)");
+    if (rows < 0)
+        return fail(ctx, RTB_ERR_INVALID, "render: bad shard (rank / world / row_block: row_block must be a multiple of 8; col_block: a multiple "
+                                          "of 8 with width a multiple of world * col_block, row-major layout)");
     const int world = frame->world > 0 ? frame->world : 1;
     if (frame->layout & ~(RTB_LAYOUT_REFERENCE | RTB_OUTPUT_RGB8)) return fail(ctx, RTB_ERR_INVALID, "render: unknown layout flags");
     if ((frame->layout & RTB_LAYOUT_REFERENCE) && world != 1)
@@ -887,7 +903,9 @@ static int makeFrame(rtb_ctx *ctx, const rtb_scene *scene, const rtb_camera *cam
     F.layout = frame->layout & RTB_LAYOUT_REFERENCE;
     F.rgb8 = (frame->layout & RTB_OUTPUT_RGB8) ? 1 : 0;
     F.n_local_rows = (int)rows;
-    F.tiles_x = (frame->width + RTB_TILE_W - 1) / RTB_TILE_W;
+    F.col_block = colSharded(frame) ? frame->col_block : 0;
+    F.local_width = (int)rtb_shard_width(frame);
+    F.tiles_x = (F.local_width + RTB_TILE_W - 1) / RTB_TILE_W;
     F.n_tiles = F.tiles_x * (int)((rows + RTB_TILE_H - 1) / RTB_TILE_H);
     F.cost_map = frame->counters == 2;
     F.warps_per_cta = RTB_CTA_THREADS / 32;
@@ -1016,7 +1034,7 @@ static int prepareTileOrder(rtb_ctx *ctx, const rtb_scene *scene, FrameParams &F
     // else starts over with a raster-order frame that measures every tile.
     OrderKey key;
     memset(&key, 0, sizeof(key));
-    key.v[0] = F.width; key.v[1] = F.height; key.v[2] = F.rank; key.v[3] = F.world; key.v[4] = F.row_block; key.v[5] = F.layout;
+    key.v[0] = F.width; key.v[1] = F.height; key.v[2] = F.rank; key.v[3] = F.world; key.v[4] = F.row_block; key.v[5] = F.layout | ((long long)F.col_block << 8);
     key.v[6] = F.setting.enable_monte_carlo; key.v[7] = F.n_tiles; key.v[8] = F.setting.max_depth; key.v[9] = F.samples;
     key.scene_signature = scene->signature;
     key.cam = F.cam;
@@ -1043,7 +1061,7 @@ static int renderCommon(rtb_ctx *ctx, const rtb_scene *scene, FrameParams &F, co
 {
     const bool host_frame = sync; // rtb_render's zero-copy path: d_out is the device alias of a page-locked host buffer
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    const size_t bytes = (size_t)F.n_local_rows * F.width * 3 * (F.rgb8 ? 1 : sizeof(float));
+    const size_t bytes = (size_t)F.n_local_rows * F.local_width * 3 * (F.rgb8 ? 1 : sizeof(float));
     if (F.n_local_rows == 0)
     {
         if (stats) { memset(stats, 0, sizeof(*stats)); }
@@ -1054,7 +1072,7 @@ static int renderCommon(rtb_ctx *ctx, const rtb_scene *scene, FrameParams &F, co
     if (rc != RTB_OK) return rc;
     // whole-tile 128-bit stores (storeTile): row-major frames whose 8-pixel row segments are 16-byte aligned
     static const bool wideStore = !(getenv("RTB_WIDE_STORE") && atoi(getenv("RTB_WIDE_STORE")) == 0);
-    F.wide_store = wideStore && !F.layout && !F.cost_map && F.width % 4 == 0 && ((uintptr_t)d_out & 15u) == 0;
+    F.wide_store = wideStore && !F.layout && !F.cost_map && F.local_width % 4 == 0 && ((uintptr_t)d_out & 15u) == 0;
     if (stats || h_out || sync) CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], stream));
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(Counters), stream));
     if (stats) CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], stream));
@@ -1109,7 +1127,7 @@ extern "C" int rtb_render(rtb_ctx *ctx, const rtb_scene *scene, const rtb_camera
     if (rc != RTB_OK) return rc;
     if (!rgb_out) return fail(ctx, RTB_ERR_INVALID, "rtb_render: null output buffer");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    const size_t bytes = (size_t)F.n_local_rows * F.width * 3 * (F.rgb8 ? 1 : sizeof(float));
+    const size_t bytes = (size_t)F.n_local_rows * F.local_width * 3 * (F.rgb8 ? 1 : sizeof(float));
     { // Page-locked output buffer (rtb_host_alloc / cudaHostAlloc / cudaHostRegister): the kernels store the pixels
       // straight into it over PCIe while they render, instead of a device framebuffer and a copy after the last
       // kernel.  Measured on the 4K SAH frame (scene upload + render + frame in host memory): 9.71 -> 8.77 ms; the
@@ -1121,7 +1139,7 @@ extern "C" int rtb_render(rtb_ctx *ctx, const rtb_scene *scene, const rtb_camera
         // whole 24-byte row segments with the light tiles in raster order (6.72 -> 6.33 ms); written byte by byte
         // they were slower than a device frame + copy (8.82 vs 7.91 ms)
         static const bool zerocopy8 = !(getenv("RTB_ZEROCOPY_RGB8") && atoi(getenv("RTB_ZEROCOPY_RGB8")) == 0);
-        const bool rgb8Direct = zerocopy8 && !F.layout && F.width % 4 == 0;
+        const bool rgb8Direct = zerocopy8 && !F.layout && F.local_width % 4 == 0;
         if (zerocopy && !F.cost_map && (!F.rgb8 || rgb8Direct) && cudaPointerGetAttributes(&attr, rgb_out) == cudaSuccess && attr.type == cudaMemoryTypeHost &&
             attr.devicePointer)
             return renderCommon(ctx, scene, F, frame, (float *)attr.devicePointer, ctx->stream, stats, nullptr, true);
@@ -1180,6 +1198,22 @@ extern "C" int rtb_unshard_device(rtb_ctx *ctx, const void *gathered, void *imag
     return RTB_OK;
 }
 
+extern "C" int rtb_unshard_cols_device(rtb_ctx *ctx, const void *gathered, void *image, int32_t width, int32_t height,
+                                       int32_t world, int32_t row_block, int32_t col_block, void *stream)
+{
+    if (!ctx || !gathered || !image || width <= 0 || height <= 0 || world <= 0 || row_block <= 0 || col_block <= 0 || col_block % 8 != 0 ||
+        width % ((int64_t)world * col_block) != 0)
+        return fail(ctx, RTB_ERR_INVALID, "rtb_unshard_cols_device: bad argument");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    unsigned int bx = (unsigned int)(((size_t)width * 3 / 4 + 255) / 256);
+    if (bx == 0) bx = 1;
+    if (bx > 8) bx = 8;
+    k_unshard_cols<<<dim3(bx, height), 256, 0, stream ? (cudaStream_t)stream : ctx->stream>>>(
+        (const float *)gathered, (float *)image, width, height, world, row_block, col_block);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return RTB_OK;
+}
+
 // ---- parity hooks -----------------------------------------------------------------------------
 template <class T> struct DevBuf
 {
@@ -1197,7 +1231,7 @@ extern "C" int rtb_trace_primary(rtb_ctx *ctx, const rtb_scene *scene, const rtb
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     FrameParams F;
     memset(&F, 0, sizeof(F));
-    F.cam = *cam; F.width = width; F.height = height; F.rank = 0; F.world = 1; F.row_block = 8; F.n_local_rows = height;
+    F.cam = *cam; F.width = width; F.height = height; F.rank = 0; F.world = 1; F.row_block = 8; F.n_local_rows = height; F.local_width = width;
     F.tiles_x = (width + RTB_TILE_W - 1) / RTB_TILE_W;
     F.n_tiles = F.tiles_x * ((height + RTB_TILE_H - 1) / RTB_TILE_H);
     F.warps_per_cta = RTB_CTA_THREADS / 32;

@@ -156,11 +156,8 @@ k_whitted_chain_oct(const __grid_constant__ DScene S, const __grid_constant__ Fr
             else
             {
                 const unsigned int p = (w & 7u) * 4u + g;
-                x = tx * RTB_TILE_W + (int)(p & 7u);
                 lr = ty * RTB_TILE_H + (int)(p >> 3);
-                const int lb = lr / F.row_block;
-                y = (lb * F.world + F.rank) * F.row_block + (lr - lb * F.row_block);
-                if (x < F.width && lr < F.n_local_rows && y < F.height)
+                if (localToGlobal(F, tx * RTB_TILE_W + (int)(p & 7u), lr, x, y))
                 {
                     const float dx = 1.0f / F.height, dy = 1.0f / F.height;
                     const float sx = (x + 0.5f) * dx, sy = 1 - (y + 0.5f) * dy;

@@ -31,11 +31,9 @@ k_whitted_chain_wide(const __grid_constant__ DScene S, const __grid_constant__ F
     if (item >= F.n_wide || item >= (unsigned int)F.n_tiles) return;
     const unsigned int tile = __ldg(F.order + item);
     const int ty = tile / F.tiles_x, tx = tile - ty * F.tiles_x;
-    const int x = tx * RTB_TILE_W + (int)(w & 7u);
     const int lr = ty * RTB_TILE_H + (int)((w >> 3) & 3u);
-    const int lb = lr / F.row_block;
-    const int y = (lb * F.world + F.rank) * F.row_block + (lr - lb * F.row_block);
-    if (!(x < F.width && lr < F.n_local_rows && y < F.height)) return; // warp-uniform
+    int x, y;
+    if (!localToGlobal(F, tx * RTB_TILE_W + (int)(w & 7u), lr, x, y)) return; // warp-uniform
     unsigned int rays = 0;
     Probe prTop, prWalk; // prTop: work every lane repeats (top-level geometries); prWalk: the tunnel walk
     const V3 c = chainWith(S, F, x, y, rays, prTop, [&](const Ray &r, Hit &h) {

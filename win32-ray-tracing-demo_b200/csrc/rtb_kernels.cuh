@@ -20,6 +20,8 @@ struct FrameParams
     rtb_render_setting setting;
     int width, height, samples;
     int rank, world, row_block, layout;
+    int col_block;   // > 0: column-block sharding (localToGlobal); 0: whole rows
+    int local_width; // width of this rank's local image (= width unless col_block)
     int n_local_rows;
     int cost_map;
     int rgb8; // RTB_OUTPUT_RGB8
@@ -65,6 +67,33 @@ __device__ __forceinline__ unsigned int heavyCount(const FrameParams &F)
 #define RTB_HEAVY_FRACTION 128 // at most 1/128 of the tiles
 #endif
 
+// Local image -> frame.  A rank renders a LOCAL image of local_width x n_local_rows pixels (tiles, tile order and
+// framebuffer slots are local); two ways of cutting the frame (rtb_frame.col_block):
+//   rows    (col_block == 0): blocks of row_block rows dealt round-robin -- local row lr is global row
+//           (lb * world + rank) * row_block + lr % row_block, lb = lr / row_block; x is unchanged;
+//   columns (col_block > 0): every rank renders every row, and of block row by = y / row_block the column blocks bx
+//           with (bx + by) % world == rank -- local column block c is global block c * world + (rank - by) mod world.
+//           The tunnel frames concentrate their cost around the vanishing point; with rows, whichever ranks own those
+//           few row blocks finish last, with narrow column blocks every rank holds the same mix of tiles.
+// false when the local pixel lies outside the frame.
+__device__ __forceinline__ bool localToGlobal(const FrameParams &F, int xl, int lr, int &x, int &y)
+{
+    if (F.col_block)
+    {
+        y = lr;
+        const int by = lr / F.row_block;
+        const int c = xl / F.col_block;
+        int shift = (F.rank - by) % F.world;
+        if (shift < 0) shift += F.world;
+        x = (c * F.world + shift) * F.col_block + (xl - c * F.col_block);
+        return xl < F.local_width && y < F.height; // x < width: width is a multiple of world * col_block
+    }
+    x = xl;
+    const int lb = lr / F.row_block;
+    y = (lb * F.world + F.rank) * F.row_block + (lr - lb * F.row_block);
+    return x < F.width && lr < F.n_local_rows && y < F.height;
+}
+
 // warp -> tile -> (x, local row, global y); false when the thread has no pixel
 __device__ __forceinline__ bool pixelOfThread(const FrameParams &F, int &x, int &lr, int &y, unsigned int &tile)
 {
@@ -77,16 +106,22 @@ __device__ __forceinline__ bool pixelOfThread(const FrameParams &F, int &x, int 
     tile = F.order ? __ldg(F.order + item) : item;
     const int ty = tile / F.tiles_x, tx = tile - ty * F.tiles_x;
     if (F.split4 && lane >= 8) return false; // 8 active lanes: row (w & 3) of the tile
-    x = tx * RTB_TILE_W + (lane & 7);
+    const int xl = tx * RTB_TILE_W + (lane & 7);
     lr = ty * RTB_TILE_H + (F.split4 ? (int)(w & 3u) : (lane >> 3));
-    const int lb = lr / F.row_block;
-    y = (lb * F.world + F.rank) * F.row_block + (lr - lb * F.row_block);
-    return x < F.width && lr < F.n_local_rows && y < F.height;
+    return localToGlobal(F, xl, lr, x, y);
 }
 
+// framebuffer slot of global pixel (x, y) = local row lr
 __device__ __forceinline__ size_t pixelSlot(const FrameParams &F, int x, int lr, int y)
 {
-    return F.layout == RTB_LAYOUT_REFERENCE ? ((size_t)x * F.height + y) : ((size_t)lr * F.width + x);
+    if (F.layout == RTB_LAYOUT_REFERENCE) return (size_t)x * F.height + y;
+    int xl = x;
+    if (F.col_block)
+    {
+        const int bx = x / F.col_block;
+        xl = (bx / F.world) * F.col_block + (x - bx * F.col_block);
+    }
+    return (size_t)lr * F.local_width + xl;
 }
 
 // framebuffer store: float RGB, or the reference's 8-bit output stage (MainWindow.cpp:305-311)
@@ -118,7 +153,7 @@ __device__ __forceinline__ bool storeTile(const FrameParams &F, float *out, unsi
     const int lane = threadIdx.x & 31;
     const int ty = tile / F.tiles_x, tx = tile - ty * F.tiles_x;
     const int row = lane / 6, j = lane - row * 6; // lanes 0..23: row 0..3, 16-byte (4-byte) chunk 0..5 of the row segment
-    const size_t rowSlot = (size_t)(ty * RTB_TILE_H + row) * F.width + (size_t)tx * RTB_TILE_W;
+    const size_t rowSlot = (size_t)(ty * RTB_TILE_H + row) * F.local_width + (size_t)tx * RTB_TILE_W;
     if (F.rgb8)
     {
         unsigned char *sb = reinterpret_cast<unsigned char *>(stage);
@@ -680,6 +715,27 @@ k_unshard(const float *__restrict__ gathered, float *__restrict__ image, int wid
     }
     else
         for (size_t i = blockIdx.x * blockDim.x + threadIdx.x; i < rowFloats; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+// Column-block shards (localToGlobal): gathered = [world][height][width / world][3]; one thread per float4 of a
+// column block row segment (col_block is a multiple of 8 pixels = 96 bytes)
+__global__ void __launch_bounds__(256)
+k_unshard_cols(const float *__restrict__ gathered, float *__restrict__ image, int width, int height, int world, int row_block,
+               int col_block)
+{
+    const int y = blockIdx.y;
+    const int by = y / row_block;
+    const int localWidth = width / world;
+    const int segFloat4 = col_block * 3 / 4, nbx = width / col_block;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nbx * segFloat4; i += gridDim.x * blockDim.x)
+    {
+        const int bx = i / segFloat4, q = i - bx * segFloat4;
+        const int rank = (bx + by) % world;
+        const int xl0 = (bx / world) * col_block;
+        const float4 *src = reinterpret_cast<const float4 *>(gathered + (((size_t)rank * height + y) * localWidth + xl0) * 3);
+        float4 *dst = reinterpret_cast<float4 *>(image + ((size_t)y * width + (size_t)bx * col_block) * 3);
+        dst[q] = src[q];
+    }
 }
 
 } // namespace rtb
