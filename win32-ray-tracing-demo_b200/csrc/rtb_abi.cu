@@ -1092,7 +1092,7 @@ static int renderCommon(rtb_ctx *ctx, const rtb_scene *scene, FrameParams &F, co
         const int floorDelta = host_frame ? floorDeltaHost : floorDeltaDevice;
         k_cost_histogram<<<blocks, 256, 0, stream>>>(ctx->d_cost, F.n_tiles, ctx->d_hist);
         const bool smallShard = F.n_tiles <= splitMaxTiles();
-        k_cost_offsets<<<1, 32, 0, stream>>>(ctx->d_hist, ctx->d_cursor, ctx->d_heavy, F.n_tiles,
+        k_cost_offsets<<<1, RTB_COST_BUCKETS, 0, stream>>>(ctx->d_hist, ctx->d_cursor, ctx->d_heavy, F.n_tiles,
                                              smallShard ? heavyBucketsSmall() : RTB_HEAVY_BUCKETS,
                                              heavyLimit(F.n_tiles), wideCount(F.n_tiles, scene->long_lists), floorDelta);
         k_cost_scatter<<<blocks, 256, 0, stream>>>(ctx->d_cost, F.n_tiles, ctx->d_cursor, ctx->d_order, ctx->d_heavy);

@@ -232,6 +232,11 @@ __global__ void k_cost_histogram(const unsigned int *__restrict__ cost, int n, u
 __global__ void k_cost_offsets(unsigned int *__restrict__ hist, unsigned int *__restrict__ cursor, unsigned int *__restrict__ n_heavy,
                                int n_tiles, int heavy_buckets, int heavy_limit, int wide_count, int floor_delta)
 {
+    // launched with RTB_COST_BUCKETS threads: the histogram is fetched (and cleared for the next frame) in parallel,
+    // the short serial pass below then runs out of shared memory (18 -> ~4 us; it sits at the end of every frame)
+    __shared__ unsigned int h[RTB_COST_BUCKETS];
+    for (int b = threadIdx.x; b < RTB_COST_BUCKETS; b += blockDim.x) { h[b] = hist[b]; hist[b] = 0; }
+    __syncthreads();
     if (threadIdx.x == 0)
     {
         int floorBucket = 0;
@@ -241,7 +246,7 @@ __global__ void k_cost_offsets(unsigned int *__restrict__ hist, unsigned int *__
             int median = 0;
             for (int b = 0; b < RTB_COST_BUCKETS; b++)
             {
-                below += hist[b];
+                below += h[b];
                 if (2u * below >= (unsigned int)n_tiles) { median = b; break; }
             }
             floorBucket = min(median + floor_delta, RTB_COST_BUCKETS - 1);
@@ -252,10 +257,9 @@ __global__ void k_cost_offsets(unsigned int *__restrict__ hist, unsigned int *__
         for (int b = RTB_COST_BUCKETS - 1; b >= 0; b--)
         {
             if (b >= floorBucket) cursor[b] = run; // buckets below the floor are placed through cursor[floorBucket]
-            run += hist[b];
+            run += h[b];
             if (top2 < 0 && run > wide) top2 = b;
             if (top2 >= 0 && b >= top2 - heavy_buckets) heavy = run;
-            hist[b] = 0;
         }
         if (heavy < wide) heavy = wide;
         // a bucket may be cut: with whole buckets only, a well-filled bucket at the top (flat cost distributions)

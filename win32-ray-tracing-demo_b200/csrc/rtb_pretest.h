@@ -187,12 +187,15 @@ __device__ __forceinline__ void sureReject2(const PreTri2 &T, float ox, float oy
     const float2 hiK = __ffma2_rn(bc(RTB_PRE_CH), mk, kap), cLo = __ffma2_rn(bc(RTB_PRE_CL), mk, kap); // cLo = -loK
     const float2 hiA = __fadd2_rn(hiK, kap);
     const float2 tLow = __fmul2_rn(bc(Lp), mlo), tHigh = __fmul2_rn(bc(Hp), mk);
+    // sign of det_M' transferred by an exact multiplication with +-1 (one packed instruction per determinant instead of
+    // one LOP3 per half; same values as xorSign up to the sign of a NaN, which no comparison sees)
+    const float2 sg = make_float2(__uint_as_float(signOf(dM.x) | 0x3f800000u), __uint_as_float(signOf(dM.y) | 0x3f800000u));
+    const float2 Bt = __fmul2_rn(dB, sg), Gn = __fmul2_rn(dGn, sg) /* = -G~ */, Tt = __fmul2_rn(dT, sg);
+    const float2 sBG = __fadd2_rn(Bt, neg2(Gn)), tPlus = __fadd2_rn(Tt, kT), tMinus = __fadd2_rn(Tt, neg2(kT));
 #define RTB_PRE_HALF(h, out)                                                                                                  \
     {                                                                                                                         \
-        const uint32_t s = signOf(dM.h);                                                                                      \
-        const float Bt = xorSign(dB.h, s), Gn = xorSign(dGn.h, s) /* = -G~ */, Tt = xorSign(dT.h, s);                          \
-        bool r = (Bt < -cLo.h) | (Bt > hiK.h) | (Gn > cLo.h) | (Gn < -hiK.h) | (Bt - Gn > hiA.h) | (Tt + kT.h < tLow.h);       \
-        if (HIGH) r = r | (Tt - kT.h > tHigh.h);                                                                              \
+        bool r = (Bt.h < -cLo.h) | (Bt.h > hiK.h) | (Gn.h > cLo.h) | (Gn.h < -hiK.h) | (sBG.h > hiA.h) | (tPlus.h < tLow.h);   \
+        if (HIGH) r = r | (tMinus.h > tHigh.h);                                                                               \
         out = r & (mlo.h > 0.f);                                                                                              \
     }
     RTB_PRE_HALF(x, rej0)
