@@ -412,6 +412,15 @@ def test_upload_rejects_bad_scenes(ctx):
     f, keep = corrupted("kd_leaf_tris", nr, C.c_uint32, lambda a: a.__setitem__(nr // 2, nt))
     with pytest.raises(rtb200.RtbError):
         ctx.upload(f)
+    # a wildly out-of-range reference must be refused BEFORE the upload's own kernels index with it (k_pack_pairs):
+    # the context stays usable afterwards
+    f, keep = corrupted("kd_leaf_tris", nr, C.c_uint32, lambda a: a.__setitem__(0, 0x7fffffff))
+    with pytest.raises(rtb200.RtbError):
+        ctx.upload(f)
+    ok = ctx.upload(s.flat)
+    img, _ = ok.render(s.camera, s.setting, rtb200.make_frame(32, 24))
+    assert np.isfinite(img).all()
+    ok.close()
     f, keep = corrupted("tri_material", nt, C.c_int32, lambda a: a.__setitem__(nt - 1, -1))
     with pytest.raises(rtb200.RtbError):
         ctx.upload(f)

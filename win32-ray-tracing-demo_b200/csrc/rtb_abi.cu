@@ -576,8 +576,8 @@ static int buildGridOnDevice(rtb_ctx *ctx, rtb_scene *s, const rtb_flat_scene *f
 
 // Index / structure checks of rtb_scene_upload that scan whole streams (k-d nodes, leaf and cell references: 0.6 ms
 // of a 1 ms upload on the host) run on worker threads while the calling thread stages and queues the copies.  The
-// verdict is collected before the upload returns: nothing that indexes with those streams is launched earlier
-// (the copies and k_pack_triangles do not).
+// verdict is collected before anything that indexes with those streams is launched (k_pack_pairs, the renders); the
+// copies and k_pack_triangles do not index.
 struct BackgroundChecks
 {
     std::vector<std::thread> threads;
@@ -723,6 +723,9 @@ extern "C" int rtb_scene_upload(rtb_ctx *ctx, const rtb_flat_scene *f, rtb_scene
             d.g_words = words;
             if ((rc = uploadArray(ctx, s, f->grid_cell_start, (size_t)f->n_cells_used + 1, &d.g_start)) != RTB_OK) return bail(rc);
             if ((rc = uploadArray(ctx, s, f->grid_cell_tris, (size_t)f->n_cell_refs, &d.g_tris)) != RTB_OK) return bail(rc);
+            // k_pack_pairs indexes the triangle stream with these references: the verdict of the checks comes first
+            checks.join();
+            if (checks.code != RTB_OK) return bail(fail(ctx, checks.code, checks.msg));
             if ((rc = packPairs(ctx, s, d.g_tris, (size_t)f->n_cell_refs)) != RTB_OK) return bail(rc);
             s->grid_cells_used = f->n_cells_used; s->grid_refs = f->n_cell_refs; s->grid_words = f->n_cellwords;
         }
@@ -760,6 +763,9 @@ extern "C" int rtb_scene_upload(rtb_ctx *ctx, const rtb_flat_scene *f, rtb_scene
             if ((rc = uploadArray(ctx, s, (const uint2 *)f->kd_nodes, (size_t)f->n_kd_nodes, &nodes)) != RTB_OK) return bail(rc);
             d.kd_nodes = nodes;
             if ((rc = uploadArray(ctx, s, f->kd_leaf_tris, (size_t)f->n_kd_refs, &d.kd_tris)) != RTB_OK) return bail(rc);
+            // k_pack_pairs indexes the triangle stream with these references: the verdict of the checks comes first
+            checks.join();
+            if (checks.code != RTB_OK) return bail(fail(ctx, checks.code, checks.msg));
             if ((rc = packPairs(ctx, s, d.kd_tris, (size_t)f->n_kd_refs)) != RTB_OK) return bail(rc);
         }
         else if (f->accel == RTB_ACCEL_CONVEX || f->accel == RTB_ACCEL_CONVEX_SIMPLE)
