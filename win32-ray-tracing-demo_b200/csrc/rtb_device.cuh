@@ -79,7 +79,8 @@ struct DScene
     const float4 *loose;
     const float4 *tri;
     // the same triangles for the conservative rejection test (rtb_pretest.h): 3 x float4 = {a.xyz, A1 eps}
-    // {e1.xyz, E eps} {e2.xyz, 0}; the per-lane list scans read THIS stream and touch `tri` only for candidates
+    // {e1.xyz, E eps} {e2.xyz, 0}, indexed by triangle; source of the pair stream below (k_pack_pairs).  The list
+    // scans read the pair stream and touch `tri` only for candidates
     const float4 *tri_pre;
     // PAIR stream of the active accelerator's reference array (kd_tris or g_tris): for positions 2p and 2p + 1 six
     // float4 with the two triangles' rejection-test records interleaved component by component (rtb_pretest.h:
@@ -161,17 +162,6 @@ __device__ __forceinline__ TriData loadTri(const float4 *base, unsigned int idx)
     return t;
 }
 __device__ __forceinline__ V3 triNormal(const TriData &t) { return v3(t.q2.y, t.q2.z, t.q2.w); }
-__device__ __forceinline__ rtb_pre::PreTri loadPreTri(const float4 *base, unsigned int idx)
-{
-    const float4 *p = base + 3ull * idx;
-    const float4 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2);
-    rtb_pre::PreTri t;
-    t.ax = q0.x; t.ay = q0.y; t.az = q0.z; t.a1e = q0.w;
-    t.e1x = q1.x; t.e1y = q1.y; t.e1z = q1.z; t.ee = q1.w;
-    t.e2x = q2.x; t.e2y = q2.y; t.e2z = q2.z; t.pad = 0.f;
-    return t;
-}
-
 __device__ __forceinline__ rtb_pre::PreTri2 loadPreTri2(const float4 *base, unsigned int pair)
 {
     const float4 *p = base + 6ull * pair;
