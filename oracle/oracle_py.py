@@ -141,7 +141,7 @@ def bounce(which, xy, radius=2000.0, angle=1.5708, arch_seg=150, path_seg=150, a
     if which == "oracle" and not os.path.exists(path):
         build_oracle()
     lib = C.CDLL(path)
-    fn = getattr(lib, {"oracle": "rt_oracle_bounce", "ref_pt": "ref_pt_bounce"}.get(which, "ref_bounce"))
+    fn = getattr(lib, {"oracle": "rt_oracle_bounce", "pretest": "rt_oracle_bounce", "ref_pt": "ref_pt_bounce"}.get(which, "ref_bounce"))
     fn.argtypes = [C.POINTER(BounceJob)]
     fn.restype = C.c_int
     xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)

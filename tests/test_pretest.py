@@ -67,3 +67,22 @@ def test_pretest_random_stress(pre):
     assert violations == 0
     assert accepts > 0.15 * pairs          # the stress really exercises accepted hits
     assert candidates >= accepts
+
+
+@pytest.mark.parametrize("algorithm,pt_builders,radius,angle", [("sah", True, 2000.0, 1.5708), ("rgrid", False, 500.0, 1.0),
+                                                                ("kd", False, 2000.0, 1.5708)])
+def test_pretest_on_mirror_bounce_chains(pre, algorithm, pt_builders, radius, angle):
+    """The PerformanceTest workload (up to 200 mirror bounces per sample down the tunnel: long chains of grazing rays
+    started exactly on a surface, the PT program's own ring orientation and event-sweep SAH tree): zero violations."""
+    import numpy as np
+    rng = np.random.default_rng(5)
+    xy = rng.random((3000, 2)).astype(np.float32)
+    pre.rt_oracle_pretest_mode(0)
+    _stats(pre)  # reset
+    O._LIBS["pretest"] = (LIB, "rt_oracle_run")
+    r = O.bounce("pretest", xy, radius=radius, angle=angle, arch_seg=150, path_seg=150, algorithm=algorithm, max_depth=200,
+                 pt_builders=pt_builders)
+    st = _stats(pre)
+    assert r["total_rays"] > 3000 and st["tests"] > 0
+    assert st["violations"] == 0
+    assert st["updates"] > 0
