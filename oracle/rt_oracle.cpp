@@ -1621,6 +1621,104 @@ extern "C" void rt_oracle_pretest_fuzz(uint64_t seed, long long n, long long *ou
     }
     out[0] = n; out[1] = acc; out[2] = cand; out[3] = viol;
 }
+// The BOUND itself, not only the decisions built on it.  For random pairs (same generator as above) the four
+// determinants are evaluated three ways -- the reference's float association (det3), the cheap FMA form of
+// rtb_pretest.h (restated here operation by operation; the decisions derived from this restatement are compared with
+// rtb_pre::sureReject so that the two cannot drift apart) and exactly, in binary128 (a product of three floats has
+// 72 significant bits) -- and the header's claims are measured:
+//   out[0] = max |det_ref - Det| / (gamma_7 S)           claim: <= 1  (S = sum of the absolute triple products)
+//   out[1] = max |det'    - Det| / (gamma_5 S)           claim: <= 1
+//   out[2] = max |det' - det_ref| / kappa (M, B, G)      claim: <= 1, the header leaves a factor >= 2.6
+//   out[3] = max |detT' - detT_ref| / kT                 claim: <= 1
+//   out[4] = pairs on which the restated decisions differ from rtb_pre::sureReject (must be 0)
+// Pairs whose determinants underflow (|S| < 1e-30) are skipped: the header's floor covers them separately.
+extern "C" void rt_oracle_pretest_bound_fuzz(uint64_t seed, long long n, double *out)
+{
+    typedef __float128 Q;
+    const double u = ldexp(1.0, -24), g7 = 7 * u / (1 - 7 * u), g5 = 5 * u / (1 - 5 * u);
+    double mRef = 0, mCheap = 0, mKap = 0, mKt = 0;
+    long long drift = 0;
+#pragma omp parallel for reduction(max : mRef, mCheap, mKap, mKt) reduction(+ : drift) schedule(static)
+    for (long long i = 0; i < n; i++)
+    {
+        uint32_t ctr[4] = {(uint32_t)i, (uint32_t)(i >> 32), 0, 0}, key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)}, r[4];
+        float v[20];
+        for (int b = 0; b < 5; b++)
+        {
+            ctr[2] = (uint32_t)b;
+            philox4x32_10(ctr, key, r);
+            for (int q = 0; q < 4; q++) v[4 * b + q] = (float)((r[q] >> 8) * (1.0 / 16777216.0));
+        }
+        const float scale = powf(10.0f, -3.0f + 7.0f * v[0]), aspect = powf(10.0f, -3.0f * v[1]);
+        const float offset = (v[2] < 0.5f) ? 0.0f : powf(10.0f, 5.0f * v[3]) - 1.0f;
+        const V3 a = v3(offset + scale * (v[4] - 0.5f), offset * 0.5f + scale * (v[5] - 0.5f), scale * (v[6] - 0.5f) - offset);
+        const V3 bb = a + v3(scale * (v[7] - 0.5f), scale * (v[8] - 0.5f), scale * (v[9] - 0.5f));
+        const V3 cc = a + v3(scale * aspect * (v[10] - 0.5f), scale * aspect * (v[11] - 0.5f), scale * aspect * (v[12] - 0.5f));
+        const float be = v[13] * 1.2f - 0.1f, ga = v[14] * 1.2f - 0.1f;
+        const V3 target = a + (bb - a) * be + (cc - a) * ga;
+        V3 dir = normalize(v3(v[16] - 0.5f, v[17] - 0.5f, v[18] - 0.5f));
+        if (v[19] < 0.3f)
+        {
+            const V3 nrm = cross(bb - a, cc - a);
+            const float nl = length(nrm);
+            if (nl > 0) { const V3 nn = nrm * (1 / nl); dir = normalize(dir - nn * (dot(dir, nn) * (1.0f - 1e-3f * v[16]))); }
+        }
+        const float dist = scale * powf(10.0f, -2.0f + 5.0f * v[17]);
+        const V3 o = target - dir * dist;
+        const V3 d = (v[18] < 0.8f) ? dir : dir * (0.25f + 3.0f * v[19]);
+        const float rec[9] = {a.x, a.y, a.z, bb.x, bb.y, bb.z, cc.x, cc.y, cc.z};
+        const rtb_pre::PreTri T = rtb_pre::makePreTri(rec);
+        // ---- the float inputs both sides share
+        const float e1[3] = {T.e1x, T.e1y, T.e1z}, e2[3] = {T.e2x, T.e2y, T.e2z}, dd[3] = {d.x, d.y, d.z};
+        const float b[3] = {T.ax - o.x, T.ay - o.y, T.az - o.z};
+        // ---- reference association (Triangle.cpp:25-36, 84-106)
+        const float rM = det3(e1[0], e2[0], dd[0], e1[1], e2[1], dd[1], e1[2], e2[2], dd[2]);
+        const float rT = det3(e1[0], e2[0], b[0], e1[1], e2[1], b[1], e1[2], e2[2], b[2]);
+        const float rB = det3(b[0], e2[0], dd[0], b[1], e2[1], dd[1], b[2], e2[2], dd[2]);
+        const float rG = det3(e1[0], b[0], dd[0], e1[1], b[1], dd[1], e1[2], b[2], dd[2]);
+        // ---- rtb_pretest.h, operation by operation
+        const float px = fmaf(e2[1], dd[2], -(e2[2] * dd[1])), py = fmaf(e2[2], dd[0], -(e2[0] * dd[2])), pz = fmaf(e2[0], dd[1], -(e2[1] * dd[0]));
+        const float cM = fmaf(e1[2], pz, fmaf(e1[1], py, e1[0] * px)), cB = fmaf(b[2], pz, fmaf(b[1], py, b[0] * px));
+        const float qx = fmaf(b[1], e1[2], -(b[2] * e1[1])), qy = fmaf(b[2], e1[0], -(b[0] * e1[2])), qz = fmaf(b[0], e1[1], -(b[1] * e1[0]));
+        const float cT = fmaf(e2[2], qz, fmaf(e2[1], qy, e2[0] * qx)), cGn = fmaf(dd[2], qz, fmaf(dd[1], qy, dd[0] * qx));
+        const float bn = fabsf(b[0]) + fabsf(b[1]) + fabsf(b[2]);
+        const float dmx = rtb_pre::dirMax(d.x, d.y, d.z);
+        const float kap = dmx * fmaf(T.ee, bn, T.a1e), kT = T.a1e * bn;
+        // ---- exact
+        auto det = [](const float *c0, const float *c1, const float *c2, Q &S) {
+            const Q t[6] = {(Q)c0[0] * c1[1] * c2[2], (Q)c1[0] * c2[1] * c0[2], (Q)c2[0] * c0[1] * c1[2],
+                            (Q)c2[0] * c1[1] * c0[2], (Q)c0[0] * c2[1] * c1[2], (Q)c1[0] * c0[1] * c2[2]};
+            S = 0;
+            for (int k = 0; k < 6; k++) S += t[k] < 0 ? -t[k] : t[k];
+            return t[0] + t[1] + t[2] - t[3] - t[4] - t[5];
+        };
+        Q sM, sT, sB, sG;
+        const Q xM = det(e1, e2, dd, sM), xT = det(e1, e2, b, sT), xB = det(b, e2, dd, sB), xG = det(e1, b, dd, sG);
+        auto ab = [](Q x) { return (double)(x < 0 ? -x : x); };
+        const struct { float ref, cheap; Q exact, S; double bound; bool isT; } D[4] = {
+            {rM, cM, xM, sM, kap, false}, {rB, cB, xB, sB, kap, false}, {rG, -cGn, xG, sG, kap, false}, {rT, cT, xT, sT, kT, true}};
+        for (int k = 0; k < 4; k++)
+        {
+            const double S = (double)D[k].S;
+            if (!(S > 1e-30) || !(S < 1e30)) continue;
+            mRef = fmax(mRef, ab((Q)D[k].ref - D[k].exact) / (g7 * S));
+            mCheap = fmax(mCheap, ab((Q)D[k].cheap - D[k].exact) / (g5 * S));
+            const double diff = fabs((double)D[k].cheap - (double)D[k].ref) / (double)D[k].bound;
+            if (D[k].isT) mKt = fmax(mKt, diff); else mKap = fmax(mKap, diff);
+        }
+        // ---- the restatement above must decide like the header
+        const float Lp = rtb_pre::lowBound(-FLT_MAX), Hp = rtb_pre::highBound(dist * 2.0f, FLT_MAX);
+        const float m = fabsf(cM);
+        const uint32_t sg = rtb_pre::signOf(cM);
+        const float Bt = rtb_pre::xorSign(cB, sg), Gt = rtb_pre::xorSign(cGn, sg ^ 0x80000000u), Tt = rtb_pre::xorSign(cT, sg);
+        const float mk = m + kap, mlo = m - kap;
+        const float hiK = fmaf(RTB_PRE_CH, mk, kap), loK = -fmaf(RTB_PRE_CL, mk, kap);
+        const bool mine = ((Bt < loK) | (Bt > hiK) | (Gt < loK) | (Gt > hiK) | (Bt + Gt > hiK + kap) | (Tt + kT < Lp * mlo) | (Tt - kT > Hp * mk)) & (mlo > 0.f);
+        drift += mine != rtb_pre::sureReject<true>(T, o.x, o.y, o.z, d.x, d.y, d.z, dmx, Lp, Hp);
+    }
+    out[0] = mRef; out[1] = mCheap; out[2] = mKap; out[3] = mKt; out[4] = (double)drift;
+}
+
 extern "C" void rt_oracle_pretest_mode(int use_nearest) { g_pre_use_nearest = use_nearest; }
 extern "C" void rt_oracle_pretest_stats(long long *out)
 {

@@ -86,3 +86,19 @@ def test_pretest_on_mirror_bounce_chains(pre, algorithm, pt_builders, radius, an
     assert r["total_rays"] > 3000 and st["tests"] > 0
     assert st["violations"] == 0
     assert st["updates"] > 0
+
+
+def test_pretest_error_bound_against_exact_determinants(pre):
+    """The bound itself: the reference's float determinants, the cheap FMA determinants of rtb_pretest.h and the exact
+    ones (binary128) on random pairs.  The header claims |det_ref - Det| <= gamma_7 S, |det' - Det| <= gamma_5 S and
+    kappa / kT >= |det' - det_ref| with a factor >= 2.6 to spare; the checker's operation-by-operation restatement of
+    the header must decide exactly like the header (no drift between the two)."""
+    pre.rt_oracle_pretest_bound_fuzz.argtypes = [C.c_uint64, C.c_longlong, C.POINTER(C.c_double)]
+    out = (C.c_double * 5)()
+    pre.rt_oracle_pretest_bound_fuzz(7, 4_000_000, out)
+    ref_vs_exact, cheap_vs_exact, kappa_ratio, kt_ratio, drift = list(out)
+    assert 0 < ref_vs_exact <= 1.0
+    assert 0 < cheap_vs_exact <= 1.0
+    assert 0 < kappa_ratio <= 1 / 2.6
+    assert 0 < kt_ratio <= 1 / 2.6
+    assert drift == 0
