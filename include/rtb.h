@@ -204,6 +204,13 @@ int64_t rtb_shard_rows(const rtb_frame *frame);
 /* width of the shard's local image: frame->width, or frame->width / world for a column-block shard */
 int64_t rtb_shard_width(const rtb_frame *frame);
 
+/* Host-only check (no device needed) that nodes[0 .. n) is a well-formed pre-order k-d array as rtb_scene_upload
+ * requires it: every inner node's right child lies behind its left subtree and before the end of the enclosing
+ * subtree, every node belongs to exactly one subtree, no node is deeper than 64.  RTB_OK and *max_depth (root = 0)
+ * or RTB_ERR_INVALID.  rtb_scene_upload runs the same check (and refuses trees whose traversal stack,
+ * 2 * max_depth + 2 entries, would exceed the reference's 50, Tunnel.cpp:1176).                                   */
+int rtb_kd_validate(const rtb_kdnode *nodes, int32_t n, int32_t *max_depth);
+
 /* Upload a flattened scene.  Replaces nothing in the reference (it has no device); it is the
  * device-side image of GeometrySet + Tunnel::grid / Tunnel::root.                           */
 int rtb_scene_upload(rtb_ctx *ctx, const rtb_flat_scene *flat, rtb_scene **scene);

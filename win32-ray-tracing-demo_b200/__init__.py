@@ -112,7 +112,7 @@ ABI_SYMBOLS = ["rtb_init", "rtb_shutdown", "rtb_last_error", "rtb_abi_version", 
                "rtb_host_alloc", "rtb_host_free",
                "rtb_scene_upload", "rtb_scene_free", "rtb_scene_device_bytes", "rtb_scene_upload_bytes", "rtb_scene_grid_hash", "rtb_render",
                "rtb_render_device", "rtb_unshard_device", "rtb_trace_primary", "rtb_intersect_rays", "rtb_bounce_rays",
-               "rtb_selftest_pretest"]
+               "rtb_selftest_pretest", "rtb_kd_validate"]
 
 _cuda = None
 _host = None

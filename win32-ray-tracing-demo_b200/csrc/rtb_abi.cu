@@ -444,6 +444,16 @@ static int kdDepth(const rtb_kdnode *nodes, int n, int &maxDepth)
     return -1; // ran out of nodes with subtrees still open (n == 0 included)
 }
 
+extern "C" int rtb_kd_validate(const rtb_kdnode *nodes, int32_t n, int32_t *max_depth)
+{
+    if (!nodes || n <= 0) return RTB_ERR_INVALID;
+    int depth = 0;
+    if (kdDepth(nodes, n, depth) != 0) return RTB_ERR_INVALID;
+    if (max_depth) *max_depth = depth;
+    return RTB_OK;
+}
+
+
 
 // ---- grid built on the device (rtb_build_grid.cuh) ------------------------------------------------------------
 template <class T> static int deviceArray(rtb_ctx *ctx, rtb_scene *s, size_t n, T **dev, bool keep)
