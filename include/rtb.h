@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define RTB_ABI_VERSION 3
+#define RTB_ABI_VERSION 4
 
 typedef enum rtb_status {
     RTB_OK = 0,
@@ -149,10 +149,23 @@ typedef struct rtb_render_setting {
  * [local_row][x][3] float RGB -- unless RTB_LAYOUT_REFERENCE is set (world must be 1), which
  * gives the reference framebuffer order index = x*height + y (MainWindow.cpp:276).          */
 enum { RTB_LAYOUT_ROWMAJOR = 0, RTB_LAYOUT_REFERENCE = 1,
+       /* OR-able: the output buffer is the WHOLE frame, row-major [height][width][3], and this rank stores only the
+        * pixels of its shard into it, at their place in the frame (slot = y * width + x).  Every rank of a frame is
+        * given the same buffer -- rank 0's device frame opened on the peers through CUDA IPC (rtb_ipc_*: the stores
+        * cross NVLink while the shard renders; no gather, no unshard pass), or one page-locked host frame that all
+        * devices of a process store into (rtb_multi_render).  The reference has exactly one framebuffer
+        * (MainWindow.cpp:257); this is that buffer, filled by several devices.                                     */
+       RTB_LAYOUT_GLOBAL = 2,
        /* OR-able: the output buffer holds 3 BYTES per pixel (R, G, B) produced by the reference's output
         * stage -- saturate (upper clamp only) then (int)(c * 255), MainWindow.cpp:305-311 -- instead of 3
         * floats.  A quarter of the bytes to read back; the float framebuffer is what parity is judged on. */
-       RTB_OUTPUT_RGB8 = 4 };
+       RTB_OUTPUT_RGB8 = 4,
+       /* OR-able, Monte Carlo only: the output buffer holds SIX floats per pixel -- the sum over this call's samples of
+        * the per-sample radiance (R, G, B; the reference accumulates radiance * (1 / samples), MainWindow.cpp:288: here
+        * the plain sum) and the sum of its squares -- the accumulation buffer (sum, sum of squares, spp) of a progressive
+        * or sample-sharded render: buffers of disjoint sample ranges add up, mean = sum / spp,
+        * variance = (sumsq - sum^2 / spp) / (spp - 1).  Not with RTB_OUTPUT_RGB8 / RTB_LAYOUT_REFERENCE.            */
+       RTB_OUTPUT_MOMENTS = 8 };
 typedef struct rtb_frame {
     int32_t width, height;
     int32_t samples;      /* spp when enable_monte_carlo                                      */
@@ -171,6 +184,12 @@ typedef struct rtb_frame {
                              world * col_block, row-major layout.  The tunnel frames concentrate their cost around
                              the vanishing point: narrow column blocks give every rank the same mix of tiles.
                              (Occupies what was tail padding of this struct: zero-initialised callers get rows.)  */
+    int32_t sample_first; /* Monte Carlo SAMPLE shard: this call renders samples [sample_first, sample_first +   */
+    int32_t sample_count; /* sample_count) of the frame's `samples` (0 = all of them).  The RNG is keyed by (pixel,
+                             sample index) and every sample is weighted 1 / samples, so the images of disjoint ranges
+                             ADD UP to the full frame (float rounding of the per-pixel sum aside: the order of the
+                             additions differs from the single pass): low-resolution / high-spp frames shard over
+                             samples instead of rows, one NCCL reduce (sum) assembles them.              */
 } rtb_frame;
 
 typedef struct rtb_stats {
@@ -283,6 +302,55 @@ int rtb_unshard_cols_device(rtb_ctx *ctx, const void *gathered, void *image, int
  * *mismatches = pairs on which the two disagree (must be 0), *rejected = pairs the test rejects (so a caller can see
  * that both outcomes occur).  No reference counterpart: diagnostic entry point.                                     */
 int rtb_selftest_pretest(rtb_ctx *ctx, int64_t n, uint64_t seed, int64_t *mismatches, int64_t *rejected);
+
+/* Progress reporting -- replaces `progress(y + 1, height)` of the reference's row loop (MainWindow.cpp:271; the
+ * ProgressCallback of Scripts.h:9).  While rtb_render / rtb_multi_render wait for the frame they poll the number of
+ * finished tiles (a device counter, read over a side stream; the kernels are not interrupted) and call `fn` from the
+ * calling host thread, every ~0.25 ms and once more when the frame is complete (done == total).  NULL turns it off.  */
+typedef void (*rtb_progress_fn)(int64_t tiles_done, int64_t tiles_total, void *user);
+int rtb_set_progress(rtb_ctx *ctx, rtb_progress_fn fn, void *user);
+
+/* Forget the tile schedule the context has learnt (heaviest-first order and latency tiers of the last view): the next
+ * frame runs like the first frame of a new view -- raster order, one throughput kernel, every tile measured.  The
+ * reference renderer keeps no state between frames (MainWindow.cpp:251-303); this makes that case measurable.       */
+int rtb_forget_schedule(rtb_ctx *ctx);
+
+/* ---- one frame buffer, several devices (RTB_LAYOUT_GLOBAL) -------------------------------------------------------
+ * Replaces the single framebuffer `colors` every OpenMP thread of the reference's Render writes its rows into
+ * (MainWindow.cpp:257, 267-276).
+ *
+ * A: one process per device (torch.distributed / MPI plumbing).  The owner rank allocates the frame with
+ *    rtb_device_alloc (plain cudaMalloc memory: exportable), exports it with rtb_ipc_export, sends the 64 handle bytes
+ *    to its peers by any means, each peer maps it with rtb_ipc_open (peer access over NVLink is enabled as needed) and
+ *    passes the mapped pointer to rtb_render_device with RTB_LAYOUT_GLOBAL.  A barrier of the caller closes the step. */
+#define RTB_IPC_HANDLE_BYTES 64
+int rtb_device_alloc(rtb_ctx *ctx, size_t bytes, void **out);
+int rtb_device_free(rtb_ctx *ctx, void *p);
+int rtb_device_download(rtb_ctx *ctx, const void *device_ptr, void *host, size_t bytes); /* synchronous read-back of such a frame */
+int rtb_ipc_export(rtb_ctx *ctx, void *device_ptr, unsigned char handle[RTB_IPC_HANDLE_BYTES]);
+int rtb_ipc_open(rtb_ctx *ctx, const unsigned char handle[RTB_IPC_HANDLE_BYTES], void **mapped);
+int rtb_ipc_close(rtb_ctx *ctx, void *mapped);
+
+/* B: ONE host thread drives n devices (SURVEY 8b threading row; the drop-in behind Scripts.h:11-12 RenderProc).
+ *    rtb_multi_render shards the frame over the devices (tile rows up to 4 devices, column blocks above), every device
+ *    stores its tiles straight into `rgb_out` -- ONE assembled host frame, row-major [height][width][3] floats (bytes
+ *    with RTB_OUTPUT_RGB8), or the reference order with RTB_LAYOUT_REFERENCE -- and the call returns when all devices
+ *    are done.  `rgb_out` from rtb_host_alloc is written directly over PCIe by all devices at once; any other host
+ *    buffer goes through a page-locked frame owned by the library and one host copy.  frame->rank / world are ignored.
+ *    stats: counts are summed over the devices, kernel_ms / total_ms are the maximum.                                */
+typedef struct rtb_multi rtb_multi;
+typedef struct rtb_multi_scene rtb_multi_scene;
+int rtb_multi_init(int n_devices, const int *devices /* NULL: 0 .. n_devices - 1 */, rtb_multi **out);
+int rtb_multi_shutdown(rtb_multi *m);
+int rtb_multi_count(const rtb_multi *m);
+rtb_ctx *rtb_multi_ctx(rtb_multi *m, int i);
+const char *rtb_multi_last_error(const rtb_multi *m);
+int rtb_multi_set_progress(rtb_multi *m, rtb_progress_fn fn, void *user);
+int rtb_multi_scene_upload(rtb_multi *m, const rtb_flat_scene *flat, rtb_multi_scene **scene); /* replicated on every device */
+int rtb_multi_scene_free(rtb_multi *m, rtb_multi_scene *scene);
+int64_t rtb_multi_scene_upload_bytes(const rtb_multi_scene *scene); /* summed over the devices */
+int rtb_multi_render(rtb_multi *m, const rtb_multi_scene *scene, const rtb_camera *camera,
+                     const rtb_render_setting *setting, const rtb_frame *frame, void *rgb_out, rtb_stats *stats);
 
 #ifdef __cplusplus
 }

@@ -89,6 +89,10 @@ typedef struct oracle_job {
     double *render_ms_all; /* optional [repeat]: every render's interval, in order (input ptr)   */
     uint8_t *rgb8;       /* optional [w*h*3]: the reference's output stage -- saturate, (int)(c*255)
                             (MainWindow.cpp:305-311) -- R,G,B bytes in framebuffer order x*height + y */
+    double *moments;     /* optional [w*h*6], Monte Carlo, librt_oracle.so only (libref.so ignores it: the reference keeps
+                            no per-sample statistics): per pixel, framebuffer order, the sum over the samples of the
+                            radiance (R, G, B) and of its square -- the per-pixel variance the statistical parity
+                            criteria of SURVEY.md 8(d) need                                                        */
 } oracle_job;
 
 int rt_oracle_run(oracle_job *job);

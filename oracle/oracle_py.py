@@ -33,7 +33,7 @@ class OracleJob(C.Structure):
         ("n_rays", C.c_int64), ("n_tri_tests", C.c_int64), ("n_steps", C.c_int64),
         ("render_ms", C.c_double), ("prepare_ms", C.c_double),
         ("stats", C.c_int64 * 16), ("struct_hash", C.c_uint64), ("tri_hash", C.c_uint64),
-        ("render_ms_all", C.c_void_p), ("rgb8", C.c_void_p),
+        ("render_ms_all", C.c_void_p), ("rgb8", C.c_void_p), ("moments", C.c_void_p),
     ]
 
 
@@ -73,7 +73,7 @@ def _fn(which):
 
 def run(which, preset, algorithm="linear", segments=150, width=400, height=300, samples=1,
         setting="preset", threads=0, rng=0, seed=0, image=False, hits=False, seq=False, seq_cap=0,
-        triangles=False, repeat=0, stl_path=None):
+        triangles=False, repeat=0, stl_path=None, moments=False):
     """Run one job; returns a dict of numpy arrays / scalars."""
     job = OracleJob()
     job.preset = preset
@@ -92,6 +92,8 @@ def run(which, preset, algorithm="linear", segments=150, width=400, height=300, 
     if image:
         out("rgb", np.zeros((width, height, 3), np.float32))  # reference order: [x][y]
         out("rgb8", np.zeros((width, height, 3), np.uint8))
+    if moments:  # librt_oracle.so only: per-pixel sum and sum of squares of the per-sample radiance
+        out("moments", np.zeros((width, height, 6), np.float64))
     if hits:
         out("hit_id", np.full(n, -2, np.int32))
         out("hit_t", np.zeros(n, np.float32))
@@ -120,6 +122,8 @@ def run(which, preset, algorithm="linear", segments=150, width=400, height=300, 
     if image:
         res["image"] = np.ascontiguousarray(res["rgb"].transpose(1, 0, 2))  # [y][x][3]
         res["image8"] = np.ascontiguousarray(res["rgb8"].transpose(1, 0, 2))
+    if moments:
+        res["moments"] = np.ascontiguousarray(res["moments"].transpose(1, 0, 2))  # [y][x][6]
     for k in ("n_rays", "n_tri_tests", "n_steps", "render_ms", "prepare_ms", "struct_hash", "tri_hash"):
         res[k] = getattr(job, k)
     return res

@@ -1394,13 +1394,19 @@ void render(const Scene &s, const oracle_job *job, float *rgb, Counters *total)
             if (s.setting.mc)
             {
                 c = v3(0, 0, 0);
+                double m[6] = {0, 0, 0, 0, 0, 0};
                 for (int i = 0; i < samples; i++)
                 {
                     if (job->rng == ORACLE_RNG_COUNTER) rngSeedSample(rng, job->seed, (uint32_t)(y * width + x), (uint32_t)i);
                     const float r1 = (float)rngNext(rng), r2 = (float)rngNext(rng);
                     const float sx = (x + r1) * dx, sy = 1 - (y + r2) * dy;
-                    c = c + radiance(s, generateRay(s.cam, sx, sy), 0, rng, &pr) * (1.0f / samples);
+                    const V3 L = radiance(s, generateRay(s.cam, sx, sy), 0, rng, &pr);
+                    c = c + L * (1.0f / samples);
+                    m[0] += L.x; m[1] += L.y; m[2] += L.z;
+                    m[3] += (double)L.x * L.x; m[4] += (double)L.y * L.y; m[5] += (double)L.z * L.z;
                 }
+                if (job->moments && rgb)
+                    for (int k = 0; k < 6; k++) job->moments[6 * index + k] = m[k];
             }
             else
             {

@@ -27,8 +27,8 @@ def test_header_symbols_exported():
 
 def test_abi_version_and_struct_sizes():
     lib = rtb200.cuda_lib()
-    assert lib.rtb_abi_version() == 3
-    assert C.sizeof(rtb200.Frame) == 48  # col_block took the tail padding: the size did not change with ABI 3
+    assert lib.rtb_abi_version() == 4
+    assert C.sizeof(rtb200.Frame) == 56  # ABI 4 appended sample_first / sample_count (col_block had taken the tail padding in ABI 3)
     assert C.sizeof(rtb200.Material) == 64 and C.sizeof(rtb200.Prim) == 48
     assert C.sizeof(rtb200.KdNode) == 8 and C.sizeof(rtb200.CellWord) == 8
 

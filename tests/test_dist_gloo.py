@@ -69,6 +69,37 @@ WORKER = textwrap.dedent("""
     xc = torch.arange(Wc, dtype=torch.float32)
     expect = torch.arange(H, dtype=torch.float32)[:, None, None] * 1000 + xc[None, :, None] + torch.tensor([0, 0.25, 0.5])[None, None, :]
     assert torch.equal(image, expect), "column-sharded frame differs"
+
+    # ---- RTB_LAYOUT_GLOBAL: every rank stores its own pixels into ONE whole frame; no gather, no unshard.  Here each
+    # rank fills a private copy of the frame at the slots it owns (shard_pixel_mask = the kernels' localToGlobal) and a
+    # reduce(sum) onto rank 0 stands in for the shared buffer: the supports must be disjoint and cover the frame ----
+    for (cb, Wg) in ((0, W), (CB, Wc)):
+        mask = torch.from_numpy(rtb200.shard_pixel_mask(Wg, H, rank, world, RB, cb))
+        assert int(mask.sum()) == rtb200.shard_rows(rtb200.make_frame(Wg, H, rank=rank, world=world, row_block=RB, col_block=cb)) * \
+            rtb200.shard_width(rtb200.make_frame(Wg, H, rank=rank, world=world, row_block=RB, col_block=cb))
+        xg = torch.arange(Wg, dtype=torch.float32)
+        full = torch.arange(H, dtype=torch.float32)[:, None, None] * 1000 + xg[None, :, None] + torch.tensor([0, 0.25, 0.5])[None, None, :]
+        mine = torch.where(mask[:, :, None], full, torch.zeros_like(full))
+        owners = mask.to(torch.int32)
+        dist.reduce(mine, dst=0, op=dist.ReduceOp.SUM)
+        dist.reduce(owners, dst=0, op=dist.ReduceOp.SUM)
+        if rank == 0:
+            assert bool((owners == 1).all()), "shards overlap or leave holes"
+            assert torch.equal(mine, full), "global-layout frame differs"
+
+    # ---- Monte-Carlo SAMPLE shards (rtb_frame.sample_first / sample_count): the ranges partition [0, samples), and the
+    # per-rank images (each sample weighted 1 / samples) sum to the frame under reduce(sum) ----
+    for samples in (64, 7, world):
+        first, count = rtb200.sample_shard(samples, rank, world)
+        cover = torch.zeros(samples, dtype=torch.int32)
+        cover[first:first + count] = 1
+        dist.all_reduce(cover)
+        assert bool((cover == 1).all()) and count >= samples // world
+        vals = torch.arange(samples, dtype=torch.float64) + 1.0            # "radiance" of sample s at one pixel
+        part = (vals[first:first + count] / samples).sum().reshape(1)
+        dist.reduce(part, dst=0, op=dist.ReduceOp.SUM)
+        if rank == 0:
+            assert abs(float(part) - float(vals.mean())) < 1e-12
     dist.barrier()
     if rank == 0:
         print("GLOO_OK", world, rows_max)

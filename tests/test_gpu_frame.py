@@ -1,0 +1,291 @@
+"""GPU tests of the frame-level entry points added with ABI 4 (include/rtb.h): one frame buffer filled by several
+shards / devices (RTB_LAYOUT_GLOBAL, rtb_multi_*, rtb_ipc_*), the Monte-Carlo accumulation buffer and sample shards
+(RTB_OUTPUT_MOMENTS, rtb_frame.sample_first / sample_count), progress / log reporting behind the reference's
+RenderProc (Scripts.h:9-12), and the first-frame schedule (rtb_forget_schedule).  Everything goes through the C ABI;
+the reference values are whole frames rendered by the same library, whose parity with the reference
+tests/test_gpu_parity.py establishes."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import rtb200
+from rtb200 import PresetScene
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = rtb200.Context(0)
+    yield c
+    c.close()
+
+
+def _bits(a):
+    return np.ascontiguousarray(a).view(np.uint8)
+
+
+def _n_gpus():
+    import torch
+    return torch.cuda.device_count()
+
+
+# ---- RTB_LAYOUT_GLOBAL: shards store straight into the whole frame -------------------------------------------
+@pytest.mark.parametrize("world,col_block,alg", [(2, 0, "sah"), (3, 0, "rgrid"), (4, 16, "sah"), (8, 8, "kd"), (8, 32, "fgrid")])
+def test_global_layout_shards_fill_one_frame(ctx, world, col_block, alg):
+    """Every rank of a frame is given the SAME page-locked frame and stores only its own pixels, at y * width + x: after
+    the last rank the buffer equals the whole-frame render bit for bit (float and 8-bit), with no gather / unshard pass.
+    Rendered twice: the second pass runs through the tile order and the latency tiers."""
+    w, h = 256, 96
+    s = PresetScene(5, alg, 24)
+    dev = ctx.upload(s.flat)
+    whole, st = dev.render(s.camera, s.setting, rtb200.make_frame(w, h))
+    whole8, _ = dev.render(s.camera, s.setting, rtb200.make_frame(w, h, layout=rtb200.OUTPUT_RGB8))
+    frame = rtb200.PinnedArray((h, w, 3))
+    frame8 = rtb200.PinnedArray(((h * w * 3 + 3) // 4,))
+    bytes8 = frame8.array.view(np.uint8)[: h * w * 3].reshape(h, w, 3)
+    for repeat in range(2):
+        frame.array[:] = -1.0
+        bytes8[:] = 7
+        rays = 0
+        for rank in range(world):
+            fr = rtb200.make_frame(w, h, rank=rank, world=world, row_block=8, col_block=col_block, layout=rtb200.LAYOUT_GLOBAL)
+            _, pst = dev.render(s.camera, s.setting, fr, out=frame.array)
+            rays += pst["n_rays"]
+            fr8 = rtb200.make_frame(w, h, rank=rank, world=world, row_block=8, col_block=col_block,
+                                    layout=rtb200.LAYOUT_GLOBAL | rtb200.OUTPUT_RGB8)
+            dev.render(s.camera, s.setting, fr8, out=bytes8)
+        assert np.array_equal(_bits(frame.array), _bits(whole))
+        assert np.array_equal(bytes8, whole8)
+        assert rays == st["n_rays"]
+    # a pageable whole-frame buffer cannot take shard stores: refused, not silently mis-assembled
+    with pytest.raises(rtb200.RtbError):
+        dev.render(s.camera, s.setting, rtb200.make_frame(w, h, rank=0, world=2, layout=rtb200.LAYOUT_GLOBAL), out=np.zeros((h, w, 3), np.float32))
+    frame.close(); frame8.close(); dev.close(); s.close()
+
+
+def test_global_layout_device_frame(ctx):
+    """The same through rtb_render_device into ONE device frame (what the ranks of a torch.distributed job do with the
+    owner's IPC-mapped frame)."""
+    import torch
+    w, h, world = 192, 144, 4
+    s = PresetScene(5, "sah", 24)
+    dev = ctx.upload(s.flat)
+    whole, _ = dev.render(s.camera, s.setting, rtb200.make_frame(w, h))
+    image = torch.full((h, w, 3), -1.0, dtype=torch.float32, device="cuda:0")
+    stream = torch.cuda.current_stream().cuda_stream
+    for col_block in (0, 8):
+        image.fill_(-1.0)
+        for rank in range(world):
+            fr = rtb200.make_frame(w, h, rank=rank, world=world, row_block=8, col_block=col_block, layout=rtb200.LAYOUT_GLOBAL)
+            dev.render_device(s.camera, s.setting, fr, image.data_ptr(), stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(_bits(image.cpu().numpy()), _bits(whole))
+    dev.close(); s.close()
+
+
+def test_global_layout_monte_carlo_and_reference_order(ctx):
+    w, h, world = 64, 48, 3
+    s = PresetScene(2)
+    dev = ctx.upload(s.flat)
+    whole, _ = dev.render(s.camera, s.setting, rtb200.make_frame(w, h, samples=3, seed=4))
+    frame = rtb200.PinnedArray((h, w, 3))
+    for rank in range(world):
+        dev.render(s.camera, s.setting, rtb200.make_frame(w, h, samples=3, seed=4, rank=rank, world=world, layout=rtb200.LAYOUT_GLOBAL),
+                   out=frame.array)
+    assert np.array_equal(_bits(frame.array), _bits(whole))
+    # the reference framebuffer order (index = x * height + y, MainWindow.cpp:276) addresses by frame coordinates: with
+    # RTB_LAYOUT_GLOBAL row shards fill one such buffer
+    col = rtb200.PinnedArray((w, h, 3))
+    for rank in range(world):
+        fr = rtb200.make_frame(w, h, samples=3, seed=4, rank=rank, world=world, layout=rtb200.LAYOUT_GLOBAL | rtb200.LAYOUT_REFERENCE)
+        dev.render(s.camera, s.setting, fr, out=col.array)
+    assert np.array_equal(_bits(col.array.transpose(1, 0, 2)), _bits(whole))
+    frame.close(); col.close(); dev.close(); s.close()
+
+
+# ---- rtb_multi_*: one host thread, n devices, one assembled host frame ------------------------------------------
+@pytest.mark.parametrize("devices", [[0], [0, 0], [0, 0, 0, 0, 0]])
+def test_multi_render_assembles_one_host_frame(ctx, devices):
+    """rtb_multi_render over n contexts (here: n contexts on device 0, which exercises the same sharding, launch and
+    assembly code as n GPUs; the all-GPU variant follows) returns the whole frame in ONE host buffer -- page-locked or
+    pageable -- identical to rtb_render's, counts included; 5 contexts take the column-block path."""
+    w, h = 320, 120
+    s = PresetScene(5, "sah", 24)
+    dev = ctx.upload(s.flat)
+    whole, st = dev.render(s.camera, s.setting, rtb200.make_frame(w, h, counters=1))
+    whole8, _ = dev.render(s.camera, s.setting, rtb200.make_frame(w, h, layout=rtb200.OUTPUT_RGB8))
+    m = rtb200.MultiContext(len(devices), devices)
+    ms = m.upload(s.flat)
+    assert ms.upload_bytes == len(devices) * dev.upload_bytes
+    pinned = rtb200.PinnedArray((h, w, 3))
+    for repeat in range(3):
+        pinned.array[:] = -1.0
+        _, mst = ms.render(s.camera, s.setting, rtb200.make_frame(w, h, counters=1), out=pinned.array)
+        assert np.array_equal(_bits(pinned.array), _bits(whole))
+        assert (mst["n_rays"], mst["n_tri_tests"], mst["n_steps"]) == (st["n_rays"], st["n_tri_tests"], st["n_steps"])
+    pageable, _ = ms.render(s.camera, s.setting, rtb200.make_frame(w, h))
+    assert np.array_equal(_bits(pageable), _bits(whole))
+    out8, _ = ms.render(s.camera, s.setting, rtb200.make_frame(w, h, layout=rtb200.OUTPUT_RGB8))
+    assert np.array_equal(out8, whole8)
+    refo, _ = ms.render(s.camera, s.setting, rtb200.make_frame(w, h, layout=rtb200.LAYOUT_REFERENCE))
+    assert refo.shape == (w, h, 3) and np.array_equal(_bits(refo.transpose(1, 0, 2)), _bits(whole))
+    pinned.close(); ms.close(); m.close(); dev.close(); s.close()
+
+
+def test_multi_render_all_gpus(ctx):
+    n = _n_gpus()
+    if n < 2:
+        pytest.skip("one GPU on this box (the n-contexts-on-one-device variant covers the code path)")
+    w, h = 1280, 960
+    s = PresetScene(5, "sah", 150)
+    dev = ctx.upload(s.flat)
+    whole, st = dev.render(s.camera, s.setting, rtb200.make_frame(w, h))
+    m = rtb200.MultiContext(n)
+    ms = m.upload(s.flat)
+    pinned = rtb200.PinnedArray((h, w, 3))
+    for _ in range(3):
+        _, mst = ms.render(s.camera, s.setting, rtb200.make_frame(w, h), out=pinned.array)
+        assert np.array_equal(_bits(pinned.array), _bits(whole)) and mst["n_rays"] == st["n_rays"]
+    pinned.close(); ms.close(); m.close(); dev.close(); s.close()
+
+
+def test_multi_render_monte_carlo(ctx):
+    w, h = 96, 72
+    s = PresetScene(2)
+    dev = ctx.upload(s.flat)
+    whole, _ = dev.render(s.camera, s.setting, rtb200.make_frame(w, h, samples=4, seed=9))
+    m = rtb200.MultiContext(3, [0, 0, 0])
+    ms = m.upload(s.flat)
+    out, _ = ms.render(s.camera, s.setting, rtb200.make_frame(w, h, samples=4, seed=9))
+    assert np.array_equal(_bits(out), _bits(whole))
+    ms.close(); m.close(); dev.close(); s.close()
+
+
+# ---- rtb_ipc_*: the owner's device frame mapped into another PROCESS ----------------------------------------------
+_PEER = r"""
+import sys, numpy as np
+sys.path.insert(0, {root!r})
+import rtb200
+handle = bytes.fromhex(sys.argv[1]); rank, world, w, h, cb = (int(v) for v in sys.argv[2:7])
+ctx = rtb200.Context(0)
+s = rtb200.PresetScene(5, "sah", 24)
+dev = ctx.upload(s.flat)
+frame = ctx.ipc_open(handle)
+fr = rtb200.make_frame(w, h, rank=rank, world=world, row_block=8, col_block=cb, layout=rtb200.LAYOUT_GLOBAL)
+st = dev.render_device(s.camera, s.setting, fr, frame, 0, want_stats=True)   # stats: synchronises
+ctx.ipc_close(frame)
+print("PEER_RAYS", st["n_rays"])
+"""
+
+
+@pytest.mark.parametrize("col_block", [0, 8])
+def test_ipc_peer_process_stores_into_owner_frame(ctx, col_block):
+    """Process A owns the frame (rtb_device_alloc + rtb_ipc_export); process B maps it (rtb_ipc_open) and renders its
+    shard straight into it while A renders its own: the frame A reads back is the whole frame.  On a multi-GPU box the
+    peers sit on other devices and the stores cross NVLink; the mapping code is the same."""
+    w, h, world = 256, 96, 2
+    s = PresetScene(5, "sah", 24)
+    dev = ctx.upload(s.flat)
+    whole, st = dev.render(s.camera, s.setting, rtb200.make_frame(w, h))
+    nbytes = w * h * 3 * 4
+    frame = ctx.device_alloc(nbytes)
+    handle = ctx.ipc_export(frame)
+    peer = subprocess.Popen([sys.executable, "-c", _PEER.format(root=ROOT), handle.hex(), "1", str(world), str(w), str(h), str(col_block)],
+                            stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    fr = rtb200.make_frame(w, h, rank=0, world=world, row_block=8, col_block=col_block, layout=rtb200.LAYOUT_GLOBAL)
+    mine = dev.render_device(s.camera, s.setting, fr, frame, 0, want_stats=True)
+    out, err = peer.communicate(timeout=300)
+    assert peer.returncode == 0, err[-2000:]
+    peer_rays = int(out.split("PEER_RAYS")[1].split()[0])
+    got = np.zeros((h, w, 3), np.float32)
+    ctx.device_download(frame, got)
+    assert np.array_equal(_bits(got), _bits(whole))
+    assert mine["n_rays"] + peer_rays == st["n_rays"]
+    ctx.device_free(frame)
+    dev.close(); s.close()
+
+
+# ---- Monte-Carlo accumulation buffer and sample shards --------------------------------------------------------------
+def test_moments_buffer_and_sample_shards(ctx):
+    """RTB_OUTPUT_MOMENTS returns (sum, sum of squares) per pixel and channel: sum / spp is the rendered mean (the
+    render accumulates radiance * (1 / spp) sample by sample, so equal up to float rounding), the variance estimate is
+    non-negative, and the buffers of disjoint SAMPLE shards add up to the buffer of the whole sample range exactly as
+    sums of the same per-sample values in another order (float rounding only).  The same for the images of sample
+    shards (each sample weighted 1 / spp)."""
+    w, h, spp = 64, 48, 24
+    s = PresetScene(2)
+    dev = ctx.upload(s.flat)
+    img, st = dev.render(s.camera, s.setting, rtb200.make_frame(w, h, samples=spp, seed=2))
+    mom, mst = dev.render(s.camera, s.setting, rtb200.make_frame(w, h, samples=spp, seed=2, layout=rtb200.OUTPUT_MOMENTS))
+    assert mom.shape == (h, w, 6) and mst["n_rays"] == st["n_rays"]
+    mean = mom[..., :3] / spp
+    assert np.allclose(mean, img, rtol=2e-5, atol=1e-6)
+    var = (mom[..., 3:] - mom[..., :3] ** 2 / spp) / (spp - 1)
+    assert var.min() > -1e-3 * max(1.0, float(var.max())) and var.mean() > 0
+    parts, imgs, rays = [], [], 0
+    for first, count in ((0, 8), (8, 8), (16, 8)):
+        fm = rtb200.make_frame(w, h, samples=spp, seed=2, layout=rtb200.OUTPUT_MOMENTS, sample_first=first, sample_count=count)
+        p, pst = dev.render(s.camera, s.setting, fm)
+        parts.append(p.astype(np.float64))
+        rays += pst["n_rays"]
+        q, _ = dev.render(s.camera, s.setting, rtb200.make_frame(w, h, samples=spp, seed=2, sample_first=first, sample_count=count))
+        imgs.append(q.astype(np.float64))
+    assert rays == st["n_rays"]
+    assert np.allclose(sum(parts), mom, rtol=2e-6, atol=1e-6)
+    assert np.allclose(sum(imgs), img, rtol=2e-5, atol=1e-6)
+    with pytest.raises(rtb200.RtbError):  # outside [0, samples)
+        dev.render(s.camera, s.setting, rtb200.make_frame(w, h, samples=spp, sample_first=20, sample_count=8))
+    with pytest.raises(rtb200.RtbError):  # Whitted has no samples to accumulate
+        t = PresetScene(5, "sah", 8)
+        d2 = ctx.upload(t.flat)
+        try:
+            d2.render(t.camera, t.setting, rtb200.make_frame(w, h, layout=rtb200.OUTPUT_MOMENTS))
+        finally:
+            d2.close(); t.close()
+    dev.close(); s.close()
+
+
+# ---- the reference's callbacks behind the RenderProc -----------------------------------------------------------------
+@pytest.mark.parametrize("n_devices", [1, 2])
+def test_progress_and_log_callbacks(ctx, n_devices):
+    """Script::Run(CudaRenderer::Render, alg, log, progress, ...): the ProgressCallback is called in the reference's unit
+    (rows of `height`, MainWindow.cpp:271), monotonically, ends at (height, height); a failing render reports through
+    the LogCallback and returns a negative time (Scripts.h:9-12 has no other error channel)."""
+    if n_devices > _n_gpus():
+        pytest.skip("needs more GPUs")
+    w, h = 1600, 1200
+    img, info = rtb200.script_run_ex(5, "sah", 150, w, h, n_devices=n_devices)
+    assert info["rc"] == 0 and img is not None
+    assert info["progress_calls"] >= 1 and info["progress_monotone"]
+    assert (info["progress_last"], info["progress_total"]) == (h, h)
+    ref, _ = rtb200.script_run(5, "sah", 150, w, h)
+    assert np.array_equal(_bits(img), _bits(ref))
+    # failure path: a frame size the library refuses
+    img, info = rtb200.script_run_ex(5, "sah", 12, 0, 10, n_devices=n_devices)
+    assert info["rc"] < 0 and img is None and "CudaRenderer" in info["log"]
+
+
+def test_first_frame_schedule_can_be_forgotten(ctx):
+    """rtb_forget_schedule: the next frame runs in raster order through one throughput kernel like the first frame of a
+    view (fewer launches than a tiered frame) and produces the same image."""
+    w, h = 1280, 960
+    s = PresetScene(5, "sah", 150)
+    dev = ctx.upload(s.flat)
+    fr = rtb200.make_frame(w, h)
+    ctx.forget_schedule()
+    first, st1 = dev.render(s.camera, s.setting, fr)
+    second, st2 = dev.render(s.camera, s.setting, fr)
+    third, st3 = dev.render(s.camera, s.setting, fr)
+    assert st1["n_launches"] == 4 and st3["n_launches"] > 4  # 1 render + 3 order kernels; then the tiers join
+    ctx.forget_schedule()
+    again, st4 = dev.render(s.camera, s.setting, fr)
+    assert st4["n_launches"] == 4
+    for img in (second, third, again):
+        assert np.array_equal(_bits(img), _bits(first))
+    dev.close(); s.close()

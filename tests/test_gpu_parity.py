@@ -98,10 +98,18 @@ FULL = ["p5_sah_s150_400x300", "p5_rgrid_s150_400x300", "p5_kd_s150_400x300", "p
         "p4_sah_s150_400x300", "p4_rgrid_s150_400x300"]
 
 
+def _checker(job, **outputs):
+    """The CPU checker for a job: the compiled reference itself when oracle/_ref travelled with the repo, else the
+    restatement (tests/test_oracle.py pins the two to each other bit for bit)."""
+    return O.run("ref" if O.available("ref") else "oracle", **outputs, **job)
+
+
 @pytest.mark.parametrize("name", FULL)
 def test_full_size_preset_digests(ctx, name):
-    """BASELINE configs at the demo's default resolution: sha256 of the per-ray arrays must equal
-    the reference's; ray / triangle-test / step counts of the whole frame must be identical."""
+    """BASELINE configs at the demo's default resolution (400x300, 150 segments): sha256 of the per-ray arrays must equal
+    the reference's; ray / triangle-test / step counts of the whole frame must be identical; and the Whitted IMAGE is
+    compared pixel by pixel at 1e-5 relative with the CPU checker's, whose own image must hash to the committed digest of
+    the reference's image (so the comparison is against the reference's pixels, without 8 MB of floats in the repo)."""
     import hashlib
     g = META[name]
     job = g["job"]
@@ -112,7 +120,18 @@ def test_full_size_preset_digests(ctx, name):
     fr = rtb200.make_frame(job["width"], job["height"], counters=1)
     img, st = dev.render(s.camera, s.setting, fr)
     assert (st["n_rays"], st["n_tri_tests"], st["n_steps"]) == (g["n_rays"], g["n_tri_tests"], g["n_steps"])
-    assert np.all(np.isfinite(img)) and img.min() >= 0.0  # Phong highlights exceed 1 before saturate()
+    ref = _checker(job, image=True)
+    assert hashlib.sha256(np.ascontiguousarray(ref["image"]).tobytes()).hexdigest() == g["sha256"]["image"]
+    _assert_image_close(img, ref["image"], name)
+    same = (_bits(img).reshape(-1, 4) == _bits(ref["image"]).reshape(-1, 4)).all(axis=1).mean()
+    assert same > (0.97 if job["preset"] == 4 else 0.995), same  # bit-exact except under the Phong ball's powf
+    # the second and third frame of the view come from the heaviest-first order and the latency tiers
+    for _ in range(2):
+        again, st2 = dev.render(s.camera, s.setting, fr)
+        assert np.array_equal(_bits(again), _bits(img)) and st2["n_rays"] == st["n_rays"]
+    # ... and the 8-bit output stage (MainWindow.cpp:305-311) against the reference's bytes
+    img8, _ = dev.render(s.camera, s.setting, rtb200.make_frame(job["width"], job["height"], layout=rtb200.OUTPUT_RGB8))
+    assert (img8 != ref["image8"]).mean() < 1e-4  # a byte can differ where a float within 1e-5 sits on a quantisation step
     dev.close(); s.close()
 
 
@@ -279,30 +298,50 @@ def test_monte_carlo_path_for_path_vs_oracle(ctx, job):
     dev.close(); s.close()
 
 
-@pytest.mark.parametrize("preset,spp", [(1, 64), (2, 64)])
-def test_monte_carlo_statistics_vs_erand48(ctx, preset, spp):
-    """Counter-RNG GPU images vs the oracle's erand48 image (the reference's own random stream) at equal
-    samples per pixel.  K = 8 independent GPU seeds give, per pixel, the mean m and
-    the standard deviation s of an spp-sample estimate; the CPU image is one more draw of that estimator:
-      (i)   image-mean luminance within 4 standard errors (estimated from the K seeds) and within 3 %;
-      (ii)  |cpu - m| <= 5 * s * sqrt(1 + 1/K) for >= 99 % of pixels (Student-t, 7 dof: 99.8 % expected);
-      (iii) CPU-vs-GPU RMSE <= 1.15 x GPU-vs-GPU RMSE between disjoint seeds."""
-    w, h, K = 48, 36, 8
-    cpu = O.run("oracle", preset, width=w, height=h, samples=spp, image=True, rng=0)["image"].mean(axis=2)
+@pytest.mark.parametrize("preset,w,h", [(1, 400, 300), (2, 400, 300), (3, 120, 90)])
+def test_monte_carlo_statistics_vs_erand48(ctx, preset, w, h):
+    """The statistical parity criteria of SURVEY.md 8(d), as stated there, at the demo's frame size and 64 spp (preset 3
+    -- 528 loose triangles per ray on the CPU -- at 120x90): the GPU (Philox, keyed by pixel and sample) returns per-pixel
+    sum and sum of squares (RTB_OUTPUT_MOMENTS); the CPU side is the oracle running the REFERENCE's random stream (erand48
+    seeded per row, MainWindow.cpp:273), whose image is bit-identical to the reference's (tests/test_oracle.py), with the
+    same moments.  With N = spp, per colour component:
+      (i)   image-mean radiance within 0.5 % -- or within 4 standard errors of the difference where the frame is too small
+            for 0.5 % to be a 4-sigma event (preset 3's 120x90 frame: two CPU runs with different seeds differ by 0.7 %);
+      (ii)  |mean_cpu - mean_gpu| <= 4 sqrt((s2_cpu + s2_gpu) / N) for >= 99.9 % of the pixels (all three components);
+      (iii) CPU-vs-GPU RMSE <= 1.1 x CPU-vs-CPU RMSE between two disjoint seed sets (the oracle's counter stream, seeds 1 / 2).
+    Measured CPU-vs-CPU in this repo's container: (i) 0.03 % / 0.24 % / 0.64 %, (ii) 99.997 % / 100 % / 100 %, (iii) 0.996-1.008."""
+    spp = 64
+    A = O.run("oracle", preset, width=w, height=h, samples=spp, image=True, moments=True, rng=0)
+    B = O.run("oracle", preset, width=w, height=h, samples=spp, image=True, rng=1, seed=1)["image"].astype(np.float64)
+    Cc = O.run("oracle", preset, width=w, height=h, samples=spp, image=True, rng=1, seed=2)["image"].astype(np.float64)
     s, dev = _scene(ctx, dict(preset=preset))
-    gpu = np.stack([dev.render(s.camera, s.setting, rtb200.make_frame(w, h, samples=spp, seed=100 + k))[0].mean(axis=2)
-                    for k in range(K)])
-    m, sd = gpu.mean(axis=0), gpu.std(axis=0, ddof=1)
-    img_means = gpu.mean(axis=(1, 2))
-    se = img_means.std(ddof=1) * np.sqrt(1 + 1.0 / K)
-    assert abs(img_means.mean() - cpu.mean()) <= max(4.0 * se, 0.002 * cpu.mean()), (img_means, cpu.mean())
-    assert abs(img_means.mean() - cpu.mean()) <= 0.03 * cpu.mean()
-    sd = np.maximum(sd, 1e-3 + 0.01 * m)
-    z = np.abs(cpu - m) / (sd * np.sqrt(1 + 1.0 / K))
-    assert (z <= 5.0).mean() >= 0.99, (z <= 5.0).mean()
-    rmse_gg = np.mean([np.sqrt(np.mean((gpu[k] - gpu[(k + 1) % K]) ** 2)) for k in range(K)])
-    rmse_gc = np.mean([np.sqrt(np.mean((gpu[k] - cpu) ** 2)) for k in range(K)])
-    assert rmse_gc <= 1.15 * rmse_gg, (rmse_gc, rmse_gg)
+    mom, _ = dev.render(s.camera, s.setting, rtb200.make_frame(w, h, samples=spp, seed=7, layout=rtb200.OUTPUT_MOMENTS))
+    img, _ = dev.render(s.camera, s.setting, rtb200.make_frame(w, h, samples=spp, seed=7))
+    mom = mom.astype(np.float64)
+
+    def mean_var(m):
+        return m[..., :3] / spp, np.maximum(m[..., 3:] - m[..., :3] ** 2 / spp, 0.0) / (spp - 1)
+
+    mg, vg = mean_var(mom)
+    mc, vc = mean_var(A["moments"])
+    assert np.allclose(mg, img, rtol=2e-5, atol=1e-6)                 # the moments describe the image that is rendered
+    assert np.allclose(mc, A["image"], rtol=2e-5, atol=1e-6)
+    # (i)
+    diff = abs(mg.mean() - mc.mean())
+    se = np.sqrt((vg.sum() + vc.sum()) / spp) / mg.size                 # standard error of the difference of the two image means
+    assert diff <= max(0.005 * mc.mean(), 4.0 * se), (diff / mc.mean(), se / mc.mean())
+    assert diff <= 0.01 * mc.mean()
+    # (ii)
+    z = np.abs(mg - mc) / np.sqrt((vg + vc) / spp + 1e-30)
+    assert ((vg + vc) > 0).mean() > 0.5 or preset == 1
+    within = (z <= 4.0).all(axis=2).mean()
+    assert within >= 0.999, within
+    # (iii)
+    def rmse(a, b):
+        return float(np.sqrt(np.mean((a - b) ** 2)))
+    cpu_cpu = rmse(B, Cc)
+    assert rmse(img.astype(np.float64), A["image"].astype(np.float64)) <= 1.1 * cpu_cpu
+    assert rmse(img.astype(np.float64), B) <= 1.1 * cpu_cpu
     dev.close(); s.close()
 
 
@@ -436,16 +475,30 @@ def test_upload_rejects_bad_scenes(ctx):
 
 
 def test_4k_frame_properties(ctx):
-    """BASELINE stress size (3840x2880, tunnel SAH): properties that do not need the CPU at full size --
-    (a) the 8 row shards reassemble to the whole frame bit for bit, (b) total rays are equal,
-    (c) down-sampling the pixel grid 8x reproduces the 480x360 primary hit ids exactly where the
-    pixel centres coincide (they do not, so instead:) the centre row/column hit ids of the 4K trace equal
-    the oracle's trace of the same pixels."""
+    """BASELINE stress size, the bench's headline frame (3840x2880, preset 5, 150 segments, k-d SAH), against the CPU
+    checker rendering the SAME frame: (a) hit id and hit distance of every primary ray bit-exact, (b) the Whitted image
+    within 1e-5 relative on every component (the vanishing-point rows with their 21-ray chains included) and bit-exact
+    on > 99.5 % of them, (c) total rays equal; then (d) the 8 row shards reassemble to the whole frame bit for bit and
+    their ray counts add up."""
     w, h = 3840, 2880
-    s, dev = _scene(ctx, dict(preset=5, algorithm="sah", segments=150))
+    job = dict(preset=5, algorithm="sah", segments=150, width=w, height=h)
+    s, dev = _scene(ctx, job)
     whole, st = dev.render(s.camera, s.setting, rtb200.make_frame(w, h))
     assert np.all(np.isfinite(whole))
-    digest = 0
+    ref = _checker(job, image=True, hits=True)
+    r = dev.trace_primary(s.camera, w, h, seq=False)
+    assert np.array_equal(r["hit_id"], ref["hit_id"])
+    assert np.array_equal(_bits(r["hit_t"]), _bits(ref["hit_t"]))
+    _assert_image_close(whole, ref["image"], "4K SAH frame")
+    same = (_bits(whole).reshape(-1, 4) == _bits(ref["image"]).reshape(-1, 4)).all(axis=1).mean()
+    assert same > 0.995, same
+    assert st["n_rays"] == ref["n_rays"]
+    # named explicitly (already covered by the whole-frame comparison): top / bottom rows, the rows and the column
+    # through the vanishing point with the longest reflection chains
+    for y in (0, h // 2 - 1, h // 2, h - 1):
+        assert np.allclose(whole[y], ref["image"][y], rtol=RTOL, atol=1e-7)
+    for x in (0, w // 2, w - 1):
+        assert np.allclose(whole[:, x], ref["image"][:, x], rtol=RTOL, atol=1e-7)
     rays = 0
     for rank in range(8):
         part, pst = dev.render(s.camera, s.setting, rtb200.make_frame(w, h, rank=rank, world=8, row_block=16))
@@ -454,6 +507,21 @@ def test_4k_frame_properties(ctx):
         rays += pst["n_rays"]
     assert rays == st["n_rays"]
     assert st["n_rays"] > 3 * w * h * 0.9  # ~3.1 rays per primary on this scene
+    dev.close(); s.close()
+
+
+@pytest.mark.parametrize("alg", ["rgrid"])
+def test_4k_regular_grid_frame_vs_checker(ctx, alg):
+    """The other headline accelerator (400 x 5 x 400 regular grid) at the bench's frame size, image and ray count."""
+    w, h = 3840, 2880
+    job = dict(preset=5, algorithm=alg, segments=150, width=w, height=h)
+    s, dev = _scene(ctx, job)
+    fr = rtb200.make_frame(w, h)
+    dev.render(s.camera, s.setting, fr)
+    img, st = dev.render(s.camera, s.setting, fr)  # second frame: the tiers are in play
+    ref = _checker(job, image=True)
+    _assert_image_close(img, ref["image"], f"4K {alg} frame")
+    assert st["n_rays"] == ref["n_rays"]
     dev.close(); s.close()
 
 

@@ -20,7 +20,8 @@ HOST_LIB = os.path.join(PKG, "librtb200_host.so")
 ALGORITHMS = {"linear": 0, "rgrid": 1, "fgrid": 2, "kd": 3, "sah": 4, "convex": 5, "convexsimple": 6}
 STAT_NAMES = ["n_top", "n_tris", "grid_x", "grid_y", "grid_z", "cells_nonempty", "cell_entries",
               "cell_max", "kd_nodes", "kd_leaves", "kd_leaf_refs", "kd_max_depth"]
-LAYOUT_ROWMAJOR, LAYOUT_REFERENCE, OUTPUT_RGB8 = 0, 1, 4
+LAYOUT_ROWMAJOR, LAYOUT_REFERENCE, LAYOUT_GLOBAL, OUTPUT_RGB8, OUTPUT_MOMENTS = 0, 1, 2, 4, 8
+IPC_HANDLE_BYTES = 64
 
 
 class RtbError(RuntimeError):
@@ -95,7 +96,7 @@ class Frame(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("samples", C.c_int32),
                 ("seed", C.c_uint64), ("rank", C.c_int32), ("world", C.c_int32),
                 ("row_block", C.c_int32), ("layout", C.c_int32), ("counters", C.c_int32),
-                ("col_block", C.c_int32)]
+                ("col_block", C.c_int32), ("sample_first", C.c_int32), ("sample_count", C.c_int32)]
 
 
 class Stats(C.Structure):
@@ -112,7 +113,10 @@ ABI_SYMBOLS = ["rtb_init", "rtb_shutdown", "rtb_last_error", "rtb_abi_version", 
                "rtb_host_alloc", "rtb_host_free",
                "rtb_scene_upload", "rtb_scene_free", "rtb_scene_device_bytes", "rtb_scene_upload_bytes", "rtb_scene_grid_hash", "rtb_render",
                "rtb_render_device", "rtb_unshard_device", "rtb_trace_primary", "rtb_intersect_rays", "rtb_bounce_rays",
-               "rtb_selftest_pretest", "rtb_kd_validate"]
+               "rtb_selftest_pretest", "rtb_kd_validate", "rtb_forget_schedule", "rtb_set_progress", "rtb_multi_set_progress",
+               "rtb_device_alloc", "rtb_device_free", "rtb_device_download", "rtb_ipc_export", "rtb_ipc_open", "rtb_ipc_close",
+               "rtb_multi_init", "rtb_multi_shutdown", "rtb_multi_count", "rtb_multi_ctx", "rtb_multi_last_error",
+               "rtb_multi_scene_upload", "rtb_multi_scene_free", "rtb_multi_scene_upload_bytes", "rtb_multi_render"]
 
 _cuda = None
 _host = None
@@ -152,6 +156,25 @@ def cuda_lib():
         lib.rtb_unshard_cols_device.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp]
         lib.rtb_trace_primary.argtypes = [vp, vp, C.POINTER(Camera), i32, i32, vp, vp, vp, vp, vp, i32]
         lib.rtb_intersect_rays.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp]
+        lib.rtb_forget_schedule.argtypes = [vp]
+        lib.rtb_device_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
+        lib.rtb_device_free.argtypes = [vp, vp]
+        lib.rtb_device_download.argtypes = [vp, vp, vp, C.c_size_t]
+        lib.rtb_ipc_export.argtypes = [vp, vp, C.c_char_p]
+        lib.rtb_ipc_open.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
+        lib.rtb_ipc_close.argtypes = [vp, vp]
+        lib.rtb_multi_init.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(vp)]
+        lib.rtb_multi_shutdown.argtypes = [vp]
+        lib.rtb_multi_count.argtypes = [vp]
+        lib.rtb_multi_ctx.argtypes = [vp, C.c_int]
+        lib.rtb_multi_ctx.restype = vp
+        lib.rtb_multi_last_error.argtypes = [vp]
+        lib.rtb_multi_last_error.restype = C.c_char_p
+        lib.rtb_multi_scene_upload.argtypes = [vp, C.POINTER(FlatScene), C.POINTER(vp)]
+        lib.rtb_multi_scene_free.argtypes = [vp, vp]
+        lib.rtb_multi_scene_upload_bytes.argtypes = [vp]
+        lib.rtb_multi_scene_upload_bytes.restype = i64
+        lib.rtb_multi_render.argtypes = [vp, vp, C.POINTER(Camera), C.POINTER(RenderSetting), C.POINTER(Frame), vp, C.POINTER(Stats)]
         _cuda = lib
     return _cuda
 
@@ -186,6 +209,8 @@ def host_lib():
             getattr(lib, f).restype = C.c_uint64
         lib.rtbh_script_run.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int,
                                         C.c_char_p, vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(Stats)]
+        lib.rtbh_script_run_ex.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int,
+                                           C.c_char_p, vp, C.POINTER(C.c_int), C.POINTER(Stats), C.POINTER(C.c_int), C.c_char_p, C.c_int]
         lib.rtbh_script_run8.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int,
                                          C.c_char_p, vp, C.c_char_p, C.POINTER(C.c_int), C.POINTER(Stats)]
         lib.rtbh_perf_test.argtypes = [C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, vp, vp, vp,
@@ -321,6 +346,22 @@ def script_run(preset, algorithm="linear", segments=150, width=400, height=300, 
     return np.ascontiguousarray(rgb.transpose(1, 0, 2)), info
 
 
+def script_run_ex(preset, algorithm="linear", segments=150, width=400, height=300, samples=1, seed=0, device=0, n_devices=1,
+                  stl_path=None):
+    """Script::Run(CudaRenderer::Render, ...) on n_devices GPUs with the reference's ProgressCallback and LogCallback attached;
+    returns (image[y][x][3] or None, info) -- info carries rc, the progress calls seen and the log text."""
+    lib = host_lib()
+    rgb = np.zeros((width, height, 3), np.float32)
+    exe, st, prog = C.c_int(0), Stats(), (C.c_int * 4)()
+    log = C.create_string_buffer(4096)
+    rc = lib.rtbh_script_run_ex(preset, _alg(algorithm), segments, width, height, samples, seed, device, n_devices,
+                                (stl_path or stl_fixture()).encode(), rgb.ctypes.data, C.byref(exe), C.byref(st), prog, log, 4096)
+    info = st.as_dict()
+    info.update(rc=rc, exec_ms=exe.value, progress_calls=prog[0], progress_last=prog[1], progress_total=prog[2],
+                progress_monotone=bool(prog[3]), log=log.value.decode(errors="replace"))
+    return (np.ascontiguousarray(rgb.transpose(1, 0, 2)) if rc == 0 else None), info
+
+
 def script_run8(preset, algorithm="linear", segments=150, width=400, height=300, samples=1, seed=0, device=0,
                 stl_path=None, bmp_path=None):
     """Drop-in path with the reference's 8-bit output stage; returns (uint8 image[y][x][3], info)."""
@@ -375,6 +416,90 @@ class Context:
     def upload(self, flat):
         return DeviceScene(self, flat)
 
+    def forget_schedule(self):
+        """The next frame runs like the first frame of a new view (raster order, no latency tiers)."""
+        self._check(self._lib.rtb_forget_schedule(self._h), "rtb_forget_schedule")
+
+    # ---- one frame buffer, several devices (RTB_LAYOUT_GLOBAL; include/rtb.h section A) ----
+    def device_alloc(self, nbytes):
+        p = C.c_void_p()
+        self._check(self._lib.rtb_device_alloc(self._h, nbytes, C.byref(p)), "rtb_device_alloc")
+        return p.value
+
+    def device_free(self, ptr):
+        self._check(self._lib.rtb_device_free(self._h, C.c_void_p(ptr)), "rtb_device_free")
+
+    def device_download(self, ptr, out):
+        """synchronous copy of out.nbytes bytes of a device frame into the numpy array `out`"""
+        self._check(self._lib.rtb_device_download(self._h, C.c_void_p(ptr), out.ctypes.data, out.nbytes), "rtb_device_download")
+        return out
+
+    def ipc_export(self, ptr):
+        buf = C.create_string_buffer(IPC_HANDLE_BYTES)
+        self._check(self._lib.rtb_ipc_export(self._h, C.c_void_p(ptr), buf), "rtb_ipc_export")
+        return buf.raw
+
+    def ipc_open(self, handle):
+        p = C.c_void_p()
+        self._check(self._lib.rtb_ipc_open(self._h, C.create_string_buffer(bytes(handle), IPC_HANDLE_BYTES), C.byref(p)), "rtb_ipc_open")
+        return p.value
+
+    def ipc_close(self, ptr):
+        self._check(self._lib.rtb_ipc_close(self._h, C.c_void_p(ptr)), "rtb_ipc_close")
+
+
+class MultiContext:
+    """rtb_multi_*: one host thread drives n devices; rtb_multi_render returns ONE assembled host frame."""
+
+    def __init__(self, n_devices, devices=None):
+        self._lib = cuda_lib()
+        self._h = C.c_void_p()
+        arr = (C.c_int * n_devices)(*devices) if devices is not None else None
+        rc = self._lib.rtb_multi_init(n_devices, arr, C.byref(self._h))
+        if rc != 0:
+            raise RtbError(f"rtb_multi_init({n_devices}) failed rc={rc}: {self._lib.rtb_last_error(None).decode()}")
+        self.n = n_devices
+
+    def close(self):
+        if self._h:
+            self._lib.rtb_multi_shutdown(self._h)
+            self._h = C.c_void_p()
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise RtbError(f"{what} failed rc={rc}: {self._lib.rtb_multi_last_error(self._h).decode()}")
+
+    def upload(self, flat):
+        return MultiScene(self, flat)
+
+
+class MultiScene:
+    def __init__(self, multi, flat):
+        self.multi = multi
+        self._h = C.c_void_p()
+        multi._check(multi._lib.rtb_multi_scene_upload(multi._h, flat, C.byref(self._h)), "rtb_multi_scene_upload")
+
+    def close(self):
+        if self._h:
+            self.multi._lib.rtb_multi_scene_free(self.multi._h, self._h)
+            self._h = C.c_void_p()
+
+    @property
+    def upload_bytes(self):
+        return int(self.multi._lib.rtb_multi_scene_upload_bytes(self._h))
+
+    def render(self, camera, setting, frame, out=None):
+        """The whole frame into ONE host buffer: [height][width][3] (reference order [width][height][3] with LAYOUT_REFERENCE)."""
+        if out is None:
+            shape = (frame.width, frame.height, 3) if frame.layout & LAYOUT_REFERENCE else (frame.height, frame.width, 3)
+            if frame.layout & OUTPUT_MOMENTS:
+                shape = shape[:2] + (6,)
+            out = np.zeros(shape, np.uint8 if frame.layout & OUTPUT_RGB8 else np.float32)
+        st = Stats()
+        self.multi._check(self.multi._lib.rtb_multi_render(self.multi._h, self._h, C.byref(camera), C.byref(setting), C.byref(frame),
+                                                           out.ctypes.data, C.byref(st)), "rtb_multi_render")
+        return out, st.as_dict()
+
 
 def unshard_device(ctx, gathered_ptr, image_ptr, width, height, world, row_block, rows_per_rank, stream=0):
     ctx._check(ctx._lib.rtb_unshard_device(ctx._h, C.c_void_p(gathered_ptr), C.c_void_p(image_ptr), width, height, world,
@@ -412,9 +537,11 @@ def shard_width(frame):
     return int(cuda_lib().rtb_shard_width(C.byref(frame)))
 
 
-def make_frame(width, height, samples=1, seed=0, rank=0, world=1, row_block=8, layout=LAYOUT_ROWMAJOR, counters=0, col_block=0):
-    """col_block > 0 (and world > 1): column-block shard, local image [height][width / world] (include/rtb.h)."""
-    return Frame(width, height, samples, seed, rank, world, row_block, layout, counters, col_block)
+def make_frame(width, height, samples=1, seed=0, rank=0, world=1, row_block=8, layout=LAYOUT_ROWMAJOR, counters=0, col_block=0,
+               sample_first=0, sample_count=0):
+    """col_block > 0 (and world > 1): column-block shard, local image [height][width / world] (include/rtb.h).
+    sample_count > 0: Monte-Carlo sample shard [sample_first, sample_first + sample_count) of `samples`."""
+    return Frame(width, height, samples, seed, rank, world, row_block, layout, counters, col_block, sample_first, sample_count)
 
 
 def shard_col_indices(width, y, rank, world, row_block, col_block):
@@ -427,6 +554,26 @@ def shard_col_indices(width, y, rank, world, row_block, col_block):
         bx = c * world + shift
         xs.extend(range(bx * col_block, (bx + 1) * col_block))
     return np.asarray(xs, np.int64)
+
+
+def sample_shard(samples, rank, world):
+    """(sample_first, sample_count) of rank's share of a Monte-Carlo frame's samples: contiguous ranges, the first
+    samples % world ranks take one more (rtb_frame.sample_first / sample_count)."""
+    base, extra = divmod(samples, world)
+    first = rank * base + min(rank, extra)
+    return first, base + (1 if rank < extra else 0)
+
+
+def shard_pixel_mask(width, height, rank, world, row_block=8, col_block=0):
+    """bool [height][width]: the pixels of the frame rank `rank` stores with RTB_LAYOUT_GLOBAL (mirror of localToGlobal
+    in csrc/rtb_kernels.cuh: row blocks dealt round-robin, or column blocks rotated from block row to block row)."""
+    m = np.zeros((height, width), bool)
+    if col_block and world > 1:
+        for y in range(height):
+            m[y, shard_col_indices(width, y, rank, world, row_block, col_block)] = True
+    else:
+        m[shard_row_indices(height, rank, world, row_block)] = True
+    return m
 
 
 def shard_row_indices(height, rank, world, row_block=8):
@@ -472,6 +619,8 @@ class DeviceScene:
             raise RtbError("bad frame: size / rank / world / row_block (must be a multiple of 8)")
         if out is None:
             shape = (frame.width, frame.height, 3) if frame.layout & LAYOUT_REFERENCE else (rows, shard_width(frame), 3)
+            if frame.layout & OUTPUT_MOMENTS:
+                shape = shape[:2] + (6,)
             out = np.zeros(shape, np.uint8 if frame.layout & OUTPUT_RGB8 else np.float32)
         st = Stats()
         self.ctx._check(self.ctx._lib.rtb_render(self.ctx._h, self._h, C.byref(camera), C.byref(setting), C.byref(frame),

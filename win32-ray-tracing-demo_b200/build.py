@@ -17,7 +17,12 @@ CUDA_LIB = os.path.join(PKG, "librtb200.so")
 HOST_LIB = os.path.join(PKG, "librtb200_host.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-fmad=false", "-Xcompiler", "-fPIC", "-shared"]
+              "-fmad=false", "-Xcompiler", "-fPIC"]
+# one translation unit per kernel family (the kernels are templates over probe x accelerator family x fold-stack size):
+# compiled side by side, linked into one library
+CUDA_UNITS = ["rtb_abi.cu", "rtb_k_chain.cu", "rtb_k_sm.cu", "rtb_k_oct.cu", "rtb_k_wide.cu", "rtb_k_mc.cu"]
+CUDA_HEADERS = ["rtb_launch.h", "rtb_misc.cuh", "rtb_chain_sm.cuh", "rtb_chain_wide.cuh", "rtb_chain_oct.cuh", "rtb_build_grid.cuh",
+                "rtb_kernels.cuh", "rtb_device.cuh", "rtb_pretest.h"]
 GXX_FLAGS = ["-O2", "-std=c++17", "-fopenmp", "-ffp-contract=off", "-fPIC", "-shared", "-Wall"]
 
 
@@ -33,13 +38,28 @@ def _nvcc():
 
 
 def build_cuda(force=False, verbose=False):
-    src = [os.path.join(PKG, "csrc", f) for f in ("rtb_abi.cu", "rtb_chain_sm.cuh", "rtb_chain_wide.cuh", "rtb_chain_oct.cuh", "rtb_build_grid.cuh", "rtb_kernels.cuh", "rtb_device.cuh")]
-    src.append(os.path.join(ROOT, "include", "rtb.h"))
-    if not force and _newer(CUDA_LIB, src):
+    from concurrent.futures import ThreadPoolExecutor
+    csrc = os.path.join(PKG, "csrc")
+    units = [os.path.join(csrc, f) for f in CUDA_UNITS]
+    deps = units + [os.path.join(csrc, f) for f in CUDA_HEADERS] + [os.path.join(ROOT, "include", "rtb.h")]
+    if not force and _newer(CUDA_LIB, deps):
         return CUDA_LIB
     extra = os.environ.get("RTB_NVCC_EXTRA", "").split()  # tuning experiments, e.g. -DRTB_CHAIN_MIN_CTAS=6
-    cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", CUDA_LIB, src[0]]
-    subprocess.check_call(cmd, cwd=PKG)
+    objdir = os.path.join(PKG, "build")
+    os.makedirs(objdir, exist_ok=True)
+    headers_t = max(os.path.getmtime(d) for d in deps[len(units):])
+
+    def compile_unit(src):
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        if not force and not extra and os.path.exists(obj) and os.path.getmtime(obj) >= max(os.path.getmtime(src), headers_t):
+            return obj
+        cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+        subprocess.check_call(cmd, cwd=PKG)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=len(units)) as pool:
+        objs = list(pool.map(compile_unit, units))
+    subprocess.check_call([_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", CUDA_LIB] + objs, cwd=PKG)
     return CUDA_LIB
 
 

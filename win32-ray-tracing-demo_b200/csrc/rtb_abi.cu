@@ -13,9 +13,8 @@
 #include <chrono>
 #include <vector>
 
-#include "rtb_chain_sm.cuh"
-#include "rtb_chain_wide.cuh"
-#include "rtb_chain_oct.cuh"
+#include "rtb_launch.h"
+#include "rtb_misc.cuh"
 #include "rtb_build_grid.cuh"
 
 #ifndef RTB_SPLIT_MAX_TILES
@@ -83,9 +82,17 @@ struct rtb_ctx
     int device = -1;
     cudaStream_t stream = nullptr;
     Counters *d_counters = nullptr;
+    rtb_progress_fn progress = nullptr; // rtb_set_progress
+    void *progress_user = nullptr;
+    cudaStream_t poll = nullptr;        // side stream of the progress reads
+    unsigned long long *h_tiles = nullptr;
+    Counters *h_counters = nullptr; // page-locked: the read-back of a timed frame must not block the launching thread
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaStream_t aux = nullptr;                 // high-priority side stream of the latency-critical tiles
     cudaEvent_t fork = nullptr, join = nullptr;
+    cudaEvent_t last_frame = nullptr;      // recorded behind the last kernel of every frame (waitLastFrame)
+    cudaStream_t last_frame_stream = nullptr;
+    bool frame_pending = false;
     float *d_frame = nullptr; // grow-only device framebuffer of the host-buffer render call
     size_t d_frame_bytes = 0;
     // heaviest-first tile scheduling (rtb_kernels.cuh): cost of the last frame and the order derived from it
@@ -217,8 +224,10 @@ extern "C" int rtb_init(int device, rtb_ctx **out)
         CUDA_TRY(ctx, cudaStreamCreateWithPriority(&ctx->aux, cudaStreamNonBlocking, hi));
         CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->fork, cudaEventDisableTiming));
         CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->join, cudaEventDisableTiming));
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->last_frame, cudaEventDisableTiming));
     }
     CUDA_TRY(ctx, cudaMalloc(&ctx->d_counters, sizeof(Counters)));
+    CUDA_TRY(ctx, cudaHostAlloc((void **)&ctx->h_counters, sizeof(Counters), cudaHostAllocDefault));
     for (int i = 0; i < 4; i++) CUDA_TRY(ctx, cudaEventCreate(&ctx->ev[i]));
     *out = ctx;
     return RTB_OK;
@@ -228,13 +237,18 @@ extern "C" int rtb_shutdown(rtb_ctx *ctx)
 {
     if (!ctx) return RTB_OK;
     cudaSetDevice(ctx->device);
+    if (ctx->frame_pending) cudaEventSynchronize(ctx->last_frame); // a frame on a caller's stream
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->last_frame) cudaEventDestroy(ctx->last_frame);
     for (int i = 0; i < 4; i++)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->aux) { cudaStreamSynchronize(ctx->aux); cudaStreamDestroy(ctx->aux); }
     if (ctx->fork) cudaEventDestroy(ctx->fork);
     if (ctx->join) cudaEventDestroy(ctx->join);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
+    if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+    if (ctx->h_tiles) cudaFreeHost(ctx->h_tiles);
+    if (ctx->poll) cudaStreamDestroy(ctx->poll);
     if (ctx->d_frame) cudaFree(ctx->d_frame);
     if (ctx->d_cost) cudaFreeAsync(ctx->d_cost, ctx->stream);
     if (ctx->d_order) cudaFreeAsync(ctx->d_order, ctx->stream);
@@ -892,17 +906,37 @@ static int makeFrame(rtb_ctx *ctx, const rtb_scene *scene, const rtb_camera *cam
 {
     if (!ctx || !scene || !cam || !setting || !frame) return fail(ctx, RTB_ERR_INVALID, "render: null argument");
     if (frame->width <= 0 || frame->height <= 0) return fail(ctx, RTB_ERR_INVALID, "render: bad image size");
-    const int64_t rows = rtb_shard_rows(frame);
+    const int world = frame->world > 0 ? frame->world : 1;
+    if (frame->layout & ~(RTB_LAYOUT_REFERENCE | RTB_LAYOUT_GLOBAL | RTB_OUTPUT_RGB8 | RTB_OUTPUT_MOMENTS))
+        return fail(ctx, RTB_ERR_INVALID, "render: unknown layout flags");
+    const bool global = (frame->layout & RTB_LAYOUT_GLOBAL) != 0;
+    const bool reference = (frame->layout & RTB_LAYOUT_REFERENCE) != 0;
+    int64_t rows;
+    if (reference && global && colSharded(frame))
+    { // the reference order addresses by frame coordinates, so a column-block shard can store into the whole frame too
+        rtb_frame plain = *frame;
+        plain.layout &= ~RTB_LAYOUT_REFERENCE;
+        rows = rtb_shard_rows(&plain);
+    }
+    else rows = rtb_shard_rows(frame);
     if (rows < 0)
         return fail(ctx, RTB_ERR_INVALID, "render: bad shard (rank / world / row_block: row_block must be a multiple of 8; col_block: a multiple "
                                           "of 8 with width a multiple of world * col_block, row-major layout)");
-    const int world = frame->world > 0 ? frame->world : 1;
-    if (frame->layout & ~(RTB_LAYOUT_REFERENCE | RTB_OUTPUT_RGB8)) return fail(ctx, RTB_ERR_INVALID, "render: unknown layout flags");
-    if ((frame->layout & RTB_LAYOUT_REFERENCE) && world != 1)
-        return fail(ctx, RTB_ERR_INVALID, "render: the reference (column-major) layout needs the whole frame on one rank");
+    if (reference && world != 1 && !global)
+        return fail(ctx, RTB_ERR_INVALID, "render: the reference (column-major) layout needs the whole frame in one buffer (one rank, or RTB_LAYOUT_GLOBAL)");
+    const bool moments = (frame->layout & RTB_OUTPUT_MOMENTS) != 0;
+    if (moments && (!setting->enable_monte_carlo || reference || (frame->layout & RTB_OUTPUT_RGB8)))
+        return fail(ctx, RTB_ERR_INVALID, "render: RTB_OUTPUT_MOMENTS needs a Monte-Carlo setting and a row-major float buffer");
+    int sFirst = 0, sEnd = frame->samples;
     if (setting->enable_monte_carlo)
     {
         if (frame->samples <= 0) return fail(ctx, RTB_ERR_INVALID, "render: samples must be positive");
+        if (frame->sample_count != 0 || frame->sample_first != 0)
+        {
+            if (frame->sample_first < 0 || frame->sample_count <= 0 || (int64_t)frame->sample_first + frame->sample_count > frame->samples)
+                return fail(ctx, RTB_ERR_INVALID, "render: sample shard outside [0, samples)");
+            sFirst = frame->sample_first; sEnd = sFirst + frame->sample_count;
+        }
         int need = setting->single_tracing_depth;
         if (setting->max_depth < need) need = setting->max_depth;
         if (need > RTB_MAX_DEPTH) need = RTB_MAX_DEPTH;
@@ -915,12 +949,15 @@ static int makeFrame(rtb_ctx *ctx, const rtb_scene *scene, const rtb_camera *cam
     F.cam = *cam;
     F.setting = *setting;
     F.width = frame->width; F.height = frame->height; F.samples = frame->samples;
+    F.sample_first = sFirst; F.sample_end = sEnd;
     F.rank = frame->rank; F.world = world; F.row_block = normRowBlock(frame);
     F.layout = frame->layout & RTB_LAYOUT_REFERENCE;
     F.rgb8 = (frame->layout & RTB_OUTPUT_RGB8) ? 1 : 0;
+    F.moments = moments ? 1 : 0;
+    F.global_out = (global && !reference) ? 1 : 0; // the reference order is addressed by frame coordinates anyway
     F.n_local_rows = (int)rows;
     F.col_block = colSharded(frame) ? frame->col_block : 0;
-    F.local_width = (int)rtb_shard_width(frame);
+    F.local_width = F.col_block ? frame->width / world : frame->width;
     F.tiles_x = (F.local_width + RTB_TILE_W - 1) / RTB_TILE_W;
     F.n_tiles = F.tiles_x * (int)((rows + RTB_TILE_H - 1) / RTB_TILE_H);
     F.cost_map = frame->counters == 2;
@@ -929,8 +966,17 @@ static int makeFrame(rtb_ctx *ctx, const rtb_scene *scene, const rtb_camera *cam
     return RTB_OK;
 }
 
-template <class Probe>
-static int launchRender(rtb_ctx *ctx, const rtb_scene *scene, FrameParams &F, float *out, Counters *counters, cudaStream_t stream,
+// bytes of the output buffer a frame's shard stores into when it is NOT the whole frame
+static size_t shardBytes(const FrameParams &F)
+{
+    return (size_t)F.n_local_rows * F.local_width * 3 * (F.rgb8 ? 1 : sizeof(float)) * (F.moments ? 2 : 1);
+}
+static size_t frameBytes(const FrameParams &F)
+{
+    return (size_t)F.height * F.width * 3 * (F.rgb8 ? 1 : sizeof(float)) * (F.moments ? 2 : 1);
+}
+
+static int launchRender(rtb_ctx *ctx, const rtb_scene *scene, FrameParams &F, bool count, float *out, Counters *counters, cudaStream_t stream,
                         int &n_kernels)
 {
     n_kernels = 1;
@@ -942,8 +988,9 @@ static int launchRender(rtb_ctx *ctx, const rtb_scene *scene, FrameParams &F, fl
     const bool kd_accel = accel == RTB_ACCEL_KD_MEDIAN || accel == RTB_ACCEL_KD_SAH;
     F.skip_heavy = 0;
     F.record_cost = 1;
-    if (F.setting.enable_monte_carlo) k_montecarlo<Probe><<<grid, RTB_CTA_THREADS, 0, stream>>>(scene->d, F, out, counters);
-    else if (scene->has_refractive) k_whitted_tree<Probe><<<grid, RTB_CTA_THREADS, 0, stream>>>(scene->d, F, out, counters);
+    auto L = [&](const FrameParams &P, dim3 g, cudaStream_t st) { Launch l; l.S = &scene->d; l.F = &P; l.out = out; l.counters = counters; l.grid = g; l.stream = st; l.count = count; return l; };
+    if (F.setting.enable_monte_carlo) launchMonteCarlo(L(F, grid, stream));
+    else if (scene->has_refractive) launchTree(L(F, grid, stream));
     else if (resumable && scene->has_tunnel && (kd_accel || grid_accel) && F.order && ctx->tiers_ok)
     { // A tile order is known.  Three kernels share the frame, all launched at once:
       //   order[0 .. n_wide)         the very heaviest tiles: one warp per pixel        (side stream, high priority)
@@ -963,7 +1010,7 @@ static int launchRender(rtb_ctx *ctx, const rtb_scene *scene, FrameParams &F, fl
             Wd.record_cost = 0;
             Wd.warps_per_cta = warpsPerCta;
             const dim3 wgrid(((unsigned int)nWide * 32u + warpsPerCta - 1) / warpsPerCta);
-            k_whitted_chain_wide<Probe><<<wgrid, RTB_CTA_THREADS, 0, ctx->aux>>>(scene->d, Wd, out, counters);
+            launchChainWide(L(Wd, wgrid, ctx->aux));
             n_kernels++;
         }
         // k_whitted_chain_oct is the latency tier of small k-d shards: worst 1/8 shard of the 4K frame SAH 1.99 -> 1.42 ms,
@@ -976,7 +1023,7 @@ static int launchRender(rtb_ctx *ctx, const rtb_scene *scene, FrameParams &F, fl
         { // one resumable launch for everything after the wide tiles
             FrameParams H = F;
             H.after_wide = 1;
-            k_whitted_chain_sm<Probe, true><<<grid, RTB_CTA_THREADS, 0, stream>>>(scene->d, H, out, counters); // records: it is this frame's throughput kernel
+            launchChainSm(L(H, grid, stream), true); // records: it is this frame's throughput kernel
             CUDA_TRY(ctx, cudaEventRecord(ctx->join, ctx->aux));
             CUDA_TRY(ctx, cudaStreamWaitEvent(stream, ctx->join, 0));
         }
@@ -996,27 +1043,33 @@ static int launchRender(rtb_ctx *ctx, const rtb_scene *scene, FrameParams &F, fl
                 H.skip_heavy = 0; H.after_wide = 0; H.split4 = 0;
                 H.item_base = F.n_wide; H.item_end = F.n_wide + (unsigned int)heavyLimit(F.n_tiles);
                 const dim3 ogrid(((unsigned int)heavyLimit(F.n_tiles) * 8u + warpsPerCta - 1) / warpsPerCta);
-                if (grid_accel) k_whitted_chain_oct<Probe, true><<<ogrid, RTB_CTA_THREADS, 0, ctx->aux>>>(scene->d, H, out, counters);
-                else k_whitted_chain_oct<Probe, false><<<ogrid, RTB_CTA_THREADS, 0, ctx->aux>>>(scene->d, H, out, counters);
+                launchChainOct(L(H, ogrid, ctx->aux), grid_accel);
                 n_kernels++;
             }
             else if (heavyLimit(F.n_tiles) > 0)
             {
                 const unsigned int heavyWarps = (unsigned int)heavyLimit(F.n_tiles) * (H.split4 ? 4u : 1u);
                 const dim3 sgrid((heavyWarps + warpsPerCta - 1) / warpsPerCta);
-                if (grid_accel) k_whitted_chain_sm<Probe, true><<<sgrid, RTB_CTA_THREADS, 0, ctx->aux>>>(scene->d, H, out, counters);
-                else k_whitted_chain_sm<Probe, false><<<sgrid, RTB_CTA_THREADS, 0, ctx->aux>>>(scene->d, H, out, counters);
+                launchChainSm(L(H, sgrid, ctx->aux), grid_accel);
                 n_kernels++;
             }
             CUDA_TRY(ctx, cudaEventRecord(ctx->join, ctx->aux));
             F.skip_heavy = 1;
-            k_whitted_chain<Probe><<<grid, RTB_CTA_THREADS, 0, stream>>>(scene->d, F, out, counters);
+            launchChain(L(F, grid, stream));
             CUDA_TRY(ctx, cudaStreamWaitEvent(stream, ctx->join, 0));
         }
     }
-    else if (resumable && scene->has_tunnel && accel == RTB_ACCEL_REGULAR_GRID)
-        k_whitted_chain_sm<Probe, true><<<grid, RTB_CTA_THREADS, 0, stream>>>(scene->d, F, out, counters);
-    else k_whitted_chain<Probe><<<grid, RTB_CTA_THREADS, 0, stream>>>(scene->d, F, out, counters);
+    else if (resumable && scene->has_tunnel && accel == RTB_ACCEL_REGULAR_GRID) launchChainSm(L(F, grid, stream), true);
+    else launchChain(L(F, grid, stream));
+    return RTB_OK;
+}
+
+// The scheduling state of a context (d_cost, d_order, d_heavy, d_hist, d_counters, the side stream) is shared by all
+// its frames.  Frames are ordered through `last_frame`, recorded behind each frame's last kernel on whatever stream it
+// ran: a frame on another stream, and anything that frees or regrows the state, waits for it first.
+static int waitLastFrame(rtb_ctx *ctx, cudaStream_t stream)
+{
+    if (ctx->frame_pending && stream != ctx->last_frame_stream) CUDA_TRY(ctx, cudaStreamWaitEvent(stream, ctx->last_frame, 0));
     return RTB_OK;
 }
 
@@ -1025,6 +1078,7 @@ static int prepareTileOrder(rtb_ctx *ctx, const rtb_scene *scene, FrameParams &F
 {
     if ((size_t)F.n_tiles > ctx->tile_capacity)
     {
+        if (ctx->frame_pending) CUDA_TRY(ctx, cudaEventSynchronize(ctx->last_frame)); // a frame on a caller's stream may still use the buffers
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
         if (ctx->d_cost) CUDA_TRY(ctx, cudaFreeAsync(ctx->d_cost, ctx->stream));
         ctx->d_cost = nullptr;
@@ -1051,7 +1105,8 @@ static int prepareTileOrder(rtb_ctx *ctx, const rtb_scene *scene, FrameParams &F
     OrderKey key;
     memset(&key, 0, sizeof(key));
     key.v[0] = F.width; key.v[1] = F.height; key.v[2] = F.rank; key.v[3] = F.world; key.v[4] = F.row_block; key.v[5] = F.layout | ((long long)F.col_block << 8);
-    key.v[6] = F.setting.enable_monte_carlo; key.v[7] = F.n_tiles; key.v[8] = F.setting.max_depth; key.v[9] = F.samples;
+    key.v[6] = F.setting.enable_monte_carlo; key.v[7] = F.n_tiles; key.v[8] = F.setting.max_depth;
+    key.v[9] = (long long)F.samples | ((long long)F.sample_first << 20) | ((long long)F.sample_end << 40);
     key.scene_signature = scene->signature;
     key.cam = F.cam;
     ctx->tiers_ok = true;
@@ -1072,34 +1127,51 @@ static int prepareTileOrder(rtb_ctx *ctx, const rtb_scene *scene, FrameParams &F
     return RTB_OK;
 }
 
-static int renderCommon(rtb_ctx *ctx, const rtb_scene *scene, FrameParams &F, const rtb_frame *frame, float *d_out,
-                        cudaStream_t stream, rtb_stats *stats, float *h_out, bool sync = false)
+extern "C" int rtb_forget_schedule(rtb_ctx *ctx)
 {
-    const bool host_frame = sync; // rtb_render's zero-copy path: d_out is the device alias of a page-locked host buffer
+    if (!ctx) return fail(nullptr, RTB_ERR_INVALID, "rtb_forget_schedule: null context");
+    ctx->order_valid = false;
+    memset(&ctx->order_key, 0, sizeof(ctx->order_key));
+    return RTB_OK;
+}
+
+// A frame in flight: what renderFinish needs to collect the statistics once the stream has drained
+struct PendingFrame
+{
+    bool active = false, timed = false;
+    cudaStream_t stream = nullptr;
+    int n_kernels = 0, n_local_rows = 0, n_tiles = 0;
+};
+
+// Queue one frame on `stream`: counters reset, render kernel(s), tile-order kernels, optional copy to h_out.  Nothing
+// here waits for the device.  `timed`: bracket the frame with the context's timing events (one timed frame per context
+// at a time: rtb_render / stats callers, which finish the frame before they return).
+static int renderLaunch(rtb_ctx *ctx, const rtb_scene *scene, FrameParams &F, const rtb_frame *frame, float *d_out,
+                        cudaStream_t stream, bool timed, float *h_out, bool host_frame, PendingFrame &P)
+{
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    const size_t bytes = (size_t)F.n_local_rows * F.local_width * 3 * (F.rgb8 ? 1 : sizeof(float));
-    if (F.n_local_rows == 0)
-    {
-        if (stats) { memset(stats, 0, sizeof(*stats)); }
-        return RTB_OK;
-    }
+    P = PendingFrame();
+    P.stream = stream;
+    P.n_local_rows = F.n_local_rows;
+    if (F.n_local_rows == 0) return RTB_OK;
     if (stream != ctx->stream) CUDA_TRY(ctx, cudaStreamWaitEvent(stream, scene->ready, 0)); // the upload ran on ctx->stream
-    int rc = prepareTileOrder(ctx, scene, F);
+    int rc = waitLastFrame(ctx, stream);
+    if (rc != RTB_OK) return rc;
+    rc = prepareTileOrder(ctx, scene, F);
     if (rc != RTB_OK) return rc;
     // whole-tile 128-bit stores (storeTile): row-major frames whose 8-pixel row segments are 16-byte aligned
     static const bool wideStore = !(getenv("RTB_WIDE_STORE") && atoi(getenv("RTB_WIDE_STORE")) == 0);
-    F.wide_store = wideStore && !F.layout && !F.cost_map && F.local_width % 4 == 0 && ((uintptr_t)d_out & 15u) == 0;
-    if (stats || h_out || sync) CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], stream));
+    F.wide_store = wideStore && !F.layout && !F.cost_map && !F.moments && (F.global_out ? F.width : F.local_width) % 4 == 0 && ((uintptr_t)d_out & 15u) == 0;
+    if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], stream));
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(Counters), stream));
-    if (stats) CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], stream));
+    if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], stream));
     CUDA_TRY(ctx, cudaPeekAtLastError()); // anything stale is reported here, not blamed on the launch
     int n_kernels = 1;
-    if (frame->counters) rc = launchRender<CountProbe>(ctx, scene, F, d_out, ctx->d_counters, stream, n_kernels);
-    else rc = launchRender<NoProbe>(ctx, scene, F, d_out, ctx->d_counters, stream, n_kernels);
+    rc = launchRender(ctx, scene, F, frame->counters != 0, d_out, ctx->d_counters, stream, n_kernels);
     if (rc != RTB_OK) return rc;
     CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cudaEventRecord(scene->last_use, stream));
-    if (stats) CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], stream));
+    if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], stream));
     { // heaviest-first order for the next frame of this geometry: counting sort of the recorded tile costs
         int blocks = (F.n_tiles + 1023) / 1024;
         if (blocks > 296) blocks = 296;
@@ -1115,24 +1187,96 @@ static int renderCommon(rtb_ctx *ctx, const rtb_scene *scene, FrameParams &F, co
         CUDA_TRY(ctx, cudaGetLastError());
         ctx->order_valid = true;
     }
-    if (h_out) CUDA_TRY(ctx, cudaMemcpyAsync(h_out, d_out, bytes, cudaMemcpyDeviceToHost, stream));
-    if (stats || h_out || sync)
+    if (h_out) CUDA_TRY(ctx, cudaMemcpyAsync(h_out, d_out, shardBytes(F), cudaMemcpyDeviceToHost, stream));
+    if (timed)
     {
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev[3], stream));
-        Counters c;
-        if (stats) CUDA_TRY(ctx, cudaMemcpyAsync(&c, ctx->d_counters, sizeof(c), cudaMemcpyDeviceToHost, stream));
-        CUDA_TRY(ctx, cudaStreamSynchronize(stream));
-        if (stats)
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
+    }
+    CUDA_TRY(ctx, cudaEventRecord(ctx->last_frame, stream));
+    ctx->frame_pending = true;
+    ctx->last_frame_stream = stream;
+    P.active = true; P.timed = timed; P.n_kernels = n_kernels; P.n_tiles = F.n_tiles;
+    return RTB_OK;
+}
+
+extern "C" int rtb_set_progress(rtb_ctx *ctx, rtb_progress_fn fn, void *user)
+{
+    if (!ctx) return fail(nullptr, RTB_ERR_INVALID, "rtb_set_progress: null context");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (fn && !ctx->poll)
+    {
+        CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->poll, cudaStreamNonBlocking));
+        CUDA_TRY(ctx, cudaHostAlloc((void **)&ctx->h_tiles, sizeof(unsigned long long), cudaHostAllocDefault));
+    }
+    ctx->progress = fn;
+    ctx->progress_user = user;
+    return RTB_OK;
+}
+
+// While the frames in flight on `ctxs` run: read their finished-tile counters over the side streams and report.
+// The render kernels are not touched; the reads are 8-byte copies that overlap them.
+static void pollProgress(rtb_ctx *const *ctxs, const PendingFrame *P, int n, rtb_progress_fn fn, void *user)
+{
+    long long total = 0;
+    for (int i = 0; i < n; i++) total += P[i].active ? P[i].n_tiles : 0;
+    if (!fn || total == 0) return;
+    long long last = -1;
+    while (true)
+    {
+        bool running = false;
+        long long done = 0;
+        for (int i = 0; i < n; i++)
         {
-            memset(stats, 0, sizeof(*stats));
-            stats->n_rays = (int64_t)c.rays; stats->n_tri_tests = (int64_t)c.tris; stats->n_steps = (int64_t)c.steps;
-            stats->n_local_rows = F.n_local_rows;
-            CUDA_TRY(ctx, cudaEventElapsedTime(&stats->kernel_ms, ctx->ev[1], ctx->ev[2]));
-            CUDA_TRY(ctx, cudaEventElapsedTime(&stats->total_ms, ctx->ev[0], ctx->ev[3]));
-            stats->n_launches = n_kernels + 3; // render kernel(s) + 3 tile-order kernels
+            if (!P[i].active) continue;
+            rtb_ctx *c = ctxs[i];
+            cudaSetDevice(c->device);
+            if (cudaStreamQuery(P[i].stream) == cudaErrorNotReady && c->poll)
+            {
+                running = true;
+                *c->h_tiles = 0;
+                if (cudaMemcpyAsync(c->h_tiles, &c->d_counters->tiles, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->poll) == cudaSuccess)
+                    cudaStreamSynchronize(c->poll);
+                const long long t = (long long)*c->h_tiles;
+                done += t < P[i].n_tiles ? t : P[i].n_tiles;
+            }
+            else done += P[i].n_tiles;
         }
+        cudaGetLastError();
+        if (!running) break;
+        if (done > last) { fn(done, total, user); last = done; }
+        std::this_thread::sleep_for(std::chrono::microseconds(250));
+    }
+    fn(total, total, user);
+}
+
+// Wait for a queued frame and collect its statistics (stats may be null)
+static int renderFinish(rtb_ctx *ctx, PendingFrame &P, rtb_stats *stats, bool poll = true)
+{
+    if (stats) memset(stats, 0, sizeof(*stats));
+    if (!P.active) return RTB_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (poll && ctx->progress) pollProgress(&ctx, &P, 1, ctx->progress, ctx->progress_user);
+    CUDA_TRY(ctx, cudaStreamSynchronize(P.stream));
+    if (stats && P.timed)
+    {
+        const Counters &c = *ctx->h_counters;
+        stats->n_rays = (int64_t)c.rays; stats->n_tri_tests = (int64_t)c.tris; stats->n_steps = (int64_t)c.steps;
+        stats->n_local_rows = P.n_local_rows;
+        CUDA_TRY(ctx, cudaEventElapsedTime(&stats->kernel_ms, ctx->ev[1], ctx->ev[2]));
+        CUDA_TRY(ctx, cudaEventElapsedTime(&stats->total_ms, ctx->ev[0], ctx->ev[3]));
+        stats->n_launches = P.n_kernels + 3; // render kernel(s) + 3 tile-order kernels
     }
     return RTB_OK;
+}
+
+// is `p` page-locked host memory the device can store into?  -> its device alias
+static float *hostAlias(void *p)
+{
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer) return (float *)attr.devicePointer;
+    cudaGetLastError(); // pageable memory: cudaPointerGetAttributes may leave an error behind on older drivers
+    return nullptr;
 }
 
 extern "C" int rtb_render(rtb_ctx *ctx, const rtb_scene *scene, const rtb_camera *cam, const rtb_render_setting *setting,
@@ -1143,33 +1287,43 @@ extern "C" int rtb_render(rtb_ctx *ctx, const rtb_scene *scene, const rtb_camera
     if (rc != RTB_OK) return rc;
     if (!rgb_out) return fail(ctx, RTB_ERR_INVALID, "rtb_render: null output buffer");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    const size_t bytes = (size_t)F.n_local_rows * F.local_width * 3 * (F.rgb8 ? 1 : sizeof(float));
+    if (F.global_out && F.world == 1) F.global_out = 0; // the whole frame on one rank: the same buffer either way
+    PendingFrame P;
     { // Page-locked output buffer (rtb_host_alloc / cudaHostAlloc / cudaHostRegister): the kernels store the pixels
       // straight into it over PCIe while they render, instead of a device framebuffer and a copy after the last
       // kernel.  Measured on the 4K SAH frame (scene upload + render + frame in host memory): 9.71 -> 8.77 ms; the
       // kernels slowed down 6.06 -> 7.47 ms under PCIe back-pressure but the 2.4 ms copy was gone; with whole-tile
       // stores and the light tiles in raster order (k_cost_offsets) the slow-down is 5.48 -> 5.75 ms.
         static const bool zerocopy = !(getenv("RTB_ZEROCOPY") && atoi(getenv("RTB_ZEROCOPY")) == 0);
-        cudaPointerAttributes attr;
         // 8-bit frames too, provided the tiles leave through storeTile (row-major, width % 4 == 0): 32-bit stores of
         // whole 24-byte row segments with the light tiles in raster order (6.72 -> 6.33 ms); written byte by byte
         // they were slower than a device frame + copy (8.82 vs 7.91 ms)
         static const bool zerocopy8 = !(getenv("RTB_ZEROCOPY_RGB8") && atoi(getenv("RTB_ZEROCOPY_RGB8")) == 0);
-        const bool rgb8Direct = zerocopy8 && !F.layout && F.local_width % 4 == 0;
-        if (zerocopy && !F.cost_map && (!F.rgb8 || rgb8Direct) && cudaPointerGetAttributes(&attr, rgb_out) == cudaSuccess && attr.type == cudaMemoryTypeHost &&
-            attr.devicePointer)
-            return renderCommon(ctx, scene, F, frame, (float *)attr.devicePointer, ctx->stream, stats, nullptr, true);
-        cudaGetLastError(); // pageable memory: cudaPointerGetAttributes may leave an error behind on older drivers
+        const bool rgb8Direct = zerocopy8 && !F.layout && (F.global_out ? F.width : F.local_width) % 4 == 0;
+        float *alias = ((zerocopy || F.global_out) && !F.cost_map && (!F.rgb8 || rgb8Direct || F.global_out)) ? hostAlias(rgb_out) : nullptr;
+        if (alias)
+        {
+            rc = renderLaunch(ctx, scene, F, frame, alias, ctx->stream, true, nullptr, true, P);
+            if (rc != RTB_OK) return rc;
+            return renderFinish(ctx, P, stats);
+        }
     }
+    if (F.global_out || (F.layout && F.world != 1))
+        return fail(ctx, RTB_ERR_UNSUPPORTED, "rtb_render: a shard stores into the whole frame (RTB_LAYOUT_GLOBAL) only when the frame is page-locked "
+                                              "host memory (rtb_host_alloc); use rtb_render_device for device frames");
+    const size_t bytes = shardBytes(F);
     if (bytes > ctx->d_frame_bytes)
     {
+        if (ctx->frame_pending) CUDA_TRY(ctx, cudaEventSynchronize(ctx->last_frame));
         if (ctx->d_frame) CUDA_TRY(ctx, cudaFree(ctx->d_frame));
         ctx->d_frame = nullptr;
         ctx->d_frame_bytes = 0;
         CUDA_TRY(ctx, cudaMalloc(&ctx->d_frame, bytes));
         ctx->d_frame_bytes = bytes;
     }
-    return renderCommon(ctx, scene, F, frame, ctx->d_frame, ctx->stream, stats, (float *)rgb_out);
+    rc = renderLaunch(ctx, scene, F, frame, ctx->d_frame, ctx->stream, true, (float *)rgb_out, false, P);
+    if (rc != RTB_OK) return rc;
+    return renderFinish(ctx, P, stats);
 }
 
 extern "C" int rtb_render_device(rtb_ctx *ctx, const rtb_scene *scene, const rtb_camera *cam,
@@ -1180,14 +1334,248 @@ extern "C" int rtb_render_device(rtb_ctx *ctx, const rtb_scene *scene, const rtb
     int rc = makeFrame(ctx, scene, cam, setting, frame, F);
     if (rc != RTB_OK) return rc;
     if (!rgb_device) return fail(ctx, RTB_ERR_INVALID, "rtb_render_device: null output buffer");
-    return renderCommon(ctx, scene, F, frame, (float *)rgb_device, stream ? (cudaStream_t)stream : ctx->stream, stats, nullptr);
+    PendingFrame P;
+    rc = renderLaunch(ctx, scene, F, frame, (float *)rgb_device, stream ? (cudaStream_t)stream : ctx->stream, stats != nullptr, nullptr, false, P);
+    if (rc != RTB_OK || !stats) return rc;
+    return renderFinish(ctx, P, stats);
+}
+
+// ---- one frame buffer, several devices ---------------------------------------------------------------------------
+extern "C" int rtb_device_alloc(rtb_ctx *ctx, size_t bytes, void **out)
+{
+    if (!ctx || !out) return fail(ctx, RTB_ERR_INVALID, "rtb_device_alloc: null argument");
+    *out = nullptr;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaMalloc(out, bytes ? bytes : 1)); // plain cudaMalloc: pool (cudaMallocAsync) memory cannot be exported
+    return RTB_OK;
+}
+
+extern "C" int rtb_device_free(rtb_ctx *ctx, void *p)
+{
+    if (!ctx) return fail(ctx, RTB_ERR_INVALID, "rtb_device_free: null context");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (p) CUDA_TRY(ctx, cudaFree(p));
+    return RTB_OK;
+}
+
+extern "C" int rtb_device_download(rtb_ctx *ctx, const void *device_ptr, void *host, size_t bytes)
+{
+    if (!ctx || !device_ptr || !host) return fail(ctx, RTB_ERR_INVALID, "rtb_device_download: null argument");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (ctx->frame_pending) CUDA_TRY(ctx, cudaEventSynchronize(ctx->last_frame));
+    CUDA_TRY(ctx, cudaMemcpy(host, device_ptr, bytes, cudaMemcpyDeviceToHost));
+    return RTB_OK;
+}
+
+static_assert(sizeof(cudaIpcMemHandle_t) == RTB_IPC_HANDLE_BYTES, "RTB_IPC_HANDLE_BYTES must match cudaIpcMemHandle_t");
+
+extern "C" int rtb_ipc_export(rtb_ctx *ctx, void *device_ptr, unsigned char handle[RTB_IPC_HANDLE_BYTES])
+{
+    if (!ctx || !device_ptr || !handle) return fail(ctx, RTB_ERR_INVALID, "rtb_ipc_export: null argument");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(ctx, cudaIpcGetMemHandle(&h, device_ptr));
+    memcpy(handle, &h, sizeof(h));
+    return RTB_OK;
+}
+
+extern "C" int rtb_ipc_open(rtb_ctx *ctx, const unsigned char handle[RTB_IPC_HANDLE_BYTES], void **mapped)
+{
+    if (!ctx || !handle || !mapped) return fail(ctx, RTB_ERR_INVALID, "rtb_ipc_open: null argument");
+    *mapped = nullptr;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    CUDA_TRY(ctx, cudaIpcOpenMemHandle(mapped, h, cudaIpcMemLazyEnablePeerAccess)); // maps the owner's memory; peer access over NVLink as needed
+    return RTB_OK;
+}
+
+extern "C" int rtb_ipc_close(rtb_ctx *ctx, void *mapped)
+{
+    if (!ctx) return fail(ctx, RTB_ERR_INVALID, "rtb_ipc_close: null context");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (mapped)
+    {
+        if (ctx->frame_pending) CUDA_TRY(ctx, cudaEventSynchronize(ctx->last_frame)); // no frame may still store into it
+        CUDA_TRY(ctx, cudaIpcCloseMemHandle(mapped));
+    }
+    return RTB_OK;
+}
+
+struct rtb_multi
+{
+    std::vector<rtb_ctx *> ctx;
+    void *frame = nullptr; // page-locked frame for callers whose buffer is pageable
+    size_t frame_bytes = 0;
+    rtb_progress_fn progress = nullptr;
+    void *progress_user = nullptr;
+    std::string error;
+};
+struct rtb_multi_scene { std::vector<rtb_scene *> s; };
+
+static int failMulti(rtb_multi *m, int code, const std::string &msg)
+{
+    if (m) m->error = msg;
+    return fail(nullptr, code, msg);
+}
+
+extern "C" const char *rtb_multi_last_error(const rtb_multi *m) { return m ? m->error.c_str() : rtb_last_error(nullptr); }
+extern "C" int rtb_multi_count(const rtb_multi *m) { return m ? (int)m->ctx.size() : 0; }
+extern "C" rtb_ctx *rtb_multi_ctx(rtb_multi *m, int i) { return (m && i >= 0 && i < (int)m->ctx.size()) ? m->ctx[(size_t)i] : nullptr; }
+
+extern "C" int rtb_multi_shutdown(rtb_multi *m)
+{
+    if (!m) return RTB_OK;
+    for (rtb_ctx *c : m->ctx) rtb_shutdown(c);
+    if (m->frame) cudaFreeHost(m->frame);
+    delete m;
+    return RTB_OK;
+}
+
+extern "C" int rtb_multi_init(int n_devices, const int *devices, rtb_multi **out)
+{
+    if (!out) return fail(nullptr, RTB_ERR_INVALID, "rtb_multi_init: null output pointer");
+    *out = nullptr;
+    if (n_devices <= 0 || n_devices > 64) return fail(nullptr, RTB_ERR_INVALID, "rtb_multi_init: device count out of range");
+    rtb_multi *m = new rtb_multi();
+    for (int i = 0; i < n_devices; i++)
+    {
+        rtb_ctx *c = nullptr;
+        const int rc = rtb_init(devices ? devices[i] : i, &c);
+        if (rc != RTB_OK) { rtb_multi_shutdown(m); return rc; }
+        m->ctx.push_back(c);
+    }
+    *out = m;
+    return RTB_OK;
+}
+
+extern "C" int rtb_multi_set_progress(rtb_multi *m, rtb_progress_fn fn, void *user)
+{
+    if (!m) return fail(nullptr, RTB_ERR_INVALID, "rtb_multi_set_progress: null argument");
+    for (rtb_ctx *c : m->ctx)
+    { // the contexts only provide the side stream and the read-back word; the reporting is done here, over all devices
+        const int rc = rtb_set_progress(c, fn, user);
+        if (rc != RTB_OK) return rc;
+        c->progress = nullptr;
+    }
+    m->progress = fn;
+    m->progress_user = user;
+    return RTB_OK;
+}
+
+extern "C" int rtb_multi_scene_free(rtb_multi *m, rtb_multi_scene *s)
+{
+    if (!s) return RTB_OK;
+    for (size_t i = 0; i < s->s.size(); i++)
+        if (s->s[i]) rtb_scene_free(m && i < m->ctx.size() ? m->ctx[i] : nullptr, s->s[i]);
+    delete s;
+    return RTB_OK;
+}
+
+extern "C" int rtb_multi_scene_upload(rtb_multi *m, const rtb_flat_scene *flat, rtb_multi_scene **out)
+{
+    if (!m || !flat || !out) return failMulti(m, RTB_ERR_INVALID, "rtb_multi_scene_upload: null argument");
+    *out = nullptr;
+    const size_t n = m->ctx.size();
+    rtb_multi_scene *s = new rtb_multi_scene();
+    s->s.assign(n, nullptr);
+    std::vector<int> rc(n, RTB_OK);
+    // one uploader per device: staging, the H2D copies and the packing kernels of the replicas run side by side
+    std::vector<std::thread> workers;
+    for (size_t i = 1; i < n; i++) workers.emplace_back([&, i]() { rc[i] = rtb_scene_upload(m->ctx[i], flat, &s->s[i]); });
+    rc[0] = rtb_scene_upload(m->ctx[0], flat, &s->s[0]);
+    for (std::thread &t : workers) t.join();
+    for (size_t i = 0; i < n; i++)
+        if (rc[i] != RTB_OK)
+        {
+            const std::string msg = std::string("device ") + std::to_string(m->ctx[i]->device) + ": " + m->ctx[i]->error;
+            rtb_multi_scene_free(m, s);
+            return failMulti(m, rc[i], msg);
+        }
+    *out = s;
+    return RTB_OK;
+}
+
+extern "C" int64_t rtb_multi_scene_upload_bytes(const rtb_multi_scene *s)
+{
+    int64_t total = 0;
+    if (s) for (const rtb_scene *x : s->s) total += rtb_scene_upload_bytes(x);
+    return total;
+}
+
+extern "C" int rtb_multi_render(rtb_multi *m, const rtb_multi_scene *scene, const rtb_camera *cam, const rtb_render_setting *setting,
+                                const rtb_frame *frame, void *rgb_out, rtb_stats *stats)
+{
+    if (!m || !scene || !cam || !setting || !frame || !rgb_out) return failMulti(m, RTB_ERR_INVALID, "rtb_multi_render: null argument");
+    const int n = (int)m->ctx.size();
+    if ((int)scene->s.size() != n) return failMulti(m, RTB_ERR_INVALID, "rtb_multi_render: the scene belongs to another device set");
+    rtb_frame fr = *frame;
+    fr.rank = 0; fr.world = n;
+    if (fr.row_block <= 0) fr.row_block = 8;
+    // up to 4 devices the heavy row blocks around the vanishing point already land on different devices; above, narrow
+    // column blocks give every device the same mix of tiles
+    if (n < 5 || fr.width % (n * 32) != 0) { if (fr.col_block > 0 && (fr.col_block % 8 != 0 || fr.width % ((int64_t)n * fr.col_block) != 0)) fr.col_block = 0; }
+    else if (fr.col_block <= 0) fr.col_block = 32;
+    if (n > 1) fr.layout |= RTB_LAYOUT_GLOBAL;
+    std::vector<FrameParams> F((size_t)n);
+    for (int i = 0; i < n; i++)
+    {
+        fr.rank = i;
+        const int rc = makeFrame(m->ctx[(size_t)i], scene->s[(size_t)i], cam, setting, &fr, F[(size_t)i]);
+        if (rc != RTB_OK) return failMulti(m, rc, m->ctx[(size_t)i]->error);
+        if (n == 1) F[(size_t)i].global_out = 0;
+    }
+    if (F[0].cost_map) return failMulti(m, RTB_ERR_UNSUPPORTED, "rtb_multi_render: no cost maps");
+    const size_t bytes = frameBytes(F[0]);
+    cudaSetDevice(m->ctx[0]->device);
+    float *alias = hostAlias(rgb_out);
+    bool staged = false;
+    if (!alias)
+    { // pageable caller buffer: the devices store into a page-locked frame of the library, one host copy follows
+        if (bytes > m->frame_bytes)
+        {
+            for (rtb_ctx *c : m->ctx) if (c->frame_pending) { cudaSetDevice(c->device); cudaEventSynchronize(c->last_frame); }
+            if (m->frame) cudaFreeHost(m->frame);
+            m->frame = nullptr; m->frame_bytes = 0;
+            if (cudaHostAlloc(&m->frame, bytes, cudaHostAllocPortable) != cudaSuccess) return failMulti(m, RTB_ERR_OOM, "rtb_multi_render: cannot allocate the page-locked frame");
+            m->frame_bytes = bytes;
+        }
+        alias = hostAlias(m->frame);
+        if (!alias) return failMulti(m, RTB_ERR_CUDA, "rtb_multi_render: page-locked frame is not device-accessible");
+        staged = true;
+    }
+    std::vector<PendingFrame> P((size_t)n);
+    int rc = RTB_OK;
+    for (int i = 0; i < n && rc == RTB_OK; i++)
+    {
+        fr.rank = i;
+        rc = renderLaunch(m->ctx[(size_t)i], scene->s[(size_t)i], F[(size_t)i], &fr, alias, m->ctx[(size_t)i]->stream, true, nullptr, true, P[(size_t)i]);
+        if (rc != RTB_OK) m->error = m->ctx[(size_t)i]->error;
+    }
+    if (rc == RTB_OK && m->progress) pollProgress(m->ctx.data(), P.data(), n, m->progress, m->progress_user);
+    rtb_stats total;
+    memset(&total, 0, sizeof(total));
+    for (int i = 0; i < n; i++)
+    { // every queued frame is waited for, whatever happened to the others
+        rtb_stats st;
+        const int rf = renderFinish(m->ctx[(size_t)i], P[(size_t)i], &st, false);
+        if (rf != RTB_OK && rc == RTB_OK) { rc = rf; m->error = m->ctx[(size_t)i]->error; }
+        total.n_rays += st.n_rays; total.n_tri_tests += st.n_tri_tests; total.n_steps += st.n_steps; total.n_local_rows += st.n_local_rows;
+        total.n_launches += st.n_launches;
+        if (st.kernel_ms > total.kernel_ms) total.kernel_ms = st.kernel_ms;
+        if (st.total_ms > total.total_ms) total.total_ms = st.total_ms;
+    }
+    if (rc != RTB_OK) return fail(nullptr, rc, m->error);
+    if (staged) memcpy(rgb_out, m->frame, bytes);
+    if (stats) *stats = total;
+    return RTB_OK;
 }
 
 extern "C" int rtb_host_alloc(size_t bytes, void **out)
 {
     if (!out) return fail(nullptr, RTB_ERR_INVALID, "rtb_host_alloc: null output pointer");
     *out = nullptr;
-    cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault);
+    cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable); // every device of the process may store into it
     if (e != cudaSuccess) return fail(nullptr, RTB_ERR_CUDA, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
     return RTB_OK;
 }

@@ -33,7 +33,7 @@ enum { OCT_NEXT = 4 };
 #endif
 
 // Eight warps per tile: group g of warp (w & 7) renders pixel (w & 7) * 4 + g of the tile.
-template <class Probe, bool GRID>
+template <class Probe, bool GRID, int FOLD>
 __global__ void __launch_bounds__(RTB_CTA_THREADS, RTB_OCT_MIN_CTAS)
 k_whitted_chain_oct(const __grid_constant__ DScene S, const __grid_constant__ FrameParams F, float *__restrict__ out,
                     Counters *__restrict__ counters)
@@ -50,7 +50,7 @@ k_whitted_chain_oct(const __grid_constant__ DScene S, const __grid_constant__ Fr
     Probe prTop, pr; // prTop: work all eight lanes repeat (top-level geometries); pr: the tunnel walk
 
     const V3 zero = v3(0, 0, 0);
-    float4 fold[RTB_MAX_DEPTH + 1];
+    float4 fold[FOLD];
     int4 stack[GRID ? 1 : RTB_KD_STACK];
     int nfold = 0, depth = 0;
     V3 c = zero;
@@ -322,6 +322,7 @@ k_whitted_chain_oct(const __grid_constant__ DScene S, const __grid_constant__ Fr
         if (nr) atomicAdd(&counters->rays, (unsigned long long)nr);
         if (tris) atomicAdd(&counters->tris, (unsigned long long)tris);
         if (steps) atomicAdd(&counters->steps, (unsigned long long)steps);
+        if ((w & 7u) == 0u) atomicAdd(&counters->tiles, 1ull); // eight warps per tile
     }
 }
 

@@ -30,7 +30,7 @@ enum { SM_STEP = 0, SM_LEAF = 1, SM_SHADE = 2, SM_DONE = 3, SM_EXACT = 4 };
 #define RTB_SM_MIN_CTAS 6
 #endif
 
-template <class Probe, bool GRID>
+template <class Probe, bool GRID, int FOLD>
 __global__ void __launch_bounds__(RTB_CTA_THREADS, GRID ? RTB_CHAIN_MIN_CTAS : RTB_SM_MIN_CTAS)
 k_whitted_chain_sm(const __grid_constant__ DScene S, const __grid_constant__ FrameParams F, float *__restrict__ out,
                    Counters *__restrict__ counters)
@@ -58,7 +58,7 @@ k_whitted_chain_sm(const __grid_constant__ DScene S, const __grid_constant__ Fra
         const float dx = 1.0f / F.height, dy = 1.0f / F.height;
         const float sx = (x + 0.5f) * dx, sy = 1 - (y + 0.5f) * dy;
         Ray r = generateRay(F.cam, sx, sy);
-        float4 fold[RTB_MAX_DEPTH + 1];
+        float4 fold[FOLD];
         int4 stack[GRID ? 1 : RTB_KD_STACK];
         int nfold = 0, depth = 0;
         V3 c = v3(0, 0, 0);

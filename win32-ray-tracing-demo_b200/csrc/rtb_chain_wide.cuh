@@ -19,7 +19,7 @@ namespace rtb {
 // 128-thread CTAs (4 pixel-warps): they fit wherever a CTA of the throughput kernels retires.  Whole-SM CTAs
 // (1024 threads at 64 registers, no co-residents) measured ~15 % faster when they get their SMs at once and
 // twice as slow whenever the other kernels of the frame reach the SMs first -- not kept.
-template <class Probe>
+template <class Probe, int FOLD>
 __global__ void __launch_bounds__(RTB_CTA_THREADS, 4)
 k_whitted_chain_wide(const __grid_constant__ DScene S, const __grid_constant__ FrameParams F, float *__restrict__ out,
                      Counters *__restrict__ counters)
@@ -36,7 +36,7 @@ k_whitted_chain_wide(const __grid_constant__ DScene S, const __grid_constant__ F
     if (!localToGlobal(F, tx * RTB_TILE_W + (int)(w & 7u), lr, x, y)) return; // warp-uniform
     unsigned int rays = 0;
     Probe prTop, prWalk; // prTop: work every lane repeats (top-level geometries); prWalk: the tunnel walk
-    const V3 c = chainWith(S, F, x, y, rays, prTop, [&](const Ray &r, Hit &h) {
+    const V3 c = chainWith<FOLD>(S, F, x, y, rays, prTop, [&](const Ray &r, Hit &h) {
         return sceneIntersectWith(S, r, h, prTop, [&](int &tri, float &t, V3 &n) {
             if (S.accel == RTB_ACCEL_REGULAR_GRID || S.accel == RTB_ACCEL_FLAT_GRID) return gridIntersect<true>(S, r, tri, t, n, prWalk);
             return kdIntersect<true>(S, r, tri, t, n, prWalk);
@@ -54,6 +54,7 @@ k_whitted_chain_wide(const __grid_constant__ DScene S, const __grid_constant__ F
         if (rays) atomicAdd(&counters->rays, (unsigned long long)rays);
         if (tris) atomicAdd(&counters->tris, (unsigned long long)tris);
         if (steps) atomicAdd(&counters->steps, (unsigned long long)steps);
+        if ((w & 31u) == 0u) atomicAdd(&counters->tiles, 1ull); // 32 warps per tile
     }
 }
 

@@ -113,7 +113,7 @@ struct DScene
 // reflected ray by trace() (MainWindow.cpp:105, PerformanceTest/main.cpp:57)
 struct RayCtx { int inTunnel, segment; };
 
-struct Counters { unsigned long long rays, tris, steps; };
+struct Counters { unsigned long long rays, tris, steps, tiles; }; // tiles: finished tiles of the frame in flight (progress reporting)
 
 // Probes: compile-time observation policy.  NoProbe costs nothing.
 struct NoProbe

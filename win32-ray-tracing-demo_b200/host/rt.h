@@ -448,6 +448,14 @@ class CudaRenderer
 public:
     static CudaRenderer &instance();
     void configure(int width, int height, int samples, int device = 0, uint64_t seed = 0);
+    // Render on `n` devices (0 .. n - 1) driven by this one host thread: the frame is sharded over them and every
+    // device stores its tiles straight into the one host frame (rtb_multi_render).  1 = the single device given to
+    // configure().  SURVEY 8b threading row.
+    void setDevices(int n);
+    int devices() const { return nDevices_; }
+    // The reference's Render has no error channel (Scripts.h:11-12): failures are reported through this callback (the
+    // LogCallback the caller also hands to Script::Run) and surface as a negative return value.
+    void setLog(LogCallback log) { log_ = log; }
     static int Render(GeometrySet &scene, PerspectiveCamera &camera, RenderSetting &setting, ProgressCallback progress);
     const std::vector<float> &image() const { return image_; } // reference order: index = x*height + y
     // Output stage of the reference's Render (MainWindow.cpp:305-311): when enabled the GPU saturates and
@@ -465,9 +473,13 @@ public:
     int width() const { return width_; }
     int height() const { return height_; }
 private:
-    int width_ = 400, height_ = 300, samples_ = 1, device_ = 0;
+    int failed(int code, const char *what, const char *detail);
+    rtb_multi *multi();
+    int width_ = 400, height_ = 300, samples_ = 1, device_ = 0, nDevices_ = 1;
     uint64_t seed_ = 0;
     rtb_ctx *ctx_ = nullptr;
+    rtb_multi *multi_ = nullptr;
+    LogCallback log_ = nullptr;
     std::vector<float> image_;
     std::vector<unsigned char> pixels_;
     bool output8_ = false;

@@ -28,6 +28,13 @@ void CudaRenderer::configure(int width, int height, int samples, int device, uin
     width_ = width; height_ = height; samples_ = samples; device_ = device; seed_ = seed;
 }
 
+void CudaRenderer::setDevices(int n)
+{
+    if (n < 1) n = 1;
+    if (n != nDevices_ && multi_) { rtb_multi_shutdown(multi_); multi_ = nullptr; }
+    nDevices_ = n;
+}
+
 rtb_ctx *CudaRenderer::context()
 {
     if (!ctx_)
@@ -38,6 +45,16 @@ rtb_ctx *CudaRenderer::context()
     return ctx_;
 }
 
+rtb_multi *CudaRenderer::multi()
+{
+    if (!multi_)
+    {
+        const int rc = rtb_multi_init(nDevices_, nullptr, &multi_);
+        if (rc != RTB_OK) { error_ = rtb_last_error(nullptr); multi_ = nullptr; }
+    }
+    return multi_;
+}
+
 void CudaRenderer::shutdown()
 {
     if (pinned_) rtb_host_free(pinned_);
@@ -45,20 +62,42 @@ void CudaRenderer::shutdown()
     pinnedFloats_ = 0;
     if (ctx_) rtb_shutdown(ctx_);
     ctx_ = nullptr;
+    if (multi_) rtb_multi_shutdown(multi_);
+    multi_ = nullptr;
+}
+
+int CudaRenderer::failed(int code, const char *what, const char *detail)
+{
+    error_ = std::string(what) + ": " + (detail ? detail : "");
+    if (log_) log_(("CudaRenderer: " + error_ + "\r\n").c_str()); // the reference's log lines end in \r\n (Scripts.cpp)
+    return code;
+}
+
+// rtb_progress_fn -> ProgressCallback(cur, total) in the reference's unit, image rows (MainWindow.cpp:271)
+struct ProgressAdapter { ProgressCallback fn; int height; int last; };
+static void progressTrampoline(int64_t done, int64_t total, void *user)
+{
+    ProgressAdapter *a = static_cast<ProgressAdapter *>(user);
+    const int cur = total > 0 ? (int)((done * a->height) / total) : a->height;
+    if (cur != a->last) { a->last = cur; a->fn(cur, a->height); }
 }
 
 int CudaRenderer::Render(GeometrySet &scene, PerspectiveCamera &camera, RenderSetting &setting, ProgressCallback progress)
 { // replaces reference MainWindow.cpp:251-316
     CudaRenderer &self = instance();
-    rtb_ctx *ctx = self.context();
-    if (!ctx) return -1;
+    const bool many = self.nDevices_ > 1;
+    rtb_ctx *ctx = many ? nullptr : self.context();
+    rtb_multi *mul = many ? self.multi() : nullptr;
+    if (!ctx && !mul) return self.failed(-1, "no CUDA device", self.error_.c_str());
     const double t0 = nowMs();
     FlatScene flat;
     scene.flatten(flat);
     flat.finish();
     rtb_scene *dev = nullptr;
-    int rc = rtb_scene_upload(ctx, &flat.view, &dev);
-    if (rc != RTB_OK) { self.error_ = rtb_last_error(ctx); return -2; }
+    rtb_multi_scene *mdev = nullptr;
+    int rc = many ? rtb_multi_scene_upload(mul, &flat.view, &mdev) : rtb_scene_upload(ctx, &flat.view, &dev);
+    if (rc != RTB_OK) return self.failed(-2, "scene upload", many ? rtb_multi_last_error(mul) : rtb_last_error(ctx));
+    auto release = [&]() { if (many) rtb_multi_scene_free(mul, mdev); else rtb_scene_free(ctx, dev); };
     const rtb_camera cam = camera.flatten();
     const rtb_render_setting rs = setting.flatten();
     rtb_frame frame;
@@ -68,18 +107,24 @@ int CudaRenderer::Render(GeometrySet &scene, PerspectiveCamera &camera, RenderSe
     frame.layout = RTB_LAYOUT_REFERENCE | (self.output8_ ? RTB_OUTPUT_RGB8 : 0); // colors[x*height + y], MainWindow.cpp:276
     const size_t floats = (size_t)self.width_ * self.height_ * 3;
     if (floats > self.pinnedFloats_)
-    { // page-locked staging buffer so the framebuffer read-back runs at full PCIe rate
+    { // page-locked frame: the devices store their pixels straight into it
         if (self.pinned_) rtb_host_free(self.pinned_);
         self.pinned_ = nullptr;
         self.pinnedFloats_ = 0;
         void *p = nullptr;
-        if (rtb_host_alloc(floats * sizeof(float), &p) != RTB_OK) { rtb_scene_free(ctx, dev); self.error_ = rtb_last_error(nullptr); return -4; }
+        if (rtb_host_alloc(floats * sizeof(float), &p) != RTB_OK) { release(); return self.failed(-4, "rtb_host_alloc", rtb_last_error(nullptr)); }
         self.pinned_ = (float *)p;
         self.pinnedFloats_ = floats;
     }
-    rc = rtb_render(ctx, dev, &cam, &rs, &frame, self.pinned_, &self.stats_);
-    rtb_scene_free(ctx, dev);
-    if (rc != RTB_OK) { self.error_ = rtb_last_error(ctx); return -3; }
+    ProgressAdapter adapter = {progress, self.height_, -1};
+    if (many) rtb_multi_set_progress(mul, progress ? progressTrampoline : nullptr, &adapter);
+    else rtb_set_progress(ctx, progress ? progressTrampoline : nullptr, &adapter);
+    rc = many ? rtb_multi_render(mul, mdev, &cam, &rs, &frame, self.pinned_, &self.stats_)
+              : rtb_render(ctx, dev, &cam, &rs, &frame, self.pinned_, &self.stats_);
+    if (many) rtb_multi_set_progress(mul, nullptr, nullptr);
+    else rtb_set_progress(ctx, nullptr, nullptr);
+    release();
+    if (rc != RTB_OK) return self.failed(-3, "render", many ? rtb_multi_last_error(mul) : rtb_last_error(ctx));
     if (self.output8_)
     {
         const unsigned char *bytes = reinterpret_cast<const unsigned char *>(self.pinned_);
@@ -91,7 +136,7 @@ int CudaRenderer::Render(GeometrySet &scene, PerspectiveCamera &camera, RenderSe
         self.image_.assign(self.pinned_, self.pinned_ + floats);
         self.pixels_.clear();
     }
-    if (progress) progress(self.height_, self.height_);
+    if (progress && adapter.last != self.height_) progress(self.height_, self.height_);
     const double ms = nowMs() - t0;
     return ms < 1.0 ? 1 : (int)(ms + 0.5);
 }
@@ -548,6 +593,45 @@ int rtbh_script_run(int preset, int algorithm, int segments, int width, int heig
     script.Run(CudaRenderer::Render, algorithm, nullptr, nullptr, prep, exec);
     if (prepare_ms) *prepare_ms = prep;
     if (exec_ms) *exec_ms = exec;
+    if (exec < 0) return exec;
+    if (rgb_out) memcpy(rgb_out, r.image().data(), r.image().size() * sizeof(float));
+    if (stats) *stats = r.stats();
+    return 0;
+}
+
+// The same path with everything a caller of the reference can observe: `n_devices` GPUs behind the one RenderProc,
+// the ProgressCallback (calls counted, monotone, last value) and the LogCallback (text collected into log_out).
+static int g_progressCalls = 0, g_progressLast = 0, g_progressTotal = 0, g_progressMonotone = 1;
+static std::string g_logText;
+static void countingProgress(int cur, int total)
+{
+    if (cur < g_progressLast) g_progressMonotone = 0;
+    g_progressCalls++; g_progressLast = cur; g_progressTotal = total;
+}
+static void collectingLog(const char *str) { g_logText += str; }
+
+int rtbh_script_run_ex(int preset, int algorithm, int segments, int width, int height, int samples, uint64_t seed, int device,
+                       int n_devices, const char *stl_path, float *rgb_out, int *exec_ms, rtb_stats *stats, int progress_out[4],
+                       char *log_out, int log_cap)
+{
+    if (preset < 1 || preset > 5) return -1;
+    CudaRenderer &r = CudaRenderer::instance();
+    r.configure(width, height, samples, device, seed);
+    r.setDevices(n_devices);
+    r.setLog(collectingLog);
+    g_progressCalls = 0; g_progressLast = 0; g_progressTotal = 0; g_progressMonotone = 1;
+    g_logText.clear();
+    Script script = *scripts[preset - 1];
+    script.tunnelSegments = segments;
+    script.samples = samples;
+    if (stl_path) script.stlPath = stl_path;
+    int prep = 0, exec = 0;
+    script.Run(CudaRenderer::Render, algorithm, collectingLog, countingProgress, prep, exec);
+    r.setDevices(1);
+    r.setLog(nullptr);
+    if (exec_ms) *exec_ms = exec;
+    if (progress_out) { progress_out[0] = g_progressCalls; progress_out[1] = g_progressLast; progress_out[2] = g_progressTotal; progress_out[3] = g_progressMonotone; }
+    if (log_out && log_cap > 0) { strncpy(log_out, g_logText.c_str(), (size_t)log_cap - 1); log_out[log_cap - 1] = 0; }
     if (exec < 0) return exec;
     if (rgb_out) memcpy(rgb_out, r.image().data(), r.image().size() * sizeof(float));
     if (stats) *stats = r.stats();
