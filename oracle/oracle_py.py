@@ -47,7 +47,7 @@ _loaded = {}
 
 
 def stl_fixture():
-    return os.path.join(os.path.dirname(HERE), "tests", "golden", "ball_fixture.stl")
+    return os.path.join(os.path.dirname(HERE), "win32-ray-tracing-demo_b200", "assets", "ball.stl")  # input data of preset 3 (the package's asset)
 
 
 def available(which):

@@ -5,7 +5,7 @@
 // citing the reference file:line it follows.  Only tests/, __graft_entry__.smoke() and bench.py's
 // cpu_baseline / --impl reference legs may load it; the product (CUDA) path never does.
 //
-// PINNING: tests/test_oracle_vs_ref.py runs identical jobs through this restatement and through
+// PINNING: tests/test_oracle.py runs identical jobs through this restatement and through
 // oracle/_ref/libref.so (the unmodified reference sources compiled headless by build_ref.sh) and
 // demands bit-equality of triangle streams, accelerator structure hashes, per-primary-ray hit ids,
 // distances and traversal sequences, Whitted images and erand48 Monte-Carlo images.  Where the

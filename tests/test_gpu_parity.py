@@ -466,6 +466,40 @@ def test_upload_rejects_bad_scenes(ctx):
     f, keep = corrupted("tri_material", nt, C.c_int32, lambda a: a.__setitem__(0, 99))
     with pytest.raises(rtb200.RtbError):
         ctx.upload(f)
+    # grid directories: word ranks must equal the running popcount of the occupancy bits, list starts must ascend
+    g = PresetScene(5, "rgrid", 8)
+    gf = g.flat.contents
+
+    def grid_corrupted(field, n, ctype, mutate):
+        f = rtb200.FlatScene.from_buffer_copy(gf)
+        arr = (ctype * n)()
+        C.memmove(arr, getattr(gf, field), C.sizeof(arr))
+        mutate(arr)
+        setattr(f, field, C.cast(arr, type(getattr(f, field))))
+        return f, arr
+
+    nw, nc = gf.n_cellwords, gf.n_cells_used
+
+    def bad_rank(words):
+        w = next(i for i in range(nw) if words[i].bits) + 1
+        words[w].rank += 3
+
+    def extra_bit(words):  # one more occupied cell than cell_start has lists for
+        w = next(i for i in range(nw) if words[i].bits != 0xffffffff)
+        words[w].bits |= (~words[w].bits) & (words[w].bits + 1)
+
+    for mutate in (bad_rank, extra_bit):
+        f, keep = grid_corrupted("grid_words", nw, rtb200.CellWord, mutate)
+        with pytest.raises(rtb200.RtbError):
+            ctx.upload(f)
+    f, keep = grid_corrupted("grid_cell_start", nc + 1, C.c_uint32, lambda a: a.__setitem__(nc // 2, a[nc // 2 + 1] + 1))  # not ascending
+    with pytest.raises(rtb200.RtbError):
+        ctx.upload(f)
+    f, keep = grid_corrupted("grid_cell_start", nc + 1, C.c_uint32, lambda a: a.__setitem__(nc, a[nc] + 5))  # past the reference array
+    with pytest.raises(rtb200.RtbError):
+        ctx.upload(f)
+    okg = ctx.upload(g.flat)
+    okg.close(); g.close()
     dev = ctx.upload(s.flat)
     with pytest.raises(rtb200.RtbError):
         dev.render(s.camera, s.setting, rtb200.make_frame(0, 10))

@@ -223,7 +223,7 @@ def host_lib():
 
 
 def stl_fixture():
-    return os.path.join(ROOT, "tests", "golden", "ball_fixture.stl")
+    return os.path.join(PKG, "assets", "ball.stl")  # the 528-triangle mesh of preset 3 (reference Scripts.cpp:113-168 reads ball.stl)
 
 
 def _alg(a):

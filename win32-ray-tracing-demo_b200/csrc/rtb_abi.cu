@@ -725,10 +725,25 @@ extern "C" int rtb_scene_upload(rtb_ctx *ctx, const rtb_flat_scene *f, rtb_scene
                 (f->n_cell_refs > 0 && !f->grid_cell_tris))
                 return bail(fail(ctx, RTB_ERR_INVALID, "rtb_scene_upload: inconsistent grid directory"));
             checks.run([f]() {
-                uint32_t maxStart = 0;
-                for (int64_t i = 0; i <= f->n_cells_used; i++) maxStart = f->grid_cell_start[i] > maxStart ? f->grid_cell_start[i] : maxStart;
-                const bool bad = f->n_cells_used < 0 || (int64_t)maxStart > f->n_cell_refs;
-                return std::make_pair(bad ? (int)RTB_ERR_INVALID : (int)RTB_OK, "rtb_scene_upload: grid cell list out of range");
+                // the directory the walks index with: every word's rank is the number of occupied cells before it, the
+                // occupied cells number n_cells_used, and the list starts ascend from 0 to n_cell_refs (no empty list:
+                // the pair scan needs at least one entry)
+                if (f->n_cells_used < 0) return std::make_pair((int)RTB_ERR_INVALID, "rtb_scene_upload: negative cell count");
+                uint64_t running = 0;
+                bool bad = false;
+                for (int64_t w = 0; w < f->n_cellwords; w++)
+                {
+                    bad |= f->grid_words[w].rank != running;
+                    running += (uint64_t)__builtin_popcount(f->grid_words[w].bits);
+                }
+                if (bad || running != (uint64_t)f->n_cells_used)
+                    return std::make_pair((int)RTB_ERR_INVALID, "rtb_scene_upload: grid word ranks do not match the occupancy bits");
+                const int64_t cells = (int64_t)f->grid_dims[0] * f->grid_dims[1] * f->grid_dims[2];
+                if (f->n_cellwords > 0 && (cells & 31) != 0 && (f->grid_words[f->n_cellwords - 1].bits >> (cells & 31)) != 0)
+                    return std::make_pair((int)RTB_ERR_INVALID, "rtb_scene_upload: occupancy bits beyond the last cell");
+                bool order = f->grid_cell_start[0] == 0 && (int64_t)f->grid_cell_start[f->n_cells_used] == f->n_cell_refs;
+                for (int64_t i = 0; i < f->n_cells_used; i++) order &= f->grid_cell_start[i] < f->grid_cell_start[i + 1];
+                return std::make_pair(order ? (int)RTB_OK : (int)RTB_ERR_INVALID, "rtb_scene_upload: grid cell list starts are not strictly ascending from 0 to n_cell_refs");
             });
             checks.run([f]() {
                 uint32_t maxRef = 0; // branch-free maximum: the compiler vectorises it (up to 6.4 M references)
@@ -830,7 +845,10 @@ extern "C" int rtb_scene_upload(rtb_ctx *ctx, const rtb_flat_scene *f, rtb_scene
     checks.join();
     if (checks.code != RTB_OK) return bail(fail(ctx, checks.code, checks.msg));
     laps.lap("checks joined");
-    CUDA_TRY(ctx, cudaEventRecord(s->ready, ctx->stream));
+    {
+        const cudaError_t e = cudaEventRecord(s->ready, ctx->stream);
+        if (e != cudaSuccess) return bail(fail(ctx, RTB_ERR_CUDA, std::string("cudaEventRecord(ready): ") + cudaGetErrorString(e)));
+    }
     s->signature = sceneSignature(f);
     laps.lap("signature");
     s->long_lists = s->has_tunnel && f->accel == RTB_ACCEL_REGULAR_GRID && s->grid_cells_used > 0 && s->grid_refs >= 16 * s->grid_cells_used;

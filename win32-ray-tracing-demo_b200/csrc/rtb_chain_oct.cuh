@@ -33,7 +33,11 @@ enum { OCT_NEXT = 4 };
 #endif
 
 // Eight warps per tile: group g of warp (w & 7) renders pixel (w & 7) * 4 + g of the tile.
-template <class Probe, bool GRID, int FOLD>
+// PRE: the list rounds go through the packed rejection test, eight PAIRS per round.  Measured on the 1/8 shards of the 4K
+// frame (one B200, slowest shard, kernel ms): k-d median 2.66 -> 2.14 (10.9 leaves per ray: the rounds are a large share
+// of the chain), k-d SAH 1.21 -> 1.37 (4 leaves per ray; a round became two dependent phases, test + exact test, and the
+// tier is bound by the chain's latency, not by issue slots).  So: median trees only (rtb_abi.cu: launchRender).
+template <class Probe, bool GRID, int FOLD, bool PRE>
 __global__ void __launch_bounds__(RTB_CTA_THREADS, RTB_OCT_MIN_CTAS)
 k_whitted_chain_oct(const __grid_constant__ DScene S, const __grid_constant__ FrameParams F, float *__restrict__ out,
                     Counters *__restrict__ counters)
@@ -68,9 +72,10 @@ k_whitted_chain_oct(const __grid_constant__ DScene S, const __grid_constant__ Fr
     float cd = 0;
     V3 cp = zero;
     bool px = false, py = false, pz = false;
-    // list
-    unsigned int li = 0, lend = 0;
+    // list [li, lend) of the reference array; lp = next pair of the pair stream; constants of the rejection test
+    unsigned int li = 0, lend = 0, lp = 0;
     float lo = 0, hi = 0, minD = FLT_MAX;
+    float dmx = 0, Lp = rtb_pre::lowBound(-FLT_MAX), Hp = rtb_pre::highBound(FLT_MAX, FLT_MAX);
     int hitTri = -1;
     bool tunnelHit = false;
 
@@ -79,6 +84,7 @@ k_whitted_chain_oct(const __grid_constant__ DScene S, const __grid_constant__ Fr
         tunnelHit = false;
         hitTri = -1;
         minD = FLT_MAX;
+        dmx = rtb_pre::dirMax(r.d.x, r.d.y, r.d.z);
         if (GRID)
         {
             if (r.o.x < S.g_origin.x || r.o.x > S.g_far.x || r.o.y < S.g_origin.y || r.o.y > S.g_far.y ||
@@ -183,8 +189,10 @@ k_whitted_chain_oct(const __grid_constant__ DScene S, const __grid_constant__ Fr
                         const unsigned int rk = wd.y + __popc(wd.x & (bit - 1));
                         li = __ldg(S.g_start + rk);
                         lend = __ldg(S.g_start + rk + 1);
-                        minD = FLT_MAX; hitTri = -1;
-                        st = SM_LEAF;
+                        minD = FLT_MAX; hitTri = -1; lp = li >> 1;
+                        Hp = rtb_pre::highBound(FLT_MAX, FLT_MAX);
+                        if (li == lend) gridAdvance(); // cannot happen with a well-formed directory
+                        else st = SM_LEAF;
                     }
                     else gridAdvance();
                 }
@@ -197,7 +205,8 @@ k_whitted_chain_oct(const __grid_constant__ DScene S, const __grid_constant__ Fr
                         li = nd.x;
                         lend = nd.x + (nd.y >> 2);
                         lo = enT - 0.001f; hi = exT + 0.001f;
-                        minD = FLT_MAX; hitTri = -1;
+                        Lp = rtb_pre::lowBound(lo); Hp = rtb_pre::highBound(hi, FLT_MAX);
+                        minD = FLT_MAX; hitTri = -1; lp = li >> 1;
                         if (li == lend) kdPop();
                         else st = SM_LEAF;
                     }
@@ -232,7 +241,64 @@ k_whitted_chain_oct(const __grid_constant__ DScene S, const __grid_constant__ Fr
                 }
             }
         }
-        if ((leafMask >> lane) & 1u)
+        if (PRE && ((leafMask >> lane) & 1u))
+        { // one round: eight PAIRS of the list, one per lane (the group was in LEAF at the top of this iteration), through the
+          // packed rejection test; the entries it cannot reject take the exact test, the group's lanes side by side (see
+          // nearestInList<.., WIDE>: same scheme with 8 lanes instead of 32)
+            const unsigned int gmask = 0xffu << (g * 8u); // the group's lanes share one state: they are all here
+            const unsigned int pEnd = (lend + 1u) >> 1;
+            const unsigned int p = lp + sub, j0 = 2u * p, j1 = j0 + 1u;
+            bool c0 = false, c1 = false;
+            if (p < pEnd)
+            {
+                const rtb_pre::PreTri2 P = loadPreTri2(S.pre2, p);
+                const bool in0 = j0 >= li, in1 = j1 < lend;
+                if (in0) pr.tri();
+                if (in1) pr.tri();
+                bool r0, r1;
+                rtb_pre::sureReject2<true>(P, r.o.x, r.o.y, r.o.z, r.d.x, r.d.y, r.d.z, dmx, Lp, Hp, r0, r1);
+                c0 = in0 && !r0; c1 = in1 && !r1;
+            }
+            if (__ballot_sync(gmask, c0 || c1))
+            {
+                const uint32_t *refs = GRID ? S.g_tris : S.kd_tris;
+                unsigned int key = 0xffffffffu, idx = 0;
+                if (c0)
+                {
+                    const uint32_t i0 = __ldg(refs + j0);
+                    const TriData T = loadTri(S.tri, i0);
+                    float t;
+                    bool ok = triIntersectT<true>(T, r, t);
+                    if (!GRID) ok = ok && (t >= lo && t <= hi);
+                    if (ok && t < FLT_MAX) { key = __float_as_uint(t); idx = i0; } // positive floats order like their bit patterns
+                }
+                if (c1)
+                {
+                    const uint32_t i1 = __ldg(refs + j1);
+                    const TriData T = loadTri(S.tri, i1);
+                    float t;
+                    bool ok = triIntersectT<true>(T, r, t);
+                    if (!GRID) ok = ok && (t >= lo && t <= hi);
+                    if (ok && t < FLT_MAX && __float_as_uint(t) < key) { key = __float_as_uint(t); idx = i1; } // strict <: j0 keeps a tie
+                }
+                unsigned int best = key;
+                best = min(best, __shfl_xor_sync(gmask, best, 1));
+                best = min(best, __shfl_xor_sync(gmask, best, 2));
+                best = min(best, __shfl_xor_sync(gmask, best, 4));
+                const unsigned int eq = (__ballot_sync(gmask, key != 0xffffffffu && key == best) >> (g * 8u)) & 0xffu;
+                const unsigned int winner = eq ? (unsigned int)(__ffs(eq) - 1) : 0u; // earliest list position among equal distances
+                const unsigned int idxW = __shfl_sync(gmask, idx, g * 8u + winner);
+                if (eq && __uint_as_float(best) < minD)
+                { // strict <: an equal distance in a later round does not replace the earlier one
+                    minD = __uint_as_float(best);
+                    hitTri = (int)idxW;
+                    Hp = rtb_pre::highBound(GRID ? FLT_MAX : hi, minD);
+                }
+            }
+            lp += 8;
+            if (lp >= pEnd) listDone();
+        }
+        if (!PRE && ((leafMask >> lane) & 1u))
         { // one round: eight triangles of the list, one per lane (the group was in LEAF at the top of this iteration)
             const unsigned int i = li + sub;
             float t = FLT_MAX;

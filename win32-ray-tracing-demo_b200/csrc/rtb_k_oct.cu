@@ -6,7 +6,9 @@ namespace rtb {
 
 template <class Probe, bool GRID, int FOLD> static void go(const Launch &L)
 {
-    k_whitted_chain_oct<Probe, GRID, FOLD><<<L.grid, RTB_CTA_THREADS, 0, L.stream>>>(*L.S, *L.F, L.out, L.counters);
+    // packed rejection test in the list rounds: k-d median trees (many short leaves per ray); see rtb_chain_oct.cuh
+    if (!GRID && L.S->accel == RTB_ACCEL_KD_MEDIAN) k_whitted_chain_oct<Probe, GRID, FOLD, true><<<L.grid, RTB_CTA_THREADS, 0, L.stream>>>(*L.S, *L.F, L.out, L.counters);
+    else k_whitted_chain_oct<Probe, GRID, FOLD, false><<<L.grid, RTB_CTA_THREADS, 0, L.stream>>>(*L.S, *L.F, L.out, L.counters);
 }
 template <class Probe, bool GRID> static void byFold(const Launch &L)
 {
