@@ -105,6 +105,20 @@ build_variant 1 "$OUT/libref.so"
 build_variant 0 "$OUT/libref_timing.so"
 echo "built $OUT/libref.so $OUT/libref_timing.so"
 
+# ---- Route A of INTEGRATION.md, compiled: the reference's own objects (hooks off) + ref/route_a.cpp (SceneFlattener over the
+# reference's classes, CudaRender as the RenderProc) + the product's librtb200.so -> libroute_a.so (tests/test_route_a.py)
+RTB_PKG="$(cd "$HERE/.." && pwd)/win32-ray-tracing-demo_b200"
+if [ -f "$RTB_PKG/librtb200.so" ]; then
+    g++ $CXXFLAGS -DREF_HOOKS=0 -c "$HERE/ref/route_a.cpp" -o "$TMP/obj0/route_a.o"
+    robjs=()
+    for f in $SOURCES; do robjs+=("$TMP/obj0/${f%.cpp}.o"); done
+    g++ -shared -fopenmp -o "$OUT/libroute_a.so" "${robjs[@]}" "$TMP/obj0/ref_utils.o" "$TMP/obj0/route_a.o" \
+        -L"$RTB_PKG" -lrtb200 -Wl,-rpath,'$ORIGIN/../../win32-ray-tracing-demo_b200'
+    echo "built $OUT/libroute_a.so"
+else
+    echo "build_ref.sh: $RTB_PKG/librtb200.so not built yet -- libroute_a.so skipped" >&2
+fi
+
 # ---- PerformanceTest (src/PerformanceTest): its own sources + ref/ref_pt_driver.cpp -> libref_pt.so ----------
 # main.cpp (console front end) and Utils.cpp (Win32) are replaced by the driver; two mechanical patches, both the
 # MSVC-dialect kind already applied to RayTracingOpt above (P1, P3), none touching arithmetic.

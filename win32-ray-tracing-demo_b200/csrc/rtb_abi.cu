@@ -21,7 +21,7 @@
 #define RTB_SPLIT_MAX_TILES 131072 // shards up to 4.2 Mpixel walk their latency-critical tiles with 4 warps each
 #endif
 #ifndef RTB_HEAVY_BUCKETS_SMALL
-#define RTB_HEAVY_BUCKETS_SMALL 6   // the latency-critical set itself stays the same (widening it to 8 / 12 / 16
+#define RTB_HEAVY_BUCKETS_SMALL 4   // quarter-octaves below the heaviest tile: 4 / 6 / 10 -> slowest 1/8 SAH shard 1.18 / 1.24 / 1.24 ms
 #endif
 #ifndef RTB_HEAVY_FRACTION_SMALL
 #define RTB_HEAVY_FRACTION_SMALL 128 //    quarter-octaves and 1/32 .. 1/8 of the shard measured slower)
@@ -53,7 +53,11 @@ static int wideCount(int n_tiles, bool long_lists)
     static const int cap = (int)tunable("RTB_WIDE_CAP", -1), fraction = (int)tunable("RTB_WIDE_FRACTION", 32); // tuning overrides
     if (cap >= 0) return n_tiles / (fraction < 1 ? 1 : fraction) < cap ? n_tiles / (fraction < 1 ? 1 : fraction) : cap;
     if (n_tiles <= RTB_SMALL_FRAME_TILES) return n_tiles / (long_lists ? 16 : 32);
-    if (long_lists) return n_tiles <= RTB_SPLIT_MAX_TILES ? (n_tiles / 32 < 1184 ? n_tiles / 32 : 1184) : 148;
+    // shards of a big frame: two tiles per SM.  (Round 1 took up to 1,184 here, tuned on row shards; with column-block
+    // shards every rank holds 1 / N of the vanishing-point tiles and the tier's own instructions -- ~4.7 M per tile --
+    // become the shard's critical path: slowest 1/8 shard of the 4K frame, kernel ms at 148 / 296 / 592 / 1,184 / 2,368
+    // tiles: 3.20 / 2.70 / 2.79 / 3.50 / 4.66, profiles/r02_sweep_tiers.log)
+    if (long_lists) return n_tiles <= RTB_SPLIT_MAX_TILES ? (n_tiles / 32 < 296 ? n_tiles / 32 : 296) : 148;
     return 0;
 }
 static int heavyBucketsSmall() { static const int v = (int)tunable("RTB_HEAVY_BUCKETS_SMALL", RTB_HEAVY_BUCKETS_SMALL); return v; }
