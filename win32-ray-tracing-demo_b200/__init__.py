@@ -14,7 +14,7 @@ import numpy as np
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
-CUDA_LIB = os.path.join(PKG, "librtb200.so")
+CUDA_LIB = os.path.join(PKG, os.environ.get("RTB_CUDA_LIB_NAME", "librtb200.so"))  # RTB_CUDA_LIB_NAME: an experiment build (tools/)
 HOST_LIB = os.path.join(PKG, "librtb200_host.so")
 
 ALGORITHMS = {"linear": 0, "rgrid": 1, "fgrid": 2, "kd": 3, "sah": 4, "convex": 5, "convexsimple": 6}

@@ -13,7 +13,7 @@ import subprocess
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
-CUDA_LIB = os.path.join(PKG, "librtb200.so")
+CUDA_LIB = os.path.join(PKG, os.environ.get("RTB_CUDA_LIB_NAME", "librtb200.so"))  # RTB_CUDA_LIB_NAME: experiment builds next to the product
 HOST_LIB = os.path.join(PKG, "librtb200_host.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -45,7 +45,7 @@ def build_cuda(force=False, verbose=False):
     if not force and _newer(CUDA_LIB, deps):
         return CUDA_LIB
     extra = os.environ.get("RTB_NVCC_EXTRA", "").split()  # tuning experiments, e.g. -DRTB_CHAIN_MIN_CTAS=6
-    objdir = os.path.join(PKG, "build")
+    objdir = os.path.join(PKG, "build" + ("_" + os.environ["RTB_CUDA_LIB_NAME"] if "RTB_CUDA_LIB_NAME" in os.environ else ""))
     os.makedirs(objdir, exist_ok=True)
     headers_t = max(os.path.getmtime(d) for d in deps[len(units):])
 

@@ -60,7 +60,15 @@ static int wideCount(int n_tiles, bool long_lists)
     if (long_lists) return n_tiles <= RTB_SPLIT_MAX_TILES ? (n_tiles / 32 < 296 ? n_tiles / 32 : 296) : 148;
     return 0;
 }
-static int heavyBucketsSmall() { static const int v = (int)tunable("RTB_HEAVY_BUCKETS_SMALL", RTB_HEAVY_BUCKETS_SMALL); return v; }
+// ... of a small shard: how far below the heaviest tile the latency-critical set reaches.  SAH trees: 4 quarter-octaves (2x);
+// k-d median trees have a flatter cost distribution and want 6 (2.8x) -- slowest 1/8 shard of the 4K frame with 4 / 6:
+// SAH 1.18 / 1.24 ms, median 3.24 / 2.14 ms (profiles/r02_sweep_tiers.log)
+static int heavyBucketsSmall(int accel)
+{
+    static const int forced = (int)tunable("RTB_HEAVY_BUCKETS_SMALL", -1);
+    if (forced >= 0) return forced;
+    return accel == RTB_ACCEL_KD_MEDIAN ? 6 : RTB_HEAVY_BUCKETS_SMALL;
+}
 static int heavyFractionSmall() { static const int v = (int)tunable("RTB_HEAVY_FRACTION_SMALL", RTB_HEAVY_FRACTION_SMALL); return v < 1 ? 1 : v; }
 // Size limit of the resumable-walk tier.  Small frames have none: there the warp-per-pixel tier takes the heavy
 // tiles and a third kernel in between measured slower (k-d median 400x300: 1.4 ms without, 2.2 ms with).
@@ -1064,7 +1072,7 @@ static int launchRender(rtb_ctx *ctx, const rtb_scene *scene, FrameParams &F, bo
             { // eight lanes per pixel, eight warps per tile
                 H.skip_heavy = 0; H.after_wide = 0; H.split4 = 0;
                 H.item_base = F.n_wide; H.item_end = F.n_wide + (unsigned int)heavyLimit(F.n_tiles);
-                const dim3 ogrid(((unsigned int)heavyLimit(F.n_tiles) * 8u + warpsPerCta - 1) / warpsPerCta);
+                const dim3 ogrid(((unsigned int)heavyLimit(F.n_tiles) * (unsigned int)octWarpsPerTile(accel, F.n_tiles) + warpsPerCta - 1) / warpsPerCta);
                 launchChainOct(L(H, ogrid, ctx->aux), grid_accel);
                 n_kernels++;
             }
@@ -1203,7 +1211,7 @@ static int renderLaunch(rtb_ctx *ctx, const rtb_scene *scene, FrameParams &F, co
         k_cost_histogram<<<blocks, 256, 0, stream>>>(ctx->d_cost, F.n_tiles, ctx->d_hist);
         const bool smallShard = F.n_tiles <= splitMaxTiles();
         k_cost_offsets<<<1, RTB_COST_BUCKETS, 0, stream>>>(ctx->d_hist, ctx->d_cursor, ctx->d_heavy, F.n_tiles,
-                                             smallShard ? heavyBucketsSmall() : RTB_HEAVY_BUCKETS,
+                                             smallShard ? heavyBucketsSmall(scene->d.accel) : RTB_HEAVY_BUCKETS,
                                              heavyLimit(F.n_tiles), wideCount(F.n_tiles, scene->long_lists), floorDelta);
         k_cost_scatter<<<blocks, 256, 0, stream>>>(ctx->d_cost, F.n_tiles, ctx->d_cursor, ctx->d_order, ctx->d_heavy);
         CUDA_TRY(ctx, cudaGetLastError());

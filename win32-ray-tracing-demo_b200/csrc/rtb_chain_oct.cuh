@@ -31,21 +31,29 @@ enum { OCT_NEXT = 4 };
 #ifndef RTB_OCT_MIN_CTAS
 #define RTB_OCT_MIN_CTAS 5
 #endif
+// LANES per pixel group (template parameter): 8 = four pixels per warp, eight warps per tile; 16 = two pixels per warp,
+// sixteen warps per tile.  The tier is bound by the latency of its chains: fewer groups per warp wait less for each other's
+// phases.  Slowest 1/8 shard of the 4K frame, kernel ms with 4 / 8 / 16 lanes: SAH 1.68 / 1.17 / 1.09, preset 4 SAH
+// - / 1.22 / 1.16, k-d median 3.57 / 2.16 / 2.51 (its many short leaves keep 8 lanes busy; 16 double the instructions for
+// nothing) -- profiles/r02_sweep_tiers.log.  So: 16 for SAH trees, 8 (with PRE) for median trees.
+#define RTB_OCT_GROUPS (32 / LANES)          // pixel groups per warp
+#define RTB_OCT_WARPS_PER_TILE LANES         // 32 pixels per tile / groups per warp
+#define RTB_OCT_GROUP_BITS ((LANES == 32) ? 0xffffffffu : ((1u << LANES) - 1u))
 
 // Eight warps per tile: group g of warp (w & 7) renders pixel (w & 7) * 4 + g of the tile.
 // PRE: the list rounds go through the packed rejection test, eight PAIRS per round.  Measured on the 1/8 shards of the 4K
 // frame (one B200, slowest shard, kernel ms): k-d median 2.66 -> 2.14 (10.9 leaves per ray: the rounds are a large share
 // of the chain), k-d SAH 1.21 -> 1.37 (4 leaves per ray; a round became two dependent phases, test + exact test, and the
 // tier is bound by the chain's latency, not by issue slots).  So: median trees only (rtb_abi.cu: launchRender).
-template <class Probe, bool GRID, int FOLD, bool PRE>
+template <class Probe, bool GRID, int FOLD, bool PRE, int LANES>
 __global__ void __launch_bounds__(RTB_CTA_THREADS, RTB_OCT_MIN_CTAS)
 k_whitted_chain_oct(const __grid_constant__ DScene S, const __grid_constant__ FrameParams F, float *__restrict__ out,
                     Counters *__restrict__ counters)
 {
     const long long t_start = clock64();
     const unsigned int w = blockIdx.x * (RTB_CTA_THREADS / 32) + (threadIdx.x >> 5);
-    const unsigned int lane = threadIdx.x & 31u, g = lane >> 3, sub = lane & 7u;
-    const unsigned int item = (w >> 3) + F.item_base;
+    const unsigned int lane = threadIdx.x & 31u, g = lane / LANES, sub = lane % LANES;
+    const unsigned int item = (w / RTB_OCT_WARPS_PER_TILE) + F.item_base;
     if (item >= F.item_end || item >= (unsigned int)F.n_tiles || item >= heavyCount(F)) return; // warp-uniform
     const unsigned int tile = F.order ? __ldg(F.order + item) : item;
     const int ty = tile / F.tiles_x, tx = tile - ty * F.tiles_x;
@@ -161,7 +169,7 @@ k_whitted_chain_oct(const __grid_constant__ DScene S, const __grid_constant__ Fr
             if (k >= 1) st = SM_DONE;
             else
             {
-                const unsigned int p = (w & 7u) * 4u + g;
+                const unsigned int p = (w % RTB_OCT_WARPS_PER_TILE) * RTB_OCT_GROUPS + g;
                 lr = ty * RTB_TILE_H + (int)(p >> 3);
                 if (localToGlobal(F, tx * RTB_TILE_W + (int)(p & 7u), lr, x, y))
                 {
@@ -245,7 +253,7 @@ k_whitted_chain_oct(const __grid_constant__ DScene S, const __grid_constant__ Fr
         { // one round: eight PAIRS of the list, one per lane (the group was in LEAF at the top of this iteration), through the
           // packed rejection test; the entries it cannot reject take the exact test, the group's lanes side by side (see
           // nearestInList<.., WIDE>: same scheme with 8 lanes instead of 32)
-            const unsigned int gmask = 0xffu << (g * 8u); // the group's lanes share one state: they are all here
+            const unsigned int gmask = RTB_OCT_GROUP_BITS << (g * LANES); // the group's lanes share one state: they are all here
             const unsigned int pEnd = (lend + 1u) >> 1;
             const unsigned int p = lp + sub, j0 = 2u * p, j1 = j0 + 1u;
             bool c0 = false, c1 = false;
@@ -284,10 +292,11 @@ k_whitted_chain_oct(const __grid_constant__ DScene S, const __grid_constant__ Fr
                 unsigned int best = key;
                 best = min(best, __shfl_xor_sync(gmask, best, 1));
                 best = min(best, __shfl_xor_sync(gmask, best, 2));
-                best = min(best, __shfl_xor_sync(gmask, best, 4));
-                const unsigned int eq = (__ballot_sync(gmask, key != 0xffffffffu && key == best) >> (g * 8u)) & 0xffu;
+                if (LANES >= 8) best = min(best, __shfl_xor_sync(gmask, best, 4));
+                if (LANES >= 16) best = min(best, __shfl_xor_sync(gmask, best, 8));
+                const unsigned int eq = (__ballot_sync(gmask, key != 0xffffffffu && key == best) >> (g * LANES)) & RTB_OCT_GROUP_BITS;
                 const unsigned int winner = eq ? (unsigned int)(__ffs(eq) - 1) : 0u; // earliest list position among equal distances
-                const unsigned int idxW = __shfl_sync(gmask, idx, g * 8u + winner);
+                const unsigned int idxW = __shfl_sync(gmask, idx, g * LANES + winner);
                 if (eq && __uint_as_float(best) < minD)
                 { // strict <: an equal distance in a later round does not replace the earlier one
                     minD = __uint_as_float(best);
@@ -295,7 +304,7 @@ k_whitted_chain_oct(const __grid_constant__ DScene S, const __grid_constant__ Fr
                     Hp = rtb_pre::highBound(GRID ? FLT_MAX : hi, minD);
                 }
             }
-            lp += 8;
+            lp += LANES;
             if (lp >= pEnd) listDone();
         }
         if (!PRE && ((leafMask >> lane) & 1u))
@@ -317,16 +326,17 @@ k_whitted_chain_oct(const __grid_constant__ DScene S, const __grid_constant__ Fr
             unsigned int best = key;
             best = min(best, __shfl_xor_sync(leafMask, best, 1));
             best = min(best, __shfl_xor_sync(leafMask, best, 2));
-            best = min(best, __shfl_xor_sync(leafMask, best, 4));
-            const unsigned int eq = (__ballot_sync(leafMask, ok && key == best) >> (g * 8u)) & 0xffu;
+            if (LANES >= 8) best = min(best, __shfl_xor_sync(leafMask, best, 4));
+            if (LANES >= 16) best = min(best, __shfl_xor_sync(leafMask, best, 8));
+            const unsigned int eq = (__ballot_sync(leafMask, ok && key == best) >> (g * LANES)) & RTB_OCT_GROUP_BITS;
             const unsigned int winner = eq ? (unsigned int)(__ffs(eq) - 1) : 0u; // earliest list position among equal distances
-            const unsigned int idxW = __shfl_sync(leafMask, idx, g * 8u + winner);
+            const unsigned int idxW = __shfl_sync(leafMask, idx, g * LANES + winner);
             if (eq && __uint_as_float(best) < minD)
             { // strict <: an equal distance in a later round does not replace the earlier one
                 minD = __uint_as_float(best);
                 hitTri = (int)idxW;
             }
-            li += 8;
+            li += LANES;
             if (li >= lend) listDone();
         }
         if (st == SM_SHADE)
@@ -388,8 +398,12 @@ k_whitted_chain_oct(const __grid_constant__ DScene S, const __grid_constant__ Fr
         if (nr) atomicAdd(&counters->rays, (unsigned long long)nr);
         if (tris) atomicAdd(&counters->tris, (unsigned long long)tris);
         if (steps) atomicAdd(&counters->steps, (unsigned long long)steps);
-        if ((w & 7u) == 0u) atomicAdd(&counters->tiles, 1ull); // eight warps per tile
+        if ((w % RTB_OCT_WARPS_PER_TILE) == 0u) atomicAdd(&counters->tiles, 1ull); // one of the tile's warps reports it
     }
 }
+
+#undef RTB_OCT_GROUPS
+#undef RTB_OCT_WARPS_PER_TILE
+#undef RTB_OCT_GROUP_BITS
 
 } // namespace rtb

@@ -21,6 +21,7 @@ struct Launch
 void launchChain(const Launch &L);                // k_whitted_chain        (rtb_k_chain.cu)
 void launchChainSm(const Launch &L, bool grid);   // k_whitted_chain_sm     (rtb_k_sm.cu)
 void launchChainOct(const Launch &L, bool grid);  // k_whitted_chain_oct    (rtb_k_oct.cu)
+int octWarpsPerTile(int accel, int n_tiles);                   // warps the 8-lane / 16-lane kernel gives a tile (its grid is sized with this)
 void launchChainWide(const Launch &L);            // k_whitted_chain_wide   (rtb_k_wide.cu)
 void launchTree(const Launch &L);                 // k_whitted_tree         (rtb_k_mc.cu)
 void launchMonteCarlo(const Launch &L);           // k_montecarlo           (rtb_k_mc.cu)
