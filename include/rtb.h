@@ -126,6 +126,12 @@ typedef struct rtb_flat_scene {
                                                        tests them all: 0 .. n_cx_edges - 1)                                   */
     const uint16_t *cx_order;                       /* RTB_ACCEL_CONVEX: [100][360][2*n_cx_edges] triangle order per
                                                        (height, angle) bin (ConvexAcc.cpp:249-270)                           */
+    int32_t grid_build_exact;                       /* device grid build (grid_build_resolution): 1 = a triangle enters a cell only
+                                                       if it passes the reference's exact overlap test Triangle::intersectWithGrid
+                                                       (Triangle.cpp:152-199), the alternative the reference compiles out at
+                                                       Tunnel.cpp:435-445 ("8 times faster" to build without, "20% slower" to
+                                                       traverse); 0 = bounding-box binning as the reference ships               */
+    int32_t pad_;
 } rtb_flat_scene;
 
 /* ---- camera: reference Camera.h:7-23; the derived fields are computed on the host exactly as

@@ -105,6 +105,23 @@ build_variant 1 "$OUT/libref.so"
 build_variant 0 "$OUT/libref_timing.so"
 echo "built $OUT/libref.so $OUT/libref_timing.so"
 
+# ---- libref_sat.so: the reference with its EXACT grid binning switched on (patch P8) -- the checker of the exact-binning
+# option of the product's grid builders.  Tunnel.cpp:435 `#if 0` guards the branch that calls Triangle::intersectWithGrid
+# (Triangle.cpp:152-199); it names a variable `size` that only exists inside the regular-grid block above (lines 377-391), so
+# the branch does not compile as it stands: P8 flips the guard and declares `float size = grid.cellSizeX;` in front of the
+# triangle loop (the regular grid's cells are cubes of that edge; for the flat grid the reference's branch would be wrong,
+# so only regular grids are compared with this build).  Nothing else differs from libref.so.
+expect Tunnel.cpp 435 '#if 0'
+expect Tunnel.cpp 411 '// For each triangle'
+cp "$TMP/Tunnel.cpp" "$TMP/Tunnel.cpp.plain"
+sed -i -e '435s/#if 0/#if 1/' -e '411s/$/ float size = grid.cellSizeX;/' "$TMP/Tunnel.cpp"
+g++ $CXXFLAGS -DREF_HOOKS=1 -c "$TMP/Tunnel.cpp" -o "$TMP/obj1/Tunnel_sat.o"
+mv "$TMP/Tunnel.cpp.plain" "$TMP/Tunnel.cpp"
+sobjs=()
+for f in $SOURCES; do if [ "$f" = Tunnel.cpp ]; then sobjs+=("$TMP/obj1/Tunnel_sat.o"); else sobjs+=("$TMP/obj1/${f%.cpp}.o"); fi; done
+g++ -shared -fopenmp -o "$OUT/libref_sat.so" "${sobjs[@]}" "$TMP/obj1/ref_utils.o" "$TMP/obj1/ref_driver.o"
+echo "built $OUT/libref_sat.so"
+
 # ---- Route A of INTEGRATION.md, compiled: the reference's own objects (hooks off) + ref/route_a.cpp (SceneFlattener over the
 # reference's classes, CudaRender as the RenderProc) + the product's librtb200.so -> libroute_a.so (tests/test_route_a.py)
 RTB_PKG="$(cd "$HERE/.." && pwd)/win32-ray-tracing-demo_b200"

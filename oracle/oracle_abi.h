@@ -93,6 +93,11 @@ typedef struct oracle_job {
                             no per-sample statistics): per pixel, framebuffer order, the sum over the samples of the
                             radiance (R, G, B) and of its square -- the per-pixel variance the statistical parity
                             criteria of SURVEY.md 8(d) need                                                        */
+    int32_t grid_exact;  /* input, grids: 1 = bin triangles with the exact overlap test Triangle::intersectWithGrid
+                            (Triangle.cpp:152-199), the branch the reference compiles out at Tunnel.cpp:435-445.
+                            librt_oracle.so honours it; of the reference builds only libref_sat.so (that branch enabled
+                            by build_ref.sh, patch P8) bins this way, whatever the field says                      */
+    int32_t pad2_;
 } oracle_job;
 
 int rt_oracle_run(oracle_job *job);

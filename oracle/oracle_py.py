@@ -34,6 +34,7 @@ class OracleJob(C.Structure):
         ("render_ms", C.c_double), ("prepare_ms", C.c_double),
         ("stats", C.c_int64 * 16), ("struct_hash", C.c_uint64), ("tri_hash", C.c_uint64),
         ("render_ms_all", C.c_void_p), ("rgb8", C.c_void_p), ("moments", C.c_void_p),
+        ("grid_exact", C.c_int32), ("pad2_", C.c_int32),
     ]
 
 
@@ -42,6 +43,8 @@ _LIBS = {
     "ref": (os.path.join(HERE, "_ref", "libref.so"), "ref_run"),
     "ref_timing": (os.path.join(HERE, "_ref", "libref_timing.so"), "ref_run"),
     "ref_pt": (os.path.join(HERE, "_ref", "libref_pt.so"), "ref_pt_bounce"),
+    # the reference with the exact grid binning it carries compiled out (Tunnel.cpp:435-445) switched on: build_ref.sh patch P8
+    "ref_sat": (os.path.join(HERE, "_ref", "libref_sat.so"), "ref_run"),
 }
 _loaded = {}
 
@@ -73,7 +76,7 @@ def _fn(which):
 
 def run(which, preset, algorithm="linear", segments=150, width=400, height=300, samples=1,
         setting="preset", threads=0, rng=0, seed=0, image=False, hits=False, seq=False, seq_cap=0,
-        triangles=False, repeat=0, stl_path=None, moments=False):
+        triangles=False, repeat=0, stl_path=None, moments=False, grid_exact=False):
     """Run one job; returns a dict of numpy arrays / scalars."""
     job = OracleJob()
     job.preset = preset
@@ -82,6 +85,7 @@ def run(which, preset, algorithm="linear", segments=150, width=400, height=300, 
     job.setting = SETTINGS[setting] if isinstance(setting, str) else int(setting)
     job.threads, job.rng, job.seed, job.repeat = threads, rng, seed, repeat
     job.stl_path = (stl_path or stl_fixture()).encode()
+    job.grid_exact = 1 if grid_exact else 0  # librt_oracle.so; libref_sat.so bins exactly whatever this says
     n = width * height
     keep = {}
 

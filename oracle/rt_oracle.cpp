@@ -319,6 +319,7 @@ struct KdNodeO { int axis; float split; int left, right; std::vector<int> list; 
 struct TunnelO
 {
     bool ptBuilders = false; // PerformanceTest's KdTreeAcc builder (event-sweep SAH + automatic termination)
+    bool exactGrid = false;  // bin with Triangle::intersectWithGrid (Tunnel.cpp:435-445, the compiled-out branch)
     int algorithm;
     std::vector<Tri> tris; // surface[seg][j] flattened in (seg, j) order
     // grid (Tunnel.h:51-67)
@@ -482,6 +483,52 @@ void tunnelBounds(const TunnelO &T, V3 &mn, V3 &mx)
     }
 }
 
+// Triangle::intersectWithGrid and its helpers, Triangle.cpp:123-199: separating-axis test of a triangle against one grid
+// cell (three box axes, the triangle normal, nine edge cross products).  Compiled out at its call site in the reference
+// (Tunnel.cpp:435-445); restated here for the exact-binning OPTION (oracle_job.grid_exact), checked against the reference
+// rebuilt with that branch enabled (oracle/_ref/libref_sat.so).
+inline float satMin(const V3 *pts, int n, V3 axis)
+{ // Triangle.cpp:124-132
+    float m = FLT_MAX;
+    for (int i = 0; i < n; i++) m = std::min(m, axis.x * pts[i].x + axis.y * pts[i].y + axis.z * pts[i].z);
+    return m;
+}
+inline float satMax(const V3 *pts, int n, V3 axis)
+{ // Triangle.cpp:134-142
+    float m = -FLT_MAX;
+    for (int i = 0; i < n; i++) m = std::max(m, axis.x * pts[i].x + axis.y * pts[i].y + axis.z * pts[i].z);
+    return m;
+}
+inline bool satOnAxis(const V3 *g, const V3 *t, V3 axis)
+{ // Triangle.cpp:144-149
+    if (satMin(g, 8, axis) > satMax(t, 3, axis)) return false;
+    if (satMax(g, 8, axis) < satMin(t, 3, axis)) return false;
+    return true;
+}
+inline V3 satCross(V3 a, V3 b) { return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); } // Vector.cpp:79-82
+bool triIntersectsCell(const Tri &T, V3 pos, V3 size)
+{ // Triangle.cpp:152-199
+    const V3 g[8] = {v3(pos.x + 0, pos.y + 0, pos.z + 0), v3(pos.x + 0, pos.y + 0, pos.z + size.z),
+                     v3(pos.x + 0, pos.y + size.y, pos.z + 0), v3(pos.x + 0, pos.y + size.y, pos.z + size.z),
+                     v3(pos.x + size.x, pos.y + 0, pos.z + 0), v3(pos.x + size.x, pos.y + 0, pos.z + size.z),
+                     v3(pos.x + size.x, pos.y + size.y, pos.z + 0), v3(pos.x + size.x, pos.y + size.y, pos.z + size.z)};
+    const V3 t[3] = {T.a, T.b, T.c};
+    if (!satOnAxis(g, t, v3(1, 0, 0))) return false;
+    if (!satOnAxis(g, t, v3(0, 1, 0))) return false;
+    if (!satOnAxis(g, t, v3(0, 0, 1))) return false;
+    if (!satOnAxis(g, t, T.n)) return false;
+    const V3 e1 = v3(T.b.x - T.a.x, T.b.y - T.a.y, T.b.z - T.a.z), e2 = v3(T.c.x - T.b.x, T.c.y - T.b.y, T.c.z - T.b.z),
+             e3 = v3(T.a.x - T.c.x, T.a.y - T.c.y, T.a.z - T.c.z);
+    const V3 box[3] = {v3(1, 0, 0), v3(0, 1, 0), v3(0, 0, 1)};
+    for (int b = 0; b < 3; b++)
+    {
+        if (!satOnAxis(g, t, satCross(box[b], e1))) return false;
+        if (!satOnAxis(g, t, satCross(box[b], e2))) return false;
+        if (!satOnAxis(g, t, satCross(box[b], e3))) return false;
+    }
+    return true;
+}
+
 void initGrid(TunnelO &T)
 { // Tunnel.cpp:346-465
     V3 mn, mx; tunnelBounds(T, mn, mx);
@@ -509,7 +556,12 @@ void initGrid(TunnelO &T)
         const int xe = (int)((b.x - T.origin.x) / T.csx), ye = (int)((b.y - T.origin.y) / T.csy), ze = (int)((b.z - T.origin.z) / T.csz);
         for (int i = xb; i <= xe; i++)
             for (int j = yb; j <= ye; j++)
-                for (int k = zb; k <= ze; k++) T.cells[((size_t)i * T.ny + j) * T.nz + k].push_back((int)m);
+                for (int k = zb; k <= ze; k++)
+                { // Tunnel.cpp:435-445: the exact branch (option) or the simple one (what the reference ships)
+                    if (T.exactGrid && !triIntersectsCell(T.tris[m], v3(T.origin.x + i * T.csx, T.origin.y + j * T.csy, T.origin.z + k * T.csz),
+                                                          v3(T.csx, T.csy, T.csz))) continue;
+                    T.cells[((size_t)i * T.ny + j) * T.nz + k].push_back((int)m);
+                }
     }
 }
 
@@ -1750,6 +1802,7 @@ extern "C" int rt_oracle_run(oracle_job *job)
     if (s.hasTunnel)
     {
         TunnelO &T = s.tunnel;
+        T.exactGrid = job->grid_exact != 0;
         const auto t0 = std::chrono::steady_clock::now();
         if (T.algorithm == 1 || T.algorithm == 2) initGrid(T);
         else if (T.algorithm == 3 || T.algorithm == 4) initKd(T);

@@ -129,7 +129,30 @@ def convex_golden():
         json.dump(meta, f, indent=1, sort_keys=True)
 
 
+SAT_JOBS = {  # regular grids binned with the reference's exact overlap test (libref_sat.so: Tunnel.cpp:435 enabled)
+    "p5_rgrid_s24_96x72": (dict(preset=5, algorithm="rgrid", segments=24, width=96, height=72), True),
+    "p4_rgrid_s16_64x48": (dict(preset=4, algorithm="rgrid", segments=16, width=64, height=48), True),
+    "p5_rgrid_s150_400x300": (dict(preset=5, algorithm="rgrid", segments=150, width=400, height=300), False),
+}
+
+
+def sat_golden():
+    """tests/golden/sat_golden.{npz,json}: the reference rebuilt with its exact grid binning enabled (build_ref.sh P8)."""
+    arrays, meta = {}, {}
+    for name, (job, keep) in SAT_JOBS.items():
+        r = O.run("ref_sat", image=True, hits=True, seq=True, **job)
+        meta[name] = {"job": job, "stats": r["stats"], "struct_hash": f"{r['struct_hash']:016x}", "n_rays": r["n_rays"],
+                      "n_tri_tests": r["n_tri_tests"], "n_steps": r["n_steps"], "sha256": {k: digest(r[k]) for k in ARRAYS}}
+        if keep:
+            for k in ARRAYS:
+                arrays[f"{name}.{k}"] = r[k]
+    np.savez_compressed(os.path.join(HERE, "sat_golden.npz"), **arrays)
+    with open(os.path.join(HERE, "sat_golden.json"), "w") as f:
+        json.dump(meta, f, indent=1, sort_keys=True)
+
+
 if __name__ == "__main__":
     bounce_golden()
     bounce_pt_golden()
     convex_golden()
+    sat_golden()

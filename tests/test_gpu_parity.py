@@ -703,6 +703,44 @@ def test_grid_built_on_device_is_identical(ctx, job):
     dh.close(); dl.close(); host.close(); lazy.close()
 
 
+@pytest.mark.parametrize("name", ["p5_rgrid_s24_96x72", "p4_rgrid_s16_64x48", "p5_rgrid_s150_400x300"])
+def test_exact_grid_binning_host_and_device(ctx, name):
+    """the exact triangle / cell overlap test (reference Triangle.cpp:152-199, compiled out at
+    Tunnel.cpp:435-445) as an option of BOTH grid builders.  Fixtures come from the reference rebuilt with that branch
+    enabled (libref_sat.so): the host-built and the device-built grid have its structure hash and statistics, and the
+    frames rendered over them have its hit ids, distances, cell sequences, counts and image."""
+    with open(os.path.join(os.path.dirname(__file__), "golden", "sat_golden.json")) as f:
+        g = json.load(f)[name]
+    sat = np.load(os.path.join(os.path.dirname(__file__), "golden", "sat_golden.npz"))
+    job = g["job"]
+    rtb200.set_exact_grid_binning(True)
+    try:
+        host = PresetScene(job["preset"], job["algorithm"], job["segments"])
+        rtb200.set_grid_on_device(True)
+        lazy = PresetScene(job["preset"], job["algorithm"], job["segments"])
+    finally:
+        rtb200.set_grid_on_device(False)
+        rtb200.set_exact_grid_binning(False)
+    assert lazy.flat.contents.grid_build_exact == 1 and not lazy.flat.contents.grid_words
+    import hashlib
+    for s in (host, lazy):
+        dev = ctx.upload(s.flat)
+        h, st = dev.grid_hash()
+        assert f"{h:016x}" == g["struct_hash"]
+        assert {k: g["stats"][k] for k in st} == st
+        r = dev.trace_primary(s.camera, job["width"], job["height"], seq=True)
+        for k in ("hit_id", "hit_t", "seq_len", "seq_hash"):
+            assert hashlib.sha256(np.ascontiguousarray(r[k]).tobytes()).hexdigest() == g["sha256"][k], k
+        fr = rtb200.make_frame(job["width"], job["height"], counters=1)
+        img, cnt = dev.render(s.camera, s.setting, fr)
+        img2, _ = dev.render(s.camera, s.setting, fr)  # tiers
+        assert np.array_equal(_bits(img), _bits(img2))
+        assert (cnt["n_rays"], cnt["n_tri_tests"], cnt["n_steps"]) == (g["n_rays"], g["n_tri_tests"], g["n_steps"])
+        if f"{name}.image" in sat.files:
+            _assert_image_close(img, sat[f"{name}.image"], name)
+        dev.close(); s.close()
+
+
 # ---- output stage (SURVEY 8f rank 4): saturate -> 8 bit, BMP writer -----------------------------------
 @pytest.mark.parametrize("name", ["p4_sah_s12_80x60", "p5_rgrid_s40_160x120", "p1_simple_80x60", "p2_simple_80x60"])
 def test_rgb8_output_stage_vs_reference(ctx, name):

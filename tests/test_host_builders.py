@@ -30,6 +30,27 @@ def test_builder_matches_reference(name):
     s.close()
 
 
+def test_exact_grid_binning_matches_the_reference_branch():
+    """Tunnel::exactGridBinning bins with Triangle::intersectWithGrid (reference Triangle.cpp:152-199): the grid must be the
+    one the reference builds with the branch it keeps compiled out (Tunnel.cpp:435-445) switched on -- fixtures from
+    oracle/_ref/libref_sat.so, tests/golden/make_golden.py: sat_golden -- and must hold fewer references than the default."""
+    with open(os.path.join(os.path.dirname(__file__), "golden", "sat_golden.json")) as f:
+        sat = json.load(f)
+    for name, g in sat.items():
+        j = g["job"]
+        plain = PresetScene(j["preset"], j["algorithm"], j["segments"])
+        rtb200.set_exact_grid_binning(True)
+        try:
+            s = PresetScene(j["preset"], j["algorithm"], j["segments"])
+        finally:
+            rtb200.set_exact_grid_binning(False)
+        assert s.stats() == g["stats"], name
+        assert f"{s.struct_hash():016x}" == g["struct_hash"], name
+        assert s.stats()["cell_entries"] < plain.stats()["cell_entries"]
+        assert s.struct_hash() != plain.struct_hash()
+        s.close(); plain.close()
+
+
 def test_reference_log_structure_kats():
     """Grid Size 400 x 5 x 400 and the leaf counts printed in the reference's logs."""
     s = PresetScene(5, "rgrid", 150)

@@ -193,3 +193,41 @@ def test_convex_presets_oracle_matches_ref(alg):
     assert a["struct_hash"] == b["struct_hash"] and a["n_rays"] == b["n_rays"]
     for k in ("hit_id", "hit_t", "image"):
         assert np.array_equal(a[k].view(np.uint8), b[k].view(np.uint8)), k
+
+
+# ---- exact grid binning: the branch the reference carries compiled out (Tunnel.cpp:435-445) -------------------------
+def _sat_golden():
+    import os
+    here = os.path.join(os.path.dirname(__file__), "golden")
+    with open(os.path.join(here, "sat_golden.json")) as f:
+        return json.load(f), np.load(os.path.join(here, "sat_golden.npz"))
+
+
+@pytest.mark.parametrize("name", ["p5_rgrid_s24_96x72", "p4_rgrid_s16_64x48", "p5_rgrid_s150_400x300"])
+def test_oracle_exact_grid_binning_matches_the_reference_branch(name):
+    """oracle_job.grid_exact restates Triangle::intersectWithGrid (Triangle.cpp:152-199).  Fixtures: the reference rebuilt
+    with the guarded branch enabled (oracle/_ref/libref_sat.so, build_ref.sh patch P8): grid statistics, structure hash,
+    per-ray hit ids / distances / cell sequences, image and counts must all be reproduced bit for bit."""
+    meta, arrays = _sat_golden()
+    g = meta[name]
+    r = O.run("oracle", image=True, hits=True, seq=True, grid_exact=True, **g["job"])
+    assert r["stats"] == g["stats"]
+    assert f"{r['struct_hash']:016x}" == g["struct_hash"]
+    assert (r["n_rays"], r["n_tri_tests"], r["n_steps"]) == (g["n_rays"], g["n_tri_tests"], g["n_steps"])
+    for k in ARRAYS:
+        assert _digest(r[k]) == g["sha256"][k], k
+        if f"{name}.{k}" in arrays.files:
+            assert np.array_equal(np.ascontiguousarray(r[k]).view(np.uint8), np.ascontiguousarray(arrays[f"{name}.{k}"]).view(np.uint8)), k
+    plain = O.run("oracle", **g["job"])
+    assert plain["stats"]["cell_entries"] > r["stats"]["cell_entries"]  # fewer references per cell: what the option is for
+
+
+def test_oracle_exact_grid_binning_live():
+    if not O.available("ref_sat"):
+        pytest.skip("oracle/_ref/libref_sat.so is built only where the reference sources exist")
+    job = dict(preset=5, algorithm="rgrid", segments=31, width=72, height=54)
+    a = O.run("ref_sat", image=True, hits=True, seq=True, **job)
+    b = O.run("oracle", image=True, hits=True, seq=True, grid_exact=True, **job)
+    assert a["stats"] == b["stats"] and a["struct_hash"] == b["struct_hash"]
+    for k in ARRAYS:
+        assert np.array_equal(np.ascontiguousarray(a[k]).view(np.uint8), np.ascontiguousarray(b[k]).view(np.uint8)), k

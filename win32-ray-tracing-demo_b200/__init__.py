@@ -71,6 +71,7 @@ class FlatScene(C.Structure):
         ("cx_table_size", C.c_int32), ("cx_round_bins", C.c_int32),
         ("cx_cell_status", C.POINTER(C.c_uint8)), ("cx_cell_range", C.POINTER(C.c_int16)),
         ("cx_order", C.POINTER(C.c_uint16)),
+        ("grid_build_exact", C.c_int32), ("pad_", C.c_int32),
     ]
 
 
@@ -308,6 +309,12 @@ class PresetScene:
         pos, nrm = np.zeros(3, np.float32), np.zeros(3, np.float32)
         host_lib().rtbh_intersect_one(self._h, ray.ctypes.data, C.byref(hid), C.byref(ht), pos.ctypes.data, nrm.ctypes.data)
         return hid.value, ht.value, pos, nrm
+
+
+def set_exact_grid_binning(on):
+    """Tunnels built from now on bin triangles into grid cells with the exact overlap test (reference
+    Triangle.cpp:152-199, compiled out at Tunnel.cpp:435-445) instead of the bounding-box overlap."""
+    host_lib().rtbh_set_exact_grid_binning(1 if on else 0)
 
 
 def set_grid_on_device(on):

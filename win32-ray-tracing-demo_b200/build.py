@@ -22,7 +22,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 # compiled side by side, linked into one library
 CUDA_UNITS = ["rtb_abi.cu", "rtb_k_chain.cu", "rtb_k_sm.cu", "rtb_k_oct.cu", "rtb_k_wide.cu", "rtb_k_mc.cu"]
 CUDA_HEADERS = ["rtb_launch.h", "rtb_misc.cuh", "rtb_chain_sm.cuh", "rtb_chain_wide.cuh", "rtb_chain_oct.cuh", "rtb_build_grid.cuh",
-                "rtb_kernels.cuh", "rtb_device.cuh", "rtb_pretest.h"]
+                "rtb_kernels.cuh", "rtb_device.cuh", "rtb_pretest.h", "rtb_sat.h"]
 GXX_FLAGS = ["-O2", "-std=c++17", "-fopenmp", "-ffp-contract=off", "-fPIC", "-shared", "-Wall"]
 
 
@@ -65,7 +65,7 @@ def build_cuda(force=False, verbose=False):
 
 def build_host(force=False):
     src = [os.path.join(PKG, "host", f) for f in ("rt_scene.cpp", "rt_tunnel.cpp", "rt_render.cpp")]
-    deps = src + [os.path.join(PKG, "host", "rt.h"), os.path.join(ROOT, "include", "rtb.h")]
+    deps = src + [os.path.join(PKG, "host", "rt.h"), os.path.join(PKG, "csrc", "rtb_sat.h"), os.path.join(ROOT, "include", "rtb.h")]
     if not force and _newer(HOST_LIB, deps) and os.path.getmtime(HOST_LIB) >= os.path.getmtime(CUDA_LIB):
         return HOST_LIB
     # plain `g++` from PATH: the image's $CXX wrapper lacks libgomp

@@ -158,6 +158,7 @@ static unsigned long long sceneSignature(const rtb_flat_scene *f)
     h = fnv(h, f->materials, sizeof(rtb_material) * (size_t)f->n_materials);
     h = fnv(h, &f->accel, sizeof(f->accel));
     h = fnv(h, &f->grid_build_resolution, sizeof(f->grid_build_resolution));
+    h = fnv(h, &f->grid_build_exact, sizeof(f->grid_build_exact));
     h = fnvSampled(h, f->loose_tri, f->loose_tri ? (size_t)f->n_loose * 12 : 0);
     h = fnvSampled(h, f->tri, f->tri ? (size_t)f->n_tris * 12 : 0);
     if (f->accel == RTB_ACCEL_REGULAR_GRID || f->accel == RTB_ACCEL_FLAT_GRID)
@@ -514,6 +515,7 @@ static int buildGridOnDevice(rtb_ctx *ctx, rtb_scene *s, const rtb_flat_scene *f
 
     // sizing with the reference's float expressions (Tunnel.cpp:372-404)
     GridSizing G;
+    G.exact = f->grid_build_exact ? 1 : 0;
     const float width = b[3] - b[0], height = b[4] - b[1], depth = b[5] - b[2];
     if (f->accel == RTB_ACCEL_REGULAR_GRID)
     {

@@ -16,10 +16,11 @@
 #pragma once
 #include <cub/cub.cuh>
 #include "rtb_device.cuh"
+#include "rtb_sat.h"
 
 namespace rtb {
 
-struct GridSizing { float origin[3], cell[3]; int dims[3]; };
+struct GridSizing { float origin[3], cell[3]; int dims[3]; int exact; };
 
 // float atomics through the ordered-integer trick (all values finite)
 __device__ __forceinline__ void atomicMinFloat(float *addr, float v)
@@ -77,13 +78,33 @@ __device__ __forceinline__ void triCellRange(const float *t, const GridSizing &G
     }
 }
 
+// exact binning (GridSizing::exact): the cell the reference would construct for (x, y, z) -- position origin + index * size
+// per axis, size per axis (Tunnel.cpp:437) -- against the triangle, rtb_sat.h
+__device__ __forceinline__ bool cellTakes(const float *t, const GridSizing &G, int x, int y, int z)
+{
+    if (!G.exact) return true;
+    const float pos[3] = {G.origin[0] + x * G.cell[0], G.origin[1] + y * G.cell[1], G.origin[2] + z * G.cell[2]};
+    return rtb_sat::triangleOverlapsCell(t, pos, G.cell);
+}
+
 __global__ void k_grid_count(const float *__restrict__ tri, int n, const __grid_constant__ GridSizing G, unsigned int *__restrict__ count)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int lo[3], hi[3];
     triCellRange(tri + 12ull * i, G, lo, hi);
-    count[i] = (unsigned int)(hi[0] - lo[0] + 1) * (unsigned int)(hi[1] - lo[1] + 1) * (unsigned int)(hi[2] - lo[2] + 1);
+    if (!G.exact)
+    {
+        count[i] = (unsigned int)(hi[0] - lo[0] + 1) * (unsigned int)(hi[1] - lo[1] + 1) * (unsigned int)(hi[2] - lo[2] + 1);
+        return;
+    }
+    float t[12];
+    for (int k = 0; k < 12; k++) t[k] = tri[12ull * i + k];
+    unsigned int c = 0;
+    for (int x = lo[0]; x <= hi[0]; x++)
+        for (int y = lo[1]; y <= hi[1]; y++)
+            for (int z = lo[2]; z <= hi[2]; z++) c += cellTakes(t, G, x, y, z) ? 1u : 0u;
+    count[i] = c;
 }
 
 __global__ void k_grid_emit(const float *__restrict__ tri, int n, const __grid_constant__ GridSizing G, const unsigned int *__restrict__ offset,
@@ -93,11 +114,14 @@ __global__ void k_grid_emit(const float *__restrict__ tri, int n, const __grid_c
     if (i >= n) return;
     int lo[3], hi[3];
     triCellRange(tri + 12ull * i, G, lo, hi);
+    float t[12];
+    for (int k = 0; k < 12; k++) t[k] = tri[12ull * i + k];
     unsigned int e = offset[i];
     for (int x = lo[0]; x <= hi[0]; x++)
         for (int y = lo[1]; y <= hi[1]; y++)
             for (int z = lo[2]; z <= hi[2]; z++)
             {
+                if (!cellTakes(t, G, x, y, z)) continue;
                 const unsigned long long cell = (unsigned long long)((x * G.dims[1] + y) * G.dims[2] + z); // Tunnel.h:63-66
                 keys[e++] = (cell << 32) | (unsigned int)i;
             }

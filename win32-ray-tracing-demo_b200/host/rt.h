@@ -306,6 +306,11 @@ public:
     // newly generated tunnels is Tunnel::gridOnDeviceDefault (false: host build, needed for host-side statistics).
     bool gridOnDevice = false;
     static bool gridOnDeviceDefault;
+    // RegularGrid / FlatGrid: a triangle enters a cell only if it passes the exact overlap test Triangle::intersectWithGrid
+    // (reference Triangle.cpp:152-199), the alternative the reference keeps compiled out at Tunnel.cpp:435-445; default
+    // false = the bounding-box binning the reference ships.  Host and device builders honour it (csrc/rtb_sat.h).
+    bool exactGridBinning = false;
+    static bool exactGridBinningDefault;
 
     // Reference Tunnel.cpp:116-133: builds the accelerator selected by `algorithm`.
     void init();

@@ -13,6 +13,7 @@
 // Float arithmetic that decides structure (bounds, cell indices, candidate positions, SAH costs)
 // follows the reference expression by expression; compile with -ffp-contract=off.
 #include "rt.h"
+#include "../csrc/rtb_sat.h"
 
 #include <algorithm>
 #include <cfloat>
@@ -87,6 +88,7 @@ bool TunnelGenerator::create(float rectWidth, float rectHeight, float archHeight
 {
     Tunnel *tunnel = new Tunnel();
     tunnel->gridOnDevice = Tunnel::gridOnDeviceDefault;
+    tunnel->exactGridBinning = Tunnel::exactGridBinningDefault;
     tunnel->height = rectHeight + archHeight;
     tunnel->width = rectWidth;
     tunnel->algorithm = algorithm;
@@ -176,6 +178,7 @@ bool TunnelGenerator::create(float rectWidth, float rectHeight, float archHeight
 
 // ---- Tunnel ------------------------------------------------------------------------------------
 bool Tunnel::gridOnDeviceDefault = false;
+bool Tunnel::exactGridBinningDefault = false;
 
 size_t Tunnel::triangleCount() const
 {
@@ -398,6 +401,13 @@ void Tunnel::initGrid(const std::vector<TunnelTriangle> &tris)
             for (int j = lo[1]; j <= hi[1]; j++)
                 for (int k = lo[2]; k <= hi[2]; k++)
                 {
+                    if (exactGridBinning)
+                    { // the cell the reference's disabled branch constructs (Tunnel.cpp:437): origin + Vector(i * size, j * size, k * size)
+                        const float pos[3] = {gridOrigin_[0] + i * gridCell_[0], gridOrigin_[1] + j * gridCell_[1], gridOrigin_[2] + k * gridCell_[2]};
+                        const TunnelTriangle &T = tris[m];
+                        const float rec[12] = {T.a.x, T.a.y, T.a.z, T.b.x, T.b.y, T.b.z, T.c.x, T.c.y, T.c.z, T.normal.x, T.normal.y, T.normal.z};
+                        if (!rtb_sat::triangleOverlapsCell(rec, pos, gridCell_)) continue;
+                    }
                     const uint64_t cell = (uint64_t)(((int64_t)i * ny + j) * nz + k);
                     keys.push_back((cell << 32) | (uint64_t)owner.size());
                     owner.push_back((uint32_t)m);
@@ -683,6 +693,7 @@ void Tunnel::flatten(FlatScene &out) const
     f.cx_width = width; f.cx_height = height;
     f.cx_table_size = cxTable_; f.cx_round_bins = performanceTestBuilders ? 1 : 0;
     f.grid_build_resolution = ((algorithm == RegularGrid || algorithm == FlatGrid) && gridOnDevice) ? gridResolution : 0;
+    f.grid_build_exact = exactGridBinning ? 1 : 0;
 }
 
 } // namespace rt
