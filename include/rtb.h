@@ -131,7 +131,11 @@ typedef struct rtb_flat_scene {
                                                        (Triangle.cpp:152-199), the alternative the reference compiles out at
                                                        Tunnel.cpp:435-445 ("8 times faster" to build without, "20% slower" to
                                                        traverse); 0 = bounding-box binning as the reference ships               */
-    int32_t pad_;
+    /* RTB_ACCEL_KD_SAH with kd_nodes == NULL and kd_build_max_depth > 0: the library builds the tree ON THE DEVICE from `tri`
+     * with the reference's builder (Tunnel.cpp:546-638, 671-784): leaf when the list holds <= kd_build_leaf_size triangles or
+     * depth > kd_build_max_depth (reference: 8 and 18), kd_build_candidates - 1 uniform planes per axis (reference: 100 - 1).
+     * kd_min / kd_max / n_kd_* and the two arrays are ignored.                                                                */
+    int32_t kd_build_leaf_size, kd_build_max_depth, kd_build_candidates;
 } rtb_flat_scene;
 
 /* ---- camera: reference Camera.h:7-23; the derived fields are computed on the host exactly as
@@ -248,6 +252,11 @@ int64_t rtb_scene_upload_bytes(const rtb_scene *scene);
  * tests/golden and the host API use for grids; stats = {dims x, y, z, occupied cells, triangle references, longest
  * cell list}.  RTB_ERR_UNSUPPORTED for other accelerators.                                                          */
 int rtb_scene_grid_hash(rtb_ctx *ctx, const rtb_scene *scene, uint64_t *hash, int64_t stats[6]);
+/* Inspection: the k-d tree resident on the device (uploaded, or built there) read back in the layout of rtb_flat_scene:
+ * nodes[counts[0]] in pre-order, leaf_tris[counts[1]]; counts[2] = levels of a device build (0 otherwise); box = root box
+ * (min xyz, size xyz).  Either array may be NULL to query the counts first.                                            */
+int rtb_scene_kd_download(rtb_ctx *ctx, const rtb_scene *scene, rtb_kdnode *nodes, int64_t node_cap, uint32_t *leaf_tris,
+                          int64_t ref_cap, int64_t counts[3], float box[6]);
 
 /* Replaces `int Render(GeometrySet&, PerspectiveCamera&, RenderSetting&, ProgressCallback)`
  * (reference MainWindow.cpp:251-303, the RenderProc of Scripts.h:11-12): ray generation,

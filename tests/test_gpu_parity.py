@@ -10,6 +10,7 @@ Whitted images agree within 1e-5 relative (in fact bit-exact wherever no libm po
 Monte-Carlo images agree path-for-path with the oracle's counter-RNG mode on almost every pixel and
 statistically with the reference's erand48 images.
 """
+import ctypes as C
 import json
 import os
 
@@ -700,6 +701,38 @@ def test_grid_built_on_device_is_identical(ctx, job):
     a, sa = dh.render(host.camera, host.setting, fr)
     b, sb = dl.render(lazy.camera, lazy.setting, fr)
     assert np.array_equal(_bits(a), _bits(b)) and sa["n_rays"] == sb["n_rays"]
+    dh.close(); dl.close(); host.close(); lazy.close()
+
+
+@pytest.mark.parametrize("preset,segments", [(5, 12), (5, 40), (4, 24), (5, 150), (4, 150)])
+def test_sah_tree_built_on_device_is_identical(ctx, preset, segments):
+    """SURVEY 8f rank 2, second half: rtb_scene_upload with RTB_ACCEL_KD_SAH, no node arrays and build parameters builds the
+    tree on the device (csrc/rtb_build_kd.cuh: reference Tunnel.cpp:546-638, 671-784 -- candidate evaluation as histogram +
+    prefix sums per node, level-synchronous).  The node array and the leaf reference array read back from the device are
+    the host builder's, ELEMENT FOR ELEMENT (the host builder's tree is the reference's: tests/test_host_builders.py, leaf
+    counts 34478 / 52778 of the reference's logs at 150 segments), and so are the root box and the rendered frame."""
+    host = PresetScene(preset, "sah", segments)
+    rtb200.set_kd_on_device(True)
+    try:
+        lazy = PresetScene(preset, "sah", segments)
+    finally:
+        rtb200.set_kd_on_device(False)
+    hf, lf = host.flat.contents, lazy.flat.contents
+    assert lf.kd_build_max_depth == 18 and lf.kd_build_leaf_size == 8 and lf.kd_build_candidates == 100 and not lf.kd_nodes
+    dh, dl = ctx.upload(host.flat), ctx.upload(lazy.flat)
+    nodes, refs, levels, box = dl.kd_download()
+    want_nodes = np.ctypeslib.as_array(C.cast(hf.kd_nodes, C.POINTER(C.c_uint32)), shape=(hf.n_kd_nodes, 2))
+    want_refs = np.ctypeslib.as_array(hf.kd_leaf_tris, shape=(hf.n_kd_refs,))
+    assert nodes.shape == want_nodes.shape and np.array_equal(nodes, want_nodes)
+    assert np.array_equal(refs, want_refs)
+    assert 1 <= levels <= 20
+    assert np.array_equal(box[:3], np.array(list(hf.kd_min), np.float32))
+    assert np.array_equal(box[3:], np.array(list(hf.kd_max), np.float32) - np.array(list(hf.kd_min), np.float32))
+    assert dl.upload_bytes < dh.upload_bytes  # nothing of the accelerator crosses PCIe
+    fr = rtb200.make_frame(160, 120, counters=1)
+    a, sa = dh.render(host.camera, host.setting, fr)
+    b, sb = dl.render(lazy.camera, lazy.setting, fr)
+    assert np.array_equal(_bits(a), _bits(b)) and (sa["n_rays"], sa["n_tri_tests"], sa["n_steps"]) == (sb["n_rays"], sb["n_tri_tests"], sb["n_steps"])
     dh.close(); dl.close(); host.close(); lazy.close()
 
 

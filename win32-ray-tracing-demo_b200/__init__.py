@@ -71,7 +71,8 @@ class FlatScene(C.Structure):
         ("cx_table_size", C.c_int32), ("cx_round_bins", C.c_int32),
         ("cx_cell_status", C.POINTER(C.c_uint8)), ("cx_cell_range", C.POINTER(C.c_int16)),
         ("cx_order", C.POINTER(C.c_uint16)),
-        ("grid_build_exact", C.c_int32), ("pad_", C.c_int32),
+        ("grid_build_exact", C.c_int32),
+        ("kd_build_leaf_size", C.c_int32), ("kd_build_max_depth", C.c_int32), ("kd_build_candidates", C.c_int32),
     ]
 
 
@@ -112,7 +113,7 @@ class Stats(C.Structure):
 ABI_SYMBOLS = ["rtb_init", "rtb_shutdown", "rtb_last_error", "rtb_abi_version", "rtb_shard_rows", "rtb_shard_width",
                "rtb_unshard_cols_device",
                "rtb_host_alloc", "rtb_host_free",
-               "rtb_scene_upload", "rtb_scene_free", "rtb_scene_device_bytes", "rtb_scene_upload_bytes", "rtb_scene_grid_hash", "rtb_render",
+               "rtb_scene_upload", "rtb_scene_free", "rtb_scene_device_bytes", "rtb_scene_upload_bytes", "rtb_scene_grid_hash", "rtb_scene_kd_download", "rtb_render",
                "rtb_render_device", "rtb_unshard_device", "rtb_trace_primary", "rtb_intersect_rays", "rtb_bounce_rays",
                "rtb_selftest_pretest", "rtb_kd_validate", "rtb_forget_schedule", "rtb_set_progress", "rtb_multi_set_progress",
                "rtb_device_alloc", "rtb_device_free", "rtb_device_download", "rtb_ipc_export", "rtb_ipc_open", "rtb_ipc_close",
@@ -149,6 +150,7 @@ def cuda_lib():
         lib.rtb_scene_upload_bytes.restype = i64
         lib.rtb_scene_grid_hash.argtypes = [vp, vp, C.POINTER(C.c_uint64), C.POINTER(C.c_int64)]
         lib.rtb_scene_grid_hash.restype = C.c_int
+        lib.rtb_scene_kd_download.argtypes = [vp, vp, vp, i64, vp, i64, C.POINTER(C.c_int64), C.POINTER(C.c_float)]
         lib.rtb_render.argtypes = [vp, vp, C.POINTER(Camera), C.POINTER(RenderSetting), C.POINTER(Frame), vp,
                                    C.POINTER(Stats)]
         lib.rtb_render_device.argtypes = [vp, vp, C.POINTER(Camera), C.POINTER(RenderSetting), C.POINTER(Frame),
@@ -315,6 +317,11 @@ def set_exact_grid_binning(on):
     """Tunnels built from now on bin triangles into grid cells with the exact overlap test (reference
     Triangle.cpp:152-199, compiled out at Tunnel.cpp:435-445) instead of the bounding-box overlap."""
     host_lib().rtbh_set_exact_grid_binning(1 if on else 0)
+
+
+def set_kd_on_device(on):
+    """Tunnels built from now on leave a KdTreeSAH accelerator to the device builder of rtb_scene_upload."""
+    host_lib().rtbh_set_kd_on_device(1 if on else 0)
 
 
 def set_grid_on_device(on):
@@ -618,6 +625,15 @@ class DeviceScene:
         h, st = C.c_uint64(0), (C.c_int64 * 6)()
         self.ctx._check(self.ctx._lib.rtb_scene_grid_hash(self.ctx._h, self._h, C.byref(h), st), "rtb_scene_grid_hash")
         return int(h.value), dict(grid_x=st[0], grid_y=st[1], grid_z=st[2], cells_nonempty=st[3], cell_entries=st[4], cell_max=st[5])
+
+    def kd_download(self):
+        """(nodes [n][2] uint32, leaf_tris [m] uint32, levels, box) of the k-d tree resident on the device."""
+        counts, box = (C.c_int64 * 3)(), (C.c_float * 6)()
+        self.ctx._check(self.ctx._lib.rtb_scene_kd_download(self.ctx._h, self._h, None, 0, None, 0, counts, box), "rtb_scene_kd_download")
+        nodes, refs = np.zeros((counts[0], 2), np.uint32), np.zeros(counts[1], np.uint32)
+        self.ctx._check(self.ctx._lib.rtb_scene_kd_download(self.ctx._h, self._h, nodes.ctypes.data, counts[0], refs.ctypes.data, counts[1],
+                                                            counts, box), "rtb_scene_kd_download")
+        return nodes, refs, int(counts[2]), np.array(list(box), np.float32)
 
     def render(self, camera, setting, frame, out=None):
         """rtb_render with HOST buffers; returns (rows x width x 3 float32 | reference-order array, stats)."""

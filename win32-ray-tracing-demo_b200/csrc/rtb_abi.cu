@@ -16,6 +16,7 @@
 #include "rtb_launch.h"
 #include "rtb_misc.cuh"
 #include "rtb_build_grid.cuh"
+#include "rtb_build_kd.cuh"
 
 #ifndef RTB_SPLIT_MAX_TILES
 #define RTB_SPLIT_MAX_TILES 131072 // shards up to 4.2 Mpixel walk their latency-critical tiles with 4 warps each
@@ -131,6 +132,8 @@ struct rtb_scene
     cudaEvent_t last_use = nullptr; // recorded after every launch that reads the scene
     cudaEvent_t ready = nullptr;    // recorded on ctx->stream behind the upload copies
     int64_t grid_cells_used = 0, grid_refs = 0, grid_words = 0;
+    int64_t kd_nodes = 0, kd_refs = 0; // k-d tree resident on the device (uploaded or built there)
+    int kd_levels = 0;
     bool long_lists = false; // regular grid with >= 16 triangle references per occupied cell (tier policy, wideCount)
     unsigned long long signature = 0; // sampled content hash, identifies "the same scene again" for the tile-order cache
 };
@@ -159,6 +162,8 @@ static unsigned long long sceneSignature(const rtb_flat_scene *f)
     h = fnv(h, &f->accel, sizeof(f->accel));
     h = fnv(h, &f->grid_build_resolution, sizeof(f->grid_build_resolution));
     h = fnv(h, &f->grid_build_exact, sizeof(f->grid_build_exact));
+    h = fnv(h, &f->kd_build_max_depth, sizeof(f->kd_build_max_depth));
+    h = fnv(h, &f->kd_build_leaf_size, sizeof(f->kd_build_leaf_size));
     h = fnvSampled(h, f->loose_tri, f->loose_tri ? (size_t)f->n_loose * 12 : 0);
     h = fnvSampled(h, f->tri, f->tri ? (size_t)f->n_tris * 12 : 0);
     if (f->accel == RTB_ACCEL_REGULAR_GRID || f->accel == RTB_ACCEL_FLAT_GRID)
@@ -168,8 +173,8 @@ static unsigned long long sceneSignature(const rtb_flat_scene *f)
     }
     else if (f->accel == RTB_ACCEL_KD_MEDIAN || f->accel == RTB_ACCEL_KD_SAH)
     {
-        h = fnvSampled(h, f->kd_nodes, (size_t)f->n_kd_nodes);
-        h = fnvSampled(h, f->kd_leaf_tris, (size_t)f->n_kd_refs);
+        h = fnvSampled(h, f->kd_nodes, f->kd_nodes ? (size_t)f->n_kd_nodes : 0);
+        h = fnvSampled(h, f->kd_leaf_tris, f->kd_leaf_tris ? (size_t)f->n_kd_refs : 0);
     }
     return h;
 }
@@ -389,8 +394,11 @@ __global__ void k_pack_triangles(const float *__restrict__ raw, int n, float4 *_
 }
 
 // raw records -> staging -> device (asynchronous), packed there; `pre` may be null (loose triangles: exact stream only)
-static int uploadTriangles(rtb_ctx *ctx, rtb_scene *s, const float *host, size_t n, const float4 **exact, const float4 **pre)
+// keepRaw != nullptr: the raw device records are handed to the caller (a device accelerator build reads them), who frees them
+static int uploadTriangles(rtb_ctx *ctx, rtb_scene *s, const float *host, size_t n, const float4 **exact, const float4 **pre,
+                           float **keepRaw = nullptr)
 {
+    if (keepRaw) *keepRaw = nullptr;
     int rc;
     *exact = nullptr;
     if (pre) *pre = nullptr;
@@ -407,7 +415,8 @@ static int uploadTriangles(rtb_ctx *ctx, rtb_scene *s, const float *host, size_t
     k_pack_triangles<<<(unsigned int)((n + 255) / 256), 256, 0, ctx->stream>>>((const float *)raw, (int)n, const_cast<float4 *>(*exact),
                                                                              pre ? const_cast<float4 *>(*pre) : nullptr);
     CUDA_TRY(ctx, cudaGetLastError());
-    CUDA_TRY(ctx, cudaFreeAsync(raw, ctx->stream));
+    if (keepRaw) *keepRaw = (float *)raw;
+    else CUDA_TRY(ctx, cudaFreeAsync(raw, ctx->stream));
     return RTB_OK;
 }
 
@@ -492,7 +501,7 @@ template <class T> static int deviceArray(rtb_ctx *ctx, rtb_scene *s, size_t n, 
     return RTB_OK;
 }
 
-static int buildGridOnDevice(rtb_ctx *ctx, rtb_scene *s, const rtb_flat_scene *f)
+static int buildGridOnDevice(rtb_ctx *ctx, rtb_scene *s, const rtb_flat_scene *f, float *d_raw)
 {
     DScene &d = s->d;
     const int n = f->n_tris, R = f->grid_build_resolution;
@@ -501,10 +510,7 @@ static int buildGridOnDevice(rtb_ctx *ctx, rtb_scene *s, const rtb_flat_scene *f
     auto temp = [&](size_t bytes, void **p) { cudaError_t e = cudaMallocAsync(p, bytes ? bytes : 1, st); if (e == cudaSuccess) temps.push_back(*p); return e; };
     auto cleanup = [&]() { for (void *p : temps) cudaFreeAsync(p, st); };
 #define GRID_TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return fail(ctx, RTB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
-    float *d_raw = nullptr, *d_bounds = nullptr;
-    GRID_TRY(temp((size_t)n * 12 * sizeof(float), (void **)&d_raw));
-    GRID_TRY(cudaMemcpyAsync(d_raw, f->tri, (size_t)n * 12 * sizeof(float), cudaMemcpyHostToDevice, st));
-    s->h2d_bytes += (int64_t)n * 12 * (int64_t)sizeof(float);
+    float *d_bounds = nullptr; // d_raw: the raw triangle records already on the device (uploadTriangles)
     GRID_TRY(temp(6 * sizeof(float), (void **)&d_bounds));
     const float init[6] = {FLT_MAX, FLT_MAX, FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
     GRID_TRY(cudaMemcpyAsync(d_bounds, init, sizeof(init), cudaMemcpyHostToDevice, st));
@@ -610,6 +616,101 @@ static int buildGridOnDevice(rtb_ctx *ctx, rtb_scene *s, const rtb_flat_scene *f
     d.g_words = d_words; d.g_start = d_cell_start; d.g_tris = d_cell_tris;
     s->grid_cells_used = nRuns; s->grid_refs = total; s->grid_words = nWords;
     return packPairs(ctx, s, d_cell_tris, (size_t)total);
+}
+
+// ---- SAH k-d tree built on the device (rtb_build_kd.cuh) -------------------------------------------------------
+static int buildKdOnDevice(rtb_ctx *ctx, rtb_scene *s, const rtb_flat_scene *f, float *d_raw)
+{
+    DScene &d = s->d;
+    const int n = f->n_tris, leafSize = f->kd_build_leaf_size > 0 ? f->kd_build_leaf_size : 8, maxDepth = f->kd_build_max_depth;
+    const int N = f->kd_build_candidates > 0 ? f->kd_build_candidates : 100;
+    if (N < 2 || N > RTB_KDB_MAX_CAND) return fail(ctx, RTB_ERR_INVALID, "rtb_scene_upload: kd_build_candidates must be in [2, 128]");
+    if (2 * (maxDepth + 1) + 2 >= RTB_KD_STACK || maxDepth + 2 > RTB_KDB_MAX_LEVELS)
+        return fail(ctx, RTB_ERR_UNSUPPORTED, "rtb_scene_upload: kd_build_max_depth too deep for the 50-entry traversal stack");
+    cudaStream_t st = ctx->stream;
+    std::vector<void *> temps;
+    auto temp = [&](size_t bytes, void **p) { cudaError_t e = cudaMallocAsync(p, bytes ? bytes : 1, st); if (e == cudaSuccess) temps.push_back(*p); return e; };
+    auto cleanup = [&]() { for (void *p : temps) cudaFreeAsync(p, st); };
+#define KD_TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return fail(ctx, RTB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
+    float *d_bounds = nullptr, *d_lo = nullptr, *d_hi = nullptr; // d_raw: the raw triangle records already on the device
+    KD_TRY(temp(6 * sizeof(float), (void **)&d_bounds));
+    const float init[6] = {FLT_MAX, FLT_MAX, FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
+    KD_TRY(cudaMemcpyAsync(d_bounds, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    k_grid_bounds<<<148, 256, 0, st>>>(d_raw, n, d_bounds); // root box = bounds of all vertices (Tunnel.cpp:486-510)
+    KD_TRY(temp((size_t)3 * n * sizeof(float), (void **)&d_lo));
+    KD_TRY(temp((size_t)3 * n * sizeof(float), (void **)&d_hi));
+    const int tb = 256, nb = (n + tb - 1) / tb;
+    k_kd_extents<<<nb, tb, 0, st>>>(d_raw, n, d_lo, d_hi);
+
+    size_t nodeCap = (size_t)n * 2 + 1024;
+    KdBuildNode *d_nodes = nullptr;
+    KD_TRY(temp(nodeCap * sizeof(KdBuildNode), (void **)&d_nodes));
+    uint32_t *d_refs = nullptr;
+    KD_TRY(temp((size_t)n * sizeof(uint32_t), (void **)&d_refs));
+    k_kd_root<<<nb, tb, 0, st>>>(d_nodes, d_bounds, n, d_refs);
+    int *d_totals = nullptr;
+    KD_TRY(temp(4 * sizeof(int), (void **)&d_totals));
+
+    KdLeafChunks chunks;
+    memset(&chunks, 0, sizeof(chunks));
+    std::vector<int> levelFirst, levelCount;
+    int first = 0, count = 1, totalNodes = 1;
+    for (int level = 0; count > 0; level++)
+    {
+        if (level >= RTB_KDB_MAX_LEVELS) { cleanup(); return fail(ctx, RTB_ERR_UNSUPPORTED, "rtb_scene_upload: k-d build exceeded the level limit"); }
+        levelFirst.push_back(first); levelCount.push_back(count);
+        int *d_childOff = nullptr, *d_leafOff = nullptr, *d_innerRank = nullptr;
+        KD_TRY(temp((size_t)count * sizeof(int), (void **)&d_childOff));
+        KD_TRY(temp((size_t)count * sizeof(int), (void **)&d_leafOff));
+        KD_TRY(temp((size_t)count * sizeof(int), (void **)&d_innerRank));
+        k_kd_eval<<<count, RTB_KDB_THREADS, 0, st>>>(d_nodes, first, d_refs, d_lo, d_hi, n, leafSize, maxDepth, N);
+        k_kd_level_scan<<<1, 1024, 0, st>>>(d_nodes, first, count, d_childOff, d_leafOff, d_innerRank, d_totals);
+        int totals[3] = {0, 0, 0};
+        KD_TRY(cudaMemcpyAsync(totals, d_totals, sizeof(totals), cudaMemcpyDeviceToHost, st));
+        KD_TRY(cudaStreamSynchronize(st));
+        const int nextRefs = totals[0], leafRefs = totals[1], inner = totals[2];
+        if (nextRefs < 0 || leafRefs < 0) { cleanup(); return fail(ctx, RTB_ERR_OOM, "rtb_scene_upload: k-d build reference count overflow"); }
+        if ((size_t)totalNodes + 2 * (size_t)inner > nodeCap)
+        { // grow the node table (level order: the children of this level follow everything built so far)
+            const size_t cap = ((size_t)totalNodes + 2 * (size_t)inner) * 2;
+            KdBuildNode *bigger = nullptr;
+            KD_TRY(temp(cap * sizeof(KdBuildNode), (void **)&bigger));
+            KD_TRY(cudaMemcpyAsync(bigger, d_nodes, (size_t)totalNodes * sizeof(KdBuildNode), cudaMemcpyDeviceToDevice, st));
+            d_nodes = bigger; nodeCap = cap;
+        }
+        uint32_t *d_next = nullptr, *d_chunk = nullptr;
+        KD_TRY(temp((size_t)nextRefs * sizeof(uint32_t), (void **)&d_next));
+        KD_TRY(temp((size_t)leafRefs * sizeof(uint32_t), (void **)&d_chunk));
+        chunks.p[level] = d_chunk;
+        k_kd_partition<<<count, RTB_KDB_THREADS, 0, st>>>(d_nodes, first, level, totalNodes, d_refs, d_next, d_chunk, d_childOff, d_leafOff,
+                                                          d_innerRank, d_lo, d_hi, n);
+        KD_TRY(cudaGetLastError());
+        d_refs = d_next;
+        first = totalNodes; count = 2 * inner; totalNodes += 2 * inner;
+    }
+    const int levels = (int)levelFirst.size();
+    for (int l = levels - 1; l >= 0; l--) k_kd_sizes<<<(levelCount[l] + 255) / 256, 256, 0, st>>>(d_nodes, levelFirst[l], levelCount[l]);
+    for (int l = 0; l < levels; l++) k_kd_place<<<(levelCount[l] + 255) / 256, 256, 0, st>>>(d_nodes, levelFirst[l], levelCount[l]);
+    KdBuildNode root;
+    float b[6];
+    KD_TRY(cudaMemcpyAsync(&root, d_nodes, sizeof(root), cudaMemcpyDeviceToHost, st));
+    KD_TRY(cudaMemcpyAsync(b, d_bounds, sizeof(b), cudaMemcpyDeviceToHost, st));
+    KD_TRY(cudaStreamSynchronize(st));
+    if (root.subNodes != totalNodes) { cleanup(); return fail(ctx, RTB_ERR_CUDA, "rtb_scene_upload: k-d build inconsistent (subtree sizes)"); }
+    uint2 *d_out = nullptr;
+    uint32_t *d_leaf = nullptr;
+    int rc;
+    if ((rc = deviceArray(ctx, s, (size_t)totalNodes, &d_out, true)) != RTB_OK) { cleanup(); return rc; }
+    if ((rc = deviceArray(ctx, s, (size_t)root.subRefs, &d_leaf, true)) != RTB_OK) { cleanup(); return rc; }
+    k_kd_emit<<<(totalNodes + 255) / 256, 256, 0, st>>>(d_nodes, totalNodes, chunks, d_out, d_leaf);
+    KD_TRY(cudaGetLastError());
+    cleanup();
+#undef KD_TRY
+    d.kd_min = {b[0], b[1], b[2]};
+    d.kd_size = {b[3] - b[0], b[4] - b[1], b[5] - b[2]}; // Grid(near, far): size = far - near (Grid.cpp:13-17)
+    d.kd_nodes = d_out; d.kd_tris = d_leaf;
+    s->kd_nodes = totalNodes; s->kd_refs = root.subRefs; s->kd_levels = levels;
+    return packPairs(ctx, s, d_leaf, (size_t)root.subRefs);
 }
 
 // Index / structure checks of rtb_scene_upload that scan whole streams (k-d nodes, leaf and cell references: 0.6 ms
@@ -721,15 +822,20 @@ extern "C" int rtb_scene_upload(rtb_ctx *ctx, const rtb_flat_scene *f, rtb_scene
             return bail(fail(ctx, RTB_ERR_INVALID, "rtb_scene_upload: triangle material out of range"));
         const size_t nTris = (size_t)f->n_tris;
         laps.lap("loose+material check");
-        if ((rc = uploadTriangles(ctx, s, f->tri, nTris, &d.tri, &d.tri_pre)) != RTB_OK) return bail(rc);
+        const bool gridAccel = f->accel == RTB_ACCEL_REGULAR_GRID || f->accel == RTB_ACCEL_FLAT_GRID;
+        const bool gridOnDevice = gridAccel && !f->grid_words && f->grid_build_resolution > 1;
+        const bool kdOnDevice = f->accel == RTB_ACCEL_KD_SAH && !f->kd_nodes && f->kd_build_max_depth > 0;
+        float *d_raw = nullptr; // kept for a device accelerator build
+        if ((rc = uploadTriangles(ctx, s, f->tri, nTris, &d.tri, &d.tri_pre, (gridOnDevice || kdOnDevice) ? &d_raw : nullptr)) != RTB_OK) return bail(rc);
+        struct RawGuard { float *&p; cudaStream_t st; ~RawGuard() { if (p) cudaFreeAsync(p, st); } } rawGuard{d_raw, ctx->stream};
         if ((rc = uploadArray(ctx, s, f->tri_material, nTris, &d.tri_material)) != RTB_OK) return bail(rc);
         d.n_tris = f->n_tris;
         laps.lap("triangle streams");
 
-        if ((f->accel == RTB_ACCEL_REGULAR_GRID || f->accel == RTB_ACCEL_FLAT_GRID) && !f->grid_words && f->grid_build_resolution > 1)
+        if (gridOnDevice)
         { // no grid arrays, a resolution: build it here, on the device
             if (f->n_tris <= 0) return bail(fail(ctx, RTB_ERR_INVALID, "rtb_scene_upload: a grid needs triangles"));
-            if ((rc = buildGridOnDevice(ctx, s, f)) != RTB_OK) return bail(rc);
+            if ((rc = buildGridOnDevice(ctx, s, f, d_raw)) != RTB_OK) return bail(rc);
         }
         else if (f->accel == RTB_ACCEL_REGULAR_GRID || f->accel == RTB_ACCEL_FLAT_GRID)
         {
@@ -782,6 +888,11 @@ extern "C" int rtb_scene_upload(rtb_ctx *ctx, const rtb_flat_scene *f, rtb_scene
             if ((rc = packPairs(ctx, s, d.g_tris, (size_t)f->n_cell_refs)) != RTB_OK) return bail(rc);
             s->grid_cells_used = f->n_cells_used; s->grid_refs = f->n_cell_refs; s->grid_words = f->n_cellwords;
         }
+        else if (kdOnDevice)
+        { // no node arrays, build parameters: the SAH tree is built here, on the device
+            if (f->n_tris <= 0) return bail(fail(ctx, RTB_ERR_INVALID, "rtb_scene_upload: a k-d tree needs triangles"));
+            if ((rc = buildKdOnDevice(ctx, s, f, d_raw)) != RTB_OK) return bail(rc);
+        }
         else if (f->accel == RTB_ACCEL_KD_MEDIAN || f->accel == RTB_ACCEL_KD_SAH)
         {
             if (f->n_kd_nodes <= 0 || !f->kd_nodes || (f->n_kd_refs > 0 && !f->kd_leaf_tris))
@@ -820,6 +931,7 @@ extern "C" int rtb_scene_upload(rtb_ctx *ctx, const rtb_flat_scene *f, rtb_scene
             checks.join();
             if (checks.code != RTB_OK) return bail(fail(ctx, checks.code, checks.msg));
             if ((rc = packPairs(ctx, s, d.kd_tris, (size_t)f->n_kd_refs)) != RTB_OK) return bail(rc);
+            s->kd_nodes = f->n_kd_nodes; s->kd_refs = f->n_kd_refs;
         }
         else if (f->accel == RTB_ACCEL_CONVEX || f->accel == RTB_ACCEL_CONVEX_SIMPLE)
         {
@@ -929,6 +1041,30 @@ extern "C" int rtb_scene_grid_hash(rtb_ctx *ctx, const rtb_scene *s, uint64_t *h
     }
     *hash = x;
     if (stats) { stats[0] = d.nx; stats[1] = d.ny; stats[2] = d.nz; stats[3] = s->grid_cells_used; stats[4] = s->grid_refs; stats[5] = longest; }
+    return RTB_OK;
+}
+
+extern "C" int rtb_scene_kd_download(rtb_ctx *ctx, const rtb_scene *s, rtb_kdnode *nodes, int64_t node_cap, uint32_t *leaf_tris,
+                                     int64_t ref_cap, int64_t counts[3], float box[6])
+{
+    if (!ctx || !s) return fail(ctx, RTB_ERR_INVALID, "rtb_scene_kd_download: null argument");
+    const DScene &d = s->d;
+    if (!s->has_tunnel || (d.accel != RTB_ACCEL_KD_MEDIAN && d.accel != RTB_ACCEL_KD_SAH))
+        return fail(ctx, RTB_ERR_UNSUPPORTED, "rtb_scene_kd_download: the scene has no k-d tree");
+    if (counts) { counts[0] = s->kd_nodes; counts[1] = s->kd_refs; counts[2] = s->kd_levels; }
+    if (box) { box[0] = d.kd_min.x; box[1] = d.kd_min.y; box[2] = d.kd_min.z; box[3] = d.kd_size.x; box[4] = d.kd_size.y; box[5] = d.kd_size.z; }
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (nodes)
+    {
+        if (node_cap < s->kd_nodes) return fail(ctx, RTB_ERR_INVALID, "rtb_scene_kd_download: node buffer too small");
+        CUDA_TRY(ctx, cudaMemcpyAsync(nodes, d.kd_nodes, (size_t)s->kd_nodes * sizeof(rtb_kdnode), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (leaf_tris)
+    {
+        if (ref_cap < s->kd_refs) return fail(ctx, RTB_ERR_INVALID, "rtb_scene_kd_download: reference buffer too small");
+        CUDA_TRY(ctx, cudaMemcpyAsync(leaf_tris, d.kd_tris, (size_t)s->kd_refs * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return RTB_OK;
 }
 

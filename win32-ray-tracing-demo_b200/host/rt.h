@@ -311,6 +311,10 @@ public:
     // false = the bounding-box binning the reference ships.  Host and device builders honour it (csrc/rtb_sat.h).
     bool exactGridBinning = false;
     static bool exactGridBinningDefault;
+    // KdTreeSAH: leave the tree to the device builder (rtb_scene_upload, include/rtb.h: kd_build_*; csrc/rtb_build_kd.cuh)
+    // instead of building it here; init() then only records the request (RayTracingOpt's 99-candidate builder only).
+    bool kdOnDevice = false;
+    static bool kdOnDeviceDefault;
 
     // Reference Tunnel.cpp:116-133: builds the accelerator selected by `algorithm`.
     void init();

@@ -476,6 +476,8 @@ rtbh_scene *rtbh_perf_scene_create(float radius, float angle, int arch_seg, int 
 void rtbh_set_grid_on_device(int on) { Tunnel::gridOnDeviceDefault = on != 0; }
 // ... bin their triangles with the exact overlap test (Tunnel::exactGridBinning)
 void rtbh_set_exact_grid_binning(int on) { Tunnel::exactGridBinningDefault = on != 0; }
+// ... leave their SAH k-d tree to the device builder (Tunnel::kdOnDevice)
+void rtbh_set_kd_on_device(int on) { Tunnel::kdOnDeviceDefault = on != 0; }
 void rtbh_free(rtbh_scene *h) { delete h; }
 const rtb_flat_scene *rtbh_flat(const rtbh_scene *h) { return &h->flat.view; }
 const rtb_camera *rtbh_camera(const rtbh_scene *h) { return &h->cam; }

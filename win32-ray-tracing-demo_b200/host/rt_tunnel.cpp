@@ -89,6 +89,7 @@ bool TunnelGenerator::create(float rectWidth, float rectHeight, float archHeight
     Tunnel *tunnel = new Tunnel();
     tunnel->gridOnDevice = Tunnel::gridOnDeviceDefault;
     tunnel->exactGridBinning = Tunnel::exactGridBinningDefault;
+    tunnel->kdOnDevice = Tunnel::kdOnDeviceDefault;
     tunnel->height = rectHeight + archHeight;
     tunnel->width = rectWidth;
     tunnel->algorithm = algorithm;
@@ -179,6 +180,7 @@ bool TunnelGenerator::create(float rectWidth, float rectHeight, float archHeight
 // ---- Tunnel ------------------------------------------------------------------------------------
 bool Tunnel::gridOnDeviceDefault = false;
 bool Tunnel::exactGridBinningDefault = false;
+bool Tunnel::kdOnDeviceDefault = false;
 
 size_t Tunnel::triangleCount() const
 {
@@ -230,6 +232,7 @@ void Tunnel::init()
     stats = BuildStats();
     if ((algorithm == RegularGrid || algorithm == FlatGrid) && gridOnDevice) { /* built by rtb_scene_upload */ }
     else if (algorithm == RegularGrid || algorithm == FlatGrid) initGrid(tris);
+    else if (algorithm == KdTreeSAH && kdOnDevice && !performanceTestBuilders) { /* built by rtb_scene_upload */ }
     else if (algorithm == KdTreeStandard || algorithm == KdTreeSAH) initKdTree(tris);
     else if (algorithm == Convex || algorithm == ConvexSimple) initConvex();
     built_ = true;
@@ -694,6 +697,10 @@ void Tunnel::flatten(FlatScene &out) const
     f.cx_table_size = cxTable_; f.cx_round_bins = performanceTestBuilders ? 1 : 0;
     f.grid_build_resolution = ((algorithm == RegularGrid || algorithm == FlatGrid) && gridOnDevice) ? gridResolution : 0;
     f.grid_build_exact = exactGridBinning ? 1 : 0;
+    const bool kdDevice = algorithm == KdTreeSAH && kdOnDevice && !performanceTestBuilders;
+    f.kd_build_max_depth = kdDevice ? kdMaxDepth : 0;
+    f.kd_build_leaf_size = kdDevice ? kdLeafSize : 0;
+    f.kd_build_candidates = kdDevice ? sahCandidates : 0;
 }
 
 } // namespace rt
