@@ -99,6 +99,25 @@ inline void rngSeedSample(Rng &g, uint64_t seed, uint32_t pixel, uint32_t sample
     g.used = 4;
 }
 
+// Counter mode, the stream of the CUDA path (csrc/rtb_kernels.cuh: k_montecarlo): ONE Philox block per traced ray -- block 0 of
+// a sample carries the pixel jitter, block k belongs to the k-th ray of the sample in the order the rays are traced -- and the
+// four values of a block are addressed by SLOT: 0 Russian roulette, 1 p_type, 2 / 3 the hemisphere pair r1 / r2, 2 the
+// reflect-or-transmit test (a vertex draws either the pair or that test).  A fixed block per ray keeps the GPU's draws
+// converged (every lane computes its block at the top of the loop) where a sequential stream made each lane refill at its
+// own time.  erand48 mode (the reference's stream) ignores blocks and slots: the draws stay sequential in the reference's order.
+inline void rngRay(Rng &g)
+{
+    if (g.kind != ORACLE_RNG_COUNTER) return;
+    philox4x32_10(g.ctr, g.key, g.buf);
+    g.ctr[0]++;
+}
+inline double rngNext(Rng &g);
+inline double rngDraw(Rng &g, int slot)
+{
+    if (g.kind != ORACLE_RNG_COUNTER) return rngNext(g);
+    return (double)((float)(g.buf[slot] >> 8) * (1.0f / 16777216.0f));
+}
+
 inline double rngNext(Rng &g)
 {
     if (g.kind == ORACLE_RNG_ERAND48)
@@ -1374,6 +1393,7 @@ V3 trace(const Scene &s, RayO r, int depth, Probe *pr, RayCtx ctx = RayCtx{false
 
 V3 radiance(const Scene &s, RayO r, int depth, Rng &rng, Probe *pr)
 {
+    rngRay(rng); // counter mode: this ray's block
     const Hit res = sceneIntersect(s, r, pr);
     if (!res.hit) return v3(0, 0, 0);
     const Mat &m = s.mats[res.mat];
@@ -1385,14 +1405,14 @@ V3 radiance(const Scene &s, RayO r, int depth, Rng &rng, Probe *pr)
     if (++depth > s.setting.maxDepth) return emission;
     if (depth > s.setting.terminationDepth)
     {
-        if (rngNext(rng) < maxColor) local = local * (1 / maxColor);
+        if (rngDraw(rng, 0) < maxColor) local = local * (1 / maxColor);
         else return emission;
     }
     if (depth > 100) return emission;
-    const float p_type = (float)rngNext(rng);
+    const float p_type = (float)rngDraw(rng, 1);
     if (m.diffusiveness > 0 && p_type < m.diffusiveness)
     { // uniform hemisphere, unit weight (MainWindow.cpp:185-200)
-        const float r1 = (float)rngNext(rng), r2 = (float)rngNext(rng);
+        const float r1 = (float)rngDraw(rng, 2), r2 = (float)rngDraw(rng, 3);
         const float theta = 2 * PI_F * r1;
         const float phi = acosf(r2);
         const V3 w = nl;
@@ -1414,7 +1434,7 @@ V3 radiance(const Scene &s, RayO r, int depth, Rng &rng, Probe *pr)
         RayO tr = {p, f.tdir};
         if (depth > s.setting.singleTracingDepth)
         {
-            if ((float)rngNext(rng) < f.P) return radiance(s, f.refl, depth, rng, pr) * f.RP;
+            if ((float)rngDraw(rng, 2) < f.P) return radiance(s, f.refl, depth, rng, pr) * f.RP;
             return radiance(s, tr, depth, rng, pr) * f.TP;
         }
         // C++ leaves the evaluation order of the two operands of `+` unspecified; the g++ 13 build of
@@ -1450,7 +1470,8 @@ void render(const Scene &s, const oracle_job *job, float *rgb, Counters *total)
                 for (int i = 0; i < samples; i++)
                 {
                     if (job->rng == ORACLE_RNG_COUNTER) rngSeedSample(rng, job->seed, (uint32_t)(y * width + x), (uint32_t)i);
-                    const float r1 = (float)rngNext(rng), r2 = (float)rngNext(rng);
+                    rngRay(rng); // counter mode: block 0 of the sample
+                    const float r1 = (float)rngDraw(rng, 0), r2 = (float)rngDraw(rng, 1);
                     const float sx = (x + r1) * dx, sy = 1 - (y + r2) * dy;
                     const V3 L = radiance(s, generateRay(s.cam, sx, sy), 0, rng, &pr);
                     c = c + L * (1.0f / samples);

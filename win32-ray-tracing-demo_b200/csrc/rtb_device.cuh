@@ -868,46 +868,29 @@ __device__ __forceinline__ Fresnel refraction(const Ray &r, V3 n, V3 nl, float n
 
 // ---------------------------------------------------------------------------------------------
 // Counter-based RNG: Philox4x32-10, key = (pixel, sample), counter = (block, seed_lo, seed_hi, 0).
-// Replaces the reference's per-row erand48 stream (erand48.h:53-81, MainWindow.cpp:273), which
-// is inherently sequential; statistical parity only (oracle/rt_oracle.cpp mirrors this stream
-// in its ORACLE_RNG_COUNTER mode so paths can also be compared one to one).
+// Replaces the reference's per-row erand48 stream (erand48.h:53-81, MainWindow.cpp:273), which is
+// inherently sequential; statistical parity only (oracle/rt_oracle.cpp mirrors this stream in its
+// ORACLE_RNG_COUNTER mode so paths can also be compared one to one).
+// ONE block per traced ray: block 0 of a sample carries the pixel jitter (slots 0, 1), block k belongs to the
+// k-th ray of the sample, and the four values are addressed by slot -- 0 Russian roulette, 1 p_type, 2 / 3 the
+// hemisphere pair, 2 the reflect-or-transmit test.  Every lane computes its block at the same point of the
+// loop; with a sequential stream each lane refilled at its own time and the ten rounds ran up to four times
+// per warp and vertex, from an inlined copy at every draw site.
 // ---------------------------------------------------------------------------------------------
-struct Philox
+__device__ __forceinline__ uint4 philoxBlock(uint32_t key0, uint32_t key1, uint32_t block, uint64_t seed)
 {
-    uint32_t key0, key1, c0, c1, c2;
-    uint32_t buf[4];
-    int used;
-    __device__ __forceinline__ void seed(uint64_t s, uint32_t pixel, uint32_t sample)
-    {
-        key0 = pixel; key1 = sample;
-        c0 = 0; c1 = (uint32_t)s; c2 = (uint32_t)(s >> 32);
-        used = 4;
-    }
-    __device__ __forceinline__ void refill()
-    {
-        uint32_t x0 = c0, x1 = c1, x2 = c2, x3 = 0, k0 = key0, k1 = key1;
+    uint32_t x0 = block, x1 = (uint32_t)seed, x2 = (uint32_t)(seed >> 32), x3 = 0, k0 = key0, k1 = key1;
 #pragma unroll
-        for (int r = 0; r < 10; r++)
-        {
-            const uint32_t hi0 = __umulhi(0xD2511F53u, x0), lo0 = 0xD2511F53u * x0;
-            const uint32_t hi1 = __umulhi(0xCD9E8D57u, x2), lo1 = 0xCD9E8D57u * x2;
-            const uint32_t n0 = hi1 ^ x1 ^ k0, n2 = hi0 ^ x3 ^ k1;
-            x0 = n0; x1 = lo1; x2 = n2; x3 = lo0;
-            k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-        }
-        buf[0] = x0; buf[1] = x1; buf[2] = x2; buf[3] = x3;
-        c0++;
-        used = 0;
-    }
-    __device__ __forceinline__ float next()
+    for (int r = 0; r < 10; r++)
     {
-        if (used == 4) refill();
-        uint32_t v;
-        // select without dynamic register-array indexing
-        v = used == 0 ? buf[0] : (used == 1 ? buf[1] : (used == 2 ? buf[2] : buf[3]));
-        used++;
-        return (float)(v >> 8) * (1.0f / 16777216.0f);
+        const uint32_t hi0 = __umulhi(0xD2511F53u, x0), lo0 = 0xD2511F53u * x0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, x2), lo1 = 0xCD9E8D57u * x2;
+        const uint32_t n0 = hi1 ^ x1 ^ k0, n2 = hi0 ^ x3 ^ k1;
+        x0 = n0; x1 = lo1; x2 = n2; x3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }
-};
+    return make_uint4(x0, x1, x2, x3);
+}
+__device__ __forceinline__ float uniform01(uint32_t v) { return (float)(v >> 8) * (1.0f / 16777216.0f); }
 
 } // namespace rtb

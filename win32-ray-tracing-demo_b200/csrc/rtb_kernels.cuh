@@ -396,11 +396,27 @@ k_whitted_tree(const __grid_constant__ DScene S, const __grid_constant__ FramePa
 #define RTB_MC_STACK 32
 struct McItem { V3 o, d, T; int depth; };
 
+#ifndef RTB_MC_MIN_CTAS
+#define RTB_MC_MIN_CTAS 5 // 96 registers
+#endif
+#ifndef RTB_MC_REFERENCE_TRIG
+#define RTB_MC_REFERENCE_TRIG 0 // 1: phi = acosf(r2), cosf(phi), sinf(phi), cosf(theta), sinf(theta) literally (MainWindow.cpp:190-197)
+#endif
+
 template <class Probe>
-__global__ void __launch_bounds__(RTB_CTA_THREADS) // register-capped variants (4/6/8 CTAs per SM) measured slower
+__global__ void __launch_bounds__(RTB_CTA_THREADS, RTB_MC_MIN_CTAS)
 k_montecarlo(const __grid_constant__ DScene S, const __grid_constant__ FrameParams F, float *__restrict__ out,
              Counters *__restrict__ counters)
 {
+    // Materials are indexed by the HIT, i.e. per lane: out of the constant bank every distinct index is a pass of its own
+    // (ncu: the address-divergence unit 33 % busy); shared memory serves them in one.
+    __shared__ rtb_material smat[RTB_MAX_INLINE_MATS];
+    {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(S.mats);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(smat);
+        for (int i = threadIdx.x; i < S.n_materials * (int)(sizeof(rtb_material) / 4); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
     int x, lr, y;
     unsigned int tile;
     const long long t_start = clock64();
@@ -414,7 +430,6 @@ k_montecarlo(const __grid_constant__ DScene S, const __grid_constant__ FramePara
         const float inv = 1.0f / F.samples;
         V3 acc = v3(0, 0, 0);
         V3 sum = v3(0, 0, 0), sumsq = v3(0, 0, 0); // RTB_OUTPUT_MOMENTS: plain sums over this launch's samples
-        Philox rng;
         McItem stack[RTB_MC_STACK];
         // ONE loop over ray segments: a lane whose path has ended accumulates the sample and starts its next
         // sample in the same iteration, so the warp never waits at a per-sample reconvergence point for its
@@ -422,102 +437,111 @@ k_montecarlo(const __grid_constant__ DScene S, const __grid_constant__ FramePara
         // was ~30 %).  Per-sample arithmetic and the accumulation order are unchanged.
         int s = F.sample_first, depth = 0, sp = 0; // a sample shard renders [sample_first, sample_end) of F.samples
         bool fresh = true;
+        const uint32_t pixel = (uint32_t)(y * F.width + x);
+        uint32_t block = 0; // Philox block of the next ray of this sample
         Ray r;
         r.o = v3(0, 0, 0); r.d = v3(0, 0, 1);
         V3 L = v3(0, 0, 0), T = v3(1, 1, 1);
+        while (s < F.sample_end)
         {
-            while (s < F.sample_end)
+            if (fresh)
             {
-                if (fresh)
-                {
-                    rng.seed(F.seed, (uint32_t)(y * F.width + x), (uint32_t)s);
-                    const float j1 = rng.next(), j2 = rng.next();
-                    const float sx = (x + j1) * dx, sy = 1 - (y + j2) * dy;
-                    r = generateRay(F.cam, sx, sy);
-                    L = v3(0, 0, 0); T = v3(1, 1, 1);
-                    depth = 0; sp = 0;
-                    fresh = false;
-                }
-                bool alive = false; // does the current path continue with (r, T, depth)?
-                rays++;
-                Hit h;
-                if (sceneIntersect(S, r, h, pr))
-                {
-                    const rtb_material &m = S.mats[h.mat];
-                    const V3 n = h.n;
-                    const V3 nl = (dot(n, r.d) < 0) ? n : n * -1;
-                    V3 local = matLocal(m, r, h.pos, n);
-                    const V3 emission = matEmission(m, h.pos);
-                    const float maxColor = (local.x + local.y + local.z) * 0.333333f;
-                    bool stop = false;
-                    if (++depth > F.setting.max_depth) stop = true;
-                    if (!stop && depth > F.setting.termination_depth)
-                    {
-                        if (rng.next() < maxColor) local = local * (1 / maxColor);
-                        else stop = true;
-                    }
-                    if (!stop && depth > RTB_MAX_DEPTH) stop = true;
-                    if (stop) L = L + mul(T, emission);
-                    else
-                    {
-                        const float p_type = rng.next();
-                        const float dif = m.diffusiveness, ref = m.reflectiveness, rfr = m.refractiveness;
-                        if (dif > 0 && p_type < dif)
-                        { // uniform hemisphere about nl, unit weight (MainWindow.cpp:185-200)
-                            const float r1 = rng.next(), r2 = rng.next();
-                            const float theta = 2 * PI_F * r1;
-                            const float phi = acosf(r2);
-                            const V3 w = nl;
-                            const V3 u = (fabsf(w.x) >= 0.1f) ? normalize(cross(v3(0, 1, 0), w)) : normalize(cross(v3(1, 0, 0), w));
-                            const V3 v = cross(w, u);
-                            const V3 dir = u * (cosf(theta) * sinf(phi)) + v * (sinf(theta) * sinf(phi)) + w * cosf(phi);
-                            L = L + mul(T, emission); T = mul(T, local);
-                            r.o = h.pos; r.d = dir; alive = true;
-                        }
-                        else if (ref > 0 && p_type >= dif && p_type <= dif + ref)
-                        {
-                            L = L + mul(T, emission); T = mul(T, local);
-                            const V3 v = r.d - nl * 2 * dot(nl, r.d);
-                            r.o = h.pos; r.d = v; alive = true;
-                        }
-                        else if (rfr > 0 && p_type > dif + ref)
-                        {
-                            const Fresnel f = refraction(r, n, nl, m.refractive_index);
-                            if (f.tir)
-                            {
-                                L = L + mul(T, emission); T = mul(T, local);
-                                r.o = h.pos; r.d = f.refl; alive = true;
-                            }
-                            else if (depth > F.setting.single_tracing_depth)
-                            {
-                                if (rng.next() < f.P) { T = T * f.RP; r.d = f.refl; }
-                                else { T = T * f.TP; r.d = f.tdir; }
-                                r.o = h.pos; alive = true;
-                            }
-                            else
-                            {
-                                if (sp < RTB_MC_STACK)
-                                {
-                                    stack[sp].o = h.pos; stack[sp].d = f.refl; stack[sp].T = T * f.Re; stack[sp].depth = depth; sp++;
-                                }
-                                T = T * f.Tr; r.o = h.pos; r.d = f.tdir; alive = true;
-                            }
-                        }
-                        else L = L + mul(T, emission); // "impossible to reach" tail, MainWindow.cpp:247-248
-                    }
-                }
-                if (alive) continue;
-                if (sp > 0)
-                {
-                    --sp;
-                    r.o = stack[sp].o; r.d = stack[sp].d; T = stack[sp].T; depth = stack[sp].depth;
-                    continue;
-                }
-                acc = acc + L * inv; // MainWindow.cpp:288
-                if (F.moments) { sum = sum + L; sumsq = sumsq + mul(L, L); }
-                s++;
-                fresh = true;
+                const uint4 j = philoxBlock(pixel, (uint32_t)s, 0u, F.seed);
+                const float sx = (x + uniform01(j.x)) * dx, sy = 1 - (y + uniform01(j.y)) * dy; // MainWindow.cpp:281-284
+                r = generateRay(F.cam, sx, sy);
+                L = v3(0, 0, 0); T = v3(1, 1, 1);
+                depth = 0; sp = 0; block = 1;
+                fresh = false;
             }
+            const uint4 u = philoxBlock(pixel, (uint32_t)s, block++, F.seed); // this ray's draws, by slot
+            bool alive = false; // does the current path continue with (r, T, depth)?
+            rays++;
+            Hit h;
+            if (sceneIntersect(S, r, h, pr))
+            {
+                const rtb_material &m = smat[h.mat];
+                const V3 n = h.n;
+                const V3 nl = (dot(n, r.d) < 0) ? n : n * -1;
+                V3 local = matLocal(m, r, h.pos, n);
+                const V3 emission = matEmission(m, h.pos);
+                const float maxColor = (local.x + local.y + local.z) * 0.333333f;
+                bool stop = false;
+                if (++depth > F.setting.max_depth) stop = true;
+                if (!stop && depth > F.setting.termination_depth)
+                {
+                    if (uniform01(u.x) < maxColor) local = local * (1 / maxColor);
+                    else stop = true;
+                }
+                if (!stop && depth > RTB_MAX_DEPTH) stop = true;
+                if (stop) L = L + mul(T, emission);
+                else
+                {
+                    const float p_type = uniform01(u.y);
+                    const float dif = m.diffusiveness, ref = m.reflectiveness, rfr = m.refractiveness;
+                    if (dif > 0 && p_type < dif)
+                    { // uniform hemisphere about nl, unit weight (MainWindow.cpp:185-200)
+                        const float r1 = uniform01(u.z), r2 = uniform01(u.w);
+                        const float theta = 2 * PI_F * r1;
+#if RTB_MC_REFERENCE_TRIG
+                        const float phi = acosf(r2);
+                        const float ct = cosf(theta), st = sinf(theta), cp = cosf(phi), sn = sinf(phi);
+#else
+                        // cos(acos(r2)) = r2 and sin(acos(r2)) = sqrt(1 - r2^2): the same direction to float rounding (the reference's
+                        // libm calls and CUDA's differ in the last ulps anyway; Monte-Carlo parity is statistical)
+                        float st, ct;
+                        sincosf(theta, &st, &ct);
+                        const float cp = r2, sn = sqrtf(fmaxf(1.0f - r2 * r2, 0.0f));
+#endif
+                        const V3 w = nl;
+                        const V3 uu = (fabsf(w.x) >= 0.1f) ? normalize(cross(v3(0, 1, 0), w)) : normalize(cross(v3(1, 0, 0), w));
+                        const V3 v = cross(w, uu);
+                        const V3 dir = uu * (ct * sn) + v * (st * sn) + w * cp;
+                        L = L + mul(T, emission); T = mul(T, local);
+                        r.o = h.pos; r.d = dir; alive = true;
+                    }
+                    else if (ref > 0 && p_type >= dif && p_type <= dif + ref)
+                    {
+                        L = L + mul(T, emission); T = mul(T, local);
+                        const V3 v = r.d - nl * 2 * dot(nl, r.d);
+                        r.o = h.pos; r.d = v; alive = true;
+                    }
+                    else if (rfr > 0 && p_type > dif + ref)
+                    {
+                        const Fresnel f = refraction(r, n, nl, m.refractive_index);
+                        if (f.tir)
+                        {
+                            L = L + mul(T, emission); T = mul(T, local);
+                            r.o = h.pos; r.d = f.refl; alive = true;
+                        }
+                        else if (depth > F.setting.single_tracing_depth)
+                        {
+                            if (uniform01(u.z) < f.P) { T = T * f.RP; r.d = f.refl; }
+                            else { T = T * f.TP; r.d = f.tdir; }
+                            r.o = h.pos; alive = true;
+                        }
+                        else
+                        {
+                            if (sp < RTB_MC_STACK)
+                            {
+                                stack[sp].o = h.pos; stack[sp].d = f.refl; stack[sp].T = T * f.Re; stack[sp].depth = depth; sp++;
+                            }
+                            T = T * f.Tr; r.o = h.pos; r.d = f.tdir; alive = true;
+                        }
+                    }
+                    else L = L + mul(T, emission); // "impossible to reach" tail, MainWindow.cpp:247-248
+                }
+            }
+            if (alive) continue;
+            if (sp > 0)
+            {
+                --sp;
+                r.o = stack[sp].o; r.d = stack[sp].d; T = stack[sp].T; depth = stack[sp].depth;
+                continue;
+            }
+            acc = acc + L * inv; // MainWindow.cpp:288
+            if (F.moments) { sum = sum + L; sumsq = sumsq + mul(L, L); }
+            s++;
+            fresh = true;
         }
         if (F.moments)
         {
