@@ -880,6 +880,23 @@ def test_performance_test_bounce_workload(ctx, alg):
     assert g["total_rays"] == o["total_rays"] and g["reached"].all()
 
 
+@pytest.mark.parametrize("alg", ["rgrid", "sah", "kd"])
+def test_performance_test_large_batch_one_lane_per_ray(ctx, alg):
+    """Batches beyond two warps per resident warp slot (18,944 rays) take the one-lane-per-ray kernel, smaller ones the
+    warp-per-ray kernel (k_bounce_rays<WIDE>): both must reproduce the oracle bit for bit, and agree with each other on
+    the rays they share."""
+    xy = np.random.default_rng(12).random((24000, 2), dtype=np.float32)
+    o = O.bounce("oracle", xy, 2000.0, 1.5708, 30, 30, alg, pt_builders=True)
+    big = rtb200.perf_test(xy, 2000.0, 1.5708, 30, 30, alg)
+    small = rtb200.perf_test(xy[:700], 2000.0, 1.5708, 30, 30, alg)
+    for k in ("reached", "depth", "last_id"):
+        assert np.array_equal(big[k], o[k]), k
+        assert np.array_equal(small[k], o[k][:700]), k
+    assert np.array_equal(_bits(big["last_pos"]), _bits(o["last_pos"]))
+    assert np.array_equal(_bits(small["last_pos"]), _bits(o["last_pos"][:700]))
+    assert big["total_rays"] == o["total_rays"]
+
+
 @pytest.mark.parametrize("case", ["r2000_s30", "r100_a75_s24x12"])
 def test_performance_test_program_golden(ctx, case):
     """The same workload against fixtures recorded from the compiled PerformanceTest sources themselves

@@ -1880,10 +1880,20 @@ extern "C" int rtb_bounce_rays(rtb_ctx *ctx, const rtb_scene *scene, int64_t n, 
     if (last_id) CUDA_TRY(ctx, d_id.alloc((size_t)n));
     if (last_pos) CUDA_TRY(ctx, d_pos.alloc((size_t)n * 3));
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(Counters), ctx->stream));
-    const unsigned int blocks = (unsigned int)((n + RTB_CTA_THREADS - 1) / RTB_CTA_THREADS);
+    // small batches (the reference program traces 1000 rays): one warp per ray; see k_bounce_rays
+    const int accel = scene->d.accel;
+    const bool walkable = scene->has_tunnel && (accel == RTB_ACCEL_REGULAR_GRID || accel == RTB_ACCEL_FLAT_GRID || accel == RTB_ACCEL_KD_MEDIAN || accel == RTB_ACCEL_KD_SAH);
+    static const long long wideMax = (long long)tunable("RTB_BOUNCE_WIDE_MAX", 148 * 64 * 2); // up to two warps per resident warp slot
+    const bool wide = walkable && n <= wideMax;
+    // one lane per ray: the lanes pull rays from a queue (Counters::steps doubles as its head), the grid fills the device once
+    const long long resident = 148ll * 16 * RTB_CTA_THREADS;
+    const long long threads = wide ? n * 32 : (n < resident ? n : resident);
+    const unsigned int blocks = (unsigned int)((threads + RTB_CTA_THREADS - 1) / RTB_CTA_THREADS);
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
-    k_bounce_rays<<<blocks, RTB_CTA_THREADS, 0, ctx->stream>>>(scene->d, (long long)n, d_rays.p, max_depth, d_ok.p, d_depth.p, d_id.p,
-                                                               d_pos.p, &ctx->d_counters->rays);
+    if (wide) k_bounce_rays<true><<<blocks, RTB_CTA_THREADS, 0, ctx->stream>>>(scene->d, (long long)n, d_rays.p, max_depth, d_ok.p, d_depth.p, d_id.p,
+                                                                             d_pos.p, &ctx->d_counters->rays, &ctx->d_counters->steps);
+    else k_bounce_rays<false><<<blocks, RTB_CTA_THREADS, 0, ctx->stream>>>(scene->d, (long long)n, d_rays.p, max_depth, d_ok.p, d_depth.p, d_id.p,
+                                                                           d_pos.p, &ctx->d_counters->rays, &ctx->d_counters->steps);
     CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
     CUDA_TRY(ctx, cudaEventRecord(scene->last_use, ctx->stream));

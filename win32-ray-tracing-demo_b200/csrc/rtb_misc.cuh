@@ -159,14 +159,24 @@ k_intersect_rays(const __grid_constant__ DScene S, long long n, const float *__r
 // PerformanceTest workload (reference src/PerformanceTest/main.cpp:29-59): mirror-reflect each ray until
 // it hits a PLANE geometry (the plane closing the tunnel exit), misses, or exceeds max_depth.
 // ---------------------------------------------------------------------------------------------
+// WIDE = false: one lane per ray (batches that fill the device).  WIDE = true: one WARP per ray -- the 32 lanes walk the
+// accelerator in lock step and test 32 triangles of a leaf / cell list at once (nearestInList<.., WIDE>), as in the
+// warp-per-pixel render tier: the reference program's own batch is 1000 rays, which as 1000 threads occupies 8 CTAs and
+// takes as long as its longest 200-bounce chain walked by one lane; as 1000 warps it fills the device.  Results are
+// identical (same arithmetic; ties in a list go to the earliest position).  k-d trees and grids only.
+template <bool WIDE>
 __global__ void __launch_bounds__(RTB_CTA_THREADS)
 k_bounce_rays(const __grid_constant__ DScene S, long long n, const float *__restrict__ rays, int max_depth,
               int *__restrict__ reached, int *__restrict__ depth_out, int *__restrict__ last_id, float *__restrict__ last_pos,
-              unsigned long long *__restrict__ total_rays)
+              unsigned long long *__restrict__ total_rays, unsigned long long *__restrict__ next_ray)
 {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool writer = !WIDE || (threadIdx.x & 31) == 0;
     unsigned int traced = 0;
-    if (i < n)
+    // One lane per ray: the chains are 1 .. 200 bounces long (35 on average), so a lane that has finished its ray takes the
+    // next one from a queue (`next_ray`, one atomic per ray) instead of idling until the longest chain of its warp ends.
+    // The launch is sized to the device, not to the batch.  Rays are independent: the order changes no result.
+    for (long long i = WIDE ? (t >> 5) : (long long)atomicAdd(next_ray, 1ull); i < n; i = WIDE ? n : (long long)atomicAdd(next_ray, 1ull))
     {
         Ray r;
         r.o = v3(rays[6 * i], rays[6 * i + 1], rays[6 * i + 2]);
@@ -180,7 +190,14 @@ k_bounce_rays(const __grid_constant__ DScene S, long long n, const float *__rest
         {
             Hit h;
             traced++;
-            if (!sceneIntersect(S, r, h, pr, ctx)) { id = -1; break; }
+            bool hit;
+            if (WIDE)
+                hit = sceneIntersectWith(S, r, h, pr, [&](int &tri, float &tt, V3 &nn) {
+                    if (S.accel == RTB_ACCEL_REGULAR_GRID || S.accel == RTB_ACCEL_FLAT_GRID) return gridIntersect<true>(S, r, tri, tt, nn, pr);
+                    return kdIntersect<true>(S, r, tri, tt, nn, pr);
+                });
+            else hit = sceneIntersect(S, r, h, pr, ctx);
+            if (!hit) { id = -1; break; }
             id = h.id; pos = h.pos;
             const V3 nl = (dot(h.n, r.d) < 0) ? h.n : h.n * -1;
             if (++depth > max_depth) break;
@@ -189,11 +206,15 @@ k_bounce_rays(const __grid_constant__ DScene S, long long n, const float *__rest
             r.o = h.pos;
             r.d = v;
         }
-        if (reached) reached[i] = ok;
-        if (depth_out) depth_out[i] = depth;
-        if (last_id) last_id[i] = id;
-        if (last_pos) { last_pos[3 * i] = pos.x; last_pos[3 * i + 1] = pos.y; last_pos[3 * i + 2] = pos.z; }
+        if (writer)
+        {
+            if (reached) reached[i] = ok;
+            if (depth_out) depth_out[i] = depth;
+            if (last_id) last_id[i] = id;
+            if (last_pos) { last_pos[3 * i] = pos.x; last_pos[3 * i + 1] = pos.y; last_pos[3 * i + 2] = pos.z; }
+        }
     }
+    if (!writer) traced = 0;
     traced = __reduce_add_sync(0xffffffffu, traced);
     if ((threadIdx.x & 31) == 0 && traced) atomicAdd(total_rays, (unsigned long long)traced);
 }
