@@ -732,8 +732,10 @@ struct BackgroundChecks
     std::mutex m;
     int code = RTB_OK;
     std::string msg;
+    bool enabled = true; // false: the caller has validated this very flat scene already (rtb_multi_scene_upload: replicas)
     template <class Fn> void run(Fn fn) // fn() -> {code, message}; the first failure is kept
     {
+        if (!enabled) return;
         threads.emplace_back([this, fn]() {
             const std::pair<int, const char *> r = fn();
             if (r.first != RTB_OK)
@@ -770,7 +772,13 @@ struct UploadLaps
     ~UploadLaps() { if (on) fprintf(stderr, "rtb_scene_upload:%s\n", text.c_str()); }
 };
 
-extern "C" int rtb_scene_upload(rtb_ctx *ctx, const rtb_flat_scene *f, rtb_scene **out)
+static int sceneUpload(rtb_ctx *ctx, const rtb_flat_scene *f, rtb_scene **out, bool validate);
+
+extern "C" int rtb_scene_upload(rtb_ctx *ctx, const rtb_flat_scene *f, rtb_scene **out) { return sceneUpload(ctx, f, out, true); }
+
+// validate = false skips the whole-stream index / structure checks: only for a flat scene that has just passed them on another
+// device of the same rtb_multi (the cheap header checks always run)
+static int sceneUpload(rtb_ctx *ctx, const rtb_flat_scene *f, rtb_scene **out, bool validate)
 {
     UploadLaps laps;
     if (!ctx || !f || !out) return fail(ctx, RTB_ERR_INVALID, "rtb_scene_upload: null argument");
@@ -813,6 +821,7 @@ extern "C" int rtb_scene_upload(rtb_ctx *ctx, const rtb_flat_scene *f, rtb_scene
 
     int rc = RTB_OK;
     BackgroundChecks checks;
+    checks.enabled = validate;
     auto bail = [&](int code) { checks.join(); rtb_scene_free(ctx, s); return code; };
     laps.lap("header");
 
@@ -826,7 +835,7 @@ extern "C" int rtb_scene_upload(rtb_ctx *ctx, const rtb_flat_scene *f, rtb_scene
         if (f->n_tris < 0 || (f->n_tris > 0 && (!f->tri || !f->tri_material)))
             return bail(fail(ctx, RTB_ERR_INVALID, "rtb_scene_upload: tunnel triangle streams missing"));
         uint32_t maxMat = 0; // negative ids wrap to huge values
-        for (int i = 0; i < f->n_tris; i++) maxMat = (uint32_t)f->tri_material[i] > maxMat ? (uint32_t)f->tri_material[i] : maxMat;
+        for (int i = 0; validate && i < f->n_tris; i++) maxMat = (uint32_t)f->tri_material[i] > maxMat ? (uint32_t)f->tri_material[i] : maxMat;
         if (f->n_tris > 0 && maxMat >= (uint32_t)f->n_materials)
             return bail(fail(ctx, RTB_ERR_INVALID, "rtb_scene_upload: triangle material out of range"));
         const size_t nTris = (size_t)f->n_tris;
@@ -953,13 +962,13 @@ extern "C" int rtb_scene_upload(rtb_ctx *ctx, const rtb_flat_scene *f, rtb_scene
             if ((int64_t)f->n_tris != (f->n_cx_path - 1) * perSegment)
                 return bail(fail(ctx, RTB_ERR_INVALID, "rtb_scene_upload: convex accelerator needs (n_cx_path - 1) * 2 * n_cx_edges triangles in segment order"));
             const size_t tableCells = (size_t)f->cx_table_size * f->cx_table_size;
-            for (size_t i = 0; i < tableCells; i++)
+            for (size_t i = 0; validate && i < tableCells; i++)
             {
                 const int st = f->cx_cell_status[i], b = f->cx_cell_range[2 * i], e = f->cx_cell_range[2 * i + 1];
                 if (st > 2 || (st == 1 && (b < 0 || e >= f->n_cx_edges)))
                     return bail(fail(ctx, RTB_ERR_INVALID, "rtb_scene_upload: bad convex cell table"));
             }
-            if (f->accel == RTB_ACCEL_CONVEX)
+            if (f->accel == RTB_ACCEL_CONVEX && validate)
                 for (int64_t i = 0; i < (int64_t)100 * 360 * perSegment; i++)
                     if (f->cx_order[i] >= perSegment) return bail(fail(ctx, RTB_ERR_INVALID, "rtb_scene_upload: bad convex order table"));
             d.cx_n_path = f->n_cx_path; d.cx_n_edges = f->n_cx_edges; d.cx_width = f->cx_width; d.cx_height = f->cx_height;
@@ -1657,11 +1666,17 @@ extern "C" int rtb_multi_scene_upload(rtb_multi *m, const rtb_flat_scene *flat, 
     rtb_multi_scene *s = new rtb_multi_scene();
     s->s.assign(n, nullptr);
     std::vector<int> rc(n, RTB_OK);
-    // one uploader per device: staging, the H2D copies and the packing kernels of the replicas run side by side
-    std::vector<std::thread> workers;
-    for (size_t i = 1; i < n; i++) workers.emplace_back([&, i]() { rc[i] = rtb_scene_upload(m->ctx[i], flat, &s->s[i]); });
-    rc[0] = rtb_scene_upload(m->ctx[0], flat, &s->s[0]);
-    for (std::thread &t : workers) t.join();
+    // The first device's upload validates the flat scene (whole-stream index / structure checks, on worker threads of its
+    // own); the replicas then upload side by side -- one uploader thread per device for staging, H2D copies and packing
+    // kernels -- without repeating the checks on the same host arrays (8 devices: 1.5 -> ~0.9 ms).
+    rc[0] = sceneUpload(m->ctx[0], flat, &s->s[0], true);
+    if (rc[0] == RTB_OK)
+    {
+        std::vector<std::thread> workers;
+        for (size_t i = 2; i < n; i++) workers.emplace_back([&, i]() { rc[i] = sceneUpload(m->ctx[i], flat, &s->s[i], false); });
+        if (n > 1) rc[1] = sceneUpload(m->ctx[1], flat, &s->s[1], false);
+        for (std::thread &t : workers) t.join();
+    }
     for (size_t i = 0; i < n; i++)
         if (rc[i] != RTB_OK)
         {
