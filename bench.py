@@ -364,8 +364,9 @@ def run_b200(args, wl_name):
                       and (args.mc_shard == "samples" or (W * H // 32) // world < 8 * 4736))
     if sample_sharded:
         col_block = 0
-    peer = world > 1 and args.gather == "peer" and not sample_sharded
-    layout = rtb200.LAYOUT_GLOBAL if peer else rtb200.LAYOUT_ROWMAJOR
+    peer = world > 1 and args.gather in ("peer", "scatter") and not sample_sharded
+    scatter = peer and args.gather == "scatter"  # render into a local shard, then ONE streaming copy into the owner's frame
+    layout = rtb200.LAYOUT_GLOBAL if (peer and not scatter) else rtb200.LAYOUT_ROWMAJOR
     if sample_sharded:
         s_first, s_count = rtb200.sample_shard(spp, rank, world)
         frame = rtb200.make_frame(W, H, samples=spp, seed=0, sample_first=s_first, sample_count=s_count)
@@ -395,6 +396,9 @@ def run_b200(args, wl_name):
         dist.broadcast_object_list(handle, src=0)
         mapped = owner_frame if rank == 0 else ctx.ipc_open(handle[0])
         target = mapped
+        if scatter:
+            local_buf = torch.zeros((rows_max, Wl, 3), dtype=torch.float32, device=dev_t)
+            target = local_buf.data_ptr()
         token = torch.zeros(1, dtype=torch.int32, device=dev_t)
     else:
         image = torch.zeros((H, W, 3), dtype=torch.float32, device=dev_t)
@@ -418,6 +422,8 @@ def run_b200(args, wl_name):
         if sample_sharded:
             dist.reduce(image, dst=0, op=dist.ReduceOp.SUM)  # rank 0: the frame; every sample carries the weight 1 / spp
         elif peer:
+            if scatter:
+                ctx.scatter_shard_device(local_buf.data_ptr(), mapped, shard, stream)
             dist.all_reduce(token)  # every rank's tiles are in the owner's frame when this completes
         else:
             dist.all_gather_into_tensor(gathered.view(world * rows_max, Wl, 3), local_buf)
@@ -459,7 +465,7 @@ def run_b200(args, wl_name):
     # kernels of this library per step, as counted by the library for this frame (rtb_stats.n_launches): the render
     # kernels (1-3: throughput walk + up to two latency tiers) + 3 tile-order kernels (+ the unshard kernel with --gather nccl)
     kst = render(want_stats=True)
-    launches_per_step = int(kst["n_launches"]) + (1 if (world > 1 and not peer) else 0)
+    launches_per_step = int(kst["n_launches"]) + (1 if (world > 1 and (not peer or scatter)) else 0)
     close_step()
 
     sampler = ClockSampler(local) if rank == 0 else None
@@ -671,7 +677,9 @@ def run_b200(args, wl_name):
                 sharding = f"SAMPLE shards: every rank renders every pixel with {spp} / {world} of the samples; NCCL reduce (sum) onto rank 0 every step"
             else:
                 sharding += ("; every rank stores its tiles straight into rank 0's device frame over NVLink (CUDA IPC mapping, RTB_LAYOUT_GLOBAL), "
-                             "a one-word NCCL all-reduce closes the step" if peer else "; NCCL all_gather_into_tensor + unshard kernel every step")
+                             "a one-word NCCL all-reduce closes the step" if (peer and not scatter) else
+                             "; every rank renders into a local shard and moves it with one streaming copy kernel into rank 0's device frame over NVLink (CUDA IPC mapping), "
+                             "a one-word NCCL all-reduce closes the step" if scatter else "; NCCL all_gather_into_tensor + unshard kernel every step")
         line = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
@@ -705,7 +713,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="p5_sah_4k", choices=sorted(WORKLOADS))
-    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"])
+    ap.add_argument("--gather", default="peer", choices=["peer", "scatter", "nccl"])
     ap.add_argument("--mc-shard", default="auto", choices=["auto", "samples", "pixels"])
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -345,6 +345,11 @@ int rtb_device_download(rtb_ctx *ctx, const void *device_ptr, void *host, size_t
 int rtb_ipc_export(rtb_ctx *ctx, void *device_ptr, unsigned char handle[RTB_IPC_HANDLE_BYTES]);
 int rtb_ipc_open(rtb_ctx *ctx, const unsigned char handle[RTB_IPC_HANDLE_BYTES], void **mapped);
 int rtb_ipc_close(rtb_ctx *ctx, void *mapped);
+/* Alternative to rendering straight into the mapped frame: render the shard into a LOCAL device buffer (row-major layout of
+ * rtb_render_device), then move it to its place in the whole frame with one streaming pass of 128-bit copies on `stream`
+ * (the frame may be peer-mapped: one bulk NVLink transfer instead of tile-sized stores issued while the kernels render).
+ * `frame` describes the shard (rank / world / row_block / col_block); float frames only.                              */
+int rtb_scatter_shard_device(rtb_ctx *ctx, const void *local, void *frame_buffer, const rtb_frame *frame, void *stream);
 
 /* B: ONE host thread drives n devices (SURVEY 8b threading row; the drop-in behind Scripts.h:11-12 RenderProc).
  *    rtb_multi_render shards the frame over the devices (tile rows up to 4 devices, column blocks above), every device

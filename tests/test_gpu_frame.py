@@ -89,6 +89,27 @@ def test_global_layout_device_frame(ctx):
     dev.close(); s.close()
 
 
+@pytest.mark.parametrize("world,col_block", [(2, 0), (4, 0), (8, 32), (4, 16)])
+def test_scatter_shard_into_whole_frame(ctx, world, col_block):
+    """rtb_scatter_shard_device: a rank's LOCAL shard image moved to its place in the whole frame by one streaming copy --
+    the alternative to RTB_LAYOUT_GLOBAL's stores from inside the render kernels; all ranks together give the whole frame."""
+    import torch
+    w, h = 512, 96
+    s = PresetScene(5, "sah", 24)
+    dev = ctx.upload(s.flat)
+    whole, _ = dev.render(s.camera, s.setting, rtb200.make_frame(w, h))
+    image = torch.full((h, w, 3), -1.0, dtype=torch.float32, device="cuda:0")
+    stream = torch.cuda.current_stream().cuda_stream
+    for rank in range(world):
+        fr = rtb200.make_frame(w, h, rank=rank, world=world, row_block=8, col_block=col_block)
+        local = torch.zeros((rtb200.shard_rows(fr), rtb200.shard_width(fr), 3), dtype=torch.float32, device="cuda:0")
+        dev.render_device(s.camera, s.setting, fr, local.data_ptr(), stream)
+        ctx.scatter_shard_device(local.data_ptr(), image.data_ptr(), fr, stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(_bits(image.cpu().numpy()), _bits(whole))
+    dev.close(); s.close()
+
+
 def test_global_layout_monte_carlo_and_reference_order(ctx):
     w, h, world = 64, 48, 3
     s = PresetScene(2)

@@ -116,7 +116,7 @@ ABI_SYMBOLS = ["rtb_init", "rtb_shutdown", "rtb_last_error", "rtb_abi_version", 
                "rtb_scene_upload", "rtb_scene_free", "rtb_scene_device_bytes", "rtb_scene_upload_bytes", "rtb_scene_grid_hash", "rtb_scene_kd_download", "rtb_render",
                "rtb_render_device", "rtb_unshard_device", "rtb_trace_primary", "rtb_intersect_rays", "rtb_bounce_rays",
                "rtb_selftest_pretest", "rtb_kd_validate", "rtb_forget_schedule", "rtb_set_progress", "rtb_multi_set_progress",
-               "rtb_device_alloc", "rtb_device_free", "rtb_device_download", "rtb_ipc_export", "rtb_ipc_open", "rtb_ipc_close",
+               "rtb_device_alloc", "rtb_device_free", "rtb_device_download", "rtb_ipc_export", "rtb_ipc_open", "rtb_ipc_close", "rtb_scatter_shard_device",
                "rtb_multi_init", "rtb_multi_shutdown", "rtb_multi_count", "rtb_multi_ctx", "rtb_multi_last_error",
                "rtb_multi_scene_upload", "rtb_multi_scene_free", "rtb_multi_scene_upload_bytes", "rtb_multi_render"]
 
@@ -166,6 +166,7 @@ def cuda_lib():
         lib.rtb_ipc_export.argtypes = [vp, vp, C.c_char_p]
         lib.rtb_ipc_open.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
         lib.rtb_ipc_close.argtypes = [vp, vp]
+        lib.rtb_scatter_shard_device.argtypes = [vp, vp, vp, C.POINTER(Frame), vp]
         lib.rtb_multi_init.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(vp)]
         lib.rtb_multi_shutdown.argtypes = [vp]
         lib.rtb_multi_count.argtypes = [vp]
@@ -457,6 +458,11 @@ class Context:
         p = C.c_void_p()
         self._check(self._lib.rtb_ipc_open(self._h, C.create_string_buffer(bytes(handle), IPC_HANDLE_BYTES), C.byref(p)), "rtb_ipc_open")
         return p.value
+
+    def scatter_shard_device(self, local_ptr, frame_ptr, frame, stream=0):
+        """rtb_scatter_shard_device: a rank's local shard image -> its place in the whole (possibly peer-mapped) frame."""
+        self._check(self._lib.rtb_scatter_shard_device(self._h, C.c_void_p(local_ptr), C.c_void_p(frame_ptr), C.byref(frame), C.c_void_p(stream)),
+                    "rtb_scatter_shard_device")
 
     def ipc_close(self, ptr):
         self._check(self._lib.rtb_ipc_close(self._h, C.c_void_p(ptr)), "rtb_ipc_close")

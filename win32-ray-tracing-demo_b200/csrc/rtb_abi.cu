@@ -19,7 +19,9 @@
 #include "rtb_build_kd.cuh"
 
 #ifndef RTB_SPLIT_MAX_TILES
-#define RTB_SPLIT_MAX_TILES 131072 // shards up to 4.2 Mpixel walk their latency-critical tiles with 4 warps each
+#define RTB_SPLIT_MAX_TILES 200000 // shards up to 6.4 Mpixel (half a 4K frame) count as "small": their latency-critical tiles go
+                                   // to the 8 / 16-lane tier (k-d) or to 4 warps of 8 lanes (grids).  1/2 shard of the 4K SAH frame, kernel
+                                   // ms: resumable tier 3.07, no tier 3.51, 8-lane tier 2.80 (profiles/r02_sweep_tiers.log)
 #endif
 #ifndef RTB_HEAVY_BUCKETS_SMALL
 #define RTB_HEAVY_BUCKETS_SMALL 4   // quarter-octaves below the heaviest tile: 4 / 6 / 10 -> slowest 1/8 SAH shard 1.18 / 1.24 / 1.24 ms
@@ -78,7 +80,11 @@ static int heavyLimit(int n_tiles)
     static const int forced = (int)tunable("RTB_HEAVY_LIMIT", -1);
     if (forced >= 0) return forced;
     if (n_tiles <= RTB_SMALL_FRAME_TILES) return 0;
-    return n_tiles / (n_tiles <= splitMaxTiles() ? heavyFractionSmall() : RTB_HEAVY_FRACTION);
+    // A whole 4K frame is throughput-bound: heaviest-first order alone is best there, any tier costs more warp-instructions than
+    // its shorter tail saves (4K frame, kernel ms with / without the resumable tier: SAH 5.03 / 4.70, k-d median 12.45 / 12.18,
+    // flat grid 19.5 / 18.8)
+    if (n_tiles > splitMaxTiles()) return 0;
+    return n_tiles / heavyFractionSmall();
 }
 
 using namespace rtb;
@@ -1806,6 +1812,28 @@ extern "C" int rtb_unshard_cols_device(rtb_ctx *ctx, const void *gathered, void 
     if (bx > 8) bx = 8;
     k_unshard_cols<<<dim3(bx, height), 256, 0, stream ? (cudaStream_t)stream : ctx->stream>>>(
         (const float *)gathered, (float *)image, width, height, world, row_block, col_block);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return RTB_OK;
+}
+
+extern "C" int rtb_scatter_shard_device(rtb_ctx *ctx, const void *local, void *frame_buffer, const rtb_frame *frame, void *stream)
+{
+    if (!ctx || !local || !frame_buffer || !frame) return fail(ctx, RTB_ERR_INVALID, "rtb_scatter_shard_device: null argument");
+    rtb_frame plain = *frame;
+    plain.layout = RTB_LAYOUT_ROWMAJOR;
+    const int64_t rows = rtb_shard_rows(&plain), lw = rtb_shard_width(&plain);
+    if (rows < 0 || (frame->layout & (RTB_LAYOUT_REFERENCE | RTB_OUTPUT_RGB8 | RTB_OUTPUT_MOMENTS)))
+        return fail(ctx, RTB_ERR_INVALID, "rtb_scatter_shard_device: bad shard, or not a row-major float frame");
+    const int world = frame->world > 0 ? frame->world : 1, cb = colSharded(frame) ? frame->col_block : 0;
+    if (lw % 4 != 0 || (cb && (cb * 3) % 4 != 0) || frame->width % 4 != 0 || ((uintptr_t)local & 15u) || ((uintptr_t)frame_buffer & 15u))
+        return fail(ctx, RTB_ERR_UNSUPPORTED, "rtb_scatter_shard_device: widths must be multiples of 4 pixels and the buffers 16-byte aligned");
+    if (rows == 0) return RTB_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    unsigned int bx = (unsigned int)((lw * 3 / 4 + 255) / 256);
+    if (bx == 0) bx = 1;
+    if (bx > 8) bx = 8;
+    k_scatter_shard<<<dim3(bx, (unsigned int)rows), 256, 0, stream ? (cudaStream_t)stream : ctx->stream>>>(
+        (const float *)local, (float *)frame_buffer, frame->width, frame->height, world, frame->rank, normRowBlock(frame), cb, (int)lw, (int)rows);
     CUDA_TRY(ctx, cudaGetLastError());
     return RTB_OK;
 }

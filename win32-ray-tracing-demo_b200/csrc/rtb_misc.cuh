@@ -265,4 +265,33 @@ k_unshard_cols(const float *__restrict__ gathered, float *__restrict__ image, in
     }
 }
 
+// A rank's local shard image -> its place in the whole frame (RTB_LAYOUT_GLOBAL addressing), as ONE streaming pass of
+// 128-bit copies: the alternative to storing tile by tile into a peer-mapped frame while rendering (rtb_scatter_shard_device).
+// One thread per float4; a local row is [local_width][3] floats; column-block shards move whole col_block segments.
+__global__ void __launch_bounds__(256)
+k_scatter_shard(const float *__restrict__ local, float *__restrict__ frame, int width, int height, int world, int rank, int row_block,
+                int col_block, int local_width, int n_local_rows)
+{
+    const int lr = blockIdx.y;
+    if (lr >= n_local_rows) return;
+    int y;
+    if (col_block) y = lr;
+    else { const int lb = lr / row_block; y = (lb * world + rank) * row_block + (lr - lb * row_block); }
+    if (y >= height) return;
+    const int rowF4 = local_width * 3 / 4; // local_width % 4 == 0 (checked by the caller)
+    const float4 *src = reinterpret_cast<const float4 *>(local + (size_t)lr * local_width * 3);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rowF4; i += gridDim.x * blockDim.x)
+    {
+        int gx4 = i; // float4 index inside the frame row
+        if (col_block)
+        {
+            const int segF4 = col_block * 3 / 4, c = i / segF4, q = i - c * segF4;
+            int shift = (rank - y / row_block) % world;
+            if (shift < 0) shift += world;
+            gx4 = (c * world + shift) * segF4 + q;
+        }
+        reinterpret_cast<float4 *>(frame + (size_t)y * width * 3)[gx4] = src[i];
+    }
+}
+
 } // namespace rtb
