@@ -77,15 +77,16 @@ def test_global_layout_device_frame(ctx):
     s = PresetScene(5, "sah", 24)
     dev = ctx.upload(s.flat)
     whole, _ = dev.render(s.camera, s.setting, rtb200.make_frame(w, h))
-    image = torch.full((h, w, 3), -1.0, dtype=torch.float32, device="cuda:0")
-    stream = torch.cuda.current_stream().cuda_stream
-    for col_block in (0, 8):
-        image.fill_(-1.0)
-        for rank in range(world):
-            fr = rtb200.make_frame(w, h, rank=rank, world=world, row_block=8, col_block=col_block, layout=rtb200.LAYOUT_GLOBAL)
-            dev.render_device(s.camera, s.setting, fr, image.data_ptr(), stream)
-        torch.cuda.synchronize()
-        assert np.array_equal(_bits(image.cpu().numpy()), _bits(whole))
+    tstream = torch.cuda.Stream()  # a real stream handle (the default stream's handle 0 would select the library's own stream)
+    with torch.cuda.stream(tstream):
+        image = torch.full((h, w, 3), -1.0, dtype=torch.float32, device="cuda:0")
+        for col_block in (0, 8):
+            image.fill_(-1.0)
+            for rank in range(world):
+                fr = rtb200.make_frame(w, h, rank=rank, world=world, row_block=8, col_block=col_block, layout=rtb200.LAYOUT_GLOBAL)
+                dev.render_device(s.camera, s.setting, fr, image.data_ptr(), tstream.cuda_stream)
+            tstream.synchronize()
+            assert np.array_equal(_bits(image.cpu().numpy()), _bits(whole))
     dev.close(); s.close()
 
 
@@ -98,13 +99,14 @@ def test_scatter_shard_into_whole_frame(ctx, world, col_block):
     s = PresetScene(5, "sah", 24)
     dev = ctx.upload(s.flat)
     whole, _ = dev.render(s.camera, s.setting, rtb200.make_frame(w, h))
-    image = torch.full((h, w, 3), -1.0, dtype=torch.float32, device="cuda:0")
-    stream = torch.cuda.current_stream().cuda_stream
-    for rank in range(world):
-        fr = rtb200.make_frame(w, h, rank=rank, world=world, row_block=8, col_block=col_block)
-        local = torch.zeros((rtb200.shard_rows(fr), rtb200.shard_width(fr), 3), dtype=torch.float32, device="cuda:0")
-        dev.render_device(s.camera, s.setting, fr, local.data_ptr(), stream)
-        ctx.scatter_shard_device(local.data_ptr(), image.data_ptr(), fr, stream)
+    tstream = torch.cuda.Stream()  # a real stream handle (the default stream's handle 0 would select the library's own stream)
+    with torch.cuda.stream(tstream):
+        image = torch.full((h, w, 3), -1.0, dtype=torch.float32, device="cuda:0")
+        for rank in range(world):
+            fr = rtb200.make_frame(w, h, rank=rank, world=world, row_block=8, col_block=col_block)
+            local = torch.zeros((rtb200.shard_rows(fr), rtb200.shard_width(fr), 3), dtype=torch.float32, device="cuda:0")
+            dev.render_device(s.camera, s.setting, fr, local.data_ptr(), tstream.cuda_stream)
+            ctx.scatter_shard_device(local.data_ptr(), image.data_ptr(), fr, tstream.cuda_stream)
     torch.cuda.synchronize()
     assert np.array_equal(_bits(image.cpu().numpy()), _bits(whole))
     dev.close(); s.close()

@@ -244,6 +244,7 @@ def test_unshard_cols_kernel(ctx):
     s, dev = _scene(ctx, dict(preset=4, algorithm="sah", segments=12))
     whole, _ = dev.render(s.camera, s.setting, rtb200.make_frame(w, h))
     gathered = torch.zeros((world, h, w // world, 3), dtype=torch.float32, device="cuda:0")
+    torch.cuda.synchronize()  # the fill above ran on torch's default stream; the handle 0 below selects the library's own stream
     stream = torch.cuda.current_stream().cuda_stream
     for rank in range(world):
         fr = rtb200.make_frame(w, h, rank=rank, world=world, row_block=rb, col_block=cb)
@@ -262,6 +263,7 @@ def test_unshard_kernel(ctx):
     whole, _ = dev.render(s.camera, s.setting, rtb200.make_frame(w, h))
     rows = max(rtb200.shard_rows(rtb200.make_frame(w, h, rank=r, world=world, row_block=rb)) for r in range(world))
     gathered = torch.zeros((world, rows, w, 3), dtype=torch.float32, device="cuda:0")
+    torch.cuda.synchronize()  # the fill above ran on torch's default stream; the handle 0 below selects the library's own stream
     stream = torch.cuda.current_stream().cuda_stream
     for rank in range(world):
         fr = rtb200.make_frame(w, h, rank=rank, world=world, row_block=rb)
