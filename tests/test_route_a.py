@@ -58,12 +58,14 @@ def test_reference_scripts_render_through_the_gpu(route_a, preset, alg):
 def test_reference_monte_carlo_scripts(route_a):
     """Presets 1-3 (Default(): Monte Carlo) through the same binding: different random streams, so the image mean only
     (the statistical criteria live in test_gpu_parity.py); preset 3 reads the STL mesh with the reference's own loader."""
-    for preset, w, h, spp in ((1, 80, 60, 16), (2, 80, 60, 16), (3, 40, 30, 8)):
+    for preset, w, h, spp, tol in ((1, 160, 120, 16, 0.03), (2, 160, 120, 16, 0.06), (3, 64, 48, 16, 0.15)):
         r = run(route_a, preset, "linear", 0, w, h, spp)
         assert r["rc"] == 0, r["log"]
         ref = O.run("ref", preset, width=w, height=h, samples=spp, image=True)
         assert np.isfinite(r["image"]).all()
-        assert abs(r["image"].mean() - ref["image"].mean()) <= 0.08 * ref["image"].mean()
+        # a few thousand pixels at 16 spp: the image mean of smallpt carries a few per cent of noise (two CPU seeds differ as much)
+        rel = abs(r["image"].mean() - ref["image"].mean()) / ref["image"].mean()
+        assert rel <= tol, (preset, rel)
 
 
 def test_route_a_on_all_devices(route_a):
