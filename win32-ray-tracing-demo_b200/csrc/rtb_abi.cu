@@ -443,17 +443,8 @@ __global__ void k_pack_pairs(const uint32_t *__restrict__ refs, unsigned int n_r
 }
 
 // builds DScene::pre2 for the reference array `refs` (device) -- queued behind the copies / kernels that produce it
-// Reference arrays beyond this many entries get no pair stream: at 48 bytes per reference it would not stay in the 126 MB L2
-// (flat grid 400^3: 3.4 M references = 163 MB) and the list scans would stream it from DRAM; they scan by index instead
-// (nearestInList).  k-d median (1.06 M, 51 MB) and everything smaller keep the pair stream.
-#ifndef RTB_PAIR_STREAM_MAX_REFS
-#define RTB_PAIR_STREAM_MAX_REFS 2000000
-#endif
 static int packPairs(rtb_ctx *ctx, rtb_scene *s, const uint32_t *refs, size_t n_refs)
 {
-    static const size_t maxRefs = (size_t)tunable("RTB_PAIR_STREAM_MAX_REFS", RTB_PAIR_STREAM_MAX_REFS);
-    s->d.pre2 = nullptr;
-    if (n_refs > maxRefs) return RTB_OK;
     const size_t pairs = (n_refs + 1) / 2;
     int rc = uploadWith<float4>(ctx, s, 6 * pairs, &s->d.pre2, [](float4 *) {}, true); // zero-filled allocation
     if (rc != RTB_OK || n_refs == 0) return rc;

@@ -83,7 +83,6 @@ k_whitted_chain_sm(const __grid_constant__ DScene S, const __grid_constant__ Fra
         float dmx = 0, Lp = rtb_pre::lowBound(-FLT_MAX), Hp = rtb_pre::highBound(FLT_MAX, FLT_MAX);
         unsigned int pend = 0xffffffffu, jend = 0, lp = 0, counted = 0; // lp: current pair of the list [li, lend)
         bool tunnelHit = false;
-        const bool pairs = S.pre2 != nullptr; // false: indexed scan, lp is a list position (see nearestInList)
 
         // start the accelerator walk of ray r (reference Tunnel.cpp:1171-1197 / 833-860)
         auto beginRay = [&]() {
@@ -181,7 +180,7 @@ k_whitted_chain_sm(const __grid_constant__ DScene S, const __grid_constant__ Fra
                             const unsigned int rk = w.y + __popc(w.x & (bit - 1));
                             li = __ldg(S.g_start + rk);
                             lend = __ldg(S.g_start + rk + 1);
-                            minD = FLT_MAX; hitTri = -1; pend = 0xffffffffu; lp = pairs ? li >> 1 : li;
+                            minD = FLT_MAX; hitTri = -1; pend = 0xffffffffu; lp = li >> 1;
                             if (li == lend) gridAdvance(); // cannot happen with a well-formed directory; the pair loop needs a non-empty list
                             else st = SM_LEAF;
                         }
@@ -197,7 +196,7 @@ k_whitted_chain_sm(const __grid_constant__ DScene S, const __grid_constant__ Fra
                             lend = nd.x + (nd.y >> 2);
                             lo = enT - 0.001f; hi = exT + 0.001f;
                             Lp = rtb_pre::lowBound(lo); Hp = rtb_pre::highBound(hi, FLT_MAX);
-                            minD = FLT_MAX; hitTri = -1; pend = 0xffffffffu; lp = pairs ? li >> 1 : li;
+                            minD = FLT_MAX; hitTri = -1; pend = 0xffffffffu; lp = li >> 1;
                             if (li == lend) kdPop();
                             else st = SM_LEAF;
                         }
@@ -237,22 +236,6 @@ k_whitted_chain_sm(const __grid_constant__ DScene S, const __grid_constant__ Fra
 #pragma unroll 1
                 for (int burst = 0; burst < RTB_SM_LEAF_BURST && st == SM_LEAF; burst++)
                 {
-                    if (!pairs)
-                    { // indexed scan: one list entry per iteration
-                        const rtb_pre::PreTri P1 = loadPreTri(S.tri_pre, __ldg((GRID ? S.g_tris : S.kd_tris) + lp));
-                        pr.tri();
-                        if (!rtb_pre::sureReject<!GRID>(P1, r.o.x, r.o.y, r.o.z, r.d.x, r.d.y, r.d.z, dmx, Lp, Hp))
-                        {
-                            if (pend != 0xffffffffu) { counted = lp + 1u; jend = lend; st = SM_EXACT; }
-                            else pend = lp;
-                        }
-                        if (st == SM_LEAF && ++lp == lend)
-                        {
-                            if (pend != 0xffffffffu) { counted = lend; jend = pend + 1; st = SM_EXACT; }
-                            else listDone();
-                        }
-                        continue;
-                    }
                     const rtb_pre::PreTri2 P = loadPreTri2(S.pre2, lp);
                     const unsigned int j0 = 2u * lp, j1 = j0 + 1u;
                     const bool in0 = j0 >= li, in1 = j1 < lend;

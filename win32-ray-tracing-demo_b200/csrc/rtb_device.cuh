@@ -162,17 +162,6 @@ __device__ __forceinline__ TriData loadTri(const float4 *base, unsigned int idx)
     return t;
 }
 __device__ __forceinline__ V3 triNormal(const TriData &t) { return v3(t.q2.y, t.q2.z, t.q2.w); }
-// rejection-test record of ONE triangle, by index (the scans of accelerators too big for a pair stream: DScene::pre2 == null)
-__device__ __forceinline__ rtb_pre::PreTri loadPreTri(const float4 *base, unsigned int idx)
-{
-    const float4 *p = base + 3ull * idx;
-    const float4 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2);
-    rtb_pre::PreTri t;
-    t.ax = q0.x; t.ay = q0.y; t.az = q0.z; t.a1e = q0.w;
-    t.e1x = q1.x; t.e1y = q1.y; t.e1z = q1.z; t.ee = q1.w;
-    t.e2x = q2.x; t.e2y = q2.y; t.e2z = q2.z; t.pad = 0.f;
-    return t;
-}
 __device__ __forceinline__ rtb_pre::PreTri2 loadPreTri2(const float4 *base, unsigned int pair)
 {
     const float4 *p = base + 6ull * pair;
@@ -296,21 +285,6 @@ __device__ __forceinline__ bool nearestInList(const DScene &S, const uint32_t *r
         uint32_t counted = last; // list positions below `counted` have gone through pr.tri()
         bool multi = false;      // the fast loop stopped at a second candidate
         const uint32_t pEnd = (last + 1u) >> 1;
-        if (S.pre2 == nullptr)
-        { // INDEXED scan (warp-uniform choice, made at upload): accelerators with millions of references -- the 400^3 flat
-          // grid: 3.4 M references in lists of 2.7 -- would need a pair stream (48 bytes per reference: 163 MB) that falls out
-          // of L2, and every short list would pull two or three 96-byte pairs from DRAM; here an entry costs its 4-byte index
-          // plus a 48-byte record of the 2.2 MB per-triangle table, which stays in L1 / L2.  Same test, same deferral.
-            for (uint32_t j = first; j < last; j++)
-            {
-                const rtb_pre::PreTri P = loadPreTri(S.tri_pre, __ldg(refs + j));
-                pr.tri();
-                if (rtb_pre::sureReject<WINDOW>(P, ray.o.x, ray.o.y, ray.o.z, ray.d.x, ray.d.y, ray.d.z, dmx, Lp, Hp)) continue;
-                if (pend != 0xffffffffu) { counted = j + 1u; multi = true; break; } // a second candidate: exact scan from the first one on
-                pend = j;
-            }
-        }
-        else
         for (uint32_t p = first >> 1; p < pEnd; p++)
         {
             const rtb_pre::PreTri2 P = loadPreTri2(S.pre2, p);

@@ -7,7 +7,7 @@ namespace rtb {
 // Variant per tree kind (rtb_chain_oct.cuh): SAH trees -- 16 lanes per pixel, exact list rounds; k-d median trees -- 8 lanes
 // per pixel, list rounds through the packed rejection test; grids (only with RTB_OCT_TIER forced: they keep the resumable
 // walk by default) -- 8 lanes, exact rounds.
-static bool medianTree(const Launch &L) { return L.S->accel == RTB_ACCEL_KD_MEDIAN && L.S->pre2 != nullptr; } // the rejection-test rounds read the pair stream
+static bool medianTree(const Launch &L) { return L.S->accel == RTB_ACCEL_KD_MEDIAN; }
 // 16 lanes per pixel pay on SAH shards up to 2 Mpixel (1/8 and 1/16 shards of a 4K frame, 1280x960 frames: 1.17 -> 1.09 ms,
 // 1.20 -> 1.06 ms); a 1920x1440 frame is better off with 8 (1.68 vs 1.86 ms: twice the warps for its larger tier)
 int octWarpsPerTile(int accel, int n_tiles) { return (accel == RTB_ACCEL_KD_SAH && n_tiles <= 65536) ? 16 : 8; }
