@@ -312,3 +312,34 @@ def test_first_frame_schedule_can_be_forgotten(ctx):
     for img in (second, third, again):
         assert np.array_equal(_bits(img), _bits(first))
     dev.close(); s.close()
+
+
+def test_frames_on_two_caller_streams_of_one_context(ctx):
+    """The tile schedule (cost / order buffers, side stream) belongs to the context and is shared by its frames; a frame
+    issued on another caller stream is ordered behind the previous one by the library (an event recorded behind each frame's
+    last kernel), including when the tile buffers have to grow.  Alternating streams and frame sizes must give, every
+    time, the image a fresh context renders."""
+    import torch
+    s = PresetScene(5, "sah", 40)
+    dev = ctx.upload(s.flat)
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    sizes = [(256, 192), (512, 384), (256, 192), (640, 480), (512, 384), (640, 480)]
+    want = {}
+    for (w, h) in set(sizes):
+        c2 = rtb200.Context(0)
+        d2 = c2.upload(s.flat)
+        want[(w, h)], _ = d2.render(s.camera, s.setting, rtb200.make_frame(w, h))
+        d2.close(); c2.close()
+    bufs = []
+    for i, (w, h) in enumerate(sizes * 2):
+        st = streams[i % 2]
+        with torch.cuda.stream(st):
+            buf = torch.empty((h, w, 3), dtype=torch.float32, device="cuda:0")
+        st.synchronize()
+        dev.render_device(s.camera, s.setting, rtb200.make_frame(w, h), buf.data_ptr(), st.cuda_stream)  # no sync in between
+        bufs.append((w, h, buf))
+    torch.cuda.synchronize()
+    for (w, h, buf) in bufs:
+        assert np.array_equal(_bits(buf.cpu().numpy()), _bits(want[(w, h)]))
+    dev.close(); s.close()
+
