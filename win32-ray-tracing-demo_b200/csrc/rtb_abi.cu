@@ -26,6 +26,9 @@
 #ifndef RTB_HEAVY_BUCKETS_SMALL
 #define RTB_HEAVY_BUCKETS_SMALL 4   // quarter-octaves below the heaviest tile: 4 / 6 / 10 -> slowest 1/8 SAH shard 1.18 / 1.24 / 1.24 ms
 #endif
+#ifndef RTB_HEAVY_ALPHA
+#define RTB_HEAVY_ALPHA 0.0f
+#endif
 #ifndef RTB_HEAVY_FRACTION_SMALL
 #define RTB_HEAVY_FRACTION_SMALL 128 //    quarter-octaves and 1/32 .. 1/8 of the shard measured slower)
 #endif
@@ -73,6 +76,9 @@ static int heavyBucketsSmall(int accel)
     return accel == RTB_ACCEL_KD_MEDIAN ? 6 : RTB_HEAVY_BUCKETS_SMALL;
 }
 static int heavyFractionSmall() { static const int v = (int)tunable("RTB_HEAVY_FRACTION_SMALL", RTB_HEAVY_FRACTION_SMALL); return v < 1 ? 1 : v; }
+// > 0: the latency-critical set of a small shard is chosen by time (k_cost_offsets: tiles whose recorded cost exceeds alpha x the
+// balanced finishing time of the kernel); 0: by distance from the heaviest tile (heavyBucketsSmall)
+static float heavyAlpha() { static const float v = (float)tunable("RTB_HEAVY_ALPHA", RTB_HEAVY_ALPHA); return v; }
 // Size limit of the resumable-walk tier.  Small frames have none: there the warp-per-pixel tier takes the heavy
 // tiles and a third kernel in between measured slower (k-d median 400x300: 1.4 ms without, 2.2 ms with).
 static int heavyLimit(int n_tiles)
@@ -1365,7 +1371,8 @@ static int renderLaunch(rtb_ctx *ctx, const rtb_scene *scene, FrameParams &F, co
         const bool smallShard = F.n_tiles <= splitMaxTiles();
         k_cost_offsets<<<1, RTB_COST_BUCKETS, 0, stream>>>(ctx->d_hist, ctx->d_cursor, ctx->d_heavy, F.n_tiles,
                                              smallShard ? heavyBucketsSmall(scene->d.accel) : RTB_HEAVY_BUCKETS,
-                                             heavyLimit(F.n_tiles), wideCount(F.n_tiles, scene->long_lists), floorDelta);
+                                             heavyLimit(F.n_tiles), wideCount(F.n_tiles, scene->long_lists), floorDelta,
+                                             smallShard ? heavyAlpha() : 0.f, 148 * RTB_CHAIN_MIN_CTAS * (RTB_CTA_THREADS / 32));
         k_cost_scatter<<<blocks, 256, 0, stream>>>(ctx->d_cost, F.n_tiles, ctx->d_cursor, ctx->d_order, ctx->d_heavy);
         CUDA_TRY(ctx, cudaGetLastError());
         ctx->order_valid = true;

@@ -30,8 +30,12 @@ enum { SM_STEP = 0, SM_LEAF = 1, SM_SHADE = 2, SM_DONE = 3, SM_EXACT = 4 };
 #define RTB_SM_MIN_CTAS 6
 #endif
 
-template <class Probe, bool GRID, int FOLD>
-__global__ void __launch_bounds__(RTB_CTA_THREADS, GRID ? RTB_CHAIN_MIN_CTAS : RTB_SM_MIN_CTAS)
+// MINCTAS: resident CTAs per SM the register budget is set for.  The regular grid's throughput launches take 8 (64 registers),
+// the tier launches of the other accelerators 6; the regular grid's SHARDS (<= 2 Mpixel) take 5: there the warp-per-pixel tier
+// runs next to this kernel on the same SMs and its chains finish sooner with fewer warps competing for the schedulers
+// (slowest 1/8 shard of the 4K frame 2.76 -> 2.40 ms; a whole 4K frame prefers 8: 10.5 vs 11.9 ms).
+template <class Probe, bool GRID, int FOLD, int MINCTAS>
+__global__ void __launch_bounds__(RTB_CTA_THREADS, MINCTAS)
 k_whitted_chain_sm(const __grid_constant__ DScene S, const __grid_constant__ FrameParams F, float *__restrict__ out,
                    Counters *__restrict__ counters)
 {

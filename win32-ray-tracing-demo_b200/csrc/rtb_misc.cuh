@@ -41,8 +41,14 @@ __global__ void k_cost_histogram(const unsigned int *__restrict__ cost, int n, u
 // page-locked host frame that is what lets the 96-byte row segments of adjacent tiles combine into long PCIe
 // writes: 4K SAH frame 6.95 -> 5.79 ms with the floor, against 5.48 ms into HBM (profiles/r01_e2e_floor_bucket.log).
 // Frames rendered into device memory keep floor_delta = 0 (pure heaviest-first is 3 % faster there).
+// heavy_alpha > 0 selects the latency-critical set by TIME instead of by distance from the heaviest tile: with every tile's
+// recorded cost c (cycles it took in the throughput kernel, on a saturated SM) the kernel's balanced finishing time is about
+// T* = sum(c) / resident warp slots; a tile whose own c exceeds heavy_alpha * T* would still be running when everything else
+// is done, wherever it is started -- those go to the latency tier (at most heavy_limit of them).  Unlike "within 2x of the
+// heaviest tile" this does not shrink the set of a shard that happens to hold one outlier tile.
 __global__ void k_cost_offsets(unsigned int *__restrict__ hist, unsigned int *__restrict__ cursor, unsigned int *__restrict__ n_heavy,
-                               int n_tiles, int heavy_buckets, int heavy_limit, int wide_count, int floor_delta)
+                               int n_tiles, int heavy_buckets, int heavy_limit, int wide_count, int floor_delta, float heavy_alpha,
+                               int warp_slots)
 {
     // launched with RTB_COST_BUCKETS threads: the histogram is fetched (and cleared for the next frame) in parallel,
     // the short serial pass below then runs out of shared memory (18 -> ~4 us; it sits at the end of every frame)
@@ -72,6 +78,21 @@ __global__ void k_cost_offsets(unsigned int *__restrict__ hist, unsigned int *__
             run += h[b];
             if (top2 < 0 && run > wide) top2 = b;
             if (top2 >= 0 && b >= top2 - heavy_buckets) heavy = run;
+        }
+        if (heavy_alpha > 0.f)
+        {
+            // centre of bucket b (costBucket: 4 buckets per power of two): 2^e * (1 + (q + 0.5) / 4), e = (b + 4) / 4, q = (b + 4) % 4
+            double total = 0;
+            for (int b = 4; b < RTB_COST_BUCKETS; b++) total += (double)h[b] * ldexp(1.0 + (((b + 4) & 3) + 0.5) * 0.25, (b + 4) >> 2);
+            const double limit = (double)heavy_alpha * total / (double)max(warp_slots, 1);
+            unsigned int r2 = 0;
+            heavy = wide;
+            for (int b = RTB_COST_BUCKETS - 1; b >= 4; b--)
+            {
+                if (ldexp(1.0 + (((b + 4) & 3) + 0.5) * 0.25, (b + 4) >> 2) < limit) break;
+                r2 += h[b];
+                heavy = max(heavy, r2);
+            }
         }
         if (heavy < wide) heavy = wide;
         // a bucket may be cut: with whole buckets only, a well-filled bucket at the top (flat cost distributions)
