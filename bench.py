@@ -531,25 +531,30 @@ def run_b200(args, wl_name):
             d.render(scene.camera, setting, fr, out=out)
             d.close()
 
-        e2e_step()
-        torch.cuda.synchronize()
-        t1 = time.perf_counter()
-        for _ in range(e2e_steps):
-            e2e_step()
-        torch.cuda.synchronize()
-        e2e_ms = (time.perf_counter() - t1) * 1e3 / e2e_steps
+        def timed_e2e(*a):
+            e2e_step(*a)
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            for _ in range(e2e_steps):
+                e2e_step(*a)
+            torch.cuda.synchronize()
+            return (time.perf_counter() - t1) * 1e3 / e2e_steps
+
+        e2e_pageable_ms = timed_e2e()  # the flat scene's arrays in pageable memory: the upload stages them (one host pass over the scene)
+        scene.pin()                    # ... page-locked where they lie (rtb_host_register): the upload copies H2D straight out of them
+        e2e_ms = timed_e2e()
         # the same call with the reference's 8-bit output stage on the GPU (3 bytes per pixel come back)
         pinned8 = rtb200.PinnedArray(((H * W * 3 + 3) // 4,))
         host8 = pinned8.array.view(np.uint8)[: H * W * 3].reshape(H, W, 3)
         f8 = rtb200.make_frame(W, H, samples=spp, seed=0, layout=rtb200.OUTPUT_RGB8)
-        e2e_step(host8, f8)
-        t1 = time.perf_counter()
-        for _ in range(e2e_steps):
-            e2e_step(host8, f8)
-        e2e8_ms = (time.perf_counter() - t1) * 1e3 / e2e_steps
+        e2e8_ms = timed_e2e(host8, f8)
+        scene.unpin()
         e2e = {"value": rays_frame / e2e_ms / 1e3, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(frame_bytes),
                "ms_per_step": e2e_ms, "steps": e2e_steps,
-               "path": "rtb_scene_upload (H2D) + rtb_render (the kernels store the float frame straight into the caller's page-locked host buffer over PCIe) + rtb_scene_free, per step",
+               "path": "rtb_scene_upload (H2D out of the caller's page-locked scene arrays, rtb_flat_scene.arrays_page_locked) + rtb_render (the kernels store the float "
+                       "frame straight into the caller's page-locked host buffer over PCIe) + rtb_scene_free, per step",
+               "pageable_scene_arrays": {"value": rays_frame / e2e_pageable_ms / 1e3, "ms_per_step": e2e_pageable_ms,
+                                         "note": "same step with the scene arrays in pageable memory (the upload stages them in its page-locked ring first)"},
                "rgb8_output_stage": {"value": rays_frame / e2e8_ms / 1e3, "ms_per_step": e2e8_ms, "d2h_bytes_per_step": int(H * W * 3),
                                      "note": "same call with RTB_OUTPUT_RGB8: saturate + (int)(c*255) on the GPU as the reference's Render ends (MainWindow.cpp:305-311)"}}
     else:
@@ -557,6 +562,7 @@ def run_b200(args, wl_name):
         if rank == 0:  # ONE host thread drives all N devices (rtb_multi_*); the other ranks' processes are idle meanwhile (parked on the host)
             multi = rtb200.MultiContext(world)
             pinned = rtb200.PinnedArray((H, W, 3))
+            scene.pin()  # scene arrays page-locked where they lie: every device copies H2D straight out of them
             mframe = rtb200.make_frame(W, H, samples=spp, seed=0, row_block=ROW_BLOCK)
 
             phases = []
@@ -585,9 +591,10 @@ def run_b200(args, wl_name):
             e2e = {"value": rays_frame / e2e_ms / 1e3, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(frame_bytes),
                    "ms_per_step": e2e_ms, "steps": e2e_steps, "assembled_host_frame_verified": same if gpu_image is not None else None,
                    "phases_ms": {"upload_all_devices": float(ph[0]), "render_all_devices": float(ph[1]), "slowest_device_kernels": float(ph[2])},
-                   "path": f"rank 0's host thread drives all {world} devices: rtb_multi_scene_upload (H2D to every device) + rtb_multi_render (every device stores "
+                   "path": f"rank 0's host thread drives all {world} devices: rtb_multi_scene_upload (H2D to every device, side by side, out of the page-locked scene arrays) + rtb_multi_render (every device stores "
                            "its tiles straight into ONE page-locked host frame over its own PCIe link) + rtb_multi_scene_free, per step"}
             multi.close()
+            scene.unpin()
         host_barrier()
 
     # ---- roofline of the frame's kernels: warp-instruction issue
@@ -608,6 +615,16 @@ def run_b200(args, wl_name):
                          "ncu": {k: counts.get(k) for k in ("issue_active_pct", "ipc_per_sm", "l1_hit_pct", "duration_ms_under_ncu")},
                          "traffic": counts.get("dram_bytes"), "compulsory_bytes": int(frame_bytes) if not mc else int(frame_bytes),
                          "counts_source": counts_source})
+    elif world > 1:
+        # a rank's shard: the instruction counts of rank 0's 1/N shard (ncu capture of the same frame rendered as a shard on one GPU),
+        # against the slowest rank's kernel time -- all ranks hold the same mix of tiles (column-block shards)
+        shard, shard_source = issue_counts(f"{wl_name}_shard_1of{world}")
+        if shard:
+            winst = shard["warp_inst"]
+            roofline.update({"achieved": winst / (kernel_ms * 1e-3) / 1e9, "frac": winst / (kernel_ms * 1e-3) / 1e9 / peak_ginst,
+                             "warp_inst_per_shard": winst, "thread_inst_per_warp_inst": shard.get("thread_inst_per_warp_inst"),
+                             "per": "rank (one GPU's issue peak against one shard's instructions and the slowest rank's kernel time)",
+                             "traffic": shard.get("dram_bytes"), "compulsory_bytes": int(frame_bytes // world), "counts_source": shard_source})
     # HBM side of the same kernels, for the record: algorithmic bytes (8 B per visited cell / k-d node, 4 B index + 36 B
     # vertices per triangle test, 12 B normal + 4 B material per ray, 12 B framebuffer per pixel) are served by L1 / L2; DRAM sees `traffic`
     algo_bytes = 8 * cst["n_steps"] + 40 * cst["n_tri_tests"] + 16 * cst["n_rays"] + 12 * rows * Wl

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define RTB_ABI_VERSION 4
+#define RTB_ABI_VERSION 5
 
 typedef enum rtb_status {
     RTB_OK = 0,
@@ -136,6 +136,12 @@ typedef struct rtb_flat_scene {
      * depth > kd_build_max_depth (reference: 8 and 18), kd_build_candidates - 1 uniform planes per axis (reference: 100 - 1).
      * kd_min / kd_max / n_kd_* and the two arrays are ignored.                                                                */
     int32_t kd_build_leaf_size, kd_build_max_depth, kd_build_candidates;
+    /* 1 = the arrays above are page-locked host memory (rtb_host_alloc / rtb_host_register) AND stay unchanged until a render
+     * of the uploaded scene has returned or the scene has been freed: the upload then copies host -> device straight out of
+     * them (truly asynchronous copies, no staging pass over the 4.5 MB of a 45,900-triangle scene, 0.6 -> 0.3 ms per upload).
+     * 0 = the arrays may be pageable and may be reused as soon as the upload call returns (they are staged).  An array that
+     * is not page-locked is staged whatever the flag says.                                                                  */
+    int32_t arrays_page_locked;
 } rtb_flat_scene;
 
 /* ---- camera: reference Camera.h:7-23; the derived fields are computed on the host exactly as
@@ -227,6 +233,10 @@ int rtb_abi_version(void);
  * device->host copies into pageable memory are staged by the driver and several times slower).   */
 int rtb_host_alloc(size_t bytes, void **out);
 int rtb_host_free(void *p);
+/* Page-lock memory the caller already owns (the arrays of a flat scene, see rtb_flat_scene.arrays_page_locked; a frame
+ * buffer): every device of the process may copy from / store into it.  Unregister before the memory is freed.          */
+int rtb_host_register(void *p, size_t bytes);
+int rtb_host_unregister(void *p);
 
 /* Number of rows / first-row list of a shard (pure host arithmetic; no device needed).       */
 int64_t rtb_shard_rows(const rtb_frame *frame);

@@ -62,7 +62,11 @@ def main():
         dur = get(r, "gpu__time_duration.sum")
         dur_ms = dur * {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(unit_of.get("gpu__time_duration.sum", "ns"), 1e-6) if dur is not None else None
         k = {"kernel": r["Kernel Name"].split("(")[0][:120], "grid": r.get("Grid Size"), "block": r.get("Block Size"),
-             "warp_inst": get(r, "smsp__inst_executed.sum"), "thread_inst": get(r, "smsp__thread_inst_executed.sum"),
+             "warp_inst": get(r, "smsp__inst_executed.sum"),
+             # --set full carries the lanes-per-instruction ratio, not the thread-instruction sum
+             "thread_inst": get(r, "smsp__thread_inst_executed.sum") if get(r, "smsp__thread_inst_executed.sum") is not None else
+             ((get(r, "smsp__inst_executed.sum") or 0) * get(r, "smsp__thread_inst_executed_per_inst_executed.ratio")
+              if get(r, "smsp__thread_inst_executed_per_inst_executed.ratio") is not None else None),
              "dram_read": get(r, "dram__bytes_read.sum", True), "dram_write": get(r, "dram__bytes_write.sum", True),
              "duration_ms_under_ncu": dur_ms,
              "issue_active_pct": get(r, "smsp__issue_active.avg.pct_of_peak_sustained_active"),

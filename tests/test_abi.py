@@ -27,10 +27,12 @@ def test_header_symbols_exported():
 
 def test_abi_version_and_struct_sizes():
     lib = rtb200.cuda_lib()
-    assert lib.rtb_abi_version() == 4
+    assert lib.rtb_abi_version() == 5
     assert C.sizeof(rtb200.Frame) == 56  # ABI 4 appended sample_first / sample_count (col_block had taken the tail padding in ABI 3)
     assert C.sizeof(rtb200.Material) == 64 and C.sizeof(rtb200.Prim) == 48
     assert C.sizeof(rtb200.KdNode) == 8 and C.sizeof(rtb200.CellWord) == 8
+    # ABI 5 appended arrays_page_locked (it took the tail padding: the size is unchanged)
+    assert C.sizeof(rtb200.FlatScene) == 320 and rtb200.FlatScene.arrays_page_locked.offset == 312
 
 
 def test_no_cpu_fallback_without_device():

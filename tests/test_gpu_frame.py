@@ -161,6 +161,62 @@ def test_multi_render_assembles_one_host_frame(ctx, devices):
     pinned.close(); ms.close(); m.close(); dev.close(); s.close()
 
 
+@pytest.mark.parametrize("algorithm", ["sah", "rgrid"])
+def test_upload_out_of_page_locked_scene_arrays(ctx, algorithm):
+    """rtb_flat_scene.arrays_page_locked: the upload copies H2D straight out of the caller's (registered) arrays instead of
+    staging them -- same device scene, same frame, same byte accounting; one context and a device set (where the first
+    device's upload publishes the source addresses to the replicas)."""
+    w, h = 256, 96
+    s = PresetScene(5, algorithm, 40)
+    dev = ctx.upload(s.flat)
+    whole, st = dev.render(s.camera, s.setting, rtb200.make_frame(w, h, counters=1))
+    staged_bytes = dev.upload_bytes
+    dev.close()
+    s.pin()
+    assert s.flat.contents.arrays_page_locked == 1 and len(s._pinned) >= 2
+    for _ in range(3):  # repeated uploads out of the same arrays
+        dev = ctx.upload(s.flat)
+        img, st2 = dev.render(s.camera, s.setting, rtb200.make_frame(w, h, counters=1))
+        assert dev.upload_bytes == staged_bytes
+        assert np.array_equal(_bits(img), _bits(whole)) and st2["n_rays"] == st["n_rays"] and st2["n_tri_tests"] == st["n_tri_tests"]
+        dev.close()
+    m = rtb200.MultiContext(3, [0, 0, 0])
+    for _ in range(2):
+        ms = m.upload(s.flat)
+        assert ms.upload_bytes == 3 * staged_bytes
+        out, mst = ms.render(s.camera, s.setting, rtb200.make_frame(w, h, counters=1))
+        assert np.array_equal(_bits(out), _bits(whole)) and mst["n_rays"] == st["n_rays"]
+        ms.close()
+    m.close()
+    s.unpin()
+    assert s.flat.contents.arrays_page_locked == 0
+    dev = ctx.upload(s.flat)  # and staged again
+    img, _ = dev.render(s.camera, s.setting, rtb200.make_frame(w, h))
+    assert np.array_equal(_bits(img), _bits(whole))
+    dev.close(); s.close()
+
+
+def test_multi_upload_reports_a_bad_scene_once(ctx):
+    """A flat scene the first device's checks refuse: the replicas (which wait for that verdict) are released, the call fails with
+    the first device's message and the device set stays usable."""
+    s = PresetScene(5, "sah", 24)
+    f = s.flat.contents
+    refs = np.ctypeslib.as_array(f.kd_leaf_tris, shape=(f.n_kd_refs,))
+    keep = int(refs[5])
+    m = rtb200.MultiContext(4, [0, 0, 0, 0])
+    refs[5] = f.n_tris + 7  # out of range
+    with pytest.raises(rtb200.RtbError) as e:
+        m.upload(s.flat)
+    assert "reference out of range" in str(e.value)
+    refs[5] = keep
+    ms = m.upload(s.flat)
+    out, _ = ms.render(s.camera, s.setting, rtb200.make_frame(160, 64))
+    dev = ctx.upload(s.flat)
+    whole, _ = dev.render(s.camera, s.setting, rtb200.make_frame(160, 64))
+    assert np.array_equal(_bits(out), _bits(whole))
+    dev.close(); ms.close(); m.close(); s.close()
+
+
 def test_multi_render_all_gpus(ctx):
     n = _n_gpus()
     if n < 2:

@@ -17,13 +17,14 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="p5_sah_4k")
 ap.add_argument("--devices", default="1,2")
 ap.add_argument("--reps", type=int, default=8)
+ap.add_argument("--same-device", action="store_true", help="n contexts on device 0 (one-GPU box: the host-side cost of the calls)")
 args = ap.parse_args()
 wl = WORKLOADS[args.workload]
 s = rtb200.PresetScene(wl["preset"], wl["algorithm"], wl["segments"])
 W, H = wl["width"], wl["height"]
 pinned = rtb200.PinnedArray((H, W, 3))
 for n in [int(v) for v in args.devices.split(",")]:
-    m = rtb200.MultiContext(n)
+    m = rtb200.MultiContext(n, [0] * n) if args.same_device else rtb200.MultiContext(n)
     fr = rtb200.make_frame(W, H, samples=wl["samples"])
     rows = []
     for i in range(args.reps):

@@ -73,7 +73,20 @@ class FlatScene(C.Structure):
         ("cx_order", C.POINTER(C.c_uint16)),
         ("grid_build_exact", C.c_int32),
         ("kd_build_leaf_size", C.c_int32), ("kd_build_max_depth", C.c_int32), ("kd_build_candidates", C.c_int32),
+        ("arrays_page_locked", C.c_int32),
     ]
+
+    def arrays(self):
+        """(address, bytes) of every array rtb_scene_upload copies for this scene (include/rtb.h: rtb_flat_scene)."""
+        def a(ptr, n, elem):
+            return (C.cast(ptr, C.c_void_p).value, int(n) * elem) if ptr and n > 0 else None
+        out = [a(self.loose_tri, self.n_loose, 48), a(self.tri, self.n_tris, 48), a(self.tri_material, self.n_tris, 4)]
+        if self.accel in (ALGORITHMS["rgrid"], ALGORITHMS["fgrid"]) and self.grid_words:
+            out += [a(self.grid_words, self.n_cellwords, 8), a(self.grid_cell_start, self.n_cells_used + 1, 4),
+                    a(self.grid_cell_tris, self.n_cell_refs, 4)]
+        if self.accel in (ALGORITHMS["kd"], ALGORITHMS["sah"]) and self.kd_nodes:
+            out += [a(self.kd_nodes, self.n_kd_nodes, 8), a(self.kd_leaf_tris, self.n_kd_refs, 4)]
+        return [x for x in out if x]
 
 
 class Camera(C.Structure):
@@ -112,7 +125,7 @@ class Stats(C.Structure):
 
 ABI_SYMBOLS = ["rtb_init", "rtb_shutdown", "rtb_last_error", "rtb_abi_version", "rtb_shard_rows", "rtb_shard_width",
                "rtb_unshard_cols_device",
-               "rtb_host_alloc", "rtb_host_free",
+               "rtb_host_alloc", "rtb_host_free", "rtb_host_register", "rtb_host_unregister",
                "rtb_scene_upload", "rtb_scene_free", "rtb_scene_device_bytes", "rtb_scene_upload_bytes", "rtb_scene_grid_hash", "rtb_scene_kd_download", "rtb_render",
                "rtb_render_device", "rtb_unshard_device", "rtb_trace_primary", "rtb_intersect_rays", "rtb_bounce_rays",
                "rtb_selftest_pretest", "rtb_kd_validate", "rtb_forget_schedule", "rtb_set_progress", "rtb_multi_set_progress",
@@ -138,6 +151,8 @@ def cuda_lib():
         lib.rtb_last_error.restype = C.c_char_p
         lib.rtb_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
         lib.rtb_host_free.argtypes = [vp]
+        lib.rtb_host_register.argtypes = [vp, C.c_size_t]
+        lib.rtb_host_unregister.argtypes = [vp]
         lib.rtb_shard_rows.argtypes = [C.POINTER(Frame)]
         lib.rtb_shard_rows.restype = i64
         lib.rtb_shard_width.argtypes = [C.POINTER(Frame)]
@@ -252,8 +267,28 @@ class PresetScene:
         self.camera = lib.rtbh_camera(self._h).contents
         self.setting = lib.rtbh_setting(self._h).contents
 
+    def pin(self):
+        """Page-lock the flat scene's arrays where they lie (rtb_host_register) and declare them page-locked and stable
+        (rtb_flat_scene.arrays_page_locked): uploads then copy host -> device straight out of them.  An array that cannot be
+        registered (it shares a page with one that is) stays pageable; the library stages such an array as before."""
+        if getattr(self, "_pinned", None):
+            return self
+        lib = cuda_lib()
+        self._pinned = [addr for addr, nbytes in self.flat.contents.arrays()
+                        if nbytes >= (64 << 10) and lib.rtb_host_register(C.c_void_p(addr), C.c_size_t(nbytes)) == 0]
+        self.flat.contents.arrays_page_locked = 1
+        return self
+
+    def unpin(self):
+        for addr in getattr(self, "_pinned", None) or []:
+            cuda_lib().rtb_host_unregister(C.c_void_p(addr))
+        self._pinned = []
+        if self._h:
+            self.flat.contents.arrays_page_locked = 0
+
     def close(self):
         if self._h:
+            self.unpin()
             host_lib().rtbh_free(self._h)
             self._h = None
 

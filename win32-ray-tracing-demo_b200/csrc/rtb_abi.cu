@@ -6,6 +6,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -102,6 +105,34 @@ struct OrderKey
     rtb_camera cam;
 };
 
+// rtb_multi_scene_upload: ONE flat scene goes to every device of the set.  The first device's upload (the producer) stages
+// each stream once into its page-locked ring (portable: every device copies from it) and publishes the staged address; the
+// other devices' uploads (replicas, on worker threads, a step behind the producer) issue their H2D copies from the same
+// staged bytes instead of staging 4.5 MB again per device.  The producer also publishes the verdict of the whole-stream
+// index checks, which a replica awaits before it launches anything that indexes with those streams.
+struct StageShare
+{
+    static const int kSlots = 64;
+    char *slot[kSlots] = {};
+    std::atomic<int> produced{0};
+    std::atomic<int> verdict{0};   // 0 pending, 1 streams validated, -1 the producer failed
+    bool waitSlot(int i) const
+    {
+        while (produced.load(std::memory_order_acquire) <= i)
+        {
+            if (verdict.load(std::memory_order_acquire) < 0) return false;
+            std::this_thread::yield();
+        }
+        return true;
+    }
+    bool waitVerdict() const
+    {
+        int v;
+        while ((v = verdict.load(std::memory_order_acquire)) == 0) std::this_thread::yield();
+        return v > 0;
+    }
+};
+
 struct rtb_ctx
 {
     int device = -1;
@@ -130,6 +161,11 @@ struct rtb_ctx
     // asynchronous H2D copies (a pageable source makes every cudaMemcpyAsync a staged, partly synchronous copy)
     char *stage = nullptr;
     size_t stage_cap = 0, stage_used = 0;
+    std::vector<rtb_ctx *> stage_readers; // contexts of the same rtb_multi whose streams copy out of this ring too
+    StageShare *share = nullptr; // set for the duration of an rtb_multi_scene_upload
+    bool share_producer = false;
+    int share_next = 0;          // replica: the next staged stream to take
+    bool sources_page_locked = false; // this upload's flat scene allows copies straight out of page-locked arrays
     std::string error;
 };
 
@@ -143,6 +179,7 @@ struct rtb_scene
     bool has_tunnel = false;
     cudaEvent_t last_use = nullptr; // recorded after every launch that reads the scene
     cudaEvent_t ready = nullptr;    // recorded on ctx->stream behind the upload copies
+    bool direct_sources = false;    // some copies read the caller's page-locked arrays: rtb_scene_free waits for `ready`
     int64_t grid_cells_used = 0, grid_refs = 0, grid_words = 0;
     int64_t kd_nodes = 0, kd_refs = 0; // k-d tree resident on the device (uploaded or built there)
     int kd_levels = 0;
@@ -331,12 +368,18 @@ static int stageReserve(rtb_ctx *ctx, size_t bytes, char **out)
     if (ctx->stage_used + bytes > ctx->stage_cap)
     {
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        for (rtb_ctx *r : ctx->stage_readers)
+        {
+            CUDA_TRY(ctx, cudaSetDevice(r->device));
+            CUDA_TRY(ctx, cudaStreamSynchronize(r->stream));
+        }
+        if (!ctx->stage_readers.empty()) CUDA_TRY(ctx, cudaSetDevice(ctx->device));
         if (bytes > ctx->stage_cap)
         {
             if (ctx->stage) cudaFreeHost(ctx->stage);
             ctx->stage = nullptr; ctx->stage_cap = 0;
             const size_t cap = bytes * 2 > ((size_t)64 << 20) ? bytes * 2 : ((size_t)64 << 20);
-            CUDA_TRY(ctx, cudaHostAlloc((void **)&ctx->stage, cap, cudaHostAllocDefault));
+            CUDA_TRY(ctx, cudaHostAlloc((void **)&ctx->stage, cap, cudaHostAllocPortable)); // every device of an rtb_multi copies from it
             ctx->stage_cap = cap;
         }
         ctx->stage_used = 0;
@@ -346,9 +389,55 @@ static int stageReserve(rtb_ctx *ctx, size_t bytes, char **out)
     return RTB_OK;
 }
 
+// `bytes` of staged data: written by fill(char *staging) into this context's ring -- or, for a replica of an
+// rtb_multi_scene_upload, the bytes the producer has staged for the same stream (StageShare)
+// is `p` page-locked host memory (cudaHostAlloc / cudaHostRegister)?
+static bool pageLocked(const void *p)
+{
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) == cudaSuccess && attr.type == cudaMemoryTypeHost) return true;
+    cudaGetLastError();
+    return false;
+}
+
+// `src` != nullptr: the staged bytes are a verbatim copy of that caller array -- if the flat scene declares its arrays
+// page-locked and stable (rtb_flat_scene.arrays_page_locked) and this one is, the copy reads the array itself (*direct)
+template <class Fill>
+static int stageFill(rtb_ctx *ctx, size_t bytes, char **out, Fill fill, const void *src = nullptr, bool *direct = nullptr)
+{
+    StageShare *sh = ctx->share;
+    if (sh && !ctx->share_producer)
+    {
+        const int i = ctx->share_next++;
+        if (i >= StageShare::kSlots || !sh->waitSlot(i)) return fail(ctx, RTB_ERR_INVALID, "rtb_multi_scene_upload: the first device's upload failed");
+        *out = sh->slot[i];
+        if (direct && *out == (const char *)src) *direct = true;
+        return RTB_OK;
+    }
+    if (src && ctx->sources_page_locked && pageLocked(src))
+    {
+        *out = (char *)const_cast<void *>(src);
+        if (direct) *direct = true;
+    }
+    else
+    {
+        const int rc = stageReserve(ctx, bytes, out);
+        if (rc != RTB_OK) return rc;
+        fill(*out);
+    }
+    if (sh)
+    {
+        const int i = sh->produced.load(std::memory_order_relaxed);
+        if (i >= StageShare::kSlots) return fail(ctx, RTB_ERR_UNSUPPORTED, "rtb_multi_scene_upload: too many streams");
+        sh->slot[i] = *out;
+        sh->produced.store(i + 1, std::memory_order_release);
+    }
+    return RTB_OK;
+}
+
 // device array of n elements; `fill(T *staging)` writes the elements into staging memory (nullptr: zero-filled)
 template <class T, class Fill>
-static int uploadWith(rtb_ctx *ctx, rtb_scene *s, size_t n, const T **dev, Fill fill, bool zero = false)
+static int uploadWith(rtb_ctx *ctx, rtb_scene *s, size_t n, const T **dev, Fill fill, bool zero = false, const T *verbatim = nullptr)
 {
     *dev = nullptr;
     const size_t count = n ? n : 1; // keep pointers valid
@@ -359,9 +448,8 @@ static int uploadWith(rtb_ctx *ctx, rtb_scene *s, size_t n, const T **dev, Fill 
     if (n && !zero)
     {
         char *st = nullptr;
-        const int rc = stageReserve(ctx, n * sizeof(T), &st);
+        const int rc = stageFill(ctx, n * sizeof(T), &st, [&](char *dst) { fill(reinterpret_cast<T *>(dst)); }, verbatim, &s->direct_sources);
         if (rc != RTB_OK) return rc;
-        fill(reinterpret_cast<T *>(st));
         CUDA_TRY(ctx, cudaMemcpyAsync(p, st, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
         s->h2d_bytes += (int64_t)(n * sizeof(T));
     }
@@ -373,7 +461,7 @@ static int uploadWith(rtb_ctx *ctx, rtb_scene *s, size_t n, const T **dev, Fill 
 template <class T>
 static int uploadArray(rtb_ctx *ctx, rtb_scene *s, const T *host, size_t n, const T **dev)
 {
-    return uploadWith<T>(ctx, s, n, dev, [&](T *st) { memcpy(st, host, n * sizeof(T)); }, host == nullptr);
+    return uploadWith<T>(ctx, s, n, dev, [&](T *st) { memcpy(st, host, n * sizeof(T)); }, host == nullptr, host);
 }
 
 // Triangle records (a, b, c, normal: 12 floats) -> the two device streams, one thread per triangle:
@@ -418,8 +506,7 @@ static int uploadTriangles(rtb_ctx *ctx, rtb_scene *s, const float *host, size_t
     if (pre && (rc = uploadWith<float4>(ctx, s, 3 * n, pre, [](float4 *) {}, true)) != RTB_OK) return rc;
     if (n == 0) return RTB_OK;
     char *st = nullptr;
-    if ((rc = stageReserve(ctx, n * 12 * sizeof(float), &st)) != RTB_OK) return rc;
-    memcpy(st, host, n * 12 * sizeof(float));
+    if ((rc = stageFill(ctx, n * 12 * sizeof(float), &st, [&](char *dst) { memcpy(dst, host, n * 12 * sizeof(float)); }, host, &s->direct_sources)) != RTB_OK) return rc;
     void *raw = nullptr;
     CUDA_TRY(ctx, cudaMallocAsync(&raw, n * 12 * sizeof(float), ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(raw, st, n * 12 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
@@ -775,6 +862,36 @@ struct UploadLaps
     ~UploadLaps() { if (on) fprintf(stderr, "rtb_scene_upload:%s\n", text.c_str()); }
 };
 
+// The verdict of the whole-stream checks, before anything indexes with the checked streams.  Within an rtb_multi_scene_upload
+// the producer publishes it and the replicas (which skipped the checks) wait for it here.
+static int collectVerdict(rtb_ctx *ctx, BackgroundChecks &checks)
+{
+    checks.join();
+    if (checks.code != RTB_OK) return fail(ctx, checks.code, checks.msg);
+    if (StageShare *sh = ctx->share)
+    {
+        if (ctx->share_producer) sh->verdict.store(1, std::memory_order_release);
+        else if (!sh->waitVerdict()) return fail(ctx, RTB_ERR_INVALID, "rtb_multi_scene_upload: the first device's upload failed");
+    }
+    return RTB_OK;
+}
+
+// upper bound of the bytes one upload of `f` stages (every stream rounded up to the ring's 256-byte granules)
+static size_t stagedBytesBound(const rtb_flat_scene *f)
+{
+    auto r = [](double n, size_t elem) { return n > 0 ? (((size_t)n * elem + 255) & ~(size_t)255) : (size_t)0; };
+    size_t t = r(f->loose_tri ? f->n_loose : 0, 48) + r(f->tri ? f->n_tris : 0, 48) + r(f->tri_material ? f->n_tris : 0, 4);
+    if ((f->accel == RTB_ACCEL_REGULAR_GRID || f->accel == RTB_ACCEL_FLAT_GRID) && f->grid_words)
+        t += r((double)f->n_cellwords, 8) + r((double)f->n_cells_used + 1, 4) + r((double)f->n_cell_refs, 4);
+    if ((f->accel == RTB_ACCEL_KD_MEDIAN || f->accel == RTB_ACCEL_KD_SAH) && f->kd_nodes) t += r(f->n_kd_nodes, 8) + r((double)f->n_kd_refs, 4);
+    if (f->accel == RTB_ACCEL_CONVEX || f->accel == RTB_ACCEL_CONVEX_SIMPLE)
+    {
+        const double cells = (double)f->cx_table_size * f->cx_table_size;
+        t += r(f->n_cx_path, 32) + r(f->n_cx_edges, 12) + r(cells, 1) + r(cells, 4) + r(72000.0 * f->n_cx_edges, 2);
+    }
+    return t + 4096;
+}
+
 static int sceneUpload(rtb_ctx *ctx, const rtb_flat_scene *f, rtb_scene **out, bool validate);
 
 extern "C" int rtb_scene_upload(rtb_ctx *ctx, const rtb_flat_scene *f, rtb_scene **out) { return sceneUpload(ctx, f, out, true); }
@@ -823,9 +940,15 @@ static int sceneUpload(rtb_ctx *ctx, const rtb_flat_scene *f, rtb_scene **out, b
     }
 
     int rc = RTB_OK;
+    ctx->sources_page_locked = f->arrays_page_locked != 0;
     BackgroundChecks checks;
     checks.enabled = validate;
-    auto bail = [&](int code) { checks.join(); rtb_scene_free(ctx, s); return code; };
+    auto bail = [&](int code) {
+        checks.join();
+        if (s->direct_sources) cudaStreamSynchronize(ctx->stream); // queued copies read the caller's arrays
+        rtb_scene_free(ctx, s);
+        return code;
+    };
     laps.lap("header");
 
     // every stream is packed / copied into the page-locked staging ring and leaves with an asynchronous copy:
@@ -904,8 +1027,7 @@ static int sceneUpload(rtb_ctx *ctx, const rtb_flat_scene *f, rtb_scene **out, b
             if ((rc = uploadArray(ctx, s, f->grid_cell_start, (size_t)f->n_cells_used + 1, &d.g_start)) != RTB_OK) return bail(rc);
             if ((rc = uploadArray(ctx, s, f->grid_cell_tris, (size_t)f->n_cell_refs, &d.g_tris)) != RTB_OK) return bail(rc);
             // k_pack_pairs indexes the triangle stream with these references: the verdict of the checks comes first
-            checks.join();
-            if (checks.code != RTB_OK) return bail(fail(ctx, checks.code, checks.msg));
+            if ((rc = collectVerdict(ctx, checks)) != RTB_OK) return bail(rc);
             if ((rc = packPairs(ctx, s, d.g_tris, (size_t)f->n_cell_refs)) != RTB_OK) return bail(rc);
             s->grid_cells_used = f->n_cells_used; s->grid_refs = f->n_cell_refs; s->grid_words = f->n_cellwords;
         }
@@ -949,8 +1071,7 @@ static int sceneUpload(rtb_ctx *ctx, const rtb_flat_scene *f, rtb_scene **out, b
             d.kd_nodes = nodes;
             if ((rc = uploadArray(ctx, s, f->kd_leaf_tris, (size_t)f->n_kd_refs, &d.kd_tris)) != RTB_OK) return bail(rc);
             // k_pack_pairs indexes the triangle stream with these references: the verdict of the checks comes first
-            checks.join();
-            if (checks.code != RTB_OK) return bail(fail(ctx, checks.code, checks.msg));
+            if ((rc = collectVerdict(ctx, checks)) != RTB_OK) return bail(rc);
             if ((rc = packPairs(ctx, s, d.kd_tris, (size_t)f->n_kd_refs)) != RTB_OK) return bail(rc);
             s->kd_nodes = f->n_kd_nodes; s->kd_refs = f->n_kd_refs;
         }
@@ -989,8 +1110,7 @@ static int sceneUpload(rtb_ctx *ctx, const rtb_flat_scene *f, rtb_scene **out, b
     // no synchronisation: the copies are queued on ctx->stream ahead of anything that reads the scene; launches on
     // another stream (rtb_render_device) wait for this event
     laps.lap("accelerator");
-    checks.join();
-    if (checks.code != RTB_OK) return bail(fail(ctx, checks.code, checks.msg));
+    if ((rc = collectVerdict(ctx, checks)) != RTB_OK) return bail(rc);
     laps.lap("checks joined");
     {
         const cudaError_t e = cudaEventRecord(s->ready, ctx->stream);
@@ -1009,6 +1129,8 @@ extern "C" int rtb_scene_free(rtb_ctx *ctx, rtb_scene *s)
     if (ctx)
     { // stream-ordered release: after the last launch that read the scene (on whichever stream it ran)
         cudaSetDevice(ctx->device);
+        // copies straight out of the caller's page-locked arrays: the caller may reuse them once the scene is freed
+        if (s->direct_sources && s->ready && cudaEventQuery(s->ready) != cudaSuccess) { cudaGetLastError(); cudaEventSynchronize(s->ready); }
         if (s->last_use) cudaStreamWaitEvent(ctx->stream, s->last_use, 0);
         for (void *p : s->allocs) cudaFreeAsync(p, ctx->stream);
     }
@@ -1592,6 +1714,69 @@ extern "C" int rtb_ipc_close(rtb_ctx *ctx, void *mapped)
     return RTB_OK;
 }
 
+// Worker threads of an rtb_multi, one per device beyond the first: the per-device halves of an upload or of a frame launch
+// run side by side (the calling thread takes device 0).  They sleep on a condition variable between calls.
+struct WorkerPool
+{
+    std::vector<std::thread> threads;
+    std::mutex m;
+    std::condition_variable cv_job, cv_done;
+    const std::function<void(int)> *job = nullptr;
+    unsigned long long generation = 0;
+    int pending = 0;
+    bool stop = false;
+
+    void start(int n_workers)
+    {
+        for (int w = 1; w <= n_workers; w++)
+            threads.emplace_back([this, w]() {
+                unsigned long long seen = 0;
+                std::unique_lock<std::mutex> lock(m);
+                for (;;)
+                {
+                    cv_job.wait(lock, [&]() { return stop || generation != seen; });
+                    if (stop) return;
+                    seen = generation;
+                    const std::function<void(int)> *fn = job;
+                    lock.unlock();
+                    (*fn)(w);
+                    lock.lock();
+                    if (--pending == 0) cv_done.notify_one();
+                }
+            });
+    }
+    // fn(i) for i = 1 .. workers on the worker threads, fn(0) on the calling thread; returns when all have returned
+    void run(const std::function<void(int)> &fn)
+    {
+        if (!threads.empty())
+        {
+            std::lock_guard<std::mutex> lock(m);
+            job = &fn;
+            pending = (int)threads.size();
+            generation++;
+        }
+        cv_job.notify_all();
+        fn(0);
+        if (!threads.empty())
+        {
+            std::unique_lock<std::mutex> lock(m);
+            cv_done.wait(lock, [&]() { return pending == 0; });
+            job = nullptr;
+        }
+    }
+    void shutdown()
+    {
+        {
+            std::lock_guard<std::mutex> lock(m);
+            stop = true;
+        }
+        cv_job.notify_all();
+        for (std::thread &t : threads) t.join();
+        threads.clear();
+    }
+    ~WorkerPool() { shutdown(); }
+};
+
 struct rtb_multi
 {
     std::vector<rtb_ctx *> ctx;
@@ -1600,6 +1785,7 @@ struct rtb_multi
     rtb_progress_fn progress = nullptr;
     void *progress_user = nullptr;
     std::string error;
+    WorkerPool pool;
 };
 struct rtb_multi_scene { std::vector<rtb_scene *> s; };
 
@@ -1616,7 +1802,9 @@ extern "C" rtb_ctx *rtb_multi_ctx(rtb_multi *m, int i) { return (m && i >= 0 && 
 extern "C" int rtb_multi_shutdown(rtb_multi *m)
 {
     if (!m) return RTB_OK;
-    for (rtb_ctx *c : m->ctx) rtb_shutdown(c);
+    m->pool.shutdown();
+    // the first context's staging ring is read by the other contexts' streams: they drain (rtb_shutdown) before it is freed
+    for (size_t i = m->ctx.size(); i-- > 0;) rtb_shutdown(m->ctx[i]);
     if (m->frame) cudaFreeHost(m->frame);
     delete m;
     return RTB_OK;
@@ -1634,7 +1822,9 @@ extern "C" int rtb_multi_init(int n_devices, const int *devices, rtb_multi **out
         const int rc = rtb_init(devices ? devices[i] : i, &c);
         if (rc != RTB_OK) { rtb_multi_shutdown(m); return rc; }
         m->ctx.push_back(c);
+        if (i > 0) m->ctx[0]->stage_readers.push_back(c);
     }
+    m->pool.start(n_devices - 1);
     *out = m;
     return RTB_OK;
 }
@@ -1670,23 +1860,47 @@ extern "C" int rtb_multi_scene_upload(rtb_multi *m, const rtb_flat_scene *flat, 
     rtb_multi_scene *s = new rtb_multi_scene();
     s->s.assign(n, nullptr);
     std::vector<int> rc(n, RTB_OK);
-    // The first device's upload validates the flat scene (whole-stream index / structure checks, on worker threads of its
-    // own); the replicas then upload side by side -- one uploader thread per device for staging, H2D copies and packing
-    // kernels -- without repeating the checks on the same host arrays (8 devices: 1.5 -> ~0.9 ms).
-    rc[0] = sceneUpload(m->ctx[0], flat, &s->s[0], true);
-    if (rc[0] == RTB_OK)
+    // All devices upload side by side.  The calling thread runs the first device's upload, which validates the flat scene
+    // (whole-stream index / structure checks on worker threads of its own) and stages every stream ONCE in its page-locked
+    // ring; the other devices' uploads run on the pool's threads a step behind it: they take the staged bytes (StageShare)
+    // for their own H2D copies and packing kernels, and wait for the verdict of the checks before anything indexes with the
+    // checked streams.  8 devices: 1.6 ms (first device, then the replicas with a staging copy each) -> see DESIGN.md section 6.
+    StageShare share;
+    if (n > 1)
     {
-        std::vector<std::thread> workers;
-        for (size_t i = 2; i < n; i++) workers.emplace_back([&, i]() { rc[i] = sceneUpload(m->ctx[i], flat, &s->s[i], false); });
-        if (n > 1) rc[1] = sceneUpload(m->ctx[1], flat, &s->s[1], false);
-        for (std::thread &t : workers) t.join();
+        // the whole upload in one stretch of the ring: a wrap in the middle would reuse bytes the replicas still copy from
+        rtb_ctx *c0 = m->ctx[0];
+        const size_t bound = stagedBytesBound(flat);
+        if (c0->stage_used + bound > c0->stage_cap)
+        {
+            char *unused = nullptr;
+            c0->stage_used = c0->stage_cap; // take stageReserve's drain-and-restart (or grow) path now
+            cudaSetDevice(c0->device);
+            const int e = stageReserve(c0, bound, &unused);
+            if (e != RTB_OK) { delete s; return failMulti(m, e, c0->error); }
+            c0->stage_used = 0;
+        }
+        for (size_t i = 0; i < n; i++)
+        {
+            m->ctx[i]->share = &share;
+            m->ctx[i]->share_producer = i == 0;
+            m->ctx[i]->share_next = 0;
+        }
     }
+    const std::function<void(int)> upload = [&](int i) {
+        rc[(size_t)i] = sceneUpload(m->ctx[(size_t)i], flat, &s->s[(size_t)i], i == 0);
+        if (i == 0 && rc[0] != RTB_OK) share.verdict.store(-1, std::memory_order_release); // releases the replicas
+    };
+    m->pool.run(upload);
+    for (size_t i = 0; i < n; i++) m->ctx[i]->share = nullptr;
     for (size_t i = 0; i < n; i++)
         if (rc[i] != RTB_OK)
         {
-            const std::string msg = std::string("device ") + std::to_string(m->ctx[i]->device) + ": " + m->ctx[i]->error;
+            const size_t blame = rc[0] != RTB_OK ? 0 : i; // a replica released by a failed first upload only reports that
+            const std::string msg = std::string("device ") + std::to_string(m->ctx[blame]->device) + ": " + m->ctx[blame]->error;
+            const int code = rc[blame];
             rtb_multi_scene_free(m, s);
-            return failMulti(m, rc[i], msg);
+            return failMulti(m, code, msg);
         }
     *out = s;
     return RTB_OK;
@@ -1742,11 +1956,16 @@ extern "C" int rtb_multi_render(rtb_multi *m, const rtb_multi_scene *scene, cons
     }
     std::vector<PendingFrame> P((size_t)n);
     int rc = RTB_OK;
-    for (int i = 0; i < n && rc == RTB_OK; i++)
-    {
-        fr.rank = i;
-        rc = renderLaunch(m->ctx[(size_t)i], scene->s[(size_t)i], F[(size_t)i], &fr, alias, m->ctx[(size_t)i]->stream, true, nullptr, true, P[(size_t)i]);
-        if (rc != RTB_OK) m->error = m->ctx[(size_t)i]->error;
+    { // every device's launch sequence (~15 runtime calls) on its own thread: the last device starts with the first
+        std::vector<int> rcs((size_t)n, RTB_OK);
+        const std::function<void(int)> launch = [&](int i) {
+            rtb_frame fi = fr;
+            fi.rank = i;
+            rcs[(size_t)i] = renderLaunch(m->ctx[(size_t)i], scene->s[(size_t)i], F[(size_t)i], &fi, alias, m->ctx[(size_t)i]->stream, true, nullptr, true, P[(size_t)i]);
+        };
+        m->pool.run(launch);
+        for (int i = 0; i < n; i++)
+            if (rcs[(size_t)i] != RTB_OK && rc == RTB_OK) { rc = rcs[(size_t)i]; m->error = m->ctx[(size_t)i]->error; }
     }
     if (rc == RTB_OK && m->progress) pollProgress(m->ctx.data(), P.data(), n, m->progress, m->progress_user);
     rtb_stats total;
@@ -1773,6 +1992,22 @@ extern "C" int rtb_host_alloc(size_t bytes, void **out)
     *out = nullptr;
     cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable); // every device of the process may store into it
     if (e != cudaSuccess) return fail(nullptr, RTB_ERR_CUDA, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
+    return RTB_OK;
+}
+
+extern "C" int rtb_host_register(void *p, size_t bytes)
+{
+    if (!p || !bytes) return fail(nullptr, RTB_ERR_INVALID, "rtb_host_register: null range");
+    const cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(nullptr, RTB_ERR_CUDA, std::string("cudaHostRegister: ") + cudaGetErrorString(e)); }
+    return RTB_OK;
+}
+
+extern "C" int rtb_host_unregister(void *p)
+{
+    if (!p) return RTB_OK;
+    const cudaError_t e = cudaHostUnregister(p);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(nullptr, RTB_ERR_CUDA, std::string("cudaHostUnregister: ") + cudaGetErrorString(e)); }
     return RTB_OK;
 }
 
