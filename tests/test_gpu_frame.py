@@ -161,6 +161,37 @@ def test_multi_render_assembles_one_host_frame(ctx, devices):
     pinned.close(); ms.close(); m.close(); dev.close(); s.close()
 
 
+@pytest.mark.parametrize("algorithm,size", [("sah", (640, 480)), ("rgrid", (640, 480)), ("fgrid", (320, 240)), ("sah", (328, 200))])
+def test_host_frames_leave_in_groups_of_four_tiles(ctx, algorithm, size):
+    """Frames rendered straight into page-locked host memory: a CTA of the throughput kernels takes four adjacent tiles and
+    stores 384-byte row segments (FrameParams::group4, storeGroup), the tile order is an order of such groups.  Pixels, counters
+    and the 8-bit output are those of the pageable path (device frame + copy, tile-granular order) frame after frame -- raster
+    first frame, learnt order, tiers -- also when frames of both kinds of the same view alternate on one context (the order a
+    tile-granular frame leaves behind is no group order), and for a width that is no multiple of 32 (no group mode)."""
+    w, h = size
+    s = PresetScene(5, algorithm, 40)
+    dev = ctx.upload(s.flat)
+    fr = rtb200.make_frame(w, h, counters=1)
+    ref, st = dev.render(s.camera, s.setting, fr)                       # pageable buffer: device frame + copy
+    ref8, _ = dev.render(s.camera, s.setting, rtb200.make_frame(w, h, layout=rtb200.OUTPUT_RGB8))
+    pinned = rtb200.PinnedArray((h, w, 3))
+    pinned8 = rtb200.PinnedArray(((h * w * 3 + 3) // 4,))
+    host8 = pinned8.array.view(np.uint8)[: h * w * 3].reshape(h, w, 3)
+    for i in range(5):
+        pinned.array[:] = -1.0
+        _, st2 = dev.render(s.camera, s.setting, fr, out=pinned.array)
+        assert np.array_equal(_bits(pinned.array), _bits(ref)), f"frame {i}"
+        assert (st2["n_rays"], st2["n_tri_tests"], st2["n_steps"]) == (st["n_rays"], st["n_tri_tests"], st["n_steps"])
+        if i == 2:  # a tile-granular frame of the same view in between
+            again, _ = dev.render(s.camera, s.setting, fr)
+            assert np.array_equal(_bits(again), _bits(ref))
+    for i in range(3):
+        host8[:] = 7
+        dev.render(s.camera, s.setting, rtb200.make_frame(w, h, layout=rtb200.OUTPUT_RGB8), out=host8)
+        assert np.array_equal(host8, ref8)
+    pinned.close(); pinned8.close(); dev.close(); s.close()
+
+
 @pytest.mark.parametrize("algorithm", ["sah", "rgrid"])
 def test_upload_out_of_page_locked_scene_arrays(ctx, algorithm):
     """rtb_flat_scene.arrays_page_locked: the upload copies H2D straight out of the caller's (registered) arrays instead of

@@ -57,7 +57,10 @@ static double tunable(const char *name, double dflt)
 //   k-d trees, 4K frame or its shards: no gain (the cost distribution is flat: ~1 % of the tiles are within 2x
 //                                      of the heaviest, far too many to render this way) -> tier off.
 #define RTB_SMALL_FRAME_TILES 16384 // up to 0.5 Mpixel
-static int wideCount(int n_tiles, bool long_lists)
+static int wideCountRaw(int n_tiles, bool long_lists);
+// (tier sizes are multiples of four tiles: in group mode, FrameParams::group4, the order is made of groups of four tiles)
+static int wideCount(int n_tiles, bool long_lists) { return wideCountRaw(n_tiles, long_lists) & ~3; }
+static int wideCountRaw(int n_tiles, bool long_lists)
 {
     static const int cap = (int)tunable("RTB_WIDE_CAP", -1), fraction = (int)tunable("RTB_WIDE_FRACTION", 32); // tuning overrides
     if (cap >= 0) return n_tiles / (fraction < 1 ? 1 : fraction) < cap ? n_tiles / (fraction < 1 ? 1 : fraction) : cap;
@@ -84,7 +87,9 @@ static int heavyFractionSmall() { static const int v = (int)tunable("RTB_HEAVY_F
 static float heavyAlpha() { static const float v = (float)tunable("RTB_HEAVY_ALPHA", RTB_HEAVY_ALPHA); return v; }
 // Size limit of the resumable-walk tier.  Small frames have none: there the warp-per-pixel tier takes the heavy
 // tiles and a third kernel in between measured slower (k-d median 400x300: 1.4 ms without, 2.2 ms with).
-static int heavyLimit(int n_tiles)
+static int heavyLimitRaw(int n_tiles);
+static int heavyLimit(int n_tiles) { return heavyLimitRaw(n_tiles) & ~3; }
+static int heavyLimitRaw(int n_tiles)
 {
     static const int forced = (int)tunable("RTB_HEAVY_LIMIT", -1);
     if (forced >= 0) return forced;
@@ -1415,7 +1420,7 @@ static int prepareTileOrder(rtb_ctx *ctx, const rtb_scene *scene, FrameParams &F
     // else starts over with a raster-order frame that measures every tile.
     OrderKey key;
     memset(&key, 0, sizeof(key));
-    key.v[0] = F.width; key.v[1] = F.height; key.v[2] = F.rank; key.v[3] = F.world; key.v[4] = F.row_block; key.v[5] = F.layout | ((long long)F.col_block << 8);
+    key.v[0] = F.width; key.v[1] = F.height; key.v[2] = F.rank; key.v[3] = F.world; key.v[4] = F.row_block; key.v[5] = F.layout | ((long long)F.col_block << 8) | ((long long)F.group4 << 40);
     key.v[6] = F.setting.enable_monte_carlo; key.v[7] = F.n_tiles; key.v[8] = F.setting.max_depth;
     key.v[9] = (long long)F.samples | ((long long)F.sample_first << 20) | ((long long)F.sample_end << 40);
     key.scene_signature = scene->signature;
@@ -1468,11 +1473,16 @@ static int renderLaunch(rtb_ctx *ctx, const rtb_scene *scene, FrameParams &F, co
     if (stream != ctx->stream) CUDA_TRY(ctx, cudaStreamWaitEvent(stream, scene->ready, 0)); // the upload ran on ctx->stream
     int rc = waitLastFrame(ctx, stream);
     if (rc != RTB_OK) return rc;
-    rc = prepareTileOrder(ctx, scene, F);
-    if (rc != RTB_OK) return rc;
     // whole-tile 128-bit stores (storeTile): row-major frames whose 8-pixel row segments are 16-byte aligned
     static const bool wideStore = !(getenv("RTB_WIDE_STORE") && atoi(getenv("RTB_WIDE_STORE")) == 0);
     F.wide_store = wideStore && !F.layout && !F.cost_map && !F.moments && (F.global_out ? F.width : F.local_width) % 4 == 0 && ((uintptr_t)d_out & 15u) == 0;
+    // frames in page-locked host memory: groups of four adjacent tiles per CTA, stored as 384-byte row segments (storeGroup);
+    // RTB_GROUP_STORE=0: tile-granular order with the light tiles in raster order, as before
+    static const bool groupStore = !(getenv("RTB_GROUP_STORE") && atoi(getenv("RTB_GROUP_STORE")) == 0);
+    F.group4 = groupStore && host_frame && F.wide_store && !F.setting.enable_monte_carlo && F.tiles_x % 4 == 0 && F.n_local_rows % RTB_TILE_H == 0 &&
+               F.local_width % (4 * RTB_TILE_W) == 0 && (!F.col_block || F.col_block % (4 * RTB_TILE_W) == 0);
+    rc = prepareTileOrder(ctx, scene, F); // (the order is keyed by group4 too)
+    if (rc != RTB_OK) return rc;
     if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], stream));
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(Counters), stream));
     if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], stream));
@@ -1488,14 +1498,22 @@ static int renderLaunch(rtb_ctx *ctx, const rtb_scene *scene, FrameParams &F, co
         if (blocks > 296) blocks = 296;
         // frames stored straight into host memory order their light tiles by position (k_cost_offsets)
         static const int floorDeltaHost = (int)tunable("RTB_FLOOR_DELTA_HOST", 9), floorDeltaDevice = (int)tunable("RTB_FLOOR_DELTA_DEVICE", 0);
-        const int floorDelta = host_frame ? floorDeltaHost : floorDeltaDevice;
-        k_cost_histogram<<<blocks, 256, 0, stream>>>(ctx->d_cost, F.n_tiles, ctx->d_hist);
+        // Group mode keeps the light tiles in raster order as well -- not for the PCIe write pattern (384-byte segments reach the
+        // link's peak in any order) but for an even OUTPUT RATE: in pure heaviest-first order the cheap floor tiles, most of the
+        // frame's pixels, all come at the end and the link becomes the bound there (4K SAH frame into host memory, kernel ms at
+        // floor 0 / 3 / 6 / 9 / 12 / 16: 5.20 / 5.05 / 4.92 / 4.85 / 4.87 / 4.92; tile-granular stores: 5.11; into HBM: 4.70.
+        // A low-discrepancy instead of raster order of the light groups: 4.80-4.85 on SAH, slower on the k-d median tree and
+        // the flat grid -- not kept.  profiles/r02_group_store.log)
+        static const int floorDeltaGroup = (int)tunable("RTB_FLOOR_DELTA_GROUP", 9);
+        const int floorDelta = host_frame ? (F.group4 ? floorDeltaGroup : floorDeltaHost) : floorDeltaDevice;
+        const int units = F.group4 ? F.n_tiles / 4 : F.n_tiles;
+        k_cost_histogram<<<blocks, 256, 0, stream>>>(ctx->d_cost, units, ctx->d_hist, F.group4);
         const bool smallShard = F.n_tiles <= splitMaxTiles();
         k_cost_offsets<<<1, RTB_COST_BUCKETS, 0, stream>>>(ctx->d_hist, ctx->d_cursor, ctx->d_heavy, F.n_tiles,
                                              smallShard ? heavyBucketsSmall(scene->d.accel) : RTB_HEAVY_BUCKETS,
                                              heavyLimit(F.n_tiles), wideCount(F.n_tiles, scene->long_lists), floorDelta,
                                              smallShard ? heavyAlpha() : 0.f, 148 * RTB_CHAIN_MIN_CTAS * (RTB_CTA_THREADS / 32));
-        k_cost_scatter<<<blocks, 256, 0, stream>>>(ctx->d_cost, F.n_tiles, ctx->d_cursor, ctx->d_order, ctx->d_heavy);
+        k_cost_scatter<<<blocks, 256, 0, stream>>>(ctx->d_cost, units, ctx->d_cursor, ctx->d_order, ctx->d_heavy, F.group4);
         CUDA_TRY(ctx, cudaGetLastError());
         ctx->order_valid = true;
     }

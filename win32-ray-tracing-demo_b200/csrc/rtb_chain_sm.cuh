@@ -327,7 +327,9 @@ k_whitted_chain_sm(const __grid_constant__ DScene S, const __grid_constant__ Fra
         cOut = c;
     }
     // split4 launches give a tile to four warps of 8 lanes: per-pixel stores there
-    if ((F.split4 || !storeTile(F, out, tile, active, cOut, stage[threadIdx.x >> 5])) && active) storePixel(F, out, x, lr, y, cOut, t_start, rays, pr);
+    // (group stores only in the launch that renders the bulk of a frame: there no warp of a CTA has left above)
+    const bool grouped = !F.split4 && !F.skip_heavy && storeGroup(F, out, tile, active, cOut, stage);
+    if (!grouped && (F.split4 || !storeTile(F, out, tile, active, cOut, stage[threadIdx.x >> 5])) && active) storePixel(F, out, x, lr, y, cOut, t_start, rays, pr);
     finishWarp(F, counters, tile, t_start, rays, ProbeCounts<Probe>::tris(pr), ProbeCounts<Probe>::steps(pr));
 }
 

@@ -29,6 +29,10 @@ struct FrameParams
     int moments;    // RTB_OUTPUT_MOMENTS (Monte Carlo): six floats per pixel, sum and sum of squares of the per-sample radiance
     int sample_first, sample_end; // Monte Carlo: this launch renders samples [sample_first, sample_end) of `samples`
     int wide_store; // row-major output, 16-byte aligned rows: full tiles leave through storeTile()
+    int group4;     // frames stored straight into page-locked HOST memory: the tile order is an order of GROUPS of four
+                    // horizontally adjacent tiles (order[4p + k] = 4g + k), so a CTA of the throughput kernels holds one
+                    // 32x4-pixel block and stores it as four 384-byte row segments (storeGroup); tier boundaries are
+                    // multiples of four
     int tiles_x, n_tiles;
     const unsigned int *order; // [n_tiles] tile ids, heaviest first; nullptr = raster order
     unsigned int *cost;        // [n_tiles] cycles >> 6 the throughput kernel last spent on each tile; may be nullptr
@@ -55,6 +59,7 @@ struct FrameParams
 __device__ __forceinline__ unsigned int heavyCount(const FrameParams &F)
 {
     unsigned int h = __ldg(F.n_heavy);
+    if (F.group4) h = (h + 3u) & ~3u; // whole groups (a count left behind by a tile-granular frame may be anything)
     if (h > F.heavy_cap) h = F.heavy_cap;
     return h < F.n_wide ? F.n_wide : h;
 }
@@ -182,6 +187,58 @@ __device__ __forceinline__ bool storeTile(const FrameParams &F, float *out, unsi
     return true;
 }
 #define RTB_TILE_STAGE_WORDS 96
+
+// CTA-wide store of the throughput kernels for frames in page-locked HOST memory (FrameParams::group4).  Written tile by
+// tile, every 96-byte row segment is its own PCIe write unless a neighbouring tile finishes at the same moment.  Measured on
+// a B200 (tools/probes/pcie_store_probe.cu, a 3840x2880 float frame stored into host memory by an otherwise idle kernel):
+// 96-byte segments reach 49.6 GB/s in raster order but 25.5 GB/s in any other order; 384-byte segments 52 GB/s in ANY order
+// (the copy engine: 57 GB/s).  So the four warps of a CTA take four horizontally adjacent tiles (the order is an order of
+// such groups), pass the 32x4 pixels through the CTA's staging memory and 96 threads store them as four 384-byte row
+// segments of 128-bit stores (8-bit frames: four 96-byte segments of 32-bit stores).  4K SAH frame into host memory:
+// 5.11 -> 4.85 ms (into HBM: 4.70), profiles/r02_group_store.log.
+// All threads of the CTA must call it.  false: group mode is off, a tile is ragged, or the CTA's tiles are not one group
+// (an order inherited from a tile-granular frame) -- nothing was stored, the caller stores per tile.
+__device__ __forceinline__ bool storeGroup(const FrameParams &F, float *out, unsigned int tile, bool active, V3 c,
+                                           uint32_t (*stage)[RTB_TILE_STAGE_WORDS])
+{
+    if (!F.group4 || !F.wide_store) return false; // uniform over the launch
+    __shared__ unsigned int groupTile[RTB_CTA_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) groupTile[warp] = tile;
+    if (!__syncthreads_and(active && tile != 0xffffffffu)) return false;
+    const unsigned int t0 = groupTile[0];
+    if ((t0 & 3u) != 0u || groupTile[1] != t0 + 1u || groupTile[2] != t0 + 2u || groupTile[3] != t0 + 3u) return false; // uniform
+    if (F.rgb8)
+    {
+        unsigned char *sb = reinterpret_cast<unsigned char *>(stage[warp]);
+        const float r = (c.x > 1.0f) ? 1.0f : c.x, g = (c.y > 1.0f) ? 1.0f : c.y, b = (c.z > 1.0f) ? 1.0f : c.z;
+        sb[3 * lane + 0] = (unsigned char)f2i(r * 255); sb[3 * lane + 1] = (unsigned char)f2i(g * 255); sb[3 * lane + 2] = (unsigned char)f2i(b * 255);
+    }
+    else
+    {
+        float *sf = reinterpret_cast<float *>(stage[warp]);
+        sf[3 * lane + 0] = c.x; sf[3 * lane + 1] = c.y; sf[3 * lane + 2] = c.z;
+    }
+    __syncthreads();
+    if (threadIdx.x < 96)
+    {
+        const int row = threadIdx.x / 24, seg = threadIdx.x - row * 24; // 16-byte (4-byte) chunk `seg` of the group's row segment
+        const int k = seg / 6, j = seg - k * 6;                         // tile k of the group, chunk j of that tile's row
+        const int ty = t0 / F.tiles_x, tx = t0 - ty * F.tiles_x;
+        size_t rowSlot = (size_t)(ty * RTB_TILE_H + row) * F.local_width + (size_t)tx * RTB_TILE_W;
+        if (F.global_out)
+        { // a group is 32 consecutive pixels of the whole frame too (column blocks are multiples of 32 in group mode)
+            int xg, yg;
+            localToGlobal(F, tx * RTB_TILE_W, ty * RTB_TILE_H + row, xg, yg);
+            rowSlot = (size_t)yg * F.width + xg;
+        }
+        if (F.rgb8)
+            *reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(out) + 3 * rowSlot + 4 * seg) = stage[k][row * 6 + j];
+        else
+            *reinterpret_cast<float4 *>(out + 3 * rowSlot + 4 * seg) = reinterpret_cast<const float4 *>(stage[k])[row * 6 + j];
+    }
+    return true;
+}
 
 // per-warp epilogue: record the tile's cost, add the warp's counters to the frame totals
 __device__ __forceinline__ void finishWarp(const FrameParams &F, Counters *g, unsigned int tile, long long t_start,
@@ -312,7 +369,8 @@ k_whitted_chain(const __grid_constant__ DScene S, const __grid_constant__ FrameP
     __shared__ __align__(16) uint32_t stage[RTB_CTA_THREADS / 32][RTB_TILE_STAGE_WORDS];
     V3 c = v3(0, 0, 0);
     if (active) c = chainPerRay<FOLD>(S, F, x, y, rays, pr);
-    if (!storeTile(F, out, tile, active, c, stage[threadIdx.x >> 5]) && active) storePixel(F, out, x, lr, y, c, t_start, rays, pr);
+    if (!storeGroup(F, out, tile, active, c, stage) && !storeTile(F, out, tile, active, c, stage[threadIdx.x >> 5]) && active)
+        storePixel(F, out, x, lr, y, c, t_start, rays, pr);
     finishWarp(F, counters, tile, t_start, rays, ProbeCounts<Probe>::tris(pr), ProbeCounts<Probe>::steps(pr));
 }
 
