@@ -21,6 +21,7 @@ ap.add_argument("--world", type=int, default=1)
 ap.add_argument("--col-block", type=int, default=0)
 ap.add_argument("--reps", type=int, default=8)
 ap.add_argument("--tag", default=os.environ.get("TAG", ""))
+ap.add_argument("--global-frame", action="store_true", help="shards store into ONE whole device frame (RTB_LAYOUT_GLOBAL), as the ranks of bench.py do")
 args = ap.parse_args()
 ctx = rtb200.Context(0)
 st = torch.cuda.Stream()
@@ -34,8 +35,9 @@ for name in args.workloads.split(","):
     for (W, H) in sizes:
         per_rank = []
         for rank in range(args.world):
-            fr = rtb200.make_frame(W, H, samples=wl["samples"], rank=rank, world=args.world, col_block=args.col_block if args.world > 1 else 0)
-            buf = torch.empty((max(rtb200.shard_rows(fr), 1), rtb200.shard_width(fr), 3), dtype=torch.float32, device="cuda:0")
+            fr = rtb200.make_frame(W, H, samples=wl["samples"], rank=rank, world=args.world, col_block=args.col_block if args.world > 1 else 0,
+                                   layout=rtb200.LAYOUT_GLOBAL if args.global_frame else 0)
+            buf = torch.empty((H, W, 3) if args.global_frame else (max(rtb200.shard_rows(fr), 1), rtb200.shard_width(fr), 3), dtype=torch.float32, device="cuda:0")
             ctx.forget_schedule()
             t = [d.render_device(s.camera, setting, fr, buf.data_ptr(), st.cuda_stream, want_stats=True) for _ in range(args.reps)]
             ms = [x["kernel_ms"] for x in t]

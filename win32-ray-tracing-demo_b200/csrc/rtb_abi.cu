@@ -1479,7 +1479,13 @@ static int renderLaunch(rtb_ctx *ctx, const rtb_scene *scene, FrameParams &F, co
     // frames in page-locked host memory: groups of four adjacent tiles per CTA, stored as 384-byte row segments (storeGroup);
     // RTB_GROUP_STORE=0: tile-granular order with the light tiles in raster order, as before
     static const bool groupStore = !(getenv("RTB_GROUP_STORE") && atoi(getenv("RTB_GROUP_STORE")) == 0);
-    F.group4 = groupStore && host_frame && F.wide_store && !F.setting.enable_monte_carlo && F.tiles_x % 4 == 0 && F.n_local_rows % RTB_TILE_H == 0 &&
+    // ... and column-block shards that store into a whole frame in DEVICE memory (RTB_LAYOUT_GLOBAL, 5 ranks and more in bench.py):
+    // for all ranks but the owner that frame is peer memory and the stores cross NVLink.  8 B200, 4K SAH step 1.282 -> 1.258 ms;
+    // row shards (2 ranks) lose instead, 2.87 -> 2.95 ms: the four tiles of a CTA wait for the slowest one, which costs more than
+    // the NVLink writes gain when a rank holds half a frame (profiles/r02_group_store.log).  RTB_GROUP_STORE_PEER=0: off.
+    static const bool groupPeer = !(getenv("RTB_GROUP_STORE_PEER") && atoi(getenv("RTB_GROUP_STORE_PEER")) == 0);
+    const bool peer_frame = groupPeer && !host_frame && F.global_out && F.world > 1 && F.col_block > 0;
+    F.group4 = groupStore && (host_frame || peer_frame) && F.wide_store && !F.setting.enable_monte_carlo && F.tiles_x % 4 == 0 && F.n_local_rows % RTB_TILE_H == 0 &&
                F.local_width % (4 * RTB_TILE_W) == 0 && (!F.col_block || F.col_block % (4 * RTB_TILE_W) == 0);
     rc = prepareTileOrder(ctx, scene, F); // (the order is keyed by group4 too)
     if (rc != RTB_OK) return rc;
