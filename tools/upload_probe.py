@@ -14,10 +14,13 @@ from bench import WORKLOADS  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="p5_sah_4k")
 ap.add_argument("--reps", type=int, default=8)
+ap.add_argument("--pin", action="store_true", help="page-lock the scene arrays in place (rtb_flat_scene.arrays_page_locked)")
 args = ap.parse_args()
 wl = WORKLOADS[args.workload]
 s = rtb200.PresetScene(wl["preset"], wl["algorithm"], wl["segments"])
 ctx = rtb200.Context(0)
+if args.pin:
+    s.pin()
 for i in range(args.reps):
     t0 = time.perf_counter()
     d = ctx.upload(s.flat)

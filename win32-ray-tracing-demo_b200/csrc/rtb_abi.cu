@@ -110,6 +110,77 @@ struct OrderKey
     rtb_camera cam;
 };
 
+// A few worker threads that sleep on a condition variable between jobs.  Two users: an rtb_multi (one worker per device beyond
+// the first: the per-device halves of an upload or of a frame launch run side by side, the calling thread takes device 0) and
+// every context's scene validation (the whole-stream checks of rtb_scene_upload, cut into tasks).  Thread creation costs
+// 30-60 us a piece, as much as the work of one task, hence a pool.
+struct WorkerPool
+{
+    std::vector<std::thread> threads;
+    std::mutex m;
+    std::condition_variable cv_job, cv_done;
+    std::function<void(int)> job;
+    unsigned long long generation = 0;
+    int pending = 0;
+    bool stop = false;
+
+    void start(int n_workers)
+    {
+        for (int w = 1; w <= n_workers; w++)
+            threads.emplace_back([this, w]() {
+                unsigned long long seen = 0;
+                std::unique_lock<std::mutex> lock(m);
+                for (;;)
+                {
+                    cv_job.wait(lock, [&]() { return stop || generation != seen; });
+                    if (stop) return;
+                    seen = generation;
+                    lock.unlock();
+                    job(w); // `job` stays untouched until finish() has seen pending == 0
+                    lock.lock();
+                    if (--pending == 0) cv_done.notify_all();
+                }
+            });
+    }
+    int workers() const { return (int)threads.size(); }
+    // fn(w) on every worker w = 1 .. workers(); returns at once.  One job at a time: finish() before the next begin().
+    void begin(std::function<void(int)> fn)
+    {
+        if (threads.empty()) return;
+        {
+            std::lock_guard<std::mutex> lock(m);
+            job = std::move(fn);
+            pending = (int)threads.size();
+            generation++;
+        }
+        cv_job.notify_all();
+    }
+    void finish()
+    {
+        if (threads.empty()) return;
+        std::unique_lock<std::mutex> lock(m);
+        cv_done.wait(lock, [&]() { return pending == 0; });
+    }
+    // fn(i) for i = 1 .. workers() on the worker threads, fn(0) on the calling thread; returns when all have returned
+    void run(const std::function<void(int)> &fn)
+    {
+        begin(fn);
+        fn(0);
+        finish();
+    }
+    void shutdown()
+    {
+        {
+            std::lock_guard<std::mutex> lock(m);
+            stop = true;
+        }
+        cv_job.notify_all();
+        for (std::thread &t : threads) t.join();
+        threads.clear();
+    }
+    ~WorkerPool() { shutdown(); }
+};
+
 // rtb_multi_scene_upload: ONE flat scene goes to every device of the set.  The first device's upload (the producer) stages
 // each stream once into its page-locked ring (portable: every device copies from it) and publishes the staged address; the
 // other devices' uploads (replicas, on worker threads, a step behind the producer) issue their H2D copies from the same
@@ -166,6 +237,7 @@ struct rtb_ctx
     // asynchronous H2D copies (a pageable source makes every cudaMemcpyAsync a staged, partly synchronous copy)
     char *stage = nullptr;
     size_t stage_cap = 0, stage_used = 0;
+    WorkerPool *checkers = nullptr;       // threads of the scene validation (started by the first validating upload)
     std::vector<rtb_ctx *> stage_readers; // contexts of the same rtb_multi whose streams copy out of this ring too
     StageShare *share = nullptr; // set for the duration of an rtb_multi_scene_upload
     bool share_producer = false;
@@ -330,6 +402,7 @@ extern "C" int rtb_shutdown(rtb_ctx *ctx)
     if (ctx->d_heavy) cudaFree(ctx->d_heavy);
     if (ctx->stage) cudaFreeHost(ctx->stage);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx->checkers;
     delete ctx;
     return RTB_OK;
 }
@@ -555,41 +628,78 @@ static int packPairs(rtb_ctx *ctx, rtb_scene *s, const uint32_t *refs, size_t n_
 // pre-order k-d array -> 0 when it is a well-formed tree (every inner node's right child lies behind its left
 // subtree, every node reached exactly once), maxDepth = deepest node.  One linear pass with an explicit stack of
 // pending right children: the recursive walk took 0.2 ms of every upload.
-static int kdDepth(const rtb_kdnode *nodes, int n, int &maxDepth)
+// (range form: is nodes[a .. b) a well-formed subtree that ends exactly at b, its root at depth `depth0`?  A well-formed pre-order
+// array consists of such ranges -- node 0's left subtree [1, right) and right subtree [right, n), and so on down -- which is how
+// rtb_scene_upload cuts the check into tasks for its worker threads.)
+static int kdDepthRange(const rtb_kdnode *nodes, int a, int b, int depth0, int &maxDepth)
 {
-    std::vector<std::pair<int, int>> pending; // (index of a right child, its depth)
-    pending.reserve(128);
-    int depth = 0;
-    maxDepth = 0;
-    for (int i = 0; i < n; i++)
+    // Pending right children, innermost last, with the depth they resume at; slot 0 is a sentinel, "the range ends at b".
+    // Whether a node is a leaf is a coin toss for the branch predictor (69 k nodes: 0.45 ms of every upload with a branch per
+    // node and a std::vector stack), so the pass is written with selects: both outcomes are computed, the slot above the top is
+    // written either way and only an inner node keeps it.  Invariant: pending entries <= depth - depth0 <= 64, so 72 slots suffice.
+    maxDepth = depth0;
+    if (b <= a) return -1;
+    int pendR[72], pendD[72];
+    pendR[0] = b; pendD[0] = depth0;
+    int sp = 0, depth = depth0, deepest = depth0;
+    unsigned int bad = 0;
+    for (int i = a; i < b; i++)
     {
-        if (depth > 64) return -1;
-        if (depth > maxDepth) maxDepth = depth;
-        if ((nodes[i].b & 3u) == 3u)
-        { // leaf: the next node in pre-order is the nearest pending right child
-            if (pending.empty()) return i == n - 1 ? 0 : -1;
-            if (pending.back().first != i + 1) return -1;
-            depth = pending.back().second;
-            pending.pop_back();
-        }
-        else
-        {
-            const int right = (int)(nodes[i].b >> 2);
-            if (right <= i + 1 || right >= n) return -1;
-            if (!pending.empty() && right >= pending.back().first) return -1; // must end before the enclosing right child
-            pending.push_back(std::make_pair(right, depth + 1));
-            depth += 1; // the left child follows directly
-        }
+        const unsigned int w = nodes[i].b;
+        const bool leaf = (w & 3u) == 3u;
+        const int right = (int)(w >> 2);
+        const int top = pendR[sp];
+        deepest = depth > deepest ? depth : deepest;
+        // leaf: the next node in pre-order is the nearest pending right child (the sentinel: the end of the range);
+        // inner: its right child lies behind its left child and before the enclosing pending right child
+        const unsigned int badLeaf = (unsigned int)(top != i + 1), badInner = (unsigned int)(right <= i + 1) | (unsigned int)(right >= top);
+        bad |= leaf ? badLeaf : badInner;
+        pendR[sp + 1] = right;
+        pendD[sp + 1] = depth + 1;
+        const int resume = pendD[sp];
+        depth = leaf ? resume : depth + 1;
+        sp += leaf ? -1 : 1;
+        if ((sp < 0) | (depth > 64)) break; // the subtree has closed (at b - 1, or `bad` is set) / deeper than any supported tree
     }
-    return -1; // ran out of nodes with subtrees still open (n == 0 included)
+    maxDepth = deepest;
+    return (!bad && sp == -1 && depth <= 64) ? 0 : -1; // sp >= 0: ran out of nodes with subtrees still open
+}
+
+// nodes[0 .. n) cut into up to 8 subtree ranges, largest split first; the nodes split at are checked here (inner, right child
+// inside the range).  A range whose root cannot be split stays whole: its own kdDepthRange reports what is wrong with it.
+struct KdRange { int a, b, depth; };
+static std::vector<KdRange> kdSubtrees(const rtb_kdnode *nodes, int n)
+{
+    std::vector<KdRange> ranges(1, KdRange{0, n, 0});
+    std::vector<char> whole(1, 0);
+    while (ranges.size() < 8)
+    {
+        int k = -1;
+        for (size_t i = 0; i < ranges.size(); i++)
+            if (!whole[i] && ranges[i].b - ranges[i].a >= 64 && (k < 0 || ranges[i].b - ranges[i].a > ranges[(size_t)k].b - ranges[(size_t)k].a)) k = (int)i;
+        if (k < 0) break;
+        const KdRange r = ranges[(size_t)k];
+        const unsigned int w = nodes[r.a].b;
+        const int right = (int)(w >> 2);
+        if ((w & 3u) == 3u || right <= r.a + 1 || right >= r.b) { whole[(size_t)k] = 1; continue; }
+        ranges[(size_t)k] = KdRange{r.a + 1, right, r.depth + 1};
+        ranges.push_back(KdRange{right, r.b, r.depth + 1});
+        whole.push_back(0);
+    }
+    return ranges;
 }
 
 extern "C" int rtb_kd_validate(const rtb_kdnode *nodes, int32_t n, int32_t *max_depth)
 {
     if (!nodes || n <= 0) return RTB_ERR_INVALID;
-    int depth = 0;
-    if (kdDepth(nodes, n, depth) != 0) return RTB_ERR_INVALID;
-    if (max_depth) *max_depth = depth;
+    int deepest = 0; // the same decomposition rtb_scene_upload hands to its checker threads, here one range after the other
+    for (const KdRange &r : kdSubtrees(nodes, n))
+    {
+        int depth = 0;
+        if (kdDepthRange(nodes, r.a, r.b, r.depth, depth) != 0) return RTB_ERR_INVALID;
+        deepest = depth > deepest ? depth : deepest;
+    }
+    if (max_depth) *max_depth = deepest;
     return RTB_OK;
 }
 
@@ -823,30 +933,126 @@ static int buildKdOnDevice(rtb_ctx *ctx, rtb_scene *s, const rtb_flat_scene *f, 
 // copies and k_pack_triangles do not index.
 struct BackgroundChecks
 {
-    std::vector<std::thread> threads;
+    typedef std::function<std::pair<int, const char *>()> Task; // -> {code, message}
+    WorkerPool *pool = nullptr;
+    std::vector<Task> tasks;
     std::mutex m;
     int code = RTB_OK;
     std::string msg;
     bool enabled = true; // false: the caller has validated this very flat scene already (rtb_multi_scene_upload: replicas)
-    template <class Fn> void run(Fn fn) // fn() -> {code, message}; the first failure is kept
+    bool started = false;
+    void keep(const std::pair<int, const char *> &r)
     {
-        if (!enabled) return;
-        threads.emplace_back([this, fn]() {
-            const std::pair<int, const char *> r = fn();
-            if (r.first != RTB_OK)
-            {
-                std::lock_guard<std::mutex> lock(m);
-                if (code == RTB_OK) { code = r.first; msg = r.second; }
-            }
-        });
+        if (r.first == RTB_OK) return;
+        std::lock_guard<std::mutex> lock(m);
+        if (code == RTB_OK) { code = r.first; msg = r.second; }
     }
-    void join()
+    template <class Fn> void run(Fn fn) { if (enabled) tasks.emplace_back(fn); } // queued; start() hands the tasks to the pool
+    void start()
     {
-        for (std::thread &t : threads) t.join();
-        threads.clear();
+        if (!enabled || started || tasks.empty() || !pool || pool->workers() == 0) return;
+        started = true;
+        const size_t W = (size_t)pool->workers();
+        pool->begin([this, W](int w) { for (size_t t = (size_t)w - 1; t < tasks.size(); t += W) keep(tasks[t]()); });
+    }
+    void join() // a failure is kept in code / msg
+    {
+        if (started) pool->finish();
+        else for (Task &t : tasks) keep(t()); // never handed to the pool: here and now
+        started = false;
+        tasks.clear();
     }
     ~BackgroundChecks() { join(); }
 };
+
+static bool gridHeaderOk(const rtb_flat_scene *f)
+{
+    const int64_t cells = (int64_t)f->grid_dims[0] * f->grid_dims[1] * f->grid_dims[2];
+    return !(f->grid_dims[0] <= 0 || f->grid_dims[1] <= 0 || f->grid_dims[2] <= 0 || cells > 0x7fffffffLL ||
+             f->n_cellwords != (cells + 31) / 32 || !f->grid_words || !f->grid_cell_start || (f->n_cell_refs > 0 && !f->grid_cell_tris));
+}
+static bool kdHeaderOk(const rtb_flat_scene *f) { return !(f->n_kd_nodes <= 0 || !f->kd_nodes || (f->n_kd_refs > 0 && !f->kd_leaf_tris)); }
+
+// The whole-stream checks of the accelerator arrays the walks index with, cut into tasks of similar size for the context's
+// checker threads (nothing is queued when the header fields are inconsistent: sceneUpload refuses such a scene before anything
+// reads its arrays).  Every condition is local -- a word's rank against the next word's, a list start against the next, a
+// reference against the triangle count -- except the shape of the k-d tree, which splits into subtrees (kdDepthRange).
+static void queueSceneChecks(const rtb_flat_scene *f, BackgroundChecks &checks)
+{
+    typedef std::pair<int, const char *> R;
+    const int64_t CHUNKS = 4;
+    auto slices = [&](int64_t n, const std::function<R(int64_t, int64_t)> &body) { // body(lo, hi) over [0, n) in CHUNKS slices
+        for (int64_t c = 0; c < CHUNKS; c++)
+        {
+            const int64_t lo = n * c / CHUNKS, hi = n * (c + 1) / CHUNKS;
+            if (hi > lo) checks.run([body, lo, hi]() { return body(lo, hi); });
+        }
+    };
+    if (f->n_tris < 0) return;
+    const uint32_t nTris = (uint32_t)f->n_tris;
+    if ((f->accel == RTB_ACCEL_REGULAR_GRID || f->accel == RTB_ACCEL_FLAT_GRID) && f->grid_words)
+    {
+        if (!gridHeaderOk(f)) return;
+        if (f->n_cells_used < 0) { checks.run([]() { return R((int)RTB_ERR_INVALID, "rtb_scene_upload: negative cell count"); }); return; }
+        // the directory the walks index with: every word's rank is the number of occupied cells before it, the occupied
+        // cells number n_cells_used, and the list starts ascend from 0 to n_cell_refs (no empty list: the pair scan needs
+        // at least one entry)
+        slices(f->n_cellwords, [f](int64_t lo, int64_t hi) {
+            bool bad = lo == 0 && f->grid_words[0].rank != 0;
+            for (int64_t w = lo; w < hi; w++)
+            {
+                const uint64_t next = w + 1 < f->n_cellwords ? (uint64_t)f->grid_words[w + 1].rank : (uint64_t)f->n_cells_used;
+                bad |= (uint64_t)f->grid_words[w].rank + (uint64_t)__builtin_popcount(f->grid_words[w].bits) != next;
+            }
+            return R(bad ? (int)RTB_ERR_INVALID : (int)RTB_OK, "rtb_scene_upload: grid word ranks do not match the occupancy bits");
+        });
+        checks.run([f]() {
+            const int64_t cells = (int64_t)f->grid_dims[0] * f->grid_dims[1] * f->grid_dims[2];
+            if (f->n_cellwords == 0 && f->n_cells_used != 0) return R((int)RTB_ERR_INVALID, "rtb_scene_upload: grid word ranks do not match the occupancy bits");
+            if (f->n_cellwords > 0 && (cells & 31) != 0 && (f->grid_words[f->n_cellwords - 1].bits >> (cells & 31)) != 0)
+                return R((int)RTB_ERR_INVALID, "rtb_scene_upload: occupancy bits beyond the last cell");
+            const bool ends = f->grid_cell_start[0] == 0 && (int64_t)f->grid_cell_start[f->n_cells_used] == f->n_cell_refs;
+            return R(ends ? (int)RTB_OK : (int)RTB_ERR_INVALID, "rtb_scene_upload: grid cell list starts are not strictly ascending from 0 to n_cell_refs");
+        });
+        slices(f->n_cells_used, [f](int64_t lo, int64_t hi) {
+            bool order = true;
+            for (int64_t i = lo; i < hi; i++) order &= f->grid_cell_start[i] < f->grid_cell_start[i + 1];
+            return R(order ? (int)RTB_OK : (int)RTB_ERR_INVALID, "rtb_scene_upload: grid cell list starts are not strictly ascending from 0 to n_cell_refs");
+        });
+        slices(f->n_cell_refs, [f, nTris](int64_t lo, int64_t hi) {
+            uint32_t maxRef = 0; // branch-free maximum: the compiler vectorises it (up to 6.4 M references)
+            for (int64_t i = lo; i < hi; i++) maxRef = f->grid_cell_tris[i] > maxRef ? f->grid_cell_tris[i] : maxRef;
+            return R(maxRef >= nTris ? (int)RTB_ERR_INVALID : (int)RTB_OK, "rtb_scene_upload: grid triangle reference out of range");
+        });
+    }
+    else if ((f->accel == RTB_ACCEL_KD_MEDIAN || f->accel == RTB_ACCEL_KD_SAH) && f->kd_nodes)
+    {
+        if (!kdHeaderOk(f)) return;
+        // the tree's shape: one task per subtree range
+        for (const KdRange &r : kdSubtrees(f->kd_nodes, f->n_kd_nodes))
+            checks.run([f, r]() {
+                int maxDepth = 0;
+                if (kdDepthRange(f->kd_nodes, r.a, r.b, r.depth, maxDepth) != 0) return R((int)RTB_ERR_INVALID, "rtb_scene_upload: k-d nodes are not a pre-order tree");
+                if (2 * maxDepth + 2 >= RTB_KD_STACK)
+                    return R((int)RTB_ERR_UNSUPPORTED, "rtb_scene_upload: k-d tree deeper than the 50-entry traversal stack allows");
+                return R((int)RTB_OK, "");
+            });
+        slices(f->n_kd_nodes, [f](int64_t lo, int64_t hi) { // branch-free maxima (the compiler vectorises them)
+            int64_t leafEnd = 0;
+            for (int64_t i = lo; i < hi; i++)
+            {
+                const int64_t e = ((f->kd_nodes[i].b & 3u) == 3u) ? (int64_t)f->kd_nodes[i].a + (f->kd_nodes[i].b >> 2) : 0;
+                leafEnd = e > leafEnd ? e : leafEnd;
+            }
+            return R(leafEnd > f->n_kd_refs ? (int)RTB_ERR_INVALID : (int)RTB_OK, "rtb_scene_upload: k-d leaf range out of bounds");
+        });
+        slices(f->n_kd_refs, [f, nTris](int64_t lo, int64_t hi) {
+            uint32_t maxRef = 0;
+            for (int64_t i = lo; i < hi; i++) maxRef = f->kd_leaf_tris[i] > maxRef ? f->kd_leaf_tris[i] : maxRef;
+            return R(maxRef >= nTris ? (int)RTB_ERR_INVALID : (int)RTB_OK, "rtb_scene_upload: k-d triangle reference out of range");
+        });
+    }
+}
 
 // RTB_UPLOAD_TIMING=1: host-side laps of rtb_scene_upload on stderr (profiling aid)
 struct UploadLaps
@@ -954,7 +1160,16 @@ static int sceneUpload(rtb_ctx *ctx, const rtb_flat_scene *f, rtb_scene **out, b
         rtb_scene_free(ctx, s);
         return code;
     };
-    laps.lap("header");
+    // The whole-array checks start first, on the context's checker threads: with page-locked source arrays nothing else of an
+    // upload takes as long (SAH scene: 0.45 ms for the tree's shape alone when it was one pass on one thread).
+    if (validate && s->has_tunnel)
+    {
+        if (!ctx->checkers) { ctx->checkers = new WorkerPool(); ctx->checkers->start(8); }
+        checks.pool = ctx->checkers;
+        queueSceneChecks(f, checks);
+        checks.start();
+    }
+    laps.lap("header + checks queued");
 
     // every stream is packed / copied into the page-locked staging ring and leaves with an asynchronous copy:
     // no intermediate synchronisation, the upload is ordered before the renders on ctx->stream
@@ -988,38 +1203,8 @@ static int sceneUpload(rtb_ctx *ctx, const rtb_flat_scene *f, rtb_scene **out, b
         }
         else if (f->accel == RTB_ACCEL_REGULAR_GRID || f->accel == RTB_ACCEL_FLAT_GRID)
         {
-            const int64_t cells = (int64_t)f->grid_dims[0] * f->grid_dims[1] * f->grid_dims[2];
-            if (f->grid_dims[0] <= 0 || f->grid_dims[1] <= 0 || f->grid_dims[2] <= 0 || cells > 0x7fffffffLL ||
-                f->n_cellwords != (cells + 31) / 32 || !f->grid_words || !f->grid_cell_start ||
-                (f->n_cell_refs > 0 && !f->grid_cell_tris))
-                return bail(fail(ctx, RTB_ERR_INVALID, "rtb_scene_upload: inconsistent grid directory"));
-            checks.run([f]() {
-                // the directory the walks index with: every word's rank is the number of occupied cells before it, the
-                // occupied cells number n_cells_used, and the list starts ascend from 0 to n_cell_refs (no empty list:
-                // the pair scan needs at least one entry)
-                if (f->n_cells_used < 0) return std::make_pair((int)RTB_ERR_INVALID, "rtb_scene_upload: negative cell count");
-                uint64_t running = 0;
-                bool bad = false;
-                for (int64_t w = 0; w < f->n_cellwords; w++)
-                {
-                    bad |= f->grid_words[w].rank != running;
-                    running += (uint64_t)__builtin_popcount(f->grid_words[w].bits);
-                }
-                if (bad || running != (uint64_t)f->n_cells_used)
-                    return std::make_pair((int)RTB_ERR_INVALID, "rtb_scene_upload: grid word ranks do not match the occupancy bits");
-                const int64_t cells = (int64_t)f->grid_dims[0] * f->grid_dims[1] * f->grid_dims[2];
-                if (f->n_cellwords > 0 && (cells & 31) != 0 && (f->grid_words[f->n_cellwords - 1].bits >> (cells & 31)) != 0)
-                    return std::make_pair((int)RTB_ERR_INVALID, "rtb_scene_upload: occupancy bits beyond the last cell");
-                bool order = f->grid_cell_start[0] == 0 && (int64_t)f->grid_cell_start[f->n_cells_used] == f->n_cell_refs;
-                for (int64_t i = 0; i < f->n_cells_used; i++) order &= f->grid_cell_start[i] < f->grid_cell_start[i + 1];
-                return std::make_pair(order ? (int)RTB_OK : (int)RTB_ERR_INVALID, "rtb_scene_upload: grid cell list starts are not strictly ascending from 0 to n_cell_refs");
-            });
-            checks.run([f]() {
-                uint32_t maxRef = 0; // branch-free maximum: the compiler vectorises it (up to 6.4 M references)
-                for (int64_t i = 0; i < f->n_cell_refs; i++) maxRef = f->grid_cell_tris[i] > maxRef ? f->grid_cell_tris[i] : maxRef;
-                const bool bad = f->n_cell_refs > 0 && maxRef >= (uint32_t)f->n_tris;
-                return std::make_pair(bad ? (int)RTB_ERR_INVALID : (int)RTB_OK, "rtb_scene_upload: grid triangle reference out of range");
-            });
+            if (!gridHeaderOk(f)) return bail(fail(ctx, RTB_ERR_INVALID, "rtb_scene_upload: inconsistent grid directory"));
+            // (the whole-array checks of the directory and the references are running: queueSceneChecks above)
             d.g_origin = {f->grid_origin[0], f->grid_origin[1], f->grid_origin[2]};
             d.g_cell = {f->grid_cell[0], f->grid_cell[1], f->grid_cell[2]};
             d.nx = f->grid_dims[0]; d.ny = f->grid_dims[1]; d.nz = f->grid_dims[2];
@@ -1043,31 +1228,7 @@ static int sceneUpload(rtb_ctx *ctx, const rtb_flat_scene *f, rtb_scene **out, b
         }
         else if (f->accel == RTB_ACCEL_KD_MEDIAN || f->accel == RTB_ACCEL_KD_SAH)
         {
-            if (f->n_kd_nodes <= 0 || !f->kd_nodes || (f->n_kd_refs > 0 && !f->kd_leaf_tris))
-                return bail(fail(ctx, RTB_ERR_INVALID, "rtb_scene_upload: k-d tree missing"));
-            checks.run([f]() {
-                int maxDepth = 0;
-                if (kdDepth(f->kd_nodes, f->n_kd_nodes, maxDepth) != 0)
-                    return std::make_pair((int)RTB_ERR_INVALID, "rtb_scene_upload: k-d nodes are not a pre-order tree");
-                if (2 * maxDepth + 2 >= RTB_KD_STACK)
-                    return std::make_pair((int)RTB_ERR_UNSUPPORTED, "rtb_scene_upload: k-d tree deeper than the 50-entry traversal stack allows");
-                return std::make_pair((int)RTB_OK, "");
-            });
-            checks.run([f]() {
-                // branch-free maxima (the compiler vectorises them): 69 k nodes + 380 k references per upload
-                int64_t leafEnd = 0;
-                for (int i = 0; i < f->n_kd_nodes; i++)
-                {
-                    const int64_t e = ((f->kd_nodes[i].b & 3u) == 3u) ? (int64_t)f->kd_nodes[i].a + (f->kd_nodes[i].b >> 2) : 0;
-                    leafEnd = e > leafEnd ? e : leafEnd;
-                }
-                if (leafEnd > f->n_kd_refs) return std::make_pair((int)RTB_ERR_INVALID, "rtb_scene_upload: k-d leaf range out of bounds");
-                uint32_t maxRef = 0;
-                for (int64_t i = 0; i < f->n_kd_refs; i++) maxRef = f->kd_leaf_tris[i] > maxRef ? f->kd_leaf_tris[i] : maxRef;
-                if (f->n_kd_refs > 0 && maxRef >= (uint32_t)f->n_tris)
-                    return std::make_pair((int)RTB_ERR_INVALID, "rtb_scene_upload: k-d triangle reference out of range");
-                return std::make_pair((int)RTB_OK, "");
-            });
+            if (!kdHeaderOk(f)) return bail(fail(ctx, RTB_ERR_INVALID, "rtb_scene_upload: k-d tree missing"));
             d.kd_min = {f->kd_min[0], f->kd_min[1], f->kd_min[2]};
             // reference Grid.cpp:13-17: Grid(near, far) keeps size = far - near
             d.kd_size = {f->kd_max[0] - f->kd_min[0], f->kd_max[1] - f->kd_min[1], f->kd_max[2] - f->kd_min[2]};
@@ -1076,7 +1237,9 @@ static int sceneUpload(rtb_ctx *ctx, const rtb_flat_scene *f, rtb_scene **out, b
             d.kd_nodes = nodes;
             if ((rc = uploadArray(ctx, s, f->kd_leaf_tris, (size_t)f->n_kd_refs, &d.kd_tris)) != RTB_OK) return bail(rc);
             // k_pack_pairs indexes the triangle stream with these references: the verdict of the checks comes first
+            laps.lap("k-d arrays queued");
             if ((rc = collectVerdict(ctx, checks)) != RTB_OK) return bail(rc);
+            laps.lap("verdict");
             if ((rc = packPairs(ctx, s, d.kd_tris, (size_t)f->n_kd_refs)) != RTB_OK) return bail(rc);
             s->kd_nodes = f->n_kd_nodes; s->kd_refs = f->n_kd_refs;
         }
@@ -1737,69 +1900,6 @@ extern "C" int rtb_ipc_close(rtb_ctx *ctx, void *mapped)
     }
     return RTB_OK;
 }
-
-// Worker threads of an rtb_multi, one per device beyond the first: the per-device halves of an upload or of a frame launch
-// run side by side (the calling thread takes device 0).  They sleep on a condition variable between calls.
-struct WorkerPool
-{
-    std::vector<std::thread> threads;
-    std::mutex m;
-    std::condition_variable cv_job, cv_done;
-    const std::function<void(int)> *job = nullptr;
-    unsigned long long generation = 0;
-    int pending = 0;
-    bool stop = false;
-
-    void start(int n_workers)
-    {
-        for (int w = 1; w <= n_workers; w++)
-            threads.emplace_back([this, w]() {
-                unsigned long long seen = 0;
-                std::unique_lock<std::mutex> lock(m);
-                for (;;)
-                {
-                    cv_job.wait(lock, [&]() { return stop || generation != seen; });
-                    if (stop) return;
-                    seen = generation;
-                    const std::function<void(int)> *fn = job;
-                    lock.unlock();
-                    (*fn)(w);
-                    lock.lock();
-                    if (--pending == 0) cv_done.notify_one();
-                }
-            });
-    }
-    // fn(i) for i = 1 .. workers on the worker threads, fn(0) on the calling thread; returns when all have returned
-    void run(const std::function<void(int)> &fn)
-    {
-        if (!threads.empty())
-        {
-            std::lock_guard<std::mutex> lock(m);
-            job = &fn;
-            pending = (int)threads.size();
-            generation++;
-        }
-        cv_job.notify_all();
-        fn(0);
-        if (!threads.empty())
-        {
-            std::unique_lock<std::mutex> lock(m);
-            cv_done.wait(lock, [&]() { return pending == 0; });
-            job = nullptr;
-        }
-    }
-    void shutdown()
-    {
-        {
-            std::lock_guard<std::mutex> lock(m);
-            stop = true;
-        }
-        cv_job.notify_all();
-        for (std::thread &t : threads) t.join();
-        threads.clear();
-    }
-    ~WorkerPool() { shutdown(); }
-};
 
 struct rtb_multi
 {
