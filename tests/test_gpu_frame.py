@@ -189,6 +189,17 @@ def test_host_frames_leave_in_groups_of_four_tiles(ctx, algorithm, size):
         host8[:] = 7
         dev.render(s.camera, s.setting, rtb200.make_frame(w, h, layout=rtb200.OUTPUT_RGB8), out=host8)
         assert np.array_equal(host8, ref8)
+    # the reference's column-major order (the RenderProc drop-in's): blocks of 8x16 pixels, 192-byte column segments
+    col = pinned.array.reshape(w, h, 3)
+    col8 = host8.reshape(w, h, 3)
+    for i in range(4):
+        col[:] = -1.0
+        _, st3 = dev.render(s.camera, s.setting, rtb200.make_frame(w, h, counters=1, layout=rtb200.LAYOUT_REFERENCE), out=col)
+        assert np.array_equal(_bits(col.transpose(1, 0, 2)), _bits(ref)), f"reference-order frame {i}"
+        assert st3["n_rays"] == st["n_rays"]
+        col8[:] = 9
+        dev.render(s.camera, s.setting, rtb200.make_frame(w, h, layout=rtb200.LAYOUT_REFERENCE | rtb200.OUTPUT_RGB8), out=col8)
+        assert np.array_equal(col8.transpose(1, 0, 2), ref8)
     pinned.close(); pinned8.close(); dev.close(); s.close()
 
 

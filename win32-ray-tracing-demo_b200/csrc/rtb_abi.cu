@@ -1546,6 +1546,12 @@ static int launchRender(rtb_ctx *ctx, const rtb_scene *scene, FrameParams &F, bo
 // The scheduling state of a context (d_cost, d_order, d_heavy, d_hist, d_counters, the side stream) is shared by all
 // its frames.  Frames are ordered through `last_frame`, recorded behind each frame's last kernel on whatever stream it
 // ran: a frame on another stream, and anything that frees or regrows the state, waits for it first.
+static bool groupStoreEnabled()
+{
+    static const bool on = !(getenv("RTB_GROUP_STORE") && atoi(getenv("RTB_GROUP_STORE")) == 0);
+    return on;
+}
+
 static int waitLastFrame(rtb_ctx *ctx, cudaStream_t stream)
 {
     if (ctx->frame_pending && stream != ctx->last_frame_stream) CUDA_TRY(ctx, cudaStreamWaitEvent(stream, ctx->last_frame, 0));
@@ -1641,7 +1647,7 @@ static int renderLaunch(rtb_ctx *ctx, const rtb_scene *scene, FrameParams &F, co
     F.wide_store = wideStore && !F.layout && !F.cost_map && !F.moments && (F.global_out ? F.width : F.local_width) % 4 == 0 && ((uintptr_t)d_out & 15u) == 0;
     // frames in page-locked host memory: groups of four adjacent tiles per CTA, stored as 384-byte row segments (storeGroup);
     // RTB_GROUP_STORE=0: tile-granular order with the light tiles in raster order, as before
-    static const bool groupStore = !(getenv("RTB_GROUP_STORE") && atoi(getenv("RTB_GROUP_STORE")) == 0);
+    const bool groupStore = groupStoreEnabled();
     // ... and column-block shards that store into a whole frame in DEVICE memory (RTB_LAYOUT_GLOBAL, 5 ranks and more in bench.py):
     // for all ranks but the owner that frame is peer memory and the stores cross NVLink.  8 B200, 4K SAH step 1.282 -> 1.258 ms;
     // row shards (2 ranks) lose instead, 2.87 -> 2.95 ms: the four tiles of a CTA wait for the slowest one, which costs more than
@@ -1650,6 +1656,10 @@ static int renderLaunch(rtb_ctx *ctx, const rtb_scene *scene, FrameParams &F, co
     const bool peer_frame = groupPeer && !host_frame && F.global_out && F.world > 1 && F.col_block > 0;
     F.group4 = groupStore && (host_frame || peer_frame) && F.wide_store && !F.setting.enable_monte_carlo && F.tiles_x % 4 == 0 && F.n_local_rows % RTB_TILE_H == 0 &&
                F.local_width % (4 * RTB_TILE_W) == 0 && (!F.col_block || F.col_block % (4 * RTB_TILE_W) == 0);
+    // the reference's column-major order (what the RenderProc drop-in asks for), whole frame on this device: blocks of 8x16 pixels
+    if (groupStore && host_frame && F.layout == RTB_LAYOUT_REFERENCE && F.world == 1 && !F.cost_map && !F.moments && !F.setting.enable_monte_carlo &&
+        F.width % RTB_TILE_W == 0 && F.height % (4 * RTB_TILE_H) == 0 && F.n_local_rows == F.height && ((uintptr_t)d_out & 15u) == 0)
+        F.group4 = 2;
     rc = prepareTileOrder(ctx, scene, F); // (the order is keyed by group4 too)
     if (rc != RTB_OK) return rc;
     if (timed) CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], stream));
@@ -1676,13 +1686,13 @@ static int renderLaunch(rtb_ctx *ctx, const rtb_scene *scene, FrameParams &F, co
         static const int floorDeltaGroup = (int)tunable("RTB_FLOOR_DELTA_GROUP", 9);
         const int floorDelta = host_frame ? (F.group4 ? floorDeltaGroup : floorDeltaHost) : floorDeltaDevice;
         const int units = F.group4 ? F.n_tiles / 4 : F.n_tiles;
-        k_cost_histogram<<<blocks, 256, 0, stream>>>(ctx->d_cost, units, ctx->d_hist, F.group4);
+        k_cost_histogram<<<blocks, 256, 0, stream>>>(ctx->d_cost, units, ctx->d_hist, F.group4, F.tiles_x);
         const bool smallShard = F.n_tiles <= splitMaxTiles();
         k_cost_offsets<<<1, RTB_COST_BUCKETS, 0, stream>>>(ctx->d_hist, ctx->d_cursor, ctx->d_heavy, F.n_tiles,
                                              smallShard ? heavyBucketsSmall(scene->d.accel) : RTB_HEAVY_BUCKETS,
                                              heavyLimit(F.n_tiles), wideCount(F.n_tiles, scene->long_lists), floorDelta,
                                              smallShard ? heavyAlpha() : 0.f, 148 * RTB_CHAIN_MIN_CTAS * (RTB_CTA_THREADS / 32));
-        k_cost_scatter<<<blocks, 256, 0, stream>>>(ctx->d_cost, units, ctx->d_cursor, ctx->d_order, ctx->d_heavy, F.group4);
+        k_cost_scatter<<<blocks, 256, 0, stream>>>(ctx->d_cost, units, ctx->d_cursor, ctx->d_order, ctx->d_heavy, F.group4, F.tiles_x);
         CUDA_TRY(ctx, cudaGetLastError());
         ctx->order_valid = true;
     }
@@ -1798,7 +1808,8 @@ extern "C" int rtb_render(rtb_ctx *ctx, const rtb_scene *scene, const rtb_camera
         // whole 24-byte row segments with the light tiles in raster order (6.72 -> 6.33 ms); written byte by byte
         // they were slower than a device frame + copy (8.82 vs 7.91 ms)
         static const bool zerocopy8 = !(getenv("RTB_ZEROCOPY_RGB8") && atoi(getenv("RTB_ZEROCOPY_RGB8")) == 0);
-        const bool rgb8Direct = zerocopy8 && !F.layout && (F.global_out ? F.width : F.local_width) % 4 == 0;
+        const bool rgb8Direct = zerocopy8 && ((!F.layout && (F.global_out ? F.width : F.local_width) % 4 == 0) ||
+                                              (groupStoreEnabled() && F.layout == RTB_LAYOUT_REFERENCE && F.world == 1 && F.width % RTB_TILE_W == 0 && F.height % (4 * RTB_TILE_H) == 0)); // 8x16 blocks
         float *alias = ((zerocopy || F.global_out) && !F.cost_map && (!F.rgb8 || rgb8Direct || F.global_out)) ? hostAlias(rgb_out) : nullptr;
         if (alias)
         {

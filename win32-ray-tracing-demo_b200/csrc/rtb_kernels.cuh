@@ -30,9 +30,11 @@ struct FrameParams
     int sample_first, sample_end; // Monte Carlo: this launch renders samples [sample_first, sample_end) of `samples`
     int wide_store; // row-major output, 16-byte aligned rows: full tiles leave through storeTile()
     int group4;     // frames stored straight into page-locked HOST memory: the tile order is an order of GROUPS of four
-                    // horizontally adjacent tiles (order[4p + k] = 4g + k), so a CTA of the throughput kernels holds one
-                    // 32x4-pixel block and stores it as four 384-byte row segments (storeGroup); tier boundaries are
-                    // multiples of four
+                    // adjacent tiles, so a CTA of the throughput kernels holds one block of pixels and stores it in long
+                    // segments (storeGroup); tier boundaries are multiples of four.
+                    // 1: row-major frames, four horizontally adjacent tiles (order[4p + k] = 4g + k): a 32x4 block, four
+                    //    384-byte row segments;  2: the reference's column-major frames (index = x * height + y), four
+                    //    vertically adjacent tiles: an 8x16 block, eight 192-byte column segments
     int tiles_x, n_tiles;
     const unsigned int *order; // [n_tiles] tile ids, heaviest first; nullptr = raster order
     unsigned int *cost;        // [n_tiles] cycles >> 6 the throughput kernel last spent on each tile; may be nullptr
@@ -196,46 +198,67 @@ __device__ __forceinline__ bool storeTile(const FrameParams &F, float *out, unsi
 // such groups), pass the 32x4 pixels through the CTA's staging memory and 96 threads store them as four 384-byte row
 // segments of 128-bit stores (8-bit frames: four 96-byte segments of 32-bit stores).  4K SAH frame into host memory:
 // 5.11 -> 4.85 ms (into HBM: 4.70), profiles/r02_group_store.log.
+// The reference's own framebuffer order, colors[x * height + y] (MainWindow.cpp:276: what CudaRenderer::Render, the RenderProc
+// drop-in, asks for), is column-major: a tile is eight 48-byte column pieces there, and written pixel by pixel into host memory
+// the 4K SAH kernel took 9.9 ms.  For that layout a group is four VERTICALLY adjacent tiles, an 8x16-pixel block that leaves as
+// eight 192-byte column segments.
 // All threads of the CTA must call it.  false: group mode is off, a tile is ragged, or the CTA's tiles are not one group
 // (an order inherited from a tile-granular frame) -- nothing was stored, the caller stores per tile.
 __device__ __forceinline__ bool storeGroup(const FrameParams &F, float *out, unsigned int tile, bool active, V3 c,
                                            uint32_t (*stage)[RTB_TILE_STAGE_WORDS])
 {
-    if (!F.group4 || !F.wide_store) return false; // uniform over the launch
+    if (!F.group4) return false; // uniform over the launch
     __shared__ unsigned int groupTile[RTB_CTA_THREADS / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool vertical = F.group4 == 2;
     if (lane == 0) groupTile[warp] = tile;
     if (!__syncthreads_and(active && tile != 0xffffffffu)) return false;
-    const unsigned int t0 = groupTile[0];
-    if ((t0 & 3u) != 0u || groupTile[1] != t0 + 1u || groupTile[2] != t0 + 2u || groupTile[3] != t0 + 3u) return false; // uniform
+    const unsigned int t0 = groupTile[0], step = vertical ? (unsigned int)F.tiles_x : 1u;
+    const int ty = t0 / F.tiles_x, tx = t0 - ty * F.tiles_x;
+    if (((vertical ? (unsigned int)ty : t0) & 3u) != 0u || groupTile[1] != t0 + step || groupTile[2] != t0 + 2u * step || groupTile[3] != t0 + 3u * step)
+        return false; // uniform
+    // the block's pixels in the order they leave: row-major blocks [4 rows][32 px][3], column-major blocks [8 columns][16 px][3]
+    const int col = lane & 7, row = lane >> 3;
+    const int at = vertical ? (col * 16 + warp * 4 + row) * 3 : 0; // (horizontal: per-tile staging, gathered by the storing threads)
     if (F.rgb8)
     {
-        unsigned char *sb = reinterpret_cast<unsigned char *>(stage[warp]);
+        unsigned char *sb = vertical ? reinterpret_cast<unsigned char *>(stage[0]) + at : reinterpret_cast<unsigned char *>(stage[warp]) + 3 * lane;
         const float r = (c.x > 1.0f) ? 1.0f : c.x, g = (c.y > 1.0f) ? 1.0f : c.y, b = (c.z > 1.0f) ? 1.0f : c.z;
-        sb[3 * lane + 0] = (unsigned char)f2i(r * 255); sb[3 * lane + 1] = (unsigned char)f2i(g * 255); sb[3 * lane + 2] = (unsigned char)f2i(b * 255);
+        sb[0] = (unsigned char)f2i(r * 255); sb[1] = (unsigned char)f2i(g * 255); sb[2] = (unsigned char)f2i(b * 255);
     }
     else
     {
-        float *sf = reinterpret_cast<float *>(stage[warp]);
-        sf[3 * lane + 0] = c.x; sf[3 * lane + 1] = c.y; sf[3 * lane + 2] = c.z;
+        float *sf = vertical ? reinterpret_cast<float *>(stage[0]) + at : reinterpret_cast<float *>(stage[warp]) + 3 * lane;
+        sf[0] = c.x; sf[1] = c.y; sf[2] = c.z;
     }
     __syncthreads();
     if (threadIdx.x < 96)
     {
-        const int row = threadIdx.x / 24, seg = threadIdx.x - row * 24; // 16-byte (4-byte) chunk `seg` of the group's row segment
-        const int k = seg / 6, j = seg - k * 6;                         // tile k of the group, chunk j of that tile's row
-        const int ty = t0 / F.tiles_x, tx = t0 - ty * F.tiles_x;
-        size_t rowSlot = (size_t)(ty * RTB_TILE_H + row) * F.local_width + (size_t)tx * RTB_TILE_W;
-        if (F.global_out)
-        { // a group is 32 consecutive pixels of the whole frame too (column blocks are multiples of 32 in group mode)
-            int xg, yg;
-            localToGlobal(F, tx * RTB_TILE_W, ty * RTB_TILE_H + row, xg, yg);
-            rowSlot = (size_t)yg * F.width + xg;
+        if (vertical)
+        { // column k of the block, 16-byte (4-byte) chunk `seg` of its 192-byte (48-byte) segment
+            const int k = threadIdx.x / 12, seg = threadIdx.x - k * 12;
+            const size_t slot = (size_t)(tx * RTB_TILE_W + k) * F.height + (size_t)ty * RTB_TILE_H; // world == 1: local rows are frame rows
+            if (F.rgb8)
+                *reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(out) + 3 * slot + 4 * seg) = stage[0][k * 12 + seg];
+            else
+                *reinterpret_cast<float4 *>(out + 3 * slot + 4 * seg) = reinterpret_cast<const float4 *>(stage[0])[k * 12 + seg];
         }
-        if (F.rgb8)
-            *reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(out) + 3 * rowSlot + 4 * seg) = stage[k][row * 6 + j];
         else
-            *reinterpret_cast<float4 *>(out + 3 * rowSlot + 4 * seg) = reinterpret_cast<const float4 *>(stage[k])[row * 6 + j];
+        {
+            const int r = threadIdx.x / 24, seg = threadIdx.x - r * 24; // 16-byte (4-byte) chunk `seg` of the group's row segment
+            const int k = seg / 6, j = seg - k * 6;                     // tile k of the group, chunk j of that tile's row
+            size_t rowSlot = (size_t)(ty * RTB_TILE_H + r) * F.local_width + (size_t)tx * RTB_TILE_W;
+            if (F.global_out)
+            { // a group is 32 consecutive pixels of the whole frame too (column blocks are multiples of 32 in group mode)
+                int xg, yg;
+                localToGlobal(F, tx * RTB_TILE_W, ty * RTB_TILE_H + r, xg, yg);
+                rowSlot = (size_t)yg * F.width + xg;
+            }
+            if (F.rgb8)
+                *reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(out) + 3 * rowSlot + 4 * seg) = stage[k][r * 6 + j];
+            else
+                *reinterpret_cast<float4 *>(out + 3 * rowSlot + 4 * seg) = reinterpret_cast<const float4 *>(stage[k])[r * 6 + j];
+        }
     }
     return true;
 }

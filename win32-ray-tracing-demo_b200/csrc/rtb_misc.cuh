@@ -14,22 +14,33 @@ __device__ __forceinline__ int costBucket(unsigned int c)
     return e * 4 + (int)((c >> (e - 2)) & 3u) - 4;
 }
 
-// Sorting unit i: tile i, or -- group mode (FrameParams::group4) -- the four horizontally adjacent tiles 4i .. 4i + 3, which
-// one CTA renders together: it is busy for as long as its slowest tile, so that is the group's cost.  Groups count as four
-// tiles in the histogram and take four consecutive entries of the order; all offsets stay in tiles.
-__device__ __forceinline__ unsigned int unitCost(const unsigned int *__restrict__ cost, int i, int group)
+// Sorting unit u: tile u, or -- group mode (FrameParams::group4) -- four adjacent tiles which one CTA renders together: it is
+// busy for as long as its slowest tile, so that is the group's cost.  Groups count as four tiles in the histogram and take four
+// consecutive entries of the order; all offsets stay in tiles.  group 1: tiles 4u .. 4u + 3 of a tile row; group 2: tiles
+// (4 gy + k) * tiles_x + tx, k = 0 .. 3, of a tile column (u = gy * tiles_x + tx).
+__device__ __forceinline__ uint4 unitTiles(int u, int group, int tiles_x)
 {
-    if (!group) return cost[i];
-    const uint4 c = reinterpret_cast<const uint4 *>(cost)[i];
-    return max(max(c.x, c.y), max(c.z, c.w));
+    if (group == 2)
+    {
+        const int gy = u / tiles_x, tx = u - gy * tiles_x;
+        const unsigned int t = (unsigned int)(4 * gy * tiles_x + tx), sx = (unsigned int)tiles_x;
+        return make_uint4(t, t + sx, t + 2u * sx, t + 3u * sx);
+    }
+    return make_uint4(4u * u, 4u * u + 1u, 4u * u + 2u, 4u * u + 3u);
+}
+__device__ __forceinline__ unsigned int unitCost(const unsigned int *__restrict__ cost, int u, int group, int tiles_x)
+{
+    if (!group) return cost[u];
+    const uint4 t = unitTiles(u, group, tiles_x);
+    return max(max(cost[t.x], cost[t.y]), max(cost[t.z], cost[t.w]));
 }
 
-__global__ void k_cost_histogram(const unsigned int *__restrict__ cost, int n, unsigned int *__restrict__ hist, int group)
+__global__ void k_cost_histogram(const unsigned int *__restrict__ cost, int n, unsigned int *__restrict__ hist, int group, int tiles_x)
 {
     __shared__ unsigned int h[RTB_COST_BUCKETS];
     for (int i = threadIdx.x; i < RTB_COST_BUCKETS; i += blockDim.x) h[i] = 0;
     __syncthreads();
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) atomicAdd(&h[costBucket(unitCost(cost, i, group))], group ? 4u : 1u);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) atomicAdd(&h[costBucket(unitCost(cost, i, group, tiles_x))], group ? 4u : 1u);
     __syncthreads();
     for (int i = threadIdx.x; i < RTB_COST_BUCKETS; i += blockDim.x)
         if (h[i]) atomicAdd(&hist[i], h[i]);
@@ -117,7 +128,7 @@ __global__ void k_cost_offsets(unsigned int *__restrict__ hist, unsigned int *__
 // range of every bucket with ONE global atomic per bucket, then place the tiles with shared-memory
 // atomics (the naive per-tile global atomic took 146 us on the 345,600 tiles of a 4K frame).
 __global__ void k_cost_scatter(const unsigned int *__restrict__ cost, int n, unsigned int *__restrict__ cursor,
-                               unsigned int *__restrict__ order, const unsigned int *__restrict__ n_heavy, int group)
+                               unsigned int *__restrict__ order, const unsigned int *__restrict__ n_heavy, int group, int tiles_x)
 {
     const unsigned int span = group ? 4u : 1u;
     const int floor_bucket = (int)n_heavy[1]; // written by k_cost_offsets just before this launch
@@ -126,7 +137,7 @@ __global__ void k_cost_scatter(const unsigned int *__restrict__ cost, int n, uns
     const int begin = blockIdx.x * per, end = min(begin + per, n);
     for (int i = threadIdx.x; i < RTB_COST_BUCKETS; i += blockDim.x) cnt[i] = 0;
     __syncthreads();
-    for (int i = begin + threadIdx.x; i < end; i += blockDim.x) atomicAdd(&cnt[max(costBucket(unitCost(cost, i, group)), floor_bucket)], span);
+    for (int i = begin + threadIdx.x; i < end; i += blockDim.x) atomicAdd(&cnt[max(costBucket(unitCost(cost, i, group, tiles_x)), floor_bucket)], span);
     __syncthreads();
     for (int i = threadIdx.x; i < RTB_COST_BUCKETS; i += blockDim.x)
     {
@@ -136,9 +147,9 @@ __global__ void k_cost_scatter(const unsigned int *__restrict__ cost, int n, uns
     __syncthreads();
     for (int i = begin + threadIdx.x; i < end; i += blockDim.x)
     {
-        const int b = max(costBucket(unitCost(cost, i, group)), floor_bucket);
+        const int b = max(costBucket(unitCost(cost, i, group, tiles_x)), floor_bucket);
         const unsigned int at = base[b] + atomicAdd(&cnt[b], span);
-        if (group) reinterpret_cast<uint4 *>(order)[at >> 2] = make_uint4(4u * i, 4u * i + 1u, 4u * i + 2u, 4u * i + 3u); // `at` is a multiple of 4
+        if (group) reinterpret_cast<uint4 *>(order)[at >> 2] = unitTiles(i, group, tiles_x); // `at` is a multiple of 4
         else order[at] = (unsigned int)i;
     }
 }
