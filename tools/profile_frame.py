@@ -23,6 +23,7 @@ ap.add_argument("--frames", type=int, default=5)
 ap.add_argument("--rank", type=int, default=0)
 ap.add_argument("--world", type=int, default=1)
 ap.add_argument("--col-block", type=int, default=0)
+ap.add_argument("--host-frame", action="store_true", help="rtb_render into a page-locked host frame (the kernels store over PCIe, in blocks)")
 args = ap.parse_args()
 wl = WORKLOADS[args.workload]
 ctx = rtb200.Context(0)
@@ -33,7 +34,12 @@ st = torch.cuda.Stream()
 torch.cuda.set_stream(st)
 fr = rtb200.make_frame(wl["width"], wl["height"], samples=wl["samples"], rank=args.rank, world=args.world, col_block=args.col_block)
 buf = torch.empty((rtb200.shard_rows(fr), rtb200.shard_width(fr), 3), dtype=torch.float32, device="cuda:0")
+pinned = rtb200.PinnedArray((wl["height"], wl["width"], 3)) if args.host_frame else None
 for i in range(args.frames):
+    if args.host_frame:
+        _, r = d.render(s.camera, setting, fr, out=pinned.array)
+        print(f"frame {i}: kernel_ms {r['kernel_ms']:.3f} launches {r['n_launches']} rays {r['n_rays']} (host frame)", flush=True)
+        continue
     r = d.render_device(s.camera, setting, fr, buf.data_ptr(), st.cuda_stream, want_stats=True)
     print(f"frame {i}: kernel_ms {r['kernel_ms']:.3f} launches {r['n_launches']} rays {r['n_rays']}", flush=True)
 d.close(); s.close(); ctx.close()
