@@ -467,8 +467,6 @@ static int stageReserve(rtb_ctx *ctx, size_t bytes, char **out)
     return RTB_OK;
 }
 
-// `bytes` of staged data: written by fill(char *staging) into this context's ring -- or, for a replica of an
-// rtb_multi_scene_upload, the bytes the producer has staged for the same stream (StageShare)
 // is `p` page-locked host memory (cudaHostAlloc / cudaHostRegister)?
 static bool pageLocked(const void *p)
 {
@@ -478,6 +476,8 @@ static bool pageLocked(const void *p)
     return false;
 }
 
+// `bytes` of staged data: written by fill(char *staging) into this context's ring -- or, for a replica of an
+// rtb_multi_scene_upload, the bytes the producer has staged for the same stream (StageShare).
 // `src` != nullptr: the staged bytes are a verbatim copy of that caller array -- if the flat scene declares its arrays
 // page-locked and stable (rtb_flat_scene.arrays_page_locked) and this one is, the copy reads the array itself (*direct)
 template <class Fill>
@@ -2001,7 +2001,7 @@ extern "C" int rtb_multi_scene_upload(rtb_multi *m, const rtb_flat_scene *flat, 
     // (whole-stream index / structure checks on worker threads of its own) and stages every stream ONCE in its page-locked
     // ring; the other devices' uploads run on the pool's threads a step behind it: they take the staged bytes (StageShare)
     // for their own H2D copies and packing kernels, and wait for the verdict of the checks before anything indexes with the
-    // checked streams.  8 devices: 1.6 ms (first device, then the replicas with a staging copy each) -> see DESIGN.md section 6.
+    // checked streams.  8 B200: 1.63 ms (first device, then the replicas side by side with a staging pass each) -> 0.42-0.66 ms.
     StageShare share;
     if (n > 1)
     {
