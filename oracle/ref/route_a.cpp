@@ -31,7 +31,23 @@ static int width = 400, height = 300, samples = 1;
 static rtb_ctx *g_ctx = nullptr;
 static rtb_multi *g_multi = nullptr;
 static int g_devices = 1;
-static std::vector<float> g_colors; // Color colors[width * height], index = x * height + y (MainWindow.cpp:257, 276)
+// Color colors[width * height], index = x * height + y (MainWindow.cpp:257, 276) -- in page-locked memory (rtb_host_alloc), so that
+// the kernels store the frame straight into it while they render (no device frame, no copy behind the last kernel)
+static float *g_colors = nullptr;
+static size_t g_colors_floats = 0;
+static bool colorsReserve(size_t floats)
+{
+    if (floats > g_colors_floats)
+    {
+        if (g_colors) rtb_host_free(g_colors);
+        g_colors = nullptr; g_colors_floats = 0;
+        void *p = nullptr;
+        if (rtb_host_alloc(floats * sizeof(float), &p) != RTB_OK) return false;
+        g_colors = (float *)p; g_colors_floats = floats;
+    }
+    memset(g_colors, 0, floats * sizeof(float));
+    return true;
+}
 static rtb_stats g_stats;
 static std::string g_log;
 static int g_progress_calls = 0, g_progress_last = 0;
@@ -260,7 +276,7 @@ int CudaRender(GeometrySet &scene, PerspectiveCamera &camera, RenderSetting &set
     memset(&fr, 0, sizeof(fr));
     fr.width = width; fr.height = height; fr.samples = samples;
     fr.world = 1; fr.row_block = 8; fr.layout = RTB_LAYOUT_REFERENCE; // Color colors[x * height + y]
-    g_colors.assign((size_t)width * height * 3, 0.0f);
+    if (!colorsReserve((size_t)width * height * 3)) { AddLog("CudaRender: rtb_host_alloc failed\r\n"); return -1; }
     g_progress = progress;
     int rc;
     int t1 = Utils::GetTickCount();
@@ -269,7 +285,7 @@ int CudaRender(GeometrySet &scene, PerspectiveCamera &camera, RenderSetting &set
         rtb_multi_scene *dev = nullptr;
         if (rtb_multi_scene_upload(g_multi, flat.view(), &dev) != RTB_OK) { AddLog(rtb_multi_last_error(g_multi)); AddLog("\r\n"); return -1; }
         rtb_multi_set_progress(g_multi, progress ? progressTrampoline : nullptr, nullptr);
-        rc = rtb_multi_render(g_multi, dev, &cam, &rs, &fr, g_colors.data(), &g_stats);
+        rc = rtb_multi_render(g_multi, dev, &cam, &rs, &fr, g_colors, &g_stats);
         rtb_multi_scene_free(g_multi, dev);
         if (rc != RTB_OK) { AddLog(rtb_multi_last_error(g_multi)); AddLog("\r\n"); return -1; }
     }
@@ -278,7 +294,7 @@ int CudaRender(GeometrySet &scene, PerspectiveCamera &camera, RenderSetting &set
         rtb_scene *dev = nullptr;
         if (rtb_scene_upload(g_ctx, flat.view(), &dev) != RTB_OK) { AddLog(rtb_last_error(g_ctx)); AddLog("\r\n"); return -1; }
         rtb_set_progress(g_ctx, progress ? progressTrampoline : nullptr, nullptr);
-        rc = rtb_render(g_ctx, dev, &cam, &rs, &fr, g_colors.data(), &g_stats);
+        rc = rtb_render(g_ctx, dev, &cam, &rs, &fr, g_colors, &g_stats);
         rtb_scene_free(g_ctx, dev);
         if (rc != RTB_OK) { AddLog(rtb_last_error(g_ctx)); AddLog("\r\n"); return -1; }
     }
@@ -320,7 +336,7 @@ int route_a_run(int preset, int algorithm, int segments, int w, int h, int spp, 
     if (progress) { progress[0] = g_progress_calls; progress[1] = g_progress_last; }
     if (exec < 0) return exec;
     if (counts) { counts[0] = g_stats.n_rays; counts[1] = g_stats.n_tri_tests; counts[2] = g_stats.n_steps; }
-    if (rgb_out) memcpy(rgb_out, g_colors.data(), g_colors.size() * sizeof(float));
+    if (rgb_out && g_colors) memcpy(rgb_out, g_colors, (size_t)w * h * 3 * sizeof(float));
     return 0;
 }
 
