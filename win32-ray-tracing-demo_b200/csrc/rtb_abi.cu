@@ -259,6 +259,8 @@ struct rtb_scene
     bool direct_sources = false;    // some copies read the caller's page-locked arrays: rtb_scene_free waits for `ready`
     int64_t grid_cells_used = 0, grid_refs = 0, grid_words = 0;
     int64_t kd_nodes = 0, kd_refs = 0; // k-d tree resident on the device (uploaded or built there)
+    const uint2 *kd_nodes_plain = nullptr;  // ... in the caller's / the builder's layout (rtb_scene_kd_download); DScene::kd_nodes /
+    const uint32_t *kd_tris_plain = nullptr; //     kd_tris are the copy with every leaf list on an even position (padKdLists)
     int kd_levels = 0;
     bool long_lists = false; // regular grid with >= 16 triangle references per occupied cell (tier policy, wideCount)
     unsigned long long signature = 0; // sampled content hash, identifies "the same scene again" for the tile-order cache
@@ -625,6 +627,62 @@ static int packPairs(rtb_ctx *ctx, rtb_scene *s, const uint32_t *refs, size_t n_
     return RTB_OK;
 }
 
+template <class T> static int deviceArray(rtb_ctx *ctx, rtb_scene *s, size_t n, T **dev, bool keep)
+{
+    void *p = nullptr;
+    CUDA_TRY(ctx, cudaMallocAsync(&p, (n ? n : 1) * sizeof(T), ctx->stream));
+    if (keep) { s->allocs.push_back(p); s->bytes += (int64_t)(n * sizeof(T)); }
+    *dev = (T *)p;
+    return RTB_OK;
+}
+
+// The k-d arrays the kernels walk: every leaf list on an even position of the reference array (k_kd_pad_sizes / k_kd_relayout,
+// rtb_misc.cuh), then the pair stream over that array.  `padded_refs` = sum of the leaves' padded list lengths (exact, or an
+// upper bound).  RTB_KD_PAD=0: the arrays as they came.
+static int padKdLists(rtb_ctx *ctx, rtb_scene *s, long long padded_refs)
+{
+    DScene &d = s->d;
+    s->kd_nodes_plain = d.kd_nodes; s->kd_tris_plain = d.kd_tris;
+    static const bool on = !(getenv("RTB_KD_PAD") && atoi(getenv("RTB_KD_PAD")) == 0);
+    const long long n = s->kd_nodes;
+    // (leaves that share or overlap lists could blow the copy up: such a tree keeps its layout)
+    if (!on || n <= 0 || padded_refs <= 0 || padded_refs > 2 * (s->kd_refs + n) + 64 || padded_refs > 0x7fffffffLL)
+        return packPairs(ctx, s, d.kd_tris, (size_t)s->kd_refs);
+    cudaStream_t st = ctx->stream;
+    unsigned int *d_size = nullptr, *d_first = nullptr;
+    void *d_tmp = nullptr;
+    uint2 *nodes_out = nullptr;
+    uint32_t *refs_out = nullptr;
+    auto cleanup = [&]() { if (d_size) cudaFreeAsync(d_size, st); if (d_first) cudaFreeAsync(d_first, st); if (d_tmp) cudaFreeAsync(d_tmp, st); };
+#define PAD_TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return fail(ctx, RTB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
+    PAD_TRY(cudaMallocAsync((void **)&d_size, (size_t)(n + 1) * sizeof(unsigned int), st));
+    PAD_TRY(cudaMallocAsync((void **)&d_first, (size_t)(n + 1) * sizeof(unsigned int), st));
+    k_kd_pad_sizes<<<(unsigned int)((n + 1 + 255) / 256), 256, 0, st>>>(d.kd_nodes, (int)n, d_size);
+    size_t need = 0;
+    PAD_TRY(cub::DeviceScan::ExclusiveSum(nullptr, need, d_size, d_first, (int)n + 1, st));
+    PAD_TRY(cudaMallocAsync(&d_tmp, need ? need : 1, st));
+    PAD_TRY(cub::DeviceScan::ExclusiveSum(d_tmp, need, d_size, d_first, (int)n + 1, st));
+    int rc;
+    if ((rc = deviceArray(ctx, s, (size_t)n, &nodes_out, true)) != RTB_OK || (rc = deviceArray(ctx, s, (size_t)padded_refs, &refs_out, true)) != RTB_OK) { cleanup(); return rc; }
+    PAD_TRY(cudaMemsetAsync(refs_out, 0, (size_t)padded_refs * sizeof(uint32_t), st));
+    k_kd_relayout<<<(unsigned int)((n + 255) / 256), 256, 0, st>>>(d.kd_nodes, (int)n, d_first, d.kd_tris, nodes_out, refs_out, (unsigned int)padded_refs);
+    PAD_TRY(cudaGetLastError());
+#undef PAD_TRY
+    cleanup();
+    d.kd_nodes = nodes_out; d.kd_tris = refs_out;
+    return packPairs(ctx, s, refs_out, (size_t)padded_refs);
+}
+
+// sum of the leaves' padded list lengths of a caller's tree (the validation tasks of rtb_scene_upload compute it on the side;
+// uploads that skip them -- the replicas of an rtb_multi_scene_upload -- take this pass)
+static long long paddedKdRefs(const rtb_flat_scene *f)
+{
+    long long total = 0;
+    for (int i = 0; i < f->n_kd_nodes; i++)
+        total += ((f->kd_nodes[i].b & 3u) == 3u) ? (long long)(((f->kd_nodes[i].b >> 2) + 1u) & ~1u) : 0;
+    return total;
+}
+
 // pre-order k-d array -> 0 when it is a well-formed tree (every inner node's right child lies behind its left
 // subtree, every node reached exactly once), maxDepth = deepest node.  One linear pass with an explicit stack of
 // pending right children: the recursive walk took 0.2 ms of every upload.
@@ -706,15 +764,6 @@ extern "C" int rtb_kd_validate(const rtb_kdnode *nodes, int32_t n, int32_t *max_
 
 
 // ---- grid built on the device (rtb_build_grid.cuh) ------------------------------------------------------------
-template <class T> static int deviceArray(rtb_ctx *ctx, rtb_scene *s, size_t n, T **dev, bool keep)
-{
-    void *p = nullptr;
-    CUDA_TRY(ctx, cudaMallocAsync(&p, (n ? n : 1) * sizeof(T), ctx->stream));
-    if (keep) { s->allocs.push_back(p); s->bytes += (int64_t)(n * sizeof(T)); }
-    *dev = (T *)p;
-    return RTB_OK;
-}
-
 static int buildGridOnDevice(rtb_ctx *ctx, rtb_scene *s, const rtb_flat_scene *f, float *d_raw)
 {
     DScene &d = s->d;
@@ -924,7 +973,7 @@ static int buildKdOnDevice(rtb_ctx *ctx, rtb_scene *s, const rtb_flat_scene *f, 
     d.kd_size = {b[3] - b[0], b[4] - b[1], b[5] - b[2]}; // Grid(near, far): size = far - near (Grid.cpp:13-17)
     d.kd_nodes = d_out; d.kd_tris = d_leaf;
     s->kd_nodes = totalNodes; s->kd_refs = root.subRefs; s->kd_levels = levels;
-    return packPairs(ctx, s, d_leaf, (size_t)root.subRefs);
+    return padKdLists(ctx, s, (long long)root.subRefs + ((long long)totalNodes + 1) / 2); // disjoint lists, at most one padding slot per leaf
 }
 
 // Index / structure checks of rtb_scene_upload that scan whole streams (k-d nodes, leaf and cell references: 0.6 ms
@@ -941,6 +990,7 @@ struct BackgroundChecks
     std::string msg;
     bool enabled = true; // false: the caller has validated this very flat scene already (rtb_multi_scene_upload: replicas)
     bool started = false;
+    std::atomic<long long> kd_padded{0}; // by-product of the k-d leaf checks: sum of the padded list lengths (padKdLists)
     void keep(const std::pair<int, const char *> &r)
     {
         if (r.first == RTB_OK) return;
@@ -1037,13 +1087,18 @@ static void queueSceneChecks(const rtb_flat_scene *f, BackgroundChecks &checks)
                     return R((int)RTB_ERR_UNSUPPORTED, "rtb_scene_upload: k-d tree deeper than the 50-entry traversal stack allows");
                 return R((int)RTB_OK, "");
             });
-        slices(f->n_kd_nodes, [f](int64_t lo, int64_t hi) { // branch-free maxima (the compiler vectorises them)
+        std::atomic<long long> *padded = &checks.kd_padded;
+        slices(f->n_kd_nodes, [f, padded](int64_t lo, int64_t hi) { // branch-free maxima (the compiler vectorises them)
             int64_t leafEnd = 0;
+            long long pad = 0;
             for (int64_t i = lo; i < hi; i++)
             {
-                const int64_t e = ((f->kd_nodes[i].b & 3u) == 3u) ? (int64_t)f->kd_nodes[i].a + (f->kd_nodes[i].b >> 2) : 0;
+                const bool leaf = (f->kd_nodes[i].b & 3u) == 3u;
+                const int64_t e = leaf ? (int64_t)f->kd_nodes[i].a + (f->kd_nodes[i].b >> 2) : 0;
                 leafEnd = e > leafEnd ? e : leafEnd;
+                pad += leaf ? (long long)(((f->kd_nodes[i].b >> 2) + 1u) & ~1u) : 0;
             }
+            padded->fetch_add(pad, std::memory_order_relaxed);
             return R(leafEnd > f->n_kd_refs ? (int)RTB_ERR_INVALID : (int)RTB_OK, "rtb_scene_upload: k-d leaf range out of bounds");
         });
         slices(f->n_kd_refs, [f, nTris](int64_t lo, int64_t hi) {
@@ -1240,8 +1295,8 @@ static int sceneUpload(rtb_ctx *ctx, const rtb_flat_scene *f, rtb_scene **out, b
             laps.lap("k-d arrays queued");
             if ((rc = collectVerdict(ctx, checks)) != RTB_OK) return bail(rc);
             laps.lap("verdict");
-            if ((rc = packPairs(ctx, s, d.kd_tris, (size_t)f->n_kd_refs)) != RTB_OK) return bail(rc);
             s->kd_nodes = f->n_kd_nodes; s->kd_refs = f->n_kd_refs;
+            if ((rc = padKdLists(ctx, s, validate ? checks.kd_padded.load() : paddedKdRefs(f))) != RTB_OK) return bail(rc);
         }
         else if (f->accel == RTB_ACCEL_CONVEX || f->accel == RTB_ACCEL_CONVEX_SIMPLE)
         {
@@ -1368,12 +1423,12 @@ extern "C" int rtb_scene_kd_download(rtb_ctx *ctx, const rtb_scene *s, rtb_kdnod
     if (nodes)
     {
         if (node_cap < s->kd_nodes) return fail(ctx, RTB_ERR_INVALID, "rtb_scene_kd_download: node buffer too small");
-        CUDA_TRY(ctx, cudaMemcpyAsync(nodes, d.kd_nodes, (size_t)s->kd_nodes * sizeof(rtb_kdnode), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(nodes, s->kd_nodes_plain ? s->kd_nodes_plain : d.kd_nodes, (size_t)s->kd_nodes * sizeof(rtb_kdnode), cudaMemcpyDeviceToHost, ctx->stream));
     }
     if (leaf_tris)
     {
         if (ref_cap < s->kd_refs) return fail(ctx, RTB_ERR_INVALID, "rtb_scene_kd_download: reference buffer too small");
-        CUDA_TRY(ctx, cudaMemcpyAsync(leaf_tris, d.kd_tris, (size_t)s->kd_refs * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(leaf_tris, s->kd_tris_plain ? s->kd_tris_plain : d.kd_tris, (size_t)s->kd_refs * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     }
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return RTB_OK;

@@ -154,6 +154,45 @@ __global__ void k_cost_scatter(const unsigned int *__restrict__ cost, int n, uns
     }
 }
 
+// ---- k-d leaf lists on even positions of the reference array (upload time) --------------------------------------------------
+// The list scans test two list positions per iteration out of the pair stream (pre2[p] = positions 2p, 2p + 1); a list that
+// starts on an odd position costs half an iteration more on average -- one of the ~17 pair iterations per ray on the SAH tree.
+// A leaf carries its own count, so the array can simply be re-laid out with every list on an even position: the slot behind an
+// odd-length list is padding that lies outside every [first, first + count) and is never tested.  size[i] = padded length of
+// leaf i (inner nodes 0); first = exclusive scan; the caller's layout is kept for rtb_scene_kd_download.
+__global__ void k_kd_pad_sizes(const uint2 *__restrict__ nodes, int n, unsigned int *__restrict__ size)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    unsigned int v = 0;
+    if (i < n)
+    {
+        const uint2 nd = nodes[i];
+        if ((nd.y & 3u) == 3u) v = ((nd.y >> 2) + 1u) & ~1u;
+    }
+    size[i] = v; // size[n] = 0: the total of the scan lands in first[n]
+}
+
+__global__ void k_kd_relayout(const uint2 *__restrict__ nodes, int n, const unsigned int *__restrict__ first, const uint32_t *__restrict__ refs,
+                              uint2 *__restrict__ nodes_out, uint32_t *__restrict__ refs_out, unsigned int cap)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint2 nd = nodes[i];
+    if ((nd.y & 3u) == 3u)
+    {
+        const unsigned int count = nd.y >> 2, from = nd.x, to = first[i];
+        if ((unsigned long long)to + ((count + 1u) & ~1u) <= cap) // (the capacity is the exact total: always true)
+        {
+            for (unsigned int j = 0; j < count; j++) refs_out[to + j] = refs[from + j];
+            if (count & 1u) refs_out[to + count] = refs[from + count - 1u]; // padding: any valid index
+            nd.x = to;
+        }
+        else nd.y = 3u; // never reached; an empty leaf rather than a list outside the array
+    }
+    nodes_out[i] = nd;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Parity hooks: primary rays with traversal recording, and arbitrary ray batches
 // ---------------------------------------------------------------------------------------------
